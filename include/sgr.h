@@ -1,0 +1,254 @@
+/*
+ * sgr.h — C ABI of the B200 batched event-replay engine ("surge gpu replay").
+ *
+ * This is the drop-in boundary for ONE path of UltimateSoftware/surge: rebuilding
+ * aggregate state by folding each aggregate's ordered event log through the model's
+ * event handler, and the AggregateStateStore recovery read that consumes the result.
+ * The reference has no FFI of its own (pure Scala/JVM); each entry point below names
+ * the JVM interface a JNI stub would bind it behind (paths relative to the reference
+ * checkout, see INTEGRATION.md for the stubs):
+ *
+ *   CORE  = modules/command-engine/core/src/main/scala/surge
+ *   SDSL  = modules/command-engine/scaladsl/src/main/scala/surge/scaladsl
+ *   COMMON= modules/common/src/main/scala/surge
+ *
+ * Conventions
+ *   - plain C, no C++/CUDA/torch types cross this boundary;
+ *   - every function returns an int32 status (SGR_OK == 0, negative == error class);
+ *     the message for the last error on an engine is sgr_last_error(engine);
+ *   - buffers are caller-allocated and caller-owned in both directions; the engine
+ *     never frees caller memory and only sgr_destroy frees engine memory;
+ *   - "_device" variants take CUDA device pointers on the engine's device and BORROW
+ *     them (no copy) — the caller keeps them alive until the next load or destroy;
+ *   - load/fold calls are serialised by the caller (the Kafka Streams stream thread in
+ *     the reference, COMMON/kafka/streams/KafkaStreamManagerActor.scala:106-133);
+ *     sgr_get / sgr_get_index may be called concurrently from many threads (the
+ *     reference reads the store from a 32-thread pool,
+ *     COMMON/kafka/streams/ThreadPools.scala:9-11).
+ *   - there is NO CPU fallback: without a usable CUDA device sgr_create fails.
+ */
+#ifndef SGR_H
+#define SGR_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SGR_ABI_VERSION 1
+
+/* ------------------------------------------------------------------ status codes */
+#define SGR_OK                 0
+#define SGR_ERR_INVALID       -1   /* bad argument / malformed buffer (IllegalArgumentException) */
+#define SGR_ERR_NO_DEVICE     -2   /* no CUDA device / extension unusable: fail loudly, never fall back */
+#define SGR_ERR_CUDA          -3   /* a CUDA call failed; message carries cudaGetErrorString */
+#define SGR_ERR_NO_PROGRAM    -4   /* fold requested before sgr_register_program */
+#define SGR_ERR_NOT_LOADED    -5   /* fold/get requested before any load */
+#define SGR_ERR_UNSUPPORTED   -6   /* model cannot be expressed as a fold program: decline the plugin */
+#define SGR_ERR_OOM           -7
+#define SGR_ERR_STATE         -8   /* store not readable now (maps to InvalidStateStoreException,
+                                      COMMON/kafka/streams/SurgeAggregateStore.scala:31-46) */
+#define SGR_ERR_DIST          -9   /* NCCL / peer-memory failure */
+#define SGR_ERR_CAPACITY     -10   /* caller buffer too small */
+
+/* ------------------------------------------------------------------ packed formats
+ *
+ * Fixed record (SGR_REC_FIXED64): 64 bytes, little-endian, 64-byte aligned in the log
+ *   +0  u32 type      event type = index into the program's rule table
+ *   +4  u32 seq       sequence number (Counter: sequenceNumber)
+ *   +8  u64 agg       dense aggregate index (or global index before routing)
+ *   +16 u8  payload[48]  program-defined view (Counter: i32 by @16;
+ *                        BankAccount: uuid @16, f64 balance @32, owner @40, code @56)
+ *
+ * Variable record (SGR_REC_VAR16): 16-byte header + payload padded to 16 bytes
+ *   +0  u32 type   +4 u32 seq   +8 u32 payload_len (unpadded)   +12 u32 agg
+ *   +16 payload, padded with zeros up to a multiple of 16
+ *
+ * CSR: u64 seg_offsets[n_agg+1], BYTE offsets into the event log; segment i is
+ *   [seg_offsets[i], seg_offsets[i+1]); every offset is a multiple of 16 so that
+ *   each segment is a legal source for a 1-D TMA bulk copy.
+ *
+ * State table: n_agg structs of state_bytes (multiple of 16, <= SGR_MAX_STATE_BYTES).
+ *   The program owns bytes [0, state_bytes-8); the engine owns the trailing 8:
+ *   +state_bytes-8  u32 flags   (SGR_ST_EXISTS | SGR_ST_CHANGED | SGR_ST_ERROR)
+ *   +state_bytes-4  u32 err_idx (index, within the aggregate's batch, of the event that
+ *                                threw; 0 when no error)
+ *   A state that does not exist (Scala None) has all program bytes zero.
+ */
+#define SGR_REC_FIXED64 0u
+#define SGR_REC_VAR16   1u
+
+#define SGR_ST_EXISTS   1u
+#define SGR_ST_CHANGED  2u   /* newState != oldState: the publish rule of
+                                CORE/internal/persistence/PersistentActor.scala:252-257 */
+#define SGR_ST_ERROR    4u   /* handler threw: state kept at its pre-batch value
+                                (PersistentActor.scala:260-263,303-309) */
+
+#define SGR_MAX_STATE_BYTES 128u
+#define SGR_MAX_TYPES        16u
+#define SGR_MAX_OPS           8u
+
+/* ------------------------------------------------------------------ fold program
+ *
+ * Declarative form of AggregateCommandModel.handleEvent(Option[Agg], Evt): Option[Agg]
+ * (SDSL/command/CommandModels.scala:14). A JVM closure cannot run on a GPU, so a model
+ * registers, next to its handler, one rule per event type:
+ *
+ *   exists_rule   what happens to Option-ness before the field ops run
+ *     SGR_IF_EXISTS    None stays None and the ops are skipped   (aggregate.map(_.copy(..)))
+ *     SGR_MATERIALISE  None becomes the all-zero default state    (agg.getOrElse(State(id,0,0)))
+ *     SGR_CREATE       state is reset to the default, then ops    (Some(Agg(evt fields)))
+ *     SGR_TOMBSTONE    state becomes None                          (handler returns None)
+ *     SGR_THROW        the handler throws                          (ExceptionThrowingEvent)
+ *   ops           word-granular field transfers record -> state, applied in order.
+ *                 All offsets/lengths are byte counts and multiples of 4.
+ *
+ * An event whose type is >= n_types is a scala.MatchError, i.e. SGR_THROW.
+ */
+#define SGR_IF_EXISTS    0u
+#define SGR_MATERIALISE  1u
+#define SGR_CREATE       2u
+#define SGR_TOMBSTONE    3u
+#define SGR_THROW        4u
+
+#define SGR_OP_SET      0u  /* state[dst .. dst+len) = record[src .. src+len)   (bit copy; f64, strings) */
+#define SGR_OP_ADD_I32  1u  /* state.i32[dst] += record.i32[src]   two's-complement wrap (JVM Int)  */
+#define SGR_OP_SUB_I32  2u  /* state.i32[dst] -= record.i32[src]                                     */
+#define SGR_OP_ADD_I64  3u  /* state.i64[dst] += record.i64[src]   wrap (JVM Long)                    */
+#define SGR_OP_SUB_I64  4u
+
+typedef struct sgr_op {
+  uint8_t  opcode;     /* SGR_OP_* */
+  uint8_t  reserved;
+  uint16_t dst_off;    /* byte offset into the state struct (program area) */
+  uint16_t src_off;    /* byte offset into the record, header included */
+  uint16_t len;        /* bytes; SET: any multiple of 4; I32 ops: 4; I64 ops: 8 */
+} sgr_op;
+
+typedef struct sgr_rule {
+  uint8_t exists_rule; /* SGR_IF_EXISTS .. SGR_THROW */
+  uint8_t n_ops;       /* <= SGR_MAX_OPS */
+  uint8_t reserved[6];
+  sgr_op  ops[SGR_MAX_OPS];
+} sgr_rule;
+
+typedef struct sgr_fold_program {
+  uint32_t state_bytes;   /* multiple of 16, 16..SGR_MAX_STATE_BYTES, includes the 8 engine bytes */
+  uint32_t record_kind;   /* SGR_REC_FIXED64 | SGR_REC_VAR16 */
+  uint32_t n_types;       /* <= SGR_MAX_TYPES */
+  uint32_t n_f64_fields;  /* <= 8: state fields that are JVM Doubles; they are bit-copied by SGR_OP_SET
+                             but compare with == for the publish rule (0.0 == -0.0, NaN != NaN), as
+                             Scala case-class equality does in PersistentActor.scala:257 */
+  uint16_t f64_field_off[8];
+  sgr_rule rules[SGR_MAX_TYPES];
+} sgr_fold_program;
+
+/* ------------------------------------------------------------------ engine */
+typedef struct sgr_engine sgr_engine;   /* opaque */
+
+typedef struct sgr_config {
+  int32_t  device;          /* CUDA device ordinal */
+  uint32_t flags;           /* reserved, 0 */
+  uint64_t reserved[6];
+} sgr_config;
+
+typedef struct sgr_stats {
+  uint64_t n_aggregates;    /* segments folded by the last fold */
+  uint64_t n_events;        /* events consumed by the last fold */
+  uint64_t event_bytes;     /* stored event-record bytes read by the last fold */
+  uint64_t algorithmic_bytes;/* event_bytes + 8*(n_agg+1) + state_bytes*n_agg (+ prior states read) */
+  uint64_t n_errors;        /* aggregates whose handler threw */
+  uint64_t n_long_segments; /* aggregates taken by the split (long-segment) path */
+  float    ms_h2d;          /* host->device copy of the last load (0 for _device loads) */
+  float    ms_group;        /* stable group-by of the last unsorted load */
+  float    ms_fold;         /* device time of the last fold (all its kernels) */
+  float    ms_d2h;          /* device->host copy of the last export */
+  uint32_t fold_launches;   /* kernels launched by the last fold */
+  uint32_t reserved[7];
+} sgr_stats;
+
+int32_t sgr_abi_version(void);
+
+/* Create an engine bound to one CUDA device. Replaces the construction of the state
+ * store inside the engine pipeline (CORE/internal/domain/SurgeMessagePipeline.scala:68-78). */
+int32_t sgr_create(const sgr_config* cfg, sgr_engine** out);
+int32_t sgr_destroy(sgr_engine* e);
+const char* sgr_last_error(const sgr_engine* e);   /* e may be NULL: last create error */
+
+/* Register the declarative form of the model's event handler
+ * (SDSL/command/CommandModels.scala:14; core entry
+ * CORE/internal/domain/AggregateProcessingModel.scala:21). */
+int32_t sgr_register_program(sgr_engine* e, const sgr_fold_program* prog);
+
+/* Load a CSR-ordered event log (host buffers; copied to HBM). The log is what
+ * AggregateRef.applyEvents would be handed per aggregate, for every aggregate at once
+ * (SDSL/common/AggregateRefBaseTrait.scala:23-28). */
+int32_t sgr_load_events(sgr_engine* e, const void* events, uint64_t nbytes,
+                        const uint64_t* seg_offsets, uint64_t n_agg);
+int32_t sgr_load_events_device(sgr_engine* e, const void* d_events, uint64_t nbytes,
+                               const uint64_t* d_seg_offsets, uint64_t n_agg);
+
+/* Load records in ARRIVAL order (a Kafka partition log interleaves aggregates) and group
+ * them, stably, by aggregate index into CSR form on the device. n_agg is the number of
+ * dense aggregate indices (records carry agg < n_agg). Fixed 64-byte records only. */
+int32_t sgr_load_unsorted(sgr_engine* e, const void* records, uint64_t n_records, uint64_t n_agg);
+int32_t sgr_load_unsorted_device(sgr_engine* e, const void* d_records, uint64_t n_records, uint64_t n_agg);
+
+/* Prior states for an incremental fold (None everywhere if never called):
+ * the actor's state before ApplyEvents, PersistentActor.scala:245-264. states may be NULL to reset. */
+int32_t sgr_set_initial_states(sgr_engine* e, const void* states, uint64_t n_agg);
+
+/* Fold every aggregate's segment left to right in event order:
+ * events.foldLeft(state)(handleEvent), SDSL/command/CommandModels.scala:25-28. */
+int32_t sgr_fold(sgr_engine* e);
+
+/* Append one micro-batch (arrival order, fixed records) to the live state table: group by
+ * aggregate, fold onto the current states, write back (PersistentActor.doApplyEvent on a
+ * live actor, PersistentActor.scala:245-264). Requires a prior fold or set_initial_states. */
+int32_t sgr_fold_incremental(sgr_engine* e, const void* records, uint64_t n_records);
+int32_t sgr_fold_incremental_device(sgr_engine* e, const void* d_records, uint64_t n_records);
+
+/* Key table: UTF-8 aggregate ids, key i = keys[key_offsets[i] .. key_offsets[i+1]).
+ * Not read by the fold; only by sgr_get. */
+int32_t sgr_load_keys(sgr_engine* e, const uint8_t* keys, const uint32_t* key_offsets, uint64_t n_agg);
+
+/* Point lookup of folded state bytes by aggregate id: the recovery read
+ * AggregateStateStoreKafkaStreams.getAggregateBytes(aggregateId): Future[Option[Array[Byte]]]
+ * (COMMON/kafka/streams/AggregateStateStoreKafkaStreams.scala:83-85). *exists == 0 is None.
+ * Thread-safe against a published snapshot. Copies the program bytes (state_bytes-8). */
+int32_t sgr_get(sgr_engine* e, const uint8_t* key, uint32_t klen,
+                void* out, uint32_t cap, uint32_t* outlen, int32_t* exists);
+int32_t sgr_get_index(sgr_engine* e, uint64_t agg, void* out, uint32_t cap,
+                      uint32_t* outlen, int32_t* exists, uint32_t* flags, uint32_t* err_idx);
+
+/* Export the whole state table (n_agg * state_bytes) and, optionally, bitmaps
+ * (bit i of byte i/8, LSB first). Any out pointer may be NULL. */
+int32_t sgr_export_states(sgr_engine* e, void* out, uint64_t cap,
+                          uint8_t* exists_bits, uint8_t* changed_bits, uint8_t* error_bits);
+/* Device pointer to the live state table (borrowed; valid until the next load/destroy). */
+int32_t sgr_states_device(sgr_engine* e, void** d_states, uint64_t* n_agg, uint32_t* state_bytes);
+/* Device pointers to the engine's CSR event log (after any load). */
+int32_t sgr_events_device(sgr_engine* e, void** d_events, uint64_t* nbytes, uint64_t** d_seg_offsets);
+
+int32_t sgr_get_stats(sgr_engine* e, sgr_stats* out);
+
+/* Tuning knob for measurements: which fold kernel variant to launch
+ * (0 = default; see DESIGN.md "kernel variants"). */
+int32_t sgr_set_option(sgr_engine* e, const char* name, int64_t value);
+
+/* The CUDA stream (cudaStream_t) the engine launches on, so callers can record events. */
+int32_t sgr_stream(sgr_engine* e, void** stream);
+
+/* ------------------------------------------------------------------ partitioner
+ * KafkaPartitionProvider.partitionForKey = abs(MurmurHash3.stringHash(s) % n)
+ * (COMMON/kafka/KafkaPartitioner.scala:7-9) over key.takeWhile(_ != ':')
+ * (PartitionStringUpToColon, :38-42). Host-side, UTF-16 code units. */
+int32_t sgr_string_hash_utf16(const uint16_t* units, uint32_t n);
+int32_t sgr_partition_for_key_utf8(const uint8_t* key, uint32_t klen, uint32_t num_partitions,
+                                   int32_t up_to_colon, int32_t* partition);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SGR_H */

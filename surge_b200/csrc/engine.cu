@@ -1,0 +1,531 @@
+// engine.cu — the C ABI of include/sgr.h over the CUDA kernels (host side of the boundary).
+//
+// No CPU fallback lives here: every compute entry point launches a kernel on the engine's
+// device or fails with a status code. Nothing in this file includes or links oracle/.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <atomic>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/sgr.h"
+#include "devbuf.h"
+#include "fold_kernels.cuh"
+#include "group_kernels.cuh"
+#include "keytable.h"
+
+using namespace sgr;
+
+namespace {
+thread_local std::string g_create_error;
+
+// host snapshot of the state table that sgr_get reads (published after a fold)
+struct Snapshot {
+  std::vector<uint8_t> states;
+  uint64_t n_agg = 0;
+  uint32_t state_bytes = 0;
+};
+}  // namespace
+
+struct sgr_engine {
+  int device = 0;
+  int num_sms = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+
+  bool has_program = false;
+  sgr_fold_program program{};
+  DevProgram dprog{};
+
+  // CSR event log: owned buffers or borrowed pointers
+  DevBuf own_events, own_offsets;
+  const uint8_t* d_events = nullptr;
+  const uint64_t* d_offsets = nullptr;
+  uint64_t event_bytes = 0;
+  uint64_t n_agg = 0;
+  bool loaded = false;
+  uint32_t max_record_bytes = 64;
+
+  DevBuf states;        // n_agg * state_bytes, live table
+  bool states_valid = false;  // holds prior states (set_initial_states or a previous fold)
+  uint64_t states_n = 0;
+  DevBuf counters;      // 8 x u64
+  GroupScratch group;   // K5 scratch
+  DevBuf inc_records, inc_offsets, inc_ids, inc_prev_ids;  // K6
+  uint64_t inc_prev_n = 0;
+
+  int64_t opt_variant = -1;
+  int64_t opt_long_threshold = 0;
+  int64_t opt_max_record_bytes = 528;
+
+  sgr_stats stats{};
+  std::string last_error;
+
+  KeyTable keys;
+  std::mutex snap_mu;
+  std::shared_ptr<Snapshot> snapshot;
+  std::atomic<bool> snapshot_dirty{true};
+};
+
+namespace {
+
+int32_t fail(sgr_engine* e, int32_t code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+  if (e) e->last_error = buf; else g_create_error = buf;
+  return code;
+}
+#define CUDA_TRY(e, call)                                                                         \
+  do {                                                                                            \
+    cudaError_t _err = (call);                                                                    \
+    if (_err != cudaSuccess)                                                                      \
+      return fail((e), _err == cudaErrorMemoryAllocation ? SGR_ERR_OOM : SGR_ERR_CUDA, "%s: %s", #call, \
+                  cudaGetErrorString(_err));                                                      \
+  } while (0)
+
+int32_t use_device(sgr_engine* e) {
+  CUDA_TRY(e, cudaSetDevice(e->device));
+  return SGR_OK;
+}
+
+int32_t compile_program(sgr_engine* e, const sgr_fold_program* p, DevProgram* d) {
+  if (p->state_bytes < 16 || p->state_bytes > SGR_MAX_STATE_BYTES || p->state_bytes % 16)
+    return fail(e, SGR_ERR_INVALID, "state_bytes %u must be a multiple of 16 in [16,%u]", p->state_bytes, SGR_MAX_STATE_BYTES);
+  if (p->record_kind != SGR_REC_FIXED64 && p->record_kind != SGR_REC_VAR16)
+    return fail(e, SGR_ERR_INVALID, "unknown record_kind %u", p->record_kind);
+  if (p->n_types == 0 || p->n_types > SGR_MAX_TYPES) return fail(e, SGR_ERR_INVALID, "n_types %u out of range", p->n_types);
+  if (p->n_f64_fields > 8) return fail(e, SGR_ERR_INVALID, "n_f64_fields %u > 8", p->n_f64_fields);
+  memset(d, 0, sizeof *d);
+  d->state_words = p->state_bytes / 4;
+  d->user_words = d->state_words - 2;
+  d->record_kind = p->record_kind;
+  d->n_types = p->n_types;
+  d->n_f64 = p->n_f64_fields;
+  const uint32_t user_bytes = p->state_bytes - 8;
+  for (uint32_t f = 0; f < p->n_f64_fields; ++f) {
+    if (p->f64_field_off[f] % 4 || p->f64_field_off[f] + 8u > user_bytes)
+      return fail(e, SGR_ERR_INVALID, "f64 field %u at offset %u outside the program area", f, p->f64_field_off[f]);
+    d->f64_word[f] = p->f64_field_off[f] / 4;
+  }
+  const uint32_t max_src = p->record_kind == SGR_REC_FIXED64 ? 64u : 0xfffcu;
+  for (uint32_t t = 0; t < p->n_types; ++t) {
+    const sgr_rule& r = p->rules[t];
+    if (r.exists_rule > SGR_THROW) return fail(e, SGR_ERR_INVALID, "rule %u: bad exists_rule %u", t, r.exists_rule);
+    if (r.n_ops > SGR_MAX_OPS) return fail(e, SGR_ERR_INVALID, "rule %u: n_ops %u > %u", t, r.n_ops, SGR_MAX_OPS);
+    DevRule& dr = d->rules[t];
+    dr.exists_rule = r.exists_rule;
+    dr.n_ops = (r.exists_rule == SGR_TOMBSTONE || r.exists_rule == SGR_THROW) ? 0 : r.n_ops;
+    dr.min_len = 16;
+    for (uint32_t i = 0; i < dr.n_ops; ++i) {
+      const sgr_op& o = r.ops[i];
+      if (o.opcode > SGR_OP_SUB_I64) return fail(e, SGR_ERR_UNSUPPORTED, "rule %u op %u: opcode %u", t, i, o.opcode);
+      uint32_t len = o.len;
+      if (o.opcode == SGR_OP_ADD_I32 || o.opcode == SGR_OP_SUB_I32) { if (len != 4) return fail(e, SGR_ERR_INVALID, "rule %u op %u: i32 op needs len 4", t, i); }
+      else if (o.opcode == SGR_OP_ADD_I64 || o.opcode == SGR_OP_SUB_I64) { if (len != 8) return fail(e, SGR_ERR_INVALID, "rule %u op %u: i64 op needs len 8", t, i); }
+      if (len == 0 || len % 4 || o.dst_off % 4 || o.src_off % 4)
+        return fail(e, SGR_ERR_INVALID, "rule %u op %u: offsets and length must be non-zero multiples of 4", t, i);
+      if (o.dst_off + len > user_bytes) return fail(e, SGR_ERR_INVALID, "rule %u op %u: writes past the program area", t, i);
+      if (o.src_off + len > max_src) return fail(e, SGR_ERR_INVALID, "rule %u op %u: reads past the record", t, i);
+      if (o.src_off + len > dr.min_len) dr.min_len = o.src_off + len;
+      dr.ops[i] = pack_op(o.opcode, len / 4, o.dst_off / 4, o.src_off / 4);
+    }
+  }
+  return SGR_OK;
+}
+
+void mark_dirty(sgr_engine* e) { e->snapshot_dirty.store(true, std::memory_order_release); }
+
+int32_t ensure_states(sgr_engine* e, uint64_t n_agg) {
+  const size_t need = (size_t)n_agg * e->program.state_bytes;
+  if (e->states_n != n_agg || e->states.cap < need) {
+    CUDA_TRY(e, e->states.reserve(need));
+    e->states_n = n_agg;
+    e->states_valid = false;
+  }
+  return SGR_OK;
+}
+
+// publish a host snapshot of the live state table for sgr_get
+int32_t refresh_snapshot(sgr_engine* e, std::shared_ptr<Snapshot>* out) {
+  std::lock_guard<std::mutex> g(e->snap_mu);
+  if (!e->snapshot_dirty.load(std::memory_order_acquire) && e->snapshot) { *out = e->snapshot; return SGR_OK; }
+  if (!e->states_valid) return fail(e, SGR_ERR_STATE, "state store is not readable: no fold has completed");
+  int32_t rc = use_device(e); if (rc) return rc;
+  auto s = std::make_shared<Snapshot>();
+  s->n_agg = e->states_n; s->state_bytes = e->program.state_bytes;
+  s->states.resize((size_t)s->n_agg * s->state_bytes);
+  CUDA_TRY(e, cudaMemcpyAsync(s->states.data(), e->states.p, s->states.size(), cudaMemcpyDeviceToHost, e->stream));
+  CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+  std::atomic_store(&e->snapshot, s);
+  e->snapshot_dirty.store(false, std::memory_order_release);
+  *out = s;
+  return SGR_OK;
+}
+
+int32_t run_fold(sgr_engine* e, const uint8_t* d_events, const uint64_t* d_offsets, const uint32_t* d_ids,
+                 uint64_t n_seg, bool use_prior, uint64_t event_bytes, bool timed) {
+  FoldArgs a{};
+  a.events = d_events; a.seg_offsets = d_offsets; a.seg_ids = d_ids; a.n_seg = n_seg;
+  a.states_in = use_prior ? (const uint8_t*)e->states.p : nullptr;
+  a.states_out = (uint8_t*)e->states.p;
+  a.counters = (unsigned long long*)e->counters.p;
+  a.long_threshold = (uint64_t)e->opt_long_threshold;
+  CUDA_TRY(e, cudaMemsetAsync(e->counters.p, 0, 64, e->stream));
+  if (timed) CUDA_TRY(e, cudaEventRecord(e->ev0, e->stream));
+  FoldLaunchInfo info{};
+  uint32_t launches = 0;
+  if (n_seg) {
+    cudaError_t le = launch_fold_stream(a, e->dprog, (int)e->opt_variant, e->num_sms, e->max_record_bytes, e->stream, &info);
+    if (le != cudaSuccess) return fail(e, SGR_ERR_CUDA, "fold launch: %s", cudaGetErrorString(le));
+    launches = 1;
+  }
+  if (timed) CUDA_TRY(e, cudaEventRecord(e->ev1, e->stream));
+  unsigned long long h[8];
+  CUDA_TRY(e, cudaMemcpyAsync(h, e->counters.p, 64, cudaMemcpyDeviceToHost, e->stream));
+  CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+  if (timed) CUDA_TRY(e, cudaEventElapsedTime(&e->stats.ms_fold, e->ev0, e->ev1));
+  e->stats.n_aggregates = n_seg;
+  e->stats.n_events = h[0];
+  e->stats.n_errors = h[1];
+  e->stats.n_long_segments = h[2];
+  e->stats.event_bytes = event_bytes;
+  e->stats.algorithmic_bytes = event_bytes + 8 * (n_seg + 1) + (uint64_t)e->program.state_bytes * n_seg * (use_prior ? 2 : 1) +
+                               (d_ids ? 4 * n_seg : 0);
+  e->stats.fold_launches = launches;
+  return SGR_OK;
+}
+
+}  // namespace
+
+// ================================================================== C ABI
+extern "C" {
+
+int32_t sgr_abi_version(void) { return SGR_ABI_VERSION; }
+
+const char* sgr_last_error(const sgr_engine* e) { return e ? e->last_error.c_str() : g_create_error.c_str(); }
+
+int32_t sgr_create(const sgr_config* cfg, sgr_engine** out) {
+  if (!out) return fail(nullptr, SGR_ERR_INVALID, "out is NULL");
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&ndev);
+  if (ce != cudaSuccess || ndev == 0)
+    return fail(nullptr, SGR_ERR_NO_DEVICE, "no CUDA device (%s); the replay engine has no CPU fallback",
+                ce != cudaSuccess ? cudaGetErrorString(ce) : "device count 0");
+  const int dev = cfg ? cfg->device : 0;
+  if (dev < 0 || dev >= ndev) return fail(nullptr, SGR_ERR_NO_DEVICE, "device %d out of range (have %d)", dev, ndev);
+  cudaDeviceProp prop;
+  if ((ce = cudaGetDeviceProperties(&prop, dev)) != cudaSuccess)
+    return fail(nullptr, SGR_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(ce));
+  if (prop.major != 10)
+    return fail(nullptr, SGR_ERR_NO_DEVICE, "device %d is sm_%d%d; kernels are built for sm_100a only", dev, prop.major, prop.minor);
+  std::unique_ptr<sgr_engine> e(new sgr_engine());
+  e->device = dev;
+  e->num_sms = prop.multiProcessorCount;
+  if ((ce = cudaSetDevice(dev)) != cudaSuccess) return fail(nullptr, SGR_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(ce));
+  if ((ce = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+      (ce = cudaEventCreate(&e->ev0)) != cudaSuccess || (ce = cudaEventCreate(&e->ev1)) != cudaSuccess ||
+      (ce = e->counters.reserve(64)) != cudaSuccess)
+    return fail(nullptr, SGR_ERR_CUDA, "engine setup: %s", cudaGetErrorString(ce));
+  *out = e.release();
+  return SGR_OK;
+}
+
+int32_t sgr_destroy(sgr_engine* e) {
+  if (!e) return SGR_OK;
+  cudaSetDevice(e->device);
+  cudaStreamSynchronize(e->stream);
+  e->own_events.release(); e->own_offsets.release(); e->states.release(); e->counters.release();
+  e->inc_records.release(); e->inc_offsets.release(); e->inc_ids.release(); e->inc_prev_ids.release();
+  e->group.release();
+  cudaEventDestroy(e->ev0); cudaEventDestroy(e->ev1);
+  cudaStreamDestroy(e->stream);
+  delete e;
+  return SGR_OK;
+}
+
+int32_t sgr_register_program(sgr_engine* e, const sgr_fold_program* prog) {
+  if (!e || !prog) return fail(e, SGR_ERR_INVALID, "null argument");
+  DevProgram d;
+  int32_t rc = compile_program(e, prog, &d);
+  if (rc) return rc;
+  e->program = *prog; e->dprog = d; e->has_program = true;
+  e->states_valid = false; e->states_n = 0;
+  mark_dirty(e);
+  return SGR_OK;
+}
+
+static int32_t after_load(sgr_engine* e, const uint8_t* d_events, const uint64_t* d_offsets, uint64_t nbytes, uint64_t n_agg) {
+  e->d_events = d_events; e->d_offsets = d_offsets; e->event_bytes = nbytes; e->n_agg = n_agg; e->loaded = true;
+  // variable records: the format caps a record at 16+512 bytes unless the caller raises
+  // "max_record_bytes"; a longer record is flagged as a malformed event by the kernel, never mis-parsed
+  e->max_record_bytes = e->program.record_kind == SGR_REC_VAR16 ? (uint32_t)e->opt_max_record_bytes : 64u;
+  return SGR_OK;
+}
+
+int32_t sgr_load_events(sgr_engine* e, const void* events, uint64_t nbytes, const uint64_t* seg_offsets, uint64_t n_agg) {
+  if (!e || (!events && nbytes) || !seg_offsets) return fail(e, SGR_ERR_INVALID, "null argument");
+  if (!e->has_program) return fail(e, SGR_ERR_NO_PROGRAM, "register a fold program before loading events");
+  if (seg_offsets[n_agg] > nbytes) return fail(e, SGR_ERR_INVALID, "seg_offsets[n_agg]=%llu exceeds nbytes=%llu",
+                                               (unsigned long long)seg_offsets[n_agg], (unsigned long long)nbytes);
+  for (uint64_t i = 0; i <= n_agg; ++i) {
+    if (seg_offsets[i] % 16) return fail(e, SGR_ERR_INVALID, "seg_offsets[%llu] is not a multiple of 16", (unsigned long long)i);
+    if (i && seg_offsets[i] < seg_offsets[i - 1]) return fail(e, SGR_ERR_INVALID, "seg_offsets not monotone at %llu", (unsigned long long)i);
+  }
+  int32_t rc = use_device(e); if (rc) return rc;
+  CUDA_TRY(e, e->own_events.reserve(nbytes));
+  CUDA_TRY(e, e->own_offsets.reserve((n_agg + 1) * 8));
+  CUDA_TRY(e, cudaEventRecord(e->ev0, e->stream));
+  CUDA_TRY(e, cudaMemcpyAsync(e->own_events.p, events, nbytes, cudaMemcpyHostToDevice, e->stream));
+  CUDA_TRY(e, cudaMemcpyAsync(e->own_offsets.p, seg_offsets, (n_agg + 1) * 8, cudaMemcpyHostToDevice, e->stream));
+  CUDA_TRY(e, cudaEventRecord(e->ev1, e->stream));
+  CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+  CUDA_TRY(e, cudaEventElapsedTime(&e->stats.ms_h2d, e->ev0, e->ev1));
+  e->stats.ms_group = 0;
+  return after_load(e, (const uint8_t*)e->own_events.p, (const uint64_t*)e->own_offsets.p, nbytes, n_agg);
+}
+
+int32_t sgr_load_events_device(sgr_engine* e, const void* d_events, uint64_t nbytes, const uint64_t* d_seg_offsets, uint64_t n_agg) {
+  if (!e || (!d_events && nbytes) || !d_seg_offsets) return fail(e, SGR_ERR_INVALID, "null argument");
+  if (!e->has_program) return fail(e, SGR_ERR_NO_PROGRAM, "register a fold program before loading events");
+  if (((uintptr_t)d_events) % 16) return fail(e, SGR_ERR_INVALID, "device event log must be 16-byte aligned");
+  int32_t rc = use_device(e); if (rc) return rc;
+  e->stats.ms_h2d = 0; e->stats.ms_group = 0;
+  return after_load(e, (const uint8_t*)d_events, d_seg_offsets, nbytes, n_agg);
+}
+
+static int32_t load_unsorted_impl(sgr_engine* e, const void* d_records, uint64_t n_records, uint64_t n_agg) {
+  if (e->program.record_kind != SGR_REC_FIXED64) return fail(e, SGR_ERR_UNSUPPORTED, "unsorted loads take fixed 64-byte records");
+  if (n_agg >= (1ull << 32) || n_records >= (1ull << 32)) return fail(e, SGR_ERR_UNSUPPORTED, "group-by is limited to 2^32 records/aggregates");
+  CUDA_TRY(e, e->own_events.reserve(n_records * 64));
+  CUDA_TRY(e, e->own_offsets.reserve((n_agg + 1) * 8));
+  CUDA_TRY(e, cudaEventRecord(e->ev0, e->stream));
+  unsigned long long bad = 0;
+  cudaError_t ce = group_by_agg_stable(e->group, (const uint8_t*)d_records, n_records, n_agg, (uint8_t*)e->own_events.p,
+                                       (uint64_t*)e->own_offsets.p, nullptr, nullptr, (unsigned long long*)e->counters.p, e->stream, &bad);
+  if (ce != cudaSuccess) return fail(e, SGR_ERR_CUDA, "group-by: %s", cudaGetErrorString(ce));
+  CUDA_TRY(e, cudaEventRecord(e->ev1, e->stream));
+  CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+  CUDA_TRY(e, cudaEventElapsedTime(&e->stats.ms_group, e->ev0, e->ev1));
+  if (bad) return fail(e, SGR_ERR_INVALID, "%llu records carry an aggregate index >= n_agg", bad);
+  return after_load(e, (const uint8_t*)e->own_events.p, (const uint64_t*)e->own_offsets.p, n_records * 64, n_agg);
+}
+
+int32_t sgr_load_unsorted_device(sgr_engine* e, const void* d_records, uint64_t n_records, uint64_t n_agg) {
+  if (!e || (!d_records && n_records)) return fail(e, SGR_ERR_INVALID, "null argument");
+  if (!e->has_program) return fail(e, SGR_ERR_NO_PROGRAM, "register a fold program before loading events");
+  int32_t rc = use_device(e); if (rc) return rc;
+  e->stats.ms_h2d = 0;
+  return load_unsorted_impl(e, d_records, n_records, n_agg);
+}
+
+int32_t sgr_load_unsorted(sgr_engine* e, const void* records, uint64_t n_records, uint64_t n_agg) {
+  if (!e || (!records && n_records)) return fail(e, SGR_ERR_INVALID, "null argument");
+  if (!e->has_program) return fail(e, SGR_ERR_NO_PROGRAM, "register a fold program before loading events");
+  int32_t rc = use_device(e); if (rc) return rc;
+  CUDA_TRY(e, e->inc_records.reserve(n_records * 64));
+  CUDA_TRY(e, cudaEventRecord(e->ev0, e->stream));
+  CUDA_TRY(e, cudaMemcpyAsync(e->inc_records.p, records, n_records * 64, cudaMemcpyHostToDevice, e->stream));
+  CUDA_TRY(e, cudaEventRecord(e->ev1, e->stream));
+  CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+  CUDA_TRY(e, cudaEventElapsedTime(&e->stats.ms_h2d, e->ev0, e->ev1));
+  return load_unsorted_impl(e, e->inc_records.p, n_records, n_agg);
+}
+
+int32_t sgr_set_initial_states(sgr_engine* e, const void* states, uint64_t n_agg) {
+  if (!e) return SGR_ERR_INVALID;
+  if (!e->has_program) return fail(e, SGR_ERR_NO_PROGRAM, "register a fold program first");
+  int32_t rc = use_device(e); if (rc) return rc;
+  if (!states) { e->states_valid = false; mark_dirty(e); return SGR_OK; }
+  rc = ensure_states(e, n_agg); if (rc) return rc;
+  CUDA_TRY(e, cudaMemcpyAsync(e->states.p, states, (size_t)n_agg * e->program.state_bytes, cudaMemcpyHostToDevice, e->stream));
+  CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+  e->states_valid = true;
+  mark_dirty(e);
+  return SGR_OK;
+}
+
+int32_t sgr_fold(sgr_engine* e) {
+  if (!e) return SGR_ERR_INVALID;
+  if (!e->has_program) return fail(e, SGR_ERR_NO_PROGRAM, "no fold program registered");
+  if (!e->loaded) return fail(e, SGR_ERR_NOT_LOADED, "no event log loaded");
+  int32_t rc = use_device(e); if (rc) return rc;
+  const bool prior = e->states_valid && e->states_n == e->n_agg;
+  rc = ensure_states(e, e->n_agg); if (rc) return rc;
+  rc = run_fold(e, e->d_events, e->d_offsets, nullptr, e->n_agg, prior, e->d_offsets ? e->event_bytes : 0, true);
+  if (rc) return rc;
+  e->states_valid = true;
+  e->inc_prev_n = 0;
+  mark_dirty(e);
+  return SGR_OK;
+}
+
+static int32_t fold_incremental_impl(sgr_engine* e, const void* d_records, uint64_t n_records) {
+  if (e->program.record_kind != SGR_REC_FIXED64) return fail(e, SGR_ERR_UNSUPPORTED, "incremental batches take fixed 64-byte records");
+  if (!e->states_valid) return fail(e, SGR_ERR_NOT_LOADED, "incremental fold needs a live state table (fold or set_initial_states first)");
+  const uint64_t n_agg = e->states_n;
+  CUDA_TRY(e, e->inc_offsets.reserve((n_records + 2) * 8));
+  CUDA_TRY(e, e->inc_ids.reserve((n_records + 1) * 4));
+  DevBuf& grouped = e->group.batch_records;
+  CUDA_TRY(e, grouped.reserve(n_records * 64));
+  CUDA_TRY(e, cudaEventRecord(e->ev0, e->stream));
+  // per-batch flags (CHANGED/ERROR) of the aggregates touched by the previous batch are cleared
+  if (e->inc_prev_n) clear_batch_flags((uint8_t*)e->states.p, e->program.state_bytes, (const uint32_t*)e->inc_prev_ids.p, e->inc_prev_n, e->stream);
+  else clear_batch_flags((uint8_t*)e->states.p, e->program.state_bytes, nullptr, n_agg, e->stream);
+  unsigned long long bad = 0;
+  uint64_t n_touched = 0;
+  cudaError_t ce = group_by_agg_stable(e->group, (const uint8_t*)d_records, n_records, n_agg, (uint8_t*)grouped.p,
+                                       (uint64_t*)e->inc_offsets.p, (uint32_t*)e->inc_ids.p, &n_touched,
+                                       (unsigned long long*)e->counters.p, e->stream, &bad);
+  if (ce != cudaSuccess) return fail(e, SGR_ERR_CUDA, "group-by: %s", cudaGetErrorString(ce));
+  CUDA_TRY(e, cudaEventRecord(e->ev1, e->stream));
+  if (bad) return fail(e, SGR_ERR_INVALID, "%llu records carry an aggregate index >= n_agg", bad);
+  int32_t rc = run_fold(e, (const uint8_t*)grouped.p, (const uint64_t*)e->inc_offsets.p, (const uint32_t*)e->inc_ids.p, n_touched, true,
+                        n_records * 64, true);
+  if (rc) return rc;
+  CUDA_TRY(e, cudaEventElapsedTime(&e->stats.ms_group, e->ev0, e->ev1));
+  // remember who was touched so the next batch can clear their per-batch flags
+  std::swap(e->inc_ids, e->inc_prev_ids);
+  e->inc_prev_n = n_touched;
+  mark_dirty(e);
+  return SGR_OK;
+}
+
+int32_t sgr_fold_incremental_device(sgr_engine* e, const void* d_records, uint64_t n_records) {
+  if (!e || (!d_records && n_records)) return fail(e, SGR_ERR_INVALID, "null argument");
+  if (!e->has_program) return fail(e, SGR_ERR_NO_PROGRAM, "no fold program registered");
+  int32_t rc = use_device(e); if (rc) return rc;
+  e->stats.ms_h2d = 0;
+  return fold_incremental_impl(e, d_records, n_records);
+}
+
+int32_t sgr_fold_incremental(sgr_engine* e, const void* records, uint64_t n_records) {
+  if (!e || (!records && n_records)) return fail(e, SGR_ERR_INVALID, "null argument");
+  if (!e->has_program) return fail(e, SGR_ERR_NO_PROGRAM, "no fold program registered");
+  int32_t rc = use_device(e); if (rc) return rc;
+  CUDA_TRY(e, e->inc_records.reserve(n_records * 64));
+  CUDA_TRY(e, cudaMemcpyAsync(e->inc_records.p, records, n_records * 64, cudaMemcpyHostToDevice, e->stream));
+  return fold_incremental_impl(e, e->inc_records.p, n_records);
+}
+
+int32_t sgr_load_keys(sgr_engine* e, const uint8_t* keys, const uint32_t* key_offsets, uint64_t n_agg) {
+  if (!e || !key_offsets || (!keys && n_agg && key_offsets[n_agg])) return fail(e, SGR_ERR_INVALID, "null argument");
+  std::string err;
+  if (!e->keys.build(keys, key_offsets, n_agg, &err)) return fail(e, SGR_ERR_INVALID, "%s", err.c_str());
+  return SGR_OK;
+}
+
+int32_t sgr_get_index(sgr_engine* e, uint64_t agg, void* out, uint32_t cap, uint32_t* outlen, int32_t* exists,
+                      uint32_t* flags, uint32_t* err_idx) {
+  if (!e) return SGR_ERR_INVALID;
+  std::shared_ptr<Snapshot> s = std::atomic_load(&e->snapshot);
+  if (!s || e->snapshot_dirty.load(std::memory_order_acquire)) {
+    int32_t rc = refresh_snapshot(e, &s); if (rc) return rc;
+  }
+  if (agg >= s->n_agg) return fail(e, SGR_ERR_INVALID, "aggregate index %llu out of range", (unsigned long long)agg);
+  const uint8_t* st = s->states.data() + agg * s->state_bytes;
+  uint32_t fl, ei;
+  memcpy(&fl, st + s->state_bytes - 8, 4); memcpy(&ei, st + s->state_bytes - 4, 4);
+  const uint32_t user = s->state_bytes - 8;
+  if (flags) *flags = fl;
+  if (err_idx) *err_idx = ei;
+  if (exists) *exists = (fl & SGR_ST_EXISTS) ? 1 : 0;
+  if (outlen) *outlen = (fl & SGR_ST_EXISTS) ? user : 0;
+  if ((fl & SGR_ST_EXISTS) && out) {
+    if (cap < user) return fail(e, SGR_ERR_CAPACITY, "buffer of %u bytes is smaller than the state (%u)", cap, user);
+    memcpy(out, st, user);
+  }
+  return SGR_OK;
+}
+
+int32_t sgr_get(sgr_engine* e, const uint8_t* key, uint32_t klen, void* out, uint32_t cap, uint32_t* outlen, int32_t* exists) {
+  if (!e || (!key && klen)) return fail(e, SGR_ERR_INVALID, "null argument");
+  int64_t idx = e->keys.find(key, klen);
+  if (idx < 0) {  // unknown aggregate id: Option.empty, like a KTable miss
+    if (exists) *exists = 0;
+    if (outlen) *outlen = 0;
+    // still surface "store not readable" the way the reference does
+    std::shared_ptr<Snapshot> s = std::atomic_load(&e->snapshot);
+    if (!s || e->snapshot_dirty.load(std::memory_order_acquire)) { int32_t rc = refresh_snapshot(e, &s); if (rc) return rc; }
+    return SGR_OK;
+  }
+  return sgr_get_index(e, (uint64_t)idx, out, cap, outlen, exists, nullptr, nullptr);
+}
+
+int32_t sgr_export_states(sgr_engine* e, void* out, uint64_t cap, uint8_t* exists_bits, uint8_t* changed_bits, uint8_t* error_bits) {
+  if (!e) return SGR_ERR_INVALID;
+  if (!e->states_valid) return fail(e, SGR_ERR_STATE, "no folded state table to export");
+  int32_t rc = use_device(e); if (rc) return rc;
+  const uint64_t n = e->states_n; const uint32_t sb = e->program.state_bytes;
+  const uint64_t need = n * sb;
+  std::vector<uint8_t> tmp;
+  uint8_t* host = (uint8_t*)out;
+  if (out) { if (cap < need) return fail(e, SGR_ERR_CAPACITY, "export needs %llu bytes, buffer has %llu", (unsigned long long)need, (unsigned long long)cap); }
+  else { tmp.resize(need); host = tmp.data(); }
+  CUDA_TRY(e, cudaEventRecord(e->ev0, e->stream));
+  CUDA_TRY(e, cudaMemcpyAsync(host, e->states.p, need, cudaMemcpyDeviceToHost, e->stream));
+  CUDA_TRY(e, cudaEventRecord(e->ev1, e->stream));
+  CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+  CUDA_TRY(e, cudaEventElapsedTime(&e->stats.ms_d2h, e->ev0, e->ev1));
+  if (exists_bits || changed_bits || error_bits) {
+    const uint64_t nb = (n + 7) / 8;
+    if (exists_bits) memset(exists_bits, 0, nb);
+    if (changed_bits) memset(changed_bits, 0, nb);
+    if (error_bits) memset(error_bits, 0, nb);
+    for (uint64_t i = 0; i < n; ++i) {
+      uint32_t fl; memcpy(&fl, host + i * sb + sb - 8, 4);
+      if (exists_bits && (fl & SGR_ST_EXISTS)) exists_bits[i >> 3] |= (uint8_t)(1u << (i & 7));
+      if (changed_bits && (fl & SGR_ST_CHANGED)) changed_bits[i >> 3] |= (uint8_t)(1u << (i & 7));
+      if (error_bits && (fl & SGR_ST_ERROR)) error_bits[i >> 3] |= (uint8_t)(1u << (i & 7));
+    }
+  }
+  return SGR_OK;
+}
+
+int32_t sgr_states_device(sgr_engine* e, void** d_states, uint64_t* n_agg, uint32_t* state_bytes) {
+  if (!e) return SGR_ERR_INVALID;
+  if (!e->states_valid) return fail(e, SGR_ERR_STATE, "no folded state table");
+  if (d_states) *d_states = e->states.p;
+  if (n_agg) *n_agg = e->states_n;
+  if (state_bytes) *state_bytes = e->program.state_bytes;
+  return SGR_OK;
+}
+
+int32_t sgr_events_device(sgr_engine* e, void** d_events, uint64_t* nbytes, uint64_t** d_seg_offsets) {
+  if (!e) return SGR_ERR_INVALID;
+  if (!e->loaded) return fail(e, SGR_ERR_NOT_LOADED, "no event log loaded");
+  if (d_events) *d_events = (void*)e->d_events;
+  if (nbytes) *nbytes = e->event_bytes;
+  if (d_seg_offsets) *d_seg_offsets = (uint64_t*)e->d_offsets;
+  return SGR_OK;
+}
+
+int32_t sgr_get_stats(sgr_engine* e, sgr_stats* out) {
+  if (!e || !out) return SGR_ERR_INVALID;
+  *out = e->stats;
+  return SGR_OK;
+}
+
+int32_t sgr_set_option(sgr_engine* e, const char* name, int64_t value) {
+  if (!e || !name) return SGR_ERR_INVALID;
+  if (!strcmp(name, "fold_variant")) { e->opt_variant = value; return SGR_OK; }
+  if (!strcmp(name, "long_threshold")) { e->opt_long_threshold = value; return SGR_OK; }
+  if (!strcmp(name, "max_record_bytes")) {
+    if (value < 16 || value > 2048 + 16) return fail(e, SGR_ERR_INVALID, "max_record_bytes must be in [16, 2064]");
+    e->opt_max_record_bytes = value; return SGR_OK;
+  }
+  return fail(e, SGR_ERR_INVALID, "unknown option '%s'", name);
+}
+
+int32_t sgr_stream(sgr_engine* e, void** stream) {
+  if (!e || !stream) return SGR_ERR_INVALID;
+  *stream = (void*)e->stream;
+  return SGR_OK;
+}
+
+}  // extern "C"
