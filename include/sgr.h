@@ -203,6 +203,12 @@ int32_t sgr_set_initial_states(sgr_engine* e, const void* states, uint64_t n_agg
  * events.foldLeft(state)(handleEvent), SDSL/command/CommandModels.scala:25-28. */
 int32_t sgr_fold(sgr_engine* e);
 
+/* The same fold without host synchronisation: sgr_fold_async enqueues the kernels on the engine's
+ * stream and returns; sgr_wait blocks until they finish and collects the statistics. Any call that
+ * reads results (get/export/stats) waits implicitly. */
+int32_t sgr_fold_async(sgr_engine* e);
+int32_t sgr_wait(sgr_engine* e);
+
 /* Append one micro-batch (arrival order, fixed records) to the live state table: group by
  * aggregate, fold onto the current states, write back (PersistentActor.doApplyEvent on a
  * live actor, PersistentActor.scala:245-264). Requires a prior fold or set_initial_states. */

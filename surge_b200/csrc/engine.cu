@@ -16,6 +16,7 @@
 #include "../../include/sgr.h"
 #include "devbuf.h"
 #include "fold_kernels.cuh"
+#include "fold_rows.cuh"
 #include "group_kernels.cuh"
 #include "keytable.h"
 
@@ -59,6 +60,21 @@ struct sgr_engine {
   DevBuf inc_records, inc_offsets, inc_ids, inc_prev_ids;  // K6
   uint64_t inc_prev_n = 0;
 
+  // record-parallel path (fold_rows.cu)
+  bool row_ok = false;            // program is inside the transformer algebra
+  RowProgram row_prog{};
+  int row_max_grid = 0;
+  DevBuf part_flags, part_data, redo_ids;
+  uint32_t epoch = 0;
+  bool offsets_aligned64 = false; // every segment offset == log_begin (mod 64)
+  uint64_t log_begin = 0, log_end = 0;
+  bool fold_pending = false;      // a fold was enqueued and not yet finished
+  bool pending_used_rows = false, pending_prior = false, pending_timed_group = false;
+  uint64_t pending_n_seg = 0, pending_event_bytes = 0;
+  const uint8_t* pending_events = nullptr; const uint64_t* pending_offsets = nullptr; const uint32_t* pending_ids = nullptr;
+  cudaEvent_t ev2 = nullptr, ev3 = nullptr;
+
+  int64_t opt_kernel = 0;         // 0 auto, 1 force lane-sequential (fold_kernels.cu), 2 force rows
   int64_t opt_variant = -1;
   int64_t opt_long_threshold = 0;
   int64_t opt_max_record_bytes = 528;
@@ -138,6 +154,8 @@ int32_t compile_program(sgr_engine* e, const sgr_fold_program* p, DevProgram* d)
   return SGR_OK;
 }
 
+int32_t finish_fold(sgr_engine* e);
+
 void mark_dirty(sgr_engine* e) { e->snapshot_dirty.store(true, std::memory_order_release); }
 
 int32_t ensure_states(sgr_engine* e, uint64_t n_agg) {
@@ -156,6 +174,7 @@ int32_t refresh_snapshot(sgr_engine* e, std::shared_ptr<Snapshot>* out) {
   if (!e->snapshot_dirty.load(std::memory_order_acquire) && e->snapshot) { *out = e->snapshot; return SGR_OK; }
   if (!e->states_valid) return fail(e, SGR_ERR_STATE, "state store is not readable: no fold has completed");
   int32_t rc = use_device(e); if (rc) return rc;
+  rc = finish_fold(e); if (rc) return rc;
   auto s = std::make_shared<Snapshot>();
   s->n_agg = e->states_n; s->state_bytes = e->program.state_bytes;
   s->states.resize((size_t)s->n_agg * s->state_bytes);
@@ -167,36 +186,102 @@ int32_t refresh_snapshot(sgr_engine* e, std::shared_ptr<Snapshot>* out) {
   return SGR_OK;
 }
 
-int32_t run_fold(sgr_engine* e, const uint8_t* d_events, const uint64_t* d_offsets, const uint32_t* d_ids,
-                 uint64_t n_seg, bool use_prior, uint64_t event_bytes, bool timed) {
-  FoldArgs a{};
-  a.events = d_events; a.seg_offsets = d_offsets; a.seg_ids = d_ids; a.n_seg = n_seg;
-  a.states_in = use_prior ? (const uint8_t*)e->states.p : nullptr;
-  a.states_out = (uint8_t*)e->states.p;
-  a.counters = (unsigned long long*)e->counters.p;
-  a.long_threshold = (uint64_t)e->opt_long_threshold;
+constexpr uint64_t kRedoCap = 1u << 20;
+
+// Enqueue one fold on the engine's stream (no host synchronisation).
+int32_t enqueue_fold(sgr_engine* e, const uint8_t* d_events, const uint64_t* d_offsets, const uint32_t* d_ids,
+                     uint64_t n_seg, bool use_prior, uint64_t event_bytes, bool aligned64, uint64_t log_begin, uint64_t log_end) {
   CUDA_TRY(e, cudaMemsetAsync(e->counters.p, 0, 64, e->stream));
-  if (timed) CUDA_TRY(e, cudaEventRecord(e->ev0, e->stream));
-  FoldLaunchInfo info{};
+  const uint8_t* states_in = use_prior ? (const uint8_t*)e->states.p : nullptr;
+  bool use_rows = e->row_ok && aligned64 && e->opt_kernel != 1 && n_seg < (1ull << 32);
+  if (e->opt_kernel == 2 && !use_rows) return fail(e, SGR_ERR_UNSUPPORTED, "record-parallel kernel cannot take this program/log");
+  CUDA_TRY(e, cudaEventRecord(e->ev0, e->stream));
   uint32_t launches = 0;
   if (n_seg) {
-    cudaError_t le = launch_fold_stream(a, e->dprog, (int)e->opt_variant, e->num_sms, e->max_record_bytes, e->stream, &info);
-    if (le != cudaSuccess) return fail(e, SGR_ERR_CUDA, "fold launch: %s", cudaGetErrorString(le));
-    launches = 1;
+    FoldArgs a{};
+    a.events = d_events; a.seg_offsets = d_offsets; a.seg_ids = d_ids; a.n_seg = n_seg;
+    a.states_in = states_in; a.states_out = (uint8_t*)e->states.p;
+    a.counters = (unsigned long long*)e->counters.p;
+    a.long_threshold = (uint64_t)e->opt_long_threshold;
+    FoldLaunchInfo info{};
+    if (use_rows) {
+      if (!e->row_max_grid) e->row_max_grid = row_kernel_max_grid(e->num_sms);
+      const uint64_t n_warps_max = (uint64_t)e->row_max_grid * (kRowThreads / 32);
+      CUDA_TRY(e, e->part_flags.reserve(n_warps_max * 4 + 256));
+      CUDA_TRY(e, e->part_data.reserve(n_warps_max * (e->row_prog.user_words + 2) * 4 + 256));
+      CUDA_TRY(e, e->redo_ids.reserve(kRedoCap * 4));
+      if (e->epoch == 0) CUDA_TRY(e, cudaMemsetAsync(e->part_flags.p, 0, e->part_flags.cap, e->stream));
+      ++e->epoch;
+      if (e->epoch == 0) { CUDA_TRY(e, cudaMemsetAsync(e->part_flags.p, 0, e->part_flags.cap, e->stream)); e->epoch = 1; }
+      RowArgs r{};
+      r.events = d_events; r.seg_offsets = d_offsets; r.seg_ids = d_ids; r.n_seg = n_seg;
+      r.log_begin = log_begin; r.log_end = log_end;
+      r.states_in = states_in; r.states_out = (uint8_t*)e->states.p;
+      r.counters = (unsigned long long*)e->counters.p;
+      r.redo_ids = (uint32_t*)e->redo_ids.p; r.redo_cap = kRedoCap;
+      r.part_flags = (uint32_t*)e->part_flags.p; r.part_data = (uint32_t*)e->part_data.p; r.epoch = e->epoch;
+      const uint64_t steps = (log_end - log_begin + 2047) / 2048;
+      uint64_t want = (steps + (kRowThreads / 32) - 1) / (kRowThreads / 32);
+      if (want == 0) want = 1;  // all segments empty: one CTA still writes every (None) state
+      const int grid = (int)(want < (uint64_t)e->row_max_grid ? want : (uint64_t)e->row_max_grid);
+      cudaError_t le = launch_fold_rows(r, e->row_prog, grid, e->stream);
+      if (le != cudaSuccess) return fail(e, SGR_ERR_CUDA, "fold_rows launch: %s", cudaGetErrorString(le));
+      // exact replay of the segments whose handler threw (count lives on the device)
+      a.seg_list = (const uint32_t*)e->redo_ids.p;
+      a.n_seg = kRedoCap;
+      a.n_seg_dev = (const unsigned long long*)e->counters.p + 3;
+      a.long_threshold = 0;
+      le = launch_fold_stream(a, e->dprog, -1, 8, e->max_record_bytes, e->stream, &info);
+      if (le != cudaSuccess) return fail(e, SGR_ERR_CUDA, "replay launch: %s", cudaGetErrorString(le));
+      launches = 2;
+    } else {
+      cudaError_t le = launch_fold_stream(a, e->dprog, (int)e->opt_variant, e->num_sms, e->max_record_bytes, e->stream, &info);
+      if (le != cudaSuccess) return fail(e, SGR_ERR_CUDA, "fold launch: %s", cudaGetErrorString(le));
+      launches = 1;
+    }
   }
-  if (timed) CUDA_TRY(e, cudaEventRecord(e->ev1, e->stream));
+  CUDA_TRY(e, cudaEventRecord(e->ev1, e->stream));
+  e->fold_pending = true; e->pending_used_rows = use_rows; e->pending_prior = use_prior;
+  e->pending_n_seg = n_seg; e->pending_event_bytes = event_bytes;
+  e->pending_events = d_events; e->pending_offsets = d_offsets; e->pending_ids = d_ids;
+  e->stats.fold_launches = launches;
+  return SGR_OK;
+}
+
+// Wait for the enqueued fold and collect its statistics.
+int32_t finish_fold(sgr_engine* e) {
+  if (!e->fold_pending) return SGR_OK;
+  e->fold_pending = false;
   unsigned long long h[8];
   CUDA_TRY(e, cudaMemcpyAsync(h, e->counters.p, 64, cudaMemcpyDeviceToHost, e->stream));
   CUDA_TRY(e, cudaStreamSynchronize(e->stream));
-  if (timed) CUDA_TRY(e, cudaEventElapsedTime(&e->stats.ms_fold, e->ev0, e->ev1));
+  CUDA_TRY(e, cudaEventElapsedTime(&e->stats.ms_fold, e->ev0, e->ev1));
+  if (e->pending_used_rows && h[3] > kRedoCap) {
+    // more throwing aggregates than the replay list holds: redo everything on the sequential kernel
+    FoldArgs a{};
+    a.events = e->pending_events; a.seg_offsets = e->pending_offsets; a.seg_ids = e->pending_ids; a.n_seg = e->pending_n_seg;
+    a.states_in = e->pending_prior ? (const uint8_t*)e->states.p : nullptr; a.states_out = (uint8_t*)e->states.p;
+    a.counters = (unsigned long long*)e->counters.p;
+    if (e->pending_prior) return fail(e, SGR_ERR_UNSUPPORTED, "replay list overflow on an in-place incremental fold");
+    CUDA_TRY(e, cudaMemsetAsync(e->counters.p, 0, 64, e->stream));
+    CUDA_TRY(e, cudaEventRecord(e->ev2, e->stream));
+    FoldLaunchInfo info{};
+    cudaError_t le = launch_fold_stream(a, e->dprog, -1, e->num_sms, e->max_record_bytes, e->stream, &info);
+    if (le != cudaSuccess) return fail(e, SGR_ERR_CUDA, "fold launch: %s", cudaGetErrorString(le));
+    CUDA_TRY(e, cudaEventRecord(e->ev3, e->stream));
+    CUDA_TRY(e, cudaMemcpyAsync(h, e->counters.p, 64, cudaMemcpyDeviceToHost, e->stream));
+    CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+    float ms2 = 0; CUDA_TRY(e, cudaEventElapsedTime(&ms2, e->ev2, e->ev3));
+    e->stats.ms_fold += ms2; e->stats.fold_launches += 1;
+  }
+  const uint64_t n_seg = e->pending_n_seg;
   e->stats.n_aggregates = n_seg;
   e->stats.n_events = h[0];
   e->stats.n_errors = h[1];
   e->stats.n_long_segments = h[2];
-  e->stats.event_bytes = event_bytes;
-  e->stats.algorithmic_bytes = event_bytes + 8 * (n_seg + 1) + (uint64_t)e->program.state_bytes * n_seg * (use_prior ? 2 : 1) +
-                               (d_ids ? 4 * n_seg : 0);
-  e->stats.fold_launches = launches;
+  e->stats.event_bytes = e->pending_event_bytes;
+  e->stats.algorithmic_bytes = e->pending_event_bytes + 8 * (n_seg + 1) +
+                               (uint64_t)e->program.state_bytes * n_seg * (e->pending_prior ? 2 : 1) + (e->pending_ids ? 4 * n_seg : 0);
   return SGR_OK;
 }
 
@@ -230,6 +315,7 @@ int32_t sgr_create(const sgr_config* cfg, sgr_engine** out) {
   if ((ce = cudaSetDevice(dev)) != cudaSuccess) return fail(nullptr, SGR_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(ce));
   if ((ce = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking)) != cudaSuccess ||
       (ce = cudaEventCreate(&e->ev0)) != cudaSuccess || (ce = cudaEventCreate(&e->ev1)) != cudaSuccess ||
+      (ce = cudaEventCreate(&e->ev2)) != cudaSuccess || (ce = cudaEventCreate(&e->ev3)) != cudaSuccess ||
       (ce = e->counters.reserve(64)) != cudaSuccess)
     return fail(nullptr, SGR_ERR_CUDA, "engine setup: %s", cudaGetErrorString(ce));
   *out = e.release();
@@ -243,7 +329,8 @@ int32_t sgr_destroy(sgr_engine* e) {
   e->own_events.release(); e->own_offsets.release(); e->states.release(); e->counters.release();
   e->inc_records.release(); e->inc_offsets.release(); e->inc_ids.release(); e->inc_prev_ids.release();
   e->group.release();
-  cudaEventDestroy(e->ev0); cudaEventDestroy(e->ev1);
+  e->part_flags.release(); e->part_data.release(); e->redo_ids.release();
+  cudaEventDestroy(e->ev0); cudaEventDestroy(e->ev1); cudaEventDestroy(e->ev2); cudaEventDestroy(e->ev3);
   cudaStreamDestroy(e->stream);
   delete e;
   return SGR_OK;
@@ -255,6 +342,7 @@ int32_t sgr_register_program(sgr_engine* e, const sgr_fold_program* prog) {
   int32_t rc = compile_program(e, prog, &d);
   if (rc) return rc;
   e->program = *prog; e->dprog = d; e->has_program = true;
+  e->row_ok = build_row_program(d, &e->row_prog);
   e->states_valid = false; e->states_n = 0;
   mark_dirty(e);
   return SGR_OK;
@@ -265,6 +353,12 @@ static int32_t after_load(sgr_engine* e, const uint8_t* d_events, const uint64_t
   // variable records: the format caps a record at 16+512 bytes unless the caller raises
   // "max_record_bytes"; a longer record is flagged as a malformed event by the kernel, never mis-parsed
   e->max_record_bytes = e->program.record_kind == SGR_REC_VAR16 ? (uint32_t)e->opt_max_record_bytes : 64u;
+  e->offsets_aligned64 = false; e->log_begin = 0; e->log_end = nbytes;
+  if (e->program.record_kind == SGR_REC_FIXED64) {
+    cudaError_t ce = inspect_offsets(d_offsets, n_agg, (unsigned long long*)e->counters.p, e->stream, &e->offsets_aligned64,
+                                     &e->log_begin, &e->log_end);
+    if (ce != cudaSuccess) return fail(e, SGR_ERR_CUDA, "offset inspection: %s", cudaGetErrorString(ce));
+  }
   return SGR_OK;
 }
 
@@ -350,14 +444,15 @@ int32_t sgr_set_initial_states(sgr_engine* e, const void* states, uint64_t n_agg
   return SGR_OK;
 }
 
-int32_t sgr_fold(sgr_engine* e) {
+static int32_t fold_begin(sgr_engine* e) {
   if (!e) return SGR_ERR_INVALID;
   if (!e->has_program) return fail(e, SGR_ERR_NO_PROGRAM, "no fold program registered");
   if (!e->loaded) return fail(e, SGR_ERR_NOT_LOADED, "no event log loaded");
   int32_t rc = use_device(e); if (rc) return rc;
+  rc = finish_fold(e); if (rc) return rc;
   const bool prior = e->states_valid && e->states_n == e->n_agg;
   rc = ensure_states(e, e->n_agg); if (rc) return rc;
-  rc = run_fold(e, e->d_events, e->d_offsets, nullptr, e->n_agg, prior, e->d_offsets ? e->event_bytes : 0, true);
+  rc = enqueue_fold(e, e->d_events, e->d_offsets, nullptr, e->n_agg, prior, e->event_bytes, e->offsets_aligned64, e->log_begin, e->log_end);
   if (rc) return rc;
   e->states_valid = true;
   e->inc_prev_n = 0;
@@ -365,15 +460,29 @@ int32_t sgr_fold(sgr_engine* e) {
   return SGR_OK;
 }
 
+int32_t sgr_fold(sgr_engine* e) {
+  int32_t rc = fold_begin(e); if (rc) return rc;
+  return finish_fold(e);
+}
+
+int32_t sgr_fold_async(sgr_engine* e) { return fold_begin(e); }
+
+int32_t sgr_wait(sgr_engine* e) {
+  if (!e) return SGR_ERR_INVALID;
+  int32_t rc = use_device(e); if (rc) return rc;
+  return finish_fold(e);
+}
+
 static int32_t fold_incremental_impl(sgr_engine* e, const void* d_records, uint64_t n_records) {
   if (e->program.record_kind != SGR_REC_FIXED64) return fail(e, SGR_ERR_UNSUPPORTED, "incremental batches take fixed 64-byte records");
   if (!e->states_valid) return fail(e, SGR_ERR_NOT_LOADED, "incremental fold needs a live state table (fold or set_initial_states first)");
+  { int32_t rc0 = finish_fold(e); if (rc0) return rc0; }
   const uint64_t n_agg = e->states_n;
   CUDA_TRY(e, e->inc_offsets.reserve((n_records + 2) * 8));
   CUDA_TRY(e, e->inc_ids.reserve((n_records + 1) * 4));
   DevBuf& grouped = e->group.batch_records;
   CUDA_TRY(e, grouped.reserve(n_records * 64));
-  CUDA_TRY(e, cudaEventRecord(e->ev0, e->stream));
+  CUDA_TRY(e, cudaEventRecord(e->ev2, e->stream));
   // per-batch flags (CHANGED/ERROR) of the aggregates touched by the previous batch are cleared
   if (e->inc_prev_n) clear_batch_flags((uint8_t*)e->states.p, e->program.state_bytes, (const uint32_t*)e->inc_prev_ids.p, e->inc_prev_n, e->stream);
   else clear_batch_flags((uint8_t*)e->states.p, e->program.state_bytes, nullptr, n_agg, e->stream);
@@ -383,12 +492,13 @@ static int32_t fold_incremental_impl(sgr_engine* e, const void* d_records, uint6
                                        (uint64_t*)e->inc_offsets.p, (uint32_t*)e->inc_ids.p, &n_touched,
                                        (unsigned long long*)e->counters.p, e->stream, &bad);
   if (ce != cudaSuccess) return fail(e, SGR_ERR_CUDA, "group-by: %s", cudaGetErrorString(ce));
-  CUDA_TRY(e, cudaEventRecord(e->ev1, e->stream));
+  CUDA_TRY(e, cudaEventRecord(e->ev3, e->stream));
   if (bad) return fail(e, SGR_ERR_INVALID, "%llu records carry an aggregate index >= n_agg", bad);
-  int32_t rc = run_fold(e, (const uint8_t*)grouped.p, (const uint64_t*)e->inc_offsets.p, (const uint32_t*)e->inc_ids.p, n_touched, true,
-                        n_records * 64, true);
+  int32_t rc = enqueue_fold(e, (const uint8_t*)grouped.p, (const uint64_t*)e->inc_offsets.p, (const uint32_t*)e->inc_ids.p, n_touched, true,
+                            n_records * 64, true, 0, n_records * 64);
   if (rc) return rc;
-  CUDA_TRY(e, cudaEventElapsedTime(&e->stats.ms_group, e->ev0, e->ev1));
+  rc = finish_fold(e); if (rc) return rc;
+  CUDA_TRY(e, cudaEventElapsedTime(&e->stats.ms_group, e->ev2, e->ev3));
   // remember who was touched so the next batch can clear their per-batch flags
   std::swap(e->inc_ids, e->inc_prev_ids);
   e->inc_prev_n = n_touched;
@@ -461,6 +571,7 @@ int32_t sgr_export_states(sgr_engine* e, void* out, uint64_t cap, uint8_t* exist
   if (!e) return SGR_ERR_INVALID;
   if (!e->states_valid) return fail(e, SGR_ERR_STATE, "no folded state table to export");
   int32_t rc = use_device(e); if (rc) return rc;
+  rc = finish_fold(e); if (rc) return rc;
   const uint64_t n = e->states_n; const uint32_t sb = e->program.state_bytes;
   const uint64_t need = n * sb;
   std::vector<uint8_t> tmp;
@@ -507,6 +618,7 @@ int32_t sgr_events_device(sgr_engine* e, void** d_events, uint64_t* nbytes, uint
 
 int32_t sgr_get_stats(sgr_engine* e, sgr_stats* out) {
   if (!e || !out) return SGR_ERR_INVALID;
+  if (e->fold_pending) { int32_t rc = use_device(e); if (rc) return rc; rc = finish_fold(e); if (rc) return rc; }
   *out = e->stats;
   return SGR_OK;
 }
@@ -514,6 +626,7 @@ int32_t sgr_get_stats(sgr_engine* e, sgr_stats* out) {
 int32_t sgr_set_option(sgr_engine* e, const char* name, int64_t value) {
   if (!e || !name) return SGR_ERR_INVALID;
   if (!strcmp(name, "fold_variant")) { e->opt_variant = value; return SGR_OK; }
+  if (!strcmp(name, "kernel")) { e->opt_kernel = value; return SGR_OK; }
   if (!strcmp(name, "long_threshold")) { e->opt_long_threshold = value; return SGR_OK; }
   if (!strcmp(name, "max_record_bytes")) {
     if (value < 16 || value > 2048 + 16) return fail(e, SGR_ERR_INVALID, "max_record_bytes must be in [16, 2064]");

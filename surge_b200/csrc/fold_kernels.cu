@@ -93,19 +93,23 @@ fold_stream_kernel(const __grid_constant__ FoldArgs a, const __grid_constant__ D
   const uint64_t policy = l2_policy_evict_first();
   const uint32_t state_words = prog->state_words;
   const uint32_t n_types = prog->n_types;
-  const uint64_t n_seg = a.n_seg;
+  uint64_t n_seg = a.n_seg;
+  if (a.n_seg_dev) { const unsigned long long d = *a.n_seg_dev; n_seg = d < n_seg ? d : n_seg; }
   const uint64_t stride = (uint64_t)gridDim.x * THREADS;
   const uint64_t first = (uint64_t)blockIdx.x * THREADS + tid;
 
   // ---- producer cursor (the lane's TMA side)
   uint64_t p_seg = first, p_pos = 0, p_end = 0, nxt_b = 0, nxt_e = 0;
   bool p_has = p_seg < n_seg;
+  auto seg_of = [&](uint64_t i) -> uint64_t { return a.seg_list ? (uint64_t)a.seg_list[i] : i; };
   if (p_has) {
-    p_pos = a.seg_offsets[p_seg];
-    p_end = a.seg_offsets[p_seg + 1];
+    const uint64_t sg = seg_of(p_seg);
+    p_pos = a.seg_offsets[sg];
+    p_end = a.seg_offsets[sg + 1];
     if (p_seg + stride < n_seg) {
-      nxt_b = a.seg_offsets[p_seg + stride];
-      nxt_e = a.seg_offsets[p_seg + stride + 1];
+      const uint64_t sn = seg_of(p_seg + stride);
+      nxt_b = a.seg_offsets[sn];
+      nxt_e = a.seg_offsets[sn + 1];
     }
   }
   bool p_fresh = true;  // at the first chunk of a segment
@@ -139,8 +143,9 @@ fold_stream_kernel(const __grid_constant__ FoldArgs a, const __grid_constant__ D
         p_end = nxt_e;
         p_fresh = true;
         if (p_seg + stride < n_seg) {
-          nxt_b = a.seg_offsets[p_seg + stride];
-          nxt_e = a.seg_offsets[p_seg + stride + 1];
+          const uint64_t sn = seg_of(p_seg + stride);
+          nxt_b = a.seg_offsets[sn];
+          nxt_e = a.seg_offsets[sn + 1];
         }
       }
     } else {
@@ -213,7 +218,8 @@ fold_stream_kernel(const __grid_constant__ FoldArgs a, const __grid_constant__ D
   auto begin_segment = [&](int s) {
     rp = (uint32_t)s * CH; avail = 0; k = 0; err = 0; err_idx = 0; exists = 0; exists0 = 0;
     if (a.states_in) {
-      const uint64_t slot = a.seg_ids ? (uint64_t)a.seg_ids[c_seg] : c_seg;
+      const uint64_t sg = seg_of(c_seg);
+      const uint64_t slot = a.seg_ids ? (uint64_t)a.seg_ids[sg] : sg;
       const uint4* src = reinterpret_cast<const uint4*>(a.states_in + slot * (uint64_t)state_words * 4);
       for (uint32_t q = 0; q < state_words / 4; ++q) {
         const uint4 v = __ldg(src + q);
@@ -231,7 +237,8 @@ fold_stream_kernel(const __grid_constant__ FoldArgs a, const __grid_constant__ D
   };
 
   auto end_segment = [&]() {
-    const uint64_t slot = a.seg_ids ? (uint64_t)a.seg_ids[c_seg] : c_seg;
+    const uint64_t sg = seg_of(c_seg);
+    const uint64_t slot = a.seg_ids ? (uint64_t)a.seg_ids[sg] : sg;
     uint4* dst = reinterpret_cast<uint4*>(a.states_out + slot * (uint64_t)state_words * 4);
     uint32_t flags;
     const uint32_t* src = st;

@@ -11,7 +11,9 @@ struct FoldArgs {
   const uint8_t* events;         // event log base, 16-byte aligned
   const uint64_t* seg_offsets;   // n_seg+1 byte offsets (multiples of 16)
   const uint32_t* seg_ids;       // optional: state slot of segment i (incremental fold); null => slot i
+  const uint32_t* seg_list;      // optional: fold only these segments (n_seg of them), e.g. an exact-replay list
   uint64_t n_seg;
+  const unsigned long long* n_seg_dev;  // optional: min(*n_seg_dev, n_seg) segments (count produced on the device)
   const uint8_t* states_in;      // optional prior states, slot-indexed; null => all None
   uint8_t* states_out;           // slot-indexed; may alias states_in
   unsigned long long* counters;  // [0] events applied, [1] aggregates in error, [2] segments left to the split path

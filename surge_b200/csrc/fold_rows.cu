@@ -1,0 +1,489 @@
+// fold_rows.cu — K1/K3: record-parallel segmented fold of fixed 64-byte records (sm_100a).
+//
+// Same contract as fold_kernels.cu (events.foldLeft(state)(handleEvent) per aggregate,
+// modules/command-engine/scaladsl/src/main/scala/surge/scaladsl/command/CommandModels.scala:25-28),
+// different shape: instead of one lane walking one segment, every lane takes ONE record and
+// the left-to-right order is restored by composing *state transformers* with warp shuffles.
+//
+//   event  e  ->  T_e = per state word (KEEP | ADD v | SET v) + exists-op      (exact: i32 wrap add, bit copy)
+//   T_b . T_a  (a before b)   word: b SET ? b : (a.mode|b.mode, a.v + b.v)     associative, NOT commutative
+//   state' = (T_n . ... . T_1)(state)                                           == the sequential fold
+//
+// This is exact for every program whose rules are MATERIALISE / CREATE / TOMBSTONE / THROW with
+// SET / ADD_I32 / SUB_I32 ops (Counter, IntBalance, ...). Programs with IF_EXISTS rules or 64-bit
+// adds take the lane-sequential kernel in fold_kernels.cu.
+//
+// Data movement (HBM-bound, no tensor cores, no shared-memory staging):
+//   * the log is cut into byte-balanced spans, one per warp (skew-proof: a hot aggregate is
+//     spread over many warps); a warp walks its span in steps of 32 records = 4 rows of 512 B;
+//   * each row is ONE fully coalesced 128-bit-per-lane load (4 x 128-B lines per instruction);
+//     the next step's rows are in flight while the current step is folded;
+//   * lane i needs words of record i: a word of chunk c sits in lane 4*(i&7) + ((c - (i>>3)) & 3)
+//     because row r is loaded with the quad rotated by r — one shuffle per needed word, no
+//     bank conflicts, no smem;
+//   * segment heads come from the CSR offsets (coalesced 8-byte loads, one window per step);
+//     a 5-step segmented inclusive scan composes the transformers in log order; the lane that
+//     holds a segment's END offset fetches the scan value at the tail record, applies it to the
+//     prior state and writes the 16-byte state — consecutive segments => coalesced stores;
+//   * a segment that crosses a span boundary is finished by the warp that sees its end, after a
+//     decoupled look-back over the predecessors' published partial transformers.
+#include "fold_rows.cuh"
+
+#include <stdio.h>
+
+#include "../../include/sgr.h"
+
+namespace sgr {
+namespace {
+
+constexpr uint32_t M_ERR = 0x80000000u;   // some event in the range threw
+constexpr uint32_t EX_SOME = 1u, EX_NONE = 2u;
+
+template <int W>
+struct Xf {
+  uint32_t m;      // bits [2w+1:2w]: mode of word w (bit0 ADD, bit1 SET; OR-composable), bit31 error
+  uint32_t v[W];   // KEEP => 0
+};
+
+// later . earlier  (apply `a` first, then `b`)
+template <int W>
+__device__ __forceinline__ Xf<W> compose(const Xf<W>& a, const Xf<W>& b) {
+  Xf<W> r;
+  r.m = a.m | b.m;
+#pragma unroll
+  for (int w = 0; w < W; ++w) r.v[w] = (b.m & (2u << (2 * w))) ? b.v[w] : a.v[w] + b.v[w];
+  return r;
+}
+
+template <int W>
+__device__ __forceinline__ Xf<W> shfl_xf(const Xf<W>& t, int src) {
+  Xf<W> r;
+  r.m = __shfl_sync(0xffffffffu, t.m, src);
+#pragma unroll
+  for (int w = 0; w < W; ++w) r.v[w] = __shfl_sync(0xffffffffu, t.v[w], src);
+  return r;
+}
+
+__device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p));
+  return v;
+}
+__device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+
+__device__ __forceinline__ uint32_t pick(const uint4& a, int k) {
+  return k == 0 ? a.x : (k == 1 ? a.y : (k == 2 ? a.z : a.w));
+}
+
+template <int W>
+__global__ void __launch_bounds__(kRowThreads, 3) fold_rows_kernel(const __grid_constant__ RowArgs a, const __grid_constant__ RowProgram pg) {
+  __shared__ uint32_t tab[16 * 8];  // per type: [0] flags (bit0 valid, bit1 ex==NONE, bit2 all-SET), [1..W] word spec
+  for (int i = threadIdx.x; i < 16 * 8; i += kRowThreads) tab[i] = pg.tab[i];
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31;
+  const uint32_t lt = (1u << lane) - 1u;
+  const uint64_t gw = (uint64_t)blockIdx.x * (kRowThreads / 32) + (threadIdx.x >> 5);  // global warp id
+  const uint64_t n_warps = (uint64_t)gridDim.x * (kRowThreads / 32);
+  const uint64_t n_seg = a.n_seg;
+  const uint64_t base = a.log_begin, log_end = a.log_end;
+  const uint64_t total_steps = (log_end - base + 2047) / 2048;
+  const uint64_t spw = (total_steps + n_warps - 1) / n_warps;  // steps per warp
+  uint64_t step = gw * spw;
+  uint64_t step_end = step + spw < total_steps ? step + spw : total_steps;
+  const bool has_span = step < step_end;
+  const uint64_t wb = base + step * 2048;
+  const uint64_t we = has_span ? (base + step_end * 2048 < log_end ? base + step_end * 2048 : log_end) : wb;
+
+  uint32_t* part_flag = a.part_flags + gw;
+  uint32_t* part_data = a.part_data + gw * (W + 2);
+
+  // ---- first boundary of the span: kc = first k in [1, n_seg] with off[k] > wb (32-ary search);
+  //      warp 0 starts at k = 1 so that leading empty segments are written too.
+  uint64_t kc = 1;
+  if (has_span && gw != 0) {
+    uint64_t lo = 1, hi = n_seg + 1;  // answer in [lo, hi]; hi == n_seg+1 means "no such boundary"
+    while (lo < hi) {
+      const uint64_t chunk = (hi - lo + 31) / 32;
+      const uint64_t p = lo + (uint64_t)lane * chunk;  // probes lo, lo+chunk, ...
+      const bool valid = p < hi;
+      const bool gt = !valid || a.seg_offsets[p] > wb;  // monotone in lane
+      const uint32_t bal = __ballot_sync(0xffffffffu, gt);
+      if (bal == 0) { lo = lo + 31 * chunk + 1; continue; }
+      const int f = __ffs(bal) - 1;
+      if (f == 0) { hi = lo; break; }
+      const uint64_t pf = lo + (uint64_t)f * chunk;
+      lo = lo + (uint64_t)(f - 1) * chunk + 1;
+      hi = pf < hi ? pf : hi;
+    }
+    kc = lo;
+  }
+  // does the span start on a segment head?
+  bool head_pending = false;
+  if (has_span) head_pending = (gw == 0) ? true : (a.seg_offsets[kc - 1] == wb);
+  bool span_has_head = head_pending;
+
+  // pending finalisation of the inherited first segment (held by every lane, uniform)
+  bool inh_pending = false;
+  uint64_t inh_seg = 0;
+  Xf<W> inh_t; inh_t.m = 0;
+#pragma unroll
+  for (int w = 0; w < W; ++w) inh_t.v[w] = 0;
+  uint32_t inh_ex = 0;
+  uint64_t inh_len = 0;
+
+  Xf<W> carry; carry.m = 0;
+#pragma unroll
+  for (int w = 0; w < W; ++w) carry.v[w] = 0;
+  uint32_t carry_ex = 0;
+  unsigned long long n_applied = 0, n_redo = 0;
+
+  // ---- row loads: row r of a step is 512 B; lane l reads chunk ((l&3)+r)&3 of quad l>>2
+  const uint8_t* ev = a.events;
+  auto row_ptr = [&](uint64_t step_byte, int r) {
+    return reinterpret_cast<const uint4*>(ev + step_byte + (uint64_t)r * 512 + (uint64_t)(lane >> 2) * 64 + (uint64_t)(((lane & 3) + r) & 3) * 16);
+  };
+  uint4 cur[4], nxt[4];
+  auto load_step = [&](uint64_t s, uint4* dst) {
+    const uint64_t sb = base + s * 2048;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const uint64_t off = sb + (uint64_t)r * 512 + (uint64_t)(lane >> 2) * 64;
+      dst[r] = (off < log_end) ? ldg_stream(row_ptr(sb, r)) : make_uint4(0xffffffffu, 0, 0, 0);
+    }
+  };
+  if (has_span) load_step(step, nxt);
+
+  const int src_quad = (lane & 7) << 2;  // lane i fetches record i's chunk c from lane src_quad + ((c - (i>>3)) & 3)
+  const int my_row = lane >> 3;
+
+  for (; step < step_end; ++step) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) cur[r] = nxt[r];
+    if (step + 1 < step_end) load_step(step + 1, nxt);
+
+    const uint64_t sb = base + step * 2048;
+    const uint64_t se = sb + 2048 < we ? sb + 2048 : we;
+    const int nvalid = (int)((se - sb) >> 6);
+
+    // ---- fetch the needed words of record `lane` (natural order) ------------------------------
+    uint32_t sv[kMaxSlots];
+#pragma unroll
+    for (int s = 0; s < kMaxSlots; ++s) {
+      sv[s] = 0;
+      if (s < (int)pg.n_slots) {
+        const int c = pg.slot_word[s] >> 2, k = pg.slot_word[s] & 3;
+        const int rs = (c - (lane & 3)) & 3;  // the row in which THIS lane holds chunk c
+        const uint4 q = rs == 0 ? cur[0] : (rs == 1 ? cur[1] : (rs == 2 ? cur[2] : cur[3]));
+        sv[s] = __shfl_sync(0xffffffffu, pick(q, k), src_quad + ((c - my_row) & 3));
+      }
+    }
+    // slot 0 is always the event type (record word 0)
+    Xf<W> t; t.m = 0;
+#pragma unroll
+    for (int w = 0; w < W; ++w) t.v[w] = 0;
+    uint32_t ex = 0;
+    if (lane < nvalid) {
+      const uint32_t type = sv[0];
+      const uint32_t fl = type < 16u ? tab[type * 8] : 0u;
+      if (!(fl & 1u)) {
+        t.m = M_ERR;  // THROW rule or scala.MatchError: replayed exactly by the sequential kernel
+      } else {
+        ex = (fl & 2u) ? EX_NONE : EX_SOME;
+#pragma unroll
+        for (int w = 0; w < W; ++w) {
+          const uint32_t spec = tab[type * 8 + 1 + w];  // mode[1:0] | neg<<2 | slot<<3
+          const uint32_t mode = spec & 3u;
+          uint32_t val = 0;
+#pragma unroll
+          for (int s = 1; s < kMaxSlots; ++s) if ((int)(spec >> 3) == s) val = sv[s];
+          if (spec & 4u) val = 0u - val;
+          t.v[w] = mode ? val : 0u;
+          t.m |= mode << (2 * w);
+        }
+      }
+    }
+
+    // ---- segment heads inside this step, from the CSR offsets ---------------------------------
+    uint32_t heads = head_pending ? 1u : 0u;
+    head_pending = false;
+    {
+      uint64_t kb = kc;
+      while (true) {
+        const uint64_t k = kb + lane;
+        const uint64_t b = k <= n_seg ? a.seg_offsets[k] : ~0ull;
+        const bool in = b <= se;
+        uint32_t bit = 0;
+        if (in && b < se && b >= sb) bit = 1u << (int)((b - sb) >> 6);
+        heads |= __reduce_or_sync(0xffffffffu, bit);
+        if (__any_sync(0xffffffffu, in && b == se)) head_pending = true;
+        const int cnt = __popc(__ballot_sync(0xffffffffu, in));
+        kb += cnt;
+        if (cnt < 32) break;
+      }
+    }
+    if (heads) span_has_head = true;
+
+    // ---- carry-in, then segmented inclusive scan in record order ------------------------------
+    if (lane == 0 && !(heads & 1u)) t = compose(carry, t);
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const Xf<W> o = shfl_xf(t, lane - d);  // lane-d < 0 wraps; masked below
+      // combine iff no head in records (lane-d, lane]
+      const int sh = lane >= d ? lane - d + 1 : 0;
+      const uint32_t window = (heads >> sh) & ((1u << d) - 1u);
+      if (lane >= d && window == 0) t = compose(o, t);
+    }
+    // carry-out: the scan value of the last valid record, and its exists-op
+    const int last = nvalid - 1;
+    carry = shfl_xf(t, last);
+    {
+      const uint32_t e_last = __shfl_sync(0xffffffffu, ex, last);
+      // if the last record's event threw, ex is 0: keep the previous exists-op (the segment is redone anyway)
+      carry_ex = e_last ? e_last : carry_ex;
+    }
+
+    // ---- outputs: the lane holding boundary k finishes segment k-1 ----------------------------
+    {
+      uint64_t kb = kc;
+      while (true) {
+        const uint64_t k = kb + lane;
+        const uint64_t b = k <= n_seg ? a.seg_offsets[k] : ~0ull;
+        const bool in = b <= se;
+        uint64_t prev = __shfl_up_sync(0xffffffffu, b, 1);
+        if (lane == 0) prev = a.seg_offsets[kb - 1];
+        const bool empty = in && (b == prev);
+        const bool mine = in && !empty;          // a non-empty segment ends in this step
+        const int tpos = mine ? (int)((b - 64 - sb) >> 6) : 0;
+        const Xf<W> ts = shfl_xf(t, tpos);
+        const uint32_t tex = __shfl_sync(0xffffffffu, ex, tpos);
+        const bool inherited = mine && prev < wb;
+        if (__any_sync(0xffffffffu, inherited)) {
+          // the segment began in an earlier span: finish it after the look-back
+          const int src = __ffs(__ballot_sync(0xffffffffu, inherited)) - 1;
+          inh_t = shfl_xf(ts, src);
+          inh_ex = __shfl_sync(0xffffffffu, tex, src);
+          inh_seg = __shfl_sync(0xffffffffu, k, src) - 1;
+          inh_len = (__shfl_sync(0xffffffffu, b, src) - __shfl_sync(0xffffffffu, prev, src)) >> 6;
+          inh_pending = true;
+        }
+        if (in && !inherited) {
+          const uint64_t seg = k - 1;
+          const uint64_t slot = a.seg_ids ? (uint64_t)a.seg_ids[seg] : seg;
+          if (mine && (ts.m & M_ERR)) {
+            // handler threw somewhere in the segment: exact replay by the sequential kernel
+            const unsigned long long pos = atomicAdd(a.counters + 3, 1ull);
+            if (pos < a.redo_cap) a.redo_ids[pos] = (uint32_t)seg;
+            ++n_redo;
+          } else {
+            uint32_t old[W], ex0 = 0;
+#pragma unroll
+            for (int w = 0; w < W; ++w) old[w] = 0;
+            if (a.states_in) {
+              const uint4* sp = reinterpret_cast<const uint4*>(a.states_in + slot * (uint64_t)(W + 2) * 4);
+              // W+2 words per state; for W == 2 that is one uint4
+              uint32_t raw[W + 2];
+#pragma unroll
+              for (int q = 0; q < (W + 2) / 4; ++q) { const uint4 v4 = __ldg(sp + q); raw[4 * q] = v4.x; raw[4 * q + 1] = v4.y; raw[4 * q + 2] = v4.z; raw[4 * q + 3] = v4.w; }
+              ex0 = raw[W] & SGR_ST_EXISTS;
+#pragma unroll
+              for (int w = 0; w < W; ++w) old[w] = ex0 ? raw[w] : 0u;
+            }
+            uint32_t nw[W], exn = ex0;
+#pragma unroll
+            for (int w = 0; w < W; ++w) nw[w] = old[w];
+            if (mine) {
+              exn = (tex == EX_NONE) ? 0u : SGR_ST_EXISTS;
+#pragma unroll
+              for (int w = 0; w < W; ++w) {
+                const uint32_t mode = (ts.m >> (2 * w)) & 3u;
+                nw[w] = (mode & 2u) ? ts.v[w] : old[w] + ts.v[w];
+                if (!exn) nw[w] = 0u;
+              }
+              n_applied += (b - prev) >> 6;
+            }
+            uint32_t changed = exn != ex0;
+            if (exn && ex0) {
+#pragma unroll
+              for (int w = 0; w < W; ++w) changed |= (nw[w] != old[w]);
+            }
+            uint32_t outw[W + 2];
+#pragma unroll
+            for (int w = 0; w < W; ++w) outw[w] = nw[w];
+            outw[W] = exn | (changed ? SGR_ST_CHANGED : 0u);
+            outw[W + 1] = 0u;
+            uint4* dp = reinterpret_cast<uint4*>(a.states_out + slot * (uint64_t)(W + 2) * 4);
+#pragma unroll
+            for (int q = 0; q < (W + 2) / 4; ++q) dp[q] = make_uint4(outw[4 * q], outw[4 * q + 1], outw[4 * q + 2], outw[4 * q + 3]);
+          }
+        }
+        const int cnt = __popc(__ballot_sync(0xffffffffu, in));
+        kb += cnt;
+        if (cnt < 32) { kc = kb; break; }
+      }
+    }
+  }
+
+  // ---- publish this span's open transformer, then finish the inherited segment -----------------
+  if (has_span) {
+    if (lane == 0) {
+      part_data[0] = carry.m;
+#pragma unroll
+      for (int w = 0; w < W; ++w) part_data[1 + w] = carry.v[w];
+      part_data[W + 1] = carry_ex | (span_has_head ? 4u : 0u);
+      __threadfence();
+      asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(part_flag), "r"(a.epoch) : "memory");
+    }
+    if (inh_pending) {
+      // decoupled look-back: compose predecessors' open transformers until one that contains a head
+      Xf<W> acc = inh_t;
+      if (lane == 0) {
+        uint64_t p = gw;
+        while (p > 0) {
+          --p;
+          const uint32_t* pf = a.part_flags + p;
+          while (ld_volatile_u32(pf) != a.epoch) { __nanosleep(64); }
+          __threadfence();
+          const uint32_t* pd = a.part_data + p * (W + 2);
+          Xf<W> e;
+          e.m = ld_volatile_u32(pd);
+#pragma unroll
+          for (int w = 0; w < W; ++w) e.v[w] = ld_volatile_u32(pd + 1 + w);
+          const uint32_t tailw = ld_volatile_u32(pd + W + 1);
+          acc = compose(e, acc);
+          if (tailw & 4u) break;
+        }
+        const uint64_t seg = inh_seg;
+        const uint64_t slot = a.seg_ids ? (uint64_t)a.seg_ids[seg] : seg;
+        if (acc.m & M_ERR) {
+          const unsigned long long pos = atomicAdd(a.counters + 3, 1ull);
+          if (pos < a.redo_cap) a.redo_ids[pos] = (uint32_t)seg;
+          ++n_redo;
+        } else {
+          uint32_t old[W], ex0 = 0;
+#pragma unroll
+          for (int w = 0; w < W; ++w) old[w] = 0;
+          if (a.states_in) {
+            const uint32_t* sp = reinterpret_cast<const uint32_t*>(a.states_in + slot * (uint64_t)(W + 2) * 4);
+            ex0 = sp[W] & SGR_ST_EXISTS;
+#pragma unroll
+            for (int w = 0; w < W; ++w) old[w] = ex0 ? sp[w] : 0u;
+          }
+          const uint32_t exn = (inh_ex == EX_NONE) ? 0u : SGR_ST_EXISTS;
+          uint32_t nw[W];
+          uint32_t changed = exn != ex0;
+#pragma unroll
+          for (int w = 0; w < W; ++w) {
+            const uint32_t mode = (acc.m >> (2 * w)) & 3u;
+            nw[w] = exn ? ((mode & 2u) ? acc.v[w] : old[w] + acc.v[w]) : 0u;
+            if (exn && ex0) changed |= (nw[w] != old[w]);
+          }
+          uint32_t* dp = reinterpret_cast<uint32_t*>(a.states_out + slot * (uint64_t)(W + 2) * 4);
+#pragma unroll
+          for (int w = 0; w < W; ++w) dp[w] = nw[w];
+          dp[W] = exn | (changed ? SGR_ST_CHANGED : 0u);
+          dp[W + 1] = 0u;
+          n_applied += inh_len;
+        }
+      }
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) n_applied += __shfl_xor_sync(0xffffffffu, n_applied, o);
+  if (lane == 0 && n_applied) atomicAdd(a.counters + 0, n_applied);
+  (void)lt; (void)n_redo;
+}
+
+// misaligned[0] += segments whose offset is not log_begin (mod 64) or not monotone; bounds = off[0], off[n]
+__global__ void inspect_offsets_kernel(const uint64_t* __restrict__ off, uint64_t n_seg, unsigned long long* __restrict__ out) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > n_seg) return;
+  const uint64_t b0 = off[0], b = off[i];
+  if (i == 0) out[1] = b0;
+  if (i == n_seg) out[2] = b;
+  bool bad = ((b - b0) & 63ull) != 0 || b < b0;
+  if (i > 0 && off[i - 1] > b) bad = true;
+  if (bad) atomicAdd(out, 1ull);
+}
+
+}  // namespace
+
+cudaError_t inspect_offsets(const uint64_t* d_off, uint64_t n_seg, unsigned long long* d_scratch, cudaStream_t st,
+                            bool* aligned64, uint64_t* log_begin, uint64_t* log_end) {
+  cudaError_t e = cudaMemsetAsync(d_scratch, 0, 24, st);
+  if (e != cudaSuccess) return e;
+  inspect_offsets_kernel<<<(unsigned)((n_seg + 256) / 256), 256, 0, st>>>(d_off, n_seg, d_scratch);
+  unsigned long long h[3];
+  if ((e = cudaMemcpyAsync(h, d_scratch, 24, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
+  if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;
+  *aligned64 = h[0] == 0;
+  *log_begin = h[1];
+  *log_end = h[2];
+  return cudaSuccess;
+}
+
+namespace {
+}  // namespace
+
+bool build_row_program(const DevProgram& dp, RowProgram* out) {
+  memset(out, 0, sizeof *out);
+  if (dp.record_kind != SGR_REC_FIXED64) return false;
+  if (dp.user_words != 2) return false;  // instantiated widths (state_bytes 16)
+  if (dp.n_f64) return false;
+  out->user_words = dp.user_words;
+  out->n_slots = 1;
+  out->slot_word[0] = 0;  // the event type
+  for (uint32_t t = 0; t < dp.n_types; ++t) {
+    const DevRule& r = dp.rules[t];
+    uint32_t* e = out->tab + t * 8;
+    if (r.exists_rule == SGR_THROW) { e[0] = 0; continue; }
+    if (r.exists_rule == SGR_IF_EXISTS) return false;
+    uint32_t mode[6] = {0, 0, 0, 0, 0, 0}, slot[6] = {0, 0, 0, 0, 0, 0}, neg[6] = {0, 0, 0, 0, 0, 0};
+    const bool reset = r.exists_rule == SGR_CREATE || r.exists_rule == SGR_TOMBSTONE;
+    if (reset) for (uint32_t w = 0; w < dp.user_words; ++w) mode[w] = 2;  // SET 0
+    for (uint32_t i = 0; i < r.n_ops; ++i) {
+      const uint32_t op = r.ops[i];
+      const uint32_t opcode = op & 15u, nwords = (op >> 4) & 63u, dw = (op >> 10) & 63u, sw = op >> 16;
+      if (opcode > SGR_OP_SUB_I32) return false;
+      for (uint32_t j = 0; j < nwords; ++j) {
+        const uint32_t w = dw + j, src = sw + j;
+        if (w >= dp.user_words || src >= 16) return false;
+        // one source per state word per event: a word written twice by the same rule is not a single (mode, value)
+        if (mode[w] != 0 && !(reset && slot[w] == 0)) return false;
+        uint32_t s = 0;
+        for (uint32_t q = 1; q < out->n_slots; ++q) if (out->slot_word[q] == src) s = q;
+        if (!s) {
+          if (out->n_slots >= (uint32_t)kMaxSlots) return false;
+          s = out->n_slots++;
+          out->slot_word[s] = src;
+        }
+        slot[w] = s;
+        neg[w] = opcode == SGR_OP_SUB_I32;
+        // over a reset state ADD v == SET v and SUB v == SET -v
+        mode[w] = (opcode == SGR_OP_SET || reset) ? 2u : 1u;
+      }
+    }
+    e[0] = 1u | (r.exists_rule == SGR_TOMBSTONE ? 2u : 0u);
+    for (uint32_t w = 0; w < dp.user_words; ++w) e[1 + w] = mode[w] | (neg[w] << 2) | (slot[w] << 3);
+  }
+  return true;
+}
+
+int row_kernel_max_grid(int num_sms) {
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fold_rows_kernel<2>, kRowThreads, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+  return per_sm * num_sms;
+}
+
+cudaError_t launch_fold_rows(const RowArgs& args, const RowProgram& prog, int grid, cudaStream_t stream) {
+  if (prog.user_words != 2) return cudaErrorInvalidValue;
+  fold_rows_kernel<2><<<grid, kRowThreads, 0, stream>>>(args, prog);
+  return cudaGetLastError();
+}
+
+}  // namespace sgr

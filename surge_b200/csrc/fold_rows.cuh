@@ -1,0 +1,48 @@
+// fold_rows.cuh — launch interface of the record-parallel fold (K1/K3, fixed 64-byte records).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string.h>
+
+#include "sgr_device.cuh"
+
+namespace sgr {
+
+constexpr int kRowThreads = 256;
+constexpr int kMaxSlots = 6;  // distinct record words a program may read (slot 0 = event type)
+
+// Program in transformer form: per event type, how each state word is produced.
+struct RowProgram {
+  uint32_t user_words;
+  uint32_t n_slots;
+  uint32_t slot_word[kMaxSlots];  // record word index (0..15) of each slot
+  uint32_t tab[16 * 8];           // per type: [0] bit0 valid, bit1 result is None; [1+w] mode | neg<<2 | slot<<3
+};
+
+struct RowArgs {
+  const uint8_t* events;        // device log; records at log_begin + 64*i
+  const uint64_t* seg_offsets;  // n_seg+1 byte offsets, all == log_begin (mod 64)
+  const uint32_t* seg_ids;      // optional state slot per segment
+  uint64_t n_seg;
+  uint64_t log_begin, log_end;  // seg_offsets[0], seg_offsets[n_seg]
+  const uint8_t* states_in;     // optional prior states
+  uint8_t* states_out;
+  unsigned long long* counters; // [0] events applied, [3] segments queued for exact replay
+  uint32_t* redo_ids;           // segments whose handler threw (replayed by the sequential kernel)
+  uint64_t redo_cap;
+  uint32_t* part_flags;         // per warp: == epoch once its open transformer is published
+  uint32_t* part_data;          // per warp: m, v[W], ex | has_head<<2
+  uint32_t epoch;
+};
+
+// false if the program is outside the transformer algebra (IF_EXISTS rules, 64-bit adds, f64 fields,
+// unsupported state width): the caller then uses the lane-sequential kernel.
+bool build_row_program(const DevProgram& dp, RowProgram* out);
+// one pass over the CSR offsets at load time: are all segments 64-byte aligned relative to the first, and
+// where does the log begin/end (device offsets are opaque to the host otherwise)
+cudaError_t inspect_offsets(const uint64_t* d_off, uint64_t n_seg, unsigned long long* d_scratch, cudaStream_t st,
+                            bool* aligned64, uint64_t* log_begin, uint64_t* log_end);
+int row_kernel_max_grid(int num_sms);  // largest co-resident grid (look-back needs forward progress)
+cudaError_t launch_fold_rows(const RowArgs& args, const RowProgram& prog, int grid, cudaStream_t stream);
+
+}  // namespace sgr

@@ -104,6 +104,13 @@ class ReplayEngine:
     def fold(self) -> None:
         self._ck(self._lib.sgr_fold(self._h))
 
+    def fold_async(self) -> None:
+        """Enqueue the fold on the engine's stream without waiting (pair with wait())."""
+        self._ck(self._lib.sgr_fold_async(self._h))
+
+    def wait(self) -> None:
+        self._ck(self._lib.sgr_wait(self._h))
+
     def fold_incremental(self, records) -> None:
         if _is_cuda_tensor(records):
             r = records.contiguous().view(-1)

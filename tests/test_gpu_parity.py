@@ -1,0 +1,367 @@
+"""-m gpu: the CUDA path, called through the C ABI, against the oracle on the same seeded inputs.
+Bit-exact: whole state tables are compared byte for byte (integer / byte work, no tolerance).
+
+kernel=1 forces the lane-sequential TMA kernel (fold_kernels.cu), kernel=0 lets the engine pick
+(record-parallel fold_rows.cu for programs inside the transformer algebra).
+"""
+import uuid
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from oracle import surge_model as M
+from surge_b200 import ReplayEngine, SgrError
+from surge_b200 import formats as F
+from surge_b200 import native as N
+from surge_b200 import programs as P
+from surge_b200 import synth as S
+
+pytestmark = pytest.mark.gpu
+
+KERNELS = [0, 1]
+
+
+def run_engine(prog, events, offsets, kernel=0, init=None, variant=None):
+    with ReplayEngine(0) as e:
+        e.register_program(prog)
+        e.set_option("kernel", kernel)
+        if variant is not None:
+            e.set_option("fold_variant", variant)
+        if init is not None:
+            e.set_initial_states(init)
+        e.load_events(events, offsets)
+        e.fold()
+        st = e.stats()
+        return e.export_states(), st
+
+
+def assert_same(got, want, what=""):
+    if not np.array_equal(got, want):
+        bad = np.nonzero((got != want).any(axis=1))[0]
+        raise AssertionError(f"{what}: {len(bad)} of {len(want)} states differ; first {bad[:8]}\n"
+                             f"got  {got[bad[:4]].tolist()}\nwant {want[bad[:4]].tolist()}")
+
+
+# ------------------------------------------------------------------ Counter, fixed records
+@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("n_agg,max_events,seed", [(1, 1, 1), (7, 3, 2), (1000, 40, 3), (20000, 70, 4), (300, 600, 5)])
+def test_counter_ragged_segments(kernel, n_agg, max_events, seed):
+    rng = np.random.default_rng(seed)
+    counts = rng.integers(0, max_events + 1, size=n_agg)
+    rec, off = S.counter_csr(n_agg, counts, seed=seed, p_throw=0.003)
+    want, nev, nerr = O.fold_packed(O.MODEL_COUNTER, O.REC_FIXED64, rec, off)
+    got, st = run_engine(P.counter_program(), rec, off, kernel)
+    assert_same(got, want, f"kernel {kernel}")
+    assert (st.n_events, st.n_errors) == (nev, nerr)
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_counter_with_prior_states_and_publish_rule(kernel):
+    rng = np.random.default_rng(11)
+    n_agg = 5000
+    counts = rng.integers(0, 20, size=n_agg)
+    rec, off = S.counter_csr(n_agg, counts, seed=12, p_throw=0.01, by_max=3)  # small `by`: unchanged states do occur
+    init = np.zeros(n_agg, dtype=F.COUNTER_STATE)
+    ex = rng.random(n_agg) < 0.6
+    init["count"][ex] = rng.integers(-5, 5, size=ex.sum())
+    init["version"][ex] = rng.integers(0, 20, size=ex.sum())
+    init["flags"][ex] = N.ST_EXISTS
+    want, nev, nerr = O.fold_packed(O.MODEL_COUNTER, O.REC_FIXED64, rec, off, init)
+    got, st = run_engine(P.counter_program(), rec, off, kernel, init=init)
+    assert_same(got, want)
+    flags = want.view(F.COUNTER_STATE).reshape(-1)["flags"]
+    assert ((flags & N.ST_CHANGED) == 0).any() and (flags & N.ST_CHANGED).any() and (flags & N.ST_ERROR).any()
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_counter_one_long_segment_and_neighbours(kernel):
+    """A hot aggregate much longer than a warp span, between short ones (skew): exercises the
+    cross-span look-back of the record-parallel kernel and the chunk ring of the sequential one."""
+    counts = np.array([3, 0, 200_000, 1, 0, 0, 5, 40_000, 2])
+    rec, off = S.counter_csr(len(counts), counts, seed=21)
+    want, nev, _ = O.fold_packed(O.MODEL_COUNTER, O.REC_FIXED64, rec, off)
+    got, st = run_engine(P.counter_program(), rec, off, kernel)
+    assert_same(got, want)
+    assert st.n_events == nev
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_counter_long_segment_with_late_throw(kernel):
+    counts = np.array([10, 150_000, 10])
+    rec, off = S.counter_csr(3, counts, seed=22)
+    rec["type"][10 + 149_990] = F.EXCEPTION_THROWING_EVENT
+    want, nev, nerr = O.fold_packed(O.MODEL_COUNTER, O.REC_FIXED64, rec, off)
+    got, st = run_engine(P.counter_program(), rec, off, kernel)
+    assert_same(got, want)
+    assert nerr == 1 and st.n_errors == 1
+    row = got.view(F.COUNTER_STATE).reshape(-1)[1]
+    assert int(row["flags"]) == N.ST_ERROR and int(row["err_idx"]) == 149_990
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_counter_uniform_config2_shape_small(kernel):
+    """configs[1] shape at a size the oracle folds in a second: 16384 aggregates x 32 events."""
+    rec, off = S.counter_csr(16384, 32, seed=2)
+    want, _, _ = O.fold_packed(O.MODEL_COUNTER, O.REC_FIXED64, rec, off, threads=4)
+    got, _ = run_engine(P.counter_program(), rec, off, kernel)
+    assert_same(got, want)
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_log_not_starting_at_zero_and_all_empty(kernel):
+    rec, off = S.counter_csr(50, 4, seed=31)
+    # the CSR may address a sub-range of a larger buffer
+    pad = np.zeros(3, dtype=F.REC64)
+    buf = np.concatenate([pad, rec, pad])
+    off2 = off + np.uint64(3 * 64)
+    want, _, _ = O.fold_packed(O.MODEL_COUNTER, O.REC_FIXED64, buf, off2)
+    got, _ = run_engine(P.counter_program(), buf, off2, kernel)
+    assert_same(got, want)
+    # all segments empty: every state is None
+    offe = np.zeros(65, dtype=np.uint64)
+    got, st = run_engine(P.counter_program(), np.zeros(1, dtype=F.REC64), offe, kernel)
+    assert not got.any() and st.n_events == 0
+
+
+@pytest.mark.parametrize("variant", range(6))
+def test_sequential_kernel_variants(variant):
+    rng = np.random.default_rng(40 + variant)
+    counts = rng.integers(0, 50, size=3000)
+    rec, off = S.counter_csr(len(counts), counts, seed=41, p_throw=0.002)
+    want, _, _ = O.fold_packed(O.MODEL_COUNTER, O.REC_FIXED64, rec, off)
+    got, _ = run_engine(P.counter_program(), rec, off, kernel=1, variant=variant)
+    assert_same(got, want)
+
+
+# ------------------------------------------------------------------ golden vectors through the GPU path
+def _counter_row(count, version, flags):
+    r = np.zeros(1, dtype=F.COUNTER_STATE)
+    r["count"], r["version"], r["flags"] = count, version, flags
+    return r
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_reference_golden_vectors_on_gpu(kernel):
+    """SURVEY.md Appendix D vectors, each as one aggregate of one batch:
+    PersistentActorSpec.scala:134-168,275-288,431-464,466-529; MultilanguageGatewayServiceImplSpec.scala:72-136."""
+    base = (3, 3, N.ST_EXISTS)
+    cases = [  # (prior, [(type, seq, by)], expected (count, version, flags, err_idx))
+        (base, [(0, 4, 1)], (4, 4, N.ST_EXISTS | N.ST_CHANGED, 0)),
+        (base, [(0, 4, 1), (0, 5, 1)], (5, 5, N.ST_EXISTS | N.ST_CHANGED, 0)),
+        (base, [(0, 3, 0)], (3, 3, N.ST_EXISTS, 0)),                       # unchanged => no publish
+        (base, [(2, 4, 0)], (3, 3, N.ST_EXISTS, 0)),                       # NoOpEvent
+        (base, [(0, 4, 7), (3, 5, 0)], (3, 3, N.ST_EXISTS | N.ST_ERROR, 1)),  # handler throws => state kept
+        (None, [(0, 1, 1), (0, 2, 1), (1, 3, 1)], (1, 3, N.ST_EXISTS | N.ST_CHANGED, 0)),  # multilanguage counter
+        (None, [(2, 1, 0)], (0, 0, N.ST_EXISTS | N.ST_CHANGED, 0)),       # NoOp materialises State(id,0,0)
+        (None, [], (0, 0, 0, 0)),
+    ]
+    init = np.concatenate([_counter_row(*(c[0] or (0, 0, 0))) for c in cases])
+    recs = [F.counter_records([t for t, _, _ in ev], [s for _, s, _ in ev], [i] * len(ev), [b for _, _, b in ev]) for i, (_, ev, _) in enumerate(cases)]
+    rec = np.concatenate(recs)
+    off = F.csr_offsets_from_counts([len(c[1]) for c in cases])
+    got, _ = run_engine(P.counter_program(), rec, off, kernel, init=init)
+    rows = got.view(F.COUNTER_STATE).reshape(-1)
+    for i, (_, _, exp) in enumerate(cases):
+        assert (int(rows[i]["count"]), int(rows[i]["version"]), int(rows[i]["flags"]), int(rows[i]["err_idx"])) == exp, i
+    want, _, _ = O.fold_packed(O.MODEL_COUNTER, O.REC_FIXED64, rec, off, init)
+    assert_same(got, want)
+
+
+# ------------------------------------------------------------------ other models
+def test_bank_account_model():
+    """BankAccount (f64 copy, strings, IF_EXISTS rule): BankAccountCommandEngineSpec.scala:43-68 + random logs."""
+    rng = np.random.default_rng(5)
+    n_agg = 2000
+    blobs, counts = [], []
+    for a in range(n_agg):
+        acct = str(uuid.UUID(int=int(rng.integers(1, 2**62))))
+        k = int(rng.integers(0, 12))
+        evs = []
+        for j in range(k):
+            if rng.random() < 0.25:
+                evs.append(F.bank_created_record(a, j + 1, acct, f"owner{a % 97}", f"{a % 10000:04d}", 1000.0 + 0.25 * j))
+            else:
+                bal = [float(j), -0.0, 0.0, float("nan"), 1e300][int(rng.integers(0, 5))]
+                evs.append(F.bank_updated_record(a, j + 1, acct, bal))
+        if a == 0:
+            n0 = str(uuid.UUID(int=0x1234))
+            evs = [F.bank_created_record(0, 1, n0, "Jane Doe", "1234", 1000.0), F.bank_updated_record(0, 2, n0, 1100.0)]
+        blobs.append(b"".join(evs))
+        counts.append(len(evs))
+    rec = np.frombuffer(b"".join(blobs), dtype=np.uint8)
+    off = F.csr_offsets_from_counts(counts)
+    want, _, _ = O.fold_packed(O.MODEL_BANK_ACCOUNT, O.REC_FIXED64, rec, off)
+    got, _ = run_engine(P.bank_account_program(), rec, off)
+    assert_same(got, want)
+    assert F.decode_bank_state(got.view(F.BANK_STATE).reshape(-1)[0]) == {
+        "accountNumber": str(uuid.UUID(int=0x1234)), "accountOwner": "Jane Doe", "securityCode": "1234", "balance": 1100.0}
+    # second batch on top: the publish rule with JVM Double equality (0.0 == -0.0, NaN != NaN)
+    rec2, cnt2 = [], []
+    for a in range(n_agg):
+        acct = str(uuid.UUID(int=a + 1))
+        bal = [0.0, -0.0, float("nan"), 5.0][a % 4]
+        rec2.append(F.bank_updated_record(a, 100, acct, bal))
+        cnt2.append(1)
+    rec2 = np.frombuffer(b"".join(rec2), dtype=np.uint8)
+    off2 = F.csr_offsets_from_counts(cnt2)
+    want2, _, _ = O.fold_packed(O.MODEL_BANK_ACCOUNT, O.REC_FIXED64, rec2, off2, want)
+    got2, _ = run_engine(P.bank_account_program(), rec2, off2, init=got)
+    assert_same(got2, want2)
+    want3, _, _ = O.fold_packed(O.MODEL_BANK_ACCOUNT, O.REC_FIXED64, rec2, off2, want2)
+    got3, _ = run_engine(P.bank_account_program(), rec2, off2, init=got2)
+    assert_same(got3, want3)
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_int_balance_and_ml_counter(kernel):
+    rng = np.random.default_rng(6)
+    counts = rng.integers(0, 30, size=4000)
+    rec, off = S.counter_csr(len(counts), counts, seed=61)
+    rec_ib = rec.copy()
+    rec_ib["type"] = np.where(rng.random(len(rec)) < 0.002, 1, 0)  # type 1 is a MatchError for IntBalance
+    want, _, _ = O.fold_packed(O.MODEL_INT_BALANCE, O.REC_FIXED64, rec_ib, off)
+    got, _ = run_engine(P.int_balance_program(), rec_ib, off, kernel)
+    assert_same(got, want)
+    want, _, nerr = O.fold_packed(O.MODEL_ML_COUNTER, O.REC_FIXED64, rec, off)  # NoOp (type 2) is a MatchError here
+    got, st = run_engine(P.ml_counter_program(), rec, off, kernel)
+    assert_same(got, want)
+    assert nerr > 0 and st.n_errors == nerr
+
+
+# ------------------------------------------------------------------ variable records (config 4 shape)
+def test_counter_variable_records():
+    rng = np.random.default_rng(7)
+    counts = rng.integers(0, 25, size=3000)
+    buf, seg = S.counter_var_csr(len(counts), counts, seed=71)
+    want, nev, nerr = O.fold_packed(O.MODEL_COUNTER, O.REC_VAR16, buf, seg)
+    got, st = run_engine(P.counter_program(N.REC_VAR16), buf, seg)
+    assert_same(got, want)
+    assert (st.n_events, st.n_errors) == (nev, nerr)
+
+
+def test_variable_records_malformed():
+    """Too-short payload for the event class, a record running past its segment, and an over-long record."""
+    segs = []
+    t, s, a, p = [0, 0], [1, 2], [0, 0], [b"\x05\0\0\0" + bytes(28), b"\x01\0"]       # second record: payload < 4 bytes
+    segs.append(F.pack_var_records(t, s, a, p)[0])
+    b1 = F.pack_var_records([0], [1], [1], [b"\x07\0\0\0" + bytes(60)])[0].copy()
+    b1[8:12] = np.frombuffer(np.uint32(4000).tobytes(), np.uint8)                       # claims more than the segment holds
+    segs.append(b1)
+    segs.append(F.pack_var_records([1, 2], [1, 2], [2, 2], [b"\x03\0\0\0" + bytes(44), bytes(32)])[0])  # fine
+    buf = np.concatenate(segs)
+    seg = np.zeros(4, dtype=np.uint64)
+    np.cumsum([len(x) for x in segs], out=seg[1:])
+    want, _, nerr = O.fold_packed(O.MODEL_COUNTER, O.REC_VAR16, buf, seg)
+    got, st = run_engine(P.counter_program(N.REC_VAR16), buf, seg)
+    assert_same(got, want)
+    assert nerr == 2 == st.n_errors
+
+
+# ------------------------------------------------------------------ K5 group-by and K6 incremental
+@pytest.mark.parametrize("n_agg,max_events,seed", [(10, 5, 1), (5000, 30, 2), (70000, 6, 3)])
+def test_unsorted_load_groups_stably(n_agg, max_events, seed):
+    rng = np.random.default_rng(seed)
+    counts = rng.integers(0, max_events + 1, size=n_agg)
+    rec, off = S.counter_csr(n_agg, counts, seed=seed + 100)
+    arrival = S.interleave_arrival(rec, seed=seed + 200)
+    grouped, goff = O.group_by_agg(arrival, n_agg)
+    assert np.array_equal(grouped.reshape(-1), rec.view(np.uint8).reshape(-1)) and np.array_equal(goff, off)  # oracle group-by == CSR
+    want, _, _ = O.fold_packed(O.MODEL_COUNTER, O.REC_FIXED64, rec, off)
+    with ReplayEngine(0) as e:
+        e.register_program(P.counter_program())
+        e.load_unsorted(arrival, n_agg)
+        e.fold()
+        assert_same(e.export_states(), want)
+        assert e.stats().n_events == len(rec)
+
+
+def test_unsorted_load_rejects_out_of_range_aggregate():
+    rec, _ = S.counter_csr(10, 3, seed=1)
+    rec["agg"][5] = 99
+    with ReplayEngine(0) as e:
+        e.register_program(P.counter_program())
+        with pytest.raises(SgrError) as ei:
+            e.load_unsorted(rec, 10)
+        assert ei.value.code == N.SGR_ERR_INVALID
+
+
+def test_incremental_micro_batches():
+    """configs[4] shape, small: batches appended to live aggregates; each batch == one ApplyEvents per touched aggregate."""
+    n_agg = 20000
+    rec, off = S.counter_csr(n_agg, 3, seed=81)
+    want, _, _ = O.fold_packed(O.MODEL_COUNTER, O.REC_FIXED64, rec, off)
+    rng = np.random.default_rng(82)
+    with ReplayEngine(0) as e:
+        e.register_program(P.counter_program())
+        e.load_events(rec, off)
+        e.fold()
+        for b in range(6):
+            n = [1000, 1, 5000, 0, 300, 20000][b]
+            aggs = rng.integers(0, n_agg, size=n).astype(np.uint64)
+            types = rng.choice([0, 1, 2, 3], size=n, p=[0.45, 0.44, 0.1, 0.01]).astype(np.uint32)
+            batch = F.counter_records(types, np.arange(n, dtype=np.uint32) + 1000 * b, aggs, rng.integers(0, 3, size=n).astype(np.int32))
+            want = O.fold_incremental(O.MODEL_COUNTER, batch, want)
+            e.fold_incremental(batch)
+            assert_same(e.export_states(), want, f"batch {b}")
+
+
+# ------------------------------------------------------------------ recovery read (getAggregateBytes)
+def test_get_aggregate_bytes_by_key():
+    n_agg = 500
+    rec, off = S.counter_csr(n_agg, 5, seed=91)
+    rec["type"][0:5] = F.EXCEPTION_THROWING_EVENT  # aggregate 0 stays None (and in error)
+    keys = [f"agg-{i:05d}" for i in range(n_agg)]
+    want, _, _ = O.fold_packed(O.MODEL_COUNTER, O.REC_FIXED64, rec, off)
+    with ReplayEngine(0) as e:
+        e.register_program(P.counter_program())
+        e.load_keys(keys)
+        with pytest.raises(N.InvalidStateStoreException):
+            e.get(keys[3])  # nothing folded yet: the store is not readable
+        e.load_events(rec, off)
+        e.fold()
+        assert e.get(keys[0]) is None
+        assert e.get("no-such-aggregate") is None
+        for i in [1, 2, 250, 499]:
+            assert e.get(keys[i]) == bytes(want[i][:8])
+        b, flags, err = e.get_index(0)
+        assert b is None and flags == N.ST_ERROR and err == 0
+
+
+# ------------------------------------------------------------------ full config-2 size: size-independent properties
+def test_config2_full_size_properties():
+    """1,048,576 aggregates x 32 x 64-byte events (configs[1]). The oracle would take minutes in Python-driven
+    pieces, so: (1) the whole table against a vectorised torch restatement of the Counter algebra
+    (count = sum of +-by mod 2^32, version = last non-NoOp seq); (2) a random sample of aggregates against the oracle;
+    (3) idempotence: folding the same log again from None gives identical bytes; both kernels agree."""
+    import torch
+
+    n_agg, epa = 1 << 20, 32
+    rec, off = S.counter_csr_device(n_agg, epa, seed=2)
+    r = rec.view(n_agg, epa, 16)
+    t, by = r[:, :, 0], r[:, :, 4].to(torch.int64)
+    cnt = torch.where(t == 0, by, torch.where(t == 1, -by, torch.zeros_like(by))).sum(1)
+    cnt = ((cnt + (1 << 31)) % (1 << 32) - (1 << 31)).to(torch.int32)
+    ver = torch.where(t != 2, r[:, :, 1], torch.zeros_like(t)).max(1).values
+    tables = []
+    for kernel in KERNELS:
+        with ReplayEngine(0) as e:
+            e.register_program(P.counter_program())
+            e.set_option("kernel", kernel)
+            e.load_events(rec.view(torch.uint8), off)
+            e.fold()
+            st = e.states_tensor().view(torch.int32).view(n_agg, 4)
+            assert bool((st[:, 0] == cnt).all()) and bool((st[:, 1] == ver).all())
+            assert bool((st[:, 2] == (N.ST_EXISTS | N.ST_CHANGED)).all()) and bool((st[:, 3] == 0).all())
+            assert e.stats().n_events == n_agg * epa
+            first = e.export_states()
+            e.set_initial_states(None)
+            e.fold()
+            assert np.array_equal(first, e.export_states())
+            tables.append(first)
+    assert np.array_equal(tables[0], tables[1])
+    sample = np.random.default_rng(3).choice(n_agg, size=4096, replace=False)
+    sample.sort()
+    host = rec.view(n_agg, epa * 16)[torch.as_tensor(sample, device=rec.device)].cpu().numpy().view(np.uint8).reshape(-1)
+    want, _, _ = O.fold_packed(O.MODEL_COUNTER, O.REC_FIXED64, host, F.csr_offsets_from_counts([epa] * len(sample)))
+    assert np.array_equal(tables[0][sample], want)
