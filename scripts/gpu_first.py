@@ -11,7 +11,7 @@ def big(n_agg, epa, kernels):
     balg = nbytes + 8 * (n_agg + 1) + 16 * n_agg
     for kernel, variant in kernels:
         e = ReplayEngine(0); e.register_program(P.counter_program()); e.set_option("kernel", kernel)
-        if variant is not None: e.set_option("fold_variant", variant)
+        if variant is not None: e.set_option("fold_variant" if kernel == 1 else "run_variant", variant)
         e.load_events(rec.view(torch.uint8), off)
         for _ in range(3):
             e.set_initial_states(None); e.fold()
@@ -31,5 +31,6 @@ def big(n_agg, epa, kernels):
 
 if __name__ == "__main__":
     print(torch.cuda.get_device_name(0), flush=True)
-    big(1 << 20, 32, [(0, None), (1, 1)])
-    big(10_000_000 // 8, 100, [(0, None), (1, 1)])
+    ks = [(2, v) for v in range(6)] + [(3, None), (1, 1)]
+    big(1 << 20, 32, ks)
+    big(10_000_000 // 8, 100, ks)

@@ -64,8 +64,11 @@ struct sgr_engine {
   bool row_ok = false;            // program is inside the transformer algebra
   RowProgram row_prog{};
   int row_max_grid = 0;
+  int run_max_grid = 0, run_max_grid_variant = -1;
+  int64_t opt_run_variant = 0;
   DevBuf part_flags, part_data, redo_ids;
   uint32_t epoch = 0;
+  size_t part_flags_cap_seen = 0;
   bool offsets_aligned64 = false; // every segment offset == log_begin (mod 64)
   uint64_t log_begin = 0, log_end = 0;
   bool fold_pending = false;      // a fold was enqueued and not yet finished
@@ -74,7 +77,8 @@ struct sgr_engine {
   const uint8_t* pending_events = nullptr; const uint64_t* pending_offsets = nullptr; const uint32_t* pending_ids = nullptr;
   cudaEvent_t ev2 = nullptr, ev3 = nullptr;
 
-  int64_t opt_kernel = 0;         // 0 auto, 1 force lane-sequential (fold_kernels.cu), 2 force rows
+  int64_t opt_kernel = 0;         // 0 auto (runs if the program allows), 1 lane-sequential TMA kernel (fold_kernels.cu),
+                                  // 2 force runs (fold_runs.cu), 3 record-per-lane rows (fold_rows.cu)
   int64_t opt_variant = -1;
   int64_t opt_long_threshold = 0;
   int64_t opt_max_record_bytes = 528;
@@ -194,7 +198,7 @@ int32_t enqueue_fold(sgr_engine* e, const uint8_t* d_events, const uint64_t* d_o
   CUDA_TRY(e, cudaMemsetAsync(e->counters.p, 0, 64, e->stream));
   const uint8_t* states_in = use_prior ? (const uint8_t*)e->states.p : nullptr;
   bool use_rows = e->row_ok && aligned64 && e->opt_kernel != 1 && n_seg < (1ull << 32);
-  if (e->opt_kernel == 2 && !use_rows) return fail(e, SGR_ERR_UNSUPPORTED, "record-parallel kernel cannot take this program/log");
+  if ((e->opt_kernel == 2 || e->opt_kernel == 3) && !use_rows) return fail(e, SGR_ERR_UNSUPPORTED, "record-parallel kernel cannot take this program/log");
   CUDA_TRY(e, cudaEventRecord(e->ev0, e->stream));
   uint32_t launches = 0;
   if (n_seg) {
@@ -205,12 +209,21 @@ int32_t enqueue_fold(sgr_engine* e, const uint8_t* d_events, const uint64_t* d_o
     a.long_threshold = (uint64_t)e->opt_long_threshold;
     FoldLaunchInfo info{};
     if (use_rows) {
-      if (!e->row_max_grid) e->row_max_grid = row_kernel_max_grid(e->num_sms);
-      const uint64_t n_warps_max = (uint64_t)e->row_max_grid * (kRowThreads / 32);
+      const bool v1 = e->opt_kernel == 3;
+      const int rv = (int)e->opt_run_variant;
+      if (v1 && !e->row_max_grid) e->row_max_grid = row_kernel_max_grid(e->num_sms, e->row_prog);
+      if (!v1 && e->run_max_grid_variant != rv) { e->run_max_grid = run_kernel_max_grid(e->num_sms, rv); e->run_max_grid_variant = rv; }
+      const int max_grid = v1 ? e->row_max_grid : e->run_max_grid;
+      const int wpc = v1 ? kRowThreads / 32 : run_warps_per_cta();
+      const uint64_t step_bytes = v1 ? 2048 : (uint64_t)run_variant_step_bytes(rv);
+      const uint64_t n_warps_max = (uint64_t)max_grid * wpc;
       CUDA_TRY(e, e->part_flags.reserve(n_warps_max * 4 + 256));
       CUDA_TRY(e, e->part_data.reserve(n_warps_max * (e->row_prog.user_words + 2) * 4 + 256));
       CUDA_TRY(e, e->redo_ids.reserve(kRedoCap * 4));
-      if (e->epoch == 0) CUDA_TRY(e, cudaMemsetAsync(e->part_flags.p, 0, e->part_flags.cap, e->stream));
+      if (e->epoch == 0 || e->part_flags_cap_seen != e->part_flags.cap) {
+        CUDA_TRY(e, cudaMemsetAsync(e->part_flags.p, 0, e->part_flags.cap, e->stream));
+        e->part_flags_cap_seen = e->part_flags.cap;
+      }
       ++e->epoch;
       if (e->epoch == 0) { CUDA_TRY(e, cudaMemsetAsync(e->part_flags.p, 0, e->part_flags.cap, e->stream)); e->epoch = 1; }
       RowArgs r{};
@@ -220,12 +233,12 @@ int32_t enqueue_fold(sgr_engine* e, const uint8_t* d_events, const uint64_t* d_o
       r.counters = (unsigned long long*)e->counters.p;
       r.redo_ids = (uint32_t*)e->redo_ids.p; r.redo_cap = kRedoCap;
       r.part_flags = (uint32_t*)e->part_flags.p; r.part_data = (uint32_t*)e->part_data.p; r.epoch = e->epoch;
-      const uint64_t steps = (log_end - log_begin + 2047) / 2048;
-      uint64_t want = (steps + (kRowThreads / 32) - 1) / (kRowThreads / 32);
+      const uint64_t steps = (log_end - log_begin + step_bytes - 1) / step_bytes;
+      uint64_t want = (steps + wpc - 1) / wpc;
       if (want == 0) want = 1;  // all segments empty: one CTA still writes every (None) state
-      const int grid = (int)(want < (uint64_t)e->row_max_grid ? want : (uint64_t)e->row_max_grid);
-      cudaError_t le = launch_fold_rows(r, e->row_prog, grid, e->stream);
-      if (le != cudaSuccess) return fail(e, SGR_ERR_CUDA, "fold_rows launch: %s", cudaGetErrorString(le));
+      const int grid = (int)(want < (uint64_t)max_grid ? want : (uint64_t)max_grid);
+      cudaError_t le = v1 ? launch_fold_rows(r, e->row_prog, grid, e->stream) : launch_fold_runs(r, e->row_prog, rv, grid, e->stream);
+      if (le != cudaSuccess) return fail(e, SGR_ERR_CUDA, "fold launch: %s", cudaGetErrorString(le));
       // exact replay of the segments whose handler threw (count lives on the device)
       a.seg_list = (const uint32_t*)e->redo_ids.p;
       a.n_seg = kRedoCap;
@@ -343,6 +356,7 @@ int32_t sgr_register_program(sgr_engine* e, const sgr_fold_program* prog) {
   if (rc) return rc;
   e->program = *prog; e->dprog = d; e->has_program = true;
   e->row_ok = build_row_program(d, &e->row_prog);
+  e->row_max_grid = 0;
   e->states_valid = false; e->states_n = 0;
   mark_dirty(e);
   return SGR_OK;
@@ -627,6 +641,10 @@ int32_t sgr_set_option(sgr_engine* e, const char* name, int64_t value) {
   if (!e || !name) return SGR_ERR_INVALID;
   if (!strcmp(name, "fold_variant")) { e->opt_variant = value; return SGR_OK; }
   if (!strcmp(name, "kernel")) { e->opt_kernel = value; return SGR_OK; }
+  if (!strcmp(name, "run_variant")) {
+    if (value < 0 || value >= run_variant_count()) return fail(e, SGR_ERR_INVALID, "run_variant out of range");
+    e->opt_run_variant = value; return SGR_OK;
+  }
   if (!strcmp(name, "long_threshold")) { e->opt_long_threshold = value; return SGR_OK; }
   if (!strcmp(name, "max_record_bytes")) {
     if (value < 16 || value > 2048 + 16) return fail(e, SGR_ERR_INVALID, "max_record_bytes must be in [16, 2064]");

@@ -77,32 +77,74 @@ __device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) {
   return v;
 }
 
-__device__ __forceinline__ uint32_t pick(const uint4& a, int k) {
-  return k == 0 ? a.x : (k == 1 ? a.y : (k == 2 ? a.z : a.w));
+
+// select one of four registers by a 2-bit lane-dependent index (3 SEL)
+__device__ __forceinline__ uint32_t sel4(uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, int i) {
+  const uint32_t lo = (i & 1) ? a1 : a0, hi = (i & 1) ? a3 : a2;
+  return (i & 2) ? hi : lo;
 }
 
+// Finish one segment: apply the composed transformer to the prior state and write the state struct.
 template <int W>
+__device__ __forceinline__ void finish_segment(const RowArgs& a, uint64_t seg, bool nonempty, const Xf<W>& ts, uint32_t tex) {
+  const uint64_t slot = a.seg_ids ? (uint64_t)a.seg_ids[seg] : seg;
+  uint32_t old[W], ex0 = 0;
+#pragma unroll
+  for (int w = 0; w < W; ++w) old[w] = 0;
+  if (a.states_in) {
+    const uint4* sp = reinterpret_cast<const uint4*>(a.states_in + slot * (uint64_t)(W + 2) * 4);
+    uint32_t raw[W + 2];
+#pragma unroll
+    for (int q = 0; q < (W + 2) / 4; ++q) { const uint4 v4 = __ldg(sp + q); raw[4 * q] = v4.x; raw[4 * q + 1] = v4.y; raw[4 * q + 2] = v4.z; raw[4 * q + 3] = v4.w; }
+    ex0 = raw[W] & SGR_ST_EXISTS;
+#pragma unroll
+    for (int w = 0; w < W; ++w) old[w] = ex0 ? raw[w] : 0u;
+  }
+  uint32_t nw[W], exn = ex0;
+#pragma unroll
+  for (int w = 0; w < W; ++w) nw[w] = old[w];
+  if (nonempty) {
+    exn = (tex == EX_NONE) ? 0u : SGR_ST_EXISTS;
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+      nw[w] = (ts.m & (2u << (2 * w))) ? ts.v[w] : old[w] + ts.v[w];
+      if (!exn) nw[w] = 0u;
+    }
+  }
+  uint32_t changed = exn != ex0;
+  if (exn && ex0) {
+#pragma unroll
+    for (int w = 0; w < W; ++w) changed |= (nw[w] != old[w]);
+  }
+  uint32_t outw[W + 2];
+#pragma unroll
+  for (int w = 0; w < W; ++w) outw[w] = nw[w];
+  outw[W] = exn | (changed ? SGR_ST_CHANGED : 0u);
+  outw[W + 1] = 0u;
+  uint4* dp = reinterpret_cast<uint4*>(a.states_out + slot * (uint64_t)(W + 2) * 4);
+#pragma unroll
+  for (int q = 0; q < (W + 2) / 4; ++q) dp[q] = make_uint4(outw[4 * q], outw[4 * q + 1], outw[4 * q + 2], outw[4 * q + 3]);
+}
+
+template <int W, int NS>
 __global__ void __launch_bounds__(kRowThreads, 3) fold_rows_kernel(const __grid_constant__ RowArgs a, const __grid_constant__ RowProgram pg) {
-  __shared__ uint32_t tab[16 * 8];  // per type: [0] flags (bit0 valid, bit1 ex==NONE, bit2 all-SET), [1..W] word spec
+  // per type, one uint4-aligned entry: [0] flags (bit0 valid, bit1 result is None), [1+w] mode | neg<<2 | slot<<3
+  __shared__ __align__(16) uint32_t tab[16 * 8];
   for (int i = threadIdx.x; i < 16 * 8; i += kRowThreads) tab[i] = pg.tab[i];
   __syncthreads();
 
   const int lane = threadIdx.x & 31;
-  const uint32_t lt = (1u << lane) - 1u;
   const uint64_t gw = (uint64_t)blockIdx.x * (kRowThreads / 32) + (threadIdx.x >> 5);  // global warp id
   const uint64_t n_warps = (uint64_t)gridDim.x * (kRowThreads / 32);
   const uint64_t n_seg = a.n_seg;
-  const uint64_t base = a.log_begin, log_end = a.log_end;
-  const uint64_t total_steps = (log_end - base + 2047) / 2048;
+  const uint64_t base = a.log_begin;
+  const uint64_t total_bytes = a.log_end - base;
+  const uint64_t total_steps = (total_bytes + 2047) / 2048;
   const uint64_t spw = (total_steps + n_warps - 1) / n_warps;  // steps per warp
   uint64_t step = gw * spw;
-  uint64_t step_end = step + spw < total_steps ? step + spw : total_steps;
+  const uint64_t step_end = step + spw < total_steps ? step + spw : total_steps;
   const bool has_span = step < step_end;
   const uint64_t wb = base + step * 2048;
-  const uint64_t we = has_span ? (base + step_end * 2048 < log_end ? base + step_end * 2048 : log_end) : wb;
-
-  uint32_t* part_flag = a.part_flags + gw;
-  uint32_t* part_data = a.part_data + gw * (W + 2);
 
   // ---- first boundary of the span: kc = first k in [1, n_seg] with off[k] > wb (32-ary search);
   //      warp 0 starts at k = 1 so that leading empty segments are written too.
@@ -124,44 +166,45 @@ __global__ void __launch_bounds__(kRowThreads, 3) fold_rows_kernel(const __grid_
     }
     kc = lo;
   }
-  // does the span start on a segment head?
-  bool head_pending = false;
-  if (has_span) head_pending = (gw == 0) ? true : (a.seg_offsets[kc - 1] == wb);
+  // offset of the last boundary already consumed (== start of the segment open at the span start)
+  uint64_t prev_last = has_span ? a.seg_offsets[kc - 1] : 0;
+  bool head_pending = has_span && (gw == 0 || prev_last == wb);  // the span starts on a segment head
   bool span_has_head = head_pending;
 
-  // pending finalisation of the inherited first segment (held by every lane, uniform)
+  // pending finalisation of the inherited first segment (uniform across the warp)
   bool inh_pending = false;
-  uint64_t inh_seg = 0;
+  uint64_t inh_seg = 0, inh_len = 0;
   Xf<W> inh_t; inh_t.m = 0;
-#pragma unroll
-  for (int w = 0; w < W; ++w) inh_t.v[w] = 0;
   uint32_t inh_ex = 0;
-  uint64_t inh_len = 0;
-
   Xf<W> carry; carry.m = 0;
 #pragma unroll
-  for (int w = 0; w < W; ++w) carry.v[w] = 0;
+  for (int w = 0; w < W; ++w) { inh_t.v[w] = 0; carry.v[w] = 0; }
   uint32_t carry_ex = 0;
-  unsigned long long n_applied = 0, n_redo = 0;
+  unsigned long long n_applied = 0;
 
   // ---- row loads: row r of a step is 512 B; lane l reads chunk ((l&3)+r)&3 of quad l>>2
-  const uint8_t* ev = a.events;
-  auto row_ptr = [&](uint64_t step_byte, int r) {
-    return reinterpret_cast<const uint4*>(ev + step_byte + (uint64_t)r * 512 + (uint64_t)(lane >> 2) * 64 + (uint64_t)(((lane & 3) + r) & 3) * 16);
-  };
+  uint32_t ro[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) ro[r] = (uint32_t)r * 512u + (uint32_t)(((lane & 3) + r) & 3) * 16u;
+  const uint32_t quad_off = (uint32_t)(lane >> 2) * 64u;
+  const uint8_t* lane_base = a.events + base + quad_off;
   uint4 cur[4], nxt[4];
   auto load_step = [&](uint64_t s, uint4* dst) {
-    const uint64_t sb = base + s * 2048;
+    const uint8_t* p = lane_base + s * 2048;
+    if ((s + 1) * 2048 <= total_bytes) {  // uniform: whole step inside the log
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      const uint64_t off = sb + (uint64_t)r * 512 + (uint64_t)(lane >> 2) * 64;
-      dst[r] = (off < log_end) ? ldg_stream(row_ptr(sb, r)) : make_uint4(0xffffffffu, 0, 0, 0);
+      for (int r = 0; r < 4; ++r) dst[r] = ldg_stream(reinterpret_cast<const uint4*>(p + ro[r]));
+    } else {
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+        dst[r] = (s * 2048 + (uint64_t)r * 512 + quad_off < total_bytes) ? ldg_stream(reinterpret_cast<const uint4*>(p + ro[r]))
+                                                                        : make_uint4(0xffffffffu, 0, 0, 0);
     }
   };
   if (has_span) load_step(step, nxt);
 
-  const int src_quad = (lane & 7) << 2;  // lane i fetches record i's chunk c from lane src_quad + ((c - (i>>3)) & 3)
-  const int my_row = lane >> 3;
+  // lane i fetches chunk c of record i from lane 4*(i&7) + ((c - (i>>3)) & 3); that lane holds chunk c in row (c - (l&3)) & 3
+  const int src_quad = (lane & 7) << 2, my_row = lane >> 3, lane3 = lane & 3;
 
   for (; step < step_end; ++step) {
 #pragma unroll
@@ -169,234 +212,184 @@ __global__ void __launch_bounds__(kRowThreads, 3) fold_rows_kernel(const __grid_
     if (step + 1 < step_end) load_step(step + 1, nxt);
 
     const uint64_t sb = base + step * 2048;
-    const uint64_t se = sb + 2048 < we ? sb + 2048 : we;
-    const int nvalid = (int)((se - sb) >> 6);
+    const uint64_t rem = a.log_end - sb;
+    const uint32_t span = rem < 2048 ? (uint32_t)rem : 2048u;  // bytes of this step
+    const int nvalid = (int)(span >> 6);
 
-    // ---- fetch the needed words of record `lane` (natural order) ------------------------------
-    uint32_t sv[kMaxSlots];
+    // ---- the needed words of record `lane`, in record order ---------------------------------------
+    uint32_t sv[NS];
 #pragma unroll
-    for (int s = 0; s < kMaxSlots; ++s) {
-      sv[s] = 0;
-      if (s < (int)pg.n_slots) {
-        const int c = pg.slot_word[s] >> 2, k = pg.slot_word[s] & 3;
-        const int rs = (c - (lane & 3)) & 3;  // the row in which THIS lane holds chunk c
-        const uint4 q = rs == 0 ? cur[0] : (rs == 1 ? cur[1] : (rs == 2 ? cur[2] : cur[3]));
-        sv[s] = __shfl_sync(0xffffffffu, pick(q, k), src_quad + ((c - my_row) & 3));
+    for (int s = 0; s < NS; ++s) {
+      const int c = (int)(pg.slot_word[s] >> 2), k = (int)(pg.slot_word[s] & 3);  // warp-uniform
+      const int rs = (c - lane3) & 3;
+      uint32_t x;
+      switch (k) {  // uniform branch
+        case 0: x = sel4(cur[0].x, cur[1].x, cur[2].x, cur[3].x, rs); break;
+        case 1: x = sel4(cur[0].y, cur[1].y, cur[2].y, cur[3].y, rs); break;
+        case 2: x = sel4(cur[0].z, cur[1].z, cur[2].z, cur[3].z, rs); break;
+        default: x = sel4(cur[0].w, cur[1].w, cur[2].w, cur[3].w, rs); break;
       }
+      sv[s] = __shfl_sync(0xffffffffu, x, src_quad + ((c - my_row) & 3));
     }
-    // slot 0 is always the event type (record word 0)
+    // ---- event -> transformer (slot 0 is the event type) --------------------------------------------
     Xf<W> t; t.m = 0;
 #pragma unroll
     for (int w = 0; w < W; ++w) t.v[w] = 0;
     uint32_t ex = 0;
     if (lane < nvalid) {
       const uint32_t type = sv[0];
-      const uint32_t fl = type < 16u ? tab[type * 8] : 0u;
-      if (!(fl & 1u)) {
+      uint4 e0 = make_uint4(0, 0, 0, 0);
+      if (type < 16u) e0 = *reinterpret_cast<const uint4*>(tab + type * 8);
+      if (!(e0.x & 1u)) {
         t.m = M_ERR;  // THROW rule or scala.MatchError: replayed exactly by the sequential kernel
       } else {
-        ex = (fl & 2u) ? EX_NONE : EX_SOME;
+        ex = (e0.x & 2u) ? EX_NONE : EX_SOME;
+        uint32_t spec[W];
+        spec[0] = e0.y;
+        if (W > 1) spec[1] = e0.z;
+        if (W > 2) spec[2] = e0.w;
+#pragma unroll
+        for (int w = 3; w < W; ++w) spec[w] = tab[type * 8 + 1 + w];
 #pragma unroll
         for (int w = 0; w < W; ++w) {
-          const uint32_t spec = tab[type * 8 + 1 + w];  // mode[1:0] | neg<<2 | slot<<3
-          const uint32_t mode = spec & 3u;
           uint32_t val = 0;
 #pragma unroll
-          for (int s = 1; s < kMaxSlots; ++s) if ((int)(spec >> 3) == s) val = sv[s];
-          if (spec & 4u) val = 0u - val;
+          for (int s = 1; s < NS; ++s) val = ((int)(spec[w] >> 3) == s) ? sv[s] : val;
+          if (spec[w] & 4u) val = 0u - val;
+          const uint32_t mode = spec[w] & 3u;
           t.v[w] = mode ? val : 0u;
           t.m |= mode << (2 * w);
         }
       }
     }
 
-    // ---- segment heads inside this step, from the CSR offsets ---------------------------------
+    // ---- segment boundaries inside (sb, sb+span], from the CSR offsets -------------------------------
+    // lane j of a window holds boundary k = kb+j: segment k-1 ends there and segment k begins.
     uint32_t heads = head_pending ? 1u : 0u;
     head_pending = false;
-    {
-      uint64_t kb = kc;
-      while (true) {
-        const uint64_t k = kb + lane;
-        const uint64_t b = k <= n_seg ? a.seg_offsets[k] : ~0ull;
-        const bool in = b <= se;
-        uint32_t bit = 0;
-        if (in && b < se && b >= sb) bit = 1u << (int)((b - sb) >> 6);
-        heads |= __reduce_or_sync(0xffffffffu, bit);
-        if (__any_sync(0xffffffffu, in && b == se)) head_pending = true;
-        const int cnt = __popc(__ballot_sync(0xffffffffu, in));
-        kb += cnt;
-        if (cnt < 32) break;
-      }
+    uint64_t kb = kc;
+    uint32_t rel0 = 0xffffffffu;  // window 0, kept for the output pass
+    int cnt0 = 0;
+    while (true) {
+      const uint64_t k = kb + lane;
+      const uint64_t b = k <= n_seg ? a.seg_offsets[k] : ~0ull;
+      const uint64_t d = b - sb;                        // > 0 for every unconsumed boundary
+      const uint32_t rel = d <= (uint64_t)span ? (uint32_t)d : 0xffffffffu;
+      const bool in = rel != 0xffffffffu;
+      heads |= __reduce_or_sync(0xffffffffu, (in && rel < span) ? (1u << (rel >> 6)) : 0u);
+      if (__any_sync(0xffffffffu, in && rel == span)) head_pending = true;
+      const int cnt = __popc(__ballot_sync(0xffffffffu, in));
+      if (kb == kc) { rel0 = rel; cnt0 = cnt; }
+      kb += cnt;
+      if (cnt < 32) break;
     }
     if (heads) span_has_head = true;
 
-    // ---- carry-in, then segmented inclusive scan in record order ------------------------------
+    // ---- carry-in, then segmented inclusive scan in record order -------------------------------------
     if (lane == 0 && !(heads & 1u)) t = compose(carry, t);
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const Xf<W> o = shfl_xf(t, lane - d);  // lane-d < 0 wraps; masked below
-      // combine iff no head in records (lane-d, lane]
-      const int sh = lane >= d ? lane - d + 1 : 0;
-      const uint32_t window = (heads >> sh) & ((1u << d) - 1u);
-      if (lane >= d && window == 0) t = compose(o, t);
+    for (int dd = 1; dd < 32; dd <<= 1) {
+      const Xf<W> o = shfl_xf(t, lane - dd);  // wraps for lane < dd; masked below
+      const int sh = lane >= dd ? lane - dd + 1 : 0;
+      const uint32_t window = (heads >> sh) & ((1u << dd) - 1u);  // a head in records (lane-dd, lane]?
+      if (lane >= dd && window == 0) t = compose(o, t);
     }
-    // carry-out: the scan value of the last valid record, and its exists-op
-    const int last = nvalid - 1;
-    carry = shfl_xf(t, last);
+    carry = shfl_xf(t, nvalid - 1);
     {
-      const uint32_t e_last = __shfl_sync(0xffffffffu, ex, last);
-      // if the last record's event threw, ex is 0: keep the previous exists-op (the segment is redone anyway)
-      carry_ex = e_last ? e_last : carry_ex;
+      const uint32_t e_last = __shfl_sync(0xffffffffu, ex, nvalid - 1);
+      carry_ex = e_last ? e_last : carry_ex;  // a throwing tail keeps the previous exists-op (segment is replayed anyway)
     }
 
-    // ---- outputs: the lane holding boundary k finishes segment k-1 ----------------------------
-    {
-      uint64_t kb = kc;
+    // ---- outputs: the lane holding boundary k finishes segment k-1 -----------------------------------
+    if (cnt0 | (int)(kb != kc)) {
+      uint64_t kw = kc;
+      uint32_t rel = rel0;
+      int cnt = cnt0;
       while (true) {
-        const uint64_t k = kb + lane;
-        const uint64_t b = k <= n_seg ? a.seg_offsets[k] : ~0ull;
-        const bool in = b <= se;
-        uint64_t prev = __shfl_up_sync(0xffffffffu, b, 1);
-        if (lane == 0) prev = a.seg_offsets[kb - 1];
-        const bool empty = in && (b == prev);
-        const bool mine = in && !empty;          // a non-empty segment ends in this step
-        const int tpos = mine ? (int)((b - 64 - sb) >> 6) : 0;
+        if (kw != kc) {
+          const uint64_t k = kw + lane;
+          const uint64_t b = k <= n_seg ? a.seg_offsets[k] : ~0ull;
+          const uint64_t d = b - sb;
+          rel = d <= (uint64_t)span ? (uint32_t)d : 0xffffffffu;
+          cnt = __popc(__ballot_sync(0xffffffffu, rel != 0xffffffffu));
+        }
+        const bool in = rel != 0xffffffffu;
+        // start of segment k-1, relative to sb (negative => before this step)
+        uint32_t relp = __shfl_up_sync(0xffffffffu, rel, 1);
+        const int64_t prev_rel0 = (int64_t)(prev_last - sb);
+        const bool prev_before = (lane == 0) && prev_rel0 < 0;
+        if (lane == 0) relp = prev_before ? 0u : (uint32_t)prev_rel0;
+        const bool empty = in && !prev_before && relp == rel;
+        const bool mine = in && !empty;
+        const int tpos = mine ? (int)((rel - 64u) >> 6) : 0;
         const Xf<W> ts = shfl_xf(t, tpos);
         const uint32_t tex = __shfl_sync(0xffffffffu, ex, tpos);
-        const bool inherited = mine && prev < wb;
-        if (__any_sync(0xffffffffu, inherited)) {
-          // the segment began in an earlier span: finish it after the look-back
-          const int src = __ffs(__ballot_sync(0xffffffffu, inherited)) - 1;
-          inh_t = shfl_xf(ts, src);
-          inh_ex = __shfl_sync(0xffffffffu, tex, src);
-          inh_seg = __shfl_sync(0xffffffffu, k, src) - 1;
-          inh_len = (__shfl_sync(0xffffffffu, b, src) - __shfl_sync(0xffffffffu, prev, src)) >> 6;
+        const bool inherited = mine && prev_before && prev_last < wb;
+        if (__any_sync(0xffffffffu, inherited)) {  // only lane 0 of the first window of a span can be
+          inh_t = shfl_xf(ts, 0);
+          inh_ex = __shfl_sync(0xffffffffu, tex, 0);
+          inh_seg = kw - 1;
+          inh_len = (sb + (uint64_t)__shfl_sync(0xffffffffu, rel, 0) - prev_last) >> 6;
           inh_pending = true;
         }
         if (in && !inherited) {
-          const uint64_t seg = k - 1;
-          const uint64_t slot = a.seg_ids ? (uint64_t)a.seg_ids[seg] : seg;
+          const uint64_t seg = kw + lane - 1;
           if (mine && (ts.m & M_ERR)) {
-            // handler threw somewhere in the segment: exact replay by the sequential kernel
-            const unsigned long long pos = atomicAdd(a.counters + 3, 1ull);
+            const unsigned long long pos = atomicAdd(a.counters + 3, 1ull);  // exact replay by the sequential kernel
             if (pos < a.redo_cap) a.redo_ids[pos] = (uint32_t)seg;
-            ++n_redo;
           } else {
-            uint32_t old[W], ex0 = 0;
-#pragma unroll
-            for (int w = 0; w < W; ++w) old[w] = 0;
-            if (a.states_in) {
-              const uint4* sp = reinterpret_cast<const uint4*>(a.states_in + slot * (uint64_t)(W + 2) * 4);
-              // W+2 words per state; for W == 2 that is one uint4
-              uint32_t raw[W + 2];
-#pragma unroll
-              for (int q = 0; q < (W + 2) / 4; ++q) { const uint4 v4 = __ldg(sp + q); raw[4 * q] = v4.x; raw[4 * q + 1] = v4.y; raw[4 * q + 2] = v4.z; raw[4 * q + 3] = v4.w; }
-              ex0 = raw[W] & SGR_ST_EXISTS;
-#pragma unroll
-              for (int w = 0; w < W; ++w) old[w] = ex0 ? raw[w] : 0u;
-            }
-            uint32_t nw[W], exn = ex0;
-#pragma unroll
-            for (int w = 0; w < W; ++w) nw[w] = old[w];
-            if (mine) {
-              exn = (tex == EX_NONE) ? 0u : SGR_ST_EXISTS;
-#pragma unroll
-              for (int w = 0; w < W; ++w) {
-                const uint32_t mode = (ts.m >> (2 * w)) & 3u;
-                nw[w] = (mode & 2u) ? ts.v[w] : old[w] + ts.v[w];
-                if (!exn) nw[w] = 0u;
-              }
-              n_applied += (b - prev) >> 6;
-            }
-            uint32_t changed = exn != ex0;
-            if (exn && ex0) {
-#pragma unroll
-              for (int w = 0; w < W; ++w) changed |= (nw[w] != old[w]);
-            }
-            uint32_t outw[W + 2];
-#pragma unroll
-            for (int w = 0; w < W; ++w) outw[w] = nw[w];
-            outw[W] = exn | (changed ? SGR_ST_CHANGED : 0u);
-            outw[W + 1] = 0u;
-            uint4* dp = reinterpret_cast<uint4*>(a.states_out + slot * (uint64_t)(W + 2) * 4);
-#pragma unroll
-            for (int q = 0; q < (W + 2) / 4; ++q) dp[q] = make_uint4(outw[4 * q], outw[4 * q + 1], outw[4 * q + 2], outw[4 * q + 3]);
+            finish_segment<W>(a, seg, mine, ts, tex);
+            if (mine) n_applied += prev_before ? ((sb + rel - prev_last) >> 6) : (uint64_t)((rel - relp) >> 6);
           }
         }
-        const int cnt = __popc(__ballot_sync(0xffffffffu, in));
-        kb += cnt;
-        if (cnt < 32) { kc = kb; break; }
+        if (cnt) prev_last = sb + (uint64_t)__shfl_sync(0xffffffffu, rel, cnt - 1);
+        kw += cnt;
+        if (cnt < 32) break;
       }
+      kc = kb;
     }
   }
 
   // ---- publish this span's open transformer, then finish the inherited segment -----------------
   if (has_span) {
+    uint32_t* part_data = a.part_data + gw * (W + 2);
     if (lane == 0) {
       part_data[0] = carry.m;
 #pragma unroll
       for (int w = 0; w < W; ++w) part_data[1 + w] = carry.v[w];
       part_data[W + 1] = carry_ex | (span_has_head ? 4u : 0u);
       __threadfence();
-      asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(part_flag), "r"(a.epoch) : "memory");
+      asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(a.part_flags + gw), "r"(a.epoch) : "memory");
     }
-    if (inh_pending) {
+    if (inh_pending && lane == 0) {
       // decoupled look-back: compose predecessors' open transformers until one that contains a head
       Xf<W> acc = inh_t;
-      if (lane == 0) {
-        uint64_t p = gw;
-        while (p > 0) {
-          --p;
-          const uint32_t* pf = a.part_flags + p;
-          while (ld_volatile_u32(pf) != a.epoch) { __nanosleep(64); }
-          __threadfence();
-          const uint32_t* pd = a.part_data + p * (W + 2);
-          Xf<W> e;
-          e.m = ld_volatile_u32(pd);
+      uint64_t p = gw;
+      while (p > 0) {
+        --p;
+        const uint32_t* pf = a.part_flags + p;
+        while (ld_volatile_u32(pf) != a.epoch) { __nanosleep(64); }
+        __threadfence();
+        const uint32_t* pd = a.part_data + p * (W + 2);
+        Xf<W> e;
+        e.m = ld_volatile_u32(pd);
 #pragma unroll
-          for (int w = 0; w < W; ++w) e.v[w] = ld_volatile_u32(pd + 1 + w);
-          const uint32_t tailw = ld_volatile_u32(pd + W + 1);
-          acc = compose(e, acc);
-          if (tailw & 4u) break;
-        }
-        const uint64_t seg = inh_seg;
-        const uint64_t slot = a.seg_ids ? (uint64_t)a.seg_ids[seg] : seg;
-        if (acc.m & M_ERR) {
-          const unsigned long long pos = atomicAdd(a.counters + 3, 1ull);
-          if (pos < a.redo_cap) a.redo_ids[pos] = (uint32_t)seg;
-          ++n_redo;
-        } else {
-          uint32_t old[W], ex0 = 0;
-#pragma unroll
-          for (int w = 0; w < W; ++w) old[w] = 0;
-          if (a.states_in) {
-            const uint32_t* sp = reinterpret_cast<const uint32_t*>(a.states_in + slot * (uint64_t)(W + 2) * 4);
-            ex0 = sp[W] & SGR_ST_EXISTS;
-#pragma unroll
-            for (int w = 0; w < W; ++w) old[w] = ex0 ? sp[w] : 0u;
-          }
-          const uint32_t exn = (inh_ex == EX_NONE) ? 0u : SGR_ST_EXISTS;
-          uint32_t nw[W];
-          uint32_t changed = exn != ex0;
-#pragma unroll
-          for (int w = 0; w < W; ++w) {
-            const uint32_t mode = (acc.m >> (2 * w)) & 3u;
-            nw[w] = exn ? ((mode & 2u) ? acc.v[w] : old[w] + acc.v[w]) : 0u;
-            if (exn && ex0) changed |= (nw[w] != old[w]);
-          }
-          uint32_t* dp = reinterpret_cast<uint32_t*>(a.states_out + slot * (uint64_t)(W + 2) * 4);
-#pragma unroll
-          for (int w = 0; w < W; ++w) dp[w] = nw[w];
-          dp[W] = exn | (changed ? SGR_ST_CHANGED : 0u);
-          dp[W + 1] = 0u;
-          n_applied += inh_len;
-        }
+        for (int w = 0; w < W; ++w) e.v[w] = ld_volatile_u32(pd + 1 + w);
+        const uint32_t tailw = ld_volatile_u32(pd + W + 1);
+        acc = compose(e, acc);
+        if (tailw & 4u) break;
+      }
+      if (acc.m & M_ERR) {
+        const unsigned long long pos = atomicAdd(a.counters + 3, 1ull);
+        if (pos < a.redo_cap) a.redo_ids[pos] = (uint32_t)inh_seg;
+      } else {
+        finish_segment<W>(a, inh_seg, true, acc, inh_ex);
+        n_applied += inh_len;
       }
     }
   }
   for (int o = 16; o > 0; o >>= 1) n_applied += __shfl_xor_sync(0xffffffffu, n_applied, o);
   if (lane == 0 && n_applied) atomicAdd(a.counters + 0, n_applied);
-  (void)lt; (void)n_redo;
 }
 
 // misaligned[0] += segments whose offset is not log_begin (mod 64) or not monotone; bounds = off[0], off[n]
@@ -474,15 +467,28 @@ bool build_row_program(const DevProgram& dp, RowProgram* out) {
   return true;
 }
 
-int row_kernel_max_grid(int num_sms) {
+namespace {
+typedef void (*RowKernel)(const RowArgs, const RowProgram);
+RowKernel pick_kernel(const RowProgram& prog) {
+  if (prog.user_words != 2) return nullptr;
+  if (prog.n_slots <= 2) return fold_rows_kernel<2, 2>;
+  if (prog.n_slots <= 3) return fold_rows_kernel<2, 3>;
+  if (prog.n_slots <= 4) return fold_rows_kernel<2, 4>;
+  return fold_rows_kernel<2, kMaxSlots>;
+}
+}  // namespace
+
+int row_kernel_max_grid(int num_sms, const RowProgram& prog) {
   int per_sm = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fold_rows_kernel<2>, kRowThreads, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+  RowKernel k = pick_kernel(prog);
+  if (!k || cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kRowThreads, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
   return per_sm * num_sms;
 }
 
 cudaError_t launch_fold_rows(const RowArgs& args, const RowProgram& prog, int grid, cudaStream_t stream) {
-  if (prog.user_words != 2) return cudaErrorInvalidValue;
-  fold_rows_kernel<2><<<grid, kRowThreads, 0, stream>>>(args, prog);
+  RowKernel k = pick_kernel(prog);
+  if (!k) return cudaErrorInvalidValue;
+  k<<<grid, kRowThreads, 0, stream>>>(args, prog);
   return cudaGetLastError();
 }
 

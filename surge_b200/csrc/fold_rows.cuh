@@ -42,7 +42,16 @@ bool build_row_program(const DevProgram& dp, RowProgram* out);
 // where does the log begin/end (device offsets are opaque to the host otherwise)
 cudaError_t inspect_offsets(const uint64_t* d_off, uint64_t n_seg, unsigned long long* d_scratch, cudaStream_t st,
                             bool* aligned64, uint64_t* log_begin, uint64_t* log_end);
-int row_kernel_max_grid(int num_sms);  // largest co-resident grid (look-back needs forward progress)
+int row_kernel_max_grid(int num_sms, const RowProgram& prog);  // largest co-resident grid (look-back needs forward progress)
 cudaError_t launch_fold_rows(const RowArgs& args, const RowProgram& prog, int grid, cudaStream_t stream);
+
+
+// ---- fold_runs.cu: lane-run variant (primary). Same RowArgs / RowProgram.
+int run_variant_count();
+const char* run_variant_name(int v);
+int run_kernel_max_grid(int num_sms, int variant);
+int run_variant_step_bytes(int variant);
+int run_warps_per_cta();
+cudaError_t launch_fold_runs(const RowArgs& args, const RowProgram& prog, int variant, int grid, cudaStream_t stream);
 
 }  // namespace sgr

@@ -1,0 +1,488 @@
+// fold_runs.cu — K1/K3 (primary): segmented fold of fixed 64-byte records, lane-runs + warp scan (sm_100a).
+//
+// Contract: for every aggregate, events.foldLeft(state)(handleEvent)
+// (modules/command-engine/scaladsl/src/main/scala/surge/scaladsl/command/CommandModels.scala:25-28) with the
+// actor's publish rule (modules/command-engine/core/src/main/scala/surge/internal/persistence/
+// PersistentActor.scala:252-257). Exactness comes from the transformer algebra of fold_rows.cuh:
+// an event is a per-word (KEEP | ADD v | SET v) map, composition is associative, so any
+// bracketing of the log-ordered product equals the sequential fold bit for bit.
+//
+// Shape (HBM-bound byte parse + segmented scan; no tensor cores):
+//   * the log is cut into byte-balanced spans, one per warp — a hot aggregate (Zipf skew) is
+//     spread over many warps instead of serialising one lane;
+//   * a warp walks its span in steps of 32*R records. The step's 2048*R bytes are staged into
+//     shared memory with coalesced 16-byte cp.async copies (512 contiguous bytes per warp
+//     instruction), NSTAGE steps deep, no register staging;
+//   * the staging layout XOR-swizzles each record's 16-byte chunks with (record/R)&7, so that
+//     lane i reading its run of R consecutive records [R*i, R*i+R) is bank-conflict free;
+//   * lane i folds its R records left to right into a running transformer (the only per-record
+//     work: 1 table read + the needed record words); segments that start and end inside the
+//     run are finished on the spot;
+//   * once per step the 32 lane-transformers are combined by a 5-step segmented warp-shuffle
+//     scan in log order; the lane holding the first segment head of its run finishes the segment
+//     that flows into it; the scan's tail is the carry into the next step;
+//   * segment heads come from the CSR offsets: a window of 32 boundaries is read with coalesced
+//     8-byte loads and scattered into a per-step head bitmap + segment-id table in smem;
+//   * a segment that crosses a span boundary is finished by the warp that sees its end, after a
+//     decoupled look-back over the predecessors' published open transformers.
+#include <stdio.h>
+
+#include "../../include/sgr.h"
+#include "fold_rows.cuh"
+
+namespace sgr {
+namespace {
+
+constexpr uint32_t M_ERR = 0x80000000u;  // some event in the range threw
+constexpr uint32_t EX_SOME = 1u, EX_NONE = 2u;
+constexpr int kRunThreads = 128;
+constexpr int kRunWarps = kRunThreads / 32;
+
+template <int W>
+struct Xf {
+  uint32_t m;     // bits [2w+1:2w]: mode of word w (bit0 ADD, bit1 SET; OR-composable), bit31 error
+  uint32_t ex;    // exists-op of the LAST event in the range: 0 = no event, EX_SOME, EX_NONE
+  uint32_t v[W];  // KEEP => 0
+};
+
+template <int W>
+__device__ __forceinline__ Xf<W> identity() {
+  Xf<W> r;
+  r.m = 0; r.ex = 0;
+#pragma unroll
+  for (int w = 0; w < W; ++w) r.v[w] = 0;
+  return r;
+}
+// later . earlier  (apply `a` first, then `b`)
+template <int W>
+__device__ __forceinline__ Xf<W> compose(const Xf<W>& a, const Xf<W>& b) {
+  Xf<W> r;
+  r.m = a.m | b.m;
+  r.ex = b.ex ? b.ex : a.ex;
+#pragma unroll
+  for (int w = 0; w < W; ++w) r.v[w] = (b.m & (2u << (2 * w))) ? b.v[w] : a.v[w] + b.v[w];
+  return r;
+}
+template <int W>
+__device__ __forceinline__ Xf<W> shfl_xf(const Xf<W>& t, int src) {
+  Xf<W> r;
+  r.m = __shfl_sync(0xffffffffu, t.m, src);
+  r.ex = __shfl_sync(0xffffffffu, t.ex, src);
+#pragma unroll
+  for (int w = 0; w < W; ++w) r.v[w] = __shfl_sync(0xffffffffu, t.v[w], src);
+  return r;
+}
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+
+// Finish one segment: apply the composed transformer to the prior state, write the state struct.
+template <int W>
+__device__ __forceinline__ void finish_segment(const RowArgs& a, uint32_t seg, const Xf<W>& ts, unsigned long long& n_applied) {
+  if (ts.m & M_ERR) {
+    // the handler threw somewhere in the segment: exact replay by the sequential kernel
+    const unsigned long long pos = atomicAdd(a.counters + 3, 1ull);
+    if (pos < a.redo_cap) a.redo_ids[pos] = seg;
+    return;
+  }
+  const uint64_t slot = a.seg_ids ? (uint64_t)a.seg_ids[seg] : (uint64_t)seg;
+  uint32_t old[W], ex0 = 0;
+#pragma unroll
+  for (int w = 0; w < W; ++w) old[w] = 0;
+  if (a.states_in) {
+    const uint4* sp = reinterpret_cast<const uint4*>(a.states_in + slot * (uint64_t)(W + 2) * 4);
+    uint32_t raw[W + 2];
+#pragma unroll
+    for (int q = 0; q < (W + 2) / 4; ++q) { const uint4 v4 = __ldg(sp + q); raw[4 * q] = v4.x; raw[4 * q + 1] = v4.y; raw[4 * q + 2] = v4.z; raw[4 * q + 3] = v4.w; }
+    ex0 = raw[W] & SGR_ST_EXISTS;
+#pragma unroll
+    for (int w = 0; w < W; ++w) old[w] = ex0 ? raw[w] : 0u;
+  }
+  uint32_t nw[W], exn = ex0;
+#pragma unroll
+  for (int w = 0; w < W; ++w) nw[w] = old[w];
+  if (ts.ex) {
+    exn = (ts.ex == EX_NONE) ? 0u : SGR_ST_EXISTS;
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+      nw[w] = (ts.m & (2u << (2 * w))) ? ts.v[w] : old[w] + ts.v[w];
+      if (!exn) nw[w] = 0u;
+    }
+  }
+  uint32_t changed = exn != ex0;
+  if (exn && ex0) {
+#pragma unroll
+    for (int w = 0; w < W; ++w) changed |= (nw[w] != old[w]);
+  }
+  uint32_t outw[W + 2];
+#pragma unroll
+  for (int w = 0; w < W; ++w) outw[w] = nw[w];
+  outw[W] = exn | (changed ? SGR_ST_CHANGED : 0u);
+  outw[W + 1] = 0u;
+  uint4* dp = reinterpret_cast<uint4*>(a.states_out + slot * (uint64_t)(W + 2) * 4);
+#pragma unroll
+  for (int q = 0; q < (W + 2) / 4; ++q) dp[q] = make_uint4(outw[4 * q], outw[4 * q + 1], outw[4 * q + 2], outw[4 * q + 3]);
+  n_applied += (a.seg_offsets[(uint64_t)seg + 1] - a.seg_offsets[seg]) >> 6;
+}
+
+// state of an aggregate that received no event in this batch: unchanged, per-batch flags cleared
+template <int W>
+__device__ __forceinline__ void finish_empty(const RowArgs& a, uint32_t seg) {
+  const uint64_t slot = a.seg_ids ? (uint64_t)a.seg_ids[seg] : (uint64_t)seg;
+  uint4* dp = reinterpret_cast<uint4*>(a.states_out + slot * (uint64_t)(W + 2) * 4);
+  if (a.states_in) {
+    const uint4* sp = reinterpret_cast<const uint4*>(a.states_in + slot * (uint64_t)(W + 2) * 4);
+#pragma unroll
+    for (int q = 0; q < (W + 2) / 4; ++q) {
+      uint4 v4 = __ldg(sp + q);
+      if (q == (W + 2) / 4 - 1) { v4.z &= SGR_ST_EXISTS; v4.w = 0u; if (!v4.z) { v4.x = 0u; v4.y = 0u; } }
+      dp[q] = v4;
+    }
+  } else {
+#pragma unroll
+    for (int q = 0; q < (W + 2) / 4; ++q) dp[q] = make_uint4(0, 0, 0, 0);
+  }
+}
+
+template <int R, int NSTAGE>
+__host__ __device__ constexpr int warp_smem_bytes() {
+  return NSTAGE * 2048 * R   // staged steps
+         + 2 * 32 * R * 4    // segment ids at head positions: starting segment, ending segment
+         + 32 * 4;           // head bitmap (R words used) + pad
+}
+
+template <int W, int R, int NSTAGE>
+__global__ void __launch_bounds__(kRunThreads) fold_runs_kernel(const __grid_constant__ RowArgs a, const __grid_constant__ RowProgram pg) {
+  constexpr int STEP_BYTES = 2048 * R;
+  constexpr int STEP_RECS = 32 * R;
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  __shared__ __align__(16) uint32_t tab[16 * 8];
+  for (int i = threadIdx.x; i < 16 * 8; i += kRunThreads) tab[i] = pg.tab[i];
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint8_t* wsm = smem_raw + (size_t)warp * warp_smem_bytes<R, NSTAGE>();
+  const uint32_t stage0 = smem_u32(wsm);
+  uint32_t* hs_start = reinterpret_cast<uint32_t*>(wsm + NSTAGE * STEP_BYTES);  // segment starting at a head
+  uint32_t* hs_end = hs_start + STEP_RECS;                                       // segment ending at a head (0xffffffff: none)
+  uint32_t* hmask = hs_end + STEP_RECS;                                          // head bitmap, R words
+
+  const uint64_t gw = (uint64_t)blockIdx.x * kRunWarps + warp;  // global warp id
+  const uint64_t n_warps = (uint64_t)gridDim.x * kRunWarps;
+  const uint64_t n_seg = a.n_seg;
+  const uint64_t base = a.log_begin;
+  const uint64_t total_bytes = a.log_end - base;
+  const uint64_t total_steps = (total_bytes + STEP_BYTES - 1) / STEP_BYTES;
+  const uint64_t spw = (total_steps + n_warps - 1) / n_warps;  // steps per warp
+  const uint64_t step0 = gw * spw;
+  const uint64_t step_end = step0 + spw < total_steps ? step0 + spw : total_steps;
+  const bool has_span = step0 < step_end;
+  const uint64_t wb = base + step0 * STEP_BYTES;
+  // the warp that owns the end of the log also finishes the last segment and trailing empty ones;
+  // with an empty log that is warp 0
+  const bool owns_end = has_span ? (step_end == total_steps) : (total_steps == 0 && gw == 0);
+
+  // ---- first boundary of the span: kc = first k in [0, n_seg] with off[k] >= wb (32-ary search)
+  uint64_t kc = 0;
+  if (has_span && gw != 0) {
+    uint64_t lo = 0, hi = n_seg + 1;  // answer in [lo, hi]; hi == n_seg+1: no such boundary
+    while (lo < hi) {
+      const uint64_t chunk = (hi - lo + 31) / 32;
+      const uint64_t p = lo + (uint64_t)lane * chunk;
+      const bool valid = p < hi;
+      const bool ge = !valid || a.seg_offsets[p] >= wb;  // monotone in lane
+      const uint32_t bal = __ballot_sync(0xffffffffu, ge);
+      if (bal == 0) { lo = lo + 31 * chunk + 1; continue; }
+      const int f = __ffs(bal) - 1;
+      if (f == 0) { hi = lo; break; }
+      const uint64_t pf = lo + (uint64_t)f * chunk;
+      lo = lo + (uint64_t)(f - 1) * chunk + 1;
+      hi = pf < hi ? pf : hi;
+    }
+    kc = lo;
+  }
+
+  bool span_has_head = false;          // a segment head was seen in this span
+  bool inh_pending = false;            // the segment flowing into the span awaits the look-back (held by lane 0)
+  uint32_t inh_seg = 0;
+  Xf<W> inh_t = identity<W>();
+  Xf<W> carry = identity<W>();         // open transformer at the end of the previous step
+  unsigned long long n_applied = 0;
+
+  // ---- staging: lane l, copy q of a step moves the 16-byte chunk g = q*32 + l (source order) to its
+  //      swizzled place: record j = g>>2, chunk c = g&3 -> line j>>1, position (4*(j&1)+c) ^ ((j/R)&7)
+  const uint8_t* src_lane = a.events + base + (uint64_t)lane * 16;
+  const uint32_t dst_lane = (uint32_t)(lane >> 3) * 128u;
+  const uint32_t low_pos = (uint32_t)(4 * ((lane >> 2) & 1) + (lane & 3));
+  auto issue_step = [&](uint64_t s, int stage) {
+    const uint64_t sbyte = s * (uint64_t)STEP_BYTES;
+    const uint8_t* src = src_lane + sbyte;
+    const uint32_t dst = stage0 + (uint32_t)stage * STEP_BYTES + dst_lane;
+    const bool full = sbyte + STEP_BYTES <= total_bytes;  // uniform
+#pragma unroll
+    for (int q = 0; q < 4 * R; ++q) {
+      const uint32_t j_over_r = (uint32_t)(q * 8) / R + (uint32_t)(lane >> 2) / R;  // (q*8 + (lane>>2)) / R, exact for R in {1,2,4,8}
+      const uint32_t pos = low_pos ^ (j_over_r & 7u);
+      if (full || sbyte + (uint64_t)q * 512 + (uint64_t)lane * 16 < total_bytes)
+        cp_async16(dst + (uint32_t)q * 512u + pos * 16u, src + (uint64_t)q * 512);
+    }
+  };
+  // prologue: NSTAGE-1 steps in flight
+  if (has_span) {
+#pragma unroll
+    for (int s = 0; s < NSTAGE - 1; ++s) {
+      if (step0 + s < step_end) issue_step(step0 + s, s);
+      cp_async_commit();
+    }
+  }
+
+  // where lane i finds word (c,k) of its record t: line = (R*i+t)>>1, position (4*((R*i+t)&1)+c) ^ (i&7)
+  uint32_t slot_c[kMaxSlots], slot_k[kMaxSlots];
+#pragma unroll
+  for (int s = 0; s < kMaxSlots; ++s) { slot_c[s] = pg.slot_word[s] >> 2; slot_k[s] = pg.slot_word[s] & 3u; }
+  const uint32_t n_slots = pg.n_slots;
+
+  int stage = 0;
+  for (uint64_t step = step0; step < step_end; ++step) {
+    // keep NSTAGE-1 steps in flight
+    {
+      const uint64_t ahead = step + (NSTAGE - 1);
+      int st = stage + (NSTAGE - 1); if (st >= NSTAGE) st -= NSTAGE;
+      if (ahead < step_end) issue_step(ahead, st);
+      cp_async_commit();
+    }
+    const uint64_t sb = base + step * (uint64_t)STEP_BYTES;
+    const uint64_t rem = a.log_end - sb;
+    const uint32_t span = rem < (uint64_t)STEP_BYTES ? (uint32_t)rem : (uint32_t)STEP_BYTES;
+    const int nvalid = (int)(span >> 6);
+
+    // ---- segment heads of this step: boundaries k with off[k] in [sb, sb+span) ----------------------
+#pragma unroll
+    for (int i = 0; i < R; ++i) { hs_end[i * 32 + lane] = 0xffffffffu; hs_start[i * 32 + lane] = 0u; }
+    if (lane < R) hmask[lane] = 0u;
+    __syncwarp();
+    while (true) {
+      const uint64_t k = kc + lane;
+      const uint64_t b = k <= n_seg ? a.seg_offsets[k] : ~0ull;
+      const uint64_t bn = k < n_seg ? a.seg_offsets[k + 1] : ~0ull;
+      const uint64_t d = b - sb;  // >= 0 for every unconsumed boundary
+      const bool in = d < (uint64_t)span;
+      if (in) {
+        const uint32_t pos = (uint32_t)d >> 6;
+        atomicOr(&hmask[pos >> 5], 1u << (pos & 31));
+        atomicMax(&hs_start[pos], (uint32_t)k);                       // the last boundary at this offset starts the live segment
+        if (k > 0) atomicMin(&hs_end[pos], (uint32_t)k - 1u);         // the first one ends the previous segment
+        if (bn == b) finish_empty<W>(a, (uint32_t)k);                 // segment k is empty
+      }
+      const int cnt = __popc(__ballot_sync(0xffffffffu, in));
+      kc += cnt;
+      if (cnt < 32) break;
+    }
+    __syncwarp();
+
+    // ---- wait for this step's bytes --------------------------------------------------------------------
+    cp_async_wait<NSTAGE - 1>();
+    __syncwarp();
+
+    // ---- lane run: R consecutive records, left to right -------------------------------------------------
+    const uint32_t sbase = stage0 + (uint32_t)stage * STEP_BYTES;
+    uint32_t hbits;
+    if (R >= 32) hbits = hmask[lane];
+    else hbits = (hmask[(lane * R) >> 5] >> ((lane * R) & 31)) & ((R >= 32) ? 0xffffffffu : ((1u << R) - 1u));
+    Xf<W> cur = identity<W>();
+    Xf<W> first = identity<W>();
+    uint32_t first_seg = 0xffffffffu;
+    bool have_first = false;
+#pragma unroll
+    for (int t = 0; t < R; ++t) {
+      const int p = lane * R + t;
+      if (hbits & (1u << t)) {
+        const uint32_t eseg = hs_end[p];
+        if (!have_first) { first = cur; first_seg = eseg; have_first = true; }
+        else if (eseg != 0xffffffffu) finish_segment<W>(a, eseg, cur, n_applied);  // began and ended inside this run
+        cur = identity<W>();
+      }
+      if (p < nvalid) {
+        const uint32_t rec = sbase + (uint32_t)(p >> 1) * 128u;
+        const uint32_t par4 = (uint32_t)(p & 1) * 4u;
+        uint32_t sv[kMaxSlots];
+#pragma unroll
+        for (int s = 0; s < kMaxSlots; ++s) {
+          sv[s] = 0;
+          if (s < (int)n_slots) sv[s] = lds32(rec + (((par4 + slot_c[s]) ^ (uint32_t)(lane & 7)) << 4) + (slot_k[s] << 2));
+        }
+        const uint32_t type = sv[0];
+        uint4 e0 = make_uint4(0, 0, 0, 0);
+        if (type < 16u) e0 = *reinterpret_cast<const uint4*>(tab + type * 8);
+        if (!(e0.x & 1u)) {
+          cur.m |= M_ERR;  // THROW rule or scala.MatchError
+        } else {
+          cur.ex = (e0.x & 2u) ? EX_NONE : EX_SOME;
+          uint32_t spec[W];
+          spec[0] = e0.y;
+          if (W > 1) spec[1] = e0.z;
+          if (W > 2) spec[2] = e0.w;
+#pragma unroll
+          for (int w = 3; w < W; ++w) spec[w] = tab[type * 8 + 1 + w];
+#pragma unroll
+          for (int w = 0; w < W; ++w) {
+            uint32_t val = 0;
+#pragma unroll
+            for (int s = 1; s < kMaxSlots; ++s) val = ((spec[w] >> 3) == (uint32_t)s) ? sv[s] : val;
+            if (spec[w] & 4u) val = 0u - val;
+            const uint32_t mode = spec[w] & 3u;
+            if (mode == 2u) cur.v[w] = val;
+            else if (mode == 1u) cur.v[w] += val;
+            cur.m |= mode << (2 * w);
+          }
+        }
+      }
+    }
+    // cur = transformer of the records after the run's last head (the whole run if it has none)
+
+    // ---- once per step: segmented inclusive scan of the 32 lane transformers, in log order -------------
+    const uint32_t lane_heads = __ballot_sync(0xffffffffu, have_first);
+    Xf<W> sc = cur;
+    if (lane == 0 && !have_first) sc = compose(carry, sc);
+#pragma unroll
+    for (int dd = 1; dd < 32; dd <<= 1) {
+      const Xf<W> o = shfl_xf(sc, lane - dd);  // wraps for lane < dd; masked below
+      const int sh = lane >= dd ? lane - dd + 1 : 0;
+      const uint32_t window = (lane_heads >> sh) & ((1u << dd) - 1u);  // a head in lanes (lane-dd, lane]?
+      if (lane >= dd && window == 0) sc = compose(o, sc);
+    }
+    // what flows INTO each lane's run: the scan value of the previous lane (lane 0: the carry)
+    Xf<W> cin = shfl_xf(sc, lane - 1);
+    if (lane == 0) cin = carry;
+    carry = shfl_xf(sc, 31);
+
+    // ---- the segment that ends at a run's first head needs what flowed in ----------------------------------
+    if (have_first && first_seg != 0xffffffffu) {
+      const Xf<W> tot = compose(cin, first);
+      // the very first head of the span ends a segment that began in an earlier span: look-back needed
+      const bool is_span_first = !span_has_head && (lane_heads & ((1u << lane) - 1u)) == 0;
+      if (is_span_first && gw != 0) { inh_t = tot; inh_seg = first_seg; inh_pending = true; }
+      else finish_segment<W>(a, first_seg, tot, n_applied);
+    }
+    if (lane_heads) {
+      // the pending look-back lives in the lane that saw the span's first head: move it to lane 0
+      if (!span_has_head) {
+        const int src = __ffs(lane_heads) - 1;
+        inh_t = shfl_xf(inh_t, src);
+        inh_seg = __shfl_sync(0xffffffffu, inh_seg, src);
+        inh_pending = __shfl_sync(0xffffffffu, (int)inh_pending, src) != 0;
+      }
+      span_has_head = true;
+    }
+    __syncwarp();
+    if (++stage == NSTAGE) stage = 0;
+  }
+  cp_async_wait<0>();
+
+  // ---- end of the log: the open segment and any trailing empty segments --------------------------------
+  // boundaries with off[k] == log_end were never a head inside a step; kc is the first of them.
+  bool end_needs_lookback = false;
+  if (owns_end) {
+    for (uint64_t k = kc + lane; k < n_seg; k += 32) finish_empty<W>(a, (uint32_t)k);  // segments kc..n_seg-1 are empty
+    if (kc >= 1 && total_steps > 0) {
+      // segment kc-1 is the last non-empty one; its transformer is the carry
+      if (span_has_head || gw == 0) { if (lane == 0) finish_segment<W>(a, (uint32_t)(kc - 1), carry, n_applied); }
+      else end_needs_lookback = true;  // the whole span lies inside that segment
+    }
+  }
+
+  // ---- publish this span's open transformer, then finish what needs the predecessors ---------------------
+  if (has_span) {
+    uint32_t* part_data = a.part_data + gw * (W + 2);
+    if (lane == 0) {
+      part_data[0] = carry.m;
+#pragma unroll
+      for (int w = 0; w < W; ++w) part_data[1 + w] = carry.v[w];
+      part_data[W + 1] = carry.ex | (span_has_head ? 4u : 0u);
+      __threadfence();
+      asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(a.part_flags + gw), "r"(a.epoch) : "memory");
+    }
+    if (lane == 0 && (inh_pending || end_needs_lookback)) {
+      // decoupled look-back: compose predecessors' open transformers until one that contains a head
+      Xf<W> pre = identity<W>();
+      uint64_t p = gw;
+      while (p > 0) {
+        --p;
+        const uint32_t* pf = a.part_flags + p;
+        while (ld_volatile_u32(pf) != a.epoch) { __nanosleep(64); }
+        __threadfence();
+        const uint32_t* pd = a.part_data + p * (W + 2);
+        Xf<W> e;
+        e.m = ld_volatile_u32(pd);
+#pragma unroll
+        for (int w = 0; w < W; ++w) e.v[w] = ld_volatile_u32(pd + 1 + w);
+        const uint32_t tailw = ld_volatile_u32(pd + W + 1);
+        e.ex = tailw & 3u;
+        pre = compose(e, pre);
+        if (tailw & 4u) break;
+      }
+      if (inh_pending) finish_segment<W>(a, inh_seg, compose(pre, inh_t), n_applied);
+      if (end_needs_lookback) finish_segment<W>(a, (uint32_t)(kc - 1), compose(pre, carry), n_applied);
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) n_applied += __shfl_xor_sync(0xffffffffu, n_applied, o);
+  if (lane == 0 && n_applied) atomicAdd(a.counters + 0, n_applied);
+}
+
+typedef void (*RunKernel)(const RowArgs, const RowProgram);
+struct RunVariant { RunKernel k; int r, nstage; const char* name; };
+const RunVariant kRunVariants[] = {
+    {fold_runs_kernel<2, 4, 3>, 4, 3, "runs W2 R4 st3"},
+    {fold_runs_kernel<2, 4, 2>, 4, 2, "runs W2 R4 st2"},
+    {fold_runs_kernel<2, 8, 2>, 8, 2, "runs W2 R8 st2"},
+    {fold_runs_kernel<2, 2, 4>, 2, 4, "runs W2 R2 st4"},
+    {fold_runs_kernel<2, 8, 3>, 8, 3, "runs W2 R8 st3"},
+    {fold_runs_kernel<2, 2, 3>, 2, 3, "runs W2 R2 st3"},
+};
+constexpr int kNumRunVariants = sizeof(kRunVariants) / sizeof(kRunVariants[0]);
+
+size_t variant_smem(int v) {
+  const int r = kRunVariants[v].r, ns = kRunVariants[v].nstage;
+  return (size_t)kRunWarps * ((size_t)ns * 2048 * r + 2 * 32 * r * 4 + 32 * 4);
+}
+
+}  // namespace
+
+int run_variant_count() { return kNumRunVariants; }
+const char* run_variant_name(int v) { return (v >= 0 && v < kNumRunVariants) ? kRunVariants[v].name : "?"; }
+
+int run_kernel_max_grid(int num_sms, int variant) {
+  if (variant < 0 || variant >= kNumRunVariants) variant = 0;
+  const size_t smem = variant_smem(variant);
+  cudaFuncSetAttribute(kRunVariants[variant].k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kRunVariants[variant].k, kRunThreads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+  return per_sm * num_sms;
+}
+
+int run_variant_step_bytes(int variant) {
+  if (variant < 0 || variant >= kNumRunVariants) variant = 0;
+  return 2048 * kRunVariants[variant].r;
+}
+int run_warps_per_cta() { return kRunWarps; }
+
+cudaError_t launch_fold_runs(const RowArgs& args, const RowProgram& prog, int variant, int grid, cudaStream_t stream) {
+  if (prog.user_words != 2) return cudaErrorInvalidValue;
+  if (variant < 0 || variant >= kNumRunVariants) variant = 0;
+  const size_t smem = variant_smem(variant);
+  cudaError_t e = cudaFuncSetAttribute(kRunVariants[variant].k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  kRunVariants[variant].k<<<grid, kRunThreads, smem, stream>>>(args, prog);
+  return cudaGetLastError();
+}
+
+}  // namespace sgr

@@ -1,8 +1,9 @@
 """-m gpu: the CUDA path, called through the C ABI, against the oracle on the same seeded inputs.
 Bit-exact: whole state tables are compared byte for byte (integer / byte work, no tolerance).
 
-kernel=1 forces the lane-sequential TMA kernel (fold_kernels.cu), kernel=0 lets the engine pick
-(record-parallel fold_rows.cu for programs inside the transformer algebra).
+kernel=0 lets the engine pick (fold_runs.cu for programs inside the transformer algebra),
+kernel=1 forces the lane-sequential TMA kernel (fold_kernels.cu), kernel=3 the record-per-lane
+rows kernel (fold_rows.cu).
 """
 import uuid
 
@@ -19,15 +20,17 @@ from surge_b200 import synth as S
 
 pytestmark = pytest.mark.gpu
 
-KERNELS = [0, 1]
+KERNELS = [0, 1, 3]
 
 
-def run_engine(prog, events, offsets, kernel=0, init=None, variant=None):
+def run_engine(prog, events, offsets, kernel=0, init=None, variant=None, run_variant=None):
     with ReplayEngine(0) as e:
         e.register_program(prog)
         e.set_option("kernel", kernel)
         if variant is not None:
             e.set_option("fold_variant", variant)
+        if run_variant is not None:
+            e.set_option("run_variant", run_variant)
         if init is not None:
             e.set_initial_states(init)
         e.load_events(events, offsets)
@@ -131,6 +134,20 @@ def test_sequential_kernel_variants(variant):
     rec, off = S.counter_csr(len(counts), counts, seed=41, p_throw=0.002)
     want, _, _ = O.fold_packed(O.MODEL_COUNTER, O.REC_FIXED64, rec, off)
     got, _ = run_engine(P.counter_program(), rec, off, kernel=1, variant=variant)
+    assert_same(got, want)
+
+
+@pytest.mark.parametrize("run_variant", range(6))
+def test_runs_kernel_variants(run_variant):
+    rng = np.random.default_rng(50 + run_variant)
+    counts = np.concatenate([rng.integers(0, 50, size=3000), [60_000], rng.integers(0, 4, size=500)])
+    rec, off = S.counter_csr(len(counts), counts, seed=51, p_throw=0.001)
+    init = np.zeros(len(counts), dtype=F.COUNTER_STATE)
+    ex = rng.random(len(counts)) < 0.5
+    init["count"][ex] = 7
+    init["flags"][ex] = N.ST_EXISTS
+    want, _, _ = O.fold_packed(O.MODEL_COUNTER, O.REC_FIXED64, rec, off, init)
+    got, _ = run_engine(P.counter_program(), rec, off, kernel=2, init=init, run_variant=run_variant)
     assert_same(got, want)
 
 
