@@ -31,6 +31,6 @@ def big(n_agg, epa, kernels):
 
 if __name__ == "__main__":
     print(torch.cuda.get_device_name(0), flush=True)
-    ks = [(2, v) for v in range(6)] + [(3, None), (1, 1)]
+    ks = [(2, v) for v in range(7)] + [(3, None), (1, 1)]
     big(1 << 20, 32, ks)
     big(10_000_000 // 8, 100, ks)

@@ -67,11 +67,15 @@ struct sgr_engine {
   int run_max_grid = 0, run_max_grid_variant = -1;
   int64_t opt_run_variant = 0;
   DevBuf part_flags, part_data, redo_ids;
+  DevBuf run_counters;            // 2 x 8 u64, ping-pong; the runs kernel zeroes the other block itself
+  int run_counter_idx = 0;
+  const void* pending_counters = nullptr;
   uint32_t epoch = 0;
   size_t part_flags_cap_seen = 0;
   bool offsets_aligned64 = false; // every segment offset == log_begin (mod 64)
   uint64_t log_begin = 0, log_end = 0;
   bool fold_pending = false;      // a fold was enqueued and not yet finished
+  bool pending_rows_v1 = false;
   bool pending_used_rows = false, pending_prior = false, pending_timed_group = false;
   uint64_t pending_n_seg = 0, pending_event_bytes = 0;
   const uint8_t* pending_events = nullptr; const uint64_t* pending_offsets = nullptr; const uint32_t* pending_ids = nullptr;
@@ -195,24 +199,36 @@ constexpr uint64_t kRedoCap = 1u << 20;
 // Enqueue one fold on the engine's stream (no host synchronisation).
 int32_t enqueue_fold(sgr_engine* e, const uint8_t* d_events, const uint64_t* d_offsets, const uint32_t* d_ids,
                      uint64_t n_seg, bool use_prior, uint64_t event_bytes, bool aligned64, uint64_t log_begin, uint64_t log_end) {
-  CUDA_TRY(e, cudaMemsetAsync(e->counters.p, 0, 64, e->stream));
   const uint8_t* states_in = use_prior ? (const uint8_t*)e->states.p : nullptr;
-  bool use_rows = e->row_ok && aligned64 && e->opt_kernel != 1 && n_seg < (1ull << 32);
-  if ((e->opt_kernel == 2 || e->opt_kernel == 3) && !use_rows) return fail(e, SGR_ERR_UNSUPPORTED, "record-parallel kernel cannot take this program/log");
+  bool use_rows = e->row_ok && aligned64 && e->opt_kernel != 1 && n_seg < (1ull << 32) && n_seg > 0;
+  if ((e->opt_kernel == 2 || e->opt_kernel == 3) && !use_rows && n_seg > 0)
+    return fail(e, SGR_ERR_UNSUPPORTED, "record-parallel kernel cannot take this program/log");
+  const bool runs = use_rows && e->opt_kernel != 3;
+  unsigned long long* counters = (unsigned long long*)e->counters.p;
+  if (runs) {
+    if (!e->run_counters.p) {
+      CUDA_TRY(e, e->run_counters.reserve(256));
+      CUDA_TRY(e, cudaMemsetAsync(e->run_counters.p, 0, 256, e->stream));
+    }
+    counters = (unsigned long long*)e->run_counters.p + 8 * e->run_counter_idx;
+  } else {
+    CUDA_TRY(e, cudaMemsetAsync(e->counters.p, 0, 64, e->stream));
+  }
+  e->pending_counters = counters;
   CUDA_TRY(e, cudaEventRecord(e->ev0, e->stream));
   uint32_t launches = 0;
   if (n_seg) {
     FoldArgs a{};
     a.events = d_events; a.seg_offsets = d_offsets; a.seg_ids = d_ids; a.n_seg = n_seg;
     a.states_in = states_in; a.states_out = (uint8_t*)e->states.p;
-    a.counters = (unsigned long long*)e->counters.p;
+    a.counters = counters;
     a.long_threshold = (uint64_t)e->opt_long_threshold;
     FoldLaunchInfo info{};
     if (use_rows) {
       const bool v1 = e->opt_kernel == 3;
       const int rv = (int)e->opt_run_variant;
       if (v1 && !e->row_max_grid) e->row_max_grid = row_kernel_max_grid(e->num_sms, e->row_prog);
-      if (!v1 && e->run_max_grid_variant != rv) { e->run_max_grid = run_kernel_max_grid(e->num_sms, rv); e->run_max_grid_variant = rv; }
+      if (!v1 && e->run_max_grid_variant != rv) { e->run_max_grid = run_kernel_max_grid(e->num_sms, rv, e->row_prog); e->run_max_grid_variant = rv; }
       const int max_grid = v1 ? e->row_max_grid : e->run_max_grid;
       const int wpc = v1 ? kRowThreads / 32 : run_warps_per_cta();
       const uint64_t step_bytes = v1 ? 2048 : (uint64_t)run_variant_step_bytes(rv);
@@ -230,7 +246,8 @@ int32_t enqueue_fold(sgr_engine* e, const uint8_t* d_events, const uint64_t* d_o
       r.events = d_events; r.seg_offsets = d_offsets; r.seg_ids = d_ids; r.n_seg = n_seg;
       r.log_begin = log_begin; r.log_end = log_end;
       r.states_in = states_in; r.states_out = (uint8_t*)e->states.p;
-      r.counters = (unsigned long long*)e->counters.p;
+      r.counters = counters;
+      r.counters_next = runs ? (unsigned long long*)e->run_counters.p + 8 * (e->run_counter_idx ^ 1) : nullptr;
       r.redo_ids = (uint32_t*)e->redo_ids.p; r.redo_cap = kRedoCap;
       r.part_flags = (uint32_t*)e->part_flags.p; r.part_data = (uint32_t*)e->part_data.p; r.epoch = e->epoch;
       const uint64_t steps = (log_end - log_begin + step_bytes - 1) / step_bytes;
@@ -239,14 +256,19 @@ int32_t enqueue_fold(sgr_engine* e, const uint8_t* d_events, const uint64_t* d_o
       const int grid = (int)(want < (uint64_t)max_grid ? want : (uint64_t)max_grid);
       cudaError_t le = v1 ? launch_fold_rows(r, e->row_prog, grid, e->stream) : launch_fold_runs(r, e->row_prog, rv, grid, e->stream);
       if (le != cudaSuccess) return fail(e, SGR_ERR_CUDA, "fold launch: %s", cudaGetErrorString(le));
-      // exact replay of the segments whose handler threw (count lives on the device)
-      a.seg_list = (const uint32_t*)e->redo_ids.p;
-      a.n_seg = kRedoCap;
-      a.n_seg_dev = (const unsigned long long*)e->counters.p + 3;
-      a.long_threshold = 0;
-      le = launch_fold_stream(a, e->dprog, -1, 8, e->max_record_bytes, e->stream, &info);
-      if (le != cudaSuccess) return fail(e, SGR_ERR_CUDA, "replay launch: %s", cudaGetErrorString(le));
-      launches = 2;
+      if (runs) {
+        e->run_counter_idx ^= 1;  // the kernel replays throwing segments itself and cleans the other block
+        launches = 1;
+      } else {
+        // rows kernel: exact replay of the segments whose handler threw (count lives on the device)
+        a.seg_list = (const uint32_t*)e->redo_ids.p;
+        a.n_seg = kRedoCap;
+        a.n_seg_dev = counters + 3;
+        a.long_threshold = 0;
+        le = launch_fold_stream(a, e->dprog, -1, 8, e->max_record_bytes, e->stream, &info);
+        if (le != cudaSuccess) return fail(e, SGR_ERR_CUDA, "replay launch: %s", cudaGetErrorString(le));
+        launches = 2;
+      }
     } else {
       cudaError_t le = launch_fold_stream(a, e->dprog, (int)e->opt_variant, e->num_sms, e->max_record_bytes, e->stream, &info);
       if (le != cudaSuccess) return fail(e, SGR_ERR_CUDA, "fold launch: %s", cudaGetErrorString(le));
@@ -254,7 +276,7 @@ int32_t enqueue_fold(sgr_engine* e, const uint8_t* d_events, const uint64_t* d_o
     }
   }
   CUDA_TRY(e, cudaEventRecord(e->ev1, e->stream));
-  e->fold_pending = true; e->pending_used_rows = use_rows; e->pending_prior = use_prior;
+  e->fold_pending = true; e->pending_used_rows = use_rows; e->pending_rows_v1 = use_rows && e->opt_kernel == 3; e->pending_prior = use_prior;
   e->pending_n_seg = n_seg; e->pending_event_bytes = event_bytes;
   e->pending_events = d_events; e->pending_offsets = d_offsets; e->pending_ids = d_ids;
   e->stats.fold_launches = launches;
@@ -266,7 +288,7 @@ int32_t finish_fold(sgr_engine* e) {
   if (!e->fold_pending) return SGR_OK;
   e->fold_pending = false;
   unsigned long long h[8];
-  CUDA_TRY(e, cudaMemcpyAsync(h, e->counters.p, 64, cudaMemcpyDeviceToHost, e->stream));
+  CUDA_TRY(e, cudaMemcpyAsync(h, e->pending_counters, 64, cudaMemcpyDeviceToHost, e->stream));
   CUDA_TRY(e, cudaStreamSynchronize(e->stream));
   CUDA_TRY(e, cudaEventElapsedTime(&e->stats.ms_fold, e->ev0, e->ev1));
   if (e->pending_used_rows && h[3] > kRedoCap) {
@@ -289,7 +311,9 @@ int32_t finish_fold(sgr_engine* e) {
   }
   const uint64_t n_seg = e->pending_n_seg;
   e->stats.n_aggregates = n_seg;
-  e->stats.n_events = h[0];
+  // runs kernel counts every record, the replay takes back what followed a throw; the rows kernel skips
+  // throwing segments, the replay adds what preceded the throw
+  e->stats.n_events = !e->pending_used_rows ? h[0] : (e->pending_rows_v1 ? h[0] + h[5] : h[0] - h[4]);
   e->stats.n_errors = h[1];
   e->stats.n_long_segments = h[2];
   e->stats.event_bytes = e->pending_event_bytes;
@@ -342,7 +366,7 @@ int32_t sgr_destroy(sgr_engine* e) {
   e->own_events.release(); e->own_offsets.release(); e->states.release(); e->counters.release();
   e->inc_records.release(); e->inc_offsets.release(); e->inc_ids.release(); e->inc_prev_ids.release();
   e->group.release();
-  e->part_flags.release(); e->part_data.release(); e->redo_ids.release();
+  e->part_flags.release(); e->part_data.release(); e->redo_ids.release(); e->run_counters.release();
   cudaEventDestroy(e->ev0); cudaEventDestroy(e->ev1); cudaEventDestroy(e->ev2); cudaEventDestroy(e->ev3);
   cudaStreamDestroy(e->stream);
   delete e;
@@ -356,10 +380,15 @@ int32_t sgr_register_program(sgr_engine* e, const sgr_fold_program* prog) {
   if (rc) return rc;
   e->program = *prog; e->dprog = d; e->has_program = true;
   e->row_ok = build_row_program(d, &e->row_prog);
-  e->row_max_grid = 0;
+  e->row_max_grid = 0; e->run_max_grid_variant = -1;
   e->states_valid = false; e->states_n = 0;
   mark_dirty(e);
   return SGR_OK;
+}
+
+static int32_t before_load(sgr_engine* e) {
+  int32_t rc = use_device(e); if (rc) return rc;
+  return finish_fold(e);
 }
 
 static int32_t after_load(sgr_engine* e, const uint8_t* d_events, const uint64_t* d_offsets, uint64_t nbytes, uint64_t n_agg) {
@@ -385,7 +414,7 @@ int32_t sgr_load_events(sgr_engine* e, const void* events, uint64_t nbytes, cons
     if (seg_offsets[i] % 16) return fail(e, SGR_ERR_INVALID, "seg_offsets[%llu] is not a multiple of 16", (unsigned long long)i);
     if (i && seg_offsets[i] < seg_offsets[i - 1]) return fail(e, SGR_ERR_INVALID, "seg_offsets not monotone at %llu", (unsigned long long)i);
   }
-  int32_t rc = use_device(e); if (rc) return rc;
+  int32_t rc = before_load(e); if (rc) return rc;
   CUDA_TRY(e, e->own_events.reserve(nbytes));
   CUDA_TRY(e, e->own_offsets.reserve((n_agg + 1) * 8));
   CUDA_TRY(e, cudaEventRecord(e->ev0, e->stream));
@@ -402,7 +431,7 @@ int32_t sgr_load_events_device(sgr_engine* e, const void* d_events, uint64_t nby
   if (!e || (!d_events && nbytes) || !d_seg_offsets) return fail(e, SGR_ERR_INVALID, "null argument");
   if (!e->has_program) return fail(e, SGR_ERR_NO_PROGRAM, "register a fold program before loading events");
   if (((uintptr_t)d_events) % 16) return fail(e, SGR_ERR_INVALID, "device event log must be 16-byte aligned");
-  int32_t rc = use_device(e); if (rc) return rc;
+  int32_t rc = before_load(e); if (rc) return rc;
   e->stats.ms_h2d = 0; e->stats.ms_group = 0;
   return after_load(e, (const uint8_t*)d_events, d_seg_offsets, nbytes, n_agg);
 }
@@ -427,7 +456,7 @@ static int32_t load_unsorted_impl(sgr_engine* e, const void* d_records, uint64_t
 int32_t sgr_load_unsorted_device(sgr_engine* e, const void* d_records, uint64_t n_records, uint64_t n_agg) {
   if (!e || (!d_records && n_records)) return fail(e, SGR_ERR_INVALID, "null argument");
   if (!e->has_program) return fail(e, SGR_ERR_NO_PROGRAM, "register a fold program before loading events");
-  int32_t rc = use_device(e); if (rc) return rc;
+  int32_t rc = before_load(e); if (rc) return rc;
   e->stats.ms_h2d = 0;
   return load_unsorted_impl(e, d_records, n_records, n_agg);
 }
@@ -435,7 +464,7 @@ int32_t sgr_load_unsorted_device(sgr_engine* e, const void* d_records, uint64_t 
 int32_t sgr_load_unsorted(sgr_engine* e, const void* records, uint64_t n_records, uint64_t n_agg) {
   if (!e || (!records && n_records)) return fail(e, SGR_ERR_INVALID, "null argument");
   if (!e->has_program) return fail(e, SGR_ERR_NO_PROGRAM, "register a fold program before loading events");
-  int32_t rc = use_device(e); if (rc) return rc;
+  int32_t rc = before_load(e); if (rc) return rc;
   CUDA_TRY(e, e->inc_records.reserve(n_records * 64));
   CUDA_TRY(e, cudaEventRecord(e->ev0, e->stream));
   CUDA_TRY(e, cudaMemcpyAsync(e->inc_records.p, records, n_records * 64, cudaMemcpyHostToDevice, e->stream));
@@ -448,8 +477,9 @@ int32_t sgr_load_unsorted(sgr_engine* e, const void* records, uint64_t n_records
 int32_t sgr_set_initial_states(sgr_engine* e, const void* states, uint64_t n_agg) {
   if (!e) return SGR_ERR_INVALID;
   if (!e->has_program) return fail(e, SGR_ERR_NO_PROGRAM, "register a fold program first");
-  int32_t rc = use_device(e); if (rc) return rc;
+  // NULL only says "the next fold starts from None everywhere": no device work, no wait
   if (!states) { e->states_valid = false; mark_dirty(e); return SGR_OK; }
+  int32_t rc = before_load(e); if (rc) return rc;
   rc = ensure_states(e, n_agg); if (rc) return rc;
   CUDA_TRY(e, cudaMemcpyAsync(e->states.p, states, (size_t)n_agg * e->program.state_bytes, cudaMemcpyHostToDevice, e->stream));
   CUDA_TRY(e, cudaStreamSynchronize(e->stream));
@@ -458,12 +488,14 @@ int32_t sgr_set_initial_states(sgr_engine* e, const void* states, uint64_t n_agg
   return SGR_OK;
 }
 
-static int32_t fold_begin(sgr_engine* e) {
+static int32_t fold_begin(sgr_engine* e, bool pipelined) {
   if (!e) return SGR_ERR_INVALID;
   if (!e->has_program) return fail(e, SGR_ERR_NO_PROGRAM, "no fold program registered");
   if (!e->loaded) return fail(e, SGR_ERR_NOT_LOADED, "no event log loaded");
   int32_t rc = use_device(e); if (rc) return rc;
-  rc = finish_fold(e); if (rc) return rc;
+  // back-to-back asynchronous folds of the same log are queued without a host round trip;
+  // only the last one is waited on (sgr_wait) and has its statistics collected
+  if (!pipelined) { rc = finish_fold(e); if (rc) return rc; }
   const bool prior = e->states_valid && e->states_n == e->n_agg;
   rc = ensure_states(e, e->n_agg); if (rc) return rc;
   rc = enqueue_fold(e, e->d_events, e->d_offsets, nullptr, e->n_agg, prior, e->event_bytes, e->offsets_aligned64, e->log_begin, e->log_end);
@@ -475,11 +507,11 @@ static int32_t fold_begin(sgr_engine* e) {
 }
 
 int32_t sgr_fold(sgr_engine* e) {
-  int32_t rc = fold_begin(e); if (rc) return rc;
+  int32_t rc = fold_begin(e, false); if (rc) return rc;
   return finish_fold(e);
 }
 
-int32_t sgr_fold_async(sgr_engine* e) { return fold_begin(e); }
+int32_t sgr_fold_async(sgr_engine* e) { return fold_begin(e, true); }
 
 int32_t sgr_wait(sgr_engine* e) {
   if (!e) return SGR_ERR_INVALID;

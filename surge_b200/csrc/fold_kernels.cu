@@ -159,7 +159,8 @@ fold_stream_kernel(const __grid_constant__ FoldArgs a, const __grid_constant__ D
   bool c_has = c_seg < n_seg;
   bool c_fresh = true;
   uint32_t rp = 0, avail = 0, k = 0, exists = 0, exists0 = 0, err = 0, err_idx = 0;
-  unsigned long long n_applied = 0, n_err = 0, n_skipped = 0;
+  unsigned long long n_applied = 0, n_err = 0, n_skipped = 0, n_dropped = 0;
+  uint32_t c_total = 0;  // bytes of the current segment received so far
 
   auto zero_state = [&]() {
     for (uint32_t w = 0; w < user_words; ++w) st[w * THREADS] = 0u;
@@ -216,7 +217,7 @@ fold_stream_kernel(const __grid_constant__ FoldArgs a, const __grid_constant__ D
   };
 
   auto begin_segment = [&](int s) {
-    rp = (uint32_t)s * CH; avail = 0; k = 0; err = 0; err_idx = 0; exists = 0; exists0 = 0;
+    rp = (uint32_t)s * CH; avail = 0; k = 0; err = 0; err_idx = 0; exists = 0; exists0 = 0; c_total = 0;
     if (a.states_in) {
       const uint64_t sg = seg_of(c_seg);
       const uint64_t slot = a.seg_ids ? (uint64_t)a.seg_ids[sg] : sg;
@@ -245,6 +246,7 @@ fold_stream_kernel(const __grid_constant__ FoldArgs a, const __grid_constant__ D
     if (err) {
       // .recover { case e => ACKError(e) }: the actor keeps its previous state
       flags = exists0 | SGR_ST_ERROR; src = st0; ++n_err;
+      if (KIND == (int)SGR_REC_FIXED64) n_dropped += (c_total >> 6) - k;  // records of this segment that were not applied
     } else {
       // shouldPublish = state.stateOpt != context.state
       uint32_t changed = exists != exists0;
@@ -289,6 +291,7 @@ fold_stream_kernel(const __grid_constant__ FoldArgs a, const __grid_constant__ D
     if (!c_has) return;
     if (c_fresh) { begin_segment(s); c_fresh = false; }
     avail += d & DESC_BYTES;
+    c_total += d & DESC_BYTES;
     if (err) avail = 0;  // drain: nothing more is applied once the handler threw
     while (true) {
       uint32_t rec_len, rec_bytes;
@@ -349,9 +352,12 @@ fold_stream_kernel(const __grid_constant__ FoldArgs a, const __grid_constant__ D
     n_applied += __shfl_xor_sync(0xffffffffu, n_applied, o);
     n_err += __shfl_xor_sync(0xffffffffu, n_err, o);
     n_skipped += __shfl_xor_sync(0xffffffffu, n_skipped, o);
+    n_dropped += __shfl_xor_sync(0xffffffffu, n_dropped, o);
   }
   if ((tid & 31) == 0 && a.counters) {
-    if (n_applied) atomicAdd(a.counters + 0, n_applied);
+    // replay mode (n_seg_dev set): the record-parallel kernel already counted every record as applied
+    if (n_applied) atomicAdd(a.counters + (a.n_seg_dev ? 5 : 0), n_applied);
+    if (n_dropped) atomicAdd(a.counters + 4, n_dropped);
     if (n_err) atomicAdd(a.counters + 1, n_err);
     if (n_skipped) atomicAdd(a.counters + 2, n_skipped);
   }

@@ -16,7 +16,8 @@ struct FoldArgs {
   const unsigned long long* n_seg_dev;  // optional: min(*n_seg_dev, n_seg) segments (count produced on the device)
   const uint8_t* states_in;      // optional prior states, slot-indexed; null => all None
   uint8_t* states_out;           // slot-indexed; may alias states_in
-  unsigned long long* counters;  // [0] events applied, [1] aggregates in error, [2] segments left to the split path
+  unsigned long long* counters;  // [0] events applied, [1] aggregates in error, [2] segments left to the split path,
+                                 // [4] records dropped after a throw (fixed records), [5] events applied in replay mode
   uint64_t long_threshold;       // segments longer than this many bytes are skipped here (0 = never)
 };
 

@@ -27,7 +27,9 @@ struct RowArgs {
   uint64_t log_begin, log_end;  // seg_offsets[0], seg_offsets[n_seg]
   const uint8_t* states_in;     // optional prior states
   uint8_t* states_out;
-  unsigned long long* counters; // [0] events applied, [3] segments queued for exact replay
+  unsigned long long* counters; // [0] events applied, [1] aggregates in error, [3] segments queued for exact replay,
+                                // [4] records dropped after a throw, [6] grid-barrier arrivals (fold_runs)
+  unsigned long long* counters_next;  // fold_runs: the other counter block, zeroed for the next fold
   uint32_t* redo_ids;           // segments whose handler threw (replayed by the sequential kernel)
   uint64_t redo_cap;
   uint32_t* part_flags;         // per warp: == epoch once its open transformer is published
@@ -49,7 +51,7 @@ cudaError_t launch_fold_rows(const RowArgs& args, const RowProgram& prog, int gr
 // ---- fold_runs.cu: lane-run variant (primary). Same RowArgs / RowProgram.
 int run_variant_count();
 const char* run_variant_name(int v);
-int run_kernel_max_grid(int num_sms, int variant);
+int run_kernel_max_grid(int num_sms, int variant, const RowProgram& prog);
 int run_variant_step_bytes(int variant);
 int run_warps_per_cta();
 cudaError_t launch_fold_runs(const RowArgs& args, const RowProgram& prog, int variant, int grid, cudaStream_t stream);

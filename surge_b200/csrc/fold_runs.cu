@@ -79,6 +79,11 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p));
+  return v;
+}
 __device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) {
   uint32_t v;
   asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p));
@@ -87,7 +92,7 @@ __device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) {
 
 // Finish one segment: apply the composed transformer to the prior state, write the state struct.
 template <int W>
-__device__ __forceinline__ void finish_segment(const RowArgs& a, uint32_t seg, const Xf<W>& ts, unsigned long long& n_applied) {
+__device__ __forceinline__ void finish_segment(const RowArgs& a, uint32_t seg, const Xf<W>& ts) {
   if (ts.m & M_ERR) {
     // the handler threw somewhere in the segment: exact replay by the sequential kernel
     const unsigned long long pos = atomicAdd(a.counters + 3, 1ull);
@@ -131,7 +136,6 @@ __device__ __forceinline__ void finish_segment(const RowArgs& a, uint32_t seg, c
   uint4* dp = reinterpret_cast<uint4*>(a.states_out + slot * (uint64_t)(W + 2) * 4);
 #pragma unroll
   for (int q = 0; q < (W + 2) / 4; ++q) dp[q] = make_uint4(outw[4 * q], outw[4 * q + 1], outw[4 * q + 2], outw[4 * q + 3]);
-  n_applied += (a.seg_offsets[(uint64_t)seg + 1] - a.seg_offsets[seg]) >> 6;
 }
 
 // state of an aggregate that received no event in this batch: unchanged, per-batch flags cleared
@@ -160,8 +164,9 @@ __host__ __device__ constexpr int warp_smem_bytes() {
          + 32 * 4;           // head bitmap (R words used) + pad
 }
 
-template <int W, int R, int NSTAGE>
-__global__ void __launch_bounds__(kRunThreads) fold_runs_kernel(const __grid_constant__ RowArgs a, const __grid_constant__ RowProgram pg) {
+template <int W, int R, int NSTAGE, int NS, int MINB>
+__global__ void __launch_bounds__(kRunThreads, MINB) fold_runs_kernel(const __grid_constant__ RowArgs a, const __grid_constant__ RowProgram pg) {
+  static_assert(R % 2 == 0 && 8 % R == 0, "R in {2,4,8}");
   constexpr int STEP_BYTES = 2048 * R;
   constexpr int STEP_RECS = 32 * R;
   extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -216,24 +221,27 @@ __global__ void __launch_bounds__(kRunThreads) fold_runs_kernel(const __grid_con
   uint32_t inh_seg = 0;
   Xf<W> inh_t = identity<W>();
   Xf<W> carry = identity<W>();         // open transformer at the end of the previous step
-  unsigned long long n_applied = 0;
 
   // ---- staging: lane l, copy q of a step moves the 16-byte chunk g = q*32 + l (source order) to its
   //      swizzled place: record j = g>>2, chunk c = g&3 -> line j>>1, position (4*(j&1)+c) ^ ((j/R)&7)
   const uint8_t* src_lane = a.events + base + (uint64_t)lane * 16;
-  const uint32_t dst_lane = (uint32_t)(lane >> 3) * 128u;
   const uint32_t low_pos = (uint32_t)(4 * ((lane >> 2) & 1) + (lane & 3));
+  const uint32_t lane_jr = (uint32_t)(lane >> 2) / R;
+  uint32_t dst_q[4 * R];  // smem offset (within a stage) of copy q
+#pragma unroll
+  for (int q = 0; q < 4 * R; ++q)
+    dst_q[q] = (uint32_t)q * 512u + (uint32_t)(lane >> 3) * 128u + ((low_pos ^ (((uint32_t)(q * 8) / R + lane_jr) & 7u)) << 4);
   auto issue_step = [&](uint64_t s, int stage) {
     const uint64_t sbyte = s * (uint64_t)STEP_BYTES;
     const uint8_t* src = src_lane + sbyte;
-    const uint32_t dst = stage0 + (uint32_t)stage * STEP_BYTES + dst_lane;
-    const bool full = sbyte + STEP_BYTES <= total_bytes;  // uniform
+    const uint32_t dst = stage0 + (uint32_t)stage * STEP_BYTES;
+    if (sbyte + STEP_BYTES <= total_bytes) {  // uniform: the whole step lies inside the log
 #pragma unroll
-    for (int q = 0; q < 4 * R; ++q) {
-      const uint32_t j_over_r = (uint32_t)(q * 8) / R + (uint32_t)(lane >> 2) / R;  // (q*8 + (lane>>2)) / R, exact for R in {1,2,4,8}
-      const uint32_t pos = low_pos ^ (j_over_r & 7u);
-      if (full || sbyte + (uint64_t)q * 512 + (uint64_t)lane * 16 < total_bytes)
-        cp_async16(dst + (uint32_t)q * 512u + pos * 16u, src + (uint64_t)q * 512);
+      for (int q = 0; q < 4 * R; ++q) cp_async16(dst + dst_q[q], src + q * 512);
+    } else {
+#pragma unroll
+      for (int q = 0; q < 4 * R; ++q)
+        if (sbyte + (uint64_t)q * 512 + (uint64_t)lane * 16 < total_bytes) cp_async16(dst + dst_q[q], src + q * 512);
     }
   };
   // prologue: NSTAGE-1 steps in flight
@@ -245,11 +253,23 @@ __global__ void __launch_bounds__(kRunThreads) fold_runs_kernel(const __grid_con
     }
   }
 
-  // where lane i finds word (c,k) of its record t: line = (R*i+t)>>1, position (4*((R*i+t)&1)+c) ^ (i&7)
-  uint32_t slot_c[kMaxSlots], slot_k[kMaxSlots];
+  // where lane i finds word (c,k) of a record of parity par: byte (((4*par + c) ^ (i&7)) << 4) + 4k of its 128-byte line
+  uint32_t soff[2][NS];
 #pragma unroll
-  for (int s = 0; s < kMaxSlots; ++s) { slot_c[s] = pg.slot_word[s] >> 2; slot_k[s] = pg.slot_word[s] & 3u; }
-  const uint32_t n_slots = pg.n_slots;
+  for (int s = 0; s < NS; ++s) {
+    const uint32_t c = pg.slot_word[s] >> 2, k = pg.slot_word[s] & 3u;
+    soff[0][s] = ((c ^ (uint32_t)(lane & 7)) << 4) + (k << 2);
+    soff[1][s] = (((4u + c) ^ (uint32_t)(lane & 7)) << 4) + (k << 2);
+  }
+  // boundary window: lane j holds off[kc+j] and off[kc+j+1]; reloaded right after boundaries are consumed,
+  // so the values a step needs were requested one step earlier
+  uint64_t win_b = ~0ull, win_bn = ~0ull;
+  auto load_window = [&]() {
+    const uint64_t k = kc + lane;
+    win_b = k <= n_seg ? a.seg_offsets[k] : ~0ull;
+    win_bn = k < n_seg ? a.seg_offsets[k + 1] : ~0ull;
+  };
+  if (has_span) load_window();
 
   int stage = 0;
   for (uint64_t step = step0; step < step_end; ++step) {
@@ -272,8 +292,7 @@ __global__ void __launch_bounds__(kRunThreads) fold_runs_kernel(const __grid_con
     __syncwarp();
     while (true) {
       const uint64_t k = kc + lane;
-      const uint64_t b = k <= n_seg ? a.seg_offsets[k] : ~0ull;
-      const uint64_t bn = k < n_seg ? a.seg_offsets[k + 1] : ~0ull;
+      const uint64_t b = win_b, bn = win_bn;  // window at kc, loaded one step ahead
       const uint64_t d = b - sb;  // >= 0 for every unconsumed boundary
       const bool in = d < (uint64_t)span;
       if (in) {
@@ -285,6 +304,7 @@ __global__ void __launch_bounds__(kRunThreads) fold_runs_kernel(const __grid_con
       }
       const int cnt = __popc(__ballot_sync(0xffffffffu, in));
       kc += cnt;
+      if (cnt) load_window();
       if (cnt < 32) break;
     }
     __syncwarp();
@@ -308,18 +328,14 @@ __global__ void __launch_bounds__(kRunThreads) fold_runs_kernel(const __grid_con
       if (hbits & (1u << t)) {
         const uint32_t eseg = hs_end[p];
         if (!have_first) { first = cur; first_seg = eseg; have_first = true; }
-        else if (eseg != 0xffffffffu) finish_segment<W>(a, eseg, cur, n_applied);  // began and ended inside this run
+        else if (eseg != 0xffffffffu) finish_segment<W>(a, eseg, cur);  // began and ended inside this run
         cur = identity<W>();
       }
       if (p < nvalid) {
         const uint32_t rec = sbase + (uint32_t)(p >> 1) * 128u;
-        const uint32_t par4 = (uint32_t)(p & 1) * 4u;
-        uint32_t sv[kMaxSlots];
+        uint32_t sv[NS];
 #pragma unroll
-        for (int s = 0; s < kMaxSlots; ++s) {
-          sv[s] = 0;
-          if (s < (int)n_slots) sv[s] = lds32(rec + (((par4 + slot_c[s]) ^ (uint32_t)(lane & 7)) << 4) + (slot_k[s] << 2));
-        }
+        for (int s = 0; s < NS; ++s) sv[s] = lds32(rec + soff[t & 1][s]);  // p&1 == t&1: R is even
         const uint32_t type = sv[0];
         uint4 e0 = make_uint4(0, 0, 0, 0);
         if (type < 16u) e0 = *reinterpret_cast<const uint4*>(tab + type * 8);
@@ -337,7 +353,7 @@ __global__ void __launch_bounds__(kRunThreads) fold_runs_kernel(const __grid_con
           for (int w = 0; w < W; ++w) {
             uint32_t val = 0;
 #pragma unroll
-            for (int s = 1; s < kMaxSlots; ++s) val = ((spec[w] >> 3) == (uint32_t)s) ? sv[s] : val;
+            for (int s = 1; s < NS; ++s) val = ((spec[w] >> 3) == (uint32_t)s) ? sv[s] : val;
             if (spec[w] & 4u) val = 0u - val;
             const uint32_t mode = spec[w] & 3u;
             if (mode == 2u) cur.v[w] = val;
@@ -371,7 +387,7 @@ __global__ void __launch_bounds__(kRunThreads) fold_runs_kernel(const __grid_con
       // the very first head of the span ends a segment that began in an earlier span: look-back needed
       const bool is_span_first = !span_has_head && (lane_heads & ((1u << lane) - 1u)) == 0;
       if (is_span_first && gw != 0) { inh_t = tot; inh_seg = first_seg; inh_pending = true; }
-      else finish_segment<W>(a, first_seg, tot, n_applied);
+      else finish_segment<W>(a, first_seg, tot);
     }
     if (lane_heads) {
       // the pending look-back lives in the lane that saw the span's first head: move it to lane 0
@@ -395,7 +411,7 @@ __global__ void __launch_bounds__(kRunThreads) fold_runs_kernel(const __grid_con
     for (uint64_t k = kc + lane; k < n_seg; k += 32) finish_empty<W>(a, (uint32_t)k);  // segments kc..n_seg-1 are empty
     if (kc >= 1 && total_steps > 0) {
       // segment kc-1 is the last non-empty one; its transformer is the carry
-      if (span_has_head || gw == 0) { if (lane == 0) finish_segment<W>(a, (uint32_t)(kc - 1), carry, n_applied); }
+      if (span_has_head || gw == 0) { if (lane == 0) finish_segment<W>(a, (uint32_t)(kc - 1), carry); }
       else end_needs_lookback = true;  // the whole span lies inside that segment
     }
   }
@@ -430,23 +446,97 @@ __global__ void __launch_bounds__(kRunThreads) fold_runs_kernel(const __grid_con
         pre = compose(e, pre);
         if (tailw & 4u) break;
       }
-      if (inh_pending) finish_segment<W>(a, inh_seg, compose(pre, inh_t), n_applied);
-      if (end_needs_lookback) finish_segment<W>(a, (uint32_t)(kc - 1), compose(pre, carry), n_applied);
+      if (inh_pending) finish_segment<W>(a, inh_seg, compose(pre, inh_t));
+      if (end_needs_lookback) finish_segment<W>(a, (uint32_t)(kc - 1), compose(pre, carry));
     }
   }
-  for (int o = 16; o > 0; o >>= 1) n_applied += __shfl_xor_sync(0xffffffffu, n_applied, o);
-  if (lane == 0 && n_applied) atomicAdd(a.counters + 0, n_applied);
+  // every record of the span was applied; records of throwing segments are taken back by the replay below
+  if (lane == 0 && has_span) {
+    const uint64_t we = base + step_end * (uint64_t)STEP_BYTES < a.log_end ? base + step_end * (uint64_t)STEP_BYTES : a.log_end;
+    atomicAdd(a.counters + 0, (unsigned long long)((we - wb) >> 6));
+  }
+
+  // ---- grid barrier (every warp of the grid is resident), then exact replay of the throwing segments ----
+  // A segment whose handler threw keeps its pre-batch state and reports the index of the throwing event
+  // (PersistentActor.scala:260-263); that needs the strictly sequential walk, done here one lane per segment.
+  if (lane == 0) {
+    __threadfence();
+    atomicAdd(a.counters + 6, 1ull);
+    while (ld_volatile_u64(a.counters + 6) < n_warps) { __nanosleep(128); }
+    __threadfence();
+  }
+  __syncwarp();
+  if (gw == 0 && lane < 8) a.counters_next[lane] = 0ull;  // the next fold starts from clean counters without a memset
+  unsigned long long n_redo = ld_volatile_u64(a.counters + 3);
+  if (n_redo == 0) return;
+  if (n_redo > a.redo_cap) n_redo = a.redo_cap;  // overflow: the host re-runs the whole fold sequentially
+  unsigned long long n_err = 0, n_dropped = 0;
+  for (unsigned long long i = gw * 32 + lane; i < n_redo; i += n_warps * 32) {
+    const uint32_t seg = a.redo_ids[i];
+    const uint64_t b = a.seg_offsets[seg], e = a.seg_offsets[(uint64_t)seg + 1];
+    const uint64_t slot = a.seg_ids ? (uint64_t)a.seg_ids[seg] : (uint64_t)seg;
+    uint32_t st[W], ex0 = 0;
+#pragma unroll
+    for (int w = 0; w < W; ++w) st[w] = 0;
+    if (a.states_in) {
+      const uint32_t* sp = reinterpret_cast<const uint32_t*>(a.states_in + slot * (uint64_t)(W + 2) * 4);
+      ex0 = sp[W] & SGR_ST_EXISTS;
+#pragma unroll
+      for (int w = 0; w < W; ++w) st[w] = ex0 ? sp[w] : 0u;
+    }
+    uint32_t old[W];
+#pragma unroll
+    for (int w = 0; w < W; ++w) old[w] = st[w];
+    uint32_t exn = ex0, k = 0;
+    bool threw = false;
+    for (uint64_t pos = b; pos < e; pos += 64, ++k) {
+      const uint32_t* rec = reinterpret_cast<const uint32_t*>(a.events + pos);
+      const uint32_t type = rec[pg.slot_word[0]];
+      const uint32_t fl = type < 16u ? tab[type * 8] : 0u;
+      if (!(fl & 1u)) { threw = true; break; }
+      if (fl & 2u) { exn = 0u; for (int w = 0; w < W; ++w) st[w] = 0u; continue; }  // tombstone
+#pragma unroll
+      for (int w = 0; w < W; ++w) {
+        const uint32_t spec = tab[type * 8 + 1 + w];
+        const uint32_t mode = spec & 3u;
+        uint32_t val = (spec >> 3) ? rec[pg.slot_word[spec >> 3]] : 0u;
+        if (spec & 4u) val = 0u - val;
+        if (mode == 2u) st[w] = val; else if (mode == 1u) st[w] = (exn ? st[w] : 0u) + val;
+        else if (!exn) st[w] = 0u;
+      }
+      exn = SGR_ST_EXISTS;
+    }
+    uint32_t* dp = reinterpret_cast<uint32_t*>(a.states_out + slot * (uint64_t)(W + 2) * 4);
+    if (threw) {
+#pragma unroll
+      for (int w = 0; w < W; ++w) dp[w] = old[w];
+      dp[W] = ex0 | SGR_ST_ERROR;
+      dp[W + 1] = k;
+      ++n_err;
+      n_dropped += ((e - b) >> 6) - k;
+    } else {
+      uint32_t changed = exn != ex0;
+#pragma unroll
+      for (int w = 0; w < W; ++w) { if (!exn) st[w] = 0u; if (exn && ex0) changed |= st[w] != old[w]; dp[w] = st[w]; }
+      dp[W] = exn | (changed ? SGR_ST_CHANGED : 0u);
+      dp[W + 1] = 0u;
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    n_err += __shfl_xor_sync(0xffffffffu, n_err, o);
+    n_dropped += __shfl_xor_sync(0xffffffffu, n_dropped, o);
+  }
+  if (lane == 0) {
+    if (n_err) atomicAdd(a.counters + 1, n_err);
+    if (n_dropped) atomicAdd(a.counters + 4, n_dropped);
+  }
 }
 
 typedef void (*RunKernel)(const RowArgs, const RowProgram);
-struct RunVariant { RunKernel k; int r, nstage; const char* name; };
+struct RunVariant { RunKernel k[3]; int r, nstage; const char* name; };  // k[i]: NS = 2, 3, kMaxSlots
+#define RUN_VARIANT(R, ST, MINB) {{fold_runs_kernel<2, R, ST, 2, MINB>, fold_runs_kernel<2, R, ST, 3, MINB>, fold_runs_kernel<2, R, ST, kMaxSlots, MINB>}, R, ST, "runs W2 R" #R " st" #ST}
 const RunVariant kRunVariants[] = {
-    {fold_runs_kernel<2, 4, 3>, 4, 3, "runs W2 R4 st3"},
-    {fold_runs_kernel<2, 4, 2>, 4, 2, "runs W2 R4 st2"},
-    {fold_runs_kernel<2, 8, 2>, 8, 2, "runs W2 R8 st2"},
-    {fold_runs_kernel<2, 2, 4>, 2, 4, "runs W2 R2 st4"},
-    {fold_runs_kernel<2, 8, 3>, 8, 3, "runs W2 R8 st3"},
-    {fold_runs_kernel<2, 2, 3>, 2, 3, "runs W2 R2 st3"},
+    RUN_VARIANT(4, 2, 3), RUN_VARIANT(4, 1, 5), RUN_VARIANT(2, 2, 5), RUN_VARIANT(2, 1, 5), RUN_VARIANT(4, 3, 2), RUN_VARIANT(8, 1, 3), RUN_VARIANT(2, 3, 4),
 };
 constexpr int kNumRunVariants = sizeof(kRunVariants) / sizeof(kRunVariants[0]);
 
@@ -454,18 +544,22 @@ size_t variant_smem(int v) {
   const int r = kRunVariants[v].r, ns = kRunVariants[v].nstage;
   return (size_t)kRunWarps * ((size_t)ns * 2048 * r + 2 * 32 * r * 4 + 32 * 4);
 }
+RunKernel variant_kernel(int v, const RowProgram& prog) {
+  return kRunVariants[v].k[prog.n_slots <= 2 ? 0 : (prog.n_slots <= 3 ? 1 : 2)];
+}
 
 }  // namespace
 
 int run_variant_count() { return kNumRunVariants; }
 const char* run_variant_name(int v) { return (v >= 0 && v < kNumRunVariants) ? kRunVariants[v].name : "?"; }
 
-int run_kernel_max_grid(int num_sms, int variant) {
+int run_kernel_max_grid(int num_sms, int variant, const RowProgram& prog) {
   if (variant < 0 || variant >= kNumRunVariants) variant = 0;
   const size_t smem = variant_smem(variant);
-  cudaFuncSetAttribute(kRunVariants[variant].k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  RunKernel k = variant_kernel(variant, prog);
+  cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   int per_sm = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kRunVariants[variant].k, kRunThreads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kRunThreads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
   return per_sm * num_sms;
 }
 
@@ -479,9 +573,8 @@ cudaError_t launch_fold_runs(const RowArgs& args, const RowProgram& prog, int va
   if (prog.user_words != 2) return cudaErrorInvalidValue;
   if (variant < 0 || variant >= kNumRunVariants) variant = 0;
   const size_t smem = variant_smem(variant);
-  cudaError_t e = cudaFuncSetAttribute(kRunVariants[variant].k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  kRunVariants[variant].k<<<grid, kRunThreads, smem, stream>>>(args, prog);
+  RunKernel k = variant_kernel(variant, prog);  // its smem attribute was set by run_kernel_max_grid
+  k<<<grid, kRunThreads, smem, stream>>>(args, prog);
   return cudaGetLastError();
 }
 

@@ -137,7 +137,7 @@ def test_sequential_kernel_variants(variant):
     assert_same(got, want)
 
 
-@pytest.mark.parametrize("run_variant", range(6))
+@pytest.mark.parametrize("run_variant", range(7))
 def test_runs_kernel_variants(run_variant):
     rng = np.random.default_rng(50 + run_variant)
     counts = np.concatenate([rng.integers(0, 50, size=3000), [60_000], rng.integers(0, 4, size=500)])
