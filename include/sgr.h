@@ -246,6 +246,34 @@ int32_t sgr_set_option(sgr_engine* e, const char* name, int64_t value);
 /* The CUDA stream (cudaStream_t) the engine launches on, so callers can record events. */
 int32_t sgr_stream(sgr_engine* e, void** stream);
 
+/* ------------------------------------------------------------------ multi-GPU (one process per GPU, one node)
+ * Aggregates are hash-partitioned across ranks exactly as Surge shards them across nodes
+ * (aggregateId -> partition -> owner): partition_of_agg[g] is
+ * KafkaPartitionProvider.partitionForKey of global aggregate g (COMMON/kafka/KafkaPartitioner.scala:7-9)
+ * and the owner rank is partition % nranks. Each rank feeds the records of ITS source partitions in arrival
+ * order (records carry the GLOBAL aggregate index at +8); one exchange over NVLink replaces the broker
+ * shuffle (KafkaProducerHelperCommon.getPartitionFor, COMMON/kafka/KafkaProducer.scala:45-57). */
+typedef struct sgr_dist_stats {
+  uint64_t n_sent, n_sent_remote, n_recv, n_local_aggregates;
+  float ms_count, ms_counts_exchange, ms_scatter, ms_exchange, ms_group, ms_fold;
+  uint32_t reserved[6];
+} sgr_dist_stats;
+
+int32_t sgr_dist_unique_id(void* out128);                       /* rank 0: a 128-byte NCCL unique id to hand to the others */
+int32_t sgr_dist_init(sgr_engine* e, int32_t rank, int32_t nranks, const void* unique_id128,
+                      uint64_t recv_capacity_records);
+int32_t sgr_dist_set_partitions(sgr_engine* e, const uint32_t* partition_of_agg, uint64_t n_global_agg);
+/* fused path: every rank exports its receive buffer (64-byte CUDA IPC handle), the host exchanges the
+ * handles, every rank imports all nranks of them (own slot ignored). */
+int32_t sgr_dist_ipc_export(sgr_engine* e, void* out64);
+int32_t sgr_dist_ipc_import(sgr_engine* e, const void* handles64_by_rank);
+/* Route + exchange + stable group-by + fold. fused != 0: the route kernel writes each record straight into
+ * its owner's receive buffer over NVLink (needs the IPC import); fused == 0: pack + one NCCL all-to-all. */
+int32_t sgr_dist_route_and_fold(sgr_engine* e, const void* d_records, uint64_t n_records, int32_t fused);
+int32_t sgr_dist_get_stats(sgr_engine* e, sgr_dist_stats* out);
+/* global aggregate index of each local state slot (host copy, n_local u32) */
+int32_t sgr_dist_local_aggregates(sgr_engine* e, uint32_t* out, uint64_t cap, uint64_t* n_local);
+
 /* ------------------------------------------------------------------ partitioner
  * KafkaPartitionProvider.partitionForKey = abs(MurmurHash3.stringHash(s) % n)
  * (COMMON/kafka/KafkaPartitioner.scala:7-9) over key.takeWhile(_ != ':')
@@ -253,6 +281,8 @@ int32_t sgr_stream(sgr_engine* e, void** stream);
 int32_t sgr_string_hash_utf16(const uint16_t* units, uint32_t n);
 int32_t sgr_partition_for_key_utf8(const uint8_t* key, uint32_t klen, uint32_t num_partitions,
                                    int32_t up_to_colon, int32_t* partition);
+int32_t sgr_partitions_for_keys(const uint8_t* keys, const uint32_t* key_offsets, uint64_t n, uint32_t num_partitions,
+                                int32_t up_to_colon, uint32_t* partition_of);
 
 #ifdef __cplusplus
 }

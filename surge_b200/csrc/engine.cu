@@ -15,6 +15,7 @@
 
 #include "../../include/sgr.h"
 #include "devbuf.h"
+#include "dist.cuh"
 #include "fold_kernels.cuh"
 #include "fold_rows.cuh"
 #include "group_kernels.cuh"
@@ -89,6 +90,9 @@ struct sgr_engine {
 
   sgr_stats stats{};
   std::string last_error;
+
+  DistState* dist = nullptr;
+  sgr_dist_stats dstats{};
 
   KeyTable keys;
   std::mutex snap_mu;
@@ -366,6 +370,7 @@ int32_t sgr_destroy(sgr_engine* e) {
   e->own_events.release(); e->own_offsets.release(); e->states.release(); e->counters.release();
   e->inc_records.release(); e->inc_offsets.release(); e->inc_ids.release(); e->inc_prev_ids.release();
   e->group.release();
+  if (e->dist) dist_destroy(e->dist);
   e->part_flags.release(); e->part_data.release(); e->redo_ids.release(); e->run_counters.release();
   cudaEventDestroy(e->ev0); cudaEventDestroy(e->ev1); cudaEventDestroy(e->ev2); cudaEventDestroy(e->ev3);
   cudaStreamDestroy(e->stream);
@@ -666,6 +671,99 @@ int32_t sgr_get_stats(sgr_engine* e, sgr_stats* out) {
   if (!e || !out) return SGR_ERR_INVALID;
   if (e->fold_pending) { int32_t rc = use_device(e); if (rc) return rc; rc = finish_fold(e); if (rc) return rc; }
   *out = e->stats;
+  return SGR_OK;
+}
+
+// ------------------------------------------------------------------ multi-GPU
+int32_t sgr_dist_unique_id(void* out128) {
+  if (!out128) return SGR_ERR_INVALID;
+  std::string err;
+  int rc = dist_unique_id(out128, &err);
+  if (rc) return fail(nullptr, rc, "%s", err.c_str());
+  return SGR_OK;
+}
+
+int32_t sgr_dist_init(sgr_engine* e, int32_t rank, int32_t nranks, const void* unique_id128, uint64_t recv_capacity_records) {
+  if (!e || (nranks > 1 && !unique_id128)) return fail(e, SGR_ERR_INVALID, "null argument");
+  int32_t rc = use_device(e); if (rc) return rc;
+  if (e->dist) { dist_destroy(e->dist); e->dist = nullptr; }
+  e->dist = dist_create();
+  std::string err;
+  int r = dist_init(e->dist, rank, nranks, unique_id128, recv_capacity_records, e->stream, &err);
+  if (r) return fail(e, r, "%s", err.c_str());
+  return SGR_OK;
+}
+
+int32_t sgr_dist_set_partitions(sgr_engine* e, const uint32_t* partition_of_agg, uint64_t n_global_agg) {
+  if (!e || !partition_of_agg) return fail(e, SGR_ERR_INVALID, "null argument");
+  if (!e->dist) return fail(e, SGR_ERR_NOT_LOADED, "call sgr_dist_init first");
+  int32_t rc = before_load(e); if (rc) return rc;
+  std::string err;
+  int r = dist_set_partitions(e->dist, partition_of_agg, n_global_agg, e->stream, &err);
+  if (r) return fail(e, r, "%s", err.c_str());
+  return SGR_OK;
+}
+
+int32_t sgr_dist_ipc_export(sgr_engine* e, void* out64) {
+  if (!e || !out64 || !e->dist) return fail(e, SGR_ERR_INVALID, "null argument / no dist state");
+  int32_t rc = use_device(e); if (rc) return rc;
+  std::string err;
+  int r = dist_ipc_export(e->dist, out64, &err);
+  if (r) return fail(e, r, "%s", err.c_str());
+  return SGR_OK;
+}
+
+int32_t sgr_dist_ipc_import(sgr_engine* e, const void* handles64_by_rank) {
+  if (!e || !handles64_by_rank || !e->dist) return fail(e, SGR_ERR_INVALID, "null argument / no dist state");
+  int32_t rc = use_device(e); if (rc) return rc;
+  std::string err;
+  int r = dist_ipc_import(e->dist, handles64_by_rank, &err);
+  if (r) return fail(e, r, "%s", err.c_str());
+  return SGR_OK;
+}
+
+int32_t sgr_dist_route_and_fold(sgr_engine* e, const void* d_records, uint64_t n_records, int32_t fused) {
+  if (!e || (!d_records && n_records)) return fail(e, SGR_ERR_INVALID, "null argument");
+  if (!e->has_program) return fail(e, SGR_ERR_NO_PROGRAM, "register a fold program first");
+  if (!e->dist) return fail(e, SGR_ERR_NOT_LOADED, "call sgr_dist_init first");
+  if (e->program.record_kind != SGR_REC_FIXED64) return fail(e, SGR_ERR_UNSUPPORTED, "routing takes fixed 64-byte records");
+  int32_t rc = before_load(e); if (rc) return rc;
+  std::string err;
+  uint64_t n_recv = 0;
+  int r = dist_route(e->dist, (const uint8_t*)d_records, n_records, fused != 0, (unsigned long long*)e->counters.p, e->stream, &n_recv, &err);
+  if (r) return fail(e, r, "%s", err.c_str());
+  e->stats.ms_h2d = 0;
+  rc = load_unsorted_impl(e, dist_recv_buffer(e->dist), n_recv, dist_n_local(e->dist));
+  if (rc) return rc;
+  e->states_valid = false;
+  rc = sgr_fold(e);
+  if (rc) return rc;
+  const DistStats* ds = dist_stats(e->dist);
+  e->dstats = sgr_dist_stats{};
+  e->dstats.n_sent = ds->n_sent; e->dstats.n_sent_remote = ds->n_sent_remote; e->dstats.n_recv = ds->n_recv;
+  e->dstats.n_local_aggregates = dist_n_local(e->dist);
+  e->dstats.ms_count = ds->ms_count; e->dstats.ms_counts_exchange = ds->ms_counts_exchange;
+  e->dstats.ms_scatter = ds->ms_scatter; e->dstats.ms_exchange = ds->ms_exchange;
+  e->dstats.ms_group = e->stats.ms_group; e->dstats.ms_fold = e->stats.ms_fold;
+  return SGR_OK;
+}
+
+int32_t sgr_dist_get_stats(sgr_engine* e, sgr_dist_stats* out) {
+  if (!e || !out) return SGR_ERR_INVALID;
+  *out = e->dstats;
+  return SGR_OK;
+}
+
+int32_t sgr_dist_local_aggregates(sgr_engine* e, uint32_t* out, uint64_t cap, uint64_t* n_local) {
+  if (!e || !e->dist) return fail(e, SGR_ERR_INVALID, "no dist state");
+  const uint64_t n = dist_n_local(e->dist);
+  if (n_local) *n_local = n;
+  if (out) {
+    if (cap < n) return fail(e, SGR_ERR_CAPACITY, "need room for %llu indices", (unsigned long long)n);
+    int32_t rc = use_device(e); if (rc) return rc;
+    CUDA_TRY(e, cudaMemcpyAsync(out, dist_global_of_local(e->dist), n * 4, cudaMemcpyDeviceToHost, e->stream));
+    CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+  }
   return SGR_OK;
 }
 

@@ -67,3 +67,16 @@ extern "C" int32_t sgr_partition_for_key_utf8(const uint8_t* key, uint32_t klen,
   *partition = r < 0 ? -r : r;
   return SGR_OK;
 }
+
+// Vectorised form for a whole key table: partition_of[i] for key i = keys[key_offsets[i] .. key_offsets[i+1]).
+extern "C" int32_t sgr_partitions_for_keys(const uint8_t* keys, const uint32_t* key_offsets, uint64_t n, uint32_t num_partitions,
+                                           int32_t up_to_colon, uint32_t* partition_of) {
+  if ((!keys && n && key_offsets[n]) || !key_offsets || !partition_of) return SGR_ERR_INVALID;
+  for (uint64_t i = 0; i < n; ++i) {
+    int32_t p = 0;
+    const int32_t rc = sgr_partition_for_key_utf8(keys + key_offsets[i], key_offsets[i + 1] - key_offsets[i], num_partitions, up_to_colon, &p);
+    if (rc != SGR_OK) return rc;
+    partition_of[i] = (uint32_t)p;
+  }
+  return SGR_OK;
+}

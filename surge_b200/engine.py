@@ -183,6 +183,42 @@ class ReplayEngine:
                                          C.byref(flags), C.byref(err)))
         return (bytes(buf.raw[:outlen.value]) if exists.value else None), int(flags.value), int(err.value)
 
+    # -- multi-GPU (one process per GPU)
+    def dist_init(self, rank: int, nranks: int, unique_id: Optional[bytes], recv_capacity_records: int) -> None:
+        buf = C.create_string_buffer(unique_id, 128) if unique_id else None
+        self._ck(self._lib.sgr_dist_init(self._h, rank, nranks, buf, recv_capacity_records))
+
+    def dist_set_partitions(self, partition_of_agg: np.ndarray) -> None:
+        p = np.ascontiguousarray(partition_of_agg, dtype=np.uint32)
+        self._ck(self._lib.sgr_dist_set_partitions(self._h, p.ctypes.data, len(p)))
+
+    def dist_ipc_export(self) -> bytes:
+        buf = C.create_string_buffer(64)
+        self._ck(self._lib.sgr_dist_ipc_export(self._h, buf))
+        return bytes(buf.raw)
+
+    def dist_ipc_import(self, handles: Sequence[bytes]) -> None:
+        blob = C.create_string_buffer(b"".join(handles), 64 * len(handles))
+        self._ck(self._lib.sgr_dist_ipc_import(self._h, blob))
+
+    def dist_route_and_fold(self, records, fused: bool) -> None:
+        """records: CUDA tensor of fixed 64-byte records in arrival order carrying GLOBAL aggregate indices."""
+        r = records.contiguous().view(-1)
+        self._keep = [r]
+        self._ck(self._lib.sgr_dist_route_and_fold(self._h, r.data_ptr(), r.numel() * r.element_size() // 64, 1 if fused else 0))
+
+    def dist_stats(self) -> N.sgr_dist_stats:
+        s = N.sgr_dist_stats()
+        self._ck(self._lib.sgr_dist_get_stats(self._h, C.byref(s)))
+        return s
+
+    def dist_local_aggregates(self) -> np.ndarray:
+        n = C.c_uint64()
+        self._ck(self._lib.sgr_dist_local_aggregates(self._h, None, 0, C.byref(n)))
+        out = np.zeros(int(n.value), dtype=np.uint32)
+        self._ck(self._lib.sgr_dist_local_aggregates(self._h, out.ctypes.data, len(out), C.byref(n)))
+        return out
+
     def stats(self) -> N.sgr_stats:
         s = N.sgr_stats()
         self._ck(self._lib.sgr_get_stats(self._h, C.byref(s)))

@@ -57,6 +57,12 @@ class sgr_config(C.Structure):
     _fields_ = [("device", C.c_int32), ("flags", C.c_uint32), ("reserved", C.c_uint64 * 6)]
 
 
+class sgr_dist_stats(C.Structure):
+    _fields_ = [("n_sent", C.c_uint64), ("n_sent_remote", C.c_uint64), ("n_recv", C.c_uint64), ("n_local_aggregates", C.c_uint64),
+                ("ms_count", C.c_float), ("ms_counts_exchange", C.c_float), ("ms_scatter", C.c_float), ("ms_exchange", C.c_float),
+                ("ms_group", C.c_float), ("ms_fold", C.c_float), ("reserved", C.c_uint32 * 6)]
+
+
 class sgr_stats(C.Structure):
     _fields_ = [("n_aggregates", C.c_uint64), ("n_events", C.c_uint64), ("event_bytes", C.c_uint64),
                 ("algorithmic_bytes", C.c_uint64), ("n_errors", C.c_uint64), ("n_long_segments", C.c_uint64),
@@ -92,6 +98,15 @@ ABI = [
     ("sgr_get_stats", C.c_int32, [_P, C.POINTER(sgr_stats)]),
     ("sgr_set_option", C.c_int32, [_P, C.c_char_p, C.c_int64]),
     ("sgr_stream", C.c_int32, [_P, C.POINTER(_P)]),
+    ("sgr_dist_unique_id", C.c_int32, [_P]),
+    ("sgr_dist_init", C.c_int32, [_P, C.c_int32, C.c_int32, _P, C.c_uint64]),
+    ("sgr_dist_set_partitions", C.c_int32, [_P, _P, C.c_uint64]),
+    ("sgr_dist_ipc_export", C.c_int32, [_P, _P]),
+    ("sgr_dist_ipc_import", C.c_int32, [_P, _P]),
+    ("sgr_dist_route_and_fold", C.c_int32, [_P, _P, C.c_uint64, C.c_int32]),
+    ("sgr_dist_get_stats", C.c_int32, [_P, C.POINTER(sgr_dist_stats)]),
+    ("sgr_dist_local_aggregates", C.c_int32, [_P, _P, C.c_uint64, C.POINTER(C.c_uint64)]),
+    ("sgr_partitions_for_keys", C.c_int32, [_P, _P, C.c_uint64, C.c_uint32, C.c_int32, _P]),
     ("sgr_string_hash_utf16", C.c_int32, [_P, C.c_uint32]),
     ("sgr_partition_for_key_utf8", C.c_int32, [_P, C.c_uint32, C.c_uint32, C.c_int32, C.POINTER(C.c_int32)]),
 ]
