@@ -1,0 +1,74 @@
+/* sgr_jni.c — JNI glue between surge.gpu.Native (shim/scala) and include/sgr.h.
+ * Built only where a JDK exists (needs <jni.h>):  gcc -shared -fPIC -I$JAVA_HOME/include -I$JAVA_HOME/include/linux
+ *     -I../../include sgr_jni.c -L../../surge_b200/lib -lsgr -o libsgr_jni.so
+ * The build image of this repository has no JDK, so this file is guarded and compiled nowhere here; all logic lives
+ * behind the C ABI, which the Python/ctypes tests cover. */
+#if defined(__has_include)
+#if __has_include(<jni.h>)
+#include <jni.h>
+#include <stdint.h>
+#include <string.h>
+
+#include "sgr.h"
+
+#define H(h) ((sgr_engine*)(intptr_t)(h))
+
+static void throw_for(JNIEnv* env, sgr_engine* e, int32_t rc) {
+  const char* cls = rc == SGR_ERR_STATE ? "org/apache/kafka/streams/errors/InvalidStateStoreException" : "java/lang/RuntimeException";
+  (*env)->ThrowNew(env, (*env)->FindClass(env, cls), sgr_last_error(e));
+}
+
+JNIEXPORT jlong JNICALL Java_surge_gpu_Native_00024_create(JNIEnv* env, jobject o, jint device) {
+  sgr_config cfg; memset(&cfg, 0, sizeof cfg); cfg.device = device;
+  sgr_engine* e = 0;
+  int32_t rc = sgr_create(&cfg, &e);
+  if (rc != SGR_OK) { throw_for(env, 0, rc); return 0; }  /* SGR_ERR_NO_DEVICE: fail loudly, never fall back */
+  return (jlong)(intptr_t)e;
+}
+JNIEXPORT jint JNICALL Java_surge_gpu_Native_00024_destroy(JNIEnv* env, jobject o, jlong h) { return sgr_destroy(H(h)); }
+JNIEXPORT jstring JNICALL Java_surge_gpu_Native_00024_lastError(JNIEnv* env, jobject o, jlong h) { return (*env)->NewStringUTF(env, sgr_last_error(H(h))); }
+JNIEXPORT jint JNICALL Java_surge_gpu_Native_00024_registerProgram(JNIEnv* env, jobject o, jlong h, jobject prog) {
+  return sgr_register_program(H(h), (const sgr_fold_program*)(*env)->GetDirectBufferAddress(env, prog));
+}
+JNIEXPORT jint JNICALL Java_surge_gpu_Native_00024_loadEvents(JNIEnv* env, jobject o, jlong h, jobject ev, jlong nbytes, jobject offs, jlong n_agg) {
+  return sgr_load_events(H(h), (*env)->GetDirectBufferAddress(env, ev), (uint64_t)nbytes, (const uint64_t*)(*env)->GetDirectBufferAddress(env, offs), (uint64_t)n_agg);
+}
+JNIEXPORT jint JNICALL Java_surge_gpu_Native_00024_loadUnsorted(JNIEnv* env, jobject o, jlong h, jobject rec, jlong n, jlong n_agg) {
+  return sgr_load_unsorted(H(h), (*env)->GetDirectBufferAddress(env, rec), (uint64_t)n, (uint64_t)n_agg);
+}
+JNIEXPORT jint JNICALL Java_surge_gpu_Native_00024_setInitialStates(JNIEnv* env, jobject o, jlong h, jobject st, jlong n_agg) {
+  return sgr_set_initial_states(H(h), st ? (*env)->GetDirectBufferAddress(env, st) : 0, (uint64_t)n_agg);
+}
+JNIEXPORT jint JNICALL Java_surge_gpu_Native_00024_fold(JNIEnv* env, jobject o, jlong h) { return sgr_fold(H(h)); }
+JNIEXPORT jint JNICALL Java_surge_gpu_Native_00024_foldIncremental(JNIEnv* env, jobject o, jlong h, jobject rec, jlong n) {
+  return sgr_fold_incremental(H(h), (*env)->GetDirectBufferAddress(env, rec), (uint64_t)n);
+}
+JNIEXPORT jint JNICALL Java_surge_gpu_Native_00024_loadKeys(JNIEnv* env, jobject o, jlong h, jobject keys, jobject offs, jlong n) {
+  return sgr_load_keys(H(h), (const uint8_t*)(*env)->GetDirectBufferAddress(env, keys), (const uint32_t*)(*env)->GetDirectBufferAddress(env, offs), (uint64_t)n);
+}
+JNIEXPORT jbyteArray JNICALL Java_surge_gpu_Native_00024_get(JNIEnv* env, jobject o, jlong h, jbyteArray key) {
+  jsize klen = (*env)->GetArrayLength(env, key);
+  jbyte* k = (*env)->GetByteArrayElements(env, key, 0);
+  uint8_t out[SGR_MAX_STATE_BYTES]; uint32_t outlen = 0; int32_t exists = 0;
+  int32_t rc = sgr_get(H(h), (const uint8_t*)k, (uint32_t)klen, out, sizeof out, &outlen, &exists);
+  (*env)->ReleaseByteArrayElements(env, key, k, JNI_ABORT);
+  if (rc != SGR_OK) { throw_for(env, H(h), rc); return 0; }
+  if (!exists) return 0;                                   /* Option.empty */
+  jbyteArray r = (*env)->NewByteArray(env, (jsize)outlen);  /* a fresh array, as RocksDB returns */
+  (*env)->SetByteArrayRegion(env, r, 0, (jsize)outlen, (const jbyte*)out);
+  return r;
+}
+JNIEXPORT jint JNICALL Java_surge_gpu_Native_00024_exportStates(JNIEnv* env, jobject o, jlong h, jobject out, jobject changed) {
+  return sgr_export_states(H(h), (*env)->GetDirectBufferAddress(env, out), (uint64_t)(*env)->GetDirectBufferCapacity(env, out), 0,
+                           changed ? (uint8_t*)(*env)->GetDirectBufferAddress(env, changed) : 0, 0);
+}
+JNIEXPORT jint JNICALL Java_surge_gpu_Native_00024_partitionForKey(JNIEnv* env, jobject o, jbyteArray key, jint n, jboolean up_to_colon) {
+  jsize klen = (*env)->GetArrayLength(env, key);
+  jbyte* k = (*env)->GetByteArrayElements(env, key, 0);
+  int32_t p = -1;
+  sgr_partition_for_key_utf8((const uint8_t*)k, (uint32_t)klen, (uint32_t)n, up_to_colon ? 1 : 0, &p);
+  (*env)->ReleaseByteArrayElements(env, key, k, JNI_ABORT);
+  return p;
+}
+#endif
+#endif

@@ -1,0 +1,29 @@
+// Native.scala — JNI face of libsgr.so (include/sgr.h). One `external` per C entry point, same order, same meaning.
+// NOT COMPILED IN THIS REPOSITORY'S IMAGE (no JDK / sbt / Surge jars); shipped as the binding a maintainer adds
+// next to modules/common. The C side of these stubs is shim/jni/sgr_jni.c.
+package surge.gpu
+
+import java.nio.ByteBuffer
+
+object Native {
+  System.loadLibrary("sgr_jni") // links libsgr.so
+
+  // status codes of include/sgr.h
+  final val OK = 0
+  final val ERR_STATE = -8 // -> org.apache.kafka.streams.errors.InvalidStateStoreException
+
+  @native def create(device: Int): Long                                            // sgr_create
+  @native def destroy(handle: Long): Int                                           // sgr_destroy
+  @native def lastError(handle: Long): String                                      // sgr_last_error
+  @native def registerProgram(handle: Long, program: ByteBuffer): Int              // sgr_register_program (packed sgr_fold_program)
+  @native def loadEvents(handle: Long, events: ByteBuffer, nbytes: Long, segOffsets: ByteBuffer, nAgg: Long): Int // sgr_load_events
+  @native def loadUnsorted(handle: Long, records: ByteBuffer, nRecords: Long, nAgg: Long): Int // sgr_load_unsorted
+  @native def setInitialStates(handle: Long, states: ByteBuffer, nAgg: Long): Int  // sgr_set_initial_states
+  @native def fold(handle: Long): Int                                              // sgr_fold
+  @native def foldIncremental(handle: Long, records: ByteBuffer, nRecords: Long): Int // sgr_fold_incremental
+  @native def loadKeys(handle: Long, keys: ByteBuffer, keyOffsets: ByteBuffer, nAgg: Long): Int // sgr_load_keys
+  /** returns null for None, the program bytes otherwise; throws on a non-OK status */
+  @native def get(handle: Long, key: Array[Byte]): Array[Byte]                     // sgr_get
+  @native def exportStates(handle: Long, out: ByteBuffer, changedBits: ByteBuffer): Int // sgr_export_states
+  @native def partitionForKey(key: Array[Byte], numPartitions: Int, upToColon: Boolean): Int // sgr_partition_for_key_utf8
+}
