@@ -174,6 +174,84 @@ def run_reference(args) -> None:
     }))
 
 
+ROUTED_AGG_PER_GPU = 1_250_000   # configs[2]: 10 M aggregates x 100 events over 8 GPUs = 1.25 M x 100 per GPU
+ROUTED_EPA = 100
+
+
+def routed_pipeline(rank, world, local_rank, dev, barrier, note):
+    """configs[2]-shaped per-GPU work (weak: 1.25 M aggregates x 100 events of 64 B originate on every rank):
+    route (K4) + exchange (NCCL all-to-all, then fused peer-memory scatter) + stable group-by (K5) + fold.
+    Stage times are CUDA-event times on the engine's stream, max over ranks; the job rate uses the wall time
+    of the whole call, max over ranks."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from surge_b200 import ReplayEngine
+    from surge_b200 import dist as D
+    from surge_b200 import programs as P
+
+    n_global = ROUTED_AGG_PER_GPU * world
+    epa = ROUTED_EPA
+    # this rank's source partitions hold the aggregates g with g % world == rank, in arrival order
+    # (event k of every aggregate before event k+1: aggregates interleaved, per-aggregate order kept)
+    g_mine = torch.arange(rank, n_global, world, device=dev, dtype=torch.int64)
+    n = g_mine.numel() * epa
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1000 + rank)
+    r = torch.zeros((n, 16), dtype=torch.int32, device=dev)
+    u = torch.rand(n, generator=gen, device=dev)
+    r[:, 0] = torch.where(u < 0.45, 0, torch.where(u < 0.9, 1, 2)).to(torch.int32)
+    del u
+    r[:, 1] = torch.arange(epa, device=dev, dtype=torch.int32).repeat_interleave(g_mine.numel()) + 1
+    agg = g_mine.repeat(epa)
+    r[:, 2] = (agg & 0xFFFFFFFF).to(torch.int32)
+    del agg
+    r[:, 4] = torch.randint(0, 1 << 31, (n,), generator=gen, device=dev, dtype=torch.int64).to(torch.int32)
+    # ownership: partition = a multiplicative hash of the dense id (ids are pre-hashed once on load, SURVEY 8e), 64 partitions
+    part = ((np.arange(n_global, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15)) >> np.uint64(40)).astype(np.uint32) % np.uint32(64)
+    cap = int(n * 1.15) + 1_000_000
+    res = {"workload": f"configs[2] shape, weak: {ROUTED_AGG_PER_GPU} aggregates x {epa} events x 64 B originate per GPU, "
+                       f"{n_global} aggregates hash-partitioned over {world} rank(s)", "events_total": int(n) * world}
+    for mode, fused in (("nccl_all_to_all", False), ("fused_peer_scatter", True)):
+        if world == 1 and fused:
+            continue
+        eng = ReplayEngine(local_rank)
+        eng.register_program(P.counter_program())
+        D.exchange_ids(eng, rank, world, cap, fused=fused)
+        eng.dist_set_partitions(part)
+        best = None
+        for it in range(3):
+            barrier()
+            t0 = time.perf_counter()
+            eng.dist_route_and_fold(r.view(torch.uint8), fused)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            ds = eng.dist_stats()
+            v = [dt, ds.ms_count, ds.ms_counts_exchange, ds.ms_scatter, ds.ms_exchange, ds.ms_group, ds.ms_fold]
+            t = torch.tensor(v, dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            v = [float(x) for x in t]
+            if it > 0 and (best is None or v[0] < best[0]):
+                best = v
+        ds = eng.dist_stats()
+        ev = int(eng.stats().n_events)
+        tot = torch.tensor([ev], dtype=torch.int64, device=dev)
+        if world > 1:
+            dist.all_reduce(tot)
+        assert int(tot[0]) == n * world, (int(tot[0]), n * world)
+        res["single_gpu_group_and_fold" if world == 1 else mode] = {
+            "events_per_s": n * world / best[0], "ms_wall": best[0] * 1e3, "ms_route_count": best[1], "ms_counts_exchange": best[2],
+            "ms_route_scatter": best[3], "ms_exchange": best[4], "ms_group": best[5], "ms_fold": best[6],
+            "fold_events_per_s_per_gpu": ds.n_recv / (best[6] * 1e-3) if best[6] else None,
+            "remote_fraction": ds.n_sent_remote / max(ds.n_sent, 1)}
+        eng.close()
+        del eng
+        torch.cuda.empty_cache()
+    return res
+
+
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -183,6 +261,7 @@ def main() -> None:
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the host-buffer region (default min(steps, 20))")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--verbose", action="store_true", help="progress markers on stderr")
+    ap.add_argument("--no-routed", action="store_true", help="skip the routed (configs[2]-shaped) pipeline measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -221,6 +300,7 @@ def main() -> None:
     note("generating the log on the device")
     rec, off = S.counter_csr_device(N_AGG, EVENTS_PER_AGG, seed=2 + rank, device=dev)
     n_events = N_AGG * EVENTS_PER_AGG
+    log_bytes = int(rec.numel() * 4)
     b_alg = algorithmic_bytes(N_AGG, EVENTS_PER_AGG)
     eng = ReplayEngine(local_rank)
     eng.register_program(P.counter_program())
@@ -286,6 +366,18 @@ def main() -> None:
     same = bool(torch.equal(torch.from_numpy(host_states_np.reshape(-1)).to(dev), eng.states_tensor().reshape(-1)))
     assert same, "e2e state table differs from the HBM-resident fold"
 
+    # ---- configs[2] shape: events arrive by source partition, one exchange routes them to the owning rank
+    routed = None
+    if not args.no_routed:
+        try:
+            note("routed pipeline")
+            e2.close(); eng.close()
+            del rec
+            torch.cuda.empty_cache()
+            routed = routed_pipeline(rank, world, local_rank, dev, barrier, note)
+        except Exception as ex:  # noqa: BLE001 - the headline line must survive a failure of the extra measurement
+            routed = {"error": f"{type(ex).__name__}: {ex}"}
+
     # ---- max over ranks
     if world > 1:
         t = torch.tensor([ms_total, e2e_s], dtype=torch.float64, device=dev)
@@ -318,11 +410,13 @@ def main() -> None:
                          "traffic": traffic, "algorithmic_bytes_per_launch": b_alg, "kernel": "fold_runs_kernel",
                          "kernel_ms": kernel_ms, "peak_source": peak_src,
                          "pipelined_frac": (b_alg / (ms_total / K * 1e-3) / 1e9) / peak},
-            "e2e": {"value": e2e_value, "unit": "events/s", "h2d_bytes_per_step": int(rec.numel() * 4 + host_off.nbytes),
+            "e2e": {"value": e2e_value, "unit": "events/s", "h2d_bytes_per_step": int(log_bytes + host_off.nbytes),
                     "d2h_bytes_per_step": int(N_AGG * STATE_BYTES), "steps": ke, "ms_per_step": e2e_s / ke * 1e3,
                     "ms_h2d": float(st2.ms_h2d), "ms_fold": float(st2.ms_fold), "ms_d2h": float(st2.ms_d2h)},
             "clocks": clocks,
         }
+        if routed is not None:
+            out["routed"] = routed
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             cpu_rec = host_log_np

@@ -244,7 +244,7 @@ int dist_init(DistState* d, int rank, int nranks, const void* unique_id, uint64_
     ncclResult_t r = g_nccl.CommInitRank(&d->comm, nranks, id, rank);
     if (r != ncclSuccess) { *err = std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(r); return SGR_ERR_DIST; }
   }
-  cudaError_t ce = d->recv_buf.reserve(recv_capacity_records * 64);
+  cudaError_t ce = nranks > 1 ? d->recv_buf.reserve(recv_capacity_records * 64) : cudaSuccess;
   if (ce != cudaSuccess) { *err = std::string("receive buffer: ") + cudaGetErrorString(ce); return SGR_ERR_OOM; }
   d->peer_recv[rank] = (uint8_t*)d->recv_buf.p;
   (void)st;
@@ -311,6 +311,8 @@ int dist_set_partitions(DistState* d, const uint32_t* partition_of_agg, uint64_t
 }
 
 uint64_t dist_n_local(const DistState* d) { return d->n_local; }
+int dist_nranks(const DistState* d) { return d->nranks; }
+void dist_clear_stats(DistState* d, uint64_t n_records) { d->stats = DistStats{}; d->stats.n_sent = n_records; d->stats.n_recv = n_records; }
 const uint32_t* dist_global_of_local(const DistState* d) { return (const uint32_t*)d->global_of_local.p; }
 const DistStats* dist_stats(const DistState* d) { return &d->stats; }
 const uint8_t* dist_recv_buffer(const DistState* d) { return (const uint8_t*)d->recv_buf.p; }

@@ -25,6 +25,8 @@ int dist_set_partitions(DistState* d, const uint32_t* partition_of_agg, uint64_t
 int dist_route(DistState* d, const uint8_t* d_records, uint64_t n, bool fused, unsigned long long* d_counters, cudaStream_t st,
                uint64_t* n_recv_out, std::string* err);
 uint64_t dist_n_local(const DistState* d);
+int dist_nranks(const DistState* d);
+void dist_clear_stats(DistState* d, uint64_t n_records);
 const uint32_t* dist_global_of_local(const DistState* d);
 const DistStats* dist_stats(const DistState* d);
 const uint8_t* dist_recv_buffer(const DistState* d);

@@ -730,11 +730,18 @@ int32_t sgr_dist_route_and_fold(sgr_engine* e, const void* d_records, uint64_t n
   int32_t rc = before_load(e); if (rc) return rc;
   std::string err;
   uint64_t n_recv = 0;
-  int r = dist_route(e->dist, (const uint8_t*)d_records, n_records, fused != 0, (unsigned long long*)e->counters.p, e->stream, &n_recv, &err);
-  if (r) return fail(e, r, "%s", err.c_str());
   e->stats.ms_h2d = 0;
-  rc = load_unsorted_impl(e, dist_recv_buffer(e->dist), n_recv, dist_n_local(e->dist));
-  if (rc) return rc;
+  if (dist_nranks(e->dist) == 1) {
+    // one rank owns everything and local index == global index: the exchange degenerates to the local group-by
+    dist_clear_stats(e->dist, n_records);
+    rc = load_unsorted_impl(e, d_records, n_records, dist_n_local(e->dist));
+    if (rc) return rc;
+  } else {
+    int r = dist_route(e->dist, (const uint8_t*)d_records, n_records, fused != 0, (unsigned long long*)e->counters.p, e->stream, &n_recv, &err);
+    if (r) return fail(e, r, "%s", err.c_str());
+    rc = load_unsorted_impl(e, dist_recv_buffer(e->dist), n_recv, dist_n_local(e->dist));
+    if (rc) return rc;
+  }
   e->states_valid = false;
   rc = sgr_fold(e);
   if (rc) return rc;
