@@ -66,16 +66,26 @@ __global__ void __launch_bounds__(kRouteThreads) route_count_kernel(const uint8_
   if (threadIdx.x < kMaxRanks) h[threadIdx.x] = 0;
   __syncthreads();
   const uint64_t base = (uint64_t)blockIdx.x * kRouteBlockRecs;
-  for (int it = 0; it < kRouteBlockRecs / kRouteThreads; ++it) {
+  constexpr int kIts = kRouteBlockRecs / kRouteThreads;
+  // all loads of a thread's 8 records first (independent, in flight together), then the owner lookups, then the votes
+  unsigned long long g[kIts];
+#pragma unroll
+  for (int it = 0; it < kIts; ++it) {
     const uint64_t i = base + (uint64_t)it * kRouteThreads + threadIdx.x;
-    uint32_t o = 0xffffffffu;
-    if (i < n) {
-      const unsigned long long g = *reinterpret_cast<const unsigned long long*>(rec + i * 64 + 8);
-      if (g < n_global) o = owner_of[g]; else atomicAdd(bad, 1ull);
-    }
+    g[it] = i < n ? *reinterpret_cast<const unsigned long long*>(rec + i * 64 + 8) : ~0ull;
+  }
+  uint32_t o[kIts];
+#pragma unroll
+  for (int it = 0; it < kIts; ++it) {
+    const uint64_t i = base + (uint64_t)it * kRouteThreads + threadIdx.x;
+    o[it] = 0xffffffffu;
+    if (i < n) { if (g[it] < n_global) o[it] = owner_of[g[it]]; else atomicAdd(bad, 1ull); }
+  }
+#pragma unroll
+  for (int it = 0; it < kIts; ++it) {
     // one atomic per (warp, owner)
     for (uint32_t r = 0; r < nranks; ++r) {
-      const uint32_t m = __ballot_sync(0xffffffffu, o == r);
+      const uint32_t m = __ballot_sync(0xffffffffu, o[it] == r);
       if ((threadIdx.x & 31) == 0 && m) atomicAdd(&h[r], __popc(m));
     }
   }

@@ -26,14 +26,12 @@ constexpr int kRounds = kPerWarp / 32;    // 16
 
 // ---------------------------------------------------------------- keys
 __global__ void extract_keys_kernel(const uint8_t* __restrict__ rec, uint32_t n, uint64_t n_agg,
-                                    uint32_t* __restrict__ keys, uint32_t* __restrict__ idx,
-                                    unsigned long long* __restrict__ bad) {
+                                    uint32_t* __restrict__ keys, unsigned long long* __restrict__ bad) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const unsigned long long agg = *reinterpret_cast<const unsigned long long*>(rec + (size_t)i * 64 + 8);
   if (agg >= n_agg) atomicAdd(bad, 1ull);
   keys[i] = (uint32_t)agg;
-  idx[i] = i;
 }
 
 // ---------------------------------------------------------------- exclusive scan (u32), three-kernel, recursive on block sums
@@ -99,6 +97,13 @@ cudaError_t exclusive_scan_u32(const uint32_t* in, uint32_t* out, uint32_t n, ui
   return cudaGetLastError();
 }
 
+// lanes holding the same 8-bit digit; invalid lanes match nobody. (Measured on B200: MATCH.ANY beats the
+// 8-ballot formulation here, 3.10 ms vs 4.13 ms for the whole group-by of 33.5 M records.)
+__device__ __forceinline__ uint32_t match_digit(uint32_t d, bool valid) {
+  const uint32_t m = __match_any_sync(0xffffffffu, valid ? d : (256u + (threadIdx.x & 31)));
+  return valid ? m : 0u;
+}
+
 // ---------------------------------------------------------------- radix pass
 // Per-block digit histogram: hist[digit * nblocks + block]
 __global__ void __launch_bounds__(kThreads) radix_hist_kernel(const uint32_t* __restrict__ keys, uint32_t n, int shift,
@@ -117,16 +122,23 @@ __global__ void __launch_bounds__(kThreads) radix_hist_kernel(const uint32_t* __
 }
 
 // Stable scatter. Warp w of the block owns keys [w*512, (w+1)*512) of the tile, in 16 rounds of 32.
-// A key's destination = scanned (digit, block) base + keys with the same digit in earlier warps
-// + in this warp's earlier rounds + in lower lanes of this round.
+// A key's place inside the tile's digit-sorted order = (keys of smaller digits in the tile) + keys with the same
+// digit in earlier warps + in this warp's earlier rounds + in lower lanes of this round. The (key, index) pairs are
+// first reordered in shared memory and then written out in that order, so every digit's run of the tile goes to
+// consecutive global addresses (coalesced) instead of 32 scattered 4-byte stores per warp instruction.
 __global__ void __launch_bounds__(kThreads) radix_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ idx_in,
                                                                  uint32_t* __restrict__ keys_out, uint32_t* __restrict__ idx_out, uint32_t n,
                                                                  int shift, const uint32_t* __restrict__ base, uint32_t nblocks) {
   __shared__ uint32_t wh[kWarps][256];
+  __shared__ uint32_t skey[kTile];
+  __shared__ uint32_t sidx[kTile];
+  __shared__ uint32_t gbase[256];
+  __shared__ uint32_t scan_sm[kWarps];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int i = threadIdx.x; i < kWarps * 256; i += kThreads) (&wh[0][0])[i] = 0;
   __syncthreads();
-  const uint32_t start = blockIdx.x * kTile + warp * kPerWarp;
+  const uint32_t tile0 = blockIdx.x * kTile;
+  const uint32_t start = tile0 + warp * kPerWarp;
   uint32_t key[kRounds];
   const uint32_t lt = (1u << lane) - 1u;
   // phase 1: this warp's digit counts
@@ -135,33 +147,47 @@ __global__ void __launch_bounds__(kThreads) radix_scatter_kernel(const uint32_t*
     const uint32_t i = start + r * 32 + lane;
     const bool valid = i < n;
     key[r] = valid ? keys_in[i] : 0u;
-    const uint32_t d = valid ? ((key[r] >> shift) & 255u) : (256u + lane);
-    const uint32_t m = __match_any_sync(0xffffffffu, d);
+    const uint32_t d = (key[r] >> shift) & 255u;
+    const uint32_t m = match_digit(d, valid);
     if (valid && (m & lt) == 0) wh[warp][d] += __popc(m);
     __syncwarp();
   }
   __syncthreads();
-  // phase 2: exclusive prefix over warps, seeded with the global base of (digit, block)
+  // phase 2: per digit, exclusive prefix over warps; then exclusive scan over digits = start of the digit's run in the tile
   {
     const uint32_t d = threadIdx.x;
-    uint32_t off = base[d * nblocks + blockIdx.x];
+    uint32_t off = 0;
 #pragma unroll
     for (int w = 0; w < kWarps; ++w) { const uint32_t c = wh[w][d]; wh[w][d] = off; off += c; }
+    uint32_t total;
+    const uint32_t tile_start = block_exclusive_scan(off, &total, scan_sm);
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) wh[w][d] += tile_start;
+    gbase[d] = base[d * nblocks + blockIdx.x] - tile_start;  // global position = gbase[digit] + place in tile
   }
   __syncthreads();
-  // phase 3: ranks and scatter
+  // phase 3: place every pair at its digit-sorted position in shared memory
 #pragma unroll
   for (int r = 0; r < kRounds; ++r) {
     const uint32_t i = start + r * 32 + lane;
     const bool valid = i < n;
-    const uint32_t d = valid ? ((key[r] >> shift) & 255u) : (256u + lane);
-    const uint32_t m = __match_any_sync(0xffffffffu, d);
+    const uint32_t d = (key[r] >> shift) & 255u;
+    const uint32_t m = match_digit(d, valid);
     uint32_t pos = 0;
     if (valid) pos = wh[warp][d] + __popc(m & lt);
     __syncwarp();
     if (valid && (m & lt) == 0) wh[warp][d] += __popc(m);
     __syncwarp();
-    if (valid) { keys_out[pos] = key[r]; idx_out[pos] = idx_in[i]; }
+    if (valid) { skey[pos] = key[r]; sidx[pos] = idx_in ? idx_in[i] : i; }
+  }
+  __syncthreads();
+  // phase 4: write the tile out in sorted order
+  const uint32_t tile_n = n - tile0 < (uint32_t)kTile ? n - tile0 : (uint32_t)kTile;
+  for (uint32_t j = threadIdx.x; j < tile_n; j += kThreads) {
+    const uint32_t k = skey[j];
+    const uint32_t pos = gbase[(k >> shift) & 255u] + j;
+    keys_out[pos] = k;
+    idx_out[pos] = sidx[j];
   }
 }
 
@@ -256,14 +282,15 @@ cudaError_t group_by_agg_stable(GroupScratch& sc, const uint8_t* d_records, uint
   uint32_t* tmp = (uint32_t*)sc.scan_tmp.p;
 
   if ((e = cudaMemsetAsync(d_counters, 0, 64, st)) != cudaSuccess) return e;
-  extract_keys_kernel<<<cdiv(n, 256), 256, 0, st>>>(d_records, n, n_agg, ka, ia, d_counters + 4);
+  extract_keys_kernel<<<cdiv(n, 256), 256, 0, st>>>(d_records, n, n_agg, ka, d_counters + 4);
 
   int bits = 1;
   while (bits < 32 && (1ull << bits) < n_agg) ++bits;
   for (int shift = 0; shift < bits; shift += 8) {
     radix_hist_kernel<<<nblocks, kThreads, 0, st>>>(ka, n, shift, hist, nblocks);
     if ((e = exclusive_scan_u32(hist, hist, 256 * nblocks, tmp, st)) != cudaSuccess) return e;
-    radix_scatter_kernel<<<nblocks, kThreads, 0, st>>>(ka, ia, kb, ib, n, shift, hist, nblocks);
+    // first pass: the arrival index is the position itself
+    radix_scatter_kernel<<<nblocks, kThreads, 0, st>>>(ka, shift == 0 ? nullptr : ia, kb, ib, n, shift, hist, nblocks);
     uint32_t* t;
     t = ka; ka = kb; kb = t;
     t = ia; ia = ib; ib = t;
