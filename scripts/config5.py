@@ -26,7 +26,9 @@ if check:
         want = O.fold_incremental(O.MODEL_COUNTER, pool[b].cpu().numpy().view(np.uint8).reshape(-1), want)
         e.fold_incremental(pool[b].view(torch.uint8))
     print("parity after 5 batches:", bool(np.array_equal(e.export_states(), want)))
+print("warm", flush=True)
 for b in range(10): e.fold_incremental(pool[b % nb_pool].view(torch.uint8))
+print("warm done", e.stats().ms_fold, flush=True)
 lat = []
 torch.cuda.synchronize(); t0 = time.perf_counter()
 for b in range(n_batches):

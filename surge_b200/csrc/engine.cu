@@ -19,6 +19,7 @@
 #include "fold_kernels.cuh"
 #include "fold_rows.cuh"
 #include "group_kernels.cuh"
+#include "incremental.cuh"
 #include "keytable.h"
 
 using namespace sgr;
@@ -60,6 +61,12 @@ struct sgr_engine {
   GroupScratch group;   // K5 scratch
   DevBuf inc_records, inc_offsets, inc_ids, inc_prev_ids;  // K6
   uint64_t inc_prev_n = 0;
+  // sort-free K6 (incremental.cu)
+  DevBuf inc_scratch, inc_touched[2], inc_err_ids, inc_counters;
+  uint64_t inc_scratch_slots = 0;
+  int inc_flip = 0;
+  bool inc_atomic_prev_valid = false;   // inc_touched[inc_flip^1] / its counter describe the previous batch
+  uint32_t inc_prev_upper = 0;
 
   // record-parallel path (fold_rows.cu)
   bool row_ok = false;            // program is inside the transformer algebra
@@ -86,6 +93,7 @@ struct sgr_engine {
                                   // 2 force runs (fold_runs.cu), 3 record-per-lane rows (fold_rows.cu)
   int64_t opt_variant = -1;
   int64_t opt_long_threshold = 0;
+  int64_t opt_incremental = 0;    // 0 auto (sort-free K6 when the program allows), 1 force the sort-based path
   int64_t opt_max_record_bytes = 528;
 
   sgr_stats stats{};
@@ -369,6 +377,7 @@ int32_t sgr_destroy(sgr_engine* e) {
   cudaStreamSynchronize(e->stream);
   e->own_events.release(); e->own_offsets.release(); e->states.release(); e->counters.release();
   e->inc_records.release(); e->inc_offsets.release(); e->inc_ids.release(); e->inc_prev_ids.release();
+  e->inc_scratch.release(); e->inc_touched[0].release(); e->inc_touched[1].release(); e->inc_err_ids.release(); e->inc_counters.release();
   e->group.release();
   if (e->dist) dist_destroy(e->dist);
   e->part_flags.release(); e->part_data.release(); e->redo_ids.release(); e->run_counters.release();
@@ -489,6 +498,7 @@ int32_t sgr_set_initial_states(sgr_engine* e, const void* states, uint64_t n_agg
   CUDA_TRY(e, cudaMemcpyAsync(e->states.p, states, (size_t)n_agg * e->program.state_bytes, cudaMemcpyHostToDevice, e->stream));
   CUDA_TRY(e, cudaStreamSynchronize(e->stream));
   e->states_valid = true;
+  e->inc_atomic_prev_valid = false; e->inc_prev_n = 0;
   mark_dirty(e);
   return SGR_OK;
 }
@@ -507,6 +517,7 @@ static int32_t fold_begin(sgr_engine* e, bool pipelined) {
   if (rc) return rc;
   e->states_valid = true;
   e->inc_prev_n = 0;
+  e->inc_atomic_prev_valid = false;
   mark_dirty(e);
   return SGR_OK;
 }
@@ -524,10 +535,59 @@ int32_t sgr_wait(sgr_engine* e) {
   return finish_fold(e);
 }
 
+// sort-free path for programs inside the transformer algebra (incremental.cu)
+static int32_t fold_incremental_atomic(sgr_engine* e, const void* d_records, uint64_t n_records) {
+  const uint64_t n_agg = e->states_n;
+  if (n_records >= (1ull << 32)) return fail(e, SGR_ERR_UNSUPPORTED, "micro-batches are limited to 2^32 records");
+  if (e->inc_scratch_slots != n_agg) {
+    CUDA_TRY(e, e->inc_scratch.reserve(inc_scratch_bytes(n_agg)));
+    CUDA_TRY(e, cudaMemsetAsync(e->inc_scratch.p, 0, inc_scratch_bytes(n_agg), e->stream));
+    e->inc_scratch_slots = n_agg;
+  }
+  // sized by the table, not by the batch: the previous batch's list must survive a larger next batch
+  CUDA_TRY(e, e->inc_touched[0].reserve((n_agg + 1) * 4)); CUDA_TRY(e, e->inc_touched[1].reserve((n_agg + 1) * 4));
+  CUDA_TRY(e, e->inc_err_ids.reserve((n_agg + 1) * 4));
+  CUDA_TRY(e, e->inc_counters.reserve(256));
+  unsigned long long* cur = (unsigned long long*)e->inc_counters.p + 8 * e->inc_flip;
+  unsigned long long* prev = (unsigned long long*)e->inc_counters.p + 8 * (e->inc_flip ^ 1);
+  CUDA_TRY(e, cudaEventRecord(e->ev0, e->stream));
+  CUDA_TRY(e, cudaMemsetAsync(cur, 0, 64, e->stream));
+  uint32_t prev_upper = 0;
+  if (!e->inc_atomic_prev_valid) {
+    // first batch after a full fold / set_initial_states / a sort-based batch: every slot may carry per-batch flags
+    clear_batch_flags((uint8_t*)e->states.p, e->program.state_bytes, nullptr, n_agg, e->stream);
+  } else {
+    prev_upper = e->inc_prev_upper;
+  }
+  cudaError_t le = launch_incremental_atomic((const uint8_t*)d_records, (uint32_t)n_records, n_agg, e->inc_scratch.p, (uint8_t*)e->states.p,
+                                             (uint32_t*)e->inc_touched[e->inc_flip].p, (uint32_t*)e->inc_err_ids.p,
+                                             (const uint32_t*)e->inc_touched[e->inc_flip ^ 1].p, prev + 5, prev_upper, e->row_prog, cur, e->stream);
+  if (le != cudaSuccess) return fail(e, SGR_ERR_CUDA, "incremental launch: %s", cudaGetErrorString(le));
+  CUDA_TRY(e, cudaEventRecord(e->ev1, e->stream));
+  unsigned long long h[8];
+  CUDA_TRY(e, cudaMemcpyAsync(h, cur, 64, cudaMemcpyDeviceToHost, e->stream));
+  CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+  CUDA_TRY(e, cudaEventElapsedTime(&e->stats.ms_fold, e->ev0, e->ev1));
+  if (h[4]) return fail(e, SGR_ERR_INVALID, "%llu records carry an aggregate index >= n_agg; the batch was not applied", h[4]);
+  e->inc_atomic_prev_valid = true;
+  e->inc_prev_upper = (uint32_t)(h[5]);
+  e->inc_flip ^= 1;
+  e->inc_prev_n = 0;
+  e->stats.ms_group = 0;
+  e->stats.n_aggregates = h[5]; e->stats.n_errors = h[1]; e->stats.n_events = n_records - h[6];
+  e->stats.event_bytes = n_records * 64; e->stats.n_long_segments = 0;
+  e->stats.algorithmic_bytes = n_records * 64 + 2 * (uint64_t)e->program.state_bytes * h[5];
+  e->stats.fold_launches = 1;
+  mark_dirty(e);
+  return SGR_OK;
+}
+
 static int32_t fold_incremental_impl(sgr_engine* e, const void* d_records, uint64_t n_records) {
   if (e->program.record_kind != SGR_REC_FIXED64) return fail(e, SGR_ERR_UNSUPPORTED, "incremental batches take fixed 64-byte records");
   if (!e->states_valid) return fail(e, SGR_ERR_NOT_LOADED, "incremental fold needs a live state table (fold or set_initial_states first)");
   { int32_t rc0 = finish_fold(e); if (rc0) return rc0; }
+  if (e->row_ok && e->opt_kernel != 1 && e->opt_kernel != 3 && e->opt_incremental != 1) return fold_incremental_atomic(e, d_records, n_records);
+  e->inc_atomic_prev_valid = false;
   const uint64_t n_agg = e->states_n;
   CUDA_TRY(e, e->inc_offsets.reserve((n_records + 2) * 8));
   CUDA_TRY(e, e->inc_ids.reserve((n_records + 1) * 4));
@@ -778,6 +838,7 @@ int32_t sgr_set_option(sgr_engine* e, const char* name, int64_t value) {
   if (!e || !name) return SGR_ERR_INVALID;
   if (!strcmp(name, "fold_variant")) { e->opt_variant = value; return SGR_OK; }
   if (!strcmp(name, "kernel")) { e->opt_kernel = value; return SGR_OK; }
+  if (!strcmp(name, "incremental")) { e->opt_incremental = value; return SGR_OK; }
   if (!strcmp(name, "run_variant")) {
     if (value < 0 || value >= run_variant_count()) return fail(e, SGR_ERR_INVALID, "run_variant out of range");
     e->opt_run_variant = value; return SGR_OK;

@@ -303,24 +303,38 @@ def test_unsorted_load_rejects_out_of_range_aggregate():
         assert ei.value.code == N.SGR_ERR_INVALID
 
 
-def test_incremental_micro_batches():
-    """configs[4] shape, small: batches appended to live aggregates; each batch == one ApplyEvents per touched aggregate."""
+@pytest.mark.parametrize("path", [0, 1])
+def test_incremental_micro_batches(path):
+    """configs[4] shape, small: batches appended to live aggregates; each batch == one ApplyEvents per touched aggregate.
+    path 0: sort-free atomic K6 (incremental.cu); path 1: sort-based K5 + fold."""
     n_agg = 20000
     rec, off = S.counter_csr(n_agg, 3, seed=81)
     want, _, _ = O.fold_packed(O.MODEL_COUNTER, O.REC_FIXED64, rec, off)
     rng = np.random.default_rng(82)
     with ReplayEngine(0) as e:
         e.register_program(P.counter_program())
+        e.set_option("incremental", path)
         e.load_events(rec, off)
         e.fold()
-        for b in range(6):
-            n = [1000, 1, 5000, 0, 300, 20000][b]
+        for b in range(8):
+            n = [1000, 1, 5000, 0, 300, 20000, 64, 3000][b]
             aggs = rng.integers(0, n_agg, size=n).astype(np.uint64)
             types = rng.choice([0, 1, 2, 3], size=n, p=[0.45, 0.44, 0.1, 0.01]).astype(np.uint32)
+            if b == 6:
+                aggs[:] = 17          # one hot aggregate, with a throw in the middle: err_idx must be exact
+                types[:] = 0
+                types[40] = 3
             batch = F.counter_records(types, np.arange(n, dtype=np.uint32) + 1000 * b, aggs, rng.integers(0, 3, size=n).astype(np.int32))
             want = O.fold_incremental(O.MODEL_COUNTER, batch, want)
             e.fold_incremental(batch)
             assert_same(e.export_states(), want, f"batch {b}")
+            st = e.stats()
+            errs = int((want.view(F.COUNTER_STATE).reshape(-1)["flags"] & N.ST_ERROR != 0).sum())
+            assert st.n_errors == errs and st.n_aggregates == len(np.unique(aggs))
+        bad = F.counter_records([0], [1], [n_agg + 5], [1])
+        with pytest.raises(SgrError):
+            e.fold_incremental(bad)
+        assert_same(e.export_states(), O.fold_incremental(O.MODEL_COUNTER, np.zeros(0, F.REC64), want), "rejected batch leaves the table alone")
 
 
 # ------------------------------------------------------------------ recovery read (getAggregateBytes)
