@@ -189,6 +189,14 @@ int32_t sgr_load_events(sgr_engine* e, const void* events, uint64_t nbytes,
 int32_t sgr_load_events_device(sgr_engine* e, const void* d_events, uint64_t nbytes,
                                const uint64_t* d_seg_offsets, uint64_t n_agg);
 
+/* Variable records with a record directory: rec_offsets[n_records+1] are the byte offsets of every record in log order
+ * (the packer knows them for free). With it the log is cut into record-balanced spans, so skewed (Zipf) keys do not
+ * serialise one lane; without it (sgr_load_events) variable records are folded one lane per aggregate. */
+int32_t sgr_load_events_indexed(sgr_engine* e, const void* events, uint64_t nbytes, const uint64_t* seg_offsets, uint64_t n_agg,
+                                const uint64_t* rec_offsets, uint64_t n_records);
+int32_t sgr_load_events_indexed_device(sgr_engine* e, const void* d_events, uint64_t nbytes, const uint64_t* d_seg_offsets,
+                                       uint64_t n_agg, const uint64_t* d_rec_offsets, uint64_t n_records);
+
 /* Load records in ARRIVAL order (a Kafka partition log interleaves aggregates) and group
  * them, stably, by aggregate index into CSR form on the device. n_agg is the number of
  * dense aggregate indices (records carry agg < n_agg). Fixed 64-byte records only. */

@@ -46,7 +46,9 @@ struct sgr_engine {
   DevProgram dprog{};
 
   // CSR event log: owned buffers or borrowed pointers
-  DevBuf own_events, own_offsets;
+  DevBuf own_events, own_offsets, own_rec_offsets;
+  const uint64_t* d_rec_offsets = nullptr;   // record directory (variable records), or null
+  uint64_t n_rec = 0;
   const uint8_t* d_events = nullptr;
   const uint64_t* d_offsets = nullptr;
   uint64_t event_bytes = 0;
@@ -83,7 +85,7 @@ struct sgr_engine {
   bool offsets_aligned64 = false; // every segment offset == log_begin (mod 64)
   uint64_t log_begin = 0, log_end = 0;
   bool fold_pending = false;      // a fold was enqueued and not yet finished
-  bool pending_rows_v1 = false;
+  bool pending_rows_v1 = false, pending_var = false;
   bool pending_used_rows = false, pending_prior = false, pending_timed_group = false;
   uint64_t pending_n_seg = 0, pending_event_bytes = 0;
   const uint8_t* pending_events = nullptr; const uint64_t* pending_offsets = nullptr; const uint32_t* pending_ids = nullptr;
@@ -93,6 +95,8 @@ struct sgr_engine {
                                   // 2 force runs (fold_runs.cu), 3 record-per-lane rows (fold_rows.cu)
   int64_t opt_variant = -1;
   int64_t opt_long_threshold = 0;
+  int64_t opt_var_stages = 2;
+  int64_t opt_var_stage_bytes = 12288;  // smem bytes staged per 32-record step of the variable-record kernel
   int64_t opt_incremental = 0;    // 0 auto (sort-free K6 when the program allows), 1 force the sort-based path
   int64_t opt_max_record_bytes = 528;
 
@@ -212,7 +216,7 @@ constexpr uint64_t kRedoCap = 1u << 20;
 int32_t enqueue_fold(sgr_engine* e, const uint8_t* d_events, const uint64_t* d_offsets, const uint32_t* d_ids,
                      uint64_t n_seg, bool use_prior, uint64_t event_bytes, bool aligned64, uint64_t log_begin, uint64_t log_end) {
   const uint8_t* states_in = use_prior ? (const uint8_t*)e->states.p : nullptr;
-  bool use_rows = e->row_ok && aligned64 && e->opt_kernel != 1 && n_seg < (1ull << 32) && n_seg > 0;
+  bool use_rows = e->row_ok && e->program.record_kind == SGR_REC_FIXED64 && aligned64 && e->opt_kernel != 1 && n_seg < (1ull << 32) && n_seg > 0;
   if ((e->opt_kernel == 2 || e->opt_kernel == 3) && !use_rows && n_seg > 0)
     return fail(e, SGR_ERR_UNSUPPORTED, "record-parallel kernel cannot take this program/log");
   const bool runs = use_rows && e->opt_kernel != 3;
@@ -227,9 +231,47 @@ int32_t enqueue_fold(sgr_engine* e, const uint8_t* d_events, const uint64_t* d_o
     CUDA_TRY(e, cudaMemsetAsync(e->counters.p, 0, 64, e->stream));
   }
   e->pending_counters = counters;
+  e->pending_var = false;
   CUDA_TRY(e, cudaEventRecord(e->ev0, e->stream));
   uint32_t launches = 0;
-  if (n_seg) {
+  const bool use_var = e->row_ok && e->program.record_kind == SGR_REC_VAR16 && e->d_rec_offsets && d_offsets == e->d_offsets && !use_prior &&
+                       !d_ids && e->opt_kernel != 1 && n_seg > 0 && n_seg < (1ull << 32) && e->n_rec > 0;
+  if (use_var) {
+    int threads = 0; size_t smem = 0; uint32_t stage = 0;
+    const int max_grid = vruns_config(e->num_sms, e->max_record_bytes, (uint32_t)e->opt_var_stage_bytes, (int)e->opt_var_stages, &threads, &smem, &stage);
+    if (max_grid > 0) {
+      const uint64_t n_warps_max = (uint64_t)max_grid * (threads / 32);
+      CUDA_TRY(e, e->part_flags.reserve(n_warps_max * 4 + 256));
+      CUDA_TRY(e, e->part_data.reserve(n_warps_max * 8 * 4 + 256));
+      CUDA_TRY(e, e->redo_ids.reserve(kRedoCap * 4));
+      if (e->epoch == 0 || e->part_flags_cap_seen != e->part_flags.cap) {
+        CUDA_TRY(e, cudaMemsetAsync(e->part_flags.p, 0, e->part_flags.cap, e->stream));
+        e->part_flags_cap_seen = e->part_flags.cap;
+      }
+      ++e->epoch;
+      if (e->epoch == 0) { CUDA_TRY(e, cudaMemsetAsync(e->part_flags.p, 0, e->part_flags.cap, e->stream)); e->epoch = 1; }
+      CUDA_TRY(e, cudaMemsetAsync(e->states.p, 0, (size_t)n_seg * e->program.state_bytes, e->stream));
+      VarArgs v{};
+      v.events = d_events; v.rec_offsets = e->d_rec_offsets; v.n_rec = e->n_rec; v.seg_offsets = d_offsets; v.n_seg = n_seg;
+      v.states_out = (uint8_t*)e->states.p; v.counters = counters; v.redo_ids = (uint32_t*)e->redo_ids.p; v.redo_cap = kRedoCap;
+      v.part_flags = (uint32_t*)e->part_flags.p; v.part_data = (uint32_t*)e->part_data.p; v.epoch = e->epoch; v.stage_bytes = stage;
+      const uint64_t steps = (e->n_rec + 31) / 32;
+      uint64_t want = (steps + (threads / 32) - 1) / (threads / 32);
+      const int grid = (int)(want < (uint64_t)max_grid ? want : (uint64_t)max_grid);
+      cudaError_t le = launch_fold_vruns(v, e->row_prog, (int)e->opt_var_stages, grid, threads, smem, e->stream);
+      if (le != cudaSuccess) return fail(e, SGR_ERR_CUDA, "fold_vruns launch: %s", cudaGetErrorString(le));
+      // exact replay of throwing / malformed segments (count lives on the device)
+      FoldArgs a{};
+      a.events = d_events; a.seg_offsets = d_offsets; a.n_seg = kRedoCap; a.seg_list = (const uint32_t*)e->redo_ids.p;
+      a.n_seg_dev = counters + 3; a.states_in = nullptr; a.states_out = (uint8_t*)e->states.p; a.counters = counters;
+      FoldLaunchInfo info{};
+      le = launch_fold_stream(a, e->dprog, -1, 8, e->max_record_bytes, e->stream, &info);
+      if (le != cudaSuccess) return fail(e, SGR_ERR_CUDA, "replay launch: %s", cudaGetErrorString(le));
+      launches = 2;
+      e->pending_var = true;
+    }
+  }
+  if (n_seg && !e->pending_var) {
     FoldArgs a{};
     a.events = d_events; a.seg_offsets = d_offsets; a.seg_ids = d_ids; a.n_seg = n_seg;
     a.states_in = states_in; a.states_out = (uint8_t*)e->states.p;
@@ -303,6 +345,24 @@ int32_t finish_fold(sgr_engine* e) {
   CUDA_TRY(e, cudaMemcpyAsync(h, e->pending_counters, 64, cudaMemcpyDeviceToHost, e->stream));
   CUDA_TRY(e, cudaStreamSynchronize(e->stream));
   CUDA_TRY(e, cudaEventElapsedTime(&e->stats.ms_fold, e->ev0, e->ev1));
+  if (e->pending_var && (h[7] != 0 || h[3] > kRedoCap)) {
+    // the directory/header view disagreed with the CSR (or too many throwing segments): the CSR is the source of truth,
+    // fold everything on the sequential kernel
+    e->pending_var = false;
+    FoldArgs a{};
+    a.events = e->pending_events; a.seg_offsets = e->pending_offsets; a.n_seg = e->pending_n_seg;
+    a.states_out = (uint8_t*)e->states.p; a.counters = (unsigned long long*)e->counters.p;
+    CUDA_TRY(e, cudaMemsetAsync(e->counters.p, 0, 64, e->stream));
+    CUDA_TRY(e, cudaEventRecord(e->ev2, e->stream));
+    FoldLaunchInfo info{};
+    cudaError_t le = launch_fold_stream(a, e->dprog, -1, e->num_sms, e->max_record_bytes, e->stream, &info);
+    if (le != cudaSuccess) return fail(e, SGR_ERR_CUDA, "fold launch: %s", cudaGetErrorString(le));
+    CUDA_TRY(e, cudaEventRecord(e->ev3, e->stream));
+    CUDA_TRY(e, cudaMemcpyAsync(h, e->counters.p, 64, cudaMemcpyDeviceToHost, e->stream));
+    CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+    float ms2 = 0; CUDA_TRY(e, cudaEventElapsedTime(&ms2, e->ev2, e->ev3));
+    e->stats.ms_fold += ms2; e->stats.fold_launches += 1;
+  }
   if (e->pending_used_rows && h[3] > kRedoCap) {
     // more throwing aggregates than the replay list holds: redo everything on the sequential kernel
     FoldArgs a{};
@@ -325,7 +385,7 @@ int32_t finish_fold(sgr_engine* e) {
   e->stats.n_aggregates = n_seg;
   // runs kernel counts every record, the replay takes back what followed a throw; the rows kernel skips
   // throwing segments, the replay adds what preceded the throw
-  e->stats.n_events = !e->pending_used_rows ? h[0] : (e->pending_rows_v1 ? h[0] + h[5] : h[0] - h[4]);
+  e->stats.n_events = e->pending_var ? h[0] - h[4] + h[5] : !e->pending_used_rows ? h[0] : (e->pending_rows_v1 ? h[0] + h[5] : h[0] - h[4]);
   e->stats.n_errors = h[1];
   e->stats.n_long_segments = h[2];
   e->stats.event_bytes = e->pending_event_bytes;
@@ -375,7 +435,7 @@ int32_t sgr_destroy(sgr_engine* e) {
   if (!e) return SGR_OK;
   cudaSetDevice(e->device);
   cudaStreamSynchronize(e->stream);
-  e->own_events.release(); e->own_offsets.release(); e->states.release(); e->counters.release();
+  e->own_events.release(); e->own_offsets.release(); e->own_rec_offsets.release(); e->states.release(); e->counters.release();
   e->inc_records.release(); e->inc_offsets.release(); e->inc_ids.release(); e->inc_prev_ids.release();
   e->inc_scratch.release(); e->inc_touched[0].release(); e->inc_touched[1].release(); e->inc_err_ids.release(); e->inc_counters.release();
   e->group.release();
@@ -407,6 +467,7 @@ static int32_t before_load(sgr_engine* e) {
 
 static int32_t after_load(sgr_engine* e, const uint8_t* d_events, const uint64_t* d_offsets, uint64_t nbytes, uint64_t n_agg) {
   e->d_events = d_events; e->d_offsets = d_offsets; e->event_bytes = nbytes; e->n_agg = n_agg; e->loaded = true;
+  e->d_rec_offsets = nullptr; e->n_rec = 0;
   // variable records: the format caps a record at 16+512 bytes unless the caller raises
   // "max_record_bytes"; a longer record is flagged as a malformed event by the kernel, never mis-parsed
   e->max_record_bytes = e->program.record_kind == SGR_REC_VAR16 ? (uint32_t)e->opt_max_record_bytes : 64u;
@@ -448,6 +509,30 @@ int32_t sgr_load_events_device(sgr_engine* e, const void* d_events, uint64_t nby
   int32_t rc = before_load(e); if (rc) return rc;
   e->stats.ms_h2d = 0; e->stats.ms_group = 0;
   return after_load(e, (const uint8_t*)d_events, d_seg_offsets, nbytes, n_agg);
+}
+
+int32_t sgr_load_events_indexed(sgr_engine* e, const void* events, uint64_t nbytes, const uint64_t* seg_offsets, uint64_t n_agg,
+                                const uint64_t* rec_offsets, uint64_t n_records) {
+  if (!rec_offsets) return fail(e, SGR_ERR_INVALID, "null record directory");
+  int32_t rc = sgr_load_events(e, events, nbytes, seg_offsets, n_agg);
+  if (rc) return rc;
+  for (uint64_t i = 0; i < n_records; ++i)
+    if (rec_offsets[i + 1] < rec_offsets[i] || rec_offsets[i] % 16) return fail(e, SGR_ERR_INVALID, "record directory is not monotone / 16-byte aligned at %llu", (unsigned long long)i);
+  if (rec_offsets[0] != seg_offsets[0] || rec_offsets[n_records] != seg_offsets[n_agg]) return fail(e, SGR_ERR_INVALID, "record directory and CSR cover different byte ranges");
+  CUDA_TRY(e, e->own_rec_offsets.reserve((n_records + 1) * 8));
+  CUDA_TRY(e, cudaMemcpyAsync(e->own_rec_offsets.p, rec_offsets, (n_records + 1) * 8, cudaMemcpyHostToDevice, e->stream));
+  CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+  e->d_rec_offsets = (const uint64_t*)e->own_rec_offsets.p; e->n_rec = n_records;
+  return SGR_OK;
+}
+
+int32_t sgr_load_events_indexed_device(sgr_engine* e, const void* d_events, uint64_t nbytes, const uint64_t* d_seg_offsets, uint64_t n_agg,
+                                       const uint64_t* d_rec_offsets, uint64_t n_records) {
+  if (!d_rec_offsets) return fail(e, SGR_ERR_INVALID, "null record directory");
+  int32_t rc = sgr_load_events_device(e, d_events, nbytes, d_seg_offsets, n_agg);
+  if (rc) return rc;
+  e->d_rec_offsets = d_rec_offsets; e->n_rec = n_records;   // consistency with the CSR is checked by the kernel at every segment head
+  return SGR_OK;
 }
 
 static int32_t load_unsorted_impl(sgr_engine* e, const void* d_records, uint64_t n_records, uint64_t n_agg) {
@@ -839,6 +924,8 @@ int32_t sgr_set_option(sgr_engine* e, const char* name, int64_t value) {
   if (!strcmp(name, "fold_variant")) { e->opt_variant = value; return SGR_OK; }
   if (!strcmp(name, "kernel")) { e->opt_kernel = value; return SGR_OK; }
   if (!strcmp(name, "incremental")) { e->opt_incremental = value; return SGR_OK; }
+  if (!strcmp(name, "var_stage_bytes")) { e->opt_var_stage_bytes = value; return SGR_OK; }
+  if (!strcmp(name, "var_stages")) { e->opt_var_stages = value == 3 ? 3 : 2; return SGR_OK; }
   if (!strcmp(name, "run_variant")) {
     if (value < 0 || value >= run_variant_count()) return fail(e, SGR_ERR_INVALID, "run_variant out of range");
     e->opt_run_variant = value; return SGR_OK;

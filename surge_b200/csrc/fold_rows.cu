@@ -425,7 +425,6 @@ namespace {
 
 bool build_row_program(const DevProgram& dp, RowProgram* out) {
   memset(out, 0, sizeof *out);
-  if (dp.record_kind != SGR_REC_FIXED64) return false;
   if (dp.user_words != 2) return false;  // instantiated widths (state_bytes 16)
   if (dp.n_f64) return false;
   out->user_words = dp.user_words;
@@ -445,7 +444,7 @@ bool build_row_program(const DevProgram& dp, RowProgram* out) {
       if (opcode > SGR_OP_SUB_I32) return false;
       for (uint32_t j = 0; j < nwords; ++j) {
         const uint32_t w = dw + j, src = sw + j;
-        if (w >= dp.user_words || src >= 16) return false;
+        if (w >= dp.user_words || src >= (dp.record_kind == SGR_REC_FIXED64 ? 16u : 136u)) return false;
         // one source per state word per event: a word written twice by the same rule is not a single (mode, value)
         if (mode[w] != 0 && !(reset && slot[w] == 0)) return false;
         uint32_t s = 0;

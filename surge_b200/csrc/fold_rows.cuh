@@ -48,6 +48,22 @@ int row_kernel_max_grid(int num_sms, const RowProgram& prog);  // largest co-res
 cudaError_t launch_fold_rows(const RowArgs& args, const RowProgram& prog, int grid, cudaStream_t stream);
 
 
+// ---- fold_vruns.cu: variable records with a record directory
+struct VarArgs {
+  const uint8_t* events;
+  const uint64_t* rec_offsets;   // n_rec+1 byte offsets, log order
+  uint64_t n_rec;
+  const uint64_t* seg_offsets;   // CSR, the source of truth (cross-checked at every segment head)
+  uint64_t n_seg;
+  uint8_t* states_out;           // zeroed before the launch (full rebuild: empty aggregates stay None)
+  unsigned long long* counters;  // [0] records seen, [3] replay list length, [4] records of replayed segments, [7] CSR mismatches
+  uint32_t* redo_ids; uint64_t redo_cap;
+  uint32_t* part_flags; uint32_t* part_data; uint32_t epoch;   // part_data: 8 words per warp
+  uint32_t stage_bytes;
+};
+int vruns_config(int num_sms, uint32_t max_record_bytes, uint32_t stage_hint, int nstage, int* threads, size_t* smem, uint32_t* stage_bytes);  // returns max grid, 0 if impossible
+cudaError_t launch_fold_vruns(const VarArgs& args, const RowProgram& prog, int nstage, int grid, int threads, size_t smem, cudaStream_t stream);
+
 // ---- fold_runs.cu: lane-run variant (primary). Same RowArgs / RowProgram.
 int run_variant_count();
 const char* run_variant_name(int v);

@@ -82,6 +82,19 @@ class ReplayEngine:
         off = np.ascontiguousarray(seg_offsets, dtype=np.uint64)
         self._ck(self._lib.sgr_load_events(self._h, ev.ctypes.data, ev.size, off.ctypes.data, len(off) - 1))
 
+    def load_events_indexed(self, events, seg_offsets, rec_offsets) -> None:
+        """Variable records + record directory (rec_offsets[n_records+1]): enables the record-parallel kernel."""
+        if _is_cuda_tensor(events):
+            ev = events.contiguous().view(-1)
+            self._keep = [ev, seg_offsets, rec_offsets]
+            self._ck(self._lib.sgr_load_events_indexed_device(self._h, ev.data_ptr(), ev.numel() * ev.element_size(), seg_offsets.data_ptr(),
+                                                              seg_offsets.numel() - 1, rec_offsets.data_ptr(), rec_offsets.numel() - 1))
+            return
+        ev = np.ascontiguousarray(events).view(np.uint8).reshape(-1)
+        off = np.ascontiguousarray(seg_offsets, dtype=np.uint64)
+        ro = np.ascontiguousarray(rec_offsets, dtype=np.uint64)
+        self._ck(self._lib.sgr_load_events_indexed(self._h, ev.ctypes.data, ev.size, off.ctypes.data, len(off) - 1, ro.ctypes.data, len(ro) - 1))
+
     def load_unsorted(self, records, n_agg: int) -> None:
         """Fixed 64-byte records in arrival order; grouped stably by aggregate on the device."""
         if _is_cuda_tensor(records):

@@ -80,6 +80,8 @@ ABI = [
     ("sgr_register_program", C.c_int32, [_P, C.POINTER(sgr_fold_program)]),
     ("sgr_load_events", C.c_int32, [_P, _P, C.c_uint64, _P, C.c_uint64]),
     ("sgr_load_events_device", C.c_int32, [_P, _P, C.c_uint64, _P, C.c_uint64]),
+    ("sgr_load_events_indexed", C.c_int32, [_P, _P, C.c_uint64, _P, C.c_uint64, _P, C.c_uint64]),
+    ("sgr_load_events_indexed_device", C.c_int32, [_P, _P, C.c_uint64, _P, C.c_uint64, _P, C.c_uint64]),
     ("sgr_load_unsorted", C.c_int32, [_P, _P, C.c_uint64, C.c_uint64]),
     ("sgr_load_unsorted_device", C.c_int32, [_P, _P, C.c_uint64, C.c_uint64]),
     ("sgr_set_initial_states", C.c_int32, [_P, _P, C.c_uint64]),

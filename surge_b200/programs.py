@@ -74,3 +74,15 @@ def int_balance_program() -> N.sgr_fold_program:
         (Some(BankAccount(b)), ...)  => Some(BankAccount(b + a))
     = materialise 0 then add (0 + a == a)."""
     return make_program(16, N.REC_FIXED64, [(N.MATERIALISE, [(N.OP_ADD_I32, 0, 16, 4)])])
+
+
+def counter_snapshot_restore_program() -> N.sgr_fold_program:
+    """Today's recovery in the reference: Kafka Streams materialises the compacted STATE topic into a KTable — last
+    write wins per key, a null value deletes (modules/common/src/main/scala/surge/kafka/streams/SurgeStateStoreConsumer.scala:57-76;
+    null = None state, modules/command-engine/core/src/main/scala/surge/internal/SurgeModel.scala:62-64).
+    As a fold over state-snapshot records it is two rules: type 0 (snapshot) = CREATE + SET every state word from the
+    record, type 1 (tombstone) = TOMBSTONE. Counter snapshot record: count @16, version @20."""
+    return make_program(16, N.REC_FIXED64, [
+        (N.CREATE, [(N.OP_SET, 0, 16, 4), (N.OP_SET, 4, 20, 4)]),
+        (N.TOMBSTONE, []),
+    ])

@@ -53,7 +53,7 @@ def interleave_arrival(records: np.ndarray, seed: int) -> np.ndarray:
     return records[perm]
 
 
-def counter_var_csr(n_agg: int, counts, seed: int, payload_min: int = 32, payload_max: int = 512) -> Tuple[np.ndarray, np.ndarray]:
+def counter_var_csr(n_agg: int, counts, seed: int, payload_min: int = 32, payload_max: int = 512, with_directory: bool = False):
     """Counter-with-payload (config 4): variable records, payload length uniform in [min,max],
     first 4 payload bytes = by, the rest is filler the fold must still read.
     Returns (bytes u8[total], seg_offsets u64[n_agg+1])."""
@@ -87,6 +87,8 @@ def counter_var_csr(n_agg: int, counts, seed: int, payload_min: int = 32, payloa
         buf[(rec_off[1:] - j)[sel]] = 0
     seg = np.zeros(n_agg + 1, dtype=np.uint64)
     seg[1:] = rec_off[starts[1:]]
+    if with_directory:
+        return buf, seg, rec_off.astype(np.uint64)
     return buf, seg
 
 

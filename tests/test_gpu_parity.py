@@ -257,6 +257,41 @@ def test_counter_variable_records():
     assert (st.n_events, st.n_errors) == (nev, nerr)
 
 
+@pytest.mark.parametrize("skew", [False, True])
+def test_counter_variable_records_with_directory(skew):
+    """configs[3] shape, small: variable records + record directory -> record-parallel kernel (fold_vruns.cu).
+    skew=True puts ~40 % of all events on one hot aggregate (crosses many warp spans) and adds throwing events."""
+    rng = np.random.default_rng(8)
+    counts = rng.integers(0, 25, size=4000)
+    if skew:
+        counts[1234] = 60_000
+    buf, seg, rec_off = S.counter_var_csr(len(counts), counts, seed=72, with_directory=True)
+    if skew:  # a few throwing events (type 3), one inside the hot aggregate
+        for j in [5, 1000, int(np.searchsorted(rec_off, seg[1234])) + 59_000]:
+            buf[int(rec_off[j]):int(rec_off[j]) + 4] = np.frombuffer(np.uint32(3).tobytes(), np.uint8)
+    want, nev, nerr = O.fold_packed(O.MODEL_COUNTER, O.REC_VAR16, buf, seg)
+    with ReplayEngine(0) as e:
+        e.register_program(P.counter_program(N.REC_VAR16))
+        e.load_events_indexed(buf, seg, rec_off)
+        e.fold()
+        got, st = e.export_states(), e.stats()
+    assert_same(got, want)
+    assert (st.n_events, st.n_errors) == (nev, nerr) and st.fold_launches == 2   # vruns + replay, not the lane-per-aggregate kernel
+
+
+def test_variable_records_directory_disagreeing_with_csr_falls_back():
+    """The CSR is the source of truth: if header aggregate indices do not match it, the engine folds sequentially."""
+    counts = np.array([3, 4, 5, 2])
+    buf, seg, rec_off = S.counter_var_csr(4, counts, seed=73, with_directory=True)
+    buf[int(rec_off[4]) + 12: int(rec_off[4]) + 16] = np.frombuffer(np.uint32(0).tobytes(), np.uint8)  # record 4 claims aggregate 0 instead of 1
+    want, _, _ = O.fold_packed(O.MODEL_COUNTER, O.REC_VAR16, buf, seg)
+    with ReplayEngine(0) as e:
+        e.register_program(P.counter_program(N.REC_VAR16))
+        e.load_events_indexed(buf, seg, rec_off)
+        e.fold()
+        assert_same(e.export_states(), want)
+
+
 def test_variable_records_malformed():
     """Too-short payload for the event class, a record running past its segment, and an over-long record."""
     segs = []
@@ -396,3 +431,31 @@ def test_config2_full_size_properties():
     host = rec.view(n_agg, epa * 16)[torch.as_tensor(sample, device=rec.device)].cpu().numpy().view(np.uint8).reshape(-1)
     want, _, _ = O.fold_packed(O.MODEL_COUNTER, O.REC_FIXED64, host, F.csr_offsets_from_counts([epa] * len(sample)))
     assert np.array_equal(tables[0][sample], want)
+
+
+# ------------------------------------------------------------------ a7: KTable restore of the state topic (last write wins)
+@pytest.mark.parametrize("kernel", [0, 1])
+def test_state_topic_restore_is_last_write_wins(kernel):
+    """AggregateStateStoreKafkaStreamsSpec.scala:64-85 at scale: replaying state snapshots in arrival order leaves, per key,
+    the bytes of the LAST snapshot; a null value (tombstone) deletes the key. Checked against the object-level KTable restatement."""
+    rng = np.random.default_rng(77)
+    n_agg, n = 3000, 40000
+    aggs = rng.integers(0, n_agg, size=n)
+    tomb = rng.random(n) < 0.08
+    counts = rng.integers(-2**31, 2**31, size=n)
+    versions = rng.integers(0, 1000, size=n)
+    rec = F.counter_records(tomb.astype(np.uint32), np.arange(n, dtype=np.uint32), aggs.astype(np.uint64), counts.astype(np.int32))
+    rec["arg1"] = versions.astype(np.int32)
+    table = M.ktable_restore([(str(a), None if t else (int(c), int(v))) for a, t, c, v in zip(aggs, tomb, counts, versions)])
+    with ReplayEngine(0) as e:
+        e.register_program(P.counter_snapshot_restore_program())
+        e.set_option("kernel", kernel)
+        e.load_unsorted(rec, n_agg)
+        e.fold()
+        rows = e.export_states().view(F.COUNTER_STATE).reshape(-1)
+    for a in range(n_agg):
+        want = table.get(str(a))
+        if want is None:
+            assert int(rows[a]["flags"]) & N.ST_EXISTS == 0 and int(rows[a]["count"]) == 0
+        else:
+            assert (int(rows[a]["count"]), int(rows[a]["version"])) == want and int(rows[a]["flags"]) & N.ST_EXISTS
