@@ -459,3 +459,103 @@ def test_state_topic_restore_is_last_write_wins(kernel):
             assert int(rows[a]["flags"]) & N.ST_EXISTS == 0 and int(rows[a]["count"]) == 0
         else:
             assert (int(rows[a]["count"]), int(rows[a]["version"])) == want and int(rows[a]["flags"]) & N.ST_EXISTS
+
+
+# ------------------------------------------------------------------ API behaviour
+def test_pipelined_async_folds_and_wait():
+    rec, off = S.counter_csr(5000, 16, seed=111)
+    want, nev, _ = O.fold_packed(O.MODEL_COUNTER, O.REC_FIXED64, rec, off)
+    with ReplayEngine(0) as e:
+        e.register_program(P.counter_program())
+        e.load_events(rec, off)
+        for _ in range(5):
+            e.set_initial_states(None)   # every fold is a rebuild from None; no host round trip in between
+            e.fold_async()
+        e.wait()
+        assert_same(e.export_states(), want)
+        assert e.stats().n_events == nev
+        # without the reset a second fold appends the same log onto the live table (ApplyEvents on live actors)
+        e.fold()
+        want2, _, _ = O.fold_packed(O.MODEL_COUNTER, O.REC_FIXED64, rec, off, want)
+        assert_same(e.export_states(), want2)
+
+
+def test_error_statuses():
+    with ReplayEngine(0) as e:
+        with pytest.raises(SgrError) as ei:
+            e.load_events(np.zeros(64, np.uint8), np.array([0, 64], np.uint64))
+        assert ei.value.code == N.SGR_ERR_NO_PROGRAM
+        bad = P.counter_program()
+        bad.state_bytes = 20
+        with pytest.raises(SgrError) as ei:
+            e.register_program(bad)
+        assert ei.value.code == N.SGR_ERR_INVALID
+        bad = P.counter_program()
+        bad.rules[0].ops[0].src_off = 62   # reads past the 64-byte record
+        with pytest.raises(SgrError) as ei:
+            e.register_program(bad)
+        assert ei.value.code == N.SGR_ERR_INVALID
+        e.register_program(P.counter_program())
+        with pytest.raises(SgrError) as ei:
+            e.fold()
+        assert ei.value.code == N.SGR_ERR_NOT_LOADED
+        with pytest.raises(SgrError) as ei:
+            e.load_events(np.zeros(128, np.uint8), np.array([0, 24, 128], np.uint64))   # offsets must be multiples of 16
+        assert ei.value.code == N.SGR_ERR_INVALID
+        with pytest.raises(SgrError) as ei:
+            e.fold_incremental(np.zeros(64, np.uint8))   # no live table yet
+        assert ei.value.code == N.SGR_ERR_NOT_LOADED
+        rec, off = S.counter_csr(10, 2, seed=1)
+        e.load_events(rec, off)
+        e.fold()
+        small = np.zeros((5, 16), np.uint8)
+        with pytest.raises(SgrError) as ei:
+            e.export_states(small)
+        assert ei.value.code == N.SGR_ERR_CAPACITY
+        e.load_keys([f"k{i}" for i in range(10)])
+        with pytest.raises(SgrError):
+            e.load_keys(["dup", "dup"])
+
+
+def test_bank_account_incremental_takes_the_sort_based_path():
+    """A program outside the transformer algebra (IF_EXISTS, 64-byte state) appended as micro-batches."""
+    n_agg = 300
+    accts = [str(uuid.UUID(int=i + 1)) for i in range(n_agg)]
+    rng = np.random.default_rng(9)
+    first = b"".join(F.bank_created_record(a, 1, accts[a], f"o{a}", "1", 10.0) for a in range(0, n_agg, 2))   # even accounts exist
+    with ReplayEngine(0) as e:
+        e.register_program(P.bank_account_program())
+        e.set_initial_states(np.zeros((n_agg, 64), np.uint8))
+        e.fold_incremental(np.frombuffer(first, np.uint8))
+        want = O.fold_incremental(O.MODEL_BANK_ACCOUNT, np.frombuffer(first, np.uint8), np.zeros((n_agg, 64), np.uint8))
+        assert_same(e.export_states(), want)
+        for b in range(3):
+            aggs = rng.integers(0, n_agg, size=500)
+            batch = b"".join(F.bank_updated_record(int(a), 10 + b, accts[int(a)], float(b) + 0.5 * int(a)) for a in aggs)
+            want = O.fold_incremental(O.MODEL_BANK_ACCOUNT, np.frombuffer(batch, np.uint8), want)
+            e.fold_incremental(np.frombuffer(batch, np.uint8))
+            assert_same(e.export_states(), want, f"batch {b}")
+        rows = want.view(F.BANK_STATE).reshape(-1)
+        assert not (rows["flags"][1::2] & N.ST_EXISTS).any()   # updates never create an account
+
+
+def test_single_rank_route_and_fold():
+    """The multi-GPU entry point on one rank: ownership tables from the real partitioner, exchange degenerates to the group-by."""
+    from surge_b200 import dist as D
+
+    n_global = 3000
+    counts = np.random.default_rng(3).integers(0, 9, size=n_global)
+    rec, off = S.counter_csr(n_global, counts, seed=31, p_throw=0.002)
+    want, _, _ = O.fold_packed(O.MODEL_COUNTER, O.REC_FIXED64, rec, off)
+    arrival = S.interleave_arrival(rec, seed=32)
+    import torch
+
+    with ReplayEngine(0) as e:
+        e.register_program(P.counter_program())
+        e.dist_init(0, 1, None, len(arrival) + 10)
+        e.dist_set_partitions(D.partitions_for_keys([f"agg-{g}" for g in range(n_global)], 32))
+        e.dist_route_and_fold(torch.from_numpy(arrival.view(np.uint8).reshape(-1).copy()).cuda(), fused=False)
+        gl = e.dist_local_aggregates()
+        assert np.array_equal(gl, np.arange(n_global, dtype=np.uint32))
+        assert_same(e.export_states(), want)
+        assert e.dist_stats().n_recv == len(arrival)
