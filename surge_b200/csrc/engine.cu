@@ -83,7 +83,7 @@ struct sgr_engine {
   uint32_t epoch = 0;
   size_t part_flags_cap_seen = 0;
   bool offsets_aligned64 = false; // every segment offset == log_begin (mod 64)
-  uint64_t log_begin = 0, log_end = 0;
+  uint64_t log_begin = 0, log_end = 0, max_seg_bytes = 0;
   bool fold_pending = false;      // a fold was enqueued and not yet finished
   bool pending_rows_v1 = false, pending_var = false;
   bool pending_used_rows = false, pending_prior = false, pending_timed_group = false;
@@ -216,9 +216,15 @@ constexpr uint64_t kRedoCap = 1u << 20;
 int32_t enqueue_fold(sgr_engine* e, const uint8_t* d_events, const uint64_t* d_offsets, const uint32_t* d_ids,
                      uint64_t n_seg, bool use_prior, uint64_t event_bytes, bool aligned64, uint64_t log_begin, uint64_t log_end) {
   const uint8_t* states_in = use_prior ? (const uint8_t*)e->states.p : nullptr;
-  bool use_rows = e->row_ok && e->program.record_kind == SGR_REC_FIXED64 && aligned64 && e->opt_kernel != 1 && n_seg < (1ull << 32) && n_seg > 0;
+  // 64-byte states: the transformer scan moves 16 registers per lane per step and the lane-per-aggregate TMA kernel is
+  // faster on balanced logs (measured 2.47 vs 1.76 TB/s on BankAccount); the record-parallel kernel is taken when a
+  // long segment would otherwise serialise one lane
+  const bool wide_balanced = e->row_prog.user_words == 14 && e->opt_kernel == 0 && d_offsets == e->d_offsets && e->max_seg_bytes <= (256u << 10);
+  bool use_rows = e->row_ok && !wide_balanced && e->program.record_kind == SGR_REC_FIXED64 && aligned64 && e->opt_kernel != 1 && n_seg < (1ull << 32) && n_seg > 0;
   if ((e->opt_kernel == 2 || e->opt_kernel == 3) && !use_rows && n_seg > 0)
     return fail(e, SGR_ERR_UNSUPPORTED, "record-parallel kernel cannot take this program/log");
+  if (use_rows && e->opt_kernel == 3 && (e->row_prog.user_words != 2 || e->row_prog.cls != 0 || e->row_prog.n_slots > 6))
+    return fail(e, SGR_ERR_UNSUPPORTED, "the record-per-lane kernel takes 16-byte class-0 programs only");
   const bool runs = use_rows && e->opt_kernel != 3;
   unsigned long long* counters = (unsigned long long*)e->counters.p;
   if (runs) {
@@ -234,7 +240,7 @@ int32_t enqueue_fold(sgr_engine* e, const uint8_t* d_events, const uint64_t* d_o
   e->pending_var = false;
   CUDA_TRY(e, cudaEventRecord(e->ev0, e->stream));
   uint32_t launches = 0;
-  const bool use_var = e->row_ok && e->program.record_kind == SGR_REC_VAR16 && e->d_rec_offsets && d_offsets == e->d_offsets && !use_prior &&
+  const bool use_var = e->row_ok && e->row_prog.user_words == 2 && e->row_prog.cls == 0 && e->program.record_kind == SGR_REC_VAR16 && e->d_rec_offsets && d_offsets == e->d_offsets && !use_prior &&
                        !d_ids && e->opt_kernel != 1 && n_seg > 0 && n_seg < (1ull << 32) && e->n_rec > 0;
   if (use_var) {
     int threads = 0; size_t smem = 0; uint32_t stage = 0;
@@ -285,7 +291,7 @@ int32_t enqueue_fold(sgr_engine* e, const uint8_t* d_events, const uint64_t* d_o
       if (!v1 && e->run_max_grid_variant != rv) { e->run_max_grid = run_kernel_max_grid(e->num_sms, rv, e->row_prog); e->run_max_grid_variant = rv; }
       const int max_grid = v1 ? e->row_max_grid : e->run_max_grid;
       const int wpc = v1 ? kRowThreads / 32 : run_warps_per_cta();
-      const uint64_t step_bytes = v1 ? 2048 : (uint64_t)run_variant_step_bytes(rv);
+      const uint64_t step_bytes = v1 ? 2048 : (uint64_t)run_variant_step_bytes(rv, e->row_prog);
       const uint64_t n_warps_max = (uint64_t)max_grid * wpc;
       CUDA_TRY(e, e->part_flags.reserve(n_warps_max * 4 + 256));
       CUDA_TRY(e, e->part_data.reserve(n_warps_max * (e->row_prog.user_words + 2) * 4 + 256));
@@ -474,7 +480,7 @@ static int32_t after_load(sgr_engine* e, const uint8_t* d_events, const uint64_t
   e->offsets_aligned64 = false; e->log_begin = 0; e->log_end = nbytes;
   if (e->program.record_kind == SGR_REC_FIXED64) {
     cudaError_t ce = inspect_offsets(d_offsets, n_agg, (unsigned long long*)e->counters.p, e->stream, &e->offsets_aligned64,
-                                     &e->log_begin, &e->log_end);
+                                     &e->log_begin, &e->log_end, &e->max_seg_bytes);
     if (ce != cudaSuccess) return fail(e, SGR_ERR_CUDA, "offset inspection: %s", cudaGetErrorString(ce));
   }
   return SGR_OK;
@@ -671,7 +677,8 @@ static int32_t fold_incremental_impl(sgr_engine* e, const void* d_records, uint6
   if (e->program.record_kind != SGR_REC_FIXED64) return fail(e, SGR_ERR_UNSUPPORTED, "incremental batches take fixed 64-byte records");
   if (!e->states_valid) return fail(e, SGR_ERR_NOT_LOADED, "incremental fold needs a live state table (fold or set_initial_states first)");
   { int32_t rc0 = finish_fold(e); if (rc0) return rc0; }
-  if (e->row_ok && e->opt_kernel != 1 && e->opt_kernel != 3 && e->opt_incremental != 1) return fold_incremental_atomic(e, d_records, n_records);
+  if (e->row_ok && e->row_prog.user_words == 2 && e->row_prog.cls == 0 && e->opt_kernel != 1 && e->opt_kernel != 3 && e->opt_incremental != 1)
+    return fold_incremental_atomic(e, d_records, n_records);
   e->inc_atomic_prev_valid = false;
   const uint64_t n_agg = e->states_n;
   CUDA_TRY(e, e->inc_offsets.reserve((n_records + 2) * 8));

@@ -129,8 +129,8 @@ __device__ __forceinline__ void finish_segment(const RowArgs& a, uint64_t seg, b
 template <int W, int NS>
 __global__ void __launch_bounds__(kRowThreads, 3) fold_rows_kernel(const __grid_constant__ RowArgs a, const __grid_constant__ RowProgram pg) {
   // per type, one uint4-aligned entry: [0] flags (bit0 valid, bit1 result is None), [1+w] mode | neg<<2 | slot<<3
-  __shared__ __align__(16) uint32_t tab[16 * 8];
-  for (int i = threadIdx.x; i < 16 * 8; i += kRowThreads) tab[i] = pg.tab[i];
+  __shared__ __align__(16) uint32_t tab[16 * kTabStride];
+  for (int i = threadIdx.x; i < 16 * kTabStride; i += kRowThreads) tab[i] = pg.tab[i];
   __syncthreads();
 
   const int lane = threadIdx.x & 31;
@@ -239,7 +239,7 @@ __global__ void __launch_bounds__(kRowThreads, 3) fold_rows_kernel(const __grid_
     if (lane < nvalid) {
       const uint32_t type = sv[0];
       uint4 e0 = make_uint4(0, 0, 0, 0);
-      if (type < 16u) e0 = *reinterpret_cast<const uint4*>(tab + type * 8);
+      if (type < 16u) e0 = *reinterpret_cast<const uint4*>(tab + type * kTabStride);
       if (!(e0.x & 1u)) {
         t.m = M_ERR;  // THROW rule or scala.MatchError: replayed exactly by the sequential kernel
       } else {
@@ -249,7 +249,7 @@ __global__ void __launch_bounds__(kRowThreads, 3) fold_rows_kernel(const __grid_
         if (W > 1) spec[1] = e0.z;
         if (W > 2) spec[2] = e0.w;
 #pragma unroll
-        for (int w = 3; w < W; ++w) spec[w] = tab[type * 8 + 1 + w];
+        for (int w = 3; w < W; ++w) spec[w] = tab[type * kTabStride + 1 + w];
 #pragma unroll
         for (int w = 0; w < W; ++w) {
           uint32_t val = 0;
@@ -402,21 +402,23 @@ __global__ void inspect_offsets_kernel(const uint64_t* __restrict__ off, uint64_
   bool bad = ((b - b0) & 63ull) != 0 || b < b0;
   if (i > 0 && off[i - 1] > b) bad = true;
   if (bad) atomicAdd(out, 1ull);
+  if (i > 0 && b >= off[i - 1]) atomicMax(out + 3, (unsigned long long)(b - off[i - 1]));  // longest segment, bytes
 }
 
 }  // namespace
 
 cudaError_t inspect_offsets(const uint64_t* d_off, uint64_t n_seg, unsigned long long* d_scratch, cudaStream_t st,
-                            bool* aligned64, uint64_t* log_begin, uint64_t* log_end) {
-  cudaError_t e = cudaMemsetAsync(d_scratch, 0, 24, st);
+                            bool* aligned64, uint64_t* log_begin, uint64_t* log_end, uint64_t* max_seg_bytes) {
+  cudaError_t e = cudaMemsetAsync(d_scratch, 0, 32, st);
   if (e != cudaSuccess) return e;
   inspect_offsets_kernel<<<(unsigned)((n_seg + 256) / 256), 256, 0, st>>>(d_off, n_seg, d_scratch);
-  unsigned long long h[3];
-  if ((e = cudaMemcpyAsync(h, d_scratch, 24, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
+  unsigned long long h[4];
+  if ((e = cudaMemcpyAsync(h, d_scratch, 32, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
   if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;
   *aligned64 = h[0] == 0;
   *log_begin = h[1];
   *log_end = h[2];
+  *max_seg_bytes = h[3];
   return cudaSuccess;
 }
 
@@ -425,23 +427,29 @@ namespace {
 
 bool build_row_program(const DevProgram& dp, RowProgram* out) {
   memset(out, 0, sizeof *out);
-  if (dp.user_words != 2) return false;  // instantiated widths (state_bytes 16)
-  if (dp.n_f64) return false;
+  if (dp.user_words != 2 && dp.user_words != 6 && dp.user_words != 14) return false;  // 16 / 32 / 64-byte states
   out->user_words = dp.user_words;
   out->n_slots = 1;
   out->slot_word[0] = 0;  // the event type
+  for (uint32_t f = 0; f < dp.n_f64; ++f) out->f64_mask |= 1u << dp.f64_word[f];
+  bool any_mat = false, any_ifx = false;
+  for (uint32_t t = 0; t < dp.n_types; ++t) {
+    any_mat |= dp.rules[t].exists_rule == SGR_MATERIALISE;
+    any_ifx |= dp.rules[t].exists_rule == SGR_IF_EXISTS;
+  }
+  if (any_mat && any_ifx) return false;  // outside both closed classes
+  out->cls = any_ifx ? 1u : 0u;
   for (uint32_t t = 0; t < dp.n_types; ++t) {
     const DevRule& r = dp.rules[t];
-    uint32_t* e = out->tab + t * 8;
+    uint32_t* e = out->tab + t * kTabStride;
     if (r.exists_rule == SGR_THROW) { e[0] = 0; continue; }
-    if (r.exists_rule == SGR_IF_EXISTS) return false;
-    uint32_t mode[6] = {0, 0, 0, 0, 0, 0}, slot[6] = {0, 0, 0, 0, 0, 0}, neg[6] = {0, 0, 0, 0, 0, 0};
+    uint32_t mode[kMaxRowWords] = {0}, slot[kMaxRowWords] = {0}, neg[kMaxRowWords] = {0};
     const bool reset = r.exists_rule == SGR_CREATE || r.exists_rule == SGR_TOMBSTONE;
     if (reset) for (uint32_t w = 0; w < dp.user_words; ++w) mode[w] = 2;  // SET 0
     for (uint32_t i = 0; i < r.n_ops; ++i) {
       const uint32_t op = r.ops[i];
       const uint32_t opcode = op & 15u, nwords = (op >> 4) & 63u, dw = (op >> 10) & 63u, sw = op >> 16;
-      if (opcode > SGR_OP_SUB_I32) return false;
+      if (opcode > SGR_OP_SUB_I32) return false;  // 64-bit adds carry between words: not a per-word map
       for (uint32_t j = 0; j < nwords; ++j) {
         const uint32_t w = dw + j, src = sw + j;
         if (w >= dp.user_words || src >= (dp.record_kind == SGR_REC_FIXED64 ? 16u : 136u)) return false;
@@ -456,24 +464,24 @@ bool build_row_program(const DevProgram& dp, RowProgram* out) {
         }
         slot[w] = s;
         neg[w] = opcode == SGR_OP_SUB_I32;
-        // over a reset state ADD v == SET v and SUB v == SET -v
-        mode[w] = (opcode == SGR_OP_SET || reset) ? 2u : 1u;
+        mode[w] = (opcode == SGR_OP_SET || reset) ? 2u : 1u;  // over a reset state ADD v == SET v and SUB v == SET -v
       }
     }
-    e[0] = 1u | (r.exists_rule == SGR_TOMBSTONE ? 2u : 0u);
+    e[0] = 1u | (r.exists_rule == SGR_TOMBSTONE ? 2u : 0u) | (r.exists_rule == SGR_IF_EXISTS ? 4u : 0u);
     for (uint32_t w = 0; w < dp.user_words; ++w) e[1 + w] = mode[w] | (neg[w] << 2) | (slot[w] << 3);
   }
   return true;
 }
 
 namespace {
+constexpr int kV1Slots = 6;
 typedef void (*RowKernel)(const RowArgs, const RowProgram);
 RowKernel pick_kernel(const RowProgram& prog) {
-  if (prog.user_words != 2) return nullptr;
+  if (prog.user_words != 2 || prog.cls != 0 || prog.n_slots > (uint32_t)kV1Slots) return nullptr;
   if (prog.n_slots <= 2) return fold_rows_kernel<2, 2>;
   if (prog.n_slots <= 3) return fold_rows_kernel<2, 3>;
   if (prog.n_slots <= 4) return fold_rows_kernel<2, 4>;
-  return fold_rows_kernel<2, kMaxSlots>;
+  return fold_rows_kernel<2, kV1Slots>;
 }
 }  // namespace
 

@@ -9,14 +9,24 @@
 namespace sgr {
 
 constexpr int kRowThreads = 256;
-constexpr int kMaxSlots = 6;  // distinct record words a program may read (slot 0 = event type)
+constexpr int kMaxSlots = 16;   // distinct record words a program may read (slot 0 = event type)
+constexpr int kMaxRowWords = 14;  // widest state in transformer form: 64-byte struct
+constexpr int kTabStride = 16;   // words per type in RowProgram::tab
 
 // Program in transformer form: per event type, how each state word is produced.
+// Two closed classes of programs (build_row_program decides):
+//   class 0  MATERIALISE / CREATE / TOMBSTONE / THROW rules          (Counter, IntBalance, snapshot restore)
+//   class 1  IF_EXISTS / CREATE / TOMBSTONE / THROW rules            (BankAccount): an IF_EXISTS event applies iff the
+//            state exists at that point, i.e. iff the input existed or a CREATE came before it — one extra
+//            composition rule (a tombstoned prefix absorbs it), still associative
+// A program mixing MATERIALISE and IF_EXISTS is outside both and takes the lane-sequential kernel.
 struct RowProgram {
   uint32_t user_words;
   uint32_t n_slots;
-  uint32_t slot_word[kMaxSlots];  // record word index (0..15) of each slot
-  uint32_t tab[16 * 8];           // per type: [0] bit0 valid, bit1 result is None; [1+w] mode | neg<<2 | slot<<3
+  uint32_t cls;                   // 0 / 1, see above
+  uint32_t f64_mask;              // bit w: state words w, w+1 form a JVM Double (numeric == for the publish rule)
+  uint32_t slot_word[kMaxSlots];  // record word index of each slot
+  uint32_t tab[16 * kTabStride];  // per type: [0] bit0 valid, bit1 result is None, bit2 IF_EXISTS rule; [1+w] mode | neg<<2 | slot<<3
 };
 
 struct RowArgs {
@@ -43,7 +53,7 @@ bool build_row_program(const DevProgram& dp, RowProgram* out);
 // one pass over the CSR offsets at load time: are all segments 64-byte aligned relative to the first, and
 // where does the log begin/end (device offsets are opaque to the host otherwise)
 cudaError_t inspect_offsets(const uint64_t* d_off, uint64_t n_seg, unsigned long long* d_scratch, cudaStream_t st,
-                            bool* aligned64, uint64_t* log_begin, uint64_t* log_end);
+                            bool* aligned64, uint64_t* log_begin, uint64_t* log_end, uint64_t* max_seg_bytes);
 int row_kernel_max_grid(int num_sms, const RowProgram& prog);  // largest co-resident grid (look-back needs forward progress)
 cudaError_t launch_fold_rows(const RowArgs& args, const RowProgram& prog, int grid, cudaStream_t stream);
 
@@ -68,7 +78,7 @@ cudaError_t launch_fold_vruns(const VarArgs& args, const RowProgram& prog, int n
 int run_variant_count();
 const char* run_variant_name(int v);
 int run_kernel_max_grid(int num_sms, int variant, const RowProgram& prog);
-int run_variant_step_bytes(int variant);
+int run_variant_step_bytes(int variant, const RowProgram& prog);
 int run_warps_per_cta();
 cudaError_t launch_fold_runs(const RowArgs& args, const RowProgram& prog, int variant, int grid, cudaStream_t stream);
 

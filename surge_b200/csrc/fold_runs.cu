@@ -54,8 +54,11 @@ __device__ __forceinline__ Xf<W> identity() {
   return r;
 }
 // later . earlier  (apply `a` first, then `b`)
-template <int W>
+template <int W, int CLS = 1>
 __device__ __forceinline__ Xf<W> compose(const Xf<W>& a, const Xf<W>& b) {
+  // class 1: b.ex == 0 means b holds only IF_EXISTS events (or nothing); they apply iff the state exists after a — a
+  // tombstoned prefix absorbs them. (In class 0, b.ex == 0 only for the identity, where the plain rule gives a too.)
+  if (CLS == 1 && b.ex == 0u && a.ex == EX_NONE) return a;
   Xf<W> r;
   r.m = a.m | b.m;
   r.ex = b.ex ? b.ex : a.ex;
@@ -92,9 +95,9 @@ __device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) {
 
 // Finish one segment: apply the composed transformer to the prior state, write the state struct.
 template <int W>
-__device__ __forceinline__ void finish_segment(const RowArgs& a, uint32_t seg, const Xf<W>& ts) {
+__device__ __forceinline__ void finish_segment(const RowArgs& a, uint32_t f64_mask, uint32_t seg, const Xf<W>& ts) {
   if (ts.m & M_ERR) {
-    // the handler threw somewhere in the segment: exact replay by the sequential kernel
+    // the handler threw somewhere in the segment: exact replay by the sequential phase
     const unsigned long long pos = atomicAdd(a.counters + 3, 1ull);
     if (pos < a.redo_cap) a.redo_ids[pos] = seg;
     return;
@@ -112,21 +115,29 @@ __device__ __forceinline__ void finish_segment(const RowArgs& a, uint32_t seg, c
 #pragma unroll
     for (int w = 0; w < W; ++w) old[w] = ex0 ? raw[w] : 0u;
   }
-  uint32_t nw[W], exn = ex0;
+  // ts.ex: SOME / NONE = exists-op of the last CREATE/MATERIALISE/TOMBSTONE-class event; 0 = only IF_EXISTS events
+  // (or none at all): the words apply iff the prior state exists
+  const uint32_t exn = ts.ex == EX_NONE ? 0u : (ts.ex == EX_SOME ? (uint32_t)SGR_ST_EXISTS : ex0);
+  uint32_t nw[W];
 #pragma unroll
-  for (int w = 0; w < W; ++w) nw[w] = old[w];
-  if (ts.ex) {
-    exn = (ts.ex == EX_NONE) ? 0u : SGR_ST_EXISTS;
-#pragma unroll
-    for (int w = 0; w < W; ++w) {
-      nw[w] = (ts.m & (2u << (2 * w))) ? ts.v[w] : old[w] + ts.v[w];
-      if (!exn) nw[w] = 0u;
-    }
+  for (int w = 0; w < W; ++w) {
+    nw[w] = (ts.m & (2u << (2 * w))) ? ts.v[w] : old[w] + ts.v[w];
+    if (!exn) nw[w] = 0u;
   }
   uint32_t changed = exn != ex0;
   if (exn && ex0) {
 #pragma unroll
-    for (int w = 0; w < W; ++w) changed |= (nw[w] != old[w]);
+    for (int w = 0; w < W; ++w) {
+      const bool f_lo = (f64_mask >> w) & 1u, f_hi = w > 0 && ((f64_mask >> (w - 1)) & 1u);
+      if (f_lo) {
+        // JVM Double ==: numeric (0.0 == -0.0, NaN != NaN), as Scala case-class equality does
+        const double x = __hiloint2double((int)nw[w + 1 < W ? w + 1 : w], (int)nw[w]);
+        const double y = __hiloint2double((int)old[w + 1 < W ? w + 1 : w], (int)old[w]);
+        changed |= !(x == y);
+      } else if (!f_hi) {
+        changed |= (nw[w] != old[w]);
+      }
+    }
   }
   uint32_t outw[W + 2];
 #pragma unroll
@@ -148,7 +159,7 @@ __device__ __forceinline__ void finish_empty(const RowArgs& a, uint32_t seg) {
 #pragma unroll
     for (int q = 0; q < (W + 2) / 4; ++q) {
       uint4 v4 = __ldg(sp + q);
-      if (q == (W + 2) / 4 - 1) { v4.z &= SGR_ST_EXISTS; v4.w = 0u; if (!v4.z) { v4.x = 0u; v4.y = 0u; } }
+      if (q == (W + 2) / 4 - 1) { v4.z &= SGR_ST_EXISTS; v4.w = 0u; }
       dp[q] = v4;
     }
   } else {
@@ -164,14 +175,17 @@ __host__ __device__ constexpr int warp_smem_bytes() {
          + 32 * 4;           // head bitmap (R words used) + pad
 }
 
-template <int W, int R, int NSTAGE, int NS, int MINB>
+// DIRECT: programs with many source words read each state word's source straight from the staged record instead of
+// pre-fetching NS slots and selecting (NS is then unused)
+template <int W, int R, int NSTAGE, int NS, int MINB, bool DIRECT, int CLS>
 __global__ void __launch_bounds__(kRunThreads, MINB) fold_runs_kernel(const __grid_constant__ RowArgs a, const __grid_constant__ RowProgram pg) {
   static_assert(R % 2 == 0 && 8 % R == 0, "R in {2,4,8}");
   constexpr int STEP_BYTES = 2048 * R;
   constexpr int STEP_RECS = 32 * R;
   extern __shared__ __align__(128) uint8_t smem_raw[];
-  __shared__ __align__(16) uint32_t tab[16 * 8];
-  for (int i = threadIdx.x; i < 16 * 8; i += kRunThreads) tab[i] = pg.tab[i];
+  __shared__ __align__(16) uint32_t tab[16 * kTabStride];
+  for (int i = threadIdx.x; i < 16 * kTabStride; i += kRunThreads) tab[i] = pg.tab[i];
+  const uint32_t f64_mask = pg.f64_mask;
   __syncthreads();
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -254,9 +268,10 @@ __global__ void __launch_bounds__(kRunThreads, MINB) fold_runs_kernel(const __gr
   }
 
   // where lane i finds word (c,k) of a record of parity par: byte (((4*par + c) ^ (i&7)) << 4) + 4k of its 128-byte line
-  uint32_t soff[2][NS];
+  constexpr int NSOFF = DIRECT ? 1 : NS;
+  uint32_t soff[2][NSOFF];
 #pragma unroll
-  for (int s = 0; s < NS; ++s) {
+  for (int s = 0; s < NSOFF; ++s) {
     const uint32_t c = pg.slot_word[s] >> 2, k = pg.slot_word[s] & 3u;
     soff[0][s] = ((c ^ (uint32_t)(lane & 7)) << 4) + (k << 2);
     soff[1][s] = (((4u + c) ^ (uint32_t)(lane & 7)) << 4) + (k << 2);
@@ -328,32 +343,44 @@ __global__ void __launch_bounds__(kRunThreads, MINB) fold_runs_kernel(const __gr
       if (hbits & (1u << t)) {
         const uint32_t eseg = hs_end[p];
         if (!have_first) { first = cur; first_seg = eseg; have_first = true; }
-        else if (eseg != 0xffffffffu) finish_segment<W>(a, eseg, cur);  // began and ended inside this run
+        else if (eseg != 0xffffffffu) finish_segment<W>(a, f64_mask, eseg, cur);  // began and ended inside this run
         cur = identity<W>();
       }
       if (p < nvalid) {
         const uint32_t rec = sbase + (uint32_t)(p >> 1) * 128u;
-        uint32_t sv[NS];
+        const uint32_t lane7 = (uint32_t)(lane & 7), par4 = (uint32_t)(t & 1) * 4u;  // p&1 == t&1: R is even
+        uint32_t sv[DIRECT ? 1 : NS];
+        if (DIRECT) {
+          sv[0] = lds32(rec + soff[t & 1][0]);
+        } else {
 #pragma unroll
-        for (int s = 0; s < NS; ++s) sv[s] = lds32(rec + soff[t & 1][s]);  // p&1 == t&1: R is even
+          for (int s = 0; s < NS; ++s) sv[s] = lds32(rec + soff[t & 1][s]);
+        }
         const uint32_t type = sv[0];
         uint4 e0 = make_uint4(0, 0, 0, 0);
-        if (type < 16u) e0 = *reinterpret_cast<const uint4*>(tab + type * 8);
+        if (type < 16u) e0 = *reinterpret_cast<const uint4*>(tab + type * kTabStride);
         if (!(e0.x & 1u)) {
           cur.m |= M_ERR;  // THROW rule or scala.MatchError
+        } else if (CLS == 1 && (e0.x & 4u) && cur.ex == EX_NONE) {
+          // IF_EXISTS event after a tombstone in this run: the state does not exist, the event is a no-op
         } else {
-          cur.ex = (e0.x & 2u) ? EX_NONE : EX_SOME;
+          if (CLS == 0 || !(e0.x & 4u)) cur.ex = (e0.x & 2u) ? EX_NONE : EX_SOME;  // an IF_EXISTS event leaves the exists-op as it is
           uint32_t spec[W];
           spec[0] = e0.y;
           if (W > 1) spec[1] = e0.z;
           if (W > 2) spec[2] = e0.w;
 #pragma unroll
-          for (int w = 3; w < W; ++w) spec[w] = tab[type * 8 + 1 + w];
+          for (int w = 3; w < W; ++w) spec[w] = tab[type * kTabStride + 1 + w];
 #pragma unroll
           for (int w = 0; w < W; ++w) {
             uint32_t val = 0;
+            if (DIRECT) {
+              const uint32_t sl = spec[w] >> 3;
+              if (sl) { const uint32_t sw = pg.slot_word[sl]; val = lds32(rec + ((((par4 + (sw >> 2)) ^ lane7) << 4) | ((sw & 3u) << 2))); }
+            } else {
 #pragma unroll
-            for (int s = 1; s < NS; ++s) val = ((spec[w] >> 3) == (uint32_t)s) ? sv[s] : val;
+              for (int s = 1; s < NS; ++s) val = ((spec[w] >> 3) == (uint32_t)s) ? sv[s] : val;
+            }
             if (spec[w] & 4u) val = 0u - val;
             const uint32_t mode = spec[w] & 3u;
             if (mode == 2u) cur.v[w] = val;
@@ -368,13 +395,13 @@ __global__ void __launch_bounds__(kRunThreads, MINB) fold_runs_kernel(const __gr
     // ---- once per step: segmented inclusive scan of the 32 lane transformers, in log order -------------
     const uint32_t lane_heads = __ballot_sync(0xffffffffu, have_first);
     Xf<W> sc = cur;
-    if (lane == 0 && !have_first) sc = compose(carry, sc);
+    if (lane == 0 && !have_first) sc = compose<W, CLS>(carry, sc);
 #pragma unroll
     for (int dd = 1; dd < 32; dd <<= 1) {
       const Xf<W> o = shfl_xf(sc, lane - dd);  // wraps for lane < dd; masked below
       const int sh = lane >= dd ? lane - dd + 1 : 0;
       const uint32_t window = (lane_heads >> sh) & ((1u << dd) - 1u);  // a head in lanes (lane-dd, lane]?
-      if (lane >= dd && window == 0) sc = compose(o, sc);
+      if (lane >= dd && window == 0) sc = compose<W, CLS>(o, sc);
     }
     // what flows INTO each lane's run: the scan value of the previous lane (lane 0: the carry)
     Xf<W> cin = shfl_xf(sc, lane - 1);
@@ -383,11 +410,11 @@ __global__ void __launch_bounds__(kRunThreads, MINB) fold_runs_kernel(const __gr
 
     // ---- the segment that ends at a run's first head needs what flowed in ----------------------------------
     if (have_first && first_seg != 0xffffffffu) {
-      const Xf<W> tot = compose(cin, first);
+      const Xf<W> tot = compose<W, CLS>(cin, first);
       // the very first head of the span ends a segment that began in an earlier span: look-back needed
       const bool is_span_first = !span_has_head && (lane_heads & ((1u << lane) - 1u)) == 0;
       if (is_span_first && gw != 0) { inh_t = tot; inh_seg = first_seg; inh_pending = true; }
-      else finish_segment<W>(a, first_seg, tot);
+      else finish_segment<W>(a, f64_mask, first_seg, tot);
     }
     if (lane_heads) {
       // the pending look-back lives in the lane that saw the span's first head: move it to lane 0
@@ -411,7 +438,7 @@ __global__ void __launch_bounds__(kRunThreads, MINB) fold_runs_kernel(const __gr
     for (uint64_t k = kc + lane; k < n_seg; k += 32) finish_empty<W>(a, (uint32_t)k);  // segments kc..n_seg-1 are empty
     if (kc >= 1 && total_steps > 0) {
       // segment kc-1 is the last non-empty one; its transformer is the carry
-      if (span_has_head || gw == 0) { if (lane == 0) finish_segment<W>(a, (uint32_t)(kc - 1), carry); }
+      if (span_has_head || gw == 0) { if (lane == 0) finish_segment<W>(a, f64_mask, (uint32_t)(kc - 1), carry); }
       else end_needs_lookback = true;  // the whole span lies inside that segment
     }
   }
@@ -443,11 +470,11 @@ __global__ void __launch_bounds__(kRunThreads, MINB) fold_runs_kernel(const __gr
         for (int w = 0; w < W; ++w) e.v[w] = ld_volatile_u32(pd + 1 + w);
         const uint32_t tailw = ld_volatile_u32(pd + W + 1);
         e.ex = tailw & 3u;
-        pre = compose(e, pre);
+        pre = compose<W, CLS>(e, pre);
         if (tailw & 4u) break;
       }
-      if (inh_pending) finish_segment<W>(a, inh_seg, compose(pre, inh_t));
-      if (end_needs_lookback) finish_segment<W>(a, (uint32_t)(kc - 1), compose(pre, carry));
+      if (inh_pending) finish_segment<W>(a, f64_mask, inh_seg, compose<W, CLS>(pre, inh_t));
+      if (end_needs_lookback) finish_segment<W>(a, f64_mask, (uint32_t)(kc - 1), compose<W, CLS>(pre, carry));
     }
   }
   // every record of the span was applied; records of throwing segments are taken back by the replay below
@@ -492,12 +519,13 @@ __global__ void __launch_bounds__(kRunThreads, MINB) fold_runs_kernel(const __gr
     for (uint64_t pos = b; pos < e; pos += 64, ++k) {
       const uint32_t* rec = reinterpret_cast<const uint32_t*>(a.events + pos);
       const uint32_t type = rec[pg.slot_word[0]];
-      const uint32_t fl = type < 16u ? tab[type * 8] : 0u;
+      const uint32_t fl = type < 16u ? tab[type * kTabStride] : 0u;
       if (!(fl & 1u)) { threw = true; break; }
       if (fl & 2u) { exn = 0u; for (int w = 0; w < W; ++w) st[w] = 0u; continue; }  // tombstone
+      if ((fl & 4u) && !exn) continue;                                                // IF_EXISTS on None: no-op
 #pragma unroll
       for (int w = 0; w < W; ++w) {
-        const uint32_t spec = tab[type * 8 + 1 + w];
+        const uint32_t spec = tab[type * kTabStride + 1 + w];
         const uint32_t mode = spec & 3u;
         uint32_t val = (spec >> 3) ? rec[pg.slot_word[spec >> 3]] : 0u;
         if (spec & 4u) val = 0u - val;
@@ -517,7 +545,7 @@ __global__ void __launch_bounds__(kRunThreads, MINB) fold_runs_kernel(const __gr
     } else {
       uint32_t changed = exn != ex0;
 #pragma unroll
-      for (int w = 0; w < W; ++w) { if (!exn) st[w] = 0u; if (exn && ex0) changed |= st[w] != old[w]; dp[w] = st[w]; }
+      for (int w = 0; w < W; ++w) { if (!exn) st[w] = 0u; if (exn && ex0) changed |= st[w] != old[w]; dp[w] = st[w]; }  // (a replayed segment that did not throw cannot occur)
       dp[W] = exn | (changed ? SGR_ST_CHANGED : 0u);
       dp[W + 1] = 0u;
     }
@@ -533,18 +561,24 @@ __global__ void __launch_bounds__(kRunThreads, MINB) fold_runs_kernel(const __gr
 }
 
 typedef void (*RunKernel)(const RowArgs, const RowProgram);
-struct RunVariant { RunKernel k[3]; int r, nstage; const char* name; };  // k[i]: NS = 2, 3, kMaxSlots
-#define RUN_VARIANT(R, ST, MINB) {{fold_runs_kernel<2, R, ST, 2, MINB>, fold_runs_kernel<2, R, ST, 3, MINB>, fold_runs_kernel<2, R, ST, kMaxSlots, MINB>}, R, ST, "runs W2 R" #R " st" #ST}
+struct RunVariant { RunKernel k[3]; int r, nstage; const char* name; };  // 16-byte states; k[i]: NS = 2, 3, 6
+#define RUN_VARIANT(R, ST, MINB) {{fold_runs_kernel<2, R, ST, 2, MINB, false, 0>, fold_runs_kernel<2, R, ST, 3, MINB, false, 0>, fold_runs_kernel<2, R, ST, 6, MINB, false, 0>}, R, ST, "runs W2 R" #R " st" #ST}
 const RunVariant kRunVariants[] = {
     RUN_VARIANT(4, 2, 3), RUN_VARIANT(4, 1, 5), RUN_VARIANT(2, 2, 5), RUN_VARIANT(2, 1, 5), RUN_VARIANT(4, 3, 2), RUN_VARIANT(8, 1, 3), RUN_VARIANT(2, 3, 4),
 };
 constexpr int kNumRunVariants = sizeof(kRunVariants) / sizeof(kRunVariants[0]);
+// wider states / many source words: one configuration each (R = 4, 2 stages, direct word reads)
+constexpr int kWideR = 4, kWideStages = 2;
 
-size_t variant_smem(int v) {
-  const int r = kRunVariants[v].r, ns = kRunVariants[v].nstage;
+size_t variant_smem(int v, const RowProgram& prog) {
+  const bool wide = prog.user_words != 2 || prog.n_slots > 6 || prog.cls != 0;
+  const int r = wide ? kWideR : kRunVariants[v].r, ns = wide ? kWideStages : kRunVariants[v].nstage;
   return (size_t)kRunWarps * ((size_t)ns * 2048 * r + 2 * 32 * r * 4 + 32 * 4);
 }
 RunKernel variant_kernel(int v, const RowProgram& prog) {
+  if (prog.user_words == 14) return fold_runs_kernel<14, kWideR, kWideStages, 1, 1, true, 1>;
+  if (prog.user_words == 6) return fold_runs_kernel<6, kWideR, kWideStages, 1, 2, true, 1>;
+  if (prog.n_slots > 6 || prog.cls != 0) return fold_runs_kernel<2, kWideR, kWideStages, 1, 3, true, 1>;
   return kRunVariants[v].k[prog.n_slots <= 2 ? 0 : (prog.n_slots <= 3 ? 1 : 2)];
 }
 
@@ -555,7 +589,7 @@ const char* run_variant_name(int v) { return (v >= 0 && v < kNumRunVariants) ? k
 
 int run_kernel_max_grid(int num_sms, int variant, const RowProgram& prog) {
   if (variant < 0 || variant >= kNumRunVariants) variant = 0;
-  const size_t smem = variant_smem(variant);
+  const size_t smem = variant_smem(variant, prog);
   RunKernel k = variant_kernel(variant, prog);
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   int per_sm = 0;
@@ -563,16 +597,16 @@ int run_kernel_max_grid(int num_sms, int variant, const RowProgram& prog) {
   return per_sm * num_sms;
 }
 
-int run_variant_step_bytes(int variant) {
+int run_variant_step_bytes(int variant, const RowProgram& prog) {
   if (variant < 0 || variant >= kNumRunVariants) variant = 0;
-  return 2048 * kRunVariants[variant].r;
+  const bool wide = prog.user_words != 2 || prog.n_slots > 6 || prog.cls != 0;
+  return 2048 * (wide ? kWideR : kRunVariants[variant].r);
 }
 int run_warps_per_cta() { return kRunWarps; }
 
 cudaError_t launch_fold_runs(const RowArgs& args, const RowProgram& prog, int variant, int grid, cudaStream_t stream) {
-  if (prog.user_words != 2) return cudaErrorInvalidValue;
   if (variant < 0 || variant >= kNumRunVariants) variant = 0;
-  const size_t smem = variant_smem(variant);
+  const size_t smem = variant_smem(variant, prog);
   RunKernel k = variant_kernel(variant, prog);  // its smem attribute was set by run_kernel_max_grid
   k<<<grid, kRunThreads, smem, stream>>>(args, prog);
   return cudaGetLastError();

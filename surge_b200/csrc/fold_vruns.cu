@@ -74,8 +74,8 @@ __device__ __forceinline__ void finish_var(const VarArgs& a, uint32_t seg, const
 template <int NSTAGE>
 __global__ void __launch_bounds__(384) fold_vruns_kernel(const __grid_constant__ VarArgs a, const __grid_constant__ RowProgram pg) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
-  __shared__ __align__(16) uint32_t tab[16 * 8];
-  for (int i = threadIdx.x; i < 16 * 8; i += blockDim.x) tab[i] = pg.tab[i];
+  __shared__ __align__(16) uint32_t tab[16 * kTabStride];
+  for (int i = threadIdx.x; i < 16 * kTabStride; i += blockDim.x) tab[i] = pg.tab[i];
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
   const uint32_t stage_bytes = a.stage_bytes;
@@ -152,13 +152,13 @@ __global__ void __launch_bounds__(384) fold_vruns_kernel(const __grid_constant__
       const uint32_t rec_bytes = 16 + hdr.z;
       ok = ok && hdr.z <= 0x10000u && ((rec_bytes + 15u) & ~15u) == len;          // directory and header agree on the length
       uint32_t fl = 0;
-      if (ok && hdr.x < 16u) fl = tab[hdr.x * 8];
+      if (ok && hdr.x < 16u) fl = tab[hdr.x * kTabStride];
       if (!(fl & 1u)) ok = false;
       if (ok) {
         uint32_t mode[W], val[W];
 #pragma unroll
         for (int w = 0; w < W; ++w) {
-          const uint32_t spec = tab[hdr.x * 8 + 1 + w];
+          const uint32_t spec = tab[hdr.x * kTabStride + 1 + w];
           mode[w] = spec & 3u;
           uint32_t v = 0;
           if (spec >> 3) {

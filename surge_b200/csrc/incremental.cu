@@ -41,11 +41,11 @@ static_assert(sizeof(Scratch) == 32, "scratch entry");
 __device__ __forceinline__ bool decode(const uint32_t* tab, const RowProgram& pg, const uint8_t* rec, uint32_t* fl, uint32_t mode[W], uint32_t val[W]) {
   const uint32_t* r = reinterpret_cast<const uint32_t*>(rec);
   const uint32_t type = r[pg.slot_word[0]];
-  *fl = type < 16u ? tab[type * 8] : 0u;
+  *fl = type < 16u ? tab[type * kTabStride] : 0u;
   if (!(*fl & 1u)) return false;
 #pragma unroll
   for (int w = 0; w < W; ++w) {
-    const uint32_t spec = tab[type * 8 + 1 + w];
+    const uint32_t spec = tab[type * kTabStride + 1 + w];
     mode[w] = spec & 3u;
     uint32_t v = (spec >> 3) ? r[pg.slot_word[spec >> 3]] : 0u;
     if (spec & 4u) v = 0u - v;
@@ -80,8 +80,8 @@ struct IncArgs {
 };
 
 __global__ void __launch_bounds__(256) inc_fused_kernel(const __grid_constant__ IncArgs a, const __grid_constant__ RowProgram pg) {
-  __shared__ uint32_t tab[16 * 8];
-  for (int i = threadIdx.x; i < 16 * 8; i += 256) tab[i] = pg.tab[i];
+  __shared__ uint32_t tab[16 * kTabStride];
+  for (int i = threadIdx.x; i < 16 * kTabStride; i += 256) tab[i] = pg.tab[i];
   __syncthreads();
   const uint64_t tid = (uint64_t)blockIdx.x * 256 + threadIdx.x, nthreads = (uint64_t)gridDim.x * 256;
   unsigned long long* bar = a.counters + 7;

@@ -186,8 +186,11 @@ def test_reference_golden_vectors_on_gpu(kernel):
 
 
 # ------------------------------------------------------------------ other models
-def test_bank_account_model():
-    """BankAccount (f64 copy, strings, IF_EXISTS rule): BankAccountCommandEngineSpec.scala:43-68 + random logs."""
+@pytest.mark.parametrize("kernel", [2, 1])
+def test_bank_account_model(kernel):
+    """BankAccount (f64 copy, strings, IF_EXISTS rule): BankAccountCommandEngineSpec.scala:43-68 + random logs.
+    kernel 2: the 64-byte class-1 instantiation of fold_runs.cu; kernel 1: the lane-sequential kernel
+    (kernel 0 would pick the latter for a balanced log of 64-byte states)."""
     rng = np.random.default_rng(5)
     n_agg = 2000
     blobs, counts = [], []
@@ -209,8 +212,9 @@ def test_bank_account_model():
     rec = np.frombuffer(b"".join(blobs), dtype=np.uint8)
     off = F.csr_offsets_from_counts(counts)
     want, _, _ = O.fold_packed(O.MODEL_BANK_ACCOUNT, O.REC_FIXED64, rec, off)
-    got, _ = run_engine(P.bank_account_program(), rec, off)
+    got, st = run_engine(P.bank_account_program(), rec, off, kernel)
     assert_same(got, want)
+    assert st.fold_launches == 1
     assert F.decode_bank_state(got.view(F.BANK_STATE).reshape(-1)[0]) == {
         "accountNumber": str(uuid.UUID(int=0x1234)), "accountOwner": "Jane Doe", "securityCode": "1234", "balance": 1100.0}
     # second batch on top: the publish rule with JVM Double equality (0.0 == -0.0, NaN != NaN)
@@ -223,10 +227,10 @@ def test_bank_account_model():
     rec2 = np.frombuffer(b"".join(rec2), dtype=np.uint8)
     off2 = F.csr_offsets_from_counts(cnt2)
     want2, _, _ = O.fold_packed(O.MODEL_BANK_ACCOUNT, O.REC_FIXED64, rec2, off2, want)
-    got2, _ = run_engine(P.bank_account_program(), rec2, off2, init=got)
+    got2, _ = run_engine(P.bank_account_program(), rec2, off2, kernel, init=got)
     assert_same(got2, want2)
     want3, _, _ = O.fold_packed(O.MODEL_BANK_ACCOUNT, O.REC_FIXED64, rec2, off2, want2)
-    got3, _ = run_engine(P.bank_account_program(), rec2, off2, init=got2)
+    got3, _ = run_engine(P.bank_account_program(), rec2, off2, kernel, init=got2)
     assert_same(got3, want3)
 
 
@@ -559,3 +563,63 @@ def test_single_rank_route_and_fold():
         assert np.array_equal(gl, np.arange(n_global, dtype=np.uint32))
         assert_same(e.export_states(), want)
         assert e.dist_stats().n_recv == len(arrival)
+
+
+def test_bank_account_long_segments_cross_spans():
+    """IF_EXISTS composition across lanes, steps and warp spans: accounts with thousands of updates, some before the
+    account exists, creations in the middle, and unknown event types (MatchError) in a long segment."""
+    rng = np.random.default_rng(15)
+    counts = [3, 30_000, 0, 12_000, 7, 25_000]
+    blobs = []
+    for a, k in enumerate(counts):
+        acct = str(uuid.UUID(int=a + 1))
+        evs = []
+        created_at = {1: 0, 3: 5000, 5: None}.get(a, 0)      # account 3 is created late, account 5 never
+        for j in range(k):
+            if created_at is not None and j == created_at:
+                evs.append(F.bank_created_record(a, j + 1, acct, f"owner{a}", "42", 100.0))
+            else:
+                evs.append(F.bank_updated_record(a, j + 1, acct, float(j) * 0.5))
+        if a == 1:
+            bad = bytearray(evs[29_000]); bad[0:4] = (7).to_bytes(4, "little"); evs[29_000] = bytes(bad)   # MatchError late in the segment
+        blobs.append(b"".join(evs))
+    rec = np.frombuffer(b"".join(blobs), dtype=np.uint8)
+    off = F.csr_offsets_from_counts(counts)
+    want, _, nerr = O.fold_packed(O.MODEL_BANK_ACCOUNT, O.REC_FIXED64, rec, off)
+    for kernel in (0, 1):
+        got, st = run_engine(P.bank_account_program(), rec, off, kernel)
+        assert_same(got, want, f"kernel {kernel}")
+        assert st.n_errors == nerr == 1
+    rows = want.view(F.BANK_STATE).reshape(-1)
+    assert int(rows[1]["flags"]) == N.ST_ERROR and int(rows[1]["err_idx"]) == 29_000
+    assert not int(rows[5]["flags"]) & N.ST_EXISTS and float(rows[3]["balance"]) == (12_000 - 1) * 0.5
+
+
+def _wide_counter_program():
+    """A 32-byte state outside the sample models: count/version as Counter, plus last `by` (SET), running sum of seq (ADD),
+    and two payload words copied on every counting event; NoOp materialises; type 3 resets everything (CREATE)."""
+    return P.make_program(32, N.REC_FIXED64, [
+        (N.MATERIALISE, [(N.OP_ADD_I32, 0, 16, 4), (N.OP_SET, 4, 4, 4), (N.OP_SET, 8, 16, 4), (N.OP_ADD_I32, 12, 4, 4), (N.OP_SET, 16, 32, 8)]),
+        (N.MATERIALISE, [(N.OP_SUB_I32, 0, 16, 4), (N.OP_SET, 4, 4, 4), (N.OP_SET, 8, 16, 4), (N.OP_ADD_I32, 12, 4, 4)]),
+        (N.MATERIALISE, []),
+        (N.CREATE, [(N.OP_SET, 0, 16, 4)]),
+        (N.TOMBSTONE, []),
+    ])
+
+
+def test_wide_state_program_matches_the_sequential_kernel():
+    """32-byte states on fold_runs.cu (W = 6): no oracle model has this shape, so the lane-sequential kernel — itself
+    pinned to the oracle on every other program — is the reference."""
+    rng = np.random.default_rng(16)
+    counts = np.concatenate([rng.integers(0, 60, size=3000), [40_000]])
+    rec, off = S.counter_csr(len(counts), counts, seed=161)
+    rec["type"] = rng.choice([0, 1, 2, 3, 4, 9], size=len(rec), p=[0.4, 0.4, 0.1, 0.05, 0.04, 0.01]).astype(np.uint32)
+    rec["pad"][:, :8] = rng.integers(0, 256, size=(len(rec), 8), dtype=np.uint8)
+    got0, st0 = run_engine(_wide_counter_program(), rec, off, kernel=0)
+    got1, st1 = run_engine(_wide_counter_program(), rec, off, kernel=1)
+    assert_same(got0, got1)
+    assert (st0.n_events, st0.n_errors) == (st1.n_events, st1.n_errors) and st0.n_errors > 0
+    init = got1.copy()
+    got0b, _ = run_engine(_wide_counter_program(), rec, off, kernel=0, init=init)
+    got1b, _ = run_engine(_wide_counter_program(), rec, off, kernel=1, init=init)
+    assert_same(got0b, got1b)
