@@ -213,11 +213,14 @@ def routed_pipeline(rank, world, local_rank, dev, barrier, note):
     cap = int(n * 1.15) + 1_000_000
     res = {"workload": f"configs[2] shape, weak: {ROUTED_AGG_PER_GPU} aggregates x {epa} events x 64 B originate per GPU, "
                        f"{n_global} aggregates hash-partitioned over {world} rank(s)", "events_total": int(n) * world}
-    for mode, fused in (("nccl_all_to_all", False), ("fused_peer_scatter", True)):
+    # sort-free: the arrived records are folded with integer atomics (K6 kernel), no group-by; sorted_group: K5 + K1
+    for mode, fused, sort_based in (("nccl_all_to_all", False, False), ("fused_peer_scatter", True, False), ("nccl_all_to_all_sorted_group", False, True)):
         if world == 1 and fused:
             continue
         eng = ReplayEngine(local_rank)
         eng.register_program(P.counter_program())
+        if sort_based:
+            eng.set_option("incremental", 1)
         D.exchange_ids(eng, rank, world, cap, fused=fused)
         eng.dist_set_partitions(part)
         best = None
@@ -241,7 +244,7 @@ def routed_pipeline(rank, world, local_rank, dev, barrier, note):
         if world > 1:
             dist.all_reduce(tot)
         assert int(tot[0]) == n * world, (int(tot[0]), n * world)
-        res["single_gpu_group_and_fold" if world == 1 else mode] = {
+        res[("single_gpu_" + ("sorted_group" if sort_based else "sort_free")) if world == 1 else mode] = {
             "events_per_s": n * world / best[0], "ms_wall": best[0] * 1e3, "ms_route_count": best[1], "ms_counts_exchange": best[2],
             "ms_route_scatter": best[3], "ms_exchange": best[4], "ms_group": best[5], "ms_fold": best[6],
             "fold_events_per_s_per_gpu": ds.n_recv / (best[6] * 1e-3) if best[6] else None,

@@ -97,6 +97,7 @@ struct sgr_engine {
   int64_t opt_long_threshold = 0;
   int64_t opt_var_stages = 2;
   int64_t opt_var_stage_bytes = 12288;  // smem bytes staged per 32-record step of the variable-record kernel
+  int64_t opt_replay_budget = 1ll << 34;  // K6: in-kernel replay of throwing slots only while n_err * n stays below this
   int64_t opt_incremental = 0;    // 0 auto (sort-free K6 when the program allows), 1 force the sort-based path
   int64_t opt_max_record_bytes = 528;
 
@@ -652,7 +653,7 @@ static int32_t fold_incremental_atomic(sgr_engine* e, const void* d_records, uin
   }
   cudaError_t le = launch_incremental_atomic((const uint8_t*)d_records, (uint32_t)n_records, n_agg, e->inc_scratch.p, (uint8_t*)e->states.p,
                                              (uint32_t*)e->inc_touched[e->inc_flip].p, (uint32_t*)e->inc_err_ids.p,
-                                             (const uint32_t*)e->inc_touched[e->inc_flip ^ 1].p, prev + 5, prev_upper, e->row_prog, cur, e->stream);
+                                             (const uint32_t*)e->inc_touched[e->inc_flip ^ 1].p, prev + 5, prev_upper, e->row_prog, cur, (unsigned long long)e->opt_replay_budget, e->stream);
   if (le != cudaSuccess) return fail(e, SGR_ERR_CUDA, "incremental launch: %s", cudaGetErrorString(le));
   CUDA_TRY(e, cudaEventRecord(e->ev1, e->stream));
   unsigned long long h[8];
@@ -660,6 +661,29 @@ static int32_t fold_incremental_atomic(sgr_engine* e, const void* d_records, uin
   CUDA_TRY(e, cudaStreamSynchronize(e->stream));
   CUDA_TRY(e, cudaEventElapsedTime(&e->stats.ms_fold, e->ev0, e->ev1));
   if (h[4]) return fail(e, SGR_ERR_INVALID, "%llu records carry an aggregate index >= n_agg; the batch was not applied", h[4]);
+  if (h[2]) {
+    // too many throwing slots to re-scan the batch for each: group the batch once and replay exactly those slots
+    // on the sequential kernel (their states are still the pre-batch ones)
+    DevBuf& grouped = e->group.batch_records;
+    CUDA_TRY(e, grouped.reserve(n_records * 64));
+    CUDA_TRY(e, e->inc_offsets.reserve((n_agg + 2) * 8));
+    unsigned long long bad = 0;
+    cudaError_t ce = group_by_agg_stable(e->group, (const uint8_t*)d_records, n_records, n_agg, (uint8_t*)grouped.p, (uint64_t*)e->inc_offsets.p,
+                                         nullptr, nullptr, (unsigned long long*)e->counters.p, e->stream, &bad);
+    if (ce != cudaSuccess) return fail(e, SGR_ERR_CUDA, "group-by (replay): %s", cudaGetErrorString(ce));
+    CUDA_TRY(e, cudaMemsetAsync(e->counters.p, 0, 64, e->stream));
+    FoldArgs a{};
+    a.events = (const uint8_t*)grouped.p; a.seg_offsets = (const uint64_t*)e->inc_offsets.p; a.n_seg = h[3];
+    a.seg_list = (const uint32_t*)e->inc_err_ids.p; a.states_in = (const uint8_t*)e->states.p; a.states_out = (uint8_t*)e->states.p;
+    a.counters = (unsigned long long*)e->counters.p;
+    FoldLaunchInfo info{};
+    cudaError_t le2 = launch_fold_stream(a, e->dprog, -1, e->num_sms, e->max_record_bytes, e->stream, &info);
+    if (le2 != cudaSuccess) return fail(e, SGR_ERR_CUDA, "replay launch: %s", cudaGetErrorString(le2));
+    unsigned long long h2[8];
+    CUDA_TRY(e, cudaMemcpyAsync(h2, e->counters.p, 64, cudaMemcpyDeviceToHost, e->stream));
+    CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+    h[1] = h2[1]; h[6] = h2[4];   // throwing slots, events dropped after their throw
+  }
   e->inc_atomic_prev_valid = true;
   e->inc_prev_upper = (uint32_t)(h[5]);
   e->inc_flip ^= 1;
@@ -884,19 +908,33 @@ int32_t sgr_dist_route_and_fold(sgr_engine* e, const void* d_records, uint64_t n
   uint64_t n_recv = 0;
   e->stats.ms_h2d = 0;
   if (dist_nranks(e->dist) == 1) {
-    // one rank owns everything and local index == global index: the exchange degenerates to the local group-by
+    // one rank owns everything and local index == global index: no exchange
     dist_clear_stats(e->dist, n_records);
-    rc = load_unsorted_impl(e, d_records, n_records, dist_n_local(e->dist));
-    if (rc) return rc;
   } else {
     int r = dist_route(e->dist, (const uint8_t*)d_records, n_records, fused != 0, (unsigned long long*)e->counters.p, e->stream, &n_recv, &err);
     if (r) return fail(e, r, "%s", err.c_str());
-    rc = load_unsorted_impl(e, dist_recv_buffer(e->dist), n_recv, dist_n_local(e->dist));
+  }
+  const uint8_t* arrived = dist_nranks(e->dist) == 1 ? (const uint8_t*)d_records : dist_recv_buffer(e->dist);
+  const uint64_t n_arrived = dist_nranks(e->dist) == 1 ? n_records : n_recv;
+  const uint64_t n_local = dist_n_local(e->dist);
+  const bool sort_free = e->row_ok && e->row_prog.user_words == 2 && e->row_prog.cls == 0 && e->opt_kernel != 1 && e->opt_kernel != 3 &&
+                         e->opt_incremental != 1 && n_arrived > 0;
+  if (sort_free) {
+    // class-0 programs need no grouping at all: arrival-order records are folded with integer atomics (incremental.cu)
+    rc = ensure_states(e, n_local); if (rc) return rc;
+    CUDA_TRY(e, cudaMemsetAsync(e->states.p, 0, (size_t)n_local * e->program.state_bytes, e->stream));
+    e->states_valid = true; e->inc_atomic_prev_valid = true; e->inc_prev_upper = 0;   // a fresh all-None table: no per-batch flags to clear
+    e->loaded = false;
+    rc = fold_incremental_atomic(e, arrived, n_arrived);
+    if (rc) return rc;
+    e->stats.ms_group = 0;
+  } else {
+    rc = load_unsorted_impl(e, arrived, n_arrived, n_local);
+    if (rc) return rc;
+    e->states_valid = false;
+    rc = sgr_fold(e);
     if (rc) return rc;
   }
-  e->states_valid = false;
-  rc = sgr_fold(e);
-  if (rc) return rc;
   const DistStats* ds = dist_stats(e->dist);
   e->dstats = sgr_dist_stats{};
   e->dstats.n_sent = ds->n_sent; e->dstats.n_sent_remote = ds->n_sent_remote; e->dstats.n_recv = ds->n_recv;
@@ -931,6 +969,7 @@ int32_t sgr_set_option(sgr_engine* e, const char* name, int64_t value) {
   if (!strcmp(name, "fold_variant")) { e->opt_variant = value; return SGR_OK; }
   if (!strcmp(name, "kernel")) { e->opt_kernel = value; return SGR_OK; }
   if (!strcmp(name, "incremental")) { e->opt_incremental = value; return SGR_OK; }
+  if (!strcmp(name, "replay_budget")) { e->opt_replay_budget = value; return SGR_OK; }
   if (!strcmp(name, "var_stage_bytes")) { e->opt_var_stage_bytes = value; return SGR_OK; }
   if (!strcmp(name, "var_stages")) { e->opt_var_stages = value == 3 ? 3 : 2; return SGR_OK; }
   if (!strcmp(name, "run_variant")) {

@@ -77,6 +77,8 @@ struct IncArgs {
   uint32_t* touched_ids; uint32_t* err_ids;
   const uint32_t* prev_ids; const unsigned long long* prev_n;   // previous batch's touched list (prev_n may be null)
   unsigned long long* counters;  // [1] throwing slots [3] error list [4] bad records [5] touched [6] dropped events [7] barrier
+  unsigned long long replay_budget;  // phase D runs only if n_err * n <= budget (it re-scans the batch per throwing slot); beyond
+                                     // that the host replays the queued slots through the sort-based path ([2] is set to 1)
 };
 
 __global__ void __launch_bounds__(256) inc_fused_kernel(const __grid_constant__ IncArgs a, const __grid_constant__ RowProgram pg) {
@@ -156,6 +158,7 @@ __global__ void __launch_bounds__(256) inc_fused_kernel(const __grid_constant__ 
   // ---- phase D: one warp per throwing slot walks the batch in arrival order (exact err_idx, state kept)
   const unsigned long long n_err = ld_volatile_u64(a.counters + 3);
   if (n_err == 0) return;
+  if (n_err * (unsigned long long)a.n > a.replay_budget) { if (tid == 0) a.counters[2] = 1ull; return; }
   const int lane = threadIdx.x & 31;
   const uint64_t warps = (uint64_t)gridDim.x * 8;
   for (uint64_t e = (uint64_t)blockIdx.x * 8 + (threadIdx.x >> 5); e < n_err; e += warps) {
@@ -213,7 +216,7 @@ size_t inc_scratch_bytes(uint64_t n_slots) { return (size_t)n_slots * sizeof(Scr
 cudaError_t launch_incremental_atomic(const uint8_t* d_records, uint32_t n, uint64_t n_slots, void* d_scratch, uint8_t* d_states,
                                       uint32_t* d_touched_ids, uint32_t* d_err_ids, const uint32_t* d_prev_ids,
                                       const unsigned long long* d_prev_n, uint32_t prev_n_upper, const RowProgram& prog,
-                                      unsigned long long* d_counters, cudaStream_t st) {
+                                      unsigned long long* d_counters, unsigned long long replay_budget, cudaStream_t st) {
   static int max_grid = 0;
   if (!max_grid) {
     int per_sm = 0, dev = 0, sms = 0;
@@ -225,7 +228,7 @@ cudaError_t launch_incremental_atomic(const uint8_t* d_records, uint32_t n, uint
   IncArgs a{};
   a.rec = d_records; a.n = n; a.n_slots = n_slots; a.scr = reinterpret_cast<Scratch*>(d_scratch); a.states = d_states;
   a.touched_ids = d_touched_ids; a.err_ids = d_err_ids; a.prev_ids = d_prev_ids; a.prev_n = prev_n_upper ? d_prev_n : nullptr;
-  a.counters = d_counters;
+  a.counters = d_counters; a.replay_budget = replay_budget;
   const uint32_t work = n > prev_n_upper ? n : prev_n_upper;
   if (!work) return cudaSuccess;
   uint32_t g = (work + 255) / 256;

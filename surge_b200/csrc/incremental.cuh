@@ -10,5 +10,5 @@ size_t inc_scratch_bytes(uint64_t n_slots);
 cudaError_t launch_incremental_atomic(const uint8_t* d_records, uint32_t n, uint64_t n_slots, void* d_scratch, uint8_t* d_states,
                                       uint32_t* d_touched_ids, uint32_t* d_err_ids, const uint32_t* d_prev_ids,
                                       const unsigned long long* d_prev_n, uint32_t prev_n_upper, const RowProgram& prog,
-                                      unsigned long long* d_counters, cudaStream_t st);
+                                      unsigned long long* d_counters, unsigned long long replay_budget, cudaStream_t st);
 }  // namespace sgr

@@ -623,3 +623,26 @@ def test_wide_state_program_matches_the_sequential_kernel():
     got0b, _ = run_engine(_wide_counter_program(), rec, off, kernel=0, init=init)
     got1b, _ = run_engine(_wide_counter_program(), rec, off, kernel=1, init=init)
     assert_same(got0b, got1b)
+
+
+def test_micro_batch_with_many_throwing_slots_takes_the_deferred_replay():
+    """K6: when re-scanning the batch per throwing slot would cost too much, the throwing slots are replayed through the
+    sort-based path instead (forced here with a zero budget)."""
+    n_agg = 5000
+    rec, off = S.counter_csr(n_agg, 2, seed=171)
+    want, _, _ = O.fold_packed(O.MODEL_COUNTER, O.REC_FIXED64, rec, off)
+    rng = np.random.default_rng(172)
+    n = 30000
+    batch = F.counter_records(rng.choice([0, 1, 2, 3], size=n, p=[0.4, 0.4, 0.1, 0.1]).astype(np.uint32), np.arange(n, dtype=np.uint32),
+                              rng.integers(0, n_agg, size=n).astype(np.uint64), rng.integers(0, 9, size=n).astype(np.int32))
+    want = O.fold_incremental(O.MODEL_COUNTER, batch, want)
+    with ReplayEngine(0) as e:
+        e.register_program(P.counter_program())
+        e.set_option("replay_budget", 0)
+        e.load_events(rec, off)
+        e.fold()
+        e.fold_incremental(batch)
+        assert_same(e.export_states(), want)
+        st = e.stats()
+        nerr = int((want.view(F.COUNTER_STATE).reshape(-1)["flags"] & N.ST_ERROR != 0).sum())
+        assert st.n_errors == nerr > 1000
