@@ -97,7 +97,8 @@ struct sgr_engine {
   int64_t opt_long_threshold = 0;
   int64_t opt_var_stages = 2;
   int64_t opt_var_stage_bytes = 12288;  // smem bytes staged per 32-record step of the variable-record kernel
-  int64_t opt_replay_budget = 1ll << 34;  // K6: in-kernel replay of throwing slots only while n_err * n stays below this
+  int64_t opt_replay_budget = 1ll << 24;  // K6: in-kernel replay of throwing slots only while n_err * n stays below this
+                                          // (measured ~15 ps per slot-record; beyond it one group-by of the batch is cheaper)
   int64_t opt_incremental = 0;    // 0 auto (sort-free K6 when the program allows), 1 force the sort-based path
   int64_t opt_max_record_bytes = 528;
 
