@@ -77,6 +77,8 @@ struct IncArgs {
   uint32_t* touched_ids; uint32_t* err_ids;
   const uint32_t* prev_ids; const unsigned long long* prev_n;   // previous batch's touched list (prev_n may be null)
   unsigned long long* counters;  // [1] throwing slots [3] error list [4] bad records [5] touched [6] dropped events [7] barrier
+  uint32_t fast2;                    // every state word is add-only or set-only across the program: phases A and B fuse
+  uint32_t set_only_mask;            // bit w: word w is only ever SET (otherwise, in fast2 mode, only ever ADDed)
   unsigned long long replay_budget;  // phase D runs only if n_err * n <= budget (it re-scans the batch per throwing slot); beyond
                                      // that the host replays the queued slots through the sort-based path ([2] is set to 1)
 };
@@ -98,6 +100,54 @@ __global__ void __launch_bounds__(256) inc_fused_kernel(const __grid_constant__ 
       *p = v;
     }
   }
+  if (a.fast2) {
+    // ---- phase A+B fused. Scratch words are reinterpreted: [0] (arrival index + 1) << 2 | exists-op of the last event,
+    //      [1] flags, then one u64 per state word: add-only word -> low half accumulates; set-only word -> max of
+    //      (arrival index + 1) << 32 | value, i.e. the value of the LAST set. No second pass is needed because no word
+    //      ever sees both a SET and an ADD.
+    for (uint64_t i = tid; i < a.n; i += nthreads) {
+      const uint8_t* r = a.rec + i * 64;
+      const unsigned long long slot = *reinterpret_cast<const unsigned long long*>(r + 8);
+      if (slot >= a.n_slots) { atomicAdd(a.counters + 4, 1ull); continue; }
+      uint32_t* sw = reinterpret_cast<uint32_t*>(a.scr + slot);
+      unsigned long long* s64 = reinterpret_cast<unsigned long long*>(sw + 2);
+      uint32_t fl, mode[W], val[W];
+      if (!decode(tab, pg, r, &fl, mode, val)) { atomicOr(sw + 1, 1u); atomicMax(sw, (((uint32_t)i + 1) << 2) | 3u); continue; }
+      atomicMax(sw, (((uint32_t)i + 1) << 2) | ((fl & 2u) ? 2u : 1u));
+#pragma unroll
+      for (int w = 0; w < W; ++w) {
+        if (mode[w] == 1u) { if (val[w]) atomicAdd(reinterpret_cast<uint32_t*>(s64 + w), val[w]); }
+        else if (mode[w] == 2u) atomicMax(s64 + w, ((unsigned long long)((uint32_t)i + 1) << 32) | val[w]);
+      }
+    }
+    grid_barrier(bar, gridDim.x);
+    const bool rejected2 = ld_volatile_u64(a.counters + 4) != 0;
+    for (uint64_t i = tid; i < a.n; i += nthreads) {
+      const unsigned long long slot = *reinterpret_cast<const unsigned long long*>(a.rec + i * 64 + 8);
+      if (slot >= a.n_slots) continue;
+      Scratch* sp = a.scr + slot;
+      const uint4 s0 = *reinterpret_cast<const uint4*>(sp);        // last_event|ex, flags, word0 (lo, hi)
+      if ((s0.x >> 2) != (uint32_t)i + 1) continue;                // only the slot's last event finishes it
+      const uint4 s1 = reinterpret_cast<const uint4*>(sp)[1];      // word1 (lo, hi), unused
+      reinterpret_cast<uint4*>(sp)[0] = make_uint4(0, 0, 0, 0);
+      reinterpret_cast<uint4*>(sp)[1] = make_uint4(0, 0, 0, 0);
+      if (rejected2) continue;
+      a.touched_ids[atomicAdd(a.counters + 5, 1ull)] = (uint32_t)slot;
+      if (s0.y & 1u) { a.err_ids[atomicAdd(a.counters + 3, 1ull)] = (uint32_t)slot; continue; }
+      uint4* st = reinterpret_cast<uint4*>(a.states + slot * ((W + 2) * 4));
+      const uint4 old = *st;
+      const uint32_t ex0 = old.z & SGR_ST_EXISTS;
+      const uint32_t exn = ((s0.x & 3u) == 2u) ? 0u : SGR_ST_EXISTS;
+      const uint32_t b0 = ex0 ? old.x : 0u, b1 = ex0 ? old.y : 0u;
+      uint32_t n0 = (a.set_only_mask & 1u) ? (s0.w ? s0.z : b0) : b0 + s0.z;
+      uint32_t n1 = (a.set_only_mask & 2u) ? (s1.y ? s1.x : b1) : b1 + s1.x;
+      if (!exn) { n0 = 0; n1 = 0; }
+      uint32_t changed = exn != ex0;
+      if (exn && ex0) changed |= (n0 != old.x) | (n1 != old.y);
+      *st = make_uint4(n0, n1, exn | (changed ? SGR_ST_CHANGED : 0u), 0u);
+    }
+    grid_barrier(bar, 2ull * gridDim.x);
+  } else {
   // ---- phase A: last event and last SET per slot
   for (uint64_t i = tid; i < a.n; i += nthreads) {
     const uint8_t* r = a.rec + i * 64;
@@ -155,6 +205,7 @@ __global__ void __launch_bounds__(256) inc_fused_kernel(const __grid_constant__ 
     *st = make_uint4(n0, n1, exn | (changed ? SGR_ST_CHANGED : 0u), 0u);
   }
   grid_barrier(bar, 3ull * gridDim.x);
+  }  // general (three-phase) mode
   // ---- phase D: one warp per throwing slot walks the batch in arrival order (exact err_idx, state kept)
   const unsigned long long n_err = ld_volatile_u64(a.counters + 3);
   if (n_err == 0) return;
@@ -229,6 +280,18 @@ cudaError_t launch_incremental_atomic(const uint8_t* d_records, uint32_t n, uint
   a.rec = d_records; a.n = n; a.n_slots = n_slots; a.scr = reinterpret_cast<Scratch*>(d_scratch); a.states = d_states;
   a.touched_ids = d_touched_ids; a.err_ids = d_err_ids; a.prev_ids = d_prev_ids; a.prev_n = prev_n_upper ? d_prev_n : nullptr;
   a.counters = d_counters; a.replay_budget = replay_budget;
+  // add-only / set-only analysis over every valid event type
+  uint32_t has_add = 0, has_set = 0;
+  for (int t = 0; t < 16; ++t) {
+    if (!(prog.tab[t * kTabStride] & 1u)) continue;
+    for (int w = 0; w < W; ++w) {
+      const uint32_t mode = prog.tab[t * kTabStride + 1 + w] & 3u;
+      if (mode == 1u) has_add |= 1u << w;
+      if (mode == 2u) has_set |= 1u << w;
+    }
+  }
+  a.fast2 = ((has_add & has_set) == 0 && n < (1u << 30)) ? 1u : 0u;
+  a.set_only_mask = has_set;
   const uint32_t work = n > prev_n_upper ? n : prev_n_upper;
   if (!work) return cudaSuccess;
   uint32_t g = (work + 255) / 256;

@@ -646,3 +646,32 @@ def test_micro_batch_with_many_throwing_slots_takes_the_deferred_replay():
         st = e.stats()
         nerr = int((want.view(F.COUNTER_STATE).reshape(-1)["flags"] & N.ST_ERROR != 0).sum())
         assert st.n_errors == nerr > 1000
+
+
+def test_micro_batches_with_a_word_that_is_both_set_and_added():
+    """K6 general (three-phase) mode: a state word that sees SETs and ADDs needs the 'adds after the last SET' rule.
+    No oracle model has this shape; the sort-based path (K5 + sequential kernel, pinned elsewhere) is the reference."""
+    prog = P.make_program(16, N.REC_FIXED64, [
+        (N.MATERIALISE, [(N.OP_ADD_I32, 0, 16, 4), (N.OP_SET, 4, 4, 4)]),      # count += by, version = seq
+        (N.MATERIALISE, [(N.OP_SET, 0, 16, 4)]),                               # count = by
+        (N.TOMBSTONE, []),
+        (N.CREATE, [(N.OP_SUB_I32, 0, 16, 4)]),                                # reset, count = -by
+    ])
+    n_agg = 3000
+    rng = np.random.default_rng(181)
+    tables = []
+    for path in (0, 1):
+        rng = np.random.default_rng(181)
+        with ReplayEngine(0) as e:
+            e.register_program(prog)
+            e.set_option("incremental", path)
+            e.set_initial_states(np.zeros((n_agg, 16), np.uint8))
+            for b in range(4):
+                n = 20000
+                batch = F.counter_records(rng.choice([0, 1, 2, 3, 7], size=n, p=[0.6, 0.2, 0.05, 0.1, 0.05]).astype(np.uint32),
+                                          np.arange(n, dtype=np.uint32) + 7 * b, rng.integers(0, n_agg, size=n).astype(np.uint64),
+                                          rng.integers(-50, 50, size=n).astype(np.int32))
+                e.fold_incremental(batch)
+            tables.append(e.export_states())
+    assert_same(tables[0], tables[1])
+    assert (tables[0].view(F.COUNTER_STATE).reshape(-1)["flags"] & N.ST_ERROR).any()
