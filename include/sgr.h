@@ -203,6 +203,13 @@ int32_t sgr_load_events_indexed_device(sgr_engine* e, const void* d_events, uint
 int32_t sgr_load_unsorted(sgr_engine* e, const void* records, uint64_t n_records, uint64_t n_agg);
 int32_t sgr_load_unsorted_device(sgr_engine* e, const void* d_records, uint64_t n_records, uint64_t n_agg);
 
+/* Rebuild every state from an arrival-order log in one call (the shape of a Kafka partition log: aggregates
+ * interleaved, each aggregate's own order kept), without exposing a CSR log afterwards. Programs inside the
+ * transformer algebra with add-only / set-only words need no grouping at all (integer-atomic fold); others are grouped
+ * and folded as sgr_load_unsorted + sgr_fold would. */
+int32_t sgr_fold_unsorted(sgr_engine* e, const void* records, uint64_t n_records, uint64_t n_agg);
+int32_t sgr_fold_unsorted_device(sgr_engine* e, const void* d_records, uint64_t n_records, uint64_t n_agg);
+
 /* Prior states for an incremental fold (None everywhere if never called):
  * the actor's state before ApplyEvents, PersistentActor.scala:245-264. states may be NULL to reset. */
 int32_t sgr_set_initial_states(sgr_engine* e, const void* states, uint64_t n_agg);

@@ -851,6 +851,52 @@ int32_t sgr_get_stats(sgr_engine* e, sgr_stats* out) {
   return SGR_OK;
 }
 
+// Fold an arrival-order log (aggregates interleaved, per-aggregate order kept) from None.
+// class-0 programs need no grouping at all: the records are folded with integer atomics (incremental.cu);
+// other programs are grouped stably (K5) and folded from the CSR.
+static int32_t fold_arrival_order(sgr_engine* e, const uint8_t* d_records, uint64_t n_records, uint64_t n_agg) {
+  const bool sort_free = e->row_ok && e->row_prog.user_words == 2 && e->row_prog.cls == 0 && e->opt_kernel != 1 && e->opt_kernel != 3 &&
+                         e->opt_incremental != 1 && n_records > 0;
+  int32_t rc;
+  if (sort_free) {
+    rc = ensure_states(e, n_agg); if (rc) return rc;
+    CUDA_TRY(e, cudaMemsetAsync(e->states.p, 0, (size_t)n_agg * e->program.state_bytes, e->stream));
+    e->states_valid = true; e->inc_atomic_prev_valid = true; e->inc_prev_upper = 0;   // a fresh all-None table: no per-batch flags to clear
+    e->loaded = false;
+    rc = fold_incremental_atomic(e, d_records, n_records);
+    if (rc) return rc;
+    e->stats.ms_group = 0;
+    return SGR_OK;
+  }
+  rc = load_unsorted_impl(e, d_records, n_records, n_agg);
+  if (rc) return rc;
+  e->states_valid = false;
+  return sgr_fold(e);
+}
+
+int32_t sgr_fold_unsorted_device(sgr_engine* e, const void* d_records, uint64_t n_records, uint64_t n_agg) {
+  if (!e || (!d_records && n_records)) return fail(e, SGR_ERR_INVALID, "null argument");
+  if (!e->has_program) return fail(e, SGR_ERR_NO_PROGRAM, "register a fold program first");
+  if (e->program.record_kind != SGR_REC_FIXED64) return fail(e, SGR_ERR_UNSUPPORTED, "arrival-order logs take fixed 64-byte records");
+  int32_t rc = before_load(e); if (rc) return rc;
+  e->stats.ms_h2d = 0;
+  return fold_arrival_order(e, (const uint8_t*)d_records, n_records, n_agg);
+}
+
+int32_t sgr_fold_unsorted(sgr_engine* e, const void* records, uint64_t n_records, uint64_t n_agg) {
+  if (!e || (!records && n_records)) return fail(e, SGR_ERR_INVALID, "null argument");
+  if (!e->has_program) return fail(e, SGR_ERR_NO_PROGRAM, "register a fold program first");
+  if (e->program.record_kind != SGR_REC_FIXED64) return fail(e, SGR_ERR_UNSUPPORTED, "arrival-order logs take fixed 64-byte records");
+  int32_t rc = before_load(e); if (rc) return rc;
+  CUDA_TRY(e, e->inc_records.reserve(n_records * 64));
+  CUDA_TRY(e, cudaEventRecord(e->ev2, e->stream));
+  CUDA_TRY(e, cudaMemcpyAsync(e->inc_records.p, records, n_records * 64, cudaMemcpyHostToDevice, e->stream));
+  CUDA_TRY(e, cudaEventRecord(e->ev3, e->stream));
+  CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+  CUDA_TRY(e, cudaEventElapsedTime(&e->stats.ms_h2d, e->ev2, e->ev3));
+  return fold_arrival_order(e, (const uint8_t*)e->inc_records.p, n_records, n_agg);
+}
+
 // ------------------------------------------------------------------ multi-GPU
 int32_t sgr_dist_unique_id(void* out128) {
   if (!out128) return SGR_ERR_INVALID;
@@ -917,25 +963,8 @@ int32_t sgr_dist_route_and_fold(sgr_engine* e, const void* d_records, uint64_t n
   }
   const uint8_t* arrived = dist_nranks(e->dist) == 1 ? (const uint8_t*)d_records : dist_recv_buffer(e->dist);
   const uint64_t n_arrived = dist_nranks(e->dist) == 1 ? n_records : n_recv;
-  const uint64_t n_local = dist_n_local(e->dist);
-  const bool sort_free = e->row_ok && e->row_prog.user_words == 2 && e->row_prog.cls == 0 && e->opt_kernel != 1 && e->opt_kernel != 3 &&
-                         e->opt_incremental != 1 && n_arrived > 0;
-  if (sort_free) {
-    // class-0 programs need no grouping at all: arrival-order records are folded with integer atomics (incremental.cu)
-    rc = ensure_states(e, n_local); if (rc) return rc;
-    CUDA_TRY(e, cudaMemsetAsync(e->states.p, 0, (size_t)n_local * e->program.state_bytes, e->stream));
-    e->states_valid = true; e->inc_atomic_prev_valid = true; e->inc_prev_upper = 0;   // a fresh all-None table: no per-batch flags to clear
-    e->loaded = false;
-    rc = fold_incremental_atomic(e, arrived, n_arrived);
-    if (rc) return rc;
-    e->stats.ms_group = 0;
-  } else {
-    rc = load_unsorted_impl(e, arrived, n_arrived, n_local);
-    if (rc) return rc;
-    e->states_valid = false;
-    rc = sgr_fold(e);
-    if (rc) return rc;
-  }
+  rc = fold_arrival_order(e, arrived, n_arrived, dist_n_local(e->dist));
+  if (rc) return rc;
   const DistStats* ds = dist_stats(e->dist);
   e->dstats = sgr_dist_stats{};
   e->dstats.n_sent = ds->n_sent; e->dstats.n_sent_remote = ds->n_sent_remote; e->dstats.n_recv = ds->n_recv;

@@ -106,6 +106,16 @@ class ReplayEngine:
         r = np.ascontiguousarray(records).view(np.uint8).reshape(-1)
         self._ck(self._lib.sgr_load_unsorted(self._h, r.ctypes.data, r.size // 64, n_agg))
 
+    def fold_unsorted(self, records, n_agg: int) -> None:
+        """Rebuild all states from an arrival-order log (Kafka partition order) in one call."""
+        if _is_cuda_tensor(records):
+            r = records.contiguous().view(-1)
+            self._keep = [r]
+            self._ck(self._lib.sgr_fold_unsorted_device(self._h, r.data_ptr(), r.numel() * r.element_size() // 64, n_agg))
+            return
+        r = np.ascontiguousarray(records).view(np.uint8).reshape(-1)
+        self._ck(self._lib.sgr_fold_unsorted(self._h, r.ctypes.data, r.size // 64, n_agg))
+
     def set_initial_states(self, states: Optional[np.ndarray]) -> None:
         if states is None:
             self._ck(self._lib.sgr_set_initial_states(self._h, None, 0))

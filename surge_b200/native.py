@@ -84,6 +84,8 @@ ABI = [
     ("sgr_load_events_indexed_device", C.c_int32, [_P, _P, C.c_uint64, _P, C.c_uint64, _P, C.c_uint64]),
     ("sgr_load_unsorted", C.c_int32, [_P, _P, C.c_uint64, C.c_uint64]),
     ("sgr_load_unsorted_device", C.c_int32, [_P, _P, C.c_uint64, C.c_uint64]),
+    ("sgr_fold_unsorted", C.c_int32, [_P, _P, C.c_uint64, C.c_uint64]),
+    ("sgr_fold_unsorted_device", C.c_int32, [_P, _P, C.c_uint64, C.c_uint64]),
     ("sgr_set_initial_states", C.c_int32, [_P, _P, C.c_uint64]),
     ("sgr_fold", C.c_int32, [_P]),
     ("sgr_fold_async", C.c_int32, [_P]),

@@ -675,3 +675,36 @@ def test_micro_batches_with_a_word_that_is_both_set_and_added():
             tables.append(e.export_states())
     assert_same(tables[0], tables[1])
     assert (tables[0].view(F.COUNTER_STATE).reshape(-1)["flags"] & N.ST_ERROR).any()
+
+
+@pytest.mark.parametrize("prog_name", ["counter", "bank"])
+def test_fold_unsorted_one_call(prog_name):
+    """sgr_fold_unsorted: an arrival-order log straight to states. Counter takes the sort-free atomic fold, BankAccount the
+    group-by + fold; both must equal the oracle's fold of the grouped log, and a following micro-batch must append correctly."""
+    rng = np.random.default_rng(191)
+    n_agg = 4000
+    if prog_name == "counter":
+        counts = rng.integers(0, 30, size=n_agg)
+        rec, off = S.counter_csr(n_agg, counts, seed=192, p_throw=0.003)
+        model, prog = O.MODEL_COUNTER, P.counter_program()
+        arrival = S.interleave_arrival(rec, seed=193)
+    else:
+        blobs, counts = [], []
+        for a in range(n_agg):
+            acct = str(uuid.UUID(int=a + 1)); k = int(rng.integers(0, 6))
+            evs = [F.bank_created_record(a, 1, acct, "o", "c", 1.0)] if k and rng.random() < 0.7 else []
+            evs += [F.bank_updated_record(a, j + 2, acct, float(j)) for j in range(max(k - len(evs), 0))]
+            blobs.append(b"".join(evs)); counts.append(len(evs))
+        rec = np.frombuffer(b"".join(blobs), dtype=np.uint8).view(F.REC64)
+        off = F.csr_offsets_from_counts(counts)
+        model, prog = O.MODEL_BANK_ACCOUNT, P.bank_account_program()
+        arrival = S.interleave_arrival(rec, seed=193)
+    want, nev, nerr = O.fold_packed(model, O.REC_FIXED64, rec, off)
+    with ReplayEngine(0) as e:
+        e.register_program(prog)
+        e.fold_unsorted(arrival, n_agg)
+        assert_same(e.export_states(), want)
+        assert (e.stats().n_events, e.stats().n_errors) == (nev, nerr)
+        batch = arrival[:777].copy()
+        e.fold_incremental(batch)
+        assert_same(e.export_states(), O.fold_incremental(model, batch, want))
