@@ -108,8 +108,7 @@ __global__ void __launch_bounds__(kRouteThreads) route_scatter_kernel(const uint
   __shared__ uint8_t down[kRouteThreads];
   __shared__ uint32_t dloc[kRouteThreads];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (threadIdx.x < nranks) run[threadIdx.x] = block_base[threadIdx.x * nblocks + blockIdx.x];  // relative to the owner's region
-  (void)owner_total_ex;
+  if (threadIdx.x < nranks) run[threadIdx.x] = block_base[threadIdx.x * nblocks + blockIdx.x] - owner_total_ex[threadIdx.x];  // relative to the owner's region
   __syncthreads();
   const uint64_t base = (uint64_t)blockIdx.x * kRouteBlockRecs;
   for (int it = 0; it < kRouteBlockRecs / kRouteThreads; ++it) {
@@ -156,23 +155,15 @@ __global__ void __launch_bounds__(kRouteThreads) route_scatter_kernel(const uint
   }
 }
 
-// exclusive scan over owners of the per-owner totals, and per-(owner, block) bases. Small: done by one block.
-__global__ void route_scan_kernel(uint32_t* __restrict__ hist, uint32_t nblocks, uint32_t nranks, uint32_t* __restrict__ owner_total,
-                                  uint32_t* __restrict__ owner_total_ex) {
-  // thread r scans row r sequentially (nblocks is n/2048: up to a few hundred thousand; rows are contiguous)
-  __shared__ uint32_t tot[kMaxRanks];
+// after the device-wide exclusive scan of hist (row-major [owner][block], one zero row appended): row r starts at
+// hist[r * nblocks]; per-owner totals are differences of consecutive row starts
+__global__ void route_totals_kernel(const uint32_t* __restrict__ hist, uint32_t nblocks, uint32_t* __restrict__ owner_total,
+                                    uint32_t* __restrict__ owner_total_ex) {
   const uint32_t r = threadIdx.x;
-  if (r < nranks) {
-    uint32_t acc = 0;
-    uint32_t* row = hist + (size_t)r * nblocks;
-    for (uint32_t b = 0; b < nblocks; ++b) { const uint32_t c = row[b]; row[b] = acc; acc += c; }
-    tot[r] = acc;
-    owner_total[r] = acc;
-  }
-  __syncthreads();
-  if (r == 0) {
-    uint32_t acc = 0;
-    for (uint32_t q = 0; q < nranks; ++q) { owner_total_ex[q] = acc; acc += tot[q]; }
+  if (r < (uint32_t)kMaxRanks) {
+    const uint32_t s0 = hist[(size_t)r * nblocks], s1 = hist[(size_t)(r + 1) * nblocks];
+    owner_total_ex[r] = s0;
+    owner_total[r] = s1 - s0;
   }
 }
 
@@ -254,7 +245,7 @@ int dist_init(DistState* d, int rank, int nranks, const void* unique_id, uint64_
     ncclResult_t r = g_nccl.CommInitRank(&d->comm, nranks, id, rank);
     if (r != ncclSuccess) { *err = std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(r); return SGR_ERR_DIST; }
   }
-  cudaError_t ce = nranks > 1 ? d->recv_buf.reserve(recv_capacity_records * 64) : cudaSuccess;
+  cudaError_t ce = d->recv_buf.reserve((nranks > 1 || recv_capacity_records) ? recv_capacity_records * 64 : 0);
   if (ce != cudaSuccess) { *err = std::string("receive buffer: ") + cudaGetErrorString(ce); return SGR_ERR_OOM; }
   d->peer_recv[rank] = (uint8_t*)d->recv_buf.p;
   (void)st;
@@ -339,7 +330,8 @@ int dist_route(DistState* d, const uint8_t* d_records, uint64_t n, bool fused, u
   if (fused && d->nranks > 1 && !d->peers_mapped) { *err = "fused route needs the peers' receive buffers (sgr_dist_ipc_import)"; return SGR_ERR_NOT_LOADED; }
   const int R = d->nranks;
   const uint32_t nblocks = n ? cdiv64(n, kRouteBlockRecs) : 1;
-  DTRY(d->hist.reserve((size_t)kMaxRanks * nblocks * 4));
+  DTRY(d->hist.reserve((size_t)(kMaxRanks + 1) * nblocks * 4 + 64));
+  DTRY(d->scan_tmp.reserve(((size_t)2 * (((size_t)(kMaxRanks + 1) * nblocks) / 4096 + 2) + 4 * 4096) * 4));
   DTRY(d->owner_total.reserve(2 * kMaxRanks * 4));
   DTRY(d->counts_all.reserve((size_t)kMaxRanks * kMaxRanks * 8 + 64));
   uint32_t* owner_total = (uint32_t*)d->owner_total.p;
@@ -347,10 +339,11 @@ int dist_route(DistState* d, const uint8_t* d_records, uint64_t n, bool fused, u
 
   DTRY(cudaEventRecord(d->ev[0], st));
   DTRY(cudaMemsetAsync(d_counters, 0, 64, st));
-  DTRY(cudaMemsetAsync(d->hist.p, 0, (size_t)kMaxRanks * nblocks * 4, st));
+  DTRY(cudaMemsetAsync(d->hist.p, 0, (size_t)(kMaxRanks + 1) * nblocks * 4 + 64, st));
   if (n) route_count_kernel<<<nblocks, kRouteThreads, 0, st>>>(d_records, n, d->n_global, (const uint8_t*)d->owner_of.p, (uint32_t)R,
                                                                (uint32_t*)d->hist.p, nblocks, d_counters + 4);
-  route_scan_kernel<<<1, 32, 0, st>>>((uint32_t*)d->hist.p, nblocks, (uint32_t)R, owner_total, owner_total_ex);
+  DTRY(exclusive_scan_u32_public((const uint32_t*)d->hist.p, (uint32_t*)d->hist.p, (uint32_t)((size_t)kMaxRanks * nblocks + 1), (uint32_t*)d->scan_tmp.p, st));
+  route_totals_kernel<<<1, 32, 0, st>>>((const uint32_t*)d->hist.p, nblocks, owner_total, owner_total_ex);
   DTRY(cudaGetLastError());
   DTRY(cudaEventRecord(d->ev[1], st));
 

@@ -99,6 +99,7 @@ struct sgr_engine {
   int64_t opt_var_stage_bytes = 12288;  // smem bytes staged per 32-record step of the variable-record kernel
   int64_t opt_replay_budget = 1ll << 24;  // K6: in-kernel replay of throwing slots only while n_err * n stays below this
                                           // (measured ~15 ps per slot-record; beyond it one group-by of the batch is cheaper)
+  int64_t opt_force_route = 0;    // profiling aid: run K4 even on a single rank
   int64_t opt_incremental = 0;    // 0 auto (sort-free K6 when the program allows), 1 force the sort-based path
   int64_t opt_max_record_bytes = 528;
 
@@ -954,15 +955,16 @@ int32_t sgr_dist_route_and_fold(sgr_engine* e, const void* d_records, uint64_t n
   std::string err;
   uint64_t n_recv = 0;
   e->stats.ms_h2d = 0;
-  if (dist_nranks(e->dist) == 1) {
+  const bool routed = dist_nranks(e->dist) > 1 || e->opt_force_route;
+  if (!routed) {
     // one rank owns everything and local index == global index: no exchange
     dist_clear_stats(e->dist, n_records);
   } else {
     int r = dist_route(e->dist, (const uint8_t*)d_records, n_records, fused != 0, (unsigned long long*)e->counters.p, e->stream, &n_recv, &err);
     if (r) return fail(e, r, "%s", err.c_str());
   }
-  const uint8_t* arrived = dist_nranks(e->dist) == 1 ? (const uint8_t*)d_records : dist_recv_buffer(e->dist);
-  const uint64_t n_arrived = dist_nranks(e->dist) == 1 ? n_records : n_recv;
+  const uint8_t* arrived = !routed ? (const uint8_t*)d_records : dist_recv_buffer(e->dist);
+  const uint64_t n_arrived = !routed ? n_records : n_recv;
   rc = fold_arrival_order(e, arrived, n_arrived, dist_n_local(e->dist));
   if (rc) return rc;
   const DistStats* ds = dist_stats(e->dist);
@@ -999,6 +1001,7 @@ int32_t sgr_set_option(sgr_engine* e, const char* name, int64_t value) {
   if (!strcmp(name, "fold_variant")) { e->opt_variant = value; return SGR_OK; }
   if (!strcmp(name, "kernel")) { e->opt_kernel = value; return SGR_OK; }
   if (!strcmp(name, "incremental")) { e->opt_incremental = value; return SGR_OK; }
+  if (!strcmp(name, "force_route")) { e->opt_force_route = value; return SGR_OK; }
   if (!strcmp(name, "replay_budget")) { e->opt_replay_budget = value; return SGR_OK; }
   if (!strcmp(name, "var_stage_bytes")) { e->opt_var_stage_bytes = value; return SGR_OK; }
   if (!strcmp(name, "var_stages")) { e->opt_var_stages = value == 3 ? 3 : 2; return SGR_OK; }

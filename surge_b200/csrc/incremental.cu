@@ -122,12 +122,20 @@ __global__ void __launch_bounds__(256) inc_fused_kernel(const __grid_constant__ 
     }
     grid_barrier(bar, gridDim.x);
     const bool rejected2 = ld_volatile_u64(a.counters + 4) != 0;
-    for (uint64_t i = tid; i < a.n; i += nthreads) {
-      const unsigned long long slot = *reinterpret_cast<const unsigned long long*>(a.rec + i * 64 + 8);
-      if (slot >= a.n_slots) continue;
+    // finishing pass: by record (the slot's last event finishes it) for a micro-batch, by slot when the batch is larger
+    // than the table — touching a record's aggregate index costs a full 64-byte DRAM burst, the 32-byte scratch entry is
+    // L2-resident
+    const bool by_slot = (uint64_t)a.n > a.n_slots;
+    const uint64_t c_end = by_slot ? a.n_slots : (uint64_t)a.n;
+    for (uint64_t i = tid; i < c_end; i += nthreads) {
+      unsigned long long slot = i;
+      if (!by_slot) {
+        slot = *reinterpret_cast<const unsigned long long*>(a.rec + i * 64 + 8);
+        if (slot >= a.n_slots) continue;
+      }
       Scratch* sp = a.scr + slot;
       const uint4 s0 = *reinterpret_cast<const uint4*>(sp);        // last_event|ex, flags, word0 (lo, hi)
-      if ((s0.x >> 2) != (uint32_t)i + 1) continue;                // only the slot's last event finishes it
+      if (by_slot ? (s0.x == 0u) : ((s0.x >> 2) != (uint32_t)i + 1)) continue;   // untouched slot / not the slot's last event
       const uint4 s1 = reinterpret_cast<const uint4*>(sp)[1];      // word1 (lo, hi), unused
       reinterpret_cast<uint4*>(sp)[0] = make_uint4(0, 0, 0, 0);
       reinterpret_cast<uint4*>(sp)[1] = make_uint4(0, 0, 0, 0);
@@ -180,13 +188,18 @@ __global__ void __launch_bounds__(256) inc_fused_kernel(const __grid_constant__ 
     }
   }
   grid_barrier(bar, 2ull * gridDim.x);
-  // ---- phase C: the slot's last event finishes it and cleans its scratch
-  for (uint64_t i = tid; i < a.n; i += nthreads) {
-    const unsigned long long slot = *reinterpret_cast<const unsigned long long*>(a.rec + i * 64 + 8);
-    if (slot >= a.n_slots) continue;
+  // ---- phase C: the slot's last event finishes it and cleans its scratch (by slot when the batch exceeds the table)
+  const bool by_slot = (uint64_t)a.n > a.n_slots;
+  const uint64_t c_end = by_slot ? a.n_slots : (uint64_t)a.n;
+  for (uint64_t i = tid; i < c_end; i += nthreads) {
+    unsigned long long slot = i;
+    if (!by_slot) {
+      slot = *reinterpret_cast<const unsigned long long*>(a.rec + i * 64 + 8);
+      if (slot >= a.n_slots) continue;
+    }
     Scratch* sp = a.scr + slot;
     const uint4 s0 = *reinterpret_cast<const uint4*>(sp);        // last_event, flags, last_set[0..1]
-    if (s0.x != (uint32_t)i + 1) continue;                       // only the slot's last event finishes it
+    if (by_slot ? (s0.x == 0u) : (s0.x != (uint32_t)i + 1)) continue;   // untouched slot / not the slot's last event
     const uint4 s1 = reinterpret_cast<const uint4*>(sp)[1];      // acc[0..1], set_val[0..1]
     reinterpret_cast<uint4*>(sp)[0] = make_uint4(0, 0, 0, 0);
     reinterpret_cast<uint4*>(sp)[1] = make_uint4(0, 0, 0, 0);
@@ -292,7 +305,7 @@ cudaError_t launch_incremental_atomic(const uint8_t* d_records, uint32_t n, uint
   }
   a.fast2 = ((has_add & has_set) == 0 && n < (1u << 30)) ? 1u : 0u;
   a.set_only_mask = has_set;
-  const uint32_t work = n > prev_n_upper ? n : prev_n_upper;
+  const uint32_t work = n > prev_n_upper ? n : prev_n_upper;  // (the by-slot finishing pass is grid-stride over n_slots < n)
   if (!work) return cudaSuccess;
   uint32_t g = (work + 255) / 256;
   if (g > (uint32_t)max_grid) g = (uint32_t)max_grid;
