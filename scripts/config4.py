@@ -1,9 +1,9 @@
 """configs[3] (Zipf alpha=1.1 keys, variable payloads 32-512 B), scaled: n_keys and n_events are arguments.
 Builds the log on the GPU with torch (headers + directory), folds it with the record-parallel variable kernel
 (and optionally the lane-per-aggregate TMA kernel for comparison)."""
-import os, sys, time, json
+import os, sys, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import numpy as np, torch
+import torch
 from surge_b200 import ReplayEngine, programs as P, native as N, synth as S
 n_keys = int(sys.argv[1]) if len(sys.argv) > 1 else 625_000
 n_events = int(sys.argv[2]) if len(sys.argv) > 2 else 20_000_000

@@ -6,7 +6,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch
 import torch.distributed as dist
-from surge_b200 import ReplayEngine, programs as P, synth as S, formats as F
+from surge_b200 import ReplayEngine, programs as P, synth as S
 from surge_b200 import dist as D
 
 def main():

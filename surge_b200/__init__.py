@@ -7,6 +7,7 @@ Only what the hot path needs lives here:
   programs.py  declarative fold programs for the reference's sample models
   engine.py    ReplayEngine: Pythonic wrapper over one sgr_engine
   store.py     host-side mirror of the reference's plugin / state-store interfaces
+  dist.py      multi-GPU rendezvous helpers (NCCL id, CUDA IPC handles) and numpy mirrors of the routing tables
   partitioner.py  KafkaPartitionProvider mirror
   synth.py     deterministic generators for the BASELINE.json configs
 """

@@ -7,7 +7,7 @@ entry points and are borrowed, not copied.
 from __future__ import annotations
 
 import ctypes as C
-from typing import List, Optional, Sequence, Tuple
+from typing import Optional, Sequence, Tuple
 
 import numpy as np
 
@@ -177,7 +177,6 @@ class ReplayEngine:
 
         p, nb, po = C.c_void_p(), C.c_uint64(), C.c_void_p()
         self._ck(self._lib.sgr_events_device(self._h, C.byref(p), C.byref(nb), C.byref(po)))
-        n = self.stats().n_aggregates if False else None
         ev = torch.as_tensor(_DevView(p.value, nb.value, self), device=f"cuda:{self.device}")
         return ev, po.value
 

@@ -24,7 +24,7 @@ from __future__ import annotations
 import json
 import struct
 import uuid as _uuid
-from typing import Iterable, List, Optional, Sequence, Tuple
+from typing import Optional, Sequence, Tuple
 
 import numpy as np
 

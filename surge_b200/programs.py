@@ -6,7 +6,7 @@ these tables — the parity tests check table == handler.
 """
 from __future__ import annotations
 
-from typing import Iterable, List, Sequence, Tuple
+from typing import Iterable, Sequence, Tuple
 
 from . import native as N
 

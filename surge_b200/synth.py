@@ -6,7 +6,7 @@ would take minutes to build and copy from the host (config 2 and up).
 """
 from __future__ import annotations
 
-from typing import Optional, Tuple
+from typing import Tuple
 
 import numpy as np
 
