@@ -95,7 +95,7 @@ struct sgr_engine {
                                   // 2 force runs (fold_runs.cu), 3 record-per-lane rows (fold_rows.cu)
   int64_t opt_variant = -1;
   int64_t opt_long_threshold = 0;
-  int64_t opt_var_stages = 2;
+  int64_t opt_var_stages = 1;     // measured: 1 stage x 16 warps/SM (5.0 TB/s) beats 2 x 9 (4.4) and 3 x 6 (3.2) on configs[3]
   int64_t opt_var_stage_bytes = 12288;  // smem bytes staged per 32-record step of the variable-record kernel
   int64_t opt_replay_budget = 1ll << 24;  // K6: in-kernel replay of throwing slots only while n_err * n stays below this
                                           // (measured ~15 ps per slot-record; beyond it one group-by of the batch is cheaper)
@@ -1004,7 +1004,7 @@ int32_t sgr_set_option(sgr_engine* e, const char* name, int64_t value) {
   if (!strcmp(name, "force_route")) { e->opt_force_route = value; return SGR_OK; }
   if (!strcmp(name, "replay_budget")) { e->opt_replay_budget = value; return SGR_OK; }
   if (!strcmp(name, "var_stage_bytes")) { e->opt_var_stage_bytes = value; return SGR_OK; }
-  if (!strcmp(name, "var_stages")) { e->opt_var_stages = value == 3 ? 3 : 2; return SGR_OK; }
+  if (!strcmp(name, "var_stages")) { e->opt_var_stages = (value >= 1 && value <= 3) ? value : 2; return SGR_OK; }
   if (!strcmp(name, "run_variant")) {
     if (value < 0 || value >= run_variant_count()) return fail(e, SGR_ERR_INVALID, "run_variant out of range");
     e->opt_run_variant = value; return SGR_OK;

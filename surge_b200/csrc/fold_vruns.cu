@@ -72,7 +72,7 @@ __device__ __forceinline__ void finish_var(const VarArgs& a, uint32_t seg, const
 }
 
 template <int NSTAGE>
-__global__ void __launch_bounds__(384) fold_vruns_kernel(const __grid_constant__ VarArgs a, const __grid_constant__ RowProgram pg) {
+__global__ void __launch_bounds__(512) fold_vruns_kernel(const __grid_constant__ VarArgs a, const __grid_constant__ RowProgram pg) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   __shared__ __align__(16) uint32_t tab[16 * kTabStride];
   for (int i = threadIdx.x; i < 16 * kTabStride; i += blockDim.x) tab[i] = pg.tab[i];
@@ -265,17 +265,17 @@ __global__ void __launch_bounds__(384) fold_vruns_kernel(const __grid_constant__
 }  // namespace
 
 typedef void (*VKernel)(const VarArgs, const RowProgram);
-static VKernel vkernel(int nstage) { return nstage == 2 ? fold_vruns_kernel<2> : fold_vruns_kernel<3>; }
+static VKernel vkernel(int nstage) { return nstage == 1 ? fold_vruns_kernel<1> : (nstage == 2 ? fold_vruns_kernel<2> : fold_vruns_kernel<3>); }
 
 int vruns_config(int num_sms, uint32_t max_record_bytes, uint32_t stage_hint, int nstage, int* threads, size_t* smem, uint32_t* stage_bytes) {
-  if (nstage != 2) nstage = 3;
+  if (nstage < 1 || nstage > 3) nstage = 2;
   const int NSTAGE = nstage;
   uint32_t stage = ((32u * max_record_bytes) + 127u) & ~127u;   // worst case: every record of a step at the maximum
   if (stage_hint && stage_hint < stage) stage = (stage_hint + 127u) & ~127u;
   const size_t per_warp = (size_t)NSTAGE * stage;
   int warps = (int)((220u * 1024u) / per_warp);
   if (warps < 1) return 0;
-  if (warps > 12) warps = 12;
+  if (warps > 16) warps = 16;
   *threads = warps * 32; *smem = per_warp * warps; *stage_bytes = stage;
   cudaFuncSetAttribute(vkernel(nstage), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*smem);
   int per_sm = 0;
