@@ -91,7 +91,34 @@ class GpuReplayKeyValueStore(storeName: String) extends KeyValueStore[Bytes, Arr
     check(Native.foldIncremental(handle, direct, batch.length / 64))
   }
 
-  private def growTable(): Unit = { /* export, enlarge, sgr_set_initial_states, sgr_load_keys — see store.py flush() */ folded = true }
+  /** (Re)build the live table with room for the keys seen so far: export, enlarge, sgr_set_initial_states, sgr_load_keys
+   *  (the executable twin is GpuReplayKeyValueStore.flush in surge_b200/store.py). */
+  private def growTable(): Unit = {
+    val stateBytes = GpuFoldPrograms.current.order(ByteOrder.LITTLE_ENDIAN).getInt(0) // sgr_fold_program.state_bytes
+    val newCapacity = math.max(2L * keyIndex.size(), 1024L)
+    val table = ByteBuffer.allocateDirect((newCapacity * stateBytes).toInt) // zero-filled: None everywhere
+    if (folded) {
+      val old = ByteBuffer.allocateDirect((capacity * stateBytes).toInt)
+      check(Native.exportStates(handle, old, null))
+      table.put(old); table.rewind()
+    }
+    check(Native.setInitialStates(handle, table, newCapacity))
+    // key table for sgr_get: ids in slot order, unused slots get unreachable placeholder keys
+    val ids = new Array[String](newCapacity.toInt)
+    keyIndex.forEach((id, slot) => ids(slot.intValue()) = id)
+    val blob = new java.io.ByteArrayOutputStream()
+    val offs = ByteBuffer.allocateDirect((newCapacity.toInt + 1) * 4).order(ByteOrder.LITTLE_ENDIAN)
+    offs.putInt(0)
+    var i = 0
+    while (i < newCapacity) {
+      val bytes = (if (ids(i) != null) ids(i) else "\u0000unused-" + i).getBytes("UTF-8")
+      blob.write(bytes); offs.putInt(blob.size()); i += 1
+    }
+    val keys = ByteBuffer.allocateDirect(math.max(blob.size(), 1)); keys.put(blob.toByteArray); keys.flip(); offs.flip()
+    check(Native.loadKeys(handle, keys, offs, newCapacity))
+    capacity = newCapacity
+    folded = true
+  }
 
   // KTable semantics for state records: last write wins, null deletes (SurgeStateStoreConsumer.scala:57-76)
   override def put(key: Bytes, value: Array[Byte]): Unit = overlay.put(key.toString, Option(value))

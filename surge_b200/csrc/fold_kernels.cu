@@ -409,16 +409,7 @@ cudaError_t launch_cfg(const FoldArgs& args, const DevProgram& prog, int num_sms
 int fold_variant_count() { return kNumVariants; }
 const char* fold_variant_name(int v) { return (v >= 0 && v < kNumVariants) ? kVariants[v].name : "?"; }
 
-cudaError_t launch_fold_stream(const FoldArgs& args, const DevProgram& prog, int variant, int num_sms,
-                               uint32_t max_record_bytes, cudaStream_t stream, FoldLaunchInfo* info) {
-  if (variant < 0 || variant >= kNumVariants || kVariants[variant].kind != (int)prog.record_kind) {
-    if (prog.record_kind == SGR_REC_FIXED64) variant = 0;
-    else variant = max_record_bytes <= 512 + 16 ? 6 : (max_record_bytes <= 1024 + 16 ? 7 : 8);
-  }
-  // a variable record must fit in LAG*CH+16 bytes of ring behind the slot being refilled
-  if (prog.record_kind == SGR_REC_VAR16 && max_record_bytes > (uint32_t)kVariants[variant].chunk * kVariants[variant].lag + 16)
-    return cudaErrorInvalidValue;
-  // shrink the thread count if the state tables do not fit next to the rings
+static cudaError_t launch_variant(int variant, const FoldArgs& args, const DevProgram& prog, int num_sms, cudaStream_t stream, FoldLaunchInfo* info) {
   switch (variant) {
     case 0: return launch_cfg<F0>(args, prog, num_sms, stream, info, variant);
     case 1: return launch_cfg<F1>(args, prog, num_sms, stream, info, variant);
@@ -431,6 +422,27 @@ cudaError_t launch_fold_stream(const FoldArgs& args, const DevProgram& prog, int
     case 8: return launch_cfg<V2>(args, prog, num_sms, stream, info, variant);
   }
   return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_fold_stream(const FoldArgs& args, const DevProgram& prog, int variant, int num_sms,
+                               uint32_t max_record_bytes, cudaStream_t stream, FoldLaunchInfo* info) {
+  const bool explicit_variant = variant >= 0 && variant < kNumVariants && kVariants[variant].kind == (int)prog.record_kind;
+  if (prog.record_kind == SGR_REC_VAR16) {
+    if (!explicit_variant) variant = max_record_bytes <= 512 + 16 ? 6 : (max_record_bytes <= 1024 + 16 ? 7 : 8);
+    // a variable record must fit in LAG*CH+16 bytes of ring behind the slot being refilled
+    if (max_record_bytes > (uint32_t)kVariants[variant].chunk * kVariants[variant].lag + 16) return cudaErrorInvalidValue;
+    return launch_variant(variant, args, prog, num_sms, stream, info);
+  }
+  if (explicit_variant) return launch_variant(variant, args, prog, num_sms, stream, info);
+  // fixed records: more warps per SM win (measured on configs[1]: 256 thr 3.0 TB/s, 192 thr 2.3, 128 thr 2.1); take the
+  // widest configuration whose rings + state tables fit in shared memory
+  const int order[] = {1, 2, 0, 3};
+  cudaError_t e = cudaErrorInvalidConfiguration;
+  for (int v : order) {
+    e = launch_variant(v, args, prog, num_sms, stream, info);
+    if (e != cudaErrorInvalidConfiguration) return e;
+  }
+  return e;
 }
 
 }  // namespace sgr
