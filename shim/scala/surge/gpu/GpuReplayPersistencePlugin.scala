@@ -57,6 +57,7 @@ class GpuReplayKeyValueStore(storeName: String) extends KeyValueStore[Bytes, Arr
   private val overlay = new util.concurrent.ConcurrentHashMap[String, Option[Array[Byte]]]()
   private var capacity = 0L
   private var folded = false
+  private var loadedKeys = -1
 
   private def check(rc: Int): Unit = if (rc != Native.OK) {
     val msg = Native.lastError(handle)
@@ -89,6 +90,7 @@ class GpuReplayKeyValueStore(storeName: String) extends KeyValueStore[Bytes, Arr
     val direct = ByteBuffer.allocateDirect(batch.length); direct.put(batch); direct.flip()
     if (!folded || keyIndex.size() > capacity) growTable()
     check(Native.foldIncremental(handle, direct, batch.length / 64))
+    if (keyIndex.size() != loadedKeys) loadKeyTable() // new ids inside the current capacity
   }
 
   /** (Re)build the live table with room for the keys seen so far: export, enlarge, sgr_set_initial_states, sgr_load_keys
@@ -103,7 +105,14 @@ class GpuReplayKeyValueStore(storeName: String) extends KeyValueStore[Bytes, Arr
       table.put(old); table.rewind()
     }
     check(Native.setInitialStates(handle, table, newCapacity))
-    // key table for sgr_get: ids in slot order, unused slots get unreachable placeholder keys
+    capacity = newCapacity
+    folded = true
+    loadKeyTable()
+  }
+
+  /** key table for sgr_get: ids in slot order, unused slots get unreachable placeholder keys */
+  private def loadKeyTable(): Unit = {
+    val newCapacity = capacity
     val ids = new Array[String](newCapacity.toInt)
     keyIndex.forEach((id, slot) => ids(slot.intValue()) = id)
     val blob = new java.io.ByteArrayOutputStream()
@@ -116,8 +125,7 @@ class GpuReplayKeyValueStore(storeName: String) extends KeyValueStore[Bytes, Arr
     }
     val keys = ByteBuffer.allocateDirect(math.max(blob.size(), 1)); keys.put(blob.toByteArray); keys.flip(); offs.flip()
     check(Native.loadKeys(handle, keys, offs, newCapacity))
-    capacity = newCapacity
-    folded = true
+    loadedKeys = keyIndex.size()
   }
 
   // KTable semantics for state records: last write wins, null deletes (SurgeStateStoreConsumer.scala:57-76)
