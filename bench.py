@@ -180,7 +180,7 @@ ROUTED_AGG_PER_GPU = 1_250_000   # configs[2]: 10 M aggregates x 100 events over
 ROUTED_EPA = 100
 
 
-def routed_pipeline(rank, world, local_rank, dev, barrier, note):
+def routed_pipeline(rank, world, local_rank, dev, barrier, note, strong=False):
     """configs[2]-shaped per-GPU work (weak: 1.25 M aggregates x 100 events of 64 B originate on every rank):
     route (K4) + exchange (NCCL all-to-all, then fused peer-memory scatter) + stable group-by (K5) + fold.
     Stage times are CUDA-event times on the engine's stream, max over ranks; the job rate uses the wall time
@@ -193,7 +193,7 @@ def routed_pipeline(rank, world, local_rank, dev, barrier, note):
     from surge_b200 import dist as D
     from surge_b200 import programs as P
 
-    n_global = ROUTED_AGG_PER_GPU * world
+    n_global = ROUTED_AGG_PER_GPU * (8 if strong else world)   # strong: always the full 10 M x 100 problem
     epa = ROUTED_EPA
     # this rank's source partitions hold the aggregates g with g % world == rank, in arrival order
     # (event k of every aggregate before event k+1: aggregates interleaved, per-aggregate order kept)
@@ -202,23 +202,28 @@ def routed_pipeline(rank, world, local_rank, dev, barrier, note):
     gen = torch.Generator(device=dev)
     gen.manual_seed(1000 + rank)
     r = torch.zeros((n, 16), dtype=torch.int32, device=dev)
-    u = torch.rand(n, generator=gen, device=dev)
-    r[:, 0] = torch.where(u < 0.45, 0, torch.where(u < 0.9, 1, 2)).to(torch.int32)
-    del u
-    r[:, 1] = torch.arange(epa, device=dev, dtype=torch.int32).repeat_interleave(g_mine.numel()) + 1
-    agg = g_mine.repeat(epa)
-    r[:, 2] = (agg & 0xFFFFFFFF).to(torch.int32)
-    del agg
-    r[:, 4] = torch.randint(0, 1 << 31, (n,), generator=gen, device=dev, dtype=torch.int64).to(torch.int32)
+    na = g_mine.numel()
+    g32 = (g_mine & 0xFFFFFFFF).to(torch.int32)
+    for k in range(epa):   # one "round" of events at a time keeps the temporaries small (matters for the 64 GB case)
+        blk = r[k * na:(k + 1) * na]
+        u = torch.rand(na, generator=gen, device=dev)
+        blk[:, 0] = torch.where(u < 0.45, 0, torch.where(u < 0.9, 1, 2)).to(torch.int32)
+        blk[:, 1] = k + 1
+        blk[:, 2] = g32
+        blk[:, 4] = torch.randint(0, 1 << 31, (na,), generator=gen, device=dev, dtype=torch.int64).to(torch.int32)
+    del u, g32
     # ownership: partition = a multiplicative hash of the dense id (ids are pre-hashed once on load), 64 partitions
     part = ((np.arange(n_global, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15)) >> np.uint64(40)).astype(np.uint32) % np.uint32(64)
     cap = int(n * 1.15) + 1_000_000
-    res = {"workload": f"configs[2] shape, weak: {ROUTED_AGG_PER_GPU} aggregates x {epa} events x 64 B originate per GPU, "
-                       f"{n_global} aggregates hash-partitioned over {world} rank(s)", "events_total": int(n) * world}
+    res = {"workload": (f"configs[2] FULL problem, strong: {n_global} aggregates x {epa} events x 64 B = {n_global * epa * 64 / 1e9:.0f} GB split over {world} rank(s)"
+                        if strong else f"configs[2] shape, weak: {ROUTED_AGG_PER_GPU} aggregates x {epa} events x 64 B originate per GPU, "
+                        f"{n_global} aggregates hash-partitioned over {world} rank(s)"), "events_total": int(n) * world}
     # sort-free: the arrived records are folded with integer atomics (K6 kernel), no group-by; sorted_group: K5 + K1
     for mode, fused, sort_based in (("nccl_all_to_all", False, False), ("fused_peer_scatter", True, False), ("nccl_all_to_all_sorted_group", False, True)):
         if world == 1 and fused:
             continue
+        if strong and sort_based:
+            continue   # the group-by's scratch does not fit next to 64 GB of records on one GPU
         eng = ReplayEngine(local_rank)
         eng.register_program(P.counter_program())
         if sort_based:
@@ -267,6 +272,9 @@ def main() -> None:
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--verbose", action="store_true", help="progress markers on stderr")
     ap.add_argument("--no-routed", action="store_true", help="skip the routed (configs[2]-shaped) pipeline measurement")
+    ap.add_argument("--routed-strong", action="store_true",
+                    help="routed pipeline on the FULL configs[2] problem (10 M aggregates x 100 events = 64 GB) split over the ranks "
+                         "(strong scaling; needs 64 GB of records on one GPU at N=1) instead of 8 GB per rank")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -379,7 +387,7 @@ def main() -> None:
             e2.close(); eng.close()
             del rec
             torch.cuda.empty_cache()
-            routed = routed_pipeline(rank, world, local_rank, dev, barrier, note)
+            routed = routed_pipeline(rank, world, local_rank, dev, barrier, note, strong=args.routed_strong)
         except Exception as ex:  # noqa: BLE001 - the headline line must survive a failure of the extra measurement
             routed = {"error": f"{type(ex).__name__}: {ex}"}
 
