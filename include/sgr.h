@@ -289,6 +289,73 @@ int32_t sgr_dist_get_stats(sgr_engine* e, sgr_dist_stats* out);
 /* global aggregate index of each local state slot (host copy, n_local u32) */
 int32_t sgr_dist_local_aggregates(sgr_engine* e, uint32_t* out, uint64_t cap, uint64_t* n_local);
 
+/* ------------------------------------------------------------------ ingest: Kafka record batches -> packed records
+ * What feeds the store today is a Kafka consumer in read_committed mode
+ * (COMMON/kafka/streams/SurgeStateStoreConsumer.scala:38; the plain wrapper is COMMON/kafka/KafkaConsumer.scala:48-105,120-132)
+ * over a topic whose producer compresses with lz4 (modules/common/src/main/resources/reference.conf:124) and writes inside
+ * transactions. sgr_ingest decodes the raw bytes of a fetch response / log segment — a concatenation of RecordBatch
+ * (magic 2) structures — into the engine's fixed 64-byte records in arrival order, interning aggregate ids
+ * (key.takeWhile(_ != ':'), COMMON/kafka/KafkaPartitioner.scala:38-42) as dense indices in first-seen order.
+ *   - verifies each batch's CRC-32C; decodes compression none and lz4 (gzip/snappy/zstd: SGR_ERR_UNSUPPORTED);
+ *   - skips control batches, and data batches of aborted transactions announced with sgr_ingest_set_aborted
+ *     (the fetch response's abortedTransactions list), the way a read_committed consumer does;
+ *   - drops records with a null/empty key: the producer's flush markers
+ *     (CORE/internal/kafka/KafkaProducerActorImpl.scala:321-329);
+ *   - a trailing partial batch is left undecoded (n_trailing_bytes), as fetch responses may end with one;
+ *   - records below the partition's decoded position are counted as duplicates and skipped (refetch after restart);
+ *   - record value = the model's packed event: u32 type, u32 seq (little endian) + up to 48 payload bytes.
+ * A malformed batch fails the whole call and leaves the pending log and the partition position untouched.
+ * The byte formats are third-party (org.apache.kafka:kafka-clients:3.2.3, lz4 frame format) and the reference holds no
+ * broker bytes: byte-level parity is UNPINNED (see oracle/kafka_batch.py).
+ *
+ * Lag gate (f2): actors trust the store only once the consumer group of the streams applicationId has no lag
+ * (CORE/internal/kafka/KafkaProducerActorImpl.scala:530-540,684-708; COMMON/kafka/KafkaAdminClient.scala:36-56).
+ * sgr_ingest_offsets reports, per partition, the next offset to fetch (decoded_next) and the offset below which every
+ * record is inside the state table (folded_next) — the value whoever consumes on the store's behalf commits. */
+typedef struct sgr_ingest sgr_ingest;
+
+typedef struct sgr_ingest_stats {
+  uint64_t n_bytes;              /* bytes consumed (whole batches) */
+  uint64_t n_trailing_bytes;     /* bytes of a trailing partial batch left undecoded (last call only) */
+  uint64_t n_batches;
+  uint64_t n_records;            /* packed records appended to the pending log */
+  uint64_t n_markers;            /* null/empty-key records dropped */
+  uint64_t n_null_values;        /* keyed records with a null value dropped */
+  uint64_t n_control_batches;
+  uint64_t n_aborted_batches, n_aborted_records;
+  uint64_t n_duplicates;         /* records below the partition's decoded position */
+  uint64_t n_new_keys;
+  uint64_t n_compressed_bytes, n_decompressed_bytes;
+  uint64_t reserved[3];
+} sgr_ingest_stats;
+
+int32_t sgr_ingest_create(sgr_ingest** out);
+int32_t sgr_ingest_destroy(sgr_ingest* g);
+const char* sgr_ingest_last_error(const sgr_ingest* g);
+/* aborted transactions of the next fetch of `partition`: (producerId, firstOffset) pairs */
+int32_t sgr_ingest_set_aborted(sgr_ingest* g, int32_t partition, const int64_t* producer_ids, const int64_t* first_offsets, uint64_t n);
+int32_t sgr_ingest_record_batches(sgr_ingest* g, int32_t partition, const void* data, uint64_t nbytes, sgr_ingest_stats* stats);
+/* the pending packed records (borrowed until the next ingest call) and the id dictionary (key i = dense index i) */
+int32_t sgr_ingest_pending(sgr_ingest* g, const void** records, uint64_t* n_records);
+int32_t sgr_ingest_keys(sgr_ingest* g, const uint8_t** keys, const uint32_t** key_offsets, uint64_t* n_keys);
+/* the pending records are inside the state table now: drop them, advance folded_next to decoded_next */
+int32_t sgr_ingest_mark_folded(sgr_ingest* g);
+int32_t sgr_ingest_offsets(sgr_ingest* g, int32_t partition, int64_t* decoded_next, int64_t* folded_next);
+int32_t sgr_ingest_get_stats(sgr_ingest* g, sgr_ingest_stats* out);   /* totals since create */
+
+/* Resize the live state table to n_agg slots on the device, keeping its content; new slots are None.
+ * (A KTable grows as new keys appear; never shrinks.) */
+int32_t sgr_grow_states(sgr_engine* e, uint64_t n_agg);
+/* Fold everything pending in `g` onto the live table (growing it for new aggregate ids), publish the id dictionary
+ * to sgr_get, and mark the ingest folded: poll -> sgr_ingest_record_batches -> sgr_fold_ingested is the whole restore loop. */
+int32_t sgr_fold_ingested(sgr_engine* e, sgr_ingest* g);
+
+/* building blocks, exported for the known-answer tests */
+uint32_t sgr_crc32c(const void* data, uint64_t nbytes);            /* RFC 3720 CRC-32C (SSE4.2 when present) */
+uint32_t sgr_crc32c_portable(const void* data, uint64_t nbytes);   /* table-driven twin */
+uint32_t sgr_xxh32(const void* data, uint64_t nbytes, uint32_t seed);
+int32_t sgr_lz4_frame_decode(const void* src, uint64_t nbytes, void* out, uint64_t cap, uint64_t* out_len);
+
 /* ------------------------------------------------------------------ partitioner
  * KafkaPartitionProvider.partitionForKey = abs(MurmurHash3.stringHash(s) % n)
  * (COMMON/kafka/KafkaPartitioner.scala:7-9) over key.takeWhile(_ != ':')

@@ -70,5 +70,40 @@ JNIEXPORT jint JNICALL Java_surge_gpu_Native_00024_partitionForKey(JNIEnv* env, 
   (*env)->ReleaseByteArrayElements(env, key, k, JNI_ABORT);
   return p;
 }
+
+/* ---- ingest (raw Kafka record batches) */
+#define G(g) ((sgr_ingest*)(intptr_t)(g))
+JNIEXPORT jlong JNICALL Java_surge_gpu_Native_00024_ingestCreate(JNIEnv* env, jobject o) {
+  sgr_ingest* g = 0;
+  if (sgr_ingest_create(&g) != SGR_OK) { (*env)->ThrowNew(env, (*env)->FindClass(env, "java/lang/OutOfMemoryError"), "sgr_ingest_create"); return 0; }
+  return (jlong)(intptr_t)g;
+}
+JNIEXPORT jint JNICALL Java_surge_gpu_Native_00024_ingestDestroy(JNIEnv* env, jobject o, jlong g) { return sgr_ingest_destroy(G(g)); }
+JNIEXPORT jint JNICALL Java_surge_gpu_Native_00024_ingestSetAborted(JNIEnv* env, jobject o, jlong g, jint partition, jlongArray pids, jlongArray firsts) {
+  jsize n = (*env)->GetArrayLength(env, pids);
+  jlong* p = (*env)->GetLongArrayElements(env, pids, 0);
+  jlong* f = (*env)->GetLongArrayElements(env, firsts, 0);
+  int32_t rc = sgr_ingest_set_aborted(G(g), partition, (const int64_t*)p, (const int64_t*)f, (uint64_t)n);
+  (*env)->ReleaseLongArrayElements(env, pids, p, JNI_ABORT);
+  (*env)->ReleaseLongArrayElements(env, firsts, f, JNI_ABORT);
+  return rc;
+}
+JNIEXPORT jlong JNICALL Java_surge_gpu_Native_00024_ingestRecordBatches(JNIEnv* env, jobject o, jlong g, jint partition, jobject data, jlong nbytes) {
+  sgr_ingest_stats st;
+  int32_t rc = sgr_ingest_record_batches(G(g), partition, (*env)->GetDirectBufferAddress(env, data), (uint64_t)nbytes, &st);
+  if (rc != SGR_OK) {   /* a corrupt batch kills the stream thread, as a CorruptRecordException would */
+    (*env)->ThrowNew(env, (*env)->FindClass(env, "java/lang/RuntimeException"), sgr_ingest_last_error(G(g)));
+    return -1;
+  }
+  return (jlong)st.n_records;
+}
+JNIEXPORT jint JNICALL Java_surge_gpu_Native_00024_foldIngested(JNIEnv* env, jobject o, jlong h, jlong g) { return sgr_fold_ingested(H(h), G(g)); }
+JNIEXPORT jlongArray JNICALL Java_surge_gpu_Native_00024_ingestOffsets(JNIEnv* env, jobject o, jlong g, jint partition) {
+  int64_t v[2] = {0, 0};
+  sgr_ingest_offsets(G(g), partition, &v[0], &v[1]);
+  jlongArray r = (*env)->NewLongArray(env, 2);
+  (*env)->SetLongArrayRegion(env, r, 0, 2, (const jlong*)v);
+  return r;
+}
 #endif
 #endif

@@ -26,4 +26,14 @@ object Native {
   @native def get(handle: Long, key: Array[Byte]): Array[Byte]                     // sgr_get
   @native def exportStates(handle: Long, out: ByteBuffer, changedBits: ByteBuffer): Int // sgr_export_states
   @native def partitionForKey(key: Array[Byte], numPartitions: Int, upToColon: Boolean): Int // sgr_partition_for_key_utf8
+
+  // raw record batches in, committed offsets out (include/sgr.h "ingest")
+  @native def ingestCreate(): Long                                                 // sgr_ingest_create
+  @native def ingestDestroy(ingest: Long): Int                                     // sgr_ingest_destroy
+  @native def ingestSetAborted(ingest: Long, partition: Int, producerIds: Array[Long], firstOffsets: Array[Long]): Int // sgr_ingest_set_aborted
+  /** decodes one fetch response's bytes for `partition`; returns the number of packed records appended; throws on malformed input */
+  @native def ingestRecordBatches(ingest: Long, partition: Int, data: ByteBuffer, nbytes: Long): Long // sgr_ingest_record_batches
+  @native def foldIngested(handle: Long, ingest: Long): Int                        // sgr_fold_ingested
+  /** Array(decodedNext, foldedNext) */
+  @native def ingestOffsets(ingest: Long, partition: Int): Array[Long]             // sgr_ingest_offsets
 }

@@ -6,6 +6,7 @@ Only what the hot path needs lives here:
   formats.py   packed record / state layouts (the binary SurgeAggregateFormatting)
   programs.py  declarative fold programs for the reference's sample models
   engine.py    ReplayEngine: Pythonic wrapper over one sgr_engine
+  ingest.py    Kafka RecordBatch bytes -> packed records (native decode) + per-partition offsets for the lag gate
   store.py     host-side mirror of the reference's plugin / state-store interfaces
   dist.py      multi-GPU rendezvous helpers (NCCL id, CUDA IPC handles) and numpy mirrors of the routing tables
   partitioner.py  KafkaPartitionProvider mirror

@@ -109,7 +109,7 @@ struct sgr_engine {
   DistState* dist = nullptr;
   sgr_dist_stats dstats{};
 
-  KeyTable keys;
+  std::shared_ptr<const KeyTable> keys;   // swapped atomically: sgr_get readers never see a table being rebuilt
   std::mutex snap_mu;
   std::shared_ptr<Snapshot> snapshot;
   std::atomic<bool> snapshot_dirty{true};
@@ -755,7 +755,51 @@ int32_t sgr_fold_incremental(sgr_engine* e, const void* records, uint64_t n_reco
 int32_t sgr_load_keys(sgr_engine* e, const uint8_t* keys, const uint32_t* key_offsets, uint64_t n_agg) {
   if (!e || !key_offsets || (!keys && n_agg && key_offsets[n_agg])) return fail(e, SGR_ERR_INVALID, "null argument");
   std::string err;
-  if (!e->keys.build(keys, key_offsets, n_agg, &err)) return fail(e, SGR_ERR_INVALID, "%s", err.c_str());
+  auto kt = std::make_shared<KeyTable>();
+  if (!kt->build(keys, key_offsets, n_agg, &err)) return fail(e, SGR_ERR_INVALID, "%s", err.c_str());
+  std::atomic_store(&e->keys, std::shared_ptr<const KeyTable>(kt));
+  return SGR_OK;
+}
+
+int32_t sgr_grow_states(sgr_engine* e, uint64_t n_agg) {
+  if (!e) return SGR_ERR_INVALID;
+  if (!e->has_program) return fail(e, SGR_ERR_NO_PROGRAM, "register a fold program first");
+  int32_t rc = use_device(e); if (rc) return rc;
+  rc = before_load(e); if (rc) return rc;
+  if (e->states_valid && n_agg <= e->states_n) return SGR_OK;
+  const size_t sb = e->program.state_bytes;
+  DevBuf nb;
+  CUDA_TRY(e, nb.reserve((size_t)n_agg * sb));
+  const size_t keep = e->states_valid ? (size_t)e->states_n * sb : 0;
+  if (keep) CUDA_TRY(e, cudaMemcpyAsync(nb.p, e->states.p, keep, cudaMemcpyDeviceToDevice, e->stream));
+  CUDA_TRY(e, cudaMemsetAsync((uint8_t*)nb.p + keep, 0, (size_t)n_agg * sb - keep, e->stream));
+  CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+  std::swap(e->states, nb);
+  nb.release();
+  e->states_n = n_agg;
+  e->states_valid = true;
+  e->inc_atomic_prev_valid = false; e->inc_prev_n = 0;
+  mark_dirty(e);
+  return SGR_OK;
+}
+
+int32_t sgr_fold_ingested(sgr_engine* e, sgr_ingest* g) {
+  if (!e || !g) return fail(e, SGR_ERR_INVALID, "null argument");
+  const void* recs = nullptr; uint64_t n_records = 0;
+  const uint8_t* keys = nullptr; const uint32_t* key_offsets = nullptr; uint64_t n_keys = 0;
+  if (sgr_ingest_pending(g, &recs, &n_records) || sgr_ingest_keys(g, &keys, &key_offsets, &n_keys))
+    return fail(e, SGR_ERR_INVALID, "ingest: %s", sgr_ingest_last_error(g));
+  if (!e->states_valid || n_keys > e->states_n) {
+    // amortised doubling, like a hash table: the resize copies the table device to device
+    uint64_t cap = e->states_valid ? e->states_n : 0;
+    if (cap < 1024) cap = 1024;
+    while (cap < n_keys) cap *= 2;
+    int32_t rc = sgr_grow_states(e, cap); if (rc) return rc;
+  }
+  if (n_records) { int32_t rc = sgr_fold_incremental(e, recs, n_records); if (rc) return rc; }
+  std::shared_ptr<const KeyTable> cur = std::atomic_load(&e->keys);
+  if (!cur || cur->size() != n_keys) { int32_t rc = sgr_load_keys(e, keys, key_offsets, n_keys); if (rc) return rc; }
+  sgr_ingest_mark_folded(g);
   return SGR_OK;
 }
 
@@ -784,7 +828,8 @@ int32_t sgr_get_index(sgr_engine* e, uint64_t agg, void* out, uint32_t cap, uint
 
 int32_t sgr_get(sgr_engine* e, const uint8_t* key, uint32_t klen, void* out, uint32_t cap, uint32_t* outlen, int32_t* exists) {
   if (!e || (!key && klen)) return fail(e, SGR_ERR_INVALID, "null argument");
-  int64_t idx = e->keys.find(key, klen);
+  std::shared_ptr<const KeyTable> kt = std::atomic_load(&e->keys);
+  int64_t idx = kt ? kt->find(key, klen) : -1;
   if (idx < 0) {  // unknown aggregate id: Option.empty, like a KTable miss
     if (exists) *exists = 0;
     if (outlen) *outlen = 0;

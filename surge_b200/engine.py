@@ -144,6 +144,14 @@ class ReplayEngine:
         r = np.ascontiguousarray(records).view(np.uint8).reshape(-1)
         self._ck(self._lib.sgr_fold_incremental(self._h, r.ctypes.data, r.size // 64))
 
+    def grow_states(self, n_agg: int) -> None:
+        """Resize the live table on the device, keeping its content (new slots are None)."""
+        self._ck(self._lib.sgr_grow_states(self._h, n_agg))
+
+    def fold_ingested(self, ingest) -> None:
+        """Fold everything pending in an Ingest onto the live table and publish its id dictionary to get()."""
+        self._ck(self._lib.sgr_fold_ingested(self._h, ingest.handle))
+
     # -- results
     def n_aggregates(self) -> int:
         p, n, sb = C.c_void_p(), C.c_uint64(), C.c_uint32()

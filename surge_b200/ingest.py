@@ -1,0 +1,95 @@
+"""Ingest: Kafka RecordBatch bytes -> packed event records, over the C ABI (include/sgr.h, "ingest" section).
+
+Host-side mirror of what sits in front of the state store in the reference: the read_committed consumer
+(modules/common/src/main/scala/surge/kafka/streams/SurgeStateStoreConsumer.scala:38) and the lag gate's view of how far the
+store has consumed (modules/common/src/main/scala/surge/kafka/KafkaAdminClient.scala:36-56). All decoding happens in
+libsgr.so; this class only moves pointers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Sequence, Tuple
+
+import numpy as np
+
+from . import native as N
+
+
+class IngestError(N.SgrError):
+    pass
+
+
+class Ingest:
+    def __init__(self):
+        self._lib = N.load_library()
+        self._h = C.c_void_p()
+        rc = self._lib.sgr_ingest_create(C.byref(self._h))
+        if rc != N.SGR_OK:
+            raise IngestError(rc, "sgr_ingest_create failed")
+
+    def close(self) -> None:
+        if self._h:
+            self._lib.sgr_ingest_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+    def _check(self, rc: int) -> None:
+        if rc != N.SGR_OK:
+            msg = self._lib.sgr_ingest_last_error(self._h)
+            raise IngestError(rc, msg.decode("utf-8", "replace") if msg else "")
+
+    @property
+    def handle(self) -> C.c_void_p:
+        return self._h
+
+    def set_aborted(self, partition: int, aborted: Sequence[Tuple[int, int]]) -> None:
+        """aborted = [(producer_id, first_offset)] from the fetch response."""
+        if not aborted:
+            return
+        pids = np.asarray([a[0] for a in aborted], dtype=np.int64)
+        offs = np.asarray([a[1] for a in aborted], dtype=np.int64)
+        self._check(self._lib.sgr_ingest_set_aborted(self._h, partition, pids.ctypes.data, offs.ctypes.data, len(aborted)))
+
+    def record_batches(self, partition: int, data: bytes) -> Dict[str, int]:
+        st = N.sgr_ingest_stats()
+        buf = (C.c_char * len(data)).from_buffer_copy(data) if data else None
+        self._check(self._lib.sgr_ingest_record_batches(self._h, partition, C.cast(buf, C.c_void_p) if buf is not None else None, len(data), C.byref(st)))
+        return {n: int(getattr(st, n)) for n, _ in N.sgr_ingest_stats._fields_ if n != "reserved"}
+
+    def pending(self) -> np.ndarray:
+        """Copy of the pending packed records, [n, 64] uint8."""
+        p = C.c_void_p()
+        n = C.c_uint64()
+        self._check(self._lib.sgr_ingest_pending(self._h, C.byref(p), C.byref(n)))
+        if not n.value:
+            return np.zeros((0, 64), dtype=np.uint8)
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(n.value * 64,)).reshape(-1, 64).copy()
+
+    def keys(self) -> List[str]:
+        kp, op = C.c_void_p(), C.c_void_p()
+        n = C.c_uint64()
+        self._check(self._lib.sgr_ingest_keys(self._h, C.byref(kp), C.byref(op), C.byref(n)))
+        if not n.value:
+            return []
+        offs = np.ctypeslib.as_array(C.cast(op, C.POINTER(C.c_uint32)), shape=(n.value + 1,)).copy()
+        raw = C.string_at(kp, int(offs[-1])) if offs[-1] else b""
+        return [raw[offs[i]:offs[i + 1]].decode("utf-8") for i in range(n.value)]
+
+    def mark_folded(self) -> None:
+        self._check(self._lib.sgr_ingest_mark_folded(self._h))
+
+    def offsets(self, partition: int) -> Tuple[int, int]:
+        """(decoded_next, folded_next): next offset to fetch, and the offset to commit for the lag gate."""
+        d, f = C.c_int64(), C.c_int64()
+        self._check(self._lib.sgr_ingest_offsets(self._h, partition, C.byref(d), C.byref(f)))
+        return d.value, f.value
+
+    def stats(self) -> Dict[str, int]:
+        st = N.sgr_ingest_stats()
+        self._check(self._lib.sgr_ingest_get_stats(self._h, C.byref(st)))
+        return {n: int(getattr(st, n)) for n, _ in N.sgr_ingest_stats._fields_ if n != "reserved"}

@@ -70,6 +70,12 @@ class sgr_stats(C.Structure):
                 ("fold_launches", C.c_uint32), ("reserved", C.c_uint32 * 7)]
 
 
+class sgr_ingest_stats(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("n_bytes", "n_trailing_bytes", "n_batches", "n_records", "n_markers", "n_null_values",
+                                          "n_control_batches", "n_aborted_batches", "n_aborted_records", "n_duplicates", "n_new_keys",
+                                          "n_compressed_bytes", "n_decompressed_bytes")] + [("reserved", C.c_uint64 * 3)]
+
+
 # every symbol include/sgr.h declares: (name, restype, argtypes)
 _P = C.c_void_p
 ABI = [
@@ -113,6 +119,22 @@ ABI = [
     ("sgr_partitions_for_keys", C.c_int32, [_P, _P, C.c_uint64, C.c_uint32, C.c_int32, _P]),
     ("sgr_string_hash_utf16", C.c_int32, [_P, C.c_uint32]),
     ("sgr_partition_for_key_utf8", C.c_int32, [_P, C.c_uint32, C.c_uint32, C.c_int32, C.POINTER(C.c_int32)]),
+    ("sgr_ingest_create", C.c_int32, [C.POINTER(_P)]),
+    ("sgr_ingest_destroy", C.c_int32, [_P]),
+    ("sgr_ingest_last_error", C.c_char_p, [_P]),
+    ("sgr_ingest_set_aborted", C.c_int32, [_P, C.c_int32, _P, _P, C.c_uint64]),
+    ("sgr_ingest_record_batches", C.c_int32, [_P, C.c_int32, _P, C.c_uint64, C.POINTER(sgr_ingest_stats)]),
+    ("sgr_ingest_pending", C.c_int32, [_P, C.POINTER(_P), C.POINTER(C.c_uint64)]),
+    ("sgr_ingest_keys", C.c_int32, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(C.c_uint64)]),
+    ("sgr_ingest_mark_folded", C.c_int32, [_P]),
+    ("sgr_ingest_offsets", C.c_int32, [_P, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    ("sgr_ingest_get_stats", C.c_int32, [_P, C.POINTER(sgr_ingest_stats)]),
+    ("sgr_grow_states", C.c_int32, [_P, C.c_uint64]),
+    ("sgr_fold_ingested", C.c_int32, [_P, _P]),
+    ("sgr_crc32c", C.c_uint32, [_P, C.c_uint64]),
+    ("sgr_crc32c_portable", C.c_uint32, [_P, C.c_uint64]),
+    ("sgr_xxh32", C.c_uint32, [_P, C.c_uint64, C.c_uint32]),
+    ("sgr_lz4_frame_decode", C.c_int32, [_P, C.c_uint64, _P, C.c_uint64, C.POINTER(C.c_uint64)]),
 ]
 
 _lib: Optional[C.CDLL] = None

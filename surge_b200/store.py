@@ -27,6 +27,7 @@ import numpy as np
 
 from . import native as N
 from .engine import ReplayEngine
+from .ingest import Ingest
 
 STATE_STORE_PLUGIN_KEY = "surge.kafka-streams.state-store-plugin"
 
@@ -136,6 +137,7 @@ class GpuReplayKeyValueStore:
         self._lock = threading.RLock()
         self._restore_callback = None
         self._keys_loaded = (-1, -1)
+        self._ingest: Optional[Ingest] = None  # set once the store is fed raw record batches
 
     # -- lifecycle (StateStore)
     def name(self) -> str:
@@ -176,6 +178,8 @@ class GpuReplayKeyValueStore:
         if len(packed_event) != 64:
             raise ValueError("packed events are 64 bytes")
         with self._lock:
+            if self._ingest is not None:
+                raise N.SgrError(N.SGR_ERR_INVALID, "this store is already fed through restore_record_batches")
             rec = np.frombuffer(packed_event, dtype=np.uint8).copy()
             rec[8:16] = np.frombuffer(np.uint64(self._slot(aggregate_id_of_record_key(record_key))).tobytes(), dtype=np.uint8)
             self._pending.append(rec)
@@ -185,8 +189,35 @@ class GpuReplayKeyValueStore:
             self.put_event(k, v)
         self.flush()
 
+    def restore_record_batches(self, partition: int, data: bytes, aborted: Sequence[Tuple[int, int]] = ()) -> Dict[str, int]:
+        """Raw bytes of one fetch response for `partition` (a concatenation of Kafka RecordBatch v2), plus the
+        response's aborted transactions [(producerId, firstOffset)]: decoded natively as a read_committed consumer
+        would (SurgeStateStoreConsumer.scala:38) into the pending batch. flush() folds it. A store is fed either this
+        way or through put_event, not both (each keeps its own id dictionary)."""
+        with self._lock:
+            if self._keys:
+                raise N.SgrError(N.SGR_ERR_INVALID, "this store is already fed through put_event")
+            if self._ingest is None:
+                self._ingest = Ingest()
+            self._ingest.set_aborted(partition, aborted)
+            return self._ingest.record_batches(partition, data)
+
+    def committed_offsets(self, partitions: Iterable[int]) -> Dict[int, int]:
+        """Per partition, the offset below which every record is inside the state table: what the consumer acting for
+        this store commits for the streams application id, so that the producer's lag check
+        (KafkaProducerActorImpl.scala:684-708 -> KafkaAdminClient.consumerLag, KafkaAdminClient.scala:44-56) reaches zero
+        exactly when get() can serve the state."""
+        with self._lock:
+            if self._ingest is None:
+                return {int(p): 0 for p in partitions}
+            return {int(p): self._ingest.offsets(int(p))[1] for p in partitions}
+
     def flush(self) -> None:
         with self._lock:
+            if self._ingest is not None:
+                self._engine.fold_ingested(self._ingest)
+                self._folded = True
+                return
             if not self._pending and self._folded:
                 return
             batch = np.concatenate(self._pending) if self._pending else np.zeros(0, dtype=np.uint8)
@@ -246,7 +277,7 @@ class GpuReplayKeyValueStore:
 
     def all(self) -> Iterator[Tuple[str, bytes]]:
         with self._lock:
-            keys = sorted(set(self._keys) | set(self._overlay))
+            keys = sorted(set(self._ingest.keys() if self._ingest is not None else self._keys) | set(self._overlay))
         for k in keys:
             v = self.get(k)
             if v is not None:

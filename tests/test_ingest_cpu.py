@@ -1,0 +1,296 @@
+"""Kafka RecordBatch decode and the per-partition offsets the lag gate needs (f2) — host logic, no GPU.
+
+The product decoder is surge_b200/csrc/ingest.cpp behind the C ABI; the checker is the independent Python
+encoder/decoder in oracle/kafka_batch.py. Byte-level parity with a real broker is UNPINNED (the reference holds no broker
+bytes); what is pinned here are the published known-answer vectors of CRC-32C (RFC 3720 B.4) and xxHash32 and the LZ4
+frame header checksum bytes.
+"""
+import ctypes as C
+import struct
+
+import numpy as np
+import pytest
+
+from oracle import kafka_batch as K
+from surge_b200 import native as N
+from surge_b200.ingest import Ingest, IngestError
+
+
+@pytest.fixture(scope="module")
+def lib():
+    return N.load_library()
+
+
+def _crc(lib, b: bytes, portable=False) -> int:
+    buf = C.create_string_buffer(b, len(b)) if b else None
+    return (lib.sgr_crc32c_portable if portable else lib.sgr_crc32c)(buf, len(b))
+
+
+# RFC 3720 appendix B.4
+CRC_VECTORS = [
+    (b"\x00" * 32, 0x8A9136AA),
+    (b"\xff" * 32, 0x62A8AB43),
+    (bytes(range(32)), 0x46DD794E),
+    (bytes(range(31, -1, -1)), 0x113FDB5C),
+    (b"123456789", 0xE3069283),
+    (b"", 0),
+]
+
+
+@pytest.mark.parametrize("data,want", CRC_VECTORS)
+def test_crc32c_known_answers(lib, data, want):
+    assert K.crc32c(data) == want
+    assert _crc(lib, data) == want
+    assert _crc(lib, data, portable=True) == want
+
+
+def test_crc32c_hw_and_table_agree_on_unaligned_lengths(lib):
+    rng = np.random.default_rng(7)
+    blob = rng.integers(0, 256, 5000, dtype=np.uint8).tobytes()
+    for start in range(0, 9):
+        for n in (0, 1, 7, 8, 9, 63, 64, 65, 1000, 4991):
+            d = blob[start:start + n]
+            assert _crc(lib, d) == _crc(lib, d, portable=True) == K.crc32c(d)
+
+
+def test_xxh32_known_answers(lib):
+    def x(b, seed=0):
+        buf = C.create_string_buffer(b, len(b)) if b else None
+        return lib.sgr_xxh32(buf, len(b), seed)
+
+    assert K.xxh32(b"") == x(b"") == 0x02CC5D05
+    assert K.xxh32(b"abc") == x(b"abc") == 0x32D153FF
+    # LZ4 frame header checksum byte = (xxh32(descriptor) >> 8) & 0xff: the two headers every lz4 tool writes
+    assert (x(bytes([0x60, 0x40])) >> 8) & 0xFF == 0x82
+    assert (x(bytes([0x64, 0x40])) >> 8) & 0xFF == 0xA7
+    rng = np.random.default_rng(3)
+    for n in (1, 3, 4, 15, 16, 17, 31, 32, 33, 100, 1000):
+        d = rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+        for seed in (0, 1, 0x9E3779B1):
+            assert x(d, seed) == K.xxh32(d, seed)
+
+
+def _lz4_decode(lib, frame: bytes, cap: int = 1 << 22):
+    out = C.create_string_buffer(cap)
+    n = C.c_uint64()
+    rc = lib.sgr_lz4_frame_decode(C.create_string_buffer(frame, len(frame)), len(frame), out, cap, C.byref(n))
+    return rc, out.raw[: n.value]
+
+
+def _compressible(rng, n):
+    words = [bytes(rng.integers(97, 123, int(rng.integers(2, 9)), dtype=np.uint8)) for _ in range(20)]
+    out = bytearray()
+    while len(out) < n:
+        out += words[int(rng.integers(0, len(words)))]
+    return bytes(out[:n])
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(block_checksum=True), dict(content_checksum=True), dict(content_size=True),
+                                dict(block_checksum=True, content_checksum=True, content_size=True, block_code=5)])
+def test_lz4_frames_round_trip(lib, kw):
+    rng = np.random.default_rng(11)
+    cases = [b"", b"a", b"abcd" * 3, b"\x00" * 100_000, _compressible(rng, 70_000), _compressible(rng, 200_001),
+             rng.integers(0, 256, 3000, dtype=np.uint8).tobytes()]  # incompressible -> stored block
+    for data in cases:
+        frame = K.lz4_frame_compress(data, **kw)
+        assert K.lz4_frame_decompress(frame) == data
+        rc, got = _lz4_decode(lib, frame)
+        assert rc == 0 and got == data
+    # the frame of a long run is much smaller than the run: matches (incl. overlapping ones) were really emitted
+    assert len(K.lz4_frame_compress(b"\x00" * 100_000)) < 1000
+
+
+def test_lz4_hand_built_overlapping_match(lib):
+    # token 0x1F: 1 literal, match length 15+4(+ext 1) = 20, offset 1 -> "a" * 21, then a literal-only tail
+    block = bytes([0x1F, ord("a"), 0x01, 0x00, 0x01]) + bytes([0x50]) + b"bcdef"
+    desc = bytes([0x60, 0x40])
+    frame = struct.pack("<I", 0x184D2204) + desc + bytes([(K.xxh32(desc) >> 8) & 0xFF]) + struct.pack("<I", len(block)) + block + struct.pack("<I", 0)
+    rc, got = _lz4_decode(lib, frame)
+    assert rc == 0 and got == b"a" * 21 + b"bcdef"
+    assert K.lz4_frame_decompress(frame) == got
+
+
+def test_lz4_rejects_corruption(lib):
+    data = _compressible(np.random.default_rng(5), 10_000)
+    frame = bytearray(K.lz4_frame_compress(data, block_checksum=True, content_checksum=True))
+    assert _lz4_decode(lib, bytes(frame))[0] == 0
+    for pos in (0, 4, 6, 20, len(frame) - 2):
+        bad = bytearray(frame)
+        bad[pos] ^= 0x40
+        assert _lz4_decode(lib, bytes(bad))[0] == N.SGR_ERR_INVALID
+    assert _lz4_decode(lib, bytes(frame[:-9]))[0] == N.SGR_ERR_INVALID        # no end mark
+    # a match that reaches before the start of the output
+    block = bytes([0x0F, 0x05, 0x00])
+    desc = bytes([0x60, 0x40])
+    f2 = struct.pack("<I", 0x184D2204) + desc + bytes([(K.xxh32(desc) >> 8) & 0xFF]) + struct.pack("<I", len(block)) + block + struct.pack("<I", 0)
+    assert _lz4_decode(lib, f2)[0] == N.SGR_ERR_INVALID
+    rc, _ = _lz4_decode(lib, K.lz4_frame_compress(data), cap=100)
+    assert rc == N.SGR_ERR_CAPACITY
+
+
+# ----------------------------------------------------------------------------- record batches
+def _event(type_, seq, by=0, extra=b""):
+    return struct.pack("<IIi", type_, seq, by) + extra
+
+
+def _batch_stream(rng, n_batches, n_keys, compression, base=0):
+    out, off = bytearray(), base
+    for _ in range(n_batches):
+        n = int(rng.integers(1, 40))
+        recs = []
+        for d in range(n):
+            k = int(rng.integers(0, n_keys))
+            key = f"agg-{k}:{off + d}".encode() if rng.random() < 0.7 else f"agg-{k}".encode()
+            recs.append((d, key, _event(int(rng.integers(0, 3)), off + d, int(rng.integers(-2**31, 2**31)), bytes(int(rng.integers(0, 45))))))
+        out += K.encode_record_batch(off, recs, compression=compression, headers=[(b"aggregate_id", b"x"), (b"n", None)])
+        off += n
+    return bytes(out), off
+
+
+@pytest.mark.parametrize("compression", ["none", "lz4"])
+def test_decode_matches_restatement(compression):
+    rng = np.random.default_rng(42)
+    fetches = []
+    nxt = {0: 0, 1: 1000}
+    for _ in range(6):
+        for p in (0, 1):
+            buf, nxt[p] = _batch_stream(rng, 5, 50, compression, nxt[p])
+            fetches.append((p, buf, []))
+    want_recs, want_keys, want_next = K.read_committed_pack(fetches)
+    ing = Ingest()
+    total = 0
+    for p, buf, _ in fetches:
+        st = ing.record_batches(p, buf)
+        assert st["n_trailing_bytes"] == 0 and st["n_bytes"] == len(buf)
+        total += st["n_records"]
+    got = ing.pending()
+    assert total == len(want_recs) == len(got)
+    assert np.array_equal(got, want_recs)
+    assert ing.keys() == [k.decode() for k in want_keys]
+    for p in (0, 1):
+        assert ing.offsets(p) == (want_next[p], 0)
+    ing.mark_folded()
+    assert len(ing.pending()) == 0
+    for p in (0, 1):
+        assert ing.offsets(p) == (want_next[p], want_next[p])
+    if compression == "lz4":
+        s = ing.stats()
+        assert 0 < s["n_compressed_bytes"] < s["n_decompressed_bytes"]
+
+
+def test_flush_markers_null_values_and_key_up_to_colon():
+    recs = [(0, b"", b""),                        # the producer's flush record: empty key, empty value
+            (1, None, _event(0, 1, 5)),            # null key
+            (2, b"acct:7", _event(0, 2, 5)),
+            (3, b"acct", _event(1, 3, 2)),         # same aggregate as "acct:7"
+            (4, b"acct2:1", None),                 # null value
+            (5, "zażółć:1".encode(), _event(0, 1, 1))]
+    ing = Ingest()
+    st = ing.record_batches(3, K.encode_record_batch(100, recs))
+    assert (st["n_records"], st["n_markers"], st["n_null_values"], st["n_new_keys"]) == (3, 2, 1, 2)
+    assert ing.keys() == ["acct", "zażółć"]
+    p = ing.pending()
+    assert p[:, 8:16].view(np.uint64).ravel().tolist() == [0, 0, 1]
+    assert p[:, 0:4].view(np.uint32).ravel().tolist() == [0, 1, 0]
+    assert p[:, 4:8].view(np.uint32).ravel().tolist() == [2, 3, 1]
+    assert p[:, 16:20].view(np.int32).ravel().tolist() == [5, 2, 1]
+    assert not p[:, 20:].any()
+    assert ing.offsets(3) == (106, 0)
+    assert ing.offsets(9) == (0, 0)
+
+
+def test_trailing_partial_batch_is_left_for_the_next_fetch():
+    b1 = K.encode_record_batch(0, [(0, b"a", _event(0, 1, 1))])
+    b2 = K.encode_record_batch(1, [(0, b"b", _event(0, 1, 1)), (1, b"a", _event(0, 2, 1))], compression="lz4")
+    ing = Ingest()
+    for cut in (5, 12, 30, len(b2) - 1):
+        g = Ingest()
+        st = g.record_batches(0, b1 + b2[:cut])
+        assert (st["n_batches"], st["n_records"], st["n_bytes"], st["n_trailing_bytes"]) == (1, 1, len(b1), cut)
+        assert g.offsets(0)[0] == 1
+    st = ing.record_batches(0, b1 + b2)
+    assert st["n_records"] == 3 and ing.offsets(0)[0] == 3
+
+
+def test_refetch_after_restart_skips_duplicates():
+    rng = np.random.default_rng(1)
+    buf, end = _batch_stream(rng, 4, 10, "none")
+    ing = Ingest()
+    n = ing.record_batches(0, buf)["n_records"]
+    st = ing.record_batches(0, buf)          # the same bytes again
+    assert st["n_records"] == 0 and st["n_duplicates"] == n
+    assert len(ing.pending()) == n and ing.offsets(0)[0] == end
+    # a batch that straddles the position: only its tail is new
+    tail = K.encode_record_batch(end - 1, [(0, b"x", _event(0, 1, 1)), (1, b"y", _event(0, 1, 1))])
+    st = ing.record_batches(0, tail)
+    assert (st["n_records"], st["n_duplicates"]) == (1, 1)
+    assert ing.keys()[-1] == "y"
+
+
+def test_read_committed_skips_aborted_transactions_and_control_batches():
+    ev = lambda s: _event(0, s, 1)  # noqa: E731
+    log = b"".join([
+        K.encode_record_batch(0, [(0, b"a", ev(1)), (1, b"b", ev(1))], producer_id=7, transactional=True),     # aborted
+        K.encode_record_batch(2, [(0, b"c", ev(1))], producer_id=8, transactional=True, compression="lz4"),    # committed
+        K.encode_record_batch(3, [(0, b"a", ev(2))], producer_id=7, transactional=True),                       # aborted
+        K.encode_control_batch(4, 7, K.ABORT),
+        K.encode_control_batch(5, 8, K.COMMIT),
+        K.encode_record_batch(6, [(0, b"a", ev(3))], producer_id=7, transactional=True),                       # new txn, committed
+        K.encode_control_batch(7, 7, K.COMMIT),
+        K.encode_record_batch(8, [(0, b"d", ev(1))]),                                                          # non-transactional
+        K.encode_record_batch(9, [(0, b"e", ev(1))], producer_id=9, transactional=True),                       # aborted later in the log
+        K.encode_control_batch(10, 9, K.ABORT),
+    ])
+    aborted = [(7, 0), (9, 9)]
+    want, want_keys, want_next = K.read_committed_pack([(0, log, aborted)])
+    ing = Ingest()
+    ing.set_aborted(0, aborted)
+    st = ing.record_batches(0, log)
+    assert (st["n_control_batches"], st["n_aborted_batches"], st["n_aborted_records"], st["n_records"]) == (4, 3, 4, 3)
+    assert ing.keys() == ["c", "a", "d"] == [k.decode() for k in want_keys]
+    assert np.array_equal(ing.pending(), want)
+    assert ing.offsets(0)[0] == 11 == want_next[0]
+    # without the aborted list (read_uncommitted view) everything is data
+    g = Ingest()
+    assert g.record_batches(0, log)["n_records"] == 7
+
+
+def test_malformed_input_fails_loudly_and_leaves_state_untouched():
+    good = K.encode_record_batch(0, [(0, b"a", _event(0, 1, 1))])
+    nxt = K.encode_record_batch(1, [(0, b"b", _event(0, 1, 1)), (1, b"c", _event(0, 2, 1))], compression="lz4")
+    ing = Ingest()
+    ing.record_batches(0, good)
+
+    def refused(buf, code, fragment):
+        with pytest.raises(IngestError) as ei:
+            ing.record_batches(0, buf)
+        assert ei.value.code == code and fragment in str(ei.value)
+        assert len(ing.pending()) == 1 and ing.offsets(0)[0] == 1
+
+    bad = bytearray(nxt)
+    bad[70] ^= 1
+    refused(good[:0] + bytes(bad), N.SGR_ERR_INVALID, "CRC-32C mismatch")
+    refused(K.encode_record_batch(1, [(0, b"b", b"x" * 8)], magic=1), N.SGR_ERR_UNSUPPORTED, "message format v1")
+    for codec in ("gzip", "snappy", "zstd"):
+        refused(K.encode_record_batch(1, [(0, b"b", _event(0, 1))], compression=codec), N.SGR_ERR_UNSUPPORTED, codec)
+    refused(K.encode_record_batch(1, [(0, b"b", b"short")]), N.SGR_ERR_INVALID, "packed event value of 5 bytes")
+    refused(K.encode_record_batch(1, [(0, b"b", bytes(57))]), N.SGR_ERR_INVALID, "packed event value of 57 bytes")
+    # a good batch followed by a bad one: nothing of the call is kept
+    refused(nxt + bytes(bad), N.SGR_ERR_INVALID, "CRC-32C mismatch")
+    # records section shorter than recordsCount says (CRC re-computed so that only the structure is wrong)
+    body = K.encode_record(0, b"b", _event(0, 1))
+    tail = struct.pack(">hiqqqhii", 0, 1, 0, 1, -1, -1, -1, 2) + body
+    lying = struct.pack(">qiib", 1, 9 + len(tail), 0, 2) + struct.pack(">I", K.crc32c(tail)) + tail
+    refused(lying, N.SGR_ERR_INVALID, "record 1")
+    st = ing.record_batches(0, nxt)
+    assert st["n_records"] == 2 and ing.offsets(0)[0] == 3
+
+
+def test_varint_extremes_round_trip():
+    for v in (0, 1, -1, 63, 64, -64, -65, 2**31 - 1, -2**31):
+        assert K.read_varint(K.varint(v), 0)[0] == v
+    big_delta = 2**31 - 1
+    b = K.encode_record_batch(5, [(0, b"k", _event(0, 1, 1)), (big_delta, b"k", _event(0, 2, 1))])
+    ing = Ingest()
+    assert ing.record_batches(0, b)["n_records"] == 2
+    assert ing.offsets(0)[0] == 5 + big_delta + 1

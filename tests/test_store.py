@@ -94,3 +94,38 @@ def test_json_model_is_served_through_a_formatter():
     store.restore([("agg:4", _ev(0, 4, 1)), ("agg:5", _ev(0, 5, 1))])
     assert store.get("agg") == b'{"aggregateId":"agg","count":2,"version":5}'
     store.close()
+
+
+@pytest.mark.gpu
+def test_store_restores_from_raw_record_batches_and_reports_committed_offsets():
+    """The whole restore loop on raw broker bytes: fetch -> restore_record_batches -> flush -> getAggregateBytes, and the
+    offsets the lag gate compares (KafkaAdminClient.scala:44-56)."""
+    import struct
+
+    from oracle import kafka_batch as K
+
+    ev = lambda t, seq, by: struct.pack("<IIi", t, seq, by)  # noqa: E731
+    store = ST.GpuReplayKeyValueStore("s", P.counter_program())
+    store.init()
+    assert store.committed_offsets([0, 1]) == {0: 0, 1: 0}
+    p0 = K.encode_record_batch(0, [(0, b"", b"")]) + K.encode_record_batch(1, [(0, b"a:1", ev(0, 1, 1)), (1, b"a:2", ev(0, 2, 1))], compression="lz4",
+                                                                          producer_id=5, transactional=True) + K.encode_control_batch(3, 5, K.COMMIT)
+    p1 = K.encode_record_batch(10, [(0, b"b:1", ev(0, 1, 9))], producer_id=6, transactional=True) + K.encode_control_batch(11, 6, K.ABORT) + \
+        K.encode_record_batch(12, [(0, b"c:1", ev(2, 1, 0))])
+    st = store.restore_record_batches(0, p0)
+    assert (st["n_records"], st["n_markers"], st["n_control_batches"]) == (2, 1, 1)
+    store.restore_record_batches(1, p1, aborted=[(6, 10)])
+    assert store.committed_offsets([0, 1]) == {0: 0, 1: 0}          # decoded, not folded yet: the gate must stay shut
+    store.flush()
+    assert store.committed_offsets([0, 1]) == {0: 4, 1: 13}
+    assert np.frombuffer(store.get("a"), dtype="<i4").tolist() == [2, 2]
+    assert store.get("b") is None                                    # its only event belonged to an aborted transaction
+    assert np.frombuffer(store.get("c"), dtype="<i4").tolist() == [0, 0]
+    store.restore_record_batches(0, K.encode_record_batch(4, [(0, b"a:3", ev(1, 3, 1))]))
+    store.flush()
+    assert np.frombuffer(store.get("a"), dtype="<i4").tolist() == [1, 3]   # the multilanguage Counter vector (1,3)
+    assert store.committed_offsets([0]) == {0: 5}
+    assert sorted(k for k, _ in store.all()) == ["a", "c"]
+    with pytest.raises(N.SgrError):
+        store.put_event("x:1", bytes(64))
+    store.close()
