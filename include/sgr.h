@@ -335,6 +335,11 @@ const char* sgr_ingest_last_error(const sgr_ingest* g);
 /* aborted transactions of the next fetch of `partition`: (producerId, firstOffset) pairs */
 int32_t sgr_ingest_set_aborted(sgr_ingest* g, int32_t partition, const int64_t* producer_ids, const int64_t* first_offsets, uint64_t n);
 int32_t sgr_ingest_record_batches(sgr_ingest* g, int32_t partition, const void* data, uint64_t nbytes, sgr_ingest_stats* stats);
+/* n fetches in one call. CRC, decompression and parsing run on up to `threads` host threads (the fetches of one partition
+ * stay on one thread, in call order); ids are interned and records appended afterwards in call order, so the outcome is
+ * identical to n single calls. All or nothing: one malformed fetch and nothing is applied. stats: n entries or NULL. */
+int32_t sgr_ingest_record_batches_mt(sgr_ingest* g, uint32_t n, const int32_t* partitions, const void* const* datas,
+                                     const uint64_t* nbytes, uint32_t threads, sgr_ingest_stats* stats);
 /* the pending packed records (borrowed until the next ingest call) and the id dictionary (key i = dense index i) */
 int32_t sgr_ingest_pending(sgr_ingest* g, const void** records, uint64_t* n_records);
 int32_t sgr_ingest_keys(sgr_ingest* g, const uint8_t** keys, const uint32_t** key_offsets, uint64_t* n_keys);

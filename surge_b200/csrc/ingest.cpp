@@ -17,9 +17,13 @@
 #include <stdarg.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <thread>
 #include <map>
 #include <string>
 #include <unordered_set>
@@ -139,30 +143,50 @@ std::string lz4_frame_decode(const uint8_t* src, uint64_t n, std::vector<uint8_t
     if (stored) {
       out->insert(out->end(), b, b + bsz);
     } else {
+      // decode through raw pointers into a window of max_block (+ slack for 8-byte copies) bytes, then trim
       const uint64_t block_out_start = out->size();
+      out->resize(block_out_start + max_block + 16);
+      uint8_t* const win = out->data() + block_out_start;
+      uint8_t* const frame_begin = out->data() + out_base;
+      uint8_t* op = win;
+      uint8_t* const op_limit = win + max_block;
       uint64_t ip = 0;
+      const char* bad = nullptr;
       for (;;) {
-        if (ip >= bsz) return "LZ4 block ends inside a sequence";
+        if (ip >= bsz) { bad = "LZ4 block ends inside a sequence"; break; }
         const uint8_t token = b[ip++];
         uint64_t lit = token >> 4;
-        if (lit == 15) { uint8_t s; do { if (ip >= bsz) return "LZ4 literal length truncated"; s = b[ip++]; lit += s; } while (s == 255); }
-        if (ip + lit > bsz) return "LZ4 literals run past the block";
-        out->insert(out->end(), b + ip, b + ip + lit);
-        ip += lit;
+        if (lit == 15) {
+          uint8_t s;
+          do { if (ip >= bsz) { bad = "LZ4 literal length truncated"; break; } s = b[ip++]; lit += s; } while (s == 255);
+          if (bad) break;
+        }
+        if (lit > bsz - ip) { bad = "LZ4 literals run past the block"; break; }
+        if (lit > (uint64_t)(op_limit - op)) { bad = "LZ4 block decodes past the frame's maximum block size"; break; }
+        memcpy(op, b + ip, lit);
+        op += lit; ip += lit;
         if (ip == bsz) break;  // the last sequence carries literals only
-        if (ip + 2 > bsz) return "LZ4 match offset truncated";
+        if (ip + 2 > bsz) { bad = "LZ4 match offset truncated"; break; }
         const uint32_t off = b[ip] | ((uint32_t)b[ip + 1] << 8); ip += 2;
         uint64_t mlen = (token & 15);
-        if (mlen == 15) { uint8_t s; do { if (ip >= bsz) return "LZ4 match length truncated"; s = b[ip++]; mlen += s; } while (s == 255); }
+        if (mlen == 15) {
+          uint8_t s;
+          do { if (ip >= bsz) { bad = "LZ4 match length truncated"; break; } s = b[ip++]; mlen += s; } while (s == 255);
+          if (bad) break;
+        }
         mlen += 4;
-        const uint64_t have = out->size() - out_base;
-        if (off == 0 || off > have) return "LZ4 match offset outside the decoded data";
-        if (out->size() - block_out_start + mlen > max_block) return "LZ4 block decodes past the frame's maximum block size";
-        uint64_t from = out->size() - off;
-        out->reserve(out->size() + mlen);
-        for (uint64_t k = 0; k < mlen; ++k) out->push_back((*out)[from + k]);  // byte-wise: overlapping matches replicate
+        if (off == 0 || off > (uint64_t)(op - frame_begin)) { bad = "LZ4 match offset outside the decoded data"; break; }
+        if (mlen > (uint64_t)(op_limit - op)) { bad = "LZ4 block decodes past the frame's maximum block size"; break; }
+        const uint8_t* from = op - off;
+        if (off >= 8) {   // 8 bytes at a time; may write up to 7 bytes past the match, inside the slack
+          for (uint64_t k = 0; k < mlen; k += 8) memcpy(op + k, from + k, 8);
+        } else {
+          for (uint64_t k = 0; k < mlen; ++k) op[k] = from[k];   // overlapping match: replicates the last `off` bytes
+        }
+        op += mlen;
       }
-      if (out->size() - block_out_start > max_block) return "LZ4 block decodes past the frame's maximum block size";
+      out->resize(block_out_start + (uint64_t)(op - win));
+      if (bad) return bad;
     }
     pos += bsz + (block_checksum ? 4 : 0);
   }
@@ -184,6 +208,7 @@ struct Cursor {
   const uint8_t* p; uint64_t n; uint64_t pos = 0; bool ok = true;
   Cursor(const uint8_t* p_, uint64_t n_) : p(p_), n(n_) {}
   int64_t varlong() {  // ByteUtils.readVarlong: zig-zag, at most 10 bytes
+    if (pos < n && !(p[pos] & 0x80)) { const uint64_t b = p[pos++]; return (int64_t)(b >> 1) ^ -(int64_t)(b & 1); }
     uint64_t v = 0; int shift = 0;
     for (int i = 0; i < 10; ++i) {
       if (pos >= n) { ok = false; return 0; }
@@ -195,6 +220,7 @@ struct Cursor {
     ok = false; return 0;
   }
   int32_t varint() {  // ByteUtils.readVarint: zig-zag, at most 5 bytes
+    if (pos < n && !(p[pos] & 0x80)) { const uint32_t b = p[pos++]; return (int32_t)(b >> 1) ^ -(int32_t)(b & 1); }
     uint32_t v = 0; int shift = 0;
     for (int i = 0; i < 5; ++i) {
       if (pos >= n) { ok = false; return 0; }
@@ -211,51 +237,83 @@ struct Cursor {
   }
 };
 
-// ------------------------------------------------------------------ growable aggregate-id dictionary (arrival order = dense index)
+// ------------------------------------------------------------------ growable aggregate-id dictionary (first-seen order = dense index)
+inline uint64_t hash_bytes(const uint8_t* k, uint32_t len) {   // 8 bytes at a time, multiply-xorshift mixing
+  uint64_t h = 0x9e3779b97f4a7c15ull ^ ((uint64_t)len * 0xff51afd7ed558ccdull);
+  while (len >= 8) { uint64_t w; memcpy(&w, k, 8); h = (h ^ w) * 0x9fb21c651e98df25ull; h ^= h >> 32; k += 8; len -= 8; }
+  if (len) { uint64_t w = 0; memcpy(&w, k, len); h = (h ^ w) * 0x9fb21c651e98df25ull; h ^= h >> 32; }
+  h *= 0xc4ceb9fe1a85ec53ull; h ^= h >> 29;
+  return h;
+}
+
 class KeyDict {
  public:
-  uint32_t intern(const uint8_t* k, uint32_t len, bool* fresh) {
-    if (slots_.empty() || (n_ + 1) * 2 > slots_.size()) grow();
+  struct Slot { uint32_t tag; uint32_t idx; uint64_t off_len; };   // tag = low 32 hash bits (also the home position, so growing
+                                                                   // never re-reads keys); off_len = byte offset << 24 | length; idx == kEmpty: free
+  static constexpr uint32_t kEmpty = 0xFFFFFFFFu;
+  KeyDict() { offs_.push_back(0); }
+  void reserve_for(uint64_t extra) { while ((n_ + extra + 1) * 2 > slots_.size()) grow(); }   // at most 2^31 ids (u32 index, tag-addressed)
+  void prefetch_slot(uint64_t h) const { if (!slots_.empty()) __builtin_prefetch(&slots_[(uint32_t)h & (slots_.size() - 1)]); }
+  void prefetch_key(uint64_t h) const {   // the slot is expected in cache by now: pull the candidate's key bytes
+    if (slots_.empty()) return;
+    const Slot& sl = slots_[(uint32_t)h & (slots_.size() - 1)];
+    if (sl.idx != kEmpty) __builtin_prefetch(bytes_.data() + (sl.off_len >> 24));
+  }
+  // call reserve_for() first: intern never grows the table itself
+  uint32_t intern(const uint8_t* k, uint32_t len, uint64_t h, bool* fresh) {
     const uint64_t mask = slots_.size() - 1;
-    uint64_t h = hash(k, len) & mask;
-    while (slots_[h] >= 0) {
-      const uint64_t j = (uint64_t)slots_[h];
-      if (offs_[j + 1] - offs_[j] == len && (len == 0 || memcmp(bytes_.data() + offs_[j], k, len) == 0)) { *fresh = false; return (uint32_t)j; }
-      h = (h + 1) & mask;
+    const uint32_t tag = (uint32_t)h;
+    uint64_t at = tag & mask;
+    for (;;) {
+      Slot& sl = slots_[at];
+      if (sl.idx == kEmpty) {
+        sl.tag = tag; sl.idx = (uint32_t)n_; sl.off_len = ((uint64_t)bytes_.size() << 24) | len;
+        bytes_.insert(bytes_.end(), k, k + len);
+        offs_.push_back((uint32_t)bytes_.size());
+        *fresh = true;
+        return (uint32_t)n_++;
+      }
+      if (sl.tag == tag && (uint32_t)(sl.off_len & 0xFFFFFF) == len && (len == 0 || memcmp(bytes_.data() + (sl.off_len >> 24), k, len) == 0)) {
+        *fresh = false; return sl.idx;
+      }
+      at = (at + 1) & mask;
     }
-    slots_[h] = (int64_t)n_;
-    bytes_.insert(bytes_.end(), k, k + len);
-    offs_.push_back((uint32_t)bytes_.size());
-    *fresh = true;
-    return (uint32_t)n_++;
   }
   uint64_t size() const { return n_; }
-  uint64_t key_bytes() const { return bytes_.size(); }
   const uint8_t* bytes() const { return bytes_.data(); }
   const uint32_t* offsets() const { return offs_.data(); }
-  KeyDict() { offs_.push_back(0); }
 
  private:
-  static uint64_t hash(const uint8_t* k, uint32_t len) {
-    uint64_t h = 1469598103934665603ull;
-    for (uint32_t i = 0; i < len; ++i) { h ^= k[i]; h *= 1099511628211ull; }
-    h ^= h >> 32; h *= 0x9e3779b97f4a7c15ull; h ^= h >> 29;
-    return h;
-  }
   void grow() {
     const uint64_t cap = slots_.empty() ? 1024 : slots_.size() * 2;
-    std::vector<int64_t> s(cap, -1);
-    for (uint64_t j = 0; j < n_; ++j) {
-      uint64_t h = hash(bytes_.data() + offs_[j], offs_[j + 1] - offs_[j]) & (cap - 1);
-      while (s[h] >= 0) h = (h + 1) & (cap - 1);
-      s[h] = (int64_t)j;
+    std::vector<Slot> s(cap, Slot{0, kEmpty, 0});
+    for (const Slot& sl : slots_) {
+      if (sl.idx == kEmpty) continue;
+      uint64_t at = sl.tag & (cap - 1);
+      while (s[at].idx != kEmpty) at = (at + 1) & (cap - 1);
+      s[at] = sl;
     }
     slots_.swap(s);
   }
   std::vector<uint8_t> bytes_;
   std::vector<uint32_t> offs_;
-  std::vector<int64_t> slots_;
+  std::vector<Slot> slots_;
   uint64_t n_ = 0;
+};
+
+// append-only byte buffer that grows without zero-filling (the pending log is written exactly once per byte)
+struct RawBuf {
+  uint8_t* p = nullptr; size_t n = 0, cap = 0;
+  ~RawBuf() { free(p); }
+  bool grow_to(size_t need) {
+    if (need <= cap) return true;
+    size_t c = cap ? cap : (1u << 16);
+    while (c < need) c *= 2;
+    uint8_t* q = (uint8_t*)realloc(p, c);
+    if (!q) return false;
+    p = q; cap = c;
+    return true;
+  }
 };
 
 struct PartitionState {
@@ -266,16 +324,31 @@ struct PartitionState {
   std::unordered_set<int64_t> aborting;              // producer ids inside an aborted transaction right now
 };
 
+struct KeyRef { uint32_t off, len; uint64_t hash; };
+struct Staged {
+  std::vector<uint8_t> recs;      // 64-byte records, agg field still zero
+  std::vector<KeyRef> keys;       // one per record, into `arena`
+  std::vector<uint8_t> arena;     // aggregate-id bytes (copied: the decompression scratch is reused per batch)
+  std::vector<uint32_t> idx;      // dense index of each record's aggregate (phase 2a)
+  std::vector<uint8_t> scratch;
+  PartitionState ps;              // the partition's state after this fetch (committed in phase 2)
+  sgr_ingest_stats st{};
+  int32_t rc = SGR_OK;
+  std::string err;
+  void reset() { recs.clear(); keys.clear(); arena.clear(); idx.clear(); scratch.clear(); st = sgr_ingest_stats{}; rc = SGR_OK; err.clear(); }
+};
+
 }  // namespace
 
 struct sgr_ingest {
   std::string last_error;
   KeyDict dict;
-  std::vector<uint8_t> pending;     // packed 64-byte records, arrival order
+  RawBuf pending;                   // packed 64-byte records, arrival order
   std::vector<uint8_t> scratch;     // decompressed records section of the batch being decoded
   std::map<int32_t, PartitionState> parts;
   sgr_ingest_stats total{};
   uint64_t keys_at_mark = 0;
+  std::vector<Staged> pool;         // staging buffers, reused across calls (a restore loop polls similar sizes)
 };
 
 namespace {
@@ -328,36 +401,39 @@ int32_t sgr_ingest_set_aborted(sgr_ingest* g, int32_t partition, const int64_t* 
   return SGR_OK;
 }
 
-int32_t sgr_ingest_record_batches(sgr_ingest* g, int32_t partition, const void* data, uint64_t nbytes, sgr_ingest_stats* stats) {
-  if (!g || (!data && nbytes)) return ifail(g, SGR_ERR_INVALID, "null argument");
-  const uint8_t* buf = (const uint8_t*)data;
-  PartitionState& ps = g->parts[partition];
-  sgr_ingest_stats st{};
-  // decode into a staging area so that a malformed batch leaves the pending log, the dictionary offsets and the
-  // partition's position exactly as they were (the caller sees an exception and the stream thread restarts)
-  const size_t pending_mark = g->pending.size();
-  const int64_t decoded_mark = ps.decoded_next;
-  const bool seen_mark = ps.seen;
-  auto rollback = [&]() { g->pending.resize(pending_mark); ps.decoded_next = decoded_mark; ps.seen = seen_mark; };
+}  // extern "C"
 
+// ---- phase 1 (any thread, touches nothing shared): one fetch -> staged records + key references
+namespace {
+int32_t sfail(Staged* o, int32_t code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+  o->err = buf; o->rc = code;
+  return code;
+}
+
+int32_t decode_fetch(int32_t partition, const uint8_t* buf, uint64_t nbytes, Staged* o) {
+  PartitionState& ps = o->ps;
+  sgr_ingest_stats& st = o->st;
+  o->recs.reserve(nbytes + nbytes / 4);
   uint64_t pos = 0;
   while (nbytes - pos >= 12) {
     const int64_t base_offset = (int64_t)be64(buf + pos);
     const int32_t batch_length = (int32_t)be32(buf + pos + 8);
-    if (batch_length < (int32_t)(kBatchHeader - 12)) { rollback(); return ifail(g, SGR_ERR_INVALID, "partition %d offset %lld: batch length %d is smaller than a v2 header", partition, (long long)base_offset, batch_length); }
+    if (batch_length < (int32_t)(kBatchHeader - 12)) return sfail(o, SGR_ERR_INVALID, "partition %d offset %lld: batch length %d is smaller than a v2 header", partition, (long long)base_offset, batch_length);
     const uint64_t total = 12ull + (uint32_t)batch_length;
     if (nbytes - pos < total) break;  // a fetch response may end with a partial batch: not an error, the next fetch repeats it
     const uint8_t* b = buf + pos;
     const int8_t magic = (int8_t)b[16];
-    if (magic != 2) { rollback(); return ifail(g, SGR_ERR_UNSUPPORTED, "partition %d offset %lld: message format v%d (only RecordBatch magic 2 is decoded)", partition, (long long)base_offset, (int)magic); }
+    if (magic != 2) return sfail(o, SGR_ERR_UNSUPPORTED, "partition %d offset %lld: message format v%d (only RecordBatch magic 2 is decoded)", partition, (long long)base_offset, (int)magic);
     const uint32_t crc = be32(b + 17);
     const uint32_t got = crc32c(b + 21, total - 21);
-    if (crc != got) { rollback(); return ifail(g, SGR_ERR_INVALID, "partition %d offset %lld: CRC-32C mismatch (stored %08x, computed %08x)", partition, (long long)base_offset, crc, got); }
+    if (crc != got) return sfail(o, SGR_ERR_INVALID, "partition %d offset %lld: CRC-32C mismatch (stored %08x, computed %08x)", partition, (long long)base_offset, crc, got);
     const uint16_t attrs = be16(b + 21);
     const int32_t last_offset_delta = (int32_t)be32(b + 23);
     const int64_t producer_id = (int64_t)be64(b + 43);
     const int32_t records_count = (int32_t)be32(b + 57);
-    if (last_offset_delta < 0 || records_count < 0) { rollback(); return ifail(g, SGR_ERR_INVALID, "partition %d offset %lld: negative lastOffsetDelta / recordsCount", partition, (long long)base_offset); }
+    if (last_offset_delta < 0 || records_count < 0) return sfail(o, SGR_ERR_INVALID, "partition %d offset %lld: negative lastOffsetDelta / recordsCount", partition, (long long)base_offset);
     const int64_t last_offset = base_offset + last_offset_delta;
     const int codec = attrs & 7;
     const bool transactional = attrs & 0x10, control = attrs & 0x20;
@@ -371,11 +447,11 @@ int32_t sgr_ingest_record_batches(sgr_ingest* g, int32_t partition, const void* 
     const uint8_t* recs = b + kBatchHeader;
     uint64_t recs_len = total - kBatchHeader;
     if (codec != 0) {
-      if (codec != 3) { rollback(); return ifail(g, SGR_ERR_UNSUPPORTED, "partition %d offset %lld: %s-compressed batch (none and lz4 are decoded)", partition, (long long)base_offset, codec_name(codec)); }
-      g->scratch.clear();
-      const std::string err = lz4_frame_decode(recs, recs_len, &g->scratch);
-      if (!err.empty()) { rollback(); return ifail(g, SGR_ERR_INVALID, "partition %d offset %lld: %s", partition, (long long)base_offset, err.c_str()); }
-      recs = g->scratch.data(); recs_len = g->scratch.size();
+      if (codec != 3) return sfail(o, SGR_ERR_UNSUPPORTED, "partition %d offset %lld: %s-compressed batch (none and lz4 are decoded)", partition, (long long)base_offset, codec_name(codec));
+      o->scratch.clear();
+      const std::string err = lz4_frame_decode(recs, recs_len, &o->scratch);
+      if (!err.empty()) return sfail(o, SGR_ERR_INVALID, "partition %d offset %lld: %s", partition, (long long)base_offset, err.c_str());
+      recs = o->scratch.data(); recs_len = o->scratch.size();
       st.n_compressed_bytes += total - kBatchHeader; st.n_decompressed_bytes += recs_len;
     }
 
@@ -383,7 +459,7 @@ int32_t sgr_ingest_record_batches(sgr_ingest* g, int32_t partition, const void* 
       ++st.n_control_batches;
       // control record key: int16 version, int16 type (0 = ABORT, 1 = COMMIT)
       Cursor c(recs, recs_len);
-      const int32_t rl = c.varint(); (void)rl;
+      c.varint();
       c.bytes(1); c.varlong(); c.varint();
       const int32_t kl = c.varint();
       const uint8_t* k = (c.ok && kl >= 4) ? c.bytes((uint64_t)kl) : nullptr;
@@ -392,9 +468,17 @@ int32_t sgr_ingest_record_batches(sgr_ingest* g, int32_t partition, const void* 
       ++st.n_aborted_batches; st.n_aborted_records += (uint64_t)records_count;
     } else {
       Cursor c(recs, recs_len);
+      // every record is at least 7 bytes on the wire, so the count cannot lie by much; size the outputs once per batch
+      if ((uint64_t)records_count > recs_len / 7 + 1) return sfail(o, SGR_ERR_INVALID, "partition %d offset %lld: recordsCount %d does not fit %llu bytes", partition, (long long)base_offset, records_count, (unsigned long long)recs_len);
+      const size_t recs_at0 = o->recs.size(), arena_at0 = o->arena.size();
+      o->recs.resize(recs_at0 + 64 * (size_t)records_count);
+      o->arena.resize(arena_at0 + recs_len);
+      o->keys.reserve(o->keys.size() + (size_t)records_count);
+      uint8_t* rec = o->recs.data() + recs_at0;
+      uint8_t* ar = o->arena.data() + arena_at0;
       for (int32_t r = 0; r < records_count; ++r) {
         const int32_t rec_len = c.varint();
-        if (!c.ok || rec_len < 0 || (uint64_t)rec_len > recs_len - c.pos) { rollback(); return ifail(g, SGR_ERR_INVALID, "partition %d offset %lld: record %d length runs past the batch", partition, (long long)base_offset, r); }
+        if (!c.ok || rec_len < 0 || (uint64_t)rec_len > recs_len - c.pos) return sfail(o, SGR_ERR_INVALID, "partition %d offset %lld: record %d length runs past the batch", partition, (long long)base_offset, r);
         Cursor q(recs + c.pos, (uint64_t)rec_len);
         c.pos += (uint64_t)rec_len;
         q.bytes(1);             // record attributes (unused in v2)
@@ -409,45 +493,149 @@ int32_t sgr_ingest_record_batches(sgr_ingest* g, int32_t partition, const void* 
           const int32_t hk = q.varint(); if (hk < 0) { q.ok = false; break; } q.bytes((uint64_t)hk);
           const int32_t hv = q.varint(); if (hv > 0) q.bytes((uint64_t)hv);
         }
-        if (!q.ok || q.pos != q.n || n_headers < 0) { rollback(); return ifail(g, SGR_ERR_INVALID, "partition %d offset %lld: record %d is malformed", partition, (long long)base_offset, r); }
+        if (!q.ok || q.pos != q.n || n_headers < 0) return sfail(o, SGR_ERR_INVALID, "partition %d offset %lld: record %d is malformed", partition, (long long)base_offset, r);
         const int64_t offset = base_offset + offset_delta;
         if (ps.seen && offset < ps.decoded_next) { ++st.n_duplicates; continue; }  // refetch after a restart: already decoded
         if (key_len <= 0) { ++st.n_markers; continue; }                              // the producer's empty-key flush record
         if (val_len < 0) { ++st.n_null_values; continue; }
-        if (val_len < 8 || val_len > 56) { rollback(); return ifail(g, SGR_ERR_INVALID, "partition %d offset %lld: packed event value of %d bytes (expected 8..56: u32 type, u32 seq, payload)", partition, (long long)offset, val_len); }
+        if (val_len < 8 || val_len > 56) return sfail(o, SGR_ERR_INVALID, "partition %d offset %lld: packed event value of %d bytes (expected 8..56: u32 type, u32 seq, payload)", partition, (long long)offset, val_len);
         uint32_t id_len = 0;
         while (id_len < (uint32_t)key_len && key[id_len] != ':') ++id_len;   // PartitionStringUpToColon (KafkaPartitioner.scala:38-42)
-        bool fresh;
-        const uint64_t agg = g->dict.intern(key, id_len, &fresh);
-        st.n_new_keys += fresh ? 1 : 0;
-        const size_t at = g->pending.size();
-        g->pending.resize(at + 64, 0);
-        uint8_t* rec = g->pending.data() + at;
-        memcpy(rec, val, 8);               // u32 type, u32 seq (little endian, as the packer wrote them)
-        memcpy(rec + 8, &agg, 8);
-        memcpy(rec + 16, val + 8, (size_t)val_len - 8);
+        if (id_len >= (1u << 24)) return sfail(o, SGR_ERR_INVALID, "partition %d offset %lld: aggregate id of %u bytes", partition, (long long)offset, id_len);
+        o->keys.push_back(KeyRef{(uint32_t)(ar - o->arena.data()), id_len, hash_bytes(key, id_len)});
+        memcpy(ar, key, id_len); ar += id_len;
+        memcpy(rec, val, 8);                    // u32 type, u32 seq (little endian, as the packer wrote them)
+        memcpy(rec + 16, val + 8, (size_t)val_len - 8);   // the rest of the slot is zero from resize(): agg, payload tail
+        rec += 64;
         ++st.n_records;
       }
-      if (c.pos != recs_len) { rollback(); return ifail(g, SGR_ERR_INVALID, "partition %d offset %lld: %llu stray bytes after the last record", partition, (long long)base_offset, (unsigned long long)(recs_len - c.pos)); }
+      o->recs.resize((size_t)(rec - o->recs.data()));
+      o->arena.resize((size_t)(ar - o->arena.data()));
+      if (c.pos != recs_len) return sfail(o, SGR_ERR_INVALID, "partition %d offset %lld: %llu stray bytes after the last record", partition, (long long)base_offset, (unsigned long long)(recs_len - c.pos));
     }
     if (!ps.seen || last_offset + 1 > ps.decoded_next) ps.decoded_next = last_offset + 1;
     ps.seen = true;
   }
   st.n_trailing_bytes = nbytes - pos;
   st.n_bytes = pos;
-  g->total.n_batches += st.n_batches; g->total.n_records += st.n_records; g->total.n_markers += st.n_markers;
-  g->total.n_null_values += st.n_null_values; g->total.n_control_batches += st.n_control_batches;
-  g->total.n_aborted_batches += st.n_aborted_batches; g->total.n_aborted_records += st.n_aborted_records;
-  g->total.n_duplicates += st.n_duplicates; g->total.n_new_keys += st.n_new_keys; g->total.n_bytes += st.n_bytes;
-  g->total.n_compressed_bytes += st.n_compressed_bytes; g->total.n_decompressed_bytes += st.n_decompressed_bytes;
-  if (stats) *stats = st;
+  if (o->arena.size() >= (1ull << 32)) return sfail(o, SGR_ERR_INVALID, "partition %d: more than 4 GiB of aggregate ids in one fetch", partition);
   return SGR_OK;
+}
+
+// ---- phase 2a (caller's thread): ids -> dense indices, in arrival order
+void intern_fetch(sgr_ingest* g, Staged* o) {
+  const size_t n = o->keys.size();
+  g->dict.reserve_for(n);
+  o->idx.resize(n);
+  const uint8_t* arena = o->arena.data();
+  // the dictionary of a big topic does not fit any cache: run the probe as a software pipeline — slot prefetched 16
+  // records ahead, the candidate's key bytes 8 ahead — so that the misses of neighbouring records overlap
+  constexpr size_t kSlotAhead = 16, kKeyAhead = 8;
+  for (size_t i = 0; i < std::min(n, kSlotAhead); ++i) g->dict.prefetch_slot(o->keys[i].hash);
+  for (size_t i = 0; i < n; ++i) {
+    if (i + kSlotAhead < n) g->dict.prefetch_slot(o->keys[i + kSlotAhead].hash);
+    if (i + kKeyAhead < n) g->dict.prefetch_key(o->keys[i + kKeyAhead].hash);
+    const KeyRef& k = o->keys[i];
+    bool fresh;
+    o->idx[i] = g->dict.intern(arena + k.off, k.len, k.hash, &fresh);
+    o->st.n_new_keys += fresh ? 1 : 0;
+  }
+}
+
+// ---- phase 2b (any thread): staged records -> their place in the pending log, aggregate index filled in
+void place_fetch(uint8_t* dst, const Staged* o) {
+  memcpy(dst, o->recs.data(), o->recs.size());
+  const size_t n = o->idx.size();
+  for (size_t i = 0; i < n; ++i) { const uint64_t agg = o->idx[i]; memcpy(dst + i * 64 + 8, &agg, 8); }
+}
+
+// ---- phase 2c (caller's thread): the partition's position and the totals
+void commit_fetch(sgr_ingest* g, int32_t partition, Staged* o) {
+  PartitionState& live = g->parts[partition];
+  const int64_t folded = live.folded_next;
+  live = std::move(o->ps);
+  live.folded_next = folded;
+  sgr_ingest_stats& t = g->total; const sgr_ingest_stats& st = o->st;
+  t.n_batches += st.n_batches; t.n_records += st.n_records; t.n_markers += st.n_markers;
+  t.n_null_values += st.n_null_values; t.n_control_batches += st.n_control_batches;
+  t.n_aborted_batches += st.n_aborted_batches; t.n_aborted_records += st.n_aborted_records;
+  t.n_duplicates += st.n_duplicates; t.n_new_keys += st.n_new_keys; t.n_bytes += st.n_bytes;
+  t.n_compressed_bytes += st.n_compressed_bytes; t.n_decompressed_bytes += st.n_decompressed_bytes;
+}
+
+template <typename F>
+void run_parallel(uint32_t n_tasks, uint32_t n_thr, F&& task) {
+  if (n_thr <= 1 || n_tasks <= 1) { for (uint32_t i = 0; i < n_tasks; ++i) task(i); return; }
+  std::atomic<uint32_t> next{0};
+  std::vector<std::thread> pool;
+  for (uint32_t t = 0; t < std::min(n_thr, n_tasks); ++t)
+    pool.emplace_back([&]() { for (uint32_t c; (c = next.fetch_add(1)) < n_tasks;) task(c); });
+  for (auto& th : pool) th.join();
+}
+}  // namespace
+
+extern "C" {
+
+// Decodes n fetches in one call: parsing, CRC and decompression run on up to `threads` host threads (fetches of one
+// partition stay on one thread, in call order); ids are interned and records appended afterwards, in call order, so
+// the result is identical to n single calls. All or nothing: if any fetch is malformed nothing is applied.
+int32_t sgr_ingest_record_batches_mt(sgr_ingest* g, uint32_t n, const int32_t* partitions, const void* const* datas, const uint64_t* nbytes,
+                                     uint32_t threads, sgr_ingest_stats* stats /* n entries or NULL */) {
+  if (!g || (n && (!partitions || !datas || !nbytes))) return ifail(g, SGR_ERR_INVALID, "null argument");
+  for (uint32_t i = 0; i < n; ++i) if (!datas[i] && nbytes[i]) return ifail(g, SGR_ERR_INVALID, "null data for fetch %u", i);
+  if (g->pool.size() < n) g->pool.resize(n);
+  std::vector<Staged>& staged = g->pool;
+  for (uint32_t i = 0; i < n; ++i) staged[i].reset();
+  // chain the fetches of one partition: fetch i starts from the state fetch prev[i] left (or the live state)
+  std::map<int32_t, std::vector<uint32_t>> by_part;
+  for (uint32_t i = 0; i < n; ++i) by_part[partitions[i]].push_back(i);
+  std::vector<const std::vector<uint32_t>*> chains;
+  for (auto& kv : by_part) chains.push_back(&kv.second);
+  for (auto& kv : by_part) g->parts[kv.first];   // create the entries now: phase 1 only reads the map
+  auto run_chain = [&](const std::vector<uint32_t>& chain) {
+    const PartitionState* from = &g->parts.find(partitions[chain[0]])->second;
+    for (uint32_t i : chain) {
+      staged[i].ps = *from;
+      if (decode_fetch(partitions[i], (const uint8_t*)datas[i], nbytes[i], &staged[i]) != SGR_OK) return;
+      from = &staged[i].ps;
+    }
+  };
+  const bool timing = getenv("SGR_INGEST_TIMING") != nullptr;
+  const auto t0 = std::chrono::steady_clock::now();
+  const uint32_t n_thr = std::max(1u, std::min<uint32_t>(threads ? threads : 1, (uint32_t)chains.size()));
+  run_parallel((uint32_t)chains.size(), n_thr, [&](uint32_t c) { run_chain(*chains[c]); });
+  for (uint32_t i = 0; i < n; ++i)
+    if (staged[i].rc != SGR_OK) { g->last_error = staged[i].err; return staged[i].rc; }
+  const auto t1 = std::chrono::steady_clock::now();
+  size_t add = 0;
+  for (uint32_t i = 0; i < n; ++i) add += staged[i].recs.size();
+  if (!g->pending.grow_to(g->pending.n + add)) return ifail(g, SGR_ERR_OOM, "pending log of %zu bytes", g->pending.n + add);
+  for (uint32_t i = 0; i < n; ++i) intern_fetch(g, &staged[i]);
+  std::vector<size_t> at(n);
+  for (uint32_t i = 0; i < n; ++i) { at[i] = g->pending.n; g->pending.n += staged[i].recs.size(); }
+  run_parallel(n, std::max(1u, threads), [&](uint32_t i) { place_fetch(g->pending.p + at[i], &staged[i]); });
+  for (uint32_t i = 0; i < n; ++i) {
+    commit_fetch(g, partitions[i], &staged[i]);
+    if (stats) stats[i] = staged[i].st;
+  }
+  if (timing) {
+    const auto t2 = std::chrono::steady_clock::now();
+    fprintf(stderr, "[sgr_ingest] %u fetches on %u threads: decode %.3f ms, intern+append %.3f ms\n", n, n_thr,
+            std::chrono::duration<double, std::milli>(t1 - t0).count(), std::chrono::duration<double, std::milli>(t2 - t1).count());
+  }
+  return SGR_OK;
+}
+
+int32_t sgr_ingest_record_batches(sgr_ingest* g, int32_t partition, const void* data, uint64_t nbytes, sgr_ingest_stats* stats) {
+  if (!g || (!data && nbytes)) return ifail(g, SGR_ERR_INVALID, "null argument");
+  const void* d[1] = {data};
+  return sgr_ingest_record_batches_mt(g, 1, &partition, d, &nbytes, 1, stats);
 }
 
 int32_t sgr_ingest_pending(sgr_ingest* g, const void** records, uint64_t* n_records) {
   if (!g || !records || !n_records) return ifail(g, SGR_ERR_INVALID, "null argument");
-  *records = g->pending.empty() ? nullptr : g->pending.data();
-  *n_records = g->pending.size() / 64;
+  *records = g->pending.n ? g->pending.p : nullptr;
+  *n_records = g->pending.n / 64;
   return SGR_OK;
 }
 
@@ -459,7 +647,7 @@ int32_t sgr_ingest_keys(sgr_ingest* g, const uint8_t** keys, const uint32_t** ke
 
 int32_t sgr_ingest_mark_folded(sgr_ingest* g) {
   if (!g) return SGR_ERR_INVALID;
-  g->pending.clear();
+  g->pending.n = 0;
   for (auto& kv : g->parts) kv.second.folded_next = kv.second.decoded_next;
   g->keys_at_mark = g->dict.size();
   return SGR_OK;

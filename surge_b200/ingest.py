@@ -61,6 +61,23 @@ class Ingest:
         self._check(self._lib.sgr_ingest_record_batches(self._h, partition, C.cast(buf, C.c_void_p) if buf is not None else None, len(data), C.byref(st)))
         return {n: int(getattr(st, n)) for n, _ in N.sgr_ingest_stats._fields_ if n != "reserved"}
 
+    def record_batches_mt(self, fetches: Sequence[Tuple[int, bytes]], threads: int = 0) -> List[Dict[str, int]]:
+        """Several fetches [(partition, bytes)] in one call, decoded on `threads` host threads (0 = one per partition,
+        capped by the host's cores); same outcome as calling record_batches on each in order."""
+        import os
+
+        n = len(fetches)
+        if not n:
+            return []
+        bufs = [(C.c_char * max(len(d), 1)).from_buffer_copy(d or b"\0") for _, d in fetches]
+        parts = (C.c_int32 * n)(*[p for p, _ in fetches])
+        ptrs = (C.c_void_p * n)(*[C.cast(b, C.c_void_p) for b in bufs])
+        lens = (C.c_uint64 * n)(*[len(d) for _, d in fetches])
+        st = (N.sgr_ingest_stats * n)()
+        thr = threads or min(len({p for p, _ in fetches}), os.cpu_count() or 1)
+        self._check(self._lib.sgr_ingest_record_batches_mt(self._h, n, parts, ptrs, lens, thr, st))
+        return [{k: int(getattr(s, k)) for k, _ in N.sgr_ingest_stats._fields_ if k != "reserved"} for s in st]
+
     def pending(self) -> np.ndarray:
         """Copy of the pending packed records, [n, 64] uint8."""
         p = C.c_void_p()

@@ -294,3 +294,51 @@ def test_varint_extremes_round_trip():
     ing = Ingest()
     assert ing.record_batches(0, b)["n_records"] == 2
     assert ing.offsets(0)[0] == 5 + big_delta + 1
+
+
+@pytest.mark.parametrize("threads", [1, 3, 8])
+def test_multi_fetch_call_equals_single_calls(threads):
+    rng = np.random.default_rng(77)
+    nxt = {p: 100 * p for p in range(4)}
+    fetches = []
+    for rnd in range(3):                       # several fetches per partition inside ONE call: they chain
+        for p in range(4):
+            buf, nxt[p] = _batch_stream(rng, 3, 200, "lz4" if (p + rnd) % 2 else "none", nxt[p])
+            if rnd == 1 and p == 2:
+                buf = buf + buf[:40]           # a trailing partial batch
+            fetches.append((p, buf))
+    fetches.append((9, b""))                  # an empty fetch
+    serial = Ingest()
+    want_stats = [serial.record_batches(p, b) for p, b in fetches]
+    par = Ingest()
+    got_stats = par.record_batches_mt(fetches, threads=threads)
+    assert got_stats == want_stats
+    assert np.array_equal(par.pending(), serial.pending())
+    assert par.keys() == serial.keys()
+    for p in (0, 1, 2, 3, 9):
+        assert par.offsets(p) == serial.offsets(p)
+    assert par.stats() == serial.stats()
+    # and again on warm staging buffers
+    more = []
+    for p in range(4):
+        buf, nxt[p] = _batch_stream(rng, 2, 300, "lz4", nxt[p])
+        more.append((p, buf))
+    assert par.record_batches_mt(more, threads=threads) == [serial.record_batches(p, b) for p, b in more]
+    assert np.array_equal(par.pending(), serial.pending()) and par.keys() == serial.keys()
+
+
+def test_multi_fetch_call_is_all_or_nothing():
+    rng = np.random.default_rng(78)
+    good0, _ = _batch_stream(rng, 3, 50, "lz4", 0)
+    good1, _ = _batch_stream(rng, 3, 50, "none", 0)
+    bad = bytearray(good1)
+    bad[len(bad) // 2] ^= 0x10
+    ing = Ingest()
+    ing.record_batches(5, K.encode_record_batch(0, [(0, b"seed", _event(0, 1, 1))]))
+    with pytest.raises(IngestError) as ei:
+        ing.record_batches_mt([(0, good0), (1, bytes(bad)), (2, good1)], threads=3)
+    assert "partition 1" in str(ei.value) and "CRC-32C" in str(ei.value)
+    assert ing.keys() == ["seed"] and len(ing.pending()) == 1
+    assert ing.offsets(0) == (0, 0) and ing.offsets(2) == (0, 0)
+    st = ing.record_batches_mt([(0, good0), (1, good1), (2, good1)], threads=3)
+    assert sum(s["n_records"] for s in st) == len(ing.pending()) - 1

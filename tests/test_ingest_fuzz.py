@@ -1,0 +1,97 @@
+"""Memory-safety fuzz of the record-batch decoder: the decoder reads bytes that came off a network.
+
+Builds surge_b200/csrc/ingest.cpp + tests/fuzz/ingest_fuzz_main.cpp with AddressSanitizer and UBSan (host-only code, no
+CUDA) and runs a few thousand mutated inputs through it. Mutants are re-sealed with a fresh CRC-32C so that the damage
+reaches the record parser and the lz4 decoder instead of stopping at the checksum.
+"""
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import kafka_batch as K
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OUT = os.path.join(ROOT, "oracle", "_build")
+BIN = os.path.join(OUT, "ingest_fuzz_asan")
+
+
+def _build():
+    os.makedirs(OUT, exist_ok=True)
+    srcs = [os.path.join(ROOT, "surge_b200", "csrc", "ingest.cpp"), os.path.join(ROOT, "tests", "fuzz", "ingest_fuzz_main.cpp")]
+    if os.path.exists(BIN) and os.path.getmtime(BIN) >= max(os.path.getmtime(s) for s in srcs):
+        return
+    cmd = ["g++", "-std=c++17", "-O1", "-g", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined", "-fno-omit-frame-pointer",
+           *srcs, "-o", BIN, "-lpthread"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        pytest.skip("sanitizer build unavailable: " + r.stderr[-300:])
+
+
+def _reseal(batch: bytearray) -> bytes:
+    """Recompute batchLength-consistent CRC of a single (mutated) batch."""
+    if len(batch) >= 21:
+        batch[17:21] = struct.pack(">I", K.crc32c(bytes(batch[21:])))
+    return bytes(batch)
+
+
+def _corpus(rng, n_cases):
+    ev = lambda s, extra=b"": struct.pack("<IIi", s % 3, s, s * 7) + extra  # noqa: E731
+    seeds = []
+    for comp in ("none", "lz4"):
+        recs = [(d, f"agg-{d % 7}:{d}".encode(), ev(d, bytes(d % 40))) for d in range(30)]
+        seeds.append(K.encode_record_batch(10, recs, compression=comp, headers=[(b"h", b"v"), (b"n", None)]))
+        seeds.append(K.encode_record_batch(0, [(0, b"", b""), (1, None, ev(1)), (2, b"k", None)], compression=comp, producer_id=3, transactional=True))
+    seeds.append(K.encode_control_batch(5, 3, K.ABORT))
+    frames = [K.lz4_frame_compress(bytes(rng.integers(97, 101, 3000, dtype=np.uint8)), **kw)
+              for kw in (dict(), dict(block_checksum=True, content_checksum=True, content_size=True))]
+    cases = [(0, s) for s in seeds] + [(1, f) for f in frames]
+    while len(cases) < n_cases:
+        if rng.random() < 0.75:
+            b = bytearray(seeds[int(rng.integers(0, len(seeds)))])
+            style = rng.random()
+            for _ in range(int(rng.integers(1, 4))):
+                pos = int(rng.integers(21, len(b))) if style < 0.8 else int(rng.integers(0, len(b)))
+                b[pos] = int(rng.integers(0, 256)) if rng.random() < 0.5 else b[pos] ^ (1 << int(rng.integers(0, 8)))
+            if rng.random() < 0.15:       # lie about recordsCount / lastOffsetDelta
+                struct.pack_into(">i", b, 57 if rng.random() < 0.5 else 23, int(rng.integers(-5, 1 << 31)))
+            data = _reseal(b) if style < 0.8 else bytes(b)
+            if rng.random() < 0.2:
+                data = data[: int(rng.integers(0, len(data) + 1))]
+            if rng.random() < 0.2:
+                data = data + seeds[int(rng.integers(0, len(seeds)))]
+            cases.append((0, data))
+        else:
+            f = bytearray(frames[int(rng.integers(0, len(frames)))])
+            for _ in range(int(rng.integers(1, 4))):
+                pos = int(rng.integers(0, len(f)))
+                f[pos] = int(rng.integers(0, 256))
+            if rng.random() < 0.3:
+                f = f[: int(rng.integers(0, len(f) + 1))]
+            if rng.random() < 0.5:
+                # wrap the damaged frame as the records section of a batch, sealed, so the batch path decodes it too
+                tail = struct.pack(">hiqqqhii", 3, 0, 0, 0, -1, -1, -1, 1) + bytes(f)
+                cases.append((0, struct.pack(">qiib", 0, 9 + len(tail), 0, 2) + struct.pack(">I", K.crc32c(tail)) + tail))
+            else:
+                cases.append((1, bytes(f)))
+    return cases
+
+
+def test_decoder_survives_mutated_input_under_asan_ubsan(tmp_path):
+    _build()
+    rng = np.random.default_rng(2024)
+    cases = _corpus(rng, 3000)
+    path = tmp_path / "corpus.bin"
+    with open(path, "wb") as f:
+        f.write(struct.pack("<I", len(cases)))
+        for kind, data in cases:
+            f.write(struct.pack("<BI", kind, len(data)) + data)
+    env = dict(os.environ, ASAN_OPTIONS="detect_leaks=1:abort_on_error=0", UBSAN_OPTIONS="print_stacktrace=1")
+    r = subprocess.run([BIN, str(path)], capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, (r.stdout[-500:], r.stderr[-3000:])
+    assert f"cases={len(cases)}" in r.stdout
+    ok = int(r.stdout.split("ok=")[1].split()[0])
+    refused = int(r.stdout.split("refused=")[1].split()[0])
+    assert ok > 50 and refused > 500      # both outcomes are exercised
