@@ -110,6 +110,13 @@ struct sgr_engine {
   sgr_dist_stats dstats{};
 
   std::shared_ptr<const KeyTable> keys;   // swapped atomically: sgr_get readers never see a table being rebuilt
+  // ids handed over by sgr_fold_ingested: appended per poll (the dictionary is append-only), hashed lazily by the first
+  // sgr_get that follows — a restore polls thousands of times before anybody reads
+  std::mutex keys_mu;
+  std::vector<uint8_t> ing_key_bytes;
+  std::vector<uint32_t> ing_key_offs;
+  const sgr_ingest* ing_keys_from = nullptr;
+  std::atomic<bool> keys_stale{false};
   std::mutex snap_mu;
   std::shared_ptr<Snapshot> snapshot;
   std::atomic<bool> snapshot_dirty{true};
@@ -757,6 +764,9 @@ int32_t sgr_load_keys(sgr_engine* e, const uint8_t* keys, const uint32_t* key_of
   std::string err;
   auto kt = std::make_shared<KeyTable>();
   if (!kt->build(keys, key_offsets, n_agg, &err)) return fail(e, SGR_ERR_INVALID, "%s", err.c_str());
+  std::lock_guard<std::mutex> lk(e->keys_mu);
+  e->ing_keys_from = nullptr; e->ing_key_bytes.clear(); e->ing_key_offs.clear();
+  e->keys_stale.store(false, std::memory_order_release);
   std::atomic_store(&e->keys, std::shared_ptr<const KeyTable>(kt));
   return SGR_OK;
 }
@@ -797,8 +807,16 @@ int32_t sgr_fold_ingested(sgr_engine* e, sgr_ingest* g) {
     int32_t rc = sgr_grow_states(e, cap); if (rc) return rc;
   }
   if (n_records) { int32_t rc = sgr_fold_incremental(e, recs, n_records); if (rc) return rc; }
-  std::shared_ptr<const KeyTable> cur = std::atomic_load(&e->keys);
-  if (!cur || cur->size() != n_keys) { int32_t rc = sgr_load_keys(e, keys, key_offsets, n_keys); if (rc) return rc; }
+  {
+    std::lock_guard<std::mutex> lk(e->keys_mu);
+    if (e->ing_keys_from != g) { e->ing_keys_from = g; e->ing_key_bytes.clear(); e->ing_key_offs.assign(1, 0u); }
+    const uint64_t have = e->ing_key_offs.size() - 1;
+    if (n_keys > have) {
+      e->ing_key_bytes.insert(e->ing_key_bytes.end(), keys + key_offsets[have], keys + key_offsets[n_keys]);
+      e->ing_key_offs.insert(e->ing_key_offs.end(), key_offsets + have + 1, key_offsets + n_keys + 1);
+      e->keys_stale.store(true, std::memory_order_release);
+    }
+  }
   sgr_ingest_mark_folded(g);
   return SGR_OK;
 }
@@ -828,6 +846,16 @@ int32_t sgr_get_index(sgr_engine* e, uint64_t agg, void* out, uint32_t cap, uint
 
 int32_t sgr_get(sgr_engine* e, const uint8_t* key, uint32_t klen, void* out, uint32_t cap, uint32_t* outlen, int32_t* exists) {
   if (!e || (!key && klen)) return fail(e, SGR_ERR_INVALID, "null argument");
+  if (e->keys_stale.load(std::memory_order_acquire)) {
+    std::lock_guard<std::mutex> lk(e->keys_mu);
+    if (e->keys_stale.load(std::memory_order_relaxed)) {
+      auto fresh = std::make_shared<KeyTable>();
+      std::string err;
+      if (!fresh->build(e->ing_key_bytes.data(), e->ing_key_offs.data(), e->ing_key_offs.size() - 1, &err)) return fail(e, SGR_ERR_INVALID, "%s", err.c_str());
+      std::atomic_store(&e->keys, std::shared_ptr<const KeyTable>(fresh));
+      e->keys_stale.store(false, std::memory_order_release);
+    }
+  }
   std::shared_ptr<const KeyTable> kt = std::atomic_load(&e->keys);
   int64_t idx = kt ? kt->find(key, klen) : -1;
   if (idx < 0) {  // unknown aggregate id: Option.empty, like a KTable miss
