@@ -105,6 +105,12 @@ extern "C" {
  *                 All offsets/lengths are byte counts and multiples of 4.
  *
  * An event whose type is >= n_types is a scala.MatchError, i.e. SGR_THROW.
+ *
+ * Instance identity: a rule with field ops, SGR_CREATE, and SGR_MATERIALISE on None build a NEW state instance
+ * (Scala constructor / copy); SGR_IF_EXISTS / SGR_MATERIALISE without ops on an existing state hand the same instance
+ * back (`current`). The publish rule compares with the case-class equals, which starts with `this eq that`: an
+ * aggregate with no events in the fold, or only instance-preserving ones, is never SGR_ST_CHANGED — even if one of its
+ * Double fields holds a NaN — while a new instance compares field by field (NaN != NaN, 0.0 == -0.0).
  */
 #define SGR_IF_EXISTS    0u
 #define SGR_MATERIALISE  1u

@@ -19,6 +19,11 @@
 /* ------------------------------------------------------------------ Option[Agg] */
 typedef struct {
   int has;   /* 0 = None, 1 = Some */
+  /* JVM object identity of the state instance: bumped whenever the handler constructs or copies a state
+   * (State(...), current.copy(...)); unchanged when it hands `current` back. Scala's generated case-class equals
+   * starts with `this eq that`, so the publish rule (PersistentActor.scala:257) sees an untouched instance as
+   * equal to itself even if one of its Double fields holds a NaN. */
+  uint32_t inst;
   union {
     orc_counter_state counter;
     orc_bank_account bank;
@@ -69,9 +74,9 @@ static int handle_event_counter(opt_state* s, const event_t* e) {
   orc_counter_state cur;
   if (s->has) cur = s->v.counter; else { cur.count = 0; cur.version = 0; }
   switch (e->type) {
-    case 0: cur.count = (int32_t)((uint32_t)cur.count + (uint32_t)e->arg); cur.version = (int32_t)e->seq; break;
-    case 1: cur.count = (int32_t)((uint32_t)cur.count - (uint32_t)e->arg); cur.version = (int32_t)e->seq; break;
-    case 2: break;
+    case 0: cur.count = (int32_t)((uint32_t)cur.count + (uint32_t)e->arg); cur.version = (int32_t)e->seq; s->inst++; break;
+    case 1: cur.count = (int32_t)((uint32_t)cur.count - (uint32_t)e->arg); cur.version = (int32_t)e->seq; s->inst++; break;
+    case 2: if (!s->has) s->inst++; break;   /* `current`: the old instance, or the getOrElse default just built */
     default: return 1; /* ExceptionThrowingEvent, or scala.MatchError for anything else */
   }
   s->has = 1; s->v.counter = cur;
@@ -92,14 +97,14 @@ static int handle_event_ml_counter(opt_state* s, const event_t* e) {
 static int handle_event_bank(opt_state* s, const event_t* e) {
   switch (e->type) {
     case 0:
-      s->has = 1;
+      s->has = 1; s->inst++;
       memcpy(s->v.bank.uuid, e->uuid, 16);
       memcpy(s->v.bank.owner, e->owner, 16);
       memcpy(s->v.bank.code, e->code, 8);
       s->v.bank.balance_bits = e->balance_bits;
       return 0;
     case 1:
-      if (s->has) s->v.bank.balance_bits = e->balance_bits;
+      if (s->has) { s->v.bank.balance_bits = e->balance_bits; s->inst++; }   /* _.copy(balance = ...) */
       return 0;
     default: return 1; /* MatchError */
   }
@@ -112,6 +117,7 @@ static int handle_event_int_balance(opt_state* s, const event_t* e) {
   if (e->type != 0) return 1;
   if (!s->has) { s->has = 1; s->v.ib.balance = e->arg; }
   else s->v.ib.balance = (int32_t)((uint32_t)s->v.ib.balance + (uint32_t)e->arg);
+  s->inst++;
   return 0;
 }
 
@@ -206,6 +212,7 @@ static void encode_state(int model, const opt_state* s, uint32_t flags, uint32_t
 static int states_equal(int model, const opt_state* a, const opt_state* b) {
   if (a->has != b->has) return 0;
   if (!a->has) return 1;
+  if (a->inst == b->inst) return 1;   /* `this eq that` */
   switch (model) {
     case ORC_MODEL_COUNTER: case ORC_MODEL_ML_COUNTER:
       return a->v.counter.count == b->v.counter.count && a->v.counter.version == b->v.counter.version;

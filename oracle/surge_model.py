@@ -13,7 +13,7 @@ Paths are relative to the reference checkout.
 from __future__ import annotations
 
 import json
-from dataclasses import dataclass, replace
+from dataclasses import dataclass, fields, replace
 from functools import reduce
 from typing import Callable, Dict, List, Optional, Sequence, Tuple
 
@@ -181,6 +181,22 @@ def fold_left(handle_event: Callable, state, events: Sequence):
     return reduce(handle_event, events, state)
 
 
+def scala_equals(a, b) -> bool:
+    """`state.stateOpt != context.state` (PersistentActor.scala:257) on Option[case class]: scalac's generated equals is
+    `(this eq that) || (same class && every field ==)`, and a Double field compares by VALUE (0.0 == -0.0, NaN != NaN).
+    Python's dataclass __eq__ compares field tuples, whose element comparison short-cuts on identity — the same NaN
+    object would compare equal — so the rule is spelled out here."""
+    if a is b:
+        return True
+    if a is None or b is None or type(a) is not type(b):
+        return False
+    for f in fields(a):
+        x, y = getattr(a, f.name), getattr(b, f.name)
+        if not (x == y):
+            return False
+    return True
+
+
 @dataclass
 class Ack:
     success: bool
@@ -197,7 +213,7 @@ def apply_events(handle_event: Callable, state, events: Sequence) -> Ack:
         new_state = fold_left(handle_event, state, events)
     except Exception as e:  # noqa: BLE001 - mirrors .recover { case e => ACKError(e) }
         return Ack(False, state, False, str(e))
-    return Ack(True, new_state, new_state != state)
+    return Ack(True, new_state, not scala_equals(new_state, state))
 
 
 def handle_command(process_command: Callable, handle_event: Callable, state, cmd) -> Tuple[object, List]:

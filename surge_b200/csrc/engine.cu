@@ -233,7 +233,7 @@ int32_t enqueue_fold(sgr_engine* e, const uint8_t* d_events, const uint64_t* d_o
   bool use_rows = e->row_ok && !wide_balanced && e->program.record_kind == SGR_REC_FIXED64 && aligned64 && e->opt_kernel != 1 && n_seg < (1ull << 32) && n_seg > 0;
   if ((e->opt_kernel == 2 || e->opt_kernel == 3) && !use_rows && n_seg > 0)
     return fail(e, SGR_ERR_UNSUPPORTED, "record-parallel kernel cannot take this program/log");
-  if (use_rows && e->opt_kernel == 3 && (e->row_prog.user_words != 2 || e->row_prog.cls != 0 || e->row_prog.n_slots > 6))
+  if (use_rows && e->opt_kernel == 3 && (e->row_prog.user_words != 2 || e->row_prog.cls != 0 || e->row_prog.n_slots > 6 || e->row_prog.f64_mask))
     return fail(e, SGR_ERR_UNSUPPORTED, "the record-per-lane kernel takes 16-byte class-0 programs only");
   const bool runs = use_rows && e->opt_kernel != 3;
   unsigned long long* counters = (unsigned long long*)e->counters.p;
@@ -710,7 +710,8 @@ static int32_t fold_incremental_impl(sgr_engine* e, const void* d_records, uint6
   if (e->program.record_kind != SGR_REC_FIXED64) return fail(e, SGR_ERR_UNSUPPORTED, "incremental batches take fixed 64-byte records");
   if (!e->states_valid) return fail(e, SGR_ERR_NOT_LOADED, "incremental fold needs a live state table (fold or set_initial_states first)");
   { int32_t rc0 = finish_fold(e); if (rc0) return rc0; }
-  if (e->row_ok && e->row_prog.user_words == 2 && e->row_prog.cls == 0 && e->opt_kernel != 1 && e->opt_kernel != 3 && e->opt_incremental != 1)
+  // (a 16-byte state that is one JVM Double compares with ==, not bitwise: it takes the sort-based path)
+  if (e->row_ok && e->row_prog.user_words == 2 && e->row_prog.cls == 0 && !e->row_prog.f64_mask && e->opt_kernel != 1 && e->opt_kernel != 3 && e->opt_incremental != 1)
     return fold_incremental_atomic(e, d_records, n_records);
   e->inc_atomic_prev_valid = false;
   const uint64_t n_agg = e->states_n;
@@ -929,7 +930,7 @@ int32_t sgr_get_stats(sgr_engine* e, sgr_stats* out) {
 // class-0 programs need no grouping at all: the records are folded with integer atomics (incremental.cu);
 // other programs are grouped stably (K5) and folded from the CSR.
 static int32_t fold_arrival_order(sgr_engine* e, const uint8_t* d_records, uint64_t n_records, uint64_t n_agg) {
-  const bool sort_free = e->row_ok && e->row_prog.user_words == 2 && e->row_prog.cls == 0 && e->opt_kernel != 1 && e->opt_kernel != 3 &&
+  const bool sort_free = e->row_ok && e->row_prog.user_words == 2 && e->row_prog.cls == 0 && !e->row_prog.f64_mask && e->opt_kernel != 1 && e->opt_kernel != 3 &&
                          e->opt_incremental != 1 && n_records > 0;
   int32_t rc;
   if (sort_free) {

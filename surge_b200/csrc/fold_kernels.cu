@@ -159,6 +159,7 @@ fold_stream_kernel(const __grid_constant__ FoldArgs a, const __grid_constant__ D
   bool c_has = c_seg < n_seg;
   bool c_fresh = true;
   uint32_t rp = 0, avail = 0, k = 0, exists = 0, exists0 = 0, err = 0, err_idx = 0;
+  uint32_t copied = 0;  // some event of this segment produced a NEW state instance (Scala copy / constructor), see end_segment
   unsigned long long n_applied = 0, n_err = 0, n_skipped = 0, n_dropped = 0;
   uint32_t c_total = 0;  // bytes of the current segment received so far
 
@@ -178,16 +179,17 @@ fold_stream_kernel(const __grid_constant__ FoldArgs a, const __grid_constant__ D
         if (!exists) { ++k; ++n_applied; return; }
         break;
       case SGR_MATERIALISE:
-        if (!exists) { zero_state(); exists = 1; }
+        if (!exists) { zero_state(); exists = 1; copied = 1; }
         break;
       case SGR_CREATE:
-        zero_state(); exists = 1;
+        zero_state(); exists = 1; copied = 1;
         break;
       case SGR_TOMBSTONE:
         zero_state(); exists = 0; ++k; ++n_applied; return;
       default:
         err = 1; err_idx = k; return;
     }
+    if (r0.y) copied = 1;   // field ops = `current.copy(...)`; a rule without ops hands the same instance back
     for (uint32_t i = 0; i < r0.y; ++i) {
       const uint32_t op = r->ops[i];
       const uint32_t opcode = op & 15u, nwords = (op >> 4) & 63u, dw = (op >> 10) & 63u, sw = op >> 16;
@@ -217,7 +219,7 @@ fold_stream_kernel(const __grid_constant__ FoldArgs a, const __grid_constant__ D
   };
 
   auto begin_segment = [&](int s) {
-    rp = (uint32_t)s * CH; avail = 0; k = 0; err = 0; err_idx = 0; exists = 0; exists0 = 0; c_total = 0;
+    rp = (uint32_t)s * CH; avail = 0; k = 0; err = 0; err_idx = 0; exists = 0; exists0 = 0; c_total = 0; copied = 0;
     if (a.states_in) {
       const uint64_t sg = seg_of(c_seg);
       const uint64_t slot = a.seg_ids ? (uint64_t)a.seg_ids[sg] : sg;
@@ -254,7 +256,9 @@ fold_stream_kernel(const __grid_constant__ FoldArgs a, const __grid_constant__ D
         if (prog->n_f64 == 0) {
           for (uint32_t w = 0; w < user_words; ++w) changed |= (st[w * THREADS] != st0[w * THREADS]);
         } else {
-          // JVM Double ==: f64 fields compare numerically (0.0 == -0.0, NaN != NaN), the rest bitwise
+          // JVM Double ==: f64 fields compare numerically (0.0 == -0.0, NaN != NaN), the rest bitwise. Case-class
+          // equals starts with `this eq that`: when no event built a new instance (empty segment, or only rules without
+          // ops) the state IS the old object and equal to itself even if it holds a NaN.
           for (uint32_t w = 0; w < user_words; ++w) {
             bool is_f64 = false;
             for (uint32_t f = 0; f < prog->n_f64; ++f) is_f64 |= (w == prog->f64_word[f]) || (w == prog->f64_word[f] + 1);
@@ -262,9 +266,10 @@ fold_stream_kernel(const __grid_constant__ FoldArgs a, const __grid_constant__ D
           }
           for (uint32_t f = 0; f < prog->n_f64; ++f) {
             const uint32_t w = prog->f64_word[f];
-            const double x = __hiloint2double((int)st[(w + 1) * THREADS], (int)st[w * THREADS]);
-            const double y = __hiloint2double((int)st0[(w + 1) * THREADS], (int)st0[w * THREADS]);
-            changed |= !(x == y);
+            const uint32_t xl = st[w * THREADS], xh = st[(w + 1) * THREADS], yl = st0[w * THREADS], yh = st0[(w + 1) * THREADS];
+            const double x = __hiloint2double((int)xh, (int)xl);
+            const double y = __hiloint2double((int)yh, (int)yl);
+            changed |= !(x == y) && (copied || xl != yl || xh != yh);
           }
         }
       }

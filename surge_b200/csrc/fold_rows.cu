@@ -467,7 +467,9 @@ bool build_row_program(const DevProgram& dp, RowProgram* out) {
         mode[w] = (opcode == SGR_OP_SET || reset) ? 2u : 1u;  // over a reset state ADD v == SET v and SUB v == SET -v
       }
     }
-    e[0] = 1u | (r.exists_rule == SGR_TOMBSTONE ? 2u : 0u) | (r.exists_rule == SGR_IF_EXISTS ? 4u : 0u);
+    // 8u: the rule builds a new state instance (Scala constructor or copy): CREATE, or any field op
+    e[0] = 1u | (r.exists_rule == SGR_TOMBSTONE ? 2u : 0u) | (r.exists_rule == SGR_IF_EXISTS ? 4u : 0u) |
+           ((r.exists_rule == SGR_CREATE || r.n_ops > 0) ? 8u : 0u);
     for (uint32_t w = 0; w < dp.user_words; ++w) e[1 + w] = mode[w] | (neg[w] << 2) | (slot[w] << 3);
   }
   return true;

@@ -34,13 +34,14 @@ namespace sgr {
 namespace {
 
 constexpr uint32_t M_ERR = 0x80000000u;  // some event in the range threw
+constexpr uint32_t M_COPY = 0x40000000u; // some applied event built a new state instance (tab flag 8u << 27), see finish_segment
 constexpr uint32_t EX_SOME = 1u, EX_NONE = 2u;
 constexpr int kRunThreads = 128;
 constexpr int kRunWarps = kRunThreads / 32;
 
 template <int W>
 struct Xf {
-  uint32_t m;     // bits [2w+1:2w]: mode of word w (bit0 ADD, bit1 SET; OR-composable), bit31 error
+  uint32_t m;     // bits [2w+1:2w]: mode of word w (bit0 ADD, bit1 SET; OR-composable), bit30 copy, bit31 error
   uint32_t ex;    // exists-op of the LAST event in the range: 0 = no event, EX_SOME, EX_NONE
   uint32_t v[W];  // KEEP => 0
 };
@@ -130,10 +131,12 @@ __device__ __forceinline__ void finish_segment(const RowArgs& a, uint32_t f64_ma
     for (int w = 0; w < W; ++w) {
       const bool f_lo = (f64_mask >> w) & 1u, f_hi = w > 0 && ((f64_mask >> (w - 1)) & 1u);
       if (f_lo) {
-        // JVM Double ==: numeric (0.0 == -0.0, NaN != NaN), as Scala case-class equality does
-        const double x = __hiloint2double((int)nw[w + 1 < W ? w + 1 : w], (int)nw[w]);
-        const double y = __hiloint2double((int)old[w + 1 < W ? w + 1 : w], (int)old[w]);
-        changed |= !(x == y);
+        // JVM Double ==: numeric (0.0 == -0.0, NaN != NaN), as Scala case-class equality does — after its `this eq that`
+        // shortcut: if no applied event built a new instance the state is the old object, equal to itself even with a NaN
+        const uint32_t xh = nw[w + 1 < W ? w + 1 : w], yh = old[w + 1 < W ? w + 1 : w];
+        const double x = __hiloint2double((int)xh, (int)nw[w]);
+        const double y = __hiloint2double((int)yh, (int)old[w]);
+        changed |= !(x == y) && ((ts.m & M_COPY) != 0u || nw[w] != old[w] || xh != yh);
       } else if (!f_hi) {
         changed |= (nw[w] != old[w]);
       }
@@ -387,6 +390,7 @@ __global__ void __launch_bounds__(kRunThreads, MINB) fold_runs_kernel(const __gr
             else if (mode == 1u) cur.v[w] += val;
             cur.m |= mode << (2 * w);
           }
+          cur.m |= (e0.x & 8u) << 27;   // M_COPY: this rule builds a new instance (CREATE, or any field op)
         }
       }
     }

@@ -710,6 +710,40 @@ def test_fold_unsorted_one_call(prog_name):
         assert_same(e.export_states(), O.fold_incremental(model, batch, want))
 
 
+@pytest.mark.parametrize("kernel", [0, 1, 2])
+def test_untouched_instance_with_nan_is_not_changed(kernel):
+    """Case-class equals starts with `this eq that`: an account whose balance is NaN and that receives no event in the
+    fold keeps its instance and is not CHANGED; one that receives Updated(NaN) is a new instance and is CHANGED
+    (tests/test_oracle_golden.py::test_untouched_instance_equals_itself_even_with_nan pins the oracle)."""
+    n_agg = 64
+    ids = [str(uuid.UUID(int=1000 + i)) for i in range(n_agg)]
+    nan = float("nan")
+    created = b"".join(F.bank_created_record(i, 1, ids[i], "o", "c", nan if i % 2 else 1.0) for i in range(n_agg))
+    off = np.arange(n_agg + 1, dtype=np.uint64) * 64
+    ev = np.frombuffer(created, np.uint8)
+    init, _, _ = O.fold_packed(O.MODEL_BANK_ACCOUNT, O.REC_FIXED64, ev, off)
+    got, _ = run_engine(P.bank_account_program(), ev, off, kernel=kernel)
+    assert_same(got, init, "create")
+    # second fold: a third of the accounts get nothing, a third Updated(same value: NaN or 1.0), a third Updated(-0.0)
+    recs, counts = [], []
+    for i in range(n_agg):
+        if i % 3 == 0:
+            counts.append(0)
+        elif i % 3 == 1:
+            recs.append(F.bank_updated_record(i, 2, ids[i], nan if i % 2 else 1.0)); counts.append(1)
+        else:
+            recs.append(F.bank_updated_record(i, 2, ids[i], -0.0)); counts.append(1)
+    ev2 = np.frombuffer(b"".join(recs), np.uint8)
+    off2 = np.zeros(n_agg + 1, np.uint64)
+    np.cumsum(np.asarray(counts) * 64, out=off2[1:])
+    want, _, _ = O.fold_packed(O.MODEL_BANK_ACCOUNT, O.REC_FIXED64, ev2, off2, init)
+    flags = want.view(F.BANK_STATE).reshape(-1)["flags"]
+    assert all(int(flags[i]) == N.ST_EXISTS for i in range(0, n_agg, 3))                       # untouched, NaN or not
+    assert all(int(flags[i]) == (N.ST_EXISTS | (N.ST_CHANGED if i % 2 else 0)) for i in range(1, n_agg, 3))
+    got2, _ = run_engine(P.bank_account_program(), ev2, off2, kernel=kernel, init=init)
+    assert_same(got2, want, "second fold")
+
+
 # ------------------------------------------------------------------ raw Kafka record batches -> fold (SURVEY §8 f1/f2)
 def test_grow_states_keeps_content():
     n_agg = 3000

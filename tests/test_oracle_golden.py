@@ -186,6 +186,33 @@ def test_bank_account_double_equality_is_numeric():
     assert M.BankAccount(n, "o", "c", 0.0) == M.BankAccount(n, "o", "c", -0.0)
 
 
+def test_untouched_instance_equals_itself_even_with_nan():
+    """scalac's case-class equals is `(this eq that) || fields ==`: an ApplyEvents that hands the SAME instance back
+    (no events; Counter NoOpEvent => current) publishes nothing even if a Double field holds NaN, while
+    `_.copy(balance = NaN)` builds a new instance whose NaN != the old NaN (PersistentActor.scala:257)."""
+    n = str(uuid.UUID(int=11))
+    nan = float("nan")
+    acct = M.BankAccount(n, "o", "c", nan)
+    assert not M.apply_events(M.bank_account_handle_event, acct, []).published_state
+    assert M.apply_events(M.bank_account_handle_event, acct, [M.BankAccountUpdated(n, nan)]).published_state
+    assert M.scala_equals(acct, acct) and not M.scala_equals(acct, M.BankAccount(n, "o", "c", nan))
+    st = M.State("a", 3, 3)
+    assert M.counter_handle_event(st, M.NoOpEvent("a", 4)) is st
+    # the C oracle: a NaN state, then an empty segment -> not CHANGED; an Updated(NaN) -> CHANGED
+    created = F.bank_created_record(0, 1, n, "o", "c", nan)
+    init, _, _ = O.fold_packed(O.MODEL_BANK_ACCOUNT, O.REC_FIXED64, np.frombuffer(created, np.uint8), np.array([0, 64], np.uint64))
+    empty, _, _ = O.fold_packed(O.MODEL_BANK_ACCOUNT, O.REC_FIXED64, np.zeros(0, np.uint8), np.array([0, 0], np.uint64), init)
+    assert int(empty.view(F.BANK_STATE).reshape(-1)[0]["flags"]) == O.ST_EXISTS
+    upd = F.bank_updated_record(0, 2, n, nan)
+    again, _, _ = O.fold_packed(O.MODEL_BANK_ACCOUNT, O.REC_FIXED64, np.frombuffer(upd, np.uint8), np.array([0, 64], np.uint64), init)
+    assert int(again.view(F.BANK_STATE).reshape(-1)[0]["flags"]) == O.ST_EXISTS | O.ST_CHANGED
+    # the program interpreter agrees with the C oracle on both
+    from oracle import program_interp as I
+    rules = [(I.CREATE, [(I.OP_SET, 0, 16, 16), (I.OP_SET, 16, 32, 8), (I.OP_SET, 24, 40, 16), (I.OP_SET, 40, 56, 8)]), (I.IF_EXISTS, [(I.OP_SET, 16, 32, 8)])]
+    assert np.array_equal(I.fold(rules, 64, np.zeros((0, 64), np.uint8), [0, 0], init, f64_fields=[16]), empty.view(np.uint8).reshape(1, 64))
+    assert np.array_equal(I.fold(rules, 64, np.frombuffer(upd, np.uint8).reshape(1, 64), [0, 64], init, f64_fields=[16]), again.view(np.uint8).reshape(1, 64))
+
+
 # ------------------------------------------------------------------ IntBalance
 def test_int_balance_fold():
     """multilanguage-scala-sdk-sample Main.scala:25-30; CQRSModel.applyEvents = foldLeft(eventHandler) (scalasdk/Model.scala:9-13)."""
