@@ -51,3 +51,68 @@ def test_c_oracle_equals_object_model(events, pr):
     if not ack.success:
         first_bad = next(i for i, e in enumerate(events) if e[0] >= 3)
         assert int(row["err_idx"]) == first_bad == nev
+
+
+# ------------------------------------------------------------------ the program interpreter against the C oracle
+# oracle/program_interp.py is the checker of tests/test_gpu_program_fuzz.py; here it is pinned to the C restatement of the
+# reference's handlers on the programs that describe them (surge_b200/programs.py), over arbitrary small logs.
+import struct  # noqa: E402
+import uuid  # noqa: E402
+
+from oracle import program_interp as I  # noqa: E402
+from surge_b200 import programs as P  # noqa: E402
+
+
+def rules_of(prog):
+    return [(int(prog.rules[t].exists_rule), [(int(o.opcode), int(o.dst_off), int(o.src_off), int(o.len)) for o in prog.rules[t].ops[: prog.rules[t].n_ops]])
+            for t in range(prog.n_types)]
+
+
+@settings(max_examples=200, deadline=None)
+@given(st.lists(st.lists(event, max_size=8), min_size=1, max_size=5), st.lists(prior, min_size=5, max_size=5), st.sampled_from(["counter", "ml_counter", "int_balance"]))
+def test_program_interpreter_equals_c_oracle_on_counter_family(segments, priors, which):
+    model, prog = {"counter": (O.MODEL_COUNTER, P.counter_program()), "ml_counter": (O.MODEL_ML_COUNTER, P.ml_counter_program()),
+                   "int_balance": (O.MODEL_INT_BALANCE, P.int_balance_program())}[which]
+    flat = [e for seg in segments for e in seg]
+    rec = F.counter_records([e[0] for e in flat], [e[2] for e in flat], [0] * len(flat), [np.int32(e[1]) for e in flat])
+    off = F.csr_offsets_from_counts([len(s) for s in segments])
+    init = np.zeros(len(segments), dtype=F.COUNTER_STATE)
+    for i, pr in enumerate(priors[: len(segments)]):
+        if pr is not None:
+            init["count"][i], init["version"][i], init["flags"][i] = pr[0], (pr[1] if which != "int_balance" else 0), O.ST_EXISTS
+    want, _, _ = O.fold_packed(model, O.REC_FIXED64, rec, off, init)
+    got = I.fold(rules_of(prog), 16, rec.view(np.uint8).reshape(-1, 64), off, init.view(np.uint8).reshape(-1, 16))
+    assert np.array_equal(got, want.view(np.uint8).reshape(got.shape))
+
+
+f64s = st.sampled_from([0.0, -0.0, float("nan"), 1.0, -1.0, float("inf"), 5e-324, 1e300])
+bank_event = st.one_of(st.tuples(st.just(0), f64s), st.tuples(st.just(1), f64s), st.tuples(st.integers(2, 9), f64s))
+
+
+@settings(max_examples=200, deadline=None)
+@given(st.lists(st.lists(bank_event, max_size=6), min_size=1, max_size=4), st.lists(st.one_of(st.none(), f64s), min_size=4, max_size=4))
+def test_program_interpreter_equals_c_oracle_on_bank_account(segments, priors):
+    """Doubles incl. NaN and signed zeros: the publish rule (== on Double after the `eq` shortcut) must agree."""
+    ids = [str(uuid.UUID(int=77 + i)) for i in range(len(segments))]
+    recs = []
+    for i, seg in enumerate(segments):
+        for k, (t, bal) in enumerate(seg):
+            if t == 0:
+                recs.append(F.bank_created_record(i, k + 1, ids[i], "own", "cd", bal))
+            else:
+                r = bytearray(F.bank_updated_record(i, k + 1, ids[i], bal))
+                struct.pack_into("<I", r, 0, t)
+                recs.append(bytes(r))
+    ev = np.frombuffer(b"".join(recs), np.uint8) if recs else np.zeros(0, np.uint8)
+    off = F.csr_offsets_from_counts([len(s) for s in segments])
+    init = None
+    if any(p is not None for p in priors[: len(segments)]):
+        created = b"".join(F.bank_created_record(i, 1, ids[i], "own", "cd", p if p is not None else 0.0) for i, p in enumerate(priors[: len(segments)]))
+        init, _, _ = O.fold_packed(O.MODEL_BANK_ACCOUNT, O.REC_FIXED64, np.frombuffer(created, np.uint8), np.arange(len(segments) + 1, dtype=np.uint64) * 64)
+        init = init.copy()
+        for i, p in enumerate(priors[: len(segments)]):
+            if p is None:
+                init.view(np.uint8).reshape(-1, 64)[i] = 0
+    want, _, _ = O.fold_packed(O.MODEL_BANK_ACCOUNT, O.REC_FIXED64, ev, off, init)
+    got = I.fold(rules_of(P.bank_account_program()), 64, ev.reshape(-1, 64), off, None if init is None else init.view(np.uint8).reshape(-1, 64), f64_fields=[16])
+    assert np.array_equal(got, want.view(np.uint8).reshape(got.shape))
