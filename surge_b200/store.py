@@ -277,16 +277,23 @@ class GpuReplayKeyValueStore:
 
     def all(self) -> Iterator[Tuple[str, bytes]]:
         with self._lock:
-            keys = sorted(set(self._ingest.keys() if self._ingest is not None else self._keys) | set(self._overlay))
+            # KeyValueStore[Bytes, _] iterates in Bytes order: unsigned lexicographic over the UTF-8 key bytes
+            keys = sorted(set(self._ingest.keys() if self._ingest is not None else self._keys) | set(self._overlay), key=lambda k: k.encode("utf-8"))
         for k in keys:
             v = self.get(k)
             if v is not None:
                 yield k, v
 
     def range(self, frm: str, to: str) -> Iterator[Tuple[str, bytes]]:
+        lo, hi = frm.encode("utf-8"), to.encode("utf-8")
         for k, v in self.all():
-            if frm <= k <= to:
+            if lo <= k.encode("utf-8") <= hi:
                 yield k, v
+
+    def restoreAll(self, records: Iterable[Tuple[Optional[str], bytes]]) -> None:  # noqa: N802
+        """BatchingStateRestoreCallback.restoreAll(Collection[KeyValue[bytes, bytes]]): Kafka Streams hands the restore
+        consumer's polls over in batches; one batch = one GPU fold."""
+        self.restore(records)
 
     def approximateNumEntries(self) -> int:  # noqa: N802
         return sum(1 for _ in self.all())

@@ -125,7 +125,10 @@ def test_store_restores_from_raw_record_batches_and_reports_committed_offsets():
     store.flush()
     assert np.frombuffer(store.get("a"), dtype="<i4").tolist() == [1, 3]   # the multilanguage Counter vector (1,3)
     assert store.committed_offsets([0]) == {0: 5}
-    assert sorted(k for k, _ in store.all()) == ["a", "c"]
+    assert [k for k, _ in store.all()] == ["a", "c"]
+    store.put("é", b"1"); store.put("z", b"2"); store.put("B", b"3")
+    assert [k for k, _ in store.all()] == ["B", "a", "c", "z", "é"]             # Bytes order: by UTF-8 bytes, not by code point collation
+    assert [k for k, _ in store.range("a", "z")] == ["a", "c", "z"]
     with pytest.raises(N.SgrError):
         store.put_event("x:1", bytes(64))
     store.close()
