@@ -15,7 +15,8 @@
  * Conventions
  *   - plain C, no C++/CUDA/torch types cross this boundary;
  *   - every function returns an int32 status (SGR_OK == 0, negative == error class);
- *     the message for the last error on an engine is sgr_last_error(engine);
+ *     the message for the calling thread's last error on an engine is sgr_last_error(engine)
+ *     (errno-style, thread-local: concurrent readers never share a message buffer);
  *   - buffers are caller-allocated and caller-owned in both directions; the engine
  *     never frees caller memory and only sgr_destroy frees engine memory;
  *   - "_device" variants take CUDA device pointers on the engine's device and BORROW

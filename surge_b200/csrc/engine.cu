@@ -26,6 +26,8 @@ using namespace sgr;
 
 namespace {
 thread_local std::string g_create_error;
+thread_local std::string t_last_error;
+thread_local const sgr_engine* t_last_engine = nullptr;
 
 // host snapshot of the state table that sgr_get reads (published after a fold)
 struct Snapshot {
@@ -104,7 +106,6 @@ struct sgr_engine {
   int64_t opt_max_record_bytes = 528;
 
   sgr_stats stats{};
-  std::string last_error;
 
   DistState* dist = nullptr;
   sgr_dist_stats dstats{};
@@ -127,7 +128,9 @@ namespace {
 int32_t fail(sgr_engine* e, int32_t code, const char* fmt, ...) {
   char buf[512];
   va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
-  if (e) e->last_error = buf; else g_create_error = buf;
+  // errno-style: the message belongs to the calling thread (sgr_get runs on a 32-thread pool in the reference; two failing
+  // readers must not race on one string). sgr_last_error(e) answers for the last failure of THIS thread on e.
+  if (e) { t_last_error = buf; t_last_engine = e; } else g_create_error = buf;
   return code;
 }
 #define CUDA_TRY(e, call)                                                                         \
@@ -417,7 +420,10 @@ extern "C" {
 
 int32_t sgr_abi_version(void) { return SGR_ABI_VERSION; }
 
-const char* sgr_last_error(const sgr_engine* e) { return e ? e->last_error.c_str() : g_create_error.c_str(); }
+const char* sgr_last_error(const sgr_engine* e) {
+  if (!e) return g_create_error.c_str();
+  return t_last_engine == e ? t_last_error.c_str() : "";
+}
 
 int32_t sgr_create(const sgr_config* cfg, sgr_engine** out) {
   if (!out) return fail(nullptr, SGR_ERR_INVALID, "out is NULL");
