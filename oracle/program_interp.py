@@ -27,7 +27,7 @@ class _Throw(Exception):
     pass
 
 
-def _handle(rules: Sequence[Rule], user_bytes: int, state: Optional[bytearray], rec: bytes) -> Optional[bytearray]:
+def _handle(rules: Sequence[Rule], user_bytes: int, state: Optional[bytearray], rec: bytes, avail: int = 64) -> Optional[bytearray]:
     """Returns the SAME object when the rule hands the instance back (no field op on an existing state: Scala `current`,
     `aggregate.map(identity)`), a NEW one when it builds or copies a state — object identity stands for JVM `eq`."""
     (etype,) = struct.unpack_from("<I", rec, 0)
@@ -38,6 +38,8 @@ def _handle(rules: Sequence[Rule], user_bytes: int, state: Optional[bytearray], 
         raise _Throw()
     if exists_rule == TOMBSTONE:
         return None
+    if any(src + ln > avail for _, _, src, ln in ops):
+        raise _Throw()                      # the record is too short for this event class (variable records)
     if exists_rule == IF_EXISTS:
         if state is None:
             return None
@@ -129,3 +131,49 @@ def fold_arrival_order(rules: Sequence[Rule], state_bytes: int, records: np.ndar
         seg = recs[idx]
         table[int(a)] = fold(rules, state_bytes, seg, [0, 64 * len(seg)], table[int(a):int(a) + 1], f64_fields)[0]
     return table
+
+
+MAX_VAR_RECORD = 16 + 512   # include/sgr.h: a variable record is capped at 16 + 512 bytes unless "max_record_bytes" is raised
+
+
+def fold_var(rules: Sequence[Rule], state_bytes: int, log: np.ndarray, seg_offsets: Sequence[int], initial: Optional[np.ndarray] = None,
+             f64_fields: Sequence[int] = ()) -> np.ndarray:
+    """Variable records (SGR_REC_VAR16): 16-byte header {type, seq, payload_len, agg} + payload padded to 16 bytes. A record
+    that does not fit its segment, or is longer than the format allows, or is too short for the ops of its event class, is a
+    malformed event: the handler throws at that record. (Do not feed records between MAX_VAR_RECORD and 64 KiB: how
+    far past the cap a kernel still parses is an implementation detail the tests stay away from.)"""
+    user = state_bytes - 8
+    buf = np.ascontiguousarray(log).view(np.uint8).reshape(-1).tobytes()
+    n_agg = len(seg_offsets) - 1
+    out = np.zeros((n_agg, state_bytes), dtype=np.uint8)
+    for i in range(n_agg):
+        old: Optional[bytearray] = None
+        if initial is not None:
+            row = np.ascontiguousarray(initial).view(np.uint8).reshape(-1, state_bytes)[i]
+            if struct.unpack_from("<I", row.tobytes(), user)[0] & ST_EXISTS:
+                old = bytearray(row[:user].tobytes())
+        cur = old
+        pos, end, k, threw_at = int(seg_offsets[i]), int(seg_offsets[i + 1]), 0, -1
+        while pos < end:
+            try:
+                if end - pos < 16:
+                    raise _Throw()
+                plen = struct.unpack_from("<I", buf, pos + 8)[0]
+                rlen = 16 + ((plen + 15) // 16) * 16
+                if 16 + plen > MAX_VAR_RECORD or rlen > end - pos:
+                    raise _Throw()
+                cur = _handle(rules, user, cur, buf[pos:pos + rlen], avail=16 + plen)
+            except _Throw:
+                threw_at = k
+                break
+            pos += rlen
+            k += 1
+        if threw_at >= 0:
+            final, flags, err = old, ST_ERROR, threw_at
+        else:
+            final, flags, err = cur, (0 if _equal(old, cur, f64_fields) else ST_CHANGED), 0
+        if final is not None:
+            out[i, :user] = np.frombuffer(bytes(final), dtype=np.uint8)
+            flags |= ST_EXISTS
+        out[i, user:] = np.frombuffer(struct.pack("<II", flags, err), dtype=np.uint8)
+    return out

@@ -136,3 +136,88 @@ def interleave(rng, aggs):
     t = rng.random(len(aggs))
     times = t[np.lexsort((t, aggs))]     # within each aggregate the arrival times ascend with the log position
     return np.argsort(times, kind="stable")
+
+
+# ------------------------------------------------------------------ variable records (SGR_REC_VAR16)
+def draw_var_program(rng):
+    """Like draw_program, with payload reads up to 80 bytes into the record and 16/32-byte states more likely (the
+    record-parallel variable-record kernel takes 16-byte class-0 programs, everything else the lane-sequential kernel)."""
+    state_bytes = int(rng.choice([16, 32, 64], p=[0.6, 0.25, 0.15]))
+    user = state_bytes - 8
+    pool = [I.MATERIALISE, I.CREATE, I.TOMBSTONE, I.THROW] if rng.random() < 0.7 else [I.IF_EXISTS, I.CREATE, I.TOMBSTONE, I.THROW]
+    rules = []
+    for t in range(int(rng.integers(1, 6))):
+        ex = int(rng.choice(pool, p=[0.6, 0.2, 0.1, 0.1])) if t else int(I.CREATE if pool[0] == I.IF_EXISTS else pool[int(rng.integers(0, 2))])
+        ops = []
+        for _ in range(int(rng.integers(0, 4))):
+            opc = int(rng.choice([I.OP_SET, I.OP_ADD_I32, I.OP_SUB_I32]))
+            ln = 4 if opc != I.OP_SET else min(int(rng.choice([4, 8])), user)
+            dst = 4 * int(rng.integers(0, (user - ln) // 4 + 1))
+            src = 4 if rng.random() < 0.2 and ln == 4 else 16 + 4 * int(rng.integers(0, (80 - ln) // 4 + 1))
+            ops.append((opc, dst, src, ln))
+        rules.append((ex, ops))
+    return state_bytes, rules
+
+
+def draw_var_log(rng, n_types, n_agg, long_len):
+    counts = rng.integers(0, 10, size=n_agg)
+    counts[rng.integers(0, n_agg)] = long_len
+    counts[rng.integers(0, n_agg, size=n_agg // 10)] = 0
+    n = int(counts.sum())
+    plen = rng.integers(80, 513, size=n)
+    short = rng.random(n) < 0.03
+    plen[short] = rng.integers(0, 80, size=int(short.sum()))          # too short for some event classes: those throw
+    rlen = 16 + ((plen + 15) // 16) * 16
+    rec_off = np.zeros(n + 1, dtype=np.uint64)
+    np.cumsum(rlen, out=rec_off[1:])
+    buf = rng.integers(0, 256, size=int(rec_off[-1]), dtype=np.uint8)
+    types = rng.integers(0, n_types, size=n).astype(np.uint32)
+    types[rng.random(n) < 0.004] = n_types
+    aggs = np.repeat(np.arange(n_agg, dtype=np.uint32), counts)
+    hdr = np.zeros((n, 4), dtype=np.uint32)
+    hdr[:, 0], hdr[:, 1], hdr[:, 2], hdr[:, 3] = types, np.arange(1, n + 1, dtype=np.uint32), plen.astype(np.uint32), aggs
+    hb = hdr.view(np.uint8).reshape(n, 16)
+    starts = rec_off[:-1].astype(np.int64)
+    for j in range(16):
+        buf[starts + j] = hb[:, j]
+    first = np.zeros(n_agg + 1, dtype=np.int64)
+    np.cumsum(counts, out=first[1:])
+    seg = rec_off[first].astype(np.uint64)
+    # malformed records: a payload length that runs past the end of its segment (last record of a few segments), and one absurd one
+    for a in rng.integers(0, n_agg, size=4):
+        if counts[a]:
+            j = int(first[a + 1] - 1)
+            buf[int(rec_off[j]) + 8:int(rec_off[j]) + 12] = np.frombuffer(np.uint32(int(plen[j]) + 64).tobytes(), np.uint8)
+    big = int(rng.integers(0, n))
+    buf[int(rec_off[big]) + 8:int(rec_off[big]) + 12] = np.frombuffer(np.uint32(0x7FFFFFF0).tobytes(), np.uint8)
+    return buf, seg, rec_off
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_random_program_variable_records(seed):
+    rng = np.random.default_rng(7000 + seed)
+    state_bytes, rules = draw_var_program(rng)
+    prog = P.make_program(state_bytes, N.REC_VAR16, rules)
+    n_agg = 300
+    buf, seg, rec_off = draw_var_log(rng, len(rules), n_agg, 900)
+    want = I.fold_var(rules, state_bytes, buf, seg)
+    what = f"seed {seed} state_bytes {state_bytes} rules {rules}"
+    with ReplayEngine(0) as e:
+        e.register_program(prog)
+        for kernel in (0, 1):
+            e.set_option("kernel", kernel)
+            e.set_initial_states(None)
+            e.load_events(buf, seg)
+            e.fold()
+            same(e.export_states(), want, f"{what} kernel {kernel}")
+        e.set_option("kernel", 0)
+        e.set_initial_states(None)
+        e.load_events_indexed(buf, seg, rec_off)       # with the record directory: the record-parallel kernel where it applies
+        e.fold()
+        same(e.export_states(), want, f"{what} with directory")
+        buf2, seg2, rec_off2 = draw_var_log(rng, len(rules), n_agg, 200)
+        want2 = I.fold_var(rules, state_bytes, buf2, seg2, initial=want)
+        e.set_initial_states(want)
+        e.load_events_indexed(buf2, seg2, rec_off2)
+        e.fold()
+        same(e.export_states(), want2, f"{what} with prior states")
