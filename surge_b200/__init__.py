@@ -5,6 +5,7 @@ Only what the hot path needs lives here:
   native.py    ctypes binding of the C ABI (fails loudly when the CUDA library is missing)
   formats.py   packed record / state layouts (the binary SurgeAggregateFormatting)
   programs.py  declarative fold programs for the reference's sample models
+  dsl.py       text front-end that compiles a state layout + event blocks to a fold program
   engine.py    ReplayEngine: Pythonic wrapper over one sgr_engine
   ingest.py    Kafka RecordBatch bytes -> packed records (native decode) + per-partition offsets for the lag gate
   store.py     host-side mirror of the reference's plugin / state-store interfaces
