@@ -347,6 +347,9 @@ int32_t sgr_ingest_record_batches(sgr_ingest* g, int32_t partition, const void* 
  * identical to n single calls. All or nothing: one malformed fetch and nothing is applied. stats: n entries or NULL. */
 int32_t sgr_ingest_record_batches_mt(sgr_ingest* g, uint32_t n, const int32_t* partitions, const void* const* datas,
                                      const uint64_t* nbytes, uint32_t threads, sgr_ingest_stats* stats);
+/* Where the pending log lives (default malloc/free). sgr_fold_ingested installs page-locked host memory so that the copy of
+ * a poll to the device is one DMA at full PCIe rate; content already pending is carried over. */
+int32_t sgr_ingest_set_allocator(sgr_ingest* g, void* (*alloc_fn)(size_t), void (*free_fn)(void*));
 /* the pending packed records (borrowed until the next ingest call) and the id dictionary (key i = dense index i) */
 int32_t sgr_ingest_pending(sgr_ingest* g, const void** records, uint64_t* n_records);
 int32_t sgr_ingest_keys(sgr_ingest* g, const uint8_t** keys, const uint32_t** key_offsets, uint64_t* n_keys);

@@ -800,8 +800,14 @@ int32_t sgr_grow_states(sgr_engine* e, uint64_t n_agg) {
   return SGR_OK;
 }
 
+static void* pinned_alloc(size_t n) { void* p = nullptr; return cudaHostAlloc(&p, n, cudaHostAllocPortable) == cudaSuccess ? p : nullptr; }
+static void pinned_free(void* p) { cudaFreeHost(p); }
+
 int32_t sgr_fold_ingested(sgr_engine* e, sgr_ingest* g) {
   if (!e || !g) return fail(e, SGR_ERR_INVALID, "null argument");
+  { int32_t rc0 = use_device(e); if (rc0) return rc0; }
+  // from now on the ingest decodes straight into page-locked memory (what is pending right now is moved once)
+  if (sgr_ingest_set_allocator(g, pinned_alloc, pinned_free)) return fail(e, SGR_ERR_OOM, "ingest: %s", sgr_ingest_last_error(g));
   const void* recs = nullptr; uint64_t n_records = 0;
   const uint8_t* keys = nullptr; const uint32_t* key_offsets = nullptr; uint64_t n_keys = 0;
   if (sgr_ingest_pending(g, &recs, &n_records) || sgr_ingest_keys(g, &keys, &key_offsets, &n_keys))

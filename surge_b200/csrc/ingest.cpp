@@ -304,14 +304,21 @@ class KeyDict {
 // append-only byte buffer that grows without zero-filling (the pending log is written exactly once per byte)
 struct RawBuf {
   uint8_t* p = nullptr; size_t n = 0, cap = 0;
-  ~RawBuf() { free(p); }
+  void* (*alloc_fn)(size_t) = malloc;     // the engine swaps in page-locked memory so the H2D copy of a poll runs at DMA speed
+  void (*free_fn)(void*) = free;
+  ~RawBuf() { if (p) free_fn(p); }
   bool grow_to(size_t need) {
     if (need <= cap) return true;
     size_t c = cap ? cap : (1u << 16);
     while (c < need) c *= 2;
-    uint8_t* q = (uint8_t*)realloc(p, c);
+    return move_to(c, alloc_fn, free_fn);
+  }
+  bool move_to(size_t c, void* (*a)(size_t), void (*f)(void*)) {
+    uint8_t* q = (uint8_t*)a(c);
     if (!q) return false;
-    p = q; cap = c;
+    if (n) memcpy(q, p, n);
+    if (p) free_fn(p);
+    p = q; cap = c; alloc_fn = a; free_fn = f;
     return true;
   }
 };
@@ -630,6 +637,14 @@ int32_t sgr_ingest_record_batches(sgr_ingest* g, int32_t partition, const void* 
   if (!g || (!data && nbytes)) return ifail(g, SGR_ERR_INVALID, "null argument");
   const void* d[1] = {data};
   return sgr_ingest_record_batches_mt(g, 1, &partition, d, &nbytes, 1, stats);
+}
+
+int32_t sgr_ingest_set_allocator(sgr_ingest* g, void* (*alloc_fn)(size_t), void (*free_fn)(void*)) {
+  if (!g || !alloc_fn || !free_fn) return ifail(g, SGR_ERR_INVALID, "null argument");
+  if (g->pending.alloc_fn == alloc_fn && g->pending.free_fn == free_fn) return SGR_OK;
+  const size_t c = g->pending.cap ? g->pending.cap : (1u << 16);
+  if (!g->pending.move_to(c, alloc_fn, free_fn)) return ifail(g, SGR_ERR_OOM, "pending log of %zu bytes", c);
+  return SGR_OK;
 }
 
 int32_t sgr_ingest_pending(sgr_ingest* g, const void** records, uint64_t* n_records) {

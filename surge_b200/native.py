@@ -125,6 +125,7 @@ ABI = [
     ("sgr_ingest_set_aborted", C.c_int32, [_P, C.c_int32, _P, _P, C.c_uint64]),
     ("sgr_ingest_record_batches", C.c_int32, [_P, C.c_int32, _P, C.c_uint64, C.POINTER(sgr_ingest_stats)]),
     ("sgr_ingest_record_batches_mt", C.c_int32, [_P, C.c_uint32, _P, _P, _P, C.c_uint32, _P]),
+    ("sgr_ingest_set_allocator", C.c_int32, [_P, _P, _P]),
     ("sgr_ingest_pending", C.c_int32, [_P, C.POINTER(_P), C.POINTER(C.c_uint64)]),
     ("sgr_ingest_keys", C.c_int32, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(C.c_uint64)]),
     ("sgr_ingest_mark_folded", C.c_int32, [_P]),

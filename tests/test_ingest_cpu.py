@@ -342,3 +342,36 @@ def test_multi_fetch_call_is_all_or_nothing():
     assert ing.offsets(0) == (0, 0) and ing.offsets(2) == (0, 0)
     st = ing.record_batches_mt([(0, good0), (1, good1), (2, good1)], threads=3)
     assert sum(s["n_records"] for s in st) == len(ing.pending()) - 1
+
+
+def test_pending_log_moves_to_a_caller_supplied_allocator(lib):
+    """sgr_fold_ingested installs page-locked memory this way; here: counting wrappers around libc malloc/free."""
+    libc = C.CDLL(None)
+    libc.malloc.restype, libc.malloc.argtypes = C.c_void_p, [C.c_size_t]
+    libc.free.restype, libc.free.argtypes = None, [C.c_void_p]
+    calls = {"alloc": 0, "free": 0}
+
+    @C.CFUNCTYPE(C.c_void_p, C.c_size_t)
+    def my_alloc(n):
+        calls["alloc"] += 1
+        return libc.malloc(n)
+
+    @C.CFUNCTYPE(None, C.c_void_p)
+    def my_free(p):
+        calls["free"] += 1
+        libc.free(p)
+
+    rng = np.random.default_rng(5)
+    ing = Ingest()
+    buf, end = _batch_stream(rng, 5, 30, "none")
+    ing.record_batches(0, buf)
+    before = ing.pending()
+    assert lib.sgr_ingest_set_allocator(ing.handle, my_alloc, my_free) == 0
+    assert calls == {"alloc": 1, "free": 0} and np.array_equal(ing.pending(), before)      # content carried over
+    assert lib.sgr_ingest_set_allocator(ing.handle, my_alloc, my_free) == 0 and calls["alloc"] == 1   # idempotent
+    big, _ = _batch_stream(rng, 200, 30, "lz4", end)       # forces growth through the new allocator
+    ing.record_batches(0, big)
+    assert calls["alloc"] >= 2 and calls["free"] == calls["alloc"] - 1
+    assert np.array_equal(ing.pending()[: len(before)], before)
+    ing.close()
+    assert calls["free"] == calls["alloc"]
