@@ -98,6 +98,7 @@ JNIEXPORT jlong JNICALL Java_surge_gpu_Native_00024_ingestRecordBatches(JNIEnv* 
   return (jlong)st.n_records;
 }
 JNIEXPORT jint JNICALL Java_surge_gpu_Native_00024_foldIngested(JNIEnv* env, jobject o, jlong h, jlong g) { return sgr_fold_ingested(H(h), G(g)); }
+JNIEXPORT jint JNICALL Java_surge_gpu_Native_00024_growStates(JNIEnv* env, jobject o, jlong h, jlong n_agg) { return sgr_grow_states(H(h), (uint64_t)n_agg); }
 JNIEXPORT jlongArray JNICALL Java_surge_gpu_Native_00024_ingestOffsets(JNIEnv* env, jobject o, jlong g, jint partition) {
   int64_t v[2] = {0, 0};
   sgr_ingest_offsets(G(g), partition, &v[0], &v[1]);

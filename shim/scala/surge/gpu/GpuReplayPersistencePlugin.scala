@@ -93,22 +93,31 @@ class GpuReplayKeyValueStore(storeName: String) extends KeyValueStore[Bytes, Arr
     if (keyIndex.size() != loadedKeys) loadKeyTable() // new ids inside the current capacity
   }
 
-  /** (Re)build the live table with room for the keys seen so far: export, enlarge, sgr_set_initial_states, sgr_load_keys
-   *  (the executable twin is GpuReplayKeyValueStore.flush in surge_b200/store.py). */
+  /** Make room for the keys seen so far: the table is resized on the device, content kept, new slots None (sgr_grow_states). */
   private def growTable(): Unit = {
-    val stateBytes = GpuFoldPrograms.current.order(ByteOrder.LITTLE_ENDIAN).getInt(0) // sgr_fold_program.state_bytes
     val newCapacity = math.max(2L * keyIndex.size(), 1024L)
-    val table = ByteBuffer.allocateDirect((newCapacity * stateBytes).toInt) // zero-filled: None everywhere
-    if (folded) {
-      val old = ByteBuffer.allocateDirect((capacity * stateBytes).toInt)
-      check(Native.exportStates(handle, old, null))
-      table.put(old); table.rewind()
-    }
-    check(Native.setInitialStates(handle, table, newCapacity))
+    check(Native.growStates(handle, newCapacity))
     capacity = newCapacity
     folded = true
     loadKeyTable()
   }
+
+  // ---- raw broker bytes (a consumer that hands over fetch responses undecoded): decode natively, fold, report offsets.
+  // A store is fed either through putEvent or through restoreRecordBatches, not both (each side keeps its own id dictionary).
+  private lazy val ingest: Long = Native.ingestCreate()
+
+  /** bytes of one fetch response for `partition` + its aborted transactions; decoded as a read_committed consumer would
+   *  (SurgeStateStoreConsumer.scala:38). Returns the number of event records appended to the pending batch. */
+  def restoreRecordBatches(partition: Int, fetch: ByteBuffer, abortedProducerIds: Array[Long], abortedFirstOffsets: Array[Long]): Long = {
+    if (abortedProducerIds.nonEmpty) Native.ingestSetAborted(ingest, partition, abortedProducerIds, abortedFirstOffsets)
+    Native.ingestRecordBatches(ingest, partition, fetch, fetch.remaining().toLong)
+  }
+
+  /** fold what restoreRecordBatches decoded; afterwards committedOffset(partition) is what the consumer acting for this
+   *  store commits for the streams application id, so that the producer's lag check reaches zero exactly when get() can
+   *  serve the state (KafkaProducerActorImpl.scala:684-708, KafkaAdminClient.scala:44-56). */
+  def flushRecordBatches(): Unit = { check(Native.foldIngested(handle, ingest)); folded = true }
+  def committedOffset(partition: Int): Long = Native.ingestOffsets(ingest, partition)(1)
 
   /** key table for sgr_get: ids in slot order, unused slots get unreachable placeholder keys */
   private def loadKeyTable(): Unit = {

@@ -34,6 +34,7 @@ object Native {
   /** decodes one fetch response's bytes for `partition`; returns the number of packed records appended; throws on malformed input */
   @native def ingestRecordBatches(ingest: Long, partition: Int, data: ByteBuffer, nbytes: Long): Long // sgr_ingest_record_batches
   @native def foldIngested(handle: Long, ingest: Long): Int                        // sgr_fold_ingested
+  @native def growStates(handle: Long, nAgg: Long): Int                            // sgr_grow_states
   /** Array(decodedNext, foldedNext) */
   @native def ingestOffsets(ingest: Long, partition: Int): Array[Long]             // sgr_ingest_offsets
 }
