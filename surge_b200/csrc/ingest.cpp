@@ -22,6 +22,10 @@
 
 #include <algorithm>
 #include <atomic>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
+#include <queue>
 #include <chrono>
 #include <thread>
 #include <map>
@@ -246,59 +250,148 @@ inline uint64_t hash_bytes(const uint8_t* k, uint32_t len) {   // 8 bytes at a t
   return h;
 }
 
-class KeyDict {
+// 64 independent open-addressing tables (shard = top 6 hash bits) over ONE append-only id arena. A decode call probes the
+// shards in parallel (each shard belongs to one worker), new ids get a provisional slot, and dense indices are then handed
+// out serially in arrival order — so the index of an id is its first-seen rank no matter how many threads decoded.
+class ShardedDict {
  public:
-  struct Slot { uint32_t tag; uint32_t idx; uint64_t off_len; };   // tag = low 32 hash bits (also the home position, so growing
-                                                                   // never re-reads keys); off_len = byte offset << 24 | length; idx == kEmpty: free
+  static constexpr int kShards = 64;
   static constexpr uint32_t kEmpty = 0xFFFFFFFFu;
-  KeyDict() { offs_.push_back(0); }
-  void reserve_for(uint64_t extra) { while ((n_ + extra + 1) * 2 > slots_.size()) grow(); }   // at most 2^31 ids (u32 index, tag-addressed)
-  void prefetch_slot(uint64_t h) const { if (!slots_.empty()) __builtin_prefetch(&slots_[(uint32_t)h & (slots_.size() - 1)]); }
-  void prefetch_key(uint64_t h) const {   // the slot is expected in cache by now: pull the candidate's key bytes
-    if (slots_.empty()) return;
-    const Slot& sl = slots_[(uint32_t)h & (slots_.size() - 1)];
-    if (sl.idx != kEmpty) __builtin_prefetch(bytes_.data() + (sl.off_len >> 24));
+  static constexpr uint32_t kProv = 0x80000000u;   // idx bit 31: provisional, low bits = position in the owner's NewKey list
+  struct Slot { uint32_t tag; uint32_t idx; uint64_t off_len; };   // tag = low 32 hash bits (also the home position, so growing
+                                                                   // never re-reads keys); off_len = arena offset << 24 | length
+  struct NewKey { uint32_t fetch, rec; const uint8_t* bytes; uint32_t len, shard, slot_pos, final_idx; };
+  ShardedDict() { offs_.push_back(0); }
+  static int shard_of(uint64_t h) { return (int)(h >> 58); }
+
+  void reserve_shard(int s, uint64_t extra) { while ((count_[s] + extra + 1) * 2 > slots_[s].size()) grow(s); }
+  void prefetch_slot(uint64_t h) const { const auto& t = slots_[shard_of(h)]; if (!t.empty()) __builtin_prefetch(&t[(uint32_t)h & (t.size() - 1)]); }
+  void prefetch_key(uint64_t h) const {   // the slot is expected in cache by now: pull the candidate's id bytes
+    const auto& t = slots_[shard_of(h)];
+    if (t.empty()) return;
+    const Slot& sl = t[(uint32_t)h & (t.size() - 1)];
+    if (sl.idx != kEmpty && !(sl.idx & kProv)) __builtin_prefetch(bytes_.data() + (sl.off_len >> 24));
   }
-  // call reserve_for() first: intern never grows the table itself
-  uint32_t intern(const uint8_t* k, uint32_t len, uint64_t h, bool* fresh) {
-    const uint64_t mask = slots_.size() - 1;
+  // Owner thread of the shard only; reserve_shard() first. Returns the dense index, or kProv | position in `news`.
+  uint32_t probe(const uint8_t* k, uint32_t len, uint64_t h, uint32_t fetch, uint32_t rec, std::vector<NewKey>* news) {
+    const int s = shard_of(h);
+    std::vector<Slot>& t = slots_[s];
+    const uint64_t mask = t.size() - 1;
     const uint32_t tag = (uint32_t)h;
     uint64_t at = tag & mask;
     for (;;) {
-      Slot& sl = slots_[at];
+      Slot& sl = t[at];
       if (sl.idx == kEmpty) {
-        sl.tag = tag; sl.idx = (uint32_t)n_; sl.off_len = ((uint64_t)bytes_.size() << 24) | len;
-        bytes_.insert(bytes_.end(), k, k + len);
-        offs_.push_back((uint32_t)bytes_.size());
-        *fresh = true;
-        return (uint32_t)n_++;
+        sl.tag = tag; sl.idx = kProv | (uint32_t)news->size(); sl.off_len = 0;
+        news->push_back(NewKey{fetch, rec, k, len, (uint32_t)s, (uint32_t)at, 0u});
+        ++count_[s];
+        return sl.idx;
       }
-      if (sl.tag == tag && (uint32_t)(sl.off_len & 0xFFFFFF) == len && (len == 0 || memcmp(bytes_.data() + (sl.off_len >> 24), k, len) == 0)) {
-        *fresh = false; return sl.idx;
+      if (sl.tag == tag) {
+        if (sl.idx & kProv) {
+          const NewKey& nk = (*news)[sl.idx & ~kProv];
+          if (nk.len == len && (len == 0 || memcmp(nk.bytes, k, len) == 0)) return sl.idx;
+        } else if ((uint32_t)(sl.off_len & 0xFFFFFF) == len && (len == 0 || memcmp(bytes_.data() + (sl.off_len >> 24), k, len) == 0)) {
+          return sl.idx;
+        }
       }
       at = (at + 1) & mask;
     }
+  }
+  // serial, in arrival order: the id gets the next dense index and its bytes move into the arena
+  void admit(NewKey* nk) {
+    nk->final_idx = (uint32_t)n_++;
+    bytes_.insert(bytes_.end(), nk->bytes, nk->bytes + nk->len);
+    offs_.push_back((uint32_t)bytes_.size());
+  }
+  // owner thread of the shard: the provisional slot becomes a final one
+  void publish(const NewKey& nk) {
+    Slot& sl = slots_[nk.shard][nk.slot_pos];
+    sl.idx = nk.final_idx;
+    sl.off_len = ((uint64_t)offs_[nk.final_idx] << 24) | nk.len;
   }
   uint64_t size() const { return n_; }
   const uint8_t* bytes() const { return bytes_.data(); }
   const uint32_t* offsets() const { return offs_.data(); }
 
  private:
-  void grow() {
-    const uint64_t cap = slots_.empty() ? 1024 : slots_.size() * 2;
+  void grow(int sh) {
+    std::vector<Slot>& t = slots_[sh];
+    const uint64_t cap = t.empty() ? 256 : t.size() * 2;
     std::vector<Slot> s(cap, Slot{0, kEmpty, 0});
-    for (const Slot& sl : slots_) {
+    for (const Slot& sl : t) {
       if (sl.idx == kEmpty) continue;
       uint64_t at = sl.tag & (cap - 1);
       while (s[at].idx != kEmpty) at = (at + 1) & (cap - 1);
       s[at] = sl;
     }
-    slots_.swap(s);
+    t.swap(s);
   }
   std::vector<uint8_t> bytes_;
   std::vector<uint32_t> offs_;
-  std::vector<Slot> slots_;
+  std::vector<Slot> slots_[kShards];
+  uint64_t count_[kShards] = {0};
   uint64_t n_ = 0;
+};
+
+// a few long-lived workers: a poll is decoded in ~10 ms, spawning threads for each of its three parallel phases would show
+class WorkerPool {
+ public:
+  ~WorkerPool() { stop(); }
+  template <typename F>
+  void run(uint32_t n_tasks, uint32_t n_thr, F&& task) {
+    if (n_thr > n_tasks) n_thr = n_tasks;
+    if (n_thr <= 1) { for (uint32_t i = 0; i < n_tasks; ++i) task(i); return; }
+    ensure(n_thr - 1);
+    std::function<void(uint32_t)> fn = std::ref(task);
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      fn_ = &fn; n_tasks_ = n_tasks; next_.store(0); active_ = n_thr - 1; want_ = n_thr - 1; ++epoch_;
+    }
+    cv_.notify_all();
+    for (uint32_t c; (c = next_.fetch_add(1)) < n_tasks;) task(c);      // the caller works too
+    std::unique_lock<std::mutex> lk(mu_);
+    done_cv_.wait(lk, [&] { return active_ == 0; });
+    fn_ = nullptr;
+  }
+
+ private:
+  void ensure(uint32_t n) {
+    while (threads_.size() < n) {
+      const uint32_t id = (uint32_t)threads_.size();
+      threads_.emplace_back([this, id] { loop(id); });
+    }
+  }
+  void loop(uint32_t id) {
+    uint64_t seen = 0;
+    for (;;) {
+      std::function<void(uint32_t)>* fn;
+      uint32_t n_tasks;
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&] { return quit_ || (epoch_ != seen && id < want_); });
+        if (quit_) return;
+        seen = epoch_; fn = fn_; n_tasks = n_tasks_;
+      }
+      for (uint32_t c; (c = next_.fetch_add(1)) < n_tasks;) (*fn)(c);
+      std::lock_guard<std::mutex> lk(mu_);
+      if (--active_ == 0) done_cv_.notify_one();
+    }
+  }
+  void stop() {
+    { std::lock_guard<std::mutex> lk(mu_); quit_ = true; }
+    cv_.notify_all();
+    for (auto& t : threads_) t.join();
+    threads_.clear();
+  }
+  std::mutex mu_;
+  std::condition_variable cv_, done_cv_;
+  std::vector<std::thread> threads_;
+  std::function<void(uint32_t)>* fn_ = nullptr;
+  std::atomic<uint32_t> next_{0};
+  uint32_t n_tasks_ = 0, active_ = 0, want_ = 0;
+  uint64_t epoch_ = 0;
+  bool quit_ = false;
 };
 
 // append-only byte buffer that grows without zero-filling (the pending log is written exactly once per byte)
@@ -336,20 +429,25 @@ struct Staged {
   std::vector<uint8_t> recs;      // 64-byte records, agg field still zero
   std::vector<KeyRef> keys;       // one per record, into `arena`
   std::vector<uint8_t> arena;     // aggregate-id bytes (copied: the decompression scratch is reused per batch)
-  std::vector<uint32_t> idx;      // dense index of each record's aggregate (phase 2a)
+  std::vector<uint32_t> idx;      // dense index of each record's aggregate, or kProv | position in its owner's NewKey list
+  std::vector<uint8_t> shard;     // dictionary shard of each record's id
+  uint32_t shard_count[ShardedDict::kShards];
   std::vector<uint8_t> scratch;
   PartitionState ps;              // the partition's state after this fetch (committed in phase 2)
   sgr_ingest_stats st{};
   int32_t rc = SGR_OK;
   std::string err;
-  void reset() { recs.clear(); keys.clear(); arena.clear(); idx.clear(); scratch.clear(); st = sgr_ingest_stats{}; rc = SGR_OK; err.clear(); }
+  void reset() { recs.clear(); keys.clear(); arena.clear(); idx.clear(); shard.clear(); memset(shard_count, 0, sizeof shard_count); scratch.clear(); st = sgr_ingest_stats{}; rc = SGR_OK; err.clear(); }
 };
 
 }  // namespace
 
 struct sgr_ingest {
   std::string last_error;
-  KeyDict dict;
+  ShardedDict dict;
+  WorkerPool workers;
+  std::vector<std::vector<ShardedDict::NewKey>> news;   // per worker, reused across calls
+  std::vector<std::vector<uint32_t>> mine;               // per worker: the record positions of the fetch it is probing
   RawBuf pending;                   // packed 64-byte records, arrival order
   std::vector<uint8_t> scratch;     // decompressed records section of the batch being decoded
   std::map<int32_t, PartitionState> parts;
@@ -509,7 +607,10 @@ int32_t decode_fetch(int32_t partition, const uint8_t* buf, uint64_t nbytes, Sta
         uint32_t id_len = 0;
         while (id_len < (uint32_t)key_len && key[id_len] != ':') ++id_len;   // PartitionStringUpToColon (KafkaPartitioner.scala:38-42)
         if (id_len >= (1u << 24)) return sfail(o, SGR_ERR_INVALID, "partition %d offset %lld: aggregate id of %u bytes", partition, (long long)offset, id_len);
-        o->keys.push_back(KeyRef{(uint32_t)(ar - o->arena.data()), id_len, hash_bytes(key, id_len)});
+        const uint64_t kh = hash_bytes(key, id_len);
+        o->keys.push_back(KeyRef{(uint32_t)(ar - o->arena.data()), id_len, kh});
+        o->shard.push_back((uint8_t)ShardedDict::shard_of(kh));
+        ++o->shard_count[ShardedDict::shard_of(kh)];
         memcpy(ar, key, id_len); ar += id_len;
         memcpy(rec, val, 8);                    // u32 type, u32 seq (little endian, as the packer wrote them)
         memcpy(rec + 16, val + 8, (size_t)val_len - 8);   // the rest of the slot is zero from resize(): agg, payload tail
@@ -529,31 +630,68 @@ int32_t decode_fetch(int32_t partition, const uint8_t* buf, uint64_t nbytes, Sta
   return SGR_OK;
 }
 
-// ---- phase 2a (caller's thread): ids -> dense indices, in arrival order
-void intern_fetch(sgr_ingest* g, Staged* o) {
-  const size_t n = o->keys.size();
-  g->dict.reserve_for(n);
-  o->idx.resize(n);
-  const uint8_t* arena = o->arena.data();
-  // the dictionary of a big topic does not fit any cache: run the probe as a software pipeline — slot prefetched 16
-  // records ahead, the candidate's key bytes 8 ahead — so that the misses of neighbouring records overlap
-  constexpr size_t kSlotAhead = 16, kKeyAhead = 8;
-  for (size_t i = 0; i < std::min(n, kSlotAhead); ++i) g->dict.prefetch_slot(o->keys[i].hash);
-  for (size_t i = 0; i < n; ++i) {
-    if (i + kSlotAhead < n) g->dict.prefetch_slot(o->keys[i + kSlotAhead].hash);
-    if (i + kKeyAhead < n) g->dict.prefetch_key(o->keys[i + kKeyAhead].hash);
-    const KeyRef& k = o->keys[i];
-    bool fresh;
-    o->idx[i] = g->dict.intern(arena + k.off, k.len, k.hash, &fresh);
-    o->st.n_new_keys += fresh ? 1 : 0;
+// ---- phase 2a (worker t of n_workers; owns the shards s with s % n_workers == t): probe every id of those shards, in
+// arrival order. Known ids get their dense index at once; new ones a provisional slot and an entry in the worker's list.
+void probe_shards(sgr_ingest* g, std::vector<Staged>& staged, uint32_t n, uint32_t t, uint32_t n_workers, std::vector<uint32_t>* mine) {
+  std::vector<ShardedDict::NewKey>& news = g->news[t];
+  news.clear();
+  uint8_t owner[ShardedDict::kShards];
+  for (int s = 0; s < ShardedDict::kShards; ++s) owner[s] = (uint8_t)(s % (int)n_workers);
+  for (int s = (int)t; s < ShardedDict::kShards; s += (int)n_workers) {
+    uint64_t extra = 0;
+    for (uint32_t i = 0; i < n; ++i) extra += staged[i].shard_count[s];
+    g->dict.reserve_shard(s, extra);
+  }
+  for (uint32_t i = 0; i < n; ++i) {
+    Staged& o = staged[i];
+    const size_t cnt = o.keys.size();
+    const uint8_t* sh = o.shard.data();
+    mine->clear();
+    if (n_workers == 1) { mine->resize(cnt); for (size_t r = 0; r < cnt; ++r) (*mine)[r] = (uint32_t)r; }
+    else for (size_t r = 0; r < cnt; ++r) if (owner[sh[r]] == t) mine->push_back((uint32_t)r);
+    const uint8_t* arena = o.arena.data();
+    const size_t m = mine->size();
+    // the dictionary of a big topic does not fit any cache: run the probe as a software pipeline — slot prefetched 16
+    // ids ahead, the candidate's id bytes 8 ahead — so that the misses of neighbouring records overlap
+    constexpr size_t kSlotAhead = 16, kKeyAhead = 8;
+    for (size_t j = 0; j < std::min(m, kSlotAhead); ++j) g->dict.prefetch_slot(o.keys[(*mine)[j]].hash);
+    for (size_t j = 0; j < m; ++j) {
+      if (j + kSlotAhead < m) g->dict.prefetch_slot(o.keys[(*mine)[j + kSlotAhead]].hash);
+      if (j + kKeyAhead < m) g->dict.prefetch_key(o.keys[(*mine)[j + kKeyAhead]].hash);
+      const uint32_t r = (*mine)[j];
+      const KeyRef& k = o.keys[r];
+      o.idx[r] = g->dict.probe(arena + k.off, k.len, k.hash, i, r, &news);
+    }
   }
 }
 
-// ---- phase 2b (any thread): staged records -> their place in the pending log, aggregate index filled in
-void place_fetch(uint8_t* dst, const Staged* o) {
+// ---- phase 2b (caller's thread): the new ids of all workers, merged back into arrival order, get the next dense indices
+void admit_new_keys(sgr_ingest* g, std::vector<Staged>& staged, uint32_t n_workers) {
+  typedef std::pair<uint64_t, uint32_t> Head;   // (fetch << 32 | rec, worker)
+  std::priority_queue<Head, std::vector<Head>, std::greater<Head>> heap;
+  std::vector<size_t> pos(n_workers, 0);
+  auto key_of = [](const ShardedDict::NewKey& k) { return ((uint64_t)k.fetch << 32) | k.rec; };
+  for (uint32_t t = 0; t < n_workers; ++t) if (!g->news[t].empty()) heap.push(Head(key_of(g->news[t][0]), t));
+  while (!heap.empty()) {
+    const uint32_t t = heap.top().second;
+    heap.pop();
+    ShardedDict::NewKey& nk = g->news[t][pos[t]++];
+    g->dict.admit(&nk);
+    ++staged[nk.fetch].st.n_new_keys;
+    if (pos[t] < g->news[t].size()) heap.push(Head(key_of(g->news[t][pos[t]]), t));
+  }
+}
+
+// ---- phase 2d (any thread): staged records -> their place in the pending log, aggregate index filled in
+void place_fetch(const sgr_ingest* g, uint8_t* dst, const Staged* o, uint32_t n_workers) {
   memcpy(dst, o->recs.data(), o->recs.size());
   const size_t n = o->idx.size();
-  for (size_t i = 0; i < n; ++i) { const uint64_t agg = o->idx[i]; memcpy(dst + i * 64 + 8, &agg, 8); }
+  for (size_t i = 0; i < n; ++i) {
+    uint32_t v = o->idx[i];
+    if (v & ShardedDict::kProv) v = g->news[o->shard[i] % n_workers][v & ~ShardedDict::kProv].final_idx;
+    const uint64_t agg = v;
+    memcpy(dst + i * 64 + 8, &agg, 8);
+  }
 }
 
 // ---- phase 2c (caller's thread): the partition's position and the totals
@@ -570,15 +708,6 @@ void commit_fetch(sgr_ingest* g, int32_t partition, Staged* o) {
   t.n_compressed_bytes += st.n_compressed_bytes; t.n_decompressed_bytes += st.n_decompressed_bytes;
 }
 
-template <typename F>
-void run_parallel(uint32_t n_tasks, uint32_t n_thr, F&& task) {
-  if (n_thr <= 1 || n_tasks <= 1) { for (uint32_t i = 0; i < n_tasks; ++i) task(i); return; }
-  std::atomic<uint32_t> next{0};
-  std::vector<std::thread> pool;
-  for (uint32_t t = 0; t < std::min(n_thr, n_tasks); ++t)
-    pool.emplace_back([&]() { for (uint32_t c; (c = next.fetch_add(1)) < n_tasks;) task(c); });
-  for (auto& th : pool) th.join();
-}
 }  // namespace
 
 extern "C" {
@@ -610,17 +739,24 @@ int32_t sgr_ingest_record_batches_mt(sgr_ingest* g, uint32_t n, const int32_t* p
   const bool timing = getenv("SGR_INGEST_TIMING") != nullptr;
   const auto t0 = std::chrono::steady_clock::now();
   const uint32_t n_thr = std::max(1u, std::min<uint32_t>(threads ? threads : 1, (uint32_t)chains.size()));
-  run_parallel((uint32_t)chains.size(), n_thr, [&](uint32_t c) { run_chain(*chains[c]); });
+  g->workers.run((uint32_t)chains.size(), n_thr, [&](uint32_t c) { run_chain(*chains[c]); });
   for (uint32_t i = 0; i < n; ++i)
     if (staged[i].rc != SGR_OK) { g->last_error = staged[i].err; return staged[i].rc; }
   const auto t1 = std::chrono::steady_clock::now();
-  size_t add = 0;
-  for (uint32_t i = 0; i < n; ++i) add += staged[i].recs.size();
+  size_t add = 0, n_rec_total = 0;
+  for (uint32_t i = 0; i < n; ++i) { add += staged[i].recs.size(); n_rec_total += staged[i].keys.size(); staged[i].idx.resize(staged[i].keys.size()); }
   if (!g->pending.grow_to(g->pending.n + add)) return ifail(g, SGR_ERR_OOM, "pending log of %zu bytes", g->pending.n + add);
-  for (uint32_t i = 0; i < n; ++i) intern_fetch(g, &staged[i]);
+  // ids -> dense indices: shards probed in parallel, new ids admitted serially in arrival order, slots published in parallel
+  const uint32_t n_workers = std::max(1u, std::min<uint32_t>(std::min<uint32_t>(threads ? threads : 1, (uint32_t)ShardedDict::kShards),
+                                                             (uint32_t)(n_rec_total / 1024 + 1)));   // a worker per ~1k ids at least
+  if (g->news.size() < n_workers) g->news.resize(n_workers);
+  if (g->mine.size() < n_workers) g->mine.resize(n_workers);
+  g->workers.run(n_workers, n_workers, [&](uint32_t t) { probe_shards(g, staged, n, t, n_workers, &g->mine[t]); });
+  admit_new_keys(g, staged, n_workers);
+  g->workers.run(n_workers, n_workers, [&](uint32_t t) { for (const auto& nk : g->news[t]) g->dict.publish(nk); });
   std::vector<size_t> at(n);
   for (uint32_t i = 0; i < n; ++i) { at[i] = g->pending.n; g->pending.n += staged[i].recs.size(); }
-  run_parallel(n, std::max(1u, threads), [&](uint32_t i) { place_fetch(g->pending.p + at[i], &staged[i]); });
+  g->workers.run(n, std::max(1u, threads), [&](uint32_t i) { place_fetch(g, g->pending.p + at[i], &staged[i], n_workers); });
   for (uint32_t i = 0; i < n; ++i) {
     commit_fetch(g, partitions[i], &staged[i]);
     if (stats) stats[i] = staged[i].st;

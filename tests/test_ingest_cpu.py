@@ -327,6 +327,38 @@ def test_multi_fetch_call_equals_single_calls(threads):
     assert np.array_equal(par.pending(), serial.pending()) and par.keys() == serial.keys()
 
 
+def test_sharded_id_probing_keeps_first_seen_order():
+    """Polls big enough for the id dictionary to be probed by several workers (one per ~1k ids): indices must still be
+    first-seen ranks, provisional ids that recur inside the poll (same and other fetches) must resolve to one index."""
+    rng = np.random.default_rng(123)
+    nxt = {p: 0 for p in range(5)}
+    serial, par = Ingest(), Ingest()
+    for poll in range(3):
+        fetches = []
+        for p in range(5):
+            blob = bytearray()
+            for _ in range(4):
+                n = 400
+                recs = [(d, f"id-{int(rng.integers(0, 3000 * (poll + 1)))}:{d}".encode() if d % 50 else f"hot-{p % 2}".encode(),
+                         _event(0, nxt[p] + d, 1)) for d in range(n)]
+                blob += K.encode_record_batch(nxt[p], recs)
+                nxt[p] += n
+            fetches.append((p, bytes(blob)))
+        for p, b in fetches:
+            serial.record_batches(p, b)
+        par.record_batches_mt(fetches, threads=7)
+        assert np.array_equal(par.pending(), serial.pending())
+        assert par.keys() == serial.keys()
+        aggs = par.pending()[:, 8:16].copy().view(np.uint64).ravel()
+        first_seen = {}
+        for a in aggs.tolist():
+            first_seen.setdefault(a, len(first_seen))
+        if poll == 0:
+            assert all(a == rank for a, rank in first_seen.items())       # dense indices ARE first-seen ranks
+        if poll == 1:
+            serial.mark_folded(); par.mark_folded()
+
+
 def test_multi_fetch_call_is_all_or_nothing():
     rng = np.random.default_rng(78)
     good0, _ = _batch_stream(rng, 3, 50, "lz4", 0)

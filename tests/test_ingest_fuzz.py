@@ -95,3 +95,47 @@ def test_decoder_survives_mutated_input_under_asan_ubsan(tmp_path):
     ok = int(r.stdout.split("ok=")[1].split()[0])
     refused = int(r.stdout.split("refused=")[1].split()[0])
     assert ok > 50 and refused > 500      # both outcomes are exercised
+
+
+TSAN_BIN = os.path.join(OUT, "ingest_mt_tsan")
+
+
+def test_multi_threaded_decode_is_race_free_and_deterministic_under_tsan(tmp_path):
+    """The parallel phases (per-partition decode, sharded id probing, slot publication, placement) under ThreadSanitizer,
+    against the single-threaded result of the same polls."""
+    os.makedirs(OUT, exist_ok=True)
+    srcs = [os.path.join(ROOT, "surge_b200", "csrc", "ingest.cpp"), os.path.join(ROOT, "tests", "fuzz", "ingest_mt_main.cpp")]
+    if not (os.path.exists(TSAN_BIN) and os.path.getmtime(TSAN_BIN) >= max(os.path.getmtime(s) for s in srcs)):
+        r = subprocess.run(["g++", "-std=c++17", "-O1", "-g", "-fsanitize=thread", *srcs, "-o", TSAN_BIN, "-lpthread"], capture_output=True, text=True)
+        if r.returncode != 0:
+            pytest.skip("thread sanitizer build unavailable: " + r.stderr[-300:])
+    rng = np.random.default_rng(31)
+    ev = lambda s: struct.pack("<IIi", s % 3, s, s)  # noqa: E731
+    nxt = {p: 0 for p in range(6)}
+    polls = []
+    for poll in range(6):
+        fetches = []
+        for p in range(6):
+            for _ in range(1 + (poll + p) % 2):       # sometimes two fetches of one partition in a poll: they chain
+                blob = bytearray()
+                for _b in range(3):
+                    n = int(rng.integers(300, 600))      # ~12k records per poll: the id probing really runs on several workers
+                    recs = [(d, f"p{p}-k{int(rng.integers(0, 4000))}:{d}".encode(), ev(nxt[p] + d)) for d in range(n)]
+                    blob += K.encode_record_batch(nxt[p], recs, compression="lz4" if (p + _b) % 2 else "none")
+                    nxt[p] += n
+                fetches.append((p, bytes(blob)))
+        if poll == 4:
+            fetches.append((0, b"\x00" * 40))          # a malformed fetch: the whole poll is refused by both
+        polls.append(fetches)
+    path = tmp_path / "polls.bin"
+    with open(path, "wb") as f:
+        f.write(struct.pack("<I", len(polls)))
+        for fetches in polls:
+            f.write(struct.pack("<I", len(fetches)))
+            for p, data in fetches:
+                f.write(struct.pack("<iI", p, len(data)) + data)
+    for threads in (4, 13):
+        r = subprocess.run([TSAN_BIN, str(path), str(threads)], capture_output=True, text=True, timeout=600,
+                           env=dict(os.environ, TSAN_OPTIONS="halt_on_error=1"))
+        assert r.returncode == 0, (r.stdout[-300:], r.stderr[-3000:])
+        assert "polls=6" in r.stdout and "records=" in r.stdout
