@@ -327,7 +327,8 @@ typedef struct sgr_ingest_stats {
   uint64_t n_batches;
   uint64_t n_records;            /* packed records appended to the pending log */
   uint64_t n_markers;            /* null/empty-key records dropped */
-  uint64_t n_null_values;        /* keyed records with a null value dropped */
+  uint64_t n_null_values;        /* keyed records with a null value: dropped, or turned into tombstone events
+                                    (sgr_ingest_set_null_value_type) */
   uint64_t n_control_batches;
   uint64_t n_aborted_batches, n_aborted_records;
   uint64_t n_duplicates;         /* records below the partition's decoded position */
@@ -339,6 +340,10 @@ typedef struct sgr_ingest_stats {
 int32_t sgr_ingest_create(sgr_ingest** out);
 int32_t sgr_ingest_destroy(sgr_ingest* g);
 const char* sgr_ingest_last_error(const sgr_ingest* g);
+/* Compacted STATE topic (what the reference restores from today, COMMON/kafka/streams/SurgeStateStoreConsumer.scala:57-76): a keyed
+ * record with a null value deletes the key (CORE/internal/SurgeModel.scala:62-64). With event_type >= 0 such a record becomes an
+ * event of that type (the program's SGR_TOMBSTONE rule) instead of being dropped; -1 (default) drops it. */
+int32_t sgr_ingest_set_null_value_type(sgr_ingest* g, int32_t event_type);
 /* aborted transactions of the next fetch of `partition`: (producerId, firstOffset) pairs */
 int32_t sgr_ingest_set_aborted(sgr_ingest* g, int32_t partition, const int64_t* producer_ids, const int64_t* first_offsets, uint64_t n);
 int32_t sgr_ingest_record_batches(sgr_ingest* g, int32_t partition, const void* data, uint64_t nbytes, sgr_ingest_stats* stats);

@@ -436,6 +436,7 @@ struct Staged {
   PartitionState ps;              // the partition's state after this fetch (committed in phase 2)
   sgr_ingest_stats st{};
   int32_t rc = SGR_OK;
+  int32_t null_value_type = -1;
   std::string err;
   void reset() { recs.clear(); keys.clear(); arena.clear(); idx.clear(); shard.clear(); memset(shard_count, 0, sizeof shard_count); scratch.clear(); st = sgr_ingest_stats{}; rc = SGR_OK; err.clear(); }
 };
@@ -453,6 +454,7 @@ struct sgr_ingest {
   std::map<int32_t, PartitionState> parts;
   sgr_ingest_stats total{};
   uint64_t keys_at_mark = 0;
+  int32_t null_value_type = -1;     // >= 0: a keyed record with a null value becomes an event of this type (state-topic tombstones)
   std::vector<Staged> pool;         // staging buffers, reused across calls (a restore loop polls similar sizes)
 };
 
@@ -497,6 +499,12 @@ int32_t sgr_ingest_create(sgr_ingest** out) {
 int32_t sgr_ingest_destroy(sgr_ingest* g) { delete g; return SGR_OK; }
 
 const char* sgr_ingest_last_error(const sgr_ingest* g) { return g ? g->last_error.c_str() : "null ingest handle"; }
+
+int32_t sgr_ingest_set_null_value_type(sgr_ingest* g, int32_t event_type) {
+  if (!g || event_type >= (int32_t)SGR_MAX_TYPES) return ifail(g, SGR_ERR_INVALID, "event type out of range");
+  g->null_value_type = event_type < 0 ? -1 : event_type;
+  return SGR_OK;
+}
 
 int32_t sgr_ingest_set_aborted(sgr_ingest* g, int32_t partition, const int64_t* producer_ids, const int64_t* first_offsets, uint64_t n) {
   if (!g || (n && (!producer_ids || !first_offsets))) return ifail(g, SGR_ERR_INVALID, "null argument");
@@ -606,8 +614,8 @@ int32_t decode_fetch(int32_t partition, const uint8_t* buf, uint64_t nbytes, Sta
         const int64_t offset = base_offset + offset_delta;
         if (ps.seen && offset < ps.decoded_next) { ++st.n_duplicates; continue; }  // refetch after a restart: already decoded
         if (key_len <= 0) { ++st.n_markers; continue; }                              // the producer's empty-key flush record
-        if (val_len < 0) { ++st.n_null_values; continue; }
-        if (val_len < 8 || val_len > 56) return sfail(o, SGR_ERR_INVALID, "partition %d offset %lld: packed event value of %d bytes (expected 8..56: u32 type, u32 seq, payload)", partition, (long long)offset, val_len);
+        if (val_len < 0 && o->null_value_type < 0) { ++st.n_null_values; continue; }
+        if (val_len >= 0 && (val_len < 8 || val_len > 56)) return sfail(o, SGR_ERR_INVALID, "partition %d offset %lld: packed event value of %d bytes (expected 8..56: u32 type, u32 seq, payload)", partition, (long long)offset, val_len);
         uint32_t id_len = 0;
         {   // PartitionStringUpToColon (KafkaPartitioner.scala:38-42)
           const void* colon = memchr(key, ':', (size_t)key_len);
@@ -619,8 +627,14 @@ int32_t decode_fetch(int32_t partition, const uint8_t* buf, uint64_t nbytes, Sta
         *shp++ = (uint8_t)ShardedDict::shard_of(kh);
         ++o->shard_count[ShardedDict::shard_of(kh)];
         memcpy(ar, key, id_len); ar += id_len;
-        memcpy(rec, val, 8);                    // u32 type, u32 seq (little endian, as the packer wrote them)
-        memcpy(rec + 16, val + 8, (size_t)val_len - 8);   // the rest of the slot is zero from resize(): agg, payload tail
+        if (val_len < 0) {                      // null value on a compacted state topic = delete the key (SurgeModel.scala:62-64)
+          const uint32_t ty = (uint32_t)o->null_value_type;
+          memcpy(rec, &ty, 4);
+          ++st.n_null_values;
+        } else {
+          memcpy(rec, val, 8);                  // u32 type, u32 seq (little endian, as the packer wrote them)
+          memcpy(rec + 16, val + 8, (size_t)val_len - 8);   // the rest of the slot is zero from resize(): agg, payload tail
+        }
         rec += 64;
         ++st.n_records;
       }
@@ -741,6 +755,7 @@ int32_t sgr_ingest_record_batches_mt(sgr_ingest* g, uint32_t n, const int32_t* p
     const PartitionState* from = &g->parts.find(partitions[chain[0]])->second;
     for (uint32_t i : chain) {
       staged[i].ps = *from;
+      staged[i].null_value_type = g->null_value_type;
       if (decode_fetch(partitions[i], (const uint8_t*)datas[i], nbytes[i], &staged[i]) != SGR_OK) return;
       from = &staged[i].ps;
     }

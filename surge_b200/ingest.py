@@ -47,6 +47,10 @@ class Ingest:
     def handle(self) -> C.c_void_p:
         return self._h
 
+    def set_null_value_type(self, event_type: int) -> None:
+        """State-topic mode: null-valued records become events of `event_type` (the program's tombstone rule); -1 drops them."""
+        self._check(self._lib.sgr_ingest_set_null_value_type(self._h, event_type))
+
     def set_aborted(self, partition: int, aborted: Sequence[Tuple[int, int]]) -> None:
         """aborted = [(producer_id, first_offset)] from the fetch response."""
         if not aborted:

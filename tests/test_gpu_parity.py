@@ -841,3 +841,44 @@ def test_record_batches_to_states(compression):
             assert e.get("never-seen") is None
         # the checker agrees with its own restatement of the whole session only through the decoder tests
         # (tests/test_ingest_cpu.py); here the point is decode -> GPU fold -> get.
+
+
+def test_state_topic_restore_from_raw_record_batches():
+    """Today's rebuild in the reference, from broker bytes: the compacted STATE topic (snapshot per write, null = delete)
+    decoded natively and folded with the snapshot-restore program must equal the object-level KTable restatement
+    (SurgeStateStoreConsumer.scala:57-76; AggregateStateStoreKafkaStreamsSpec.scala:64-85)."""
+    import struct
+
+    from oracle import kafka_batch as K
+    from surge_b200.ingest import Ingest
+
+    rng = np.random.default_rng(612)
+    ing = Ingest()
+    ing.set_null_value_type(1)
+    history = []
+    off = 0
+    with ReplayEngine(0) as e:
+        e.register_program(P.counter_snapshot_restore_program())
+        for poll in range(4):
+            blob = bytearray()
+            for _ in range(5):
+                recs = []
+                for d in range(int(rng.integers(50, 300))):
+                    key = f"agg-{int(rng.integers(0, 500))}"
+                    if rng.random() < 0.1:
+                        recs.append((d, key.encode(), None)); history.append((key, None))
+                    else:
+                        c, v = int(rng.integers(-2**31, 2**31)), int(rng.integers(0, 1000))
+                        recs.append((d, key.encode(), struct.pack("<IIii", 0, 0, c, v))); history.append((key, (c, v)))
+                blob += K.encode_record_batch(off, recs, compression="lz4")
+                off += len(recs)
+            ing.record_batches(0, bytes(blob))
+            e.fold_ingested(ing)
+            table = M.ktable_restore(history)
+            for key in {k for k, _ in history}:
+                got = e.get(key)
+                want = table.get(key)
+                assert (got is None) == (want is None), key
+                if want is not None:
+                    assert tuple(np.frombuffer(got, "<i4").tolist()) == want
+        assert ing.offsets(0) == (off, off)

@@ -407,3 +407,26 @@ def test_pending_log_moves_to_a_caller_supplied_allocator(lib):
     assert np.array_equal(ing.pending()[: len(before)], before)
     ing.close()
     assert calls["free"] == calls["alloc"]
+
+
+def test_state_topic_tombstones_become_events():
+    """A compacted state topic: a keyed record with a null value deletes the key (SurgeModel.scala:62-64). By default such
+    records are dropped (events topics never hold them); in state-topic mode they become events of the chosen type."""
+    snap = lambda c, v: struct.pack("<IIii", 0, 0, c, v)  # noqa: E731   type 0 = snapshot {count, version}
+    recs = [(0, b"a", snap(1, 1)), (1, b"b", snap(7, 2)), (2, b"a", None), (3, None, None), (4, b"c", None)]
+    batch = K.encode_record_batch(0, recs, compression="lz4")
+    dropped = Ingest()
+    st = dropped.record_batches(0, batch)
+    assert (st["n_records"], st["n_null_values"], st["n_markers"]) == (2, 2, 1) and dropped.keys() == ["a", "b"]
+    ing = Ingest()
+    ing.set_null_value_type(1)
+    st = ing.record_batches(0, batch)
+    assert (st["n_records"], st["n_null_values"], st["n_markers"]) == (4, 2, 1) and ing.keys() == ["a", "b", "c"]
+    p = ing.pending()
+    assert p[:, 0:4].view(np.uint32).ravel().tolist() == [0, 0, 1, 1]
+    assert p[:, 8:16].view(np.uint64).ravel().tolist() == [0, 1, 0, 2]
+    assert not p[2:, 16:].any() and not p[2:, 4:8].any()
+    with pytest.raises(IngestError):
+        ing.set_null_value_type(16)
+    ing.set_null_value_type(-1)
+    assert ing.record_batches(1, batch)["n_records"] == 2
