@@ -264,7 +264,7 @@ class ShardedDict {
   ShardedDict() { offs_.push_back(0); }
   static int shard_of(uint64_t h) { return (int)(h >> 58); }
 
-  void reserve_shard(int s, uint64_t extra) { while ((count_[s] + extra + 1) * 2 > slots_[s].size()) grow(s); }
+  void reserve_shard(int s, uint64_t extra) { while ((count_[s].n + extra + 1) * 2 > slots_[s].size()) grow(s); }
   void prefetch_slot(uint64_t h) const { const auto& t = slots_[shard_of(h)]; if (!t.empty()) __builtin_prefetch(&t[(uint32_t)h & (t.size() - 1)]); }
   void prefetch_key(uint64_t h) const {   // the slot is expected in cache by now: pull the candidate's id bytes
     const auto& t = slots_[shard_of(h)];
@@ -284,7 +284,7 @@ class ShardedDict {
       if (sl.idx == kEmpty) {
         sl.tag = tag; sl.idx = kProv | (uint32_t)news->size(); sl.off_len = 0;
         news->push_back(NewKey{fetch, rec, k, len, (uint32_t)s, (uint32_t)at, 0u});
-        ++count_[s];
+        ++count_[s].n;
         return sl.idx;
       }
       if (sl.tag == tag) {
@@ -330,7 +330,8 @@ class ShardedDict {
   std::vector<uint8_t> bytes_;
   std::vector<uint32_t> offs_;
   std::vector<Slot> slots_[kShards];
-  uint64_t count_[kShards] = {0};
+  struct alignas(64) Count { uint64_t n = 0; };   // one cache line per shard: each is bumped by a different worker
+  Count count_[kShards];
   uint64_t n_ = 0;
 };
 
@@ -416,6 +417,11 @@ struct RawBuf {
   }
 };
 
+struct ProbeOut {                 // one worker's probe results: (record position, dense index or provisional) per fetch
+  std::vector<uint32_t> pos, val;
+  std::vector<size_t> off;        // n_fetches + 1
+};
+
 struct PartitionState {
   int64_t decoded_next = 0;   // next offset this partition expects (last decoded batch's lastOffset + 1)
   int64_t folded_next = 0;    // everything below this offset is inside the state table
@@ -429,7 +435,6 @@ struct Staged {
   std::vector<uint8_t> recs;      // 64-byte records, agg field still zero
   std::vector<KeyRef> keys;       // one per record, into `arena`
   std::vector<uint8_t> arena;     // aggregate-id bytes (copied: the decompression scratch is reused per batch)
-  std::vector<uint32_t> idx;      // dense index of each record's aggregate, or kProv | position in its owner's NewKey list
   std::vector<uint8_t> shard;     // dictionary shard of each record's id
   uint32_t shard_count[ShardedDict::kShards];
   std::vector<uint8_t> scratch;
@@ -438,7 +443,7 @@ struct Staged {
   int32_t rc = SGR_OK;
   int32_t null_value_type = -1;
   std::string err;
-  void reset() { recs.clear(); keys.clear(); arena.clear(); idx.clear(); shard.clear(); memset(shard_count, 0, sizeof shard_count); scratch.clear(); st = sgr_ingest_stats{}; rc = SGR_OK; err.clear(); }
+  void reset() { recs.clear(); keys.clear(); arena.clear(); shard.clear(); memset(shard_count, 0, sizeof shard_count); scratch.clear(); st = sgr_ingest_stats{}; rc = SGR_OK; err.clear(); }
 };
 
 }  // namespace
@@ -448,7 +453,7 @@ struct sgr_ingest {
   ShardedDict dict;
   WorkerPool workers;
   std::vector<std::vector<ShardedDict::NewKey>> news;   // per worker, reused across calls
-  std::vector<std::vector<uint32_t>> mine;               // per worker: the record positions of the fetch it is probing
+  std::vector<ProbeOut> probed;                          // per worker, reused across calls
   RawBuf pending;                   // packed 64-byte records, arrival order
   std::vector<uint8_t> scratch;     // decompressed records section of the batch being decoded
   std::map<int32_t, PartitionState> parts;
@@ -655,9 +660,13 @@ int32_t decode_fetch(int32_t partition, const uint8_t* buf, uint64_t nbytes, Sta
 
 // ---- phase 2a (worker t of n_workers; owns the shards s with s % n_workers == t): probe every id of those shards, in
 // arrival order. Known ids get their dense index at once; new ones a provisional slot and an entry in the worker's list.
-void probe_shards(sgr_ingest* g, std::vector<Staged>& staged, uint32_t n, uint32_t t, uint32_t n_workers, std::vector<uint32_t>* mine) {
+void probe_shards(sgr_ingest* g, std::vector<Staged>& staged, uint32_t n, uint32_t t, uint32_t n_workers) {
   std::vector<ShardedDict::NewKey>& news = g->news[t];
   news.clear();
+  // Results stay in the worker's own arrays (record position, index), fetch by fetch: neighbouring records belong to
+  // different workers, and writing into one shared per-record array would bounce its cache lines between all of them.
+  ProbeOut& out = g->probed[t];
+  out.pos.clear(); out.val.clear(); out.off.assign(1, 0);
   uint8_t owner[ShardedDict::kShards];
   for (int s = 0; s < ShardedDict::kShards; ++s) owner[s] = (uint8_t)(s % (int)n_workers);
   for (int s = (int)t; s < ShardedDict::kShards; s += (int)n_workers) {
@@ -666,25 +675,29 @@ void probe_shards(sgr_ingest* g, std::vector<Staged>& staged, uint32_t n, uint32
     g->dict.reserve_shard(s, extra);
   }
   for (uint32_t i = 0; i < n; ++i) {
-    Staged& o = staged[i];
+    const Staged& o = staged[i];
     const size_t cnt = o.keys.size();
     const uint8_t* sh = o.shard.data();
-    mine->clear();
-    if (n_workers == 1) { mine->resize(cnt); for (size_t r = 0; r < cnt; ++r) (*mine)[r] = (uint32_t)r; }
-    else for (size_t r = 0; r < cnt; ++r) if (owner[sh[r]] == t) mine->push_back((uint32_t)r);
+    const size_t base = out.pos.size();
+    if (n_workers == 1) { out.pos.resize(base + cnt); for (size_t r = 0; r < cnt; ++r) out.pos[base + r] = (uint32_t)r; }
+    else for (size_t r = 0; r < cnt; ++r) if (owner[sh[r]] == t) out.pos.push_back((uint32_t)r);
+    const size_t m = out.pos.size() - base;
+    out.val.resize(base + m);
+    const uint32_t* mine = out.pos.data() + base;
+    uint32_t* val = out.val.data() + base;
     const uint8_t* arena = o.arena.data();
-    const size_t m = mine->size();
     // the dictionary of a big topic does not fit any cache: run the probe as a software pipeline — slot prefetched 16
     // ids ahead, the candidate's id bytes 8 ahead — so that the misses of neighbouring records overlap
     constexpr size_t kSlotAhead = 16, kKeyAhead = 8;
-    for (size_t j = 0; j < std::min(m, kSlotAhead); ++j) g->dict.prefetch_slot(o.keys[(*mine)[j]].hash);
+    for (size_t j = 0; j < std::min(m, kSlotAhead); ++j) g->dict.prefetch_slot(o.keys[mine[j]].hash);
     for (size_t j = 0; j < m; ++j) {
-      if (j + kSlotAhead < m) g->dict.prefetch_slot(o.keys[(*mine)[j + kSlotAhead]].hash);
-      if (j + kKeyAhead < m) g->dict.prefetch_key(o.keys[(*mine)[j + kKeyAhead]].hash);
-      const uint32_t r = (*mine)[j];
+      if (j + kSlotAhead < m) g->dict.prefetch_slot(o.keys[mine[j + kSlotAhead]].hash);
+      if (j + kKeyAhead < m) g->dict.prefetch_key(o.keys[mine[j + kKeyAhead]].hash);
+      const uint32_t r = mine[j];
       const KeyRef& k = o.keys[r];
-      o.idx[r] = g->dict.probe(arena + k.off, k.len, k.hash, i, r, &news);
+      val[j] = g->dict.probe(arena + k.off, k.len, k.hash, i, r, &news);
     }
+    out.off.push_back(out.pos.size());
   }
 }
 
@@ -705,15 +718,19 @@ void admit_new_keys(sgr_ingest* g, std::vector<Staged>& staged, uint32_t n_worke
   }
 }
 
-// ---- phase 2d (any thread): staged records -> their place in the pending log, aggregate index filled in
-void place_fetch(const sgr_ingest* g, uint8_t* dst, const Staged* o, uint32_t n_workers) {
+// ---- phase 2d (any thread; one task per fetch = the only writer of that part of the pending log): staged records to
+// their place, aggregate indices gathered from the workers' result lists
+void place_fetch(const sgr_ingest* g, uint8_t* dst, const Staged* o, uint32_t fetch, uint32_t n_workers) {
   memcpy(dst, o->recs.data(), o->recs.size());
-  const size_t n = o->idx.size();
-  for (size_t i = 0; i < n; ++i) {
-    uint32_t v = o->idx[i];
-    if (v & ShardedDict::kProv) v = g->news[o->shard[i] % n_workers][v & ~ShardedDict::kProv].final_idx;
-    const uint64_t agg = v;
-    memcpy(dst + i * 64 + 8, &agg, 8);
+  for (uint32_t t = 0; t < n_workers; ++t) {
+    const ProbeOut& out = g->probed[t];
+    const std::vector<ShardedDict::NewKey>& news = g->news[t];
+    for (size_t j = out.off[fetch]; j < out.off[fetch + 1]; ++j) {
+      uint32_t v = out.val[j];
+      if (v & ShardedDict::kProv) v = news[v & ~ShardedDict::kProv].final_idx;
+      const uint64_t agg = v;
+      memcpy(dst + (size_t)out.pos[j] * 64 + 8, &agg, 8);
+    }
   }
 }
 
@@ -768,19 +785,19 @@ int32_t sgr_ingest_record_batches_mt(sgr_ingest* g, uint32_t n, const int32_t* p
     if (staged[i].rc != SGR_OK) { g->last_error = staged[i].err; return staged[i].rc; }
   const auto t1 = std::chrono::steady_clock::now();
   size_t add = 0, n_rec_total = 0;
-  for (uint32_t i = 0; i < n; ++i) { add += staged[i].recs.size(); n_rec_total += staged[i].keys.size(); staged[i].idx.resize(staged[i].keys.size()); }
+  for (uint32_t i = 0; i < n; ++i) { add += staged[i].recs.size(); n_rec_total += staged[i].keys.size(); }
   if (!g->pending.grow_to(g->pending.n + add)) return ifail(g, SGR_ERR_OOM, "pending log of %zu bytes", g->pending.n + add);
   // ids -> dense indices: shards probed in parallel, new ids admitted serially in arrival order, slots published in parallel
   const uint32_t n_workers = std::max(1u, std::min<uint32_t>(std::min<uint32_t>(threads ? threads : 1, (uint32_t)ShardedDict::kShards),
                                                              (uint32_t)(n_rec_total / 1024 + 1)));   // a worker per ~1k ids at least
   if (g->news.size() < n_workers) g->news.resize(n_workers);
-  if (g->mine.size() < n_workers) g->mine.resize(n_workers);
-  g->workers.run(n_workers, n_workers, [&](uint32_t t) { probe_shards(g, staged, n, t, n_workers, &g->mine[t]); });
+  if (g->probed.size() < n_workers) g->probed.resize(n_workers);
+  g->workers.run(n_workers, n_workers, [&](uint32_t t) { probe_shards(g, staged, n, t, n_workers); });
   admit_new_keys(g, staged, n_workers);
   g->workers.run(n_workers, n_workers, [&](uint32_t t) { for (const auto& nk : g->news[t]) g->dict.publish(nk); });
   std::vector<size_t> at(n);
   for (uint32_t i = 0; i < n; ++i) { at[i] = g->pending.n; g->pending.n += staged[i].recs.size(); }
-  g->workers.run(n, std::max(1u, threads), [&](uint32_t i) { place_fetch(g, g->pending.p + at[i], &staged[i], n_workers); });
+  g->workers.run(n, std::max(1u, threads), [&](uint32_t i) { place_fetch(g, g->pending.p + at[i], &staged[i], i, n_workers); });
   for (uint32_t i = 0; i < n; ++i) {
     commit_fetch(g, partitions[i], &staged[i]);
     if (stats) stats[i] = staged[i].st;
