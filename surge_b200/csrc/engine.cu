@@ -785,14 +785,14 @@ int32_t sgr_grow_states(sgr_engine* e, uint64_t n_agg) {
   rc = before_load(e); if (rc) return rc;
   if (e->states_valid && n_agg <= e->states_n) return SGR_OK;
   const size_t sb = e->program.state_bytes;
-  DevBuf nb;
+  struct Guard { DevBuf b; ~Guard() { b.release(); } } guard;   // frees the old table on success, the new one on failure
+  DevBuf& nb = guard.b;
   CUDA_TRY(e, nb.reserve((size_t)n_agg * sb));
   const size_t keep = e->states_valid ? (size_t)e->states_n * sb : 0;
   if (keep) CUDA_TRY(e, cudaMemcpyAsync(nb.p, e->states.p, keep, cudaMemcpyDeviceToDevice, e->stream));
   CUDA_TRY(e, cudaMemsetAsync((uint8_t*)nb.p + keep, 0, (size_t)n_agg * sb - keep, e->stream));
   CUDA_TRY(e, cudaStreamSynchronize(e->stream));
   std::swap(e->states, nb);
-  nb.release();
   e->states_n = n_agg;
   e->states_valid = true;
   e->inc_atomic_prev_valid = false; e->inc_prev_n = 0;
