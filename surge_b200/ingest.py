@@ -19,6 +19,15 @@ class IngestError(N.SgrError):
     pass
 
 
+def _as_pointer(data) -> C.c_void_p:
+    """Address of a bytes-like object's buffer, without copying it (the decoder only reads)."""
+    if not len(data):
+        return C.c_void_p(None)
+    if isinstance(data, bytes):
+        return C.cast(C.c_char_p(data), C.c_void_p)
+    return C.c_void_p(np.frombuffer(data, dtype=np.uint8).ctypes.data)
+
+
 class Ingest:
     def __init__(self):
         self._lib = N.load_library()
@@ -61,8 +70,7 @@ class Ingest:
 
     def record_batches(self, partition: int, data: bytes) -> Dict[str, int]:
         st = N.sgr_ingest_stats()
-        buf = (C.c_char * len(data)).from_buffer_copy(data) if data else None
-        self._check(self._lib.sgr_ingest_record_batches(self._h, partition, C.cast(buf, C.c_void_p) if buf is not None else None, len(data), C.byref(st)))
+        self._check(self._lib.sgr_ingest_record_batches(self._h, partition, _as_pointer(data), len(data), C.byref(st)))
         return {n: int(getattr(st, n)) for n, _ in N.sgr_ingest_stats._fields_ if n != "reserved"}
 
     def record_batches_mt(self, fetches: Sequence[Tuple[int, bytes]], threads: int = 0) -> List[Dict[str, int]]:
@@ -73,9 +81,8 @@ class Ingest:
         n = len(fetches)
         if not n:
             return []
-        bufs = [(C.c_char * max(len(d), 1)).from_buffer_copy(d or b"\0") for _, d in fetches]
         parts = (C.c_int32 * n)(*[p for p, _ in fetches])
-        ptrs = (C.c_void_p * n)(*[C.cast(b, C.c_void_p) for b in bufs])
+        ptrs = (C.c_void_p * n)(*[_as_pointer(d) for _, d in fetches])     # borrowed for the call: `fetches` keeps the bytes alive
         lens = (C.c_uint64 * n)(*[len(d) for _, d in fetches])
         st = (N.sgr_ingest_stats * n)()
         thr = threads or min(len({p for p, _ in fetches}), os.cpu_count() or 1)
