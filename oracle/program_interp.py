@@ -12,7 +12,7 @@ Only tests/ may import it. One Python loop per event: use it on thousands of eve
 from __future__ import annotations
 
 import struct
-from typing import List, Optional, Sequence, Tuple
+from typing import Optional, Sequence, Tuple
 
 import numpy as np
 
