@@ -54,7 +54,6 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ uint32_t ldv32(const uint32_t* p) { uint32_t v; asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p)); return v; }
-__device__ __forceinline__ unsigned long long ldv64(const unsigned long long* p) { unsigned long long v; asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p)); return v; }
 
 // full rebuild only: prior state is None (the table is zeroed before the launch, empty aggregates stay None)
 __device__ __forceinline__ void finish_var(const VarArgs& a, uint32_t seg, const Xv& ts) {
