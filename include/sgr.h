@@ -340,6 +340,14 @@ typedef struct sgr_ingest_stats {
 int32_t sgr_ingest_create(sgr_ingest** out);
 int32_t sgr_ingest_destroy(sgr_ingest* g);
 const char* sgr_ingest_last_error(const sgr_ingest* g);
+/* How the record value wraps the packed event. SGR_VALUE_PACKED (default): the value IS `u32 type, u32 seq, payload`.
+ * SGR_VALUE_PROTOBUF_EVENT: the value is the multilanguage module's protobuf `Event { string aggregateId = 1; bytes payload = 2; }`
+ * (modules/multilanguage-protocol/src/main/protobuf/multilanguage-protocol.proto:17-20, written by
+ * modules/multilanguage/src/main/scala/com/ukg/surge/multilanguage/GenericSurgeCommandBusinessLogic.scala:30-33) and the packed
+ * event is its payload. The framing is pinned against the protobuf runtime in tests/test_ingest_cpu.py. */
+#define SGR_VALUE_PACKED          0
+#define SGR_VALUE_PROTOBUF_EVENT  1
+int32_t sgr_ingest_set_value_framing(sgr_ingest* g, int32_t framing);
 /* Compacted STATE topic (what the reference restores from today, COMMON/kafka/streams/SurgeStateStoreConsumer.scala:57-76): a keyed
  * record with a null value deletes the key (CORE/internal/SurgeModel.scala:62-64). With event_type >= 0 such a record becomes an
  * event of that type (the program's SGR_TOMBSTONE rule) instead of being dropped; -1 (default) drops it. */

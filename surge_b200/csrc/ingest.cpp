@@ -235,6 +235,17 @@ struct Cursor {
     }
     ok = false; return 0;
   }
+  uint64_t uvarint() {   // protobuf base-128 varint (no zig-zag), at most 10 bytes
+    uint64_t v = 0; int shift = 0;
+    for (int i = 0; i < 10; ++i) {
+      if (pos >= n) { ok = false; return 0; }
+      const uint8_t b = p[pos++];
+      v |= (uint64_t)(b & 0x7f) << shift;
+      if (!(b & 0x80)) return v;
+      shift += 7;
+    }
+    ok = false; return 0;
+  }
   const uint8_t* bytes(uint64_t k) {
     if (k > n - pos) { ok = false; return nullptr; }
     const uint8_t* r = p + pos; pos += k; return r;
@@ -442,6 +453,7 @@ struct Staged {
   sgr_ingest_stats st{};
   int32_t rc = SGR_OK;
   int32_t null_value_type = -1;
+  int32_t value_framing = 0;
   std::string err;
   void reset() { recs.clear(); keys.clear(); arena.clear(); shard.clear(); memset(shard_count, 0, sizeof shard_count); scratch.clear(); st = sgr_ingest_stats{}; rc = SGR_OK; err.clear(); }
 };
@@ -459,6 +471,7 @@ struct sgr_ingest {
   std::map<int32_t, PartitionState> parts;
   sgr_ingest_stats total{};
   uint64_t keys_at_mark = 0;
+  int32_t value_framing = 0;        // SGR_VALUE_PACKED | SGR_VALUE_PROTOBUF_EVENT
   int32_t null_value_type = -1;     // >= 0: a keyed record with a null value becomes an event of this type (state-topic tombstones)
   std::vector<Staged> pool;         // staging buffers, reused across calls (a restore loop polls similar sizes)
 };
@@ -504,6 +517,12 @@ int32_t sgr_ingest_create(sgr_ingest** out) {
 int32_t sgr_ingest_destroy(sgr_ingest* g) { delete g; return SGR_OK; }
 
 const char* sgr_ingest_last_error(const sgr_ingest* g) { return g ? g->last_error.c_str() : "null ingest handle"; }
+
+int32_t sgr_ingest_set_value_framing(sgr_ingest* g, int32_t framing) {
+  if (!g || (framing != SGR_VALUE_PACKED && framing != SGR_VALUE_PROTOBUF_EVENT)) return ifail(g, SGR_ERR_INVALID, "unknown value framing %d", framing);
+  g->value_framing = framing;
+  return SGR_OK;
+}
 
 int32_t sgr_ingest_set_null_value_type(sgr_ingest* g, int32_t event_type) {
   if (!g || event_type >= (int32_t)SGR_MAX_TYPES) return ifail(g, SGR_ERR_INVALID, "event type out of range");
@@ -608,8 +627,8 @@ int32_t decode_fetch(int32_t partition, const uint8_t* buf, uint64_t nbytes, Sta
         const int32_t offset_delta = q.varint();
         const int32_t key_len = q.varint();
         const uint8_t* key = key_len > 0 ? q.bytes((uint64_t)key_len) : nullptr;
-        const int32_t val_len = q.varint();
-        const uint8_t* val = val_len > 0 ? q.bytes((uint64_t)val_len) : nullptr;
+        const int32_t wire_val_len = q.varint();
+        const uint8_t* val = wire_val_len > 0 ? q.bytes((uint64_t)wire_val_len) : nullptr;
         const int32_t n_headers = q.varint();
         for (int32_t h = 0; q.ok && h < n_headers; ++h) {
           const int32_t hk = q.varint(); if (hk < 0) { q.ok = false; break; } q.bytes((uint64_t)hk);
@@ -619,7 +638,32 @@ int32_t decode_fetch(int32_t partition, const uint8_t* buf, uint64_t nbytes, Sta
         const int64_t offset = base_offset + offset_delta;
         if (ps.seen && offset < ps.decoded_next) { ++st.n_duplicates; continue; }  // refetch after a restart: already decoded
         if (key_len <= 0) { ++st.n_markers; continue; }                              // the producer's empty-key flush record
-        if (val_len < 0 && o->null_value_type < 0) { ++st.n_null_values; continue; }
+        if (wire_val_len < 0 && o->null_value_type < 0) { ++st.n_null_values; continue; }
+        int32_t val_len = wire_val_len;
+        if (val_len >= 0 && o->value_framing == SGR_VALUE_PROTOBUF_EVENT) {
+          // multilanguage topics: the value is protobuf Event { string aggregateId = 1; bytes payload = 2; }
+          // (multilanguage-protocol.proto:17-20, written by GenericSurgeCommandBusinessLogic.scala:30-33); the packed event is the payload
+          Cursor pb(val, (uint64_t)val_len);
+          const uint8_t* payload = nullptr; uint64_t payload_len = 0;
+          while (pb.ok && pb.pos < pb.n) {
+            const uint64_t tag = pb.uvarint();
+            if (!pb.ok) break;
+            switch (tag & 7) {
+              case 0: pb.uvarint(); break;
+              case 1: pb.bytes(8); break;
+              case 5: pb.bytes(4); break;
+              case 2: {
+                const uint64_t ln = pb.uvarint();
+                const uint8_t* b = pb.ok ? pb.bytes(ln) : nullptr;
+                if (pb.ok && (tag >> 3) == 2) { payload = b; payload_len = ln; }
+                break;
+              }
+              default: pb.ok = false;
+            }
+          }
+          if (!pb.ok) return sfail(o, SGR_ERR_INVALID, "partition %d offset %lld: value is not a protobuf Event", partition, (long long)offset);
+          val = payload; val_len = (int32_t)(payload_len > 0x7fffffff ? 0x7fffffff : payload_len);
+        }
         if (val_len >= 0 && (val_len < 8 || val_len > 56)) return sfail(o, SGR_ERR_INVALID, "partition %d offset %lld: packed event value of %d bytes (expected 8..56: u32 type, u32 seq, payload)", partition, (long long)offset, val_len);
         uint32_t id_len = 0;
         {   // PartitionStringUpToColon (KafkaPartitioner.scala:38-42)
@@ -773,6 +817,7 @@ int32_t sgr_ingest_record_batches_mt(sgr_ingest* g, uint32_t n, const int32_t* p
     for (uint32_t i : chain) {
       staged[i].ps = *from;
       staged[i].null_value_type = g->null_value_type;
+      staged[i].value_framing = g->value_framing;
       if (decode_fetch(partitions[i], (const uint8_t*)datas[i], nbytes[i], &staged[i]) != SGR_OK) return;
       from = &staged[i].ps;
     }

@@ -108,3 +108,66 @@ def counter_state_json(aggregate_id: str, count: int, version: int) -> bytes:
     binary table (the shim calls the user's own writeState on the JVM)."""
     return json.dumps({"aggregateId": aggregate_id, "count": int(count), "version": int(version)},
                       separators=(",", ":"), ensure_ascii=False).encode("utf-8")
+
+
+# ----------------------------------------------------------------------------- multilanguage protobuf framing
+# modules/multilanguage-protocol/src/main/protobuf/multilanguage-protocol.proto:7-20: State, Command and Event are all
+#   message X { string aggregateId = 1; bytes payload = 2; }
+# and GenericSurgeCommandBusinessLogic.scala:25-38 reads/writes the state and event topics as X.toByteArray.
+# proto3 canonical encoding: fields in number order, default (empty) values omitted.
+def _pb_uvarint(n: int) -> bytes:
+    out = bytearray()
+    while n >= 0x80:
+        out.append((n & 0x7F) | 0x80)
+        n >>= 7
+    out.append(n)
+    return bytes(out)
+
+
+def multilanguage_proto(aggregate_id: str, payload: bytes) -> bytes:
+    """protobuf.State / protobuf.Event .toByteArray for (aggregateId, payload)."""
+    aid = aggregate_id.encode("utf-8")
+    out = b""
+    if aid:
+        out += b"\x0a" + _pb_uvarint(len(aid)) + aid
+    if payload:
+        out += b"\x12" + _pb_uvarint(len(payload)) + bytes(payload)
+    return out
+
+
+def parse_multilanguage_proto(data: bytes):
+    """-> (aggregateId, payload); unknown fields are skipped, the last occurrence of a field wins (protobuf semantics)."""
+    aid, payload, p = "", b"", 0
+
+    def uvar(p):
+        v = shift = 0
+        while True:
+            b = data[p]
+            p += 1
+            v |= (b & 0x7F) << shift
+            if not b & 0x80:
+                return v, p
+            shift += 7
+
+    while p < len(data):
+        tag, p = uvar(p)
+        wt, field = tag & 7, tag >> 3
+        if wt == 0:
+            _, p = uvar(p)
+        elif wt == 1:
+            p += 8
+        elif wt == 5:
+            p += 4
+        elif wt == 2:
+            ln, p = uvar(p)
+            body = data[p:p + ln]
+            if len(body) != ln:
+                raise ValueError("truncated protobuf field")
+            p += ln
+            if field == 1:
+                aid = body.decode("utf-8")
+            elif field == 2:
+                payload = bytes(body)
+        else:
+            raise ValueError(f"unsupported protobuf wire type {wt}")
+    return aid, payload

@@ -56,6 +56,10 @@ class Ingest:
     def handle(self) -> C.c_void_p:
         return self._h
 
+    def set_value_framing(self, framing: int) -> None:
+        """0 = the value is the packed event; 1 = protobuf Event{aggregateId, payload} of the multilanguage module."""
+        self._check(self._lib.sgr_ingest_set_value_framing(self._h, framing))
+
     def set_null_value_type(self, event_type: int) -> None:
         """State-topic mode: null-valued records become events of `event_type` (the program's tombstone rule); -1 drops them."""
         self._check(self._lib.sgr_ingest_set_null_value_type(self._h, event_type))

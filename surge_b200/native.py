@@ -122,6 +122,7 @@ ABI = [
     ("sgr_ingest_create", C.c_int32, [C.POINTER(_P)]),
     ("sgr_ingest_destroy", C.c_int32, [_P]),
     ("sgr_ingest_last_error", C.c_char_p, [_P]),
+    ("sgr_ingest_set_value_framing", C.c_int32, [_P, C.c_int32]),
     ("sgr_ingest_set_null_value_type", C.c_int32, [_P, C.c_int32]),
     ("sgr_ingest_set_aborted", C.c_int32, [_P, C.c_int32, _P, _P, C.c_uint64]),
     ("sgr_ingest_record_batches", C.c_int32, [_P, C.c_int32, _P, C.c_uint64, C.POINTER(sgr_ingest_stats)]),

@@ -430,3 +430,54 @@ def test_state_topic_tombstones_become_events():
         ing.set_null_value_type(16)
     ing.set_null_value_type(-1)
     assert ing.record_batches(1, batch)["n_records"] == 2
+
+
+# ----------------------------------------------------------------------------- multilanguage protobuf framing
+def _pb_class(name):
+    """protobuf.State / protobuf.Event of modules/multilanguage-protocol/src/main/protobuf/multilanguage-protocol.proto:7-20, built
+    at run time with the protobuf runtime that ships in this image (an independent implementation of the wire format)."""
+    from google.protobuf import descriptor_pb2, descriptor_pool, message_factory
+
+    fdp = descriptor_pb2.FileDescriptorProto(name=f"{name}.proto", package="surge.multilanguage", syntax="proto3")
+    m = fdp.message_type.add(name=name)
+    m.field.add(name="aggregateId", number=1, type=descriptor_pb2.FieldDescriptorProto.TYPE_STRING, label=descriptor_pb2.FieldDescriptorProto.LABEL_OPTIONAL)
+    m.field.add(name="payload", number=2, type=descriptor_pb2.FieldDescriptorProto.TYPE_BYTES, label=descriptor_pb2.FieldDescriptorProto.LABEL_OPTIONAL)
+    pool = descriptor_pool.DescriptorPool()
+    pool.Add(fdp)
+    return message_factory.GetMessageClass(pool.FindMessageTypeByName(f"surge.multilanguage.{name}"))
+
+
+def test_multilanguage_protobuf_framing_matches_the_protobuf_runtime():
+    from surge_b200 import formats as F
+
+    State = _pb_class("State")
+    rng = np.random.default_rng(8)
+    for aid, n in [("", 0), ("a", 0), ("", 5), ("agg-1", 8), ("zażółć", 127), ("x" * 200, 128), ("id", 20000)]:
+        payload = rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+        want = State(aggregateId=aid, payload=payload).SerializeToString()
+        assert F.multilanguage_proto(aid, payload) == want
+        assert F.parse_multilanguage_proto(want) == (aid, payload)
+        back = State()
+        back.ParseFromString(F.multilanguage_proto(aid, payload))
+        assert (back.aggregateId, back.payload) == (aid, payload)
+
+
+def test_events_wrapped_in_protobuf_are_unwrapped_natively():
+    Event = _pb_class("Event")
+    evs = [("a", _event(0, 1, 5)), ("b", _event(1, 2, 7, bytes(range(40)))), ("a", _event(2, 3, 0))]
+    recs = [(d, aid.encode(), Event(aggregateId=aid, payload=p).SerializeToString()) for d, (aid, p) in enumerate(evs)]
+    # unknown fields and a field order no canonical writer produces must still parse (protobuf semantics)
+    odd = b"\x18\x07" + b"\x12\x0c" + _event(0, 4, 9) + b"\x0a\x01a" + b"\x25\x01\x02\x03\x04"
+    recs.append((3, b"a", odd))
+    plain = Ingest()
+    plain.record_batches(0, K.encode_record_batch(0, [(d, aid.encode(), p) for d, (aid, p) in enumerate(evs)] + [(3, b"a", _event(0, 4, 9))]))
+    ing = Ingest()
+    ing.set_value_framing(1)
+    st = ing.record_batches(0, K.encode_record_batch(0, recs, compression="lz4"))
+    assert st["n_records"] == 4 and np.array_equal(ing.pending(), plain.pending()) and ing.keys() == ["a", "b"]
+    for bad, why in [(b"\x12\x7f" + bytes(5), "not a protobuf Event"), (b"\x0a\x01a", "packed event value of 0 bytes"), (b"\x13", "not a protobuf Event")]:
+        with pytest.raises(IngestError) as ei:
+            ing.record_batches(0, K.encode_record_batch(4, [(0, b"k", bad)]))
+        assert why in str(ei.value)
+    with pytest.raises(IngestError):
+        ing.set_value_framing(7)
