@@ -312,8 +312,9 @@ int32_t sgr_dist_local_aggregates(sgr_engine* e, uint32_t* out, uint64_t cap, ui
  *   - records below the partition's decoded position are counted as duplicates and skipped (refetch after restart);
  *   - record value = the model's packed event: u32 type, u32 seq (little endian) + up to 48 payload bytes.
  * A malformed batch fails the whole call and leaves the pending log and the partition position untouched.
- * The byte formats are third-party (org.apache.kafka:kafka-clients:3.2.3, lz4 frame format) and the reference holds no
- * broker bytes: byte-level parity is UNPINNED (see oracle/kafka_batch.py).
+ * The RecordBatch framing is third-party (org.apache.kafka:kafka-clients:3.2.3) and the reference holds no broker bytes:
+ * its byte-level parity is UNPINNED (see oracle/kafka_batch.py); lz4, xxHash32, CRC-32C and the protobuf framing are pinned
+ * against real implementations.
  *
  * Lag gate (f2): actors trust the store only once the consumer group of the streams applicationId has no lag
  * (CORE/internal/kafka/KafkaProducerActorImpl.scala:530-540,684-708; COMMON/kafka/KafkaAdminClient.scala:36-56).

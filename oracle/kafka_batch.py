@@ -14,8 +14,9 @@ reference's tests hold no broker bytes:
   * LZ4 frame + block format (lz4 frame format 1.6.x) as written by KafkaLZ4BlockOutputStream for magic >= 2
     (FLG = 0x60: version 01, independent blocks, no checksums; BD = 0x40: 64 KiB blocks; correct header checksum).
   * CRC-32C (RFC 3720 appendix B.4 vectors) and xxHash32 (published vectors).
-What IS pinned: the published known-answer vectors of CRC-32C and xxHash32, and the two well-known LZ4 frame header
-checksum bytes (60 40 -> 82, 64 40 -> a7) — see tests/test_ingest_cpu.py.
+What IS pinned (tests/test_ingest_cpu.py): CRC-32C by the RFC 3720 vectors; xxHash32 by the `xxhash` package; the LZ4 frame
+and block codec by liblz4 itself (pyarrow's "lz4" codec: frames made by the library decode here, frames made here decode in the
+library); the record-batch FRAMING around them stays unpinned — no Kafka client exists in this image.
 """
 from __future__ import annotations
 

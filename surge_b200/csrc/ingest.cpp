@@ -8,9 +8,10 @@
 // (modules/command-engine/core/src/main/scala/surge/internal/kafka/KafkaProducerActorImpl.scala:321-329). The byte format
 // itself lives in a third-party dependency that is not under the reference checkout: org.apache.kafka:kafka-clients:3.2.3
 // (project/Dependencies.scala:42) — DefaultRecordBatch / DefaultRecord / KafkaLZ4BlockInputStream. No test of the
-// reference holds broker bytes, so byte-level parity of this decoder is UNPINNED; it is restated from the published
-// format (KIP-98 message format v2, LZ4 frame format 1.6.x, CRC-32C RFC 3720, xxHash32) and checked against an
-// independent encoder/decoder in oracle/kafka_batch.py plus the published known-answer vectors of CRC-32C / xxHash32.
+// reference holds broker bytes, so byte-level parity of the RecordBatch framing is UNPINNED; it is restated from the
+// published format (KIP-98 message format v2) and checked against an independent encoder/decoder in oracle/kafka_batch.py.
+// The layers below it are pinned against real implementations: lz4 frames by liblz4 (via pyarrow), xxHash32 by the xxhash
+// package, CRC-32C by the RFC 3720 vectors, the multilanguage protobuf framing by the protobuf runtime (tests/test_ingest_cpu.py).
 //
 // Host-only C++: the decode is byte parsing with data-dependent control flow on a few MB per poll; the fold it
 // feeds is the GPU path. Nothing here touches CUDA.

@@ -481,3 +481,47 @@ def test_events_wrapped_in_protobuf_are_unwrapped_natively():
         assert why in str(ei.value)
     with pytest.raises(IngestError):
         ing.set_value_framing(7)
+
+
+# ----------------------------------------------------------------------------- pinned against real implementations in the image
+def test_lz4_frames_from_liblz4_decode_and_ours_decode_with_liblz4(lib):
+    """pyarrow's "lz4" codec is liblz4's frame API — and writes exactly the header Kafka's producer does (FLG 0x60, BD 0x40,
+    HC 0x82). Frames made by the real library must decode through the product decoder and the Python restatement; frames made
+    by the restatement's compressor must decode through the real library."""
+    pa = pytest.importorskip("pyarrow")
+    codec = pa.Codec("lz4")
+    rng = np.random.default_rng(21)
+    cases = [b"", b"x", b"hello hello hello hello hello hello hello", b"\x00" * 300_000, _compressible(rng, 1_000_000),
+             rng.integers(0, 256, 70_000, dtype=np.uint8).tobytes(), _compressible(rng, 65_536), _compressible(rng, 65_537)]
+    for data in cases:
+        frame = codec.compress(data, asbytes=True)
+        if data:
+            # small inputs come out with Kafka's exact header; multi-block ones with linked blocks (FLG 0x40), which
+            # exercises matches that reach back into the previous block
+            assert frame[:4] == bytes.fromhex("04224d18") and frame[4] in (0x60, 0x40) and frame[5] == 0x40
+        rc, got = _lz4_decode(lib, frame)
+        assert rc == 0 and got == data
+        assert K.lz4_frame_decompress(frame) == data
+        ours = K.lz4_frame_compress(data)
+        assert codec.decompress(ours, decompressed_size=len(data), asbytes=True) == data
+    # a record batch whose records section was compressed by liblz4 (what a broker hands out) decodes like our own
+    recs = [(d, f"k{d % 5}:{d}".encode(), _event(d % 3, d, d)) for d in range(400)]
+    plain = K.encode_record_batch(0, recs)
+    body = codec.compress(plain[61:], asbytes=True)
+    tail = struct.pack(">h", 3) + plain[23:61] + body
+    batch = struct.pack(">qiib", 0, 9 + len(tail), 0, 2) + struct.pack(">I", K.crc32c(tail)) + tail
+    a, b = Ingest(), Ingest()
+    a.record_batches(0, plain)
+    assert b.record_batches(0, batch)["n_records"] == 400
+    assert np.array_equal(a.pending(), b.pending()) and a.keys() == b.keys()
+
+
+def test_xxh32_matches_the_xxhash_library(lib):
+    xxhash = pytest.importorskip("xxhash")
+    rng = np.random.default_rng(22)
+    for n in list(range(0, 40)) + [63, 64, 65, 1000, 4096, 100_003]:
+        d = rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+        for seed in (0, 1, 0xDEADBEEF):
+            want = xxhash.xxh32(d, seed=seed).intdigest()
+            buf = C.create_string_buffer(d, len(d)) if d else None
+            assert lib.sgr_xxh32(buf, len(d), seed) == want == K.xxh32(d, seed)
