@@ -379,7 +379,8 @@ int orc_fold_incremental(int model, const uint8_t* records, uint64_t n_records,
  *   stringHash(str, seed): h = seed; pairs of chars: data = (c0 << 16) + c1; h = mix(h, data)
  *                          odd tail: h = mixLast(h, c); finalizeHash(h, str.length)
  *   stringSeed = 0xf7ca7fd2
- * PARITY UNPINNED: the reference holds no known-answer vector for this hash. */
+ * PARITY UNPINNED against Scala itself: the reference holds no known-answer vector for this hash. Pinned against a real
+ * MurmurHash3_x86_32 through the byte-order / length-word bijection in tests/test_partition_hash_pin.py. */
 static uint32_t rotl32(uint32_t x, int r) { return (x << r) | (x >> (32 - r)); }
 static uint32_t mm3_mix_last(uint32_t h, uint32_t k) {
   k *= 0xcc9e2d51u; k = rotl32(k, 15); k *= 0x1b873593u; return h ^ k;

@@ -10,7 +10,8 @@
  * it cites, and is pinned against every golden vector the reference's own tests hold for
  * the path (tests/test_oracle_golden.py). Two items stay
  * "parity unpinned" because the reference holds no vector for them: the partition hash
- * (scala-library 2.13.8 MurmurHash3.stringHash, third-party) and serialized JSON bytes.
+ * (scala-library 2.13.8 MurmurHash3.stringHash, third-party — pinned one level down, to a real
+ * MurmurHash3_x86_32, by tests/test_partition_hash_pin.py) and serialized JSON bytes.
  *
  * Paths are relative to the reference checkout.
  */

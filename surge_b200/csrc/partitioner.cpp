@@ -5,7 +5,8 @@
 // over PartitionStringUpToColon: s.takeWhile(_ != ':')           (same file, :38-42)
 // The hash is scala-library 2.13.8's MurmurHash3.stringHash over UTF-16 code units (a
 // third-party dependency of the reference; the reference holds no known-answer vector for
-// it, so ownership parity is "unpinned" — see DESIGN.md). Folded state bytes never depend
+// it, so ownership parity is "unpinned" against Scala — tests/test_partition_hash_pin.py pins this code to a real
+// MurmurHash3_x86_32 instead). Folded state bytes never depend
 // on it; it only decides which rank owns an aggregate.
 #include <stdint.h>
 
