@@ -60,6 +60,7 @@ import struct  # noqa: E402
 import uuid  # noqa: E402
 
 from oracle import program_interp as I  # noqa: E402
+from surge_b200 import native as N  # noqa: E402
 from surge_b200 import programs as P  # noqa: E402
 
 
@@ -115,4 +116,30 @@ def test_program_interpreter_equals_c_oracle_on_bank_account(segments, priors):
                 init.view(np.uint8).reshape(-1, 64)[i] = 0
     want, _, _ = O.fold_packed(O.MODEL_BANK_ACCOUNT, O.REC_FIXED64, ev, off, init)
     got = I.fold(rules_of(P.bank_account_program()), 64, ev.reshape(-1, 64), off, None if init is None else init.view(np.uint8).reshape(-1, 64), f64_fields=[16])
+    assert np.array_equal(got, want.view(np.uint8).reshape(got.shape))
+
+
+@settings(max_examples=150, deadline=None)
+@given(st.lists(st.lists(st.tuples(st.integers(0, 5), st.integers(0, 70), st.integers(-2**31, 2**31 - 1)), max_size=6), min_size=1, max_size=4),
+       st.integers(0, 3), st.booleans())
+def test_variable_record_interpreter_equals_c_oracle(segments, cut, corrupt_len):
+    """fold_var (the checker of the variable-record program fuzz) against the C oracle's VAR16 decoding of the Counter model:
+    payloads of any length (too short for `by` -> the event throws), a truncated tail, a length field that lies."""
+    rules = rules_of(P.counter_program(N.REC_VAR16))
+    buf = bytearray()
+    seg = [0]
+    for i, events in enumerate(segments):
+        for k, (t, plen, by) in enumerate(events):
+            payload = (struct.pack("<i", by) + bytes(plen))[:plen]
+            buf += struct.pack("<IIII", t, k + 1, plen, i) + payload + bytes((-plen) % 16)
+        seg.append(len(buf))
+    if corrupt_len and len(buf) >= 16:
+        struct.pack_into("<I", buf, 8, struct.unpack_from("<I", buf, 8)[0] + 64)     # the first record claims 64 more bytes than it has
+    if cut and seg[-1] - seg[-2] >= 32:
+        seg[-1] -= 16                                                                  # the last segment ends inside its last record
+        del buf[seg[-1]:]
+    ev = np.frombuffer(bytes(buf), np.uint8) if buf else np.zeros(0, np.uint8)
+    off = np.asarray(seg, dtype=np.uint64)
+    want, _, _ = O.fold_packed(O.MODEL_COUNTER, O.REC_VAR16, ev, off)
+    got = I.fold_var(rules, 16, ev, off)
     assert np.array_equal(got, want.view(np.uint8).reshape(got.shape))
