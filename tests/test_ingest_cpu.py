@@ -525,3 +525,18 @@ def test_xxh32_matches_the_xxhash_library(lib):
             want = xxhash.xxh32(d, seed=seed).intdigest()
             buf = C.create_string_buffer(d, len(d)) if d else None
             assert lib.sgr_xxh32(buf, len(d), seed) == want == K.xxh32(d, seed)
+
+
+def test_kafka_varints_are_protobuf_zigzag_varints():
+    """ByteUtils.writeVarint / writeVarlong (kafka-clients) are protobuf's sint32 / sint64 encoding; the protobuf runtime in the
+    image pins the restatement's encoder, whose output the product decoder parses in every other test of this file."""
+    enc = pytest.importorskip("google.protobuf.internal.encoder")
+    wf = pytest.importorskip("google.protobuf.internal.wire_format")
+    rng = np.random.default_rng(4)
+    ints = [0, 1, -1, 63, 64, -64, -65, 127, 128, 300, 2**31 - 1, -2**31] + rng.integers(-2**31, 2**31, 200).tolist()
+    for v in ints:
+        assert K.varint(int(v)) == enc._VarintBytes(wf.ZigZagEncode(int(v)))
+        assert K.read_varint(K.varint(int(v)), 0)[0] == int(v)
+    longs = [2**63 - 1, -2**63, 2**40, -2**40] + rng.integers(-2**62, 2**62, 200).tolist()
+    for v in ints + longs:
+        assert K.varlong(int(v)) == enc._VarintBytes(wf.ZigZagEncode(int(v)))
