@@ -348,7 +348,31 @@ const char* sgr_ingest_last_error(const sgr_ingest* g);
  * event is its payload. The framing is pinned against the protobuf runtime in tests/test_ingest_cpu.py. */
 #define SGR_VALUE_PACKED          0
 #define SGR_VALUE_PROTOBUF_EVENT  1
+#define SGR_VALUE_JSON            2
 int32_t sgr_ingest_set_value_framing(sgr_ingest* g, int32_t framing);
+
+/* SGR_VALUE_JSON: the value is a flat JSON object as the reference's sample models write their events with play-json,
+ * e.g. {"_type":"...CountIncremented","aggregateId":"a","incrementBy":1,"sequenceNumber":4}
+ * (modules/command-engine/core/src/test/scala/surge/core/TestBoundedContext.scala:44-56 formats, :159-161 writer).
+ * The model registers the discriminator member, the event type index of each class name and where each numeric member
+ * lands in the packed record (record byte offsets: 4 = the sequence number, 16..63 = payload). Members are found by name —
+ * order, whitespace and extra members do not matter; an unknown class name becomes event type `unknown_type` (a
+ * scala.MatchError in the handler) or, with -1, fails the call. Doubles are parsed correctly rounded (strtod), as
+ * java.lang.Double.parseDouble does. The exact bytes play-json writes are NOT pinned (no JVM here); the parser is checked
+ * against Python's json module on both well-formed and hostile input. */
+#define SGR_JSON_I32 0u
+#define SGR_JSON_I64 1u
+#define SGR_JSON_F64 2u
+#define SGR_JSON_MAX_FIELDS 8u
+typedef struct sgr_json_field { const char* name; uint8_t kind; uint8_t reserved; uint16_t dst_off; uint32_t reserved2; } sgr_json_field;
+typedef struct sgr_json_event {
+  const char* type_name;     /* value of the discriminator member */
+  uint32_t event_type;       /* index into the fold program's rules */
+  uint32_t n_fields;
+  sgr_json_field fields[SGR_JSON_MAX_FIELDS];
+} sgr_json_event;
+int32_t sgr_ingest_set_json_packer(sgr_ingest* g, const char* discriminator, const sgr_json_event* events, uint32_t n_events,
+                                   int32_t unknown_type);
 /* Compacted STATE topic (what the reference restores from today, COMMON/kafka/streams/SurgeStateStoreConsumer.scala:57-76): a keyed
  * record with a null value deletes the key (CORE/internal/SurgeModel.scala:62-64). With event_type >= 0 such a record becomes an
  * event of that type (the program's SGR_TOMBSTONE rule) instead of being dropped; -1 (default) drops it. */

@@ -15,6 +15,7 @@
 //
 // Host-only C++: the decode is byte parsing with data-dependent control flow on a few MB per poll; the fold it
 // feeds is the GPU path. Nothing here touches CUDA.
+#include <errno.h>
 #include <stdarg.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -429,6 +430,202 @@ struct RawBuf {
   }
 };
 
+// ------------------------------------------------------------------ flat JSON event -> packed event (SGR_VALUE_JSON)
+// The reference's sample models write their events as play-json objects, e.g. (core TestBoundedContext.scala:44-56,153-161)
+//   {"_type":"...CountIncremented","aggregateId":"a","incrementBy":1,"sequenceNumber":4}
+// A model registers which member is the class discriminator, which event type index each class name maps to, and which
+// numeric members land at which byte of the packed record. Members are looked up by name: order and extra members do not matter.
+struct JsonFieldSpec { std::string name; uint8_t kind; uint16_t dst_off; };
+struct JsonEventSpec { std::string type_name; uint32_t event_type; std::vector<JsonFieldSpec> fields; };
+struct JsonPacker {
+  std::string discriminator;
+  std::vector<JsonEventSpec> events;
+  int32_t unknown_type = -1;          // >= 0: an unknown class name becomes this event type (a scala.MatchError in the handler)
+};
+
+struct JsonMember { const uint8_t* key; uint32_t key_len; bool key_escaped; const uint8_t* val; uint32_t val_len; char kind; };  // kind: s n o a t f z
+
+struct JsonScan {
+  const uint8_t* p; const uint8_t* end; const char* err = nullptr;
+  void ws() { while (p < end && (*p == ' ' || *p == '\t' || *p == '\n' || *p == '\r')) ++p; }
+  // p at the opening quote; leaves p after the closing quote; [*b, *b + *n) is the raw content between the quotes
+  bool string(const uint8_t** b, uint32_t* n, bool* escaped) {
+    if (p >= end || *p != '"') { err = "expected a string"; return false; }
+    ++p; *b = p; *escaped = false;
+    while (p < end && *p != '"') {
+      if (*p < 0x20) { err = "control character inside a string"; return false; }
+      if (*p == '\\') { *escaped = true; ++p; if (p >= end) break; }
+      ++p;
+    }
+    if (p >= end) { err = "unterminated string"; return false; }
+    *n = (uint32_t)(p - *b); ++p;
+    return true;
+  }
+  bool value(JsonMember* m, int depth) {
+    ws();
+    if (p >= end) { err = "value expected"; return false; }
+    m->val = p;
+    const uint8_t c = *p;
+    if (c == '"') {
+      const uint8_t* b; uint32_t n; bool esc;
+      if (!string(&b, &n, &esc)) return false;
+      m->kind = 's'; m->val = b; m->val_len = n;
+      if (esc) m->kind = 'S';   // string with escapes: compared after unescaping
+      return true;
+    }
+    if (c == '{' || c == '[') {
+      if (depth > 32) { err = "nesting too deep"; return false; }
+      const uint8_t close = c == '{' ? '}' : ']';
+      ++p; ws();
+      if (p < end && *p == close) { ++p; m->kind = c == '{' ? 'o' : 'a'; m->val_len = (uint32_t)(p - m->val); return true; }
+      for (;;) {
+        if (c == '{') {
+          ws();
+          const uint8_t* b; uint32_t n; bool esc;
+          if (!string(&b, &n, &esc)) return false;
+          ws();
+          if (p >= end || *p != ':') { err = "':' expected"; return false; }
+          ++p;
+        }
+        JsonMember inner{};
+        if (!value(&inner, depth + 1)) return false;
+        ws();
+        if (p < end && *p == ',') { ++p; continue; }
+        if (p < end && *p == close) { ++p; break; }
+        err = "',' or a closing bracket expected"; return false;
+      }
+      m->kind = c == '{' ? 'o' : 'a'; m->val_len = (uint32_t)(p - m->val);
+      return true;
+    }
+    if (c == '-' || (c >= '0' && c <= '9')) {
+      const uint8_t* q = p;
+      if (*q == '-') ++q;
+      if (q >= end || *q < '0' || *q > '9') { err = "malformed number"; return false; }
+      if (*q == '0') ++q; else while (q < end && *q >= '0' && *q <= '9') ++q;
+      if (q < end && *q == '.') { ++q; if (q >= end || *q < '0' || *q > '9') { err = "malformed number"; return false; } while (q < end && *q >= '0' && *q <= '9') ++q; }
+      if (q < end && (*q == 'e' || *q == 'E')) {
+        ++q; if (q < end && (*q == '+' || *q == '-')) ++q;
+        if (q >= end || *q < '0' || *q > '9') { err = "malformed number"; return false; }
+        while (q < end && *q >= '0' && *q <= '9') ++q;
+      }
+      m->kind = 'n'; m->val_len = (uint32_t)(q - p); p = q;
+      return true;
+    }
+    auto lit = [&](const char* w, char k) { const size_t n = strlen(w); if ((size_t)(end - p) >= n && memcmp(p, w, n) == 0) { p += n; m->kind = k; m->val_len = (uint32_t)n; return true; } return false; };
+    if (lit("true", 't') || lit("false", 'f') || lit("null", 'z')) return true;
+    err = "unexpected character";
+    return false;
+  }
+};
+
+// JSON string content (between the quotes) -> bytes; \uXXXX incl. surrogate pairs -> UTF-8
+bool json_unescape(const uint8_t* b, uint32_t n, std::string* out) {
+  out->clear();
+  auto hex4 = [&](uint32_t i, uint32_t* v) { if (i + 4 > n) return false; *v = 0; for (int k = 0; k < 4; ++k) { const uint8_t c = b[i + k]; uint32_t d; if (c >= '0' && c <= '9') d = c - '0'; else if (c >= 'a' && c <= 'f') d = c - 'a' + 10; else if (c >= 'A' && c <= 'F') d = c - 'A' + 10; else return false; *v = *v * 16 + d; } return true; };
+  for (uint32_t i = 0; i < n; ++i) {
+    if (b[i] != '\\') { out->push_back((char)b[i]); continue; }
+    if (++i >= n) return false;
+    switch (b[i]) {
+      case '"': out->push_back('"'); break;   case '\\': out->push_back('\\'); break; case '/': out->push_back('/'); break;
+      case 'b': out->push_back('\b'); break;  case 'f': out->push_back('\f'); break;  case 'n': out->push_back('\n'); break;
+      case 'r': out->push_back('\r'); break;  case 't': out->push_back('\t'); break;
+      case 'u': {
+        uint32_t cp;
+        if (!hex4(i + 1, &cp)) return false;
+        i += 4;
+        if (cp >= 0xD800 && cp < 0xDC00 && i + 6 < n + 0u && b[i + 1] == '\\' && b[i + 2] == 'u') {
+          uint32_t lo;
+          if (hex4(i + 3, &lo) && lo >= 0xDC00 && lo < 0xE000) { cp = 0x10000 + ((cp - 0xD800) << 10) + (lo - 0xDC00); i += 6; }
+        }
+        if (cp < 0x80) out->push_back((char)cp);
+        else if (cp < 0x800) { out->push_back((char)(0xC0 | (cp >> 6))); out->push_back((char)(0x80 | (cp & 0x3F))); }
+        else if (cp < 0x10000) { out->push_back((char)(0xE0 | (cp >> 12))); out->push_back((char)(0x80 | ((cp >> 6) & 0x3F))); out->push_back((char)(0x80 | (cp & 0x3F))); }
+        else { out->push_back((char)(0xF0 | (cp >> 18))); out->push_back((char)(0x80 | ((cp >> 12) & 0x3F))); out->push_back((char)(0x80 | ((cp >> 6) & 0x3F))); out->push_back((char)(0x80 | (cp & 0x3F))); }
+        break;
+      }
+      default: return false;
+    }
+  }
+  return true;
+}
+
+bool json_name_is(const uint8_t* b, uint32_t n, bool escaped, const std::string& want, std::string* tmp) {
+  if (!escaped) return n == want.size() && memcmp(b, want.data(), n) == 0;
+  return json_unescape(b, n, tmp) && *tmp == want;
+}
+
+// value bytes -> the 56 bytes the record parser copies into the packed record (type, seq, payload). Returns nullptr on success.
+const char* json_pack(const JsonPacker& jp, const uint8_t* val, uint32_t val_len, uint8_t out[56], std::string* tmp) {
+  JsonScan sc{val, val + val_len};
+  JsonMember members[48];
+  uint32_t n_members = 0;
+  sc.ws();
+  if (sc.p >= sc.end || *sc.p != '{') return "the value is not a JSON object";
+  ++sc.p; sc.ws();
+  if (sc.p < sc.end && *sc.p == '}') { ++sc.p; }
+  else {
+    for (;;) {
+      sc.ws();
+      JsonMember m{};
+      if (!sc.string(&m.key, &m.key_len, &m.key_escaped)) return sc.err;
+      sc.ws();
+      if (sc.p >= sc.end || *sc.p != ':') return "':' expected";
+      ++sc.p;
+      if (!sc.value(&m, 1)) return sc.err;
+      if (n_members >= 48) return "more than 48 members";
+      members[n_members++] = m;
+      sc.ws();
+      if (sc.p < sc.end && *sc.p == ',') { ++sc.p; continue; }
+      if (sc.p < sc.end && *sc.p == '}') { ++sc.p; break; }
+      return "',' or '}' expected";
+    }
+  }
+  sc.ws();
+  if (sc.p != sc.end) return "bytes after the JSON object";
+  // later duplicates of a member win, as in play-json's JsObject
+  auto find = [&](const std::string& name) -> const JsonMember* {
+    const JsonMember* hit = nullptr;
+    for (uint32_t i = 0; i < n_members; ++i) if (json_name_is(members[i].key, members[i].key_len, members[i].key_escaped, name, tmp)) hit = &members[i];
+    return hit;
+  };
+  const JsonMember* d = find(jp.discriminator);
+  if (!d || (d->kind != 's' && d->kind != 'S')) return "the class discriminator member is missing or not a string";
+  const JsonEventSpec* ev = nullptr;
+  std::string cls;
+  for (const JsonEventSpec& e : jp.events) if (json_name_is(d->val, d->val_len, d->kind == 'S', e.type_name, &cls)) { ev = &e; break; }
+  memset(out, 0, 56);
+  if (!ev) {
+    if (jp.unknown_type < 0) return "unknown event class";
+    const uint32_t ty = (uint32_t)jp.unknown_type;
+    memcpy(out, &ty, 4);
+    return nullptr;
+  }
+  memcpy(out, &ev->event_type, 4);
+  for (const JsonFieldSpec& f : ev->fields) {
+    const JsonMember* m = find(f.name);
+    if (!m || m->kind != 'n') return "a numeric member of the event is missing or not a number";
+    char num[64];
+    if (m->val_len >= sizeof num) return "number too long";
+    memcpy(num, m->val, m->val_len); num[m->val_len] = 0;
+    uint8_t* dst = out + (f.dst_off < 8 ? f.dst_off : f.dst_off - 8);   // record offsets 0..7 = type, seq; 16.. = payload (value bytes 8..)
+    if (f.kind == 2) {
+      const double v = strtod(num, nullptr);      // correctly rounded, like java.lang.Double.parseDouble
+      memcpy(dst, &v, 8);
+    } else {
+      bool integral = true;
+      for (uint32_t i = 0; i < m->val_len; ++i) if (num[i] == '.' || num[i] == 'e' || num[i] == 'E') integral = false;
+      if (!integral) return "an integer member holds a fraction or an exponent";
+      errno = 0;
+      char* endp = nullptr;
+      const long long v = strtoll(num, &endp, 10);
+      if (errno || *endp) return "integer out of range";
+      if (f.kind == 0) { if (v < INT32_MIN || v > INT32_MAX) return "integer does not fit an Int"; const int32_t w = (int32_t)v; memcpy(dst, &w, 4); }
+      else memcpy(dst, &v, 8);
+    }
+  }
+  return nullptr;
+}
+
 struct ProbeOut {                 // one worker's probe results: (record position, dense index or provisional) per fetch
   std::vector<uint32_t> pos, val;
   std::vector<size_t> off;        // n_fetches + 1
@@ -455,6 +652,8 @@ struct Staged {
   int32_t rc = SGR_OK;
   int32_t null_value_type = -1;
   int32_t value_framing = 0;
+  const JsonPacker* json = nullptr;
+  std::string json_tmp;
   std::string err;
   void reset() { recs.clear(); keys.clear(); arena.clear(); shard.clear(); memset(shard_count, 0, sizeof shard_count); scratch.clear(); st = sgr_ingest_stats{}; rc = SGR_OK; err.clear(); }
 };
@@ -472,7 +671,8 @@ struct sgr_ingest {
   std::map<int32_t, PartitionState> parts;
   sgr_ingest_stats total{};
   uint64_t keys_at_mark = 0;
-  int32_t value_framing = 0;        // SGR_VALUE_PACKED | SGR_VALUE_PROTOBUF_EVENT
+  int32_t value_framing = 0;        // SGR_VALUE_PACKED | SGR_VALUE_PROTOBUF_EVENT | SGR_VALUE_JSON
+  JsonPacker json;
   int32_t null_value_type = -1;     // >= 0: a keyed record with a null value becomes an event of this type (state-topic tombstones)
   std::vector<Staged> pool;         // staging buffers, reused across calls (a restore loop polls similar sizes)
 };
@@ -519,8 +719,33 @@ int32_t sgr_ingest_destroy(sgr_ingest* g) { delete g; return SGR_OK; }
 
 const char* sgr_ingest_last_error(const sgr_ingest* g) { return g ? g->last_error.c_str() : "null ingest handle"; }
 
+int32_t sgr_ingest_set_json_packer(sgr_ingest* g, const char* discriminator, const sgr_json_event* events, uint32_t n_events, int32_t unknown_type) {
+  if (!g || !discriminator || (n_events && !events)) return ifail(g, SGR_ERR_INVALID, "null argument");
+  if (unknown_type >= (int32_t)SGR_MAX_TYPES) return ifail(g, SGR_ERR_INVALID, "unknown_type out of range");
+  JsonPacker jp;
+  jp.discriminator = discriminator;
+  jp.unknown_type = unknown_type < 0 ? -1 : unknown_type;
+  for (uint32_t i = 0; i < n_events; ++i) {
+    const sgr_json_event& e = events[i];
+    if (!e.type_name || e.event_type >= SGR_MAX_TYPES || e.n_fields > SGR_JSON_MAX_FIELDS) return ifail(g, SGR_ERR_INVALID, "JSON event %u: bad type name, type index or field count", i);
+    JsonEventSpec es{e.type_name, e.event_type, {}};
+    for (uint32_t f = 0; f < e.n_fields; ++f) {
+      const sgr_json_field& jf = e.fields[f];
+      const uint32_t size = jf.kind == SGR_JSON_I32 ? 4u : 8u;
+      // a member may land on the sequence number (+4) or anywhere in the payload (+16 .. +64); never on type or agg
+      const bool ok = jf.name && jf.kind <= SGR_JSON_F64 && jf.dst_off % 4 == 0 && ((jf.dst_off == 4 && size == 4) || (jf.dst_off >= 16 && jf.dst_off + size <= 64));
+      if (!ok) return ifail(g, SGR_ERR_INVALID, "JSON event %u field %u: bad name, kind or record offset", i, f);
+      es.fields.push_back(JsonFieldSpec{jf.name, jf.kind, jf.dst_off});
+    }
+    jp.events.push_back(es);
+  }
+  g->json = jp;
+  return SGR_OK;
+}
+
 int32_t sgr_ingest_set_value_framing(sgr_ingest* g, int32_t framing) {
-  if (!g || (framing != SGR_VALUE_PACKED && framing != SGR_VALUE_PROTOBUF_EVENT)) return ifail(g, SGR_ERR_INVALID, "unknown value framing %d", framing);
+  if (!g || (framing != SGR_VALUE_PACKED && framing != SGR_VALUE_PROTOBUF_EVENT && framing != SGR_VALUE_JSON)) return ifail(g, SGR_ERR_INVALID, "unknown value framing %d", framing);
+  if (framing == SGR_VALUE_JSON && g->json.discriminator.empty()) return ifail(g, SGR_ERR_INVALID, "register a JSON packer first (sgr_ingest_set_json_packer)");
   g->value_framing = framing;
   return SGR_OK;
 }
@@ -664,6 +889,12 @@ int32_t decode_fetch(int32_t partition, const uint8_t* buf, uint64_t nbytes, Sta
           }
           if (!pb.ok) return sfail(o, SGR_ERR_INVALID, "partition %d offset %lld: value is not a protobuf Event", partition, (long long)offset);
           val = payload; val_len = (int32_t)(payload_len > 0x7fffffff ? 0x7fffffff : payload_len);
+        }
+        uint8_t json_out[56];
+        if (val_len >= 0 && o->value_framing == SGR_VALUE_JSON) {
+          const char* why = json_pack(*o->json, val, (uint32_t)val_len, json_out, &o->json_tmp);
+          if (why) return sfail(o, SGR_ERR_INVALID, "partition %d offset %lld: JSON event: %s", partition, (long long)offset, why);
+          val = json_out; val_len = 56;
         }
         if (val_len >= 0 && (val_len < 8 || val_len > 56)) return sfail(o, SGR_ERR_INVALID, "partition %d offset %lld: packed event value of %d bytes (expected 8..56: u32 type, u32 seq, payload)", partition, (long long)offset, val_len);
         uint32_t id_len = 0;
@@ -819,6 +1050,7 @@ int32_t sgr_ingest_record_batches_mt(sgr_ingest* g, uint32_t n, const int32_t* p
       staged[i].ps = *from;
       staged[i].null_value_type = g->null_value_type;
       staged[i].value_framing = g->value_framing;
+      staged[i].json = &g->json;
       if (decode_fetch(partitions[i], (const uint8_t*)datas[i], nbytes[i], &staged[i]) != SGR_OK) return;
       from = &staged[i].ps;
     }

@@ -60,6 +60,22 @@ class Ingest:
         """0 = the value is the packed event; 1 = protobuf Event{aggregateId, payload} of the multilanguage module."""
         self._check(self._lib.sgr_ingest_set_value_framing(self._h, framing))
 
+    def set_json_packer(self, discriminator: str, events: Sequence[Tuple[str, int, Sequence[Tuple[str, int, int]]]], unknown_type: int = -1) -> None:
+        """events = [(class name, event type index, [(member name, N.JSON_I32 | JSON_I64 | JSON_F64, record byte offset)])].
+        Switches nothing by itself: follow with set_value_framing(N.VALUE_JSON)."""
+        arr = (N.sgr_json_event * max(len(events), 1))()
+        for i, (type_name, event_type, fields) in enumerate(events):
+            arr[i].type_name = type_name.encode("utf-8")
+            arr[i].event_type = event_type
+            arr[i].n_fields = len(fields)
+            if len(fields) > 8:
+                raise IngestError(N.SGR_ERR_INVALID, "at most 8 numeric members per event")
+            for j, (name, kind, dst_off) in enumerate(fields):
+                arr[i].fields[j].name = name.encode("utf-8")
+                arr[i].fields[j].kind = kind
+                arr[i].fields[j].dst_off = dst_off
+        self._check(self._lib.sgr_ingest_set_json_packer(self._h, discriminator.encode("utf-8"), arr, len(events), unknown_type))
+
     def set_null_value_type(self, event_type: int) -> None:
         """State-topic mode: null-valued records become events of `event_type` (the program's tombstone rule); -1 drops them."""
         self._check(self._lib.sgr_ingest_set_null_value_type(self._h, event_type))

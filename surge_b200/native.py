@@ -76,6 +76,17 @@ class sgr_ingest_stats(C.Structure):
                                           "n_compressed_bytes", "n_decompressed_bytes")] + [("reserved", C.c_uint64 * 3)]
 
 
+class sgr_json_field(C.Structure):
+    _fields_ = [("name", C.c_char_p), ("kind", C.c_uint8), ("reserved", C.c_uint8), ("dst_off", C.c_uint16), ("reserved2", C.c_uint32)]
+
+
+class sgr_json_event(C.Structure):
+    _fields_ = [("type_name", C.c_char_p), ("event_type", C.c_uint32), ("n_fields", C.c_uint32), ("fields", sgr_json_field * 8)]
+
+
+JSON_I32, JSON_I64, JSON_F64 = 0, 1, 2
+VALUE_PACKED, VALUE_PROTOBUF_EVENT, VALUE_JSON = 0, 1, 2
+
 # every symbol include/sgr.h declares: (name, restype, argtypes)
 _P = C.c_void_p
 ABI = [
@@ -123,6 +134,7 @@ ABI = [
     ("sgr_ingest_destroy", C.c_int32, [_P]),
     ("sgr_ingest_last_error", C.c_char_p, [_P]),
     ("sgr_ingest_set_value_framing", C.c_int32, [_P, C.c_int32]),
+    ("sgr_ingest_set_json_packer", C.c_int32, [_P, C.c_char_p, C.POINTER(sgr_json_event), C.c_uint32, C.c_int32]),
     ("sgr_ingest_set_null_value_type", C.c_int32, [_P, C.c_int32]),
     ("sgr_ingest_set_aborted", C.c_int32, [_P, C.c_int32, _P, _P, C.c_uint64]),
     ("sgr_ingest_record_batches", C.c_int32, [_P, C.c_int32, _P, C.c_uint64, C.POINTER(sgr_ingest_stats)]),

@@ -540,3 +540,91 @@ def test_kafka_varints_are_protobuf_zigzag_varints():
     longs = [2**63 - 1, -2**63, 2**40, -2**40] + rng.integers(-2**62, 2**62, 200).tolist()
     for v in ints + longs:
         assert K.varlong(int(v)) == enc._VarintBytes(wf.ZigZagEncode(int(v)))
+
+
+# ----------------------------------------------------------------------------- JSON-valued events (play-json style)
+import json  # noqa: E402
+
+COUNTER_JSON = [("surge.core.TestBoundedContext.CountIncremented", 0, [("incrementBy", N.JSON_I32, 16), ("sequenceNumber", N.JSON_I32, 4)]),
+                ("surge.core.TestBoundedContext.CountDecremented", 1, [("decrementBy", N.JSON_I32, 16), ("sequenceNumber", N.JSON_I32, 4)]),
+                ("surge.core.TestBoundedContext.NoOpEvent", 2, [("sequenceNumber", N.JSON_I32, 4)])]
+
+
+def _json_ingest(unknown_type=3):
+    ing = Ingest()
+    ing.set_json_packer("_type", COUNTER_JSON, unknown_type=unknown_type)
+    ing.set_value_framing(N.VALUE_JSON)
+    return ing
+
+
+def test_json_events_pack_like_hand_packed_ones():
+    """The reference's own test model writes Json.toJson(evt) (core TestBoundedContext.scala:159-161); whatever the member
+    order or spacing, the packed record must equal the hand-packed one."""
+    rng = np.random.default_rng(55)
+    recs_json, recs_packed = [], []
+    for d in range(300):
+        t = int(rng.integers(0, 4))
+        by, seq = int(rng.integers(-2**31, 2**31)), int(rng.integers(0, 2**31))
+        aid = f"agg-{int(rng.integers(0, 40))}"
+        name = ["CountIncremented", "CountDecremented", "NoOpEvent", "SomethingElse"][t]
+        obj = {"_type": f"surge.core.TestBoundedContext.{name}", "aggregateId": aid, "sequenceNumber": seq}
+        if t == 0:
+            obj["incrementBy"] = by
+        if t == 1:
+            obj["decrementBy"] = by
+        items = list(obj.items()) + [("extra", {"nested": [1, "two", {"x": None}], "s": 'a"b\\'}), ("flag", True)]
+        rng.shuffle(items)                                        # member order must not matter
+        text = json.dumps(dict(items), separators=((",", ":") if d % 2 else (", ", " : ")), ensure_ascii=bool(d % 3))
+        recs_json.append((d, f"{aid}:{seq}".encode(), text.encode("utf-8")))
+        packed = struct.pack("<II", t, seq if t < 3 else 0) + (struct.pack("<i", by) if t < 2 else b"")
+        recs_packed.append((d, f"{aid}:{seq}".encode(), packed))
+    a, b = _json_ingest(), Ingest()
+    a.record_batches(0, K.encode_record_batch(0, recs_json, compression="lz4"))
+    b.record_batches(0, K.encode_record_batch(0, recs_packed))
+    assert np.array_equal(a.pending(), b.pending()) and a.keys() == b.keys()
+
+
+def test_json_values_numbers_escapes_and_errors():
+    f64 = Ingest()
+    f64.set_json_packer("t", [("Upd\u00e9", 1, [("newBalance", N.JSON_F64, 32), ("big", N.JSON_I64, 40)])])    # class name "Updé"
+    f64.set_value_framing(N.VALUE_JSON)
+    cases = [0.1, -0.0, 1e300, 5e-324, 2.2250738585072014e-308, 123456789.12345679, 1.0]
+    # ensure_ascii=True writes the class name as "Upd\\u00e9" inside the JSON text: it must match after unescaping
+    recs = [(d, b"k", json.dumps({"t": "Upd\u00e9", "newBalance": v, "big": -2**63 + d}, ensure_ascii=bool(d % 2)).encode("utf-8")) for d, v in enumerate(cases)]
+    assert b"\\u00e9" in recs[1][2] and "Upd\u00e9".encode("utf-8") in recs[0][2]
+    f64.record_batches(0, K.encode_record_batch(0, recs))
+    p = f64.pending()
+    assert p[:, 32:40].copy().view("<f8").ravel().tolist() == cases
+    assert struct.pack("<d", float(p[1, 32:40].copy().view("<f8")[0])) == struct.pack("<d", -0.0)
+    assert p[:, 40:48].copy().view("<i8").ravel().tolist() == [-2**63 + d for d in range(len(cases))]
+    assert p[:, 0:4].copy().view("<u4").ravel().tolist() == [1] * len(cases)
+
+    ing = _json_ingest(unknown_type=-1)
+
+    def refused(value: bytes, why: str):
+        with pytest.raises(IngestError) as ei:
+            ing.record_batches(0, K.encode_record_batch(0, [(0, b"k", value)]))
+        assert why in str(ei.value), str(ei.value)
+        assert len(ing.pending()) == 0
+
+    T = "surge.core.TestBoundedContext.CountIncremented"
+    refused(b'{"_type":"%s","incrementBy":1.5,"sequenceNumber":1}' % T.encode(), "fraction or an exponent")
+    refused(b'{"_type":"%s","incrementBy":2147483648,"sequenceNumber":1}' % T.encode(), "does not fit an Int")
+    refused(b'{"_type":"%s","incrementBy":"1","sequenceNumber":1}' % T.encode(), "missing or not a number")
+    refused(b'{"_type":"%s","sequenceNumber":1}' % T.encode(), "missing or not a number")
+    refused(b'{"_type":"nope","sequenceNumber":1}', "unknown event class")
+    refused(b'{"sequenceNumber":1}', "discriminator member is missing")
+    refused(b'[1,2]', "not a JSON object")
+    refused(b'{"_type":"%s","incrementBy":1,"sequenceNumber":1} x' % T.encode(), "bytes after the JSON object")
+    refused(b'{"_type":"%s","incrementBy":01,"sequenceNumber":1}' % T.encode(), "expected")
+    refused(b'{"_type":"%s","incrementBy":1,"sequenceNumber":1' % T.encode(), "expected")
+    refused(b'{"_type":"%s" "incrementBy":1}' % T.encode(), "expected")
+    refused(b'{"a":"unterminated', "unterminated string")
+    # a later duplicate member wins (JsObject semantics), nested look-alikes are not members
+    ok = b'{"x":{"_type":"nope","incrementBy":9},"_type":"nope","_type":"%s","incrementBy":7,"incrementBy":8,"sequenceNumber":2}' % T.encode()
+    ing.record_batches(0, K.encode_record_batch(0, [(0, b"k", ok)]))
+    assert ing.pending()[0, 16:20].copy().view("<i4")[0] == 8 and ing.pending()[0, 4:8].copy().view("<u4")[0] == 2
+    with pytest.raises(IngestError):
+        Ingest().set_value_framing(N.VALUE_JSON)                  # no packer registered
+    with pytest.raises(IngestError):
+        Ingest().set_json_packer("_type", [("A", 0, [("x", N.JSON_I32, 8)])])   # would overwrite the aggregate index
