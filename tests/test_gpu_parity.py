@@ -882,3 +882,42 @@ def test_state_topic_restore_from_raw_record_batches():
                 if want is not None:
                     assert tuple(np.frombuffer(got, "<i4").tolist()) == want
         assert ing.offsets(0) == (off, off)
+
+
+def test_json_events_of_the_reference_test_model_fold_to_its_golden_states():
+    """The reference's own Counter test model writes Json.toJson(evt) to the events topic (core TestBoundedContext.scala:159-161)
+    and its specs pin (3,3) -Incr(1, seq 4)-> (4,4) -Incr(1, seq 5)-> (5,5) (PersistentActorSpec.scala:140-145,181) and the
+    multilanguage None -> (1,1) -> (2,2) -Decr-> (1,3) (MultilanguageGatewayServiceImplSpec.scala:72-136): JSON bytes in,
+    golden states out, nothing re-encoded on the host."""
+    import json
+
+    from oracle import kafka_batch as K
+    from surge_b200.ingest import Ingest
+
+    cls = "surge.core.TestBoundedContext."
+    ing = Ingest()
+    ing.set_json_packer("_type", [(cls + "CountIncremented", 0, [("incrementBy", N.JSON_I32, 16), ("sequenceNumber", N.JSON_I32, 4)]),
+                                  (cls + "CountDecremented", 1, [("decrementBy", N.JSON_I32, 16), ("sequenceNumber", N.JSON_I32, 4)]),
+                                  (cls + "NoOpEvent", 2, [("sequenceNumber", N.JSON_I32, 4)])], unknown_type=3)
+    ing.set_value_framing(N.VALUE_JSON)
+
+    def ev(name, agg, seq, **kw):
+        return (f"{agg}:{seq}".encode(), json.dumps({"_type": cls + name, "aggregateId": agg, **kw, "sequenceNumber": seq}, separators=(",", ":")).encode())
+
+    events = [ev("CountIncremented", "a", s, incrementBy=1) for s in (1, 2, 3, 4, 5)]
+    events += [ev("CountIncremented", "ml", 1, incrementBy=1), ev("CountIncremented", "ml", 2, incrementBy=1), ev("CountDecremented", "ml", 3, decrementBy=1)]
+    events += [ev("NoOpEvent", "n", 9), ev("ExceptionThrowingEvent", "x", 1, errorMsg="boom")]
+    recs = [(d, k, v) for d, (k, v) in enumerate(events)]
+    with ReplayEngine(0) as e:
+        e.register_program(P.counter_program())
+        ing.record_batches(0, K.encode_record_batch(0, recs[:3], compression="lz4"))
+        e.fold_ingested(ing)
+        assert np.frombuffer(e.get("a"), "<i4").tolist() == [3, 3]
+        ing.record_batches(0, K.encode_record_batch(3, [(d - 3, k, v) for d, k, v in recs[3:]], compression="lz4"))
+        e.fold_ingested(ing)
+        assert np.frombuffer(e.get("a"), "<i4").tolist() == [5, 5]
+        assert np.frombuffer(e.get("ml"), "<i4").tolist() == [1, 3]
+        assert np.frombuffer(e.get("n"), "<i4").tolist() == [0, 0]          # NoOp materialises State(id, 0, 0)
+        assert e.get("x") is None                                            # the handler threw: no state
+        rows = e.export_states().view(F.COUNTER_STATE).reshape(-1)
+        assert int(rows[ing.keys().index("x")]["flags"]) & N.ST_ERROR
