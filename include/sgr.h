@@ -360,11 +360,13 @@ int32_t sgr_ingest_set_value_framing(sgr_ingest* g, int32_t framing);
  * scala.MatchError in the handler) or, with -1, fails the call. Doubles are parsed correctly rounded (strtod), as
  * java.lang.Double.parseDouble does. The exact bytes play-json writes are NOT pinned (no JVM here); the parser is checked
  * against Python's json module on both well-formed and hostile input. */
-#define SGR_JSON_I32 0u
-#define SGR_JSON_I64 1u
-#define SGR_JSON_F64 2u
+#define SGR_JSON_I32  0u
+#define SGR_JSON_I64  1u
+#define SGR_JSON_F64  2u
+#define SGR_JSON_UUID 3u   /* "8-4-4-4-12" string (java.util.UUID.toString) -> 16 bytes, most significant first */
+#define SGR_JSON_PSTR 4u   /* string -> length byte + UTF-8 bytes, zero padded to `len` bytes (must fit: len - 1 bytes at most) */
 #define SGR_JSON_MAX_FIELDS 8u
-typedef struct sgr_json_field { const char* name; uint8_t kind; uint8_t reserved; uint16_t dst_off; uint32_t reserved2; } sgr_json_field;
+typedef struct sgr_json_field { const char* name; uint8_t kind; uint8_t reserved; uint16_t dst_off; uint32_t len; /* PSTR slot */ } sgr_json_field;
 typedef struct sgr_json_event {
   const char* type_name;     /* value of the discriminator member */
   uint32_t event_type;       /* index into the fold program's rules */

@@ -435,7 +435,7 @@ struct RawBuf {
 //   {"_type":"...CountIncremented","aggregateId":"a","incrementBy":1,"sequenceNumber":4}
 // A model registers which member is the class discriminator, which event type index each class name maps to, and which
 // numeric members land at which byte of the packed record. Members are looked up by name: order and extra members do not matter.
-struct JsonFieldSpec { std::string name; uint8_t kind; uint16_t dst_off; };
+struct JsonFieldSpec { std::string name; uint8_t kind; uint16_t dst_off; uint32_t len; };
 struct JsonEventSpec { std::string type_name; uint32_t event_type; std::vector<JsonFieldSpec> fields; };
 struct JsonPacker {
   std::string discriminator;
@@ -603,11 +603,35 @@ const char* json_pack(const JsonPacker& jp, const uint8_t* val, uint32_t val_len
   memcpy(out, &ev->event_type, 4);
   for (const JsonFieldSpec& f : ev->fields) {
     const JsonMember* m = find(f.name);
+    uint8_t* dst = out + (f.dst_off < 8 ? f.dst_off : f.dst_off - 8);   // record offsets 0..7 = type, seq; 16.. = payload (value bytes 8..)
+    if (f.kind == SGR_JSON_UUID || f.kind == SGR_JSON_PSTR) {
+      if (!m || (m->kind != 's' && m->kind != 'S')) return "a string member of the event is missing or not a string";
+      const uint8_t* sb = m->val; uint32_t sn = m->val_len;
+      if (m->kind == 'S') { if (!json_unescape(m->val, m->val_len, tmp)) return "bad escape in a string member"; sb = (const uint8_t*)tmp->data(); sn = (uint32_t)tmp->size(); }
+      if (f.kind == SGR_JSON_UUID) {
+        // java.util.UUID.toString: 8-4-4-4-12 hex digits; stored as the 16 bytes most significant first
+        if (sn != 36 || sb[8] != '-' || sb[13] != '-' || sb[18] != '-' || sb[23] != '-') return "a UUID member is not in 8-4-4-4-12 form";
+        uint32_t k = 0;
+        for (uint32_t i = 0; i < 36; ++i) {
+          if (i == 8 || i == 13 || i == 18 || i == 23) continue;
+          const uint8_t c = sb[i];
+          uint32_t d;
+          if (c >= '0' && c <= '9') d = c - '0'; else if (c >= 'a' && c <= 'f') d = c - 'a' + 10; else if (c >= 'A' && c <= 'F') d = c - 'A' + 10; else return "a UUID member holds a non-hex digit";
+          if (k & 1) dst[k >> 1] |= (uint8_t)d; else dst[k >> 1] = (uint8_t)(d << 4);
+          ++k;
+        }
+      } else {
+        // length byte + UTF-8 bytes, zero padded to the slot (surge_b200/formats.py _pstr)
+        if (sn > f.len - 1 || sn > 255) return "a string member does not fit its slot";
+        dst[0] = (uint8_t)sn;
+        memcpy(dst + 1, sb, sn);
+      }
+      continue;
+    }
     if (!m || m->kind != 'n') return "a numeric member of the event is missing or not a number";
     char num[64];
     if (m->val_len >= sizeof num) return "number too long";
     memcpy(num, m->val, m->val_len); num[m->val_len] = 0;
-    uint8_t* dst = out + (f.dst_off < 8 ? f.dst_off : f.dst_off - 8);   // record offsets 0..7 = type, seq; 16.. = payload (value bytes 8..)
     if (f.kind == 2) {
       const double v = strtod(num, nullptr);      // correctly rounded, like java.lang.Double.parseDouble
       memcpy(dst, &v, 8);
@@ -731,11 +755,12 @@ int32_t sgr_ingest_set_json_packer(sgr_ingest* g, const char* discriminator, con
     JsonEventSpec es{e.type_name, e.event_type, {}};
     for (uint32_t f = 0; f < e.n_fields; ++f) {
       const sgr_json_field& jf = e.fields[f];
-      const uint32_t size = jf.kind == SGR_JSON_I32 ? 4u : 8u;
-      // a member may land on the sequence number (+4) or anywhere in the payload (+16 .. +64); never on type or agg
-      const bool ok = jf.name && jf.kind <= SGR_JSON_F64 && jf.dst_off % 4 == 0 && ((jf.dst_off == 4 && size == 4) || (jf.dst_off >= 16 && jf.dst_off + size <= 64));
-      if (!ok) return ifail(g, SGR_ERR_INVALID, "JSON event %u field %u: bad name, kind or record offset", i, f);
-      es.fields.push_back(JsonFieldSpec{jf.name, jf.kind, jf.dst_off});
+      const uint32_t size = jf.kind == SGR_JSON_I32 ? 4u : jf.kind == SGR_JSON_UUID ? 16u : jf.kind == SGR_JSON_PSTR ? jf.len : 8u;
+      // a member may land on the sequence number (+4, Int only) or anywhere in the payload (+16 .. +64); never on type or agg
+      const bool ok = jf.name && jf.kind <= SGR_JSON_PSTR && jf.dst_off % 4 == 0 && size >= 4 && size % 4 == 0 &&
+                      ((jf.dst_off == 4 && jf.kind == SGR_JSON_I32) || (jf.dst_off >= 16 && jf.dst_off + size <= 64));
+      if (!ok) return ifail(g, SGR_ERR_INVALID, "JSON event %u field %u: bad name, kind, length or record offset", i, f);
+      es.fields.push_back(JsonFieldSpec{jf.name, jf.kind, jf.dst_off, size});
     }
     jp.events.push_back(es);
   }

@@ -61,7 +61,8 @@ class Ingest:
         self._check(self._lib.sgr_ingest_set_value_framing(self._h, framing))
 
     def set_json_packer(self, discriminator: str, events: Sequence[Tuple[str, int, Sequence[Tuple[str, int, int]]]], unknown_type: int = -1) -> None:
-        """events = [(class name, event type index, [(member name, N.JSON_I32 | JSON_I64 | JSON_F64, record byte offset)])].
+        """events = [(class name, event type index, [(member name, N.JSON_I32 | JSON_I64 | JSON_F64 | JSON_UUID, record byte offset) or
+        (member name, N.JSON_PSTR, record byte offset, slot bytes)])].
         Switches nothing by itself: follow with set_value_framing(N.VALUE_JSON)."""
         arr = (N.sgr_json_event * max(len(events), 1))()
         for i, (type_name, event_type, fields) in enumerate(events):
@@ -70,10 +71,12 @@ class Ingest:
             arr[i].n_fields = len(fields)
             if len(fields) > 8:
                 raise IngestError(N.SGR_ERR_INVALID, "at most 8 numeric members per event")
-            for j, (name, kind, dst_off) in enumerate(fields):
+            for j, spec in enumerate(fields):
+                name, kind, dst_off = spec[:3]
                 arr[i].fields[j].name = name.encode("utf-8")
                 arr[i].fields[j].kind = kind
                 arr[i].fields[j].dst_off = dst_off
+                arr[i].fields[j].len = spec[3] if len(spec) > 3 else 0      # slot size of a JSON_PSTR member
         self._check(self._lib.sgr_ingest_set_json_packer(self._h, discriminator.encode("utf-8"), arr, len(events), unknown_type))
 
     def set_null_value_type(self, event_type: int) -> None:

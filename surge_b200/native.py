@@ -77,14 +77,14 @@ class sgr_ingest_stats(C.Structure):
 
 
 class sgr_json_field(C.Structure):
-    _fields_ = [("name", C.c_char_p), ("kind", C.c_uint8), ("reserved", C.c_uint8), ("dst_off", C.c_uint16), ("reserved2", C.c_uint32)]
+    _fields_ = [("name", C.c_char_p), ("kind", C.c_uint8), ("reserved", C.c_uint8), ("dst_off", C.c_uint16), ("len", C.c_uint32)]
 
 
 class sgr_json_event(C.Structure):
     _fields_ = [("type_name", C.c_char_p), ("event_type", C.c_uint32), ("n_fields", C.c_uint32), ("fields", sgr_json_field * 8)]
 
 
-JSON_I32, JSON_I64, JSON_F64 = 0, 1, 2
+JSON_I32, JSON_I64, JSON_F64, JSON_UUID, JSON_PSTR = 0, 1, 2, 3, 4
 VALUE_PACKED, VALUE_PROTOBUF_EVENT, VALUE_JSON = 0, 1, 2
 
 # every symbol include/sgr.h declares: (name, restype, argtypes)

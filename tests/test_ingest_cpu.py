@@ -628,3 +628,43 @@ def test_json_values_numbers_escapes_and_errors():
         Ingest().set_value_framing(N.VALUE_JSON)                  # no packer registered
     with pytest.raises(IngestError):
         Ingest().set_json_packer("_type", [("A", 0, [("x", N.JSON_I32, 8)])])   # would overwrite the aggregate index
+
+
+def test_bank_account_json_events_pack_like_the_binary_formatting():
+    """surge-docs BankAccountSurgeModel.scala:30-32 writes Json.toJson(evt)(Json.format[BankAccountEvent]); UUID and String
+    members land in the packed record exactly as surge_b200/formats.py packs them by hand."""
+    import uuid as _uuid
+
+    from surge_b200 import formats as F
+
+    spec = [("docs.command.BankAccountCreated", 0, [("accountNumber", N.JSON_UUID, 16), ("balance", N.JSON_F64, 32),
+                                                     ("accountOwner", N.JSON_PSTR, 40, 16), ("securityCode", N.JSON_PSTR, 56, 8)]),
+            ("docs.command.BankAccountUpdated", 1, [("accountNumber", N.JSON_UUID, 16), ("newBalance", N.JSON_F64, 32)])]
+    ing = Ingest()
+    ing.set_json_packer("_type", spec)
+    ing.set_value_framing(N.VALUE_JSON)
+    rng = np.random.default_rng(3)
+    recs, want = [], []
+    for d in range(60):
+        acct = str(_uuid.UUID(int=int(rng.integers(0, 2**63)) << 64 | int(rng.integers(0, 2**63))))
+        if d % 3:
+            owner, code, bal = ["Jane Doe", "Zo\\u00eb", "", "x" * 15][d % 4], ["1234", "", "abcdefg"][d % 3], float(rng.integers(0, 10**6)) / 8
+            obj = {"_type": "docs.command.BankAccountCreated", "accountNumber": acct.upper() if d % 5 == 0 else acct, "accountOwner": owner, "securityCode": code, "balance": bal}
+            want.append(F.bank_created_record(d % 7, 0, acct, owner, code, bal))
+        else:
+            bal = [0.0, -0.0, 1e-3, 12345.678][d % 4]
+            obj = {"_type": "docs.command.BankAccountUpdated", "accountNumber": acct, "newBalance": bal}
+            want.append(F.bank_updated_record(d % 7, 0, acct, bal))
+        recs.append((d, f"k{d % 7}".encode(), json.dumps(obj, ensure_ascii=bool(d % 2)).encode("utf-8")))
+    ing.record_batches(0, K.encode_record_batch(0, recs))
+    got = ing.pending()
+    assert [bytes(r) for r in got] == want
+    for bad, why in [({"_type": "docs.command.BankAccountUpdated", "accountNumber": "not-a-uuid", "newBalance": 1.0}, "8-4-4-4-12"),
+                     ({"_type": "docs.command.BankAccountUpdated", "accountNumber": "0000000g-0000-0000-0000-000000000000", "newBalance": 1.0}, "non-hex"),
+                     ({"_type": "docs.command.BankAccountCreated", "accountNumber": str(_uuid.UUID(int=1)), "accountOwner": "x" * 16, "securityCode": "", "balance": 1.0}, "does not fit"),
+                     ({"_type": "docs.command.BankAccountCreated", "accountNumber": str(_uuid.UUID(int=1)), "accountOwner": 5, "securityCode": "", "balance": 1.0}, "not a string")]:
+        with pytest.raises(IngestError) as ei:
+            ing.record_batches(1, K.encode_record_batch(0, [(0, b"k", json.dumps(bad).encode())]))
+        assert why in str(ei.value)
+    with pytest.raises(IngestError):
+        Ingest().set_json_packer("_type", [("A", 0, [("s", N.JSON_PSTR, 56, 12)])])      # runs past the record
