@@ -356,7 +356,8 @@ int32_t sgr_ingest_set_value_framing(sgr_ingest* g, int32_t framing);
  * (modules/command-engine/core/src/test/scala/surge/core/TestBoundedContext.scala:44-56 formats, :159-161 writer).
  * The model registers the discriminator member, the event type index of each class name and where each numeric member
  * lands in the packed record (record byte offsets: 4 = the sequence number, 16..63 = payload). Members are found by name —
- * order, whitespace and extra members do not matter; an unknown class name becomes event type `unknown_type` (a
+ * order, whitespace and extra members do not matter; with an empty discriminator exactly one class is registered and every
+ * value is that class (a state topic: Json.toJson(agg) carries no discriminator); an unknown class name becomes event type `unknown_type` (a
  * scala.MatchError in the handler) or, with -1, fails the call. Doubles are parsed correctly rounded (strtod), as
  * java.lang.Double.parseDouble does. The exact bytes play-json writes are NOT pinned (no JVM here); the parser is checked
  * against Python's json module on both well-formed and hostile input. */

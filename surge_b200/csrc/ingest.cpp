@@ -588,11 +588,15 @@ const char* json_pack(const JsonPacker& jp, const uint8_t* val, uint32_t val_len
     for (uint32_t i = 0; i < n_members; ++i) if (json_name_is(members[i].key, members[i].key_len, members[i].key_escaped, name, tmp)) hit = &members[i];
     return hit;
   };
-  const JsonMember* d = find(jp.discriminator);
-  if (!d || (d->kind != 's' && d->kind != 'S')) return "the class discriminator member is missing or not a string";
   const JsonEventSpec* ev = nullptr;
-  std::string cls;
-  for (const JsonEventSpec& e : jp.events) if (json_name_is(d->val, d->val_len, d->kind == 'S', e.type_name, &cls)) { ev = &e; break; }
+  if (jp.discriminator.empty()) {
+    ev = &jp.events[0];       // one class only (a state topic: Json.toJson(agg) carries no discriminator)
+  } else {
+    const JsonMember* d = find(jp.discriminator);
+    if (!d || (d->kind != 's' && d->kind != 'S')) return "the class discriminator member is missing or not a string";
+    std::string cls;
+    for (const JsonEventSpec& e : jp.events) if (json_name_is(d->val, d->val_len, d->kind == 'S', e.type_name, &cls)) { ev = &e; break; }
+  }
   memset(out, 0, 56);
   if (!ev) {
     if (jp.unknown_type < 0) return "unknown event class";
@@ -746,6 +750,7 @@ const char* sgr_ingest_last_error(const sgr_ingest* g) { return g ? g->last_erro
 int32_t sgr_ingest_set_json_packer(sgr_ingest* g, const char* discriminator, const sgr_json_event* events, uint32_t n_events, int32_t unknown_type) {
   if (!g || !discriminator || (n_events && !events)) return ifail(g, SGR_ERR_INVALID, "null argument");
   if (unknown_type >= (int32_t)SGR_MAX_TYPES) return ifail(g, SGR_ERR_INVALID, "unknown_type out of range");
+  if (!*discriminator && n_events != 1) return ifail(g, SGR_ERR_INVALID, "without a discriminator member exactly one class can be registered");
   JsonPacker jp;
   jp.discriminator = discriminator;
   jp.unknown_type = unknown_type < 0 ? -1 : unknown_type;
@@ -770,7 +775,7 @@ int32_t sgr_ingest_set_json_packer(sgr_ingest* g, const char* discriminator, con
 
 int32_t sgr_ingest_set_value_framing(sgr_ingest* g, int32_t framing) {
   if (!g || (framing != SGR_VALUE_PACKED && framing != SGR_VALUE_PROTOBUF_EVENT && framing != SGR_VALUE_JSON)) return ifail(g, SGR_ERR_INVALID, "unknown value framing %d", framing);
-  if (framing == SGR_VALUE_JSON && g->json.discriminator.empty()) return ifail(g, SGR_ERR_INVALID, "register a JSON packer first (sgr_ingest_set_json_packer)");
+  if (framing == SGR_VALUE_JSON && g->json.events.empty()) return ifail(g, SGR_ERR_INVALID, "register a JSON packer first (sgr_ingest_set_json_packer)");
   g->value_framing = framing;
   return SGR_OK;
 }

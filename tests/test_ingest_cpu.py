@@ -668,3 +668,21 @@ def test_bank_account_json_events_pack_like_the_binary_formatting():
         assert why in str(ei.value)
     with pytest.raises(IngestError):
         Ingest().set_json_packer("_type", [("A", 0, [("s", N.JSON_PSTR, 56, 12)])])      # runs past the record
+
+
+def test_json_state_topic_snapshots_and_tombstones():
+    """The reference test model writes its STATE topic as Json.toJson(agg) = {"aggregateId":..,"count":..,"version":..}
+    (core TestBoundedContext.scala:151-157), no discriminator, null = deleted: one registered class + the tombstone type."""
+    ing = Ingest()
+    ing.set_json_packer("", [("State", 0, [("count", N.JSON_I32, 16), ("version", N.JSON_I32, 20)])])
+    ing.set_value_framing(N.VALUE_JSON)
+    ing.set_null_value_type(1)
+    recs = [(0, b"a", b'{"aggregateId":"a","count":4,"version":4}'), (1, b"b", b'{"aggregateId":"b","count":-7,"version":2}'), (2, b"a", None),
+            (3, b"a", b'{"version":9,"count":1,"aggregateId":"a"}')]
+    ing.record_batches(0, K.encode_record_batch(0, recs))
+    p = ing.pending()
+    assert p[:, 0:4].copy().view("<u4").ravel().tolist() == [0, 0, 1, 0]
+    assert p[:, 16:24].copy().view("<i4").reshape(-1, 2).tolist() == [[4, 4], [-7, 2], [0, 0], [1, 9]]
+    assert ing.keys() == ["a", "b"]
+    with pytest.raises(IngestError):
+        Ingest().set_json_packer("", [("A", 0, []), ("B", 1, [])])
