@@ -79,6 +79,9 @@ JNIEXPORT jlong JNICALL Java_surge_gpu_Native_00024_ingestCreate(JNIEnv* env, jo
   return (jlong)(intptr_t)g;
 }
 JNIEXPORT jint JNICALL Java_surge_gpu_Native_00024_ingestDestroy(JNIEnv* env, jobject o, jlong g) { return sgr_ingest_destroy(G(g)); }
+JNIEXPORT jint JNICALL Java_surge_gpu_Native_00024_ingestSetValueFraming(JNIEnv* env, jobject o, jlong g, jint framing) { return sgr_ingest_set_value_framing(G(g), framing); }
+JNIEXPORT jint JNICALL Java_surge_gpu_Native_00024_ingestSetNullValueType(JNIEnv* env, jobject o, jlong g, jint event_type) { return sgr_ingest_set_null_value_type(G(g), event_type); }
+/* sgr_ingest_set_json_packer takes an array of structs with strings: bind it with a small marshaller (or JNA) on the maintainer's side. */
 JNIEXPORT jint JNICALL Java_surge_gpu_Native_00024_ingestSetAborted(JNIEnv* env, jobject o, jlong g, jint partition, jlongArray pids, jlongArray firsts) {
   jsize n = (*env)->GetArrayLength(env, pids);
   jlong* p = (*env)->GetLongArrayElements(env, pids, 0);

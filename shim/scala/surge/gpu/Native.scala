@@ -30,6 +30,8 @@ object Native {
   // raw record batches in, committed offsets out (include/sgr.h "ingest")
   @native def ingestCreate(): Long                                                 // sgr_ingest_create
   @native def ingestDestroy(ingest: Long): Int                                     // sgr_ingest_destroy
+  @native def ingestSetValueFraming(ingest: Long, framing: Int): Int               // sgr_ingest_set_value_framing (0 packed, 1 protobuf Event, 2 JSON)
+  @native def ingestSetNullValueType(ingest: Long, eventType: Int): Int            // sgr_ingest_set_null_value_type (state-topic tombstones)
   @native def ingestSetAborted(ingest: Long, partition: Int, producerIds: Array[Long], firstOffsets: Array[Long]): Int // sgr_ingest_set_aborted
   /** decodes one fetch response's bytes for `partition`; returns the number of packed records appended; throws on malformed input */
   @native def ingestRecordBatches(ingest: Long, partition: Int, data: ByteBuffer, nbytes: Long): Long // sgr_ingest_record_batches
