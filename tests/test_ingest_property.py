@@ -73,3 +73,35 @@ def test_decoder_equals_restatement_under_arbitrary_fetch_cuts(batches, cuts, re
     assert got.shape == want_recs.shape and np.array_equal(got, want_recs)
     assert ing.keys() == [k.decode() for k in want_keys]
     assert ing.offsets(0)[0] == want_next.get(0, 0)
+
+
+# ----------------------------------------------------------------------------- JSON values: the native scanner vs Python's json module
+import json  # noqa: E402
+
+from surge_b200 import native as N  # noqa: E402
+
+json_leaf = st.one_of(st.none(), st.booleans(), st.integers(-2**53, 2**53), st.floats(allow_nan=False, allow_infinity=False), st.text(max_size=12))
+json_tree = st.recursive(json_leaf, lambda kids: st.one_of(st.lists(kids, max_size=4), st.dictionaries(st.text(max_size=6), kids, max_size=4)), max_leaves=12)
+
+
+@settings(max_examples=300, deadline=None)
+@given(st.dictionaries(st.text(max_size=8).filter(lambda k: k not in ("_t", "by", "seq", "w", "big")), json_tree, max_size=6),
+       st.integers(-2**31, 2**31 - 1), st.integers(0, 2**31 - 1), st.floats(allow_nan=False, allow_infinity=False), st.integers(-2**63, 2**63 - 1),
+       st.booleans(), st.booleans(), st.randoms(use_true_random=False))
+def test_json_scanner_accepts_what_python_writes_and_finds_the_members(extra, by, seq, w, big, ascii_only, spaced, rnd):
+    """Any JSON object Python's json module can write — arbitrary nesting, escapes, unicode, member order, spacing — must be
+    accepted, and the registered members must be found by name and parsed to the same numbers."""
+    members = list(extra.items()) + [("_t", "Evt"), ("by", by), ("seq", seq), ("w", w), ("big", big)]
+    rnd.shuffle(members)
+    text = json.dumps(dict(members), ensure_ascii=ascii_only, separators=((", ", " : ") if spaced else (",", ":")))
+    assert json.loads(text)["by"] == by
+    ing = Ingest()
+    ing.set_json_packer("_t", [("Evt", 2, [("by", N.JSON_I32, 16), ("seq", N.JSON_I32, 4), ("w", N.JSON_F64, 24), ("big", N.JSON_I64, 32)])])
+    ing.set_value_framing(N.VALUE_JSON)
+    ing.record_batches(0, K.encode_record_batch(0, [(0, b"k", text.encode("utf-8"))]))
+    rec = bytes(ing.pending()[0])
+    assert struct.unpack_from("<II", rec, 0) == (2, seq)
+    assert struct.unpack_from("<i", rec, 16)[0] == by
+    assert struct.unpack_from("<d", rec, 24)[0] == w and struct.pack("<d", w) == rec[24:32]
+    assert struct.unpack_from("<q", rec, 32)[0] == big
+    assert rec[20:24] == bytes(4) and rec[40:] == bytes(24)
