@@ -31,6 +31,7 @@
 #ifndef SGR_H
 #define SGR_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -310,7 +311,8 @@ int32_t sgr_dist_local_aggregates(sgr_engine* e, uint32_t* out, uint64_t cap, ui
  *     (CORE/internal/kafka/KafkaProducerActorImpl.scala:321-329);
  *   - a trailing partial batch is left undecoded (n_trailing_bytes), as fetch responses may end with one;
  *   - records below the partition's decoded position are counted as duplicates and skipped (refetch after restart);
- *   - record value = the model's packed event: u32 type, u32 seq (little endian) + up to 48 payload bytes.
+ *   - record value = the model's packed event: u32 type, u32 seq (little endian) + up to 48 payload bytes — as is, inside the
+ *     multilanguage protobuf Event, or produced from a flat JSON object by a registered member table (sgr_ingest_set_value_framing).
  * A malformed batch fails the whole call and leaves the pending log and the partition position untouched.
  * The RecordBatch framing is third-party (org.apache.kafka:kafka-clients:3.2.3) and the reference holds no broker bytes:
  * its byte-level parity is UNPINNED (see oracle/kafka_batch.py); lz4, xxHash32, CRC-32C and the protobuf framing are pinned
