@@ -24,3 +24,13 @@ def test_every_scala_native_has_its_c_definition():
     defined = set(re.findall(r"Java_surge_gpu_Native_00024_(\w+)\s*\(", c_src))
     assert set(natives) <= defined, sorted(set(natives) - defined)
     assert defined <= set(natives), sorted(defined - set(natives))
+
+
+def test_the_c_abi_header_is_self_contained_in_c_and_cxx(tmp_path):
+    src = tmp_path / "only_sgr.c"
+    src.write_text('#include "sgr.h"\nint main(void) { return SGR_ABI_VERSION - 1; }\n')
+    inc = os.path.join(ROOT, "include")
+    for cmd in (["gcc", "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-I", inc, str(src)],
+                ["g++", "-std=c++17", "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-x", "c++", "-I", inc, str(src)]):
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-2000:]
