@@ -55,6 +55,13 @@ def route_on_host(records: np.ndarray, owner: np.ndarray, local: np.ndarray, nra
     return out
 
 
+def partitions_of_rank(rank: int, nranks: int, num_partitions: int) -> List[int]:
+    """Topic partitions a rank consumes when the store is fed from the topic itself (surge_b200/ingest.py): the broker has already
+    done the shuffle — every record of an aggregate sits in partition partitionForKey(id) — so rank r decodes and folds the
+    partitions p with p % nranks == r and NO exchange between GPUs is needed; the same owner rule as the routed path."""
+    return [p for p in range(num_partitions) if p % nranks == rank]
+
+
 def exchange_ids(engine, rank: int, nranks: int, recv_capacity_records: int, fused: bool = True) -> None:
     """Rendezvous over torch.distributed: NCCL unique id from rank 0, then (fused path) the IPC handles."""
     import torch.distributed as dist

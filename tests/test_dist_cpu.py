@@ -82,3 +82,24 @@ def test_owner_tables_follow_the_reference_partitioner():
     assert (owner == part % 4).all()
     for r in range(4):
         assert (owner[globals_of[r]] == r).all() and (local[globals_of[r]] == np.arange(len(globals_of[r]))).all()
+
+
+def test_topic_partitions_split_over_ranks_need_no_exchange():
+    """Feeding from the topic: rank r takes the partitions p % nranks == r; because the partition of a record IS
+    partitionForKey(aggregate id), every aggregate's records land on exactly one rank and ranks share no aggregate."""
+    from surge_b200 import dist as D
+
+    keys = [f"agg-{i}" for i in range(5000)]
+    n_part, nranks = 32, 4
+    part = D.partitions_for_keys(keys, n_part)
+    owners = {}
+    for r in range(nranks):
+        mine = set(D.partitions_of_rank(r, nranks, n_part))
+        assert mine == {p for p in range(n_part) if p % nranks == r}
+        for k, p in zip(keys, part.tolist()):
+            if p in mine:
+                assert k not in owners
+                owners[k] = r
+    assert len(owners) == len(keys)
+    owner, _, _ = D.owner_and_local_index(part, nranks)          # the routed path's owner table says the same
+    assert [owners[k] for k in keys] == owner.tolist()
