@@ -279,7 +279,9 @@ int32_t sgr_stream(sgr_engine* e, void** stream);
 typedef struct sgr_dist_stats {
   uint64_t n_sent, n_sent_remote, n_recv, n_local_aggregates;
   float ms_count, ms_counts_exchange, ms_scatter, ms_exchange, ms_group, ms_fold;
-  uint32_t reserved[6];
+  float ms_pipeline;               /* fused >= 2: device time of the whole overlapped route + exchange + fold */
+  uint32_t exchange_record_bytes;  /* bytes per record that crossed NVLink (64, or the projected size with fused == 3) */
+  uint32_t reserved[4];
 } sgr_dist_stats;
 
 int32_t sgr_dist_unique_id(void* out128);                       /* rank 0: a 128-byte NCCL unique id to hand to the others */
@@ -290,9 +292,30 @@ int32_t sgr_dist_set_partitions(sgr_engine* e, const uint32_t* partition_of_agg,
  * handles, every rank imports all nranks of them (own slot ignored). */
 int32_t sgr_dist_ipc_export(sgr_engine* e, void* out64);
 int32_t sgr_dist_ipc_import(sgr_engine* e, const void* handles64_by_rank);
-/* Route + exchange + stable group-by + fold. fused != 0: the route kernel writes each record straight into
- * its owner's receive buffer over NVLink (needs the IPC import); fused == 0: pack + one NCCL all-to-all. */
+/* Route + exchange + (group-by) + fold.
+ *   fused == 0  count + pack, one NCCL all-to-all (grouped ncclSend/ncclRecv), then the fold;
+ *   fused == 1  count, then the route kernel writes each record straight into its owner's receive buffer over NVLink;
+ *   fused == 2  ONE pass, pipelined: the log is cut into chunks (option "push_chunks", the same on every rank); a push kernel
+ *               partitions each chunk in shared memory and writes every owner's run contiguously into that owner's receive
+ *               region over NVLink, an arrival flag per (source, chunk) follows, and the owner folds chunk c while chunk c+1 is
+ *               still in flight. No count pass, no send buffer, no host synchronisation inside. Needs the peers' receive buffers
+ *               (IPC import) and a program in the sort-free class (16-byte state, class 0, every word add-only or set-only) —
+ *               other programs silently take fused == 1. Receive regions have a fixed capacity of
+ *               recv_capacity / (nranks * push_chunks) records per (source, chunk): a region that would overflow fails the call
+ *               with SGR_ERR_CAPACITY on EVERY rank (nothing is written out of bounds); retry with fused <= 1 or more capacity.
+ *   fused == 3  as 2, but only the record words the fold program reads cross NVLink (u32 local index + slot words:
+ *               16 bytes per record for the Counter model). */
 int32_t sgr_dist_route_and_fold(sgr_engine* e, const void* d_records, uint64_t n_records, int32_t fused);
+/* Several ranks inside ONE process on one device ("loopback", for single-GPU tests of the multi-rank logic): sgr_dist_init with
+ * unique_id128 == NULL and nranks > 1 creates such a rank; the ranks hand each other their receive allocation as plain device
+ * pointers (sgr_dist_recv_base -> sgr_dist_set_peers) and the caller runs every rank's sgr_dist_route_and_fold(fused >= 2)
+ * concurrently (one host thread per rank), with a barrier of its own between calls. fused <= 1 needs NCCL and is refused. */
+int32_t sgr_dist_recv_base(sgr_engine* e, void** base);
+int32_t sgr_dist_set_peers(sgr_engine* e, void* const* recv_bases_by_rank);
+/* 64-bit order-independent hash of the live state table: sum over slots of mix(aggregate index, state bytes) mod 2^64, the
+ * index being the GLOBAL aggregate index on a routed engine — so the sum of the ranks' hashes does not depend on how many ranks
+ * there are. The parity check of the multi-GPU runs (bench.py, tests/test_gpu_dist.py; twin: surge_b200/dist.py states_hash). */
+int32_t sgr_states_hash(sgr_engine* e, uint64_t* out);
 int32_t sgr_dist_get_stats(sgr_engine* e, sgr_dist_stats* out);
 /* global aggregate index of each local state slot (host copy, n_local u32) */
 int32_t sgr_dist_local_aggregates(sgr_engine* e, uint32_t* out, uint64_t cap, uint64_t* n_local);

@@ -30,6 +30,7 @@
 #include "../../include/sgr.h"
 #include "devbuf.h"
 #include "dist.cuh"
+#include "dist_state.h"
 
 namespace sgr {
 namespace {
@@ -54,6 +55,11 @@ __global__ void local_index_kernel(const uint8_t* __restrict__ owner_of, uint64_
     local_of[i] = pos[i];
     if (r == my_rank && global_of_local) global_of_local[pos[i]] = (uint32_t)i;
   }
+}
+
+__global__ void route_table_kernel(const uint8_t* __restrict__ owner_of, const uint32_t* __restrict__ local_of, uint64_t n, uint32_t* __restrict__ route_of) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) route_of[i] = ((uint32_t)owner_of[i] << 28) | (local_of[i] & 0x0fffffffu);
 }
 
 // ---------------------------------------------------------------- K4: count
@@ -169,48 +175,23 @@ __global__ void route_totals_kernel(const uint32_t* __restrict__ hist, uint32_t 
 
 inline uint32_t cdiv64(uint64_t a, uint32_t b) { return (uint32_t)((a + b - 1) / b); }
 
-// ---------------------------------------------------------------- NCCL through dlopen (no link-time dependency)
-struct NcclApi {
-  void* lib = nullptr;
-  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
-  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
-  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
-  ncclResult_t (*GroupStart)() = nullptr;
-  ncclResult_t (*GroupEnd)() = nullptr;
-  ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
-  ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
-  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
-  const char* (*GetErrorString)(ncclResult_t) = nullptr;
-  bool load(std::string* err) {
-    if (lib) return true;
-    lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
-    if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
-    if (!lib) { *err = std::string("dlopen libnccl.so.2: ") + dlerror(); return false; }
-#define SGR_SYM(field, name) *(void**)(&field) = dlsym(lib, name); if (!field) { *err = std::string("missing symbol ") + name; return false; }
-    SGR_SYM(GetUniqueId, "ncclGetUniqueId") SGR_SYM(CommInitRank, "ncclCommInitRank") SGR_SYM(CommDestroy, "ncclCommDestroy")
-    SGR_SYM(GroupStart, "ncclGroupStart") SGR_SYM(GroupEnd, "ncclGroupEnd") SGR_SYM(Send, "ncclSend") SGR_SYM(Recv, "ncclRecv")
-    SGR_SYM(AllGather, "ncclAllGather") SGR_SYM(GetErrorString, "ncclGetErrorString")
-#undef SGR_SYM
-    return true;
-  }
-};
-NcclApi g_nccl;
-
 }  // namespace
 
-struct DistState {
-  int rank = 0, nranks = 1;
-  ncclComm_t comm = nullptr;
-  uint64_t n_global = 0, n_local = 0;
-  DevBuf owner_of, local_of, global_of_local, part_tmp, flags, pos, scan_tmp;
-  DevBuf hist, owner_total, counts_all, send_buf, recv_buf;
-  uint64_t recv_capacity = 0;            // records
-  uint8_t* peer_recv[kMaxRanks] = {};    // fused path: every rank's receive buffer, mapped here
-  bool peers_mapped = false;
-  std::vector<void*> opened;             // IPC mappings to close
-  DistStats stats{};
-  cudaEvent_t ev[6] = {};
-};
+// ---------------------------------------------------------------- NCCL through dlopen (no link-time dependency)
+bool NcclApi::load(std::string* err) {
+  if (lib) return true;
+  lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!lib) { *err = std::string("dlopen libnccl.so.2: ") + dlerror(); return false; }
+#define SGR_SYM(field, name) *(void**)(&field) = dlsym(lib, name); if (!field) { *err = std::string("missing symbol ") + name; return false; }
+  SGR_SYM(GetUniqueId, "ncclGetUniqueId") SGR_SYM(CommInitRank, "ncclCommInitRank") SGR_SYM(CommDestroy, "ncclCommDestroy")
+  SGR_SYM(GroupStart, "ncclGroupStart") SGR_SYM(GroupEnd, "ncclGroupEnd") SGR_SYM(Send, "ncclSend") SGR_SYM(Recv, "ncclRecv")
+  SGR_SYM(AllGather, "ncclAllGather") SGR_SYM(GetErrorString, "ncclGetErrorString")
+#undef SGR_SYM
+  return true;
+}
+NcclApi& nccl_api() { static NcclApi api; return api; }
+#define g_nccl (nccl_api())
 
 DistState* dist_create() { return new DistState(); }
 
@@ -221,6 +202,9 @@ void dist_destroy(DistState* d) {
   d->owner_of.release(); d->local_of.release(); d->global_of_local.release(); d->part_tmp.release(); d->flags.release();
   d->pos.release(); d->scan_tmp.release(); d->hist.release(); d->owner_total.release(); d->counts_all.release();
   d->send_buf.release(); d->recv_buf.release();
+  d->route_of.release(); d->lb.release(); d->push_ctl.release(); d->gather_buf.release();
+  if (d->stream2) cudaStreamDestroy(d->stream2);
+  for (auto& e : d->pev) if (e) cudaEventDestroy(e);
   for (auto& e : d->ev) if (e) cudaEventDestroy(e);
   delete d;
 }
@@ -238,17 +222,29 @@ int dist_unique_id(void* out128, std::string* err) {
 int dist_init(DistState* d, int rank, int nranks, const void* unique_id, uint64_t recv_capacity_records, cudaStream_t st, std::string* err) {
   if (nranks < 1 || nranks > kMaxRanks || rank < 0 || rank >= nranks) { *err = "rank/nranks out of range"; return SGR_ERR_INVALID; }
   d->rank = rank; d->nranks = nranks; d->recv_capacity = recv_capacity_records;
+  d->loopback = nranks > 1 && !unique_id;   // ranks of one process (tests): peers arrive through dist_set_peers, barriers are the caller's
   for (auto& e : d->ev) if (!e && cudaEventCreate(&e) != cudaSuccess) { *err = "cudaEventCreate"; return SGR_ERR_CUDA; }
-  if (nranks > 1) {
+  for (auto& e : d->pev) if (!e && cudaEventCreate(&e) != cudaSuccess) { *err = "cudaEventCreate"; return SGR_ERR_CUDA; }
+  if (!d->stream2) {
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    if (cudaStreamCreateWithPriority(&d->stream2, cudaStreamNonBlocking, hi) != cudaSuccess) { *err = "cudaStreamCreate"; return SGR_ERR_CUDA; }
+  }
+  if (nranks > 1 && !d->loopback) {
     if (!g_nccl.load(err)) return SGR_ERR_DIST;
     ncclUniqueId id; memcpy(&id, unique_id, 128);
     ncclResult_t r = g_nccl.CommInitRank(&d->comm, nranks, id, rank);
     if (r != ncclSuccess) { *err = std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(r); return SGR_ERR_DIST; }
   }
-  cudaError_t ce = d->recv_buf.reserve((nranks > 1 || recv_capacity_records) ? recv_capacity_records * 64 : 0);
+  const size_t rec_bytes = (nranks > 1 || recv_capacity_records) ? recv_capacity_records * 64 : 0;
+  cudaError_t ce = d->recv_buf.reserve(kRecvHeaderBytes + rec_bytes);
   if (ce != cudaSuccess) { *err = std::string("receive buffer: ") + cudaGetErrorString(ce); return SGR_ERR_OOM; }
-  d->peer_recv[rank] = (uint8_t*)d->recv_buf.p;
-  (void)st;
+  if ((ce = cudaMemsetAsync(d->recv_buf.p, 0, kRecvHeaderBytes, st)) != cudaSuccess || (ce = cudaStreamSynchronize(st)) != cudaSuccess) {
+    *err = std::string("receive header: ") + cudaGetErrorString(ce); return SGR_ERR_CUDA;
+  }
+  d->peer_base[rank] = (uint8_t*)d->recv_buf.p;
+  d->peer_recv[rank] = (uint8_t*)d->recv_buf.p + kRecvHeaderBytes;
+  d->epoch = 0;
   return SGR_OK;
 }
 
@@ -268,12 +264,27 @@ int dist_ipc_import(DistState* d, const void* handles, std::string* err) {
     void* p = nullptr;
     cudaError_t ce = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
     if (ce != cudaSuccess) { *err = std::string("cudaIpcOpenMemHandle(rank ") + std::to_string(r) + "): " + cudaGetErrorString(ce); return SGR_ERR_DIST; }
-    d->peer_recv[r] = (uint8_t*)p;
+    d->peer_base[r] = (uint8_t*)p;
+    d->peer_recv[r] = (uint8_t*)p + kRecvHeaderBytes;
     d->opened.push_back(p);
   }
   d->peers_mapped = true;
   return SGR_OK;
 }
+
+// loopback ranks (one process, one device): the other ranks' receive allocations as plain device pointers
+int dist_set_peers(DistState* d, void* const* bases, std::string* err) {
+  if (!d->loopback) { *err = "sgr_dist_set_peers is for loopback ranks (sgr_dist_init without a unique id)"; return SGR_ERR_INVALID; }
+  for (int r = 0; r < d->nranks; ++r) {
+    if (r == d->rank) continue;
+    if (!bases[r]) { *err = "null peer base"; return SGR_ERR_INVALID; }
+    d->peer_base[r] = (uint8_t*)bases[r];
+    d->peer_recv[r] = (uint8_t*)bases[r] + kRecvHeaderBytes;
+  }
+  d->peers_mapped = true;
+  return SGR_OK;
+}
+void* dist_recv_base(const DistState* d) { return d->recv_buf.p; }
 
 cudaError_t exclusive_scan_u32_public(const uint32_t* in, uint32_t* out, uint32_t n, uint32_t* tmp, cudaStream_t st);
 
@@ -305,6 +316,10 @@ int dist_set_partitions(DistState* d, const uint32_t* partition_of_agg, uint64_t
     local_index_kernel<<<nb, 256, 0, st>>>((const uint8_t*)d->owner_of.p, n_global, (uint32_t)r, (const uint32_t*)d->pos.p,
                                            (uint32_t*)d->local_of.p, (uint32_t*)d->global_of_local.p, (uint32_t)d->rank);
   }
+  // owner << 28 | local index in one word: one lookup per record in the push kernel (route_push.cu)
+  // (the push path is taken only while n_global <= 2^28, so every local index fits its 28 bits)
+  DTRY(d->route_of.reserve(n_global * 4 + 4));
+  route_table_kernel<<<nb, 256, 0, st>>>((const uint8_t*)d->owner_of.p, (const uint32_t*)d->local_of.p, n_global, (uint32_t*)d->route_of.p);
   DTRY(cudaStreamSynchronize(st));
   d->n_global = n_global; d->n_local = n_local;
 #undef DTRY
@@ -316,7 +331,7 @@ int dist_nranks(const DistState* d) { return d->nranks; }
 void dist_clear_stats(DistState* d, uint64_t n_records) { d->stats = DistStats{}; d->stats.n_sent = n_records; d->stats.n_recv = n_records; }
 const uint32_t* dist_global_of_local(const DistState* d) { return (const uint32_t*)d->global_of_local.p; }
 const DistStats* dist_stats(const DistState* d) { return &d->stats; }
-const uint8_t* dist_recv_buffer(const DistState* d) { return (const uint8_t*)d->recv_buf.p; }
+const uint8_t* dist_recv_buffer(const DistState* d) { return d->peer_recv[d->rank]; }
 
 // Route this rank's records to their owners. On return (stream-ordered) the receive buffer holds n_recv records,
 // grouped by source rank, each with its agg field rewritten to the local aggregate index.
@@ -326,6 +341,7 @@ int dist_route(DistState* d, const uint8_t* d_records, uint64_t n, bool fused, u
 #define DTRY(x) if ((ce = (x)) != cudaSuccess) { *err = std::string(#x ": ") + cudaGetErrorString(ce); return SGR_ERR_CUDA; }
 #define NTRY(x) { ncclResult_t _r = (x); if (_r != ncclSuccess) { *err = std::string(#x ": ") + g_nccl.GetErrorString(_r); return SGR_ERR_DIST; } }
   if (!d->n_global) { *err = "no partition table: call sgr_dist_set_partitions first"; return SGR_ERR_NOT_LOADED; }
+  if (d->loopback) { *err = "loopback ranks have no NCCL communicator: use fused >= 2 with a sort-free program"; return SGR_ERR_UNSUPPORTED; }
   if (n >= (1ull << 32)) { *err = "at most 2^32 records per rank per exchange"; return SGR_ERR_UNSUPPORTED; }
   if (fused && d->nranks > 1 && !d->peers_mapped) { *err = "fused route needs the peers' receive buffers (sgr_dist_ipc_import)"; return SGR_ERR_NOT_LOADED; }
   const int R = d->nranks;
@@ -383,7 +399,7 @@ int dist_route(DistState* d, const uint8_t* d_records, uint64_t n, bool fused, u
     DTRY(d->send_buf.reserve(n * 64));
     uint64_t off = 0;
     for (int q = 0; q < R; ++q) { dst.p[q] = (uint8_t*)d->send_buf.p + off * 64; off += send_cnt[q]; }
-    if (R == 1) dst.p[0] = (uint8_t*)d->recv_buf.p;
+    if (R == 1) dst.p[0] = d->peer_recv[d->rank];
   }
   if (n) route_scatter_kernel<<<nblocks, kRouteThreads, 0, st>>>(d_records, n, d->n_global, (const uint8_t*)d->owner_of.p,
                                                                  (const uint32_t*)d->local_of.p, (uint32_t)R, (const uint32_t*)d->hist.p,
@@ -401,7 +417,7 @@ int dist_route(DistState* d, const uint8_t* d_records, uint64_t n, bool fused, u
         if (send_cnt[q]) NTRY(g_nccl.Send((const uint8_t*)d->send_buf.p + off * 64, (size_t)send_cnt[q] * 64, ncclUint8, q, d->comm, st));
         off += send_cnt[q];
         const uint64_t rc = all_cnt[(size_t)q * kMaxRanks + d->rank];
-        if (rc) NTRY(g_nccl.Recv((uint8_t*)d->recv_buf.p + recv_off[q] * 64, (size_t)rc * 64, ncclUint8, q, d->comm, st));
+        if (rc) NTRY(g_nccl.Recv(d->peer_recv[d->rank] + recv_off[q] * 64, (size_t)rc * 64, ncclUint8, q, d->comm, st));
       }
       NTRY(g_nccl.GroupEnd());
     }

@@ -21,6 +21,8 @@ int dist_unique_id(void* out128, std::string* err);
 int dist_init(DistState* d, int rank, int nranks, const void* unique_id, uint64_t recv_capacity_records, cudaStream_t st, std::string* err);
 int dist_ipc_export(DistState* d, void* out64, std::string* err);
 int dist_ipc_import(DistState* d, const void* handles, std::string* err);
+int dist_set_peers(DistState* d, void* const* bases, std::string* err);
+void* dist_recv_base(const DistState* d);
 int dist_set_partitions(DistState* d, const uint32_t* partition_of_agg, uint64_t n_global, cudaStream_t st, std::string* err);
 int dist_route(DistState* d, const uint8_t* d_records, uint64_t n, bool fused, unsigned long long* d_counters, cudaStream_t st,
                uint64_t* n_recv_out, std::string* err);

@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "../../include/sgr.h"
+#include "bulk_fold.cuh"
 #include "devbuf.h"
 #include "dist.cuh"
 #include "fold_kernels.cuh"
@@ -21,6 +22,7 @@
 #include "group_kernels.cuh"
 #include "incremental.cuh"
 #include "keytable.h"
+#include "route_push.cuh"
 
 using namespace sgr;
 
@@ -105,6 +107,14 @@ struct sgr_engine {
   int64_t opt_incremental = 0;    // 0 auto (sort-free K6 when the program allows), 1 force the sort-based path
   int64_t opt_max_record_bytes = 528;
 
+  // sort-free fold of large arrival-order logs (bulk_fold.cu)
+  bool bulk_ok = false;
+  BulkLayout bulk_lay{};
+  DevBuf bulk_scratch, bulk_err_ids, bulk_counters, hash_out;
+  uint64_t bulk_scratch_slots = 0;
+  int64_t opt_bulk = 1;           // 0: keep arrival-order logs on the single-launch micro-batch kernel (incremental.cu)
+  int64_t opt_push_chunks = 16;   // chunks of the pipelined route + exchange + fold (route_push.cu); the same on every rank
+
   sgr_stats stats{};
 
   DistState* dist = nullptr;
@@ -118,12 +128,22 @@ struct sgr_engine {
   std::vector<uint32_t> ing_key_offs;
   const sgr_ingest* ing_keys_from = nullptr;
   std::atomic<bool> keys_stale{false};
-  std::mutex snap_mu;
+  // Every call that changes the engine (loads, folds, table growth) and the snapshot refresh of a reader hold op_mu:
+  // a reader never sees a table being freed or swapped, and a snapshot is only marked clean for the generation it copied.
+  std::recursive_mutex op_mu;
+  std::atomic<uint64_t> generation{0};
   std::shared_ptr<Snapshot> snapshot;
   std::atomic<bool> snapshot_dirty{true};
 };
 
 namespace {
+
+// serialises engine mutation against the snapshot refresh of concurrent readers (reader threads touched a table
+// the stream thread was freeing); recursive because public entry points call each other (sgr_fold_ingested)
+struct OpLock {
+  std::unique_lock<std::recursive_mutex> l;
+  explicit OpLock(sgr_engine* e) { if (e) l = std::unique_lock<std::recursive_mutex>(e->op_mu); }
+};
 
 int32_t fail(sgr_engine* e, int32_t code, const char* fmt, ...) {
   char buf[512];
@@ -193,7 +213,7 @@ int32_t compile_program(sgr_engine* e, const sgr_fold_program* p, DevProgram* d)
 
 int32_t finish_fold(sgr_engine* e);
 
-void mark_dirty(sgr_engine* e) { e->snapshot_dirty.store(true, std::memory_order_release); }
+void mark_dirty(sgr_engine* e) { e->generation.fetch_add(1, std::memory_order_acq_rel); e->snapshot_dirty.store(true, std::memory_order_release); }
 
 int32_t ensure_states(sgr_engine* e, uint64_t n_agg) {
   const size_t need = (size_t)n_agg * e->program.state_bytes;
@@ -207,8 +227,10 @@ int32_t ensure_states(sgr_engine* e, uint64_t n_agg) {
 
 // publish a host snapshot of the live state table for sgr_get
 int32_t refresh_snapshot(sgr_engine* e, std::shared_ptr<Snapshot>* out) {
-  std::lock_guard<std::mutex> g(e->snap_mu);
+  // readers (sgr_get on the store's 32-thread pool) and the stream thread's loads/folds exclude each other here
+  std::lock_guard<std::recursive_mutex> g(e->op_mu);
   if (!e->snapshot_dirty.load(std::memory_order_acquire) && e->snapshot) { *out = e->snapshot; return SGR_OK; }
+  const uint64_t gen = e->generation.load(std::memory_order_acquire);
   if (!e->states_valid) return fail(e, SGR_ERR_STATE, "state store is not readable: no fold has completed");
   int32_t rc = use_device(e); if (rc) return rc;
   rc = finish_fold(e); if (rc) return rc;
@@ -218,7 +240,8 @@ int32_t refresh_snapshot(sgr_engine* e, std::shared_ptr<Snapshot>* out) {
   CUDA_TRY(e, cudaMemcpyAsync(s->states.data(), e->states.p, s->states.size(), cudaMemcpyDeviceToHost, e->stream));
   CUDA_TRY(e, cudaStreamSynchronize(e->stream));
   std::atomic_store(&e->snapshot, s);
-  e->snapshot_dirty.store(false, std::memory_order_release);
+  // clean only for the generation that was copied (op_mu makes a concurrent bump impossible today; the check keeps it so)
+  if (e->generation.load(std::memory_order_acquire) == gen) e->snapshot_dirty.store(false, std::memory_order_release);
   *out = s;
   return SGR_OK;
 }
@@ -461,6 +484,7 @@ int32_t sgr_destroy(sgr_engine* e) {
   e->inc_records.release(); e->inc_offsets.release(); e->inc_ids.release(); e->inc_prev_ids.release();
   e->inc_scratch.release(); e->inc_touched[0].release(); e->inc_touched[1].release(); e->inc_err_ids.release(); e->inc_counters.release();
   e->group.release();
+  e->bulk_scratch.release(); e->bulk_err_ids.release(); e->bulk_counters.release(); e->hash_out.release();
   if (e->dist) dist_destroy(e->dist);
   e->part_flags.release(); e->part_data.release(); e->redo_ids.release(); e->run_counters.release();
   cudaEventDestroy(e->ev0); cudaEventDestroy(e->ev1); cudaEventDestroy(e->ev2); cudaEventDestroy(e->ev3);
@@ -470,12 +494,15 @@ int32_t sgr_destroy(sgr_engine* e) {
 }
 
 int32_t sgr_register_program(sgr_engine* e, const sgr_fold_program* prog) {
+  OpLock op_lock(e);
   if (!e || !prog) return fail(e, SGR_ERR_INVALID, "null argument");
   DevProgram d;
   int32_t rc = compile_program(e, prog, &d);
   if (rc) return rc;
   e->program = *prog; e->dprog = d; e->has_program = true;
   e->row_ok = build_row_program(d, &e->row_prog);
+  e->bulk_ok = e->row_ok && prog->record_kind == SGR_REC_FIXED64 && bulk_layout_for(e->row_prog, &e->bulk_lay);
+  e->bulk_scratch_slots = 0;
   e->row_max_grid = 0; e->run_max_grid_variant = -1;
   e->states_valid = false; e->states_n = 0;
   mark_dirty(e);
@@ -503,6 +530,7 @@ static int32_t after_load(sgr_engine* e, const uint8_t* d_events, const uint64_t
 }
 
 int32_t sgr_load_events(sgr_engine* e, const void* events, uint64_t nbytes, const uint64_t* seg_offsets, uint64_t n_agg) {
+  OpLock op_lock(e);
   if (!e || (!events && nbytes) || !seg_offsets) return fail(e, SGR_ERR_INVALID, "null argument");
   if (!e->has_program) return fail(e, SGR_ERR_NO_PROGRAM, "register a fold program before loading events");
   if (seg_offsets[n_agg] > nbytes) return fail(e, SGR_ERR_INVALID, "seg_offsets[n_agg]=%llu exceeds nbytes=%llu",
@@ -525,6 +553,7 @@ int32_t sgr_load_events(sgr_engine* e, const void* events, uint64_t nbytes, cons
 }
 
 int32_t sgr_load_events_device(sgr_engine* e, const void* d_events, uint64_t nbytes, const uint64_t* d_seg_offsets, uint64_t n_agg) {
+  OpLock op_lock(e);
   if (!e || (!d_events && nbytes) || !d_seg_offsets) return fail(e, SGR_ERR_INVALID, "null argument");
   if (!e->has_program) return fail(e, SGR_ERR_NO_PROGRAM, "register a fold program before loading events");
   if (((uintptr_t)d_events) % 16) return fail(e, SGR_ERR_INVALID, "device event log must be 16-byte aligned");
@@ -535,6 +564,7 @@ int32_t sgr_load_events_device(sgr_engine* e, const void* d_events, uint64_t nby
 
 int32_t sgr_load_events_indexed(sgr_engine* e, const void* events, uint64_t nbytes, const uint64_t* seg_offsets, uint64_t n_agg,
                                 const uint64_t* rec_offsets, uint64_t n_records) {
+  OpLock op_lock(e);
   if (!rec_offsets) return fail(e, SGR_ERR_INVALID, "null record directory");
   int32_t rc = sgr_load_events(e, events, nbytes, seg_offsets, n_agg);
   if (rc) return rc;
@@ -550,6 +580,7 @@ int32_t sgr_load_events_indexed(sgr_engine* e, const void* events, uint64_t nbyt
 
 int32_t sgr_load_events_indexed_device(sgr_engine* e, const void* d_events, uint64_t nbytes, const uint64_t* d_seg_offsets, uint64_t n_agg,
                                        const uint64_t* d_rec_offsets, uint64_t n_records) {
+  OpLock op_lock(e);
   if (!d_rec_offsets) return fail(e, SGR_ERR_INVALID, "null record directory");
   int32_t rc = sgr_load_events_device(e, d_events, nbytes, d_seg_offsets, n_agg);
   if (rc) return rc;
@@ -575,6 +606,7 @@ static int32_t load_unsorted_impl(sgr_engine* e, const void* d_records, uint64_t
 }
 
 int32_t sgr_load_unsorted_device(sgr_engine* e, const void* d_records, uint64_t n_records, uint64_t n_agg) {
+  OpLock op_lock(e);
   if (!e || (!d_records && n_records)) return fail(e, SGR_ERR_INVALID, "null argument");
   if (!e->has_program) return fail(e, SGR_ERR_NO_PROGRAM, "register a fold program before loading events");
   int32_t rc = before_load(e); if (rc) return rc;
@@ -583,6 +615,7 @@ int32_t sgr_load_unsorted_device(sgr_engine* e, const void* d_records, uint64_t 
 }
 
 int32_t sgr_load_unsorted(sgr_engine* e, const void* records, uint64_t n_records, uint64_t n_agg) {
+  OpLock op_lock(e);
   if (!e || (!records && n_records)) return fail(e, SGR_ERR_INVALID, "null argument");
   if (!e->has_program) return fail(e, SGR_ERR_NO_PROGRAM, "register a fold program before loading events");
   int32_t rc = before_load(e); if (rc) return rc;
@@ -596,6 +629,7 @@ int32_t sgr_load_unsorted(sgr_engine* e, const void* records, uint64_t n_records
 }
 
 int32_t sgr_set_initial_states(sgr_engine* e, const void* states, uint64_t n_agg) {
+  OpLock op_lock(e);
   if (!e) return SGR_ERR_INVALID;
   if (!e->has_program) return fail(e, SGR_ERR_NO_PROGRAM, "register a fold program first");
   // NULL only says "the next fold starts from None everywhere": no device work, no wait
@@ -630,17 +664,22 @@ static int32_t fold_begin(sgr_engine* e, bool pipelined) {
 }
 
 int32_t sgr_fold(sgr_engine* e) {
+  OpLock op_lock(e);
   int32_t rc = fold_begin(e, false); if (rc) return rc;
   return finish_fold(e);
 }
 
-int32_t sgr_fold_async(sgr_engine* e) { return fold_begin(e, true); }
+int32_t sgr_fold_async(sgr_engine* e) { OpLock op_lock(e); return fold_begin(e, true); }
 
 int32_t sgr_wait(sgr_engine* e) {
+  OpLock op_lock(e);
   if (!e) return SGR_ERR_INVALID;
   int32_t rc = use_device(e); if (rc) return rc;
   return finish_fold(e);
 }
+
+static int32_t replay_throwing_slots(sgr_engine* e, const void* d_records, uint64_t n_records, uint64_t n_agg, const uint32_t* d_err_ids,
+                                     uint64_t n_err, unsigned long long* h_throwing, unsigned long long* h_dropped);
 
 // sort-free path for programs inside the transformer algebra (incremental.cu)
 static int32_t fold_incremental_atomic(sgr_engine* e, const void* d_records, uint64_t n_records) {
@@ -679,25 +718,10 @@ static int32_t fold_incremental_atomic(sgr_engine* e, const void* d_records, uin
   if (h[2]) {
     // too many throwing slots to re-scan the batch for each: group the batch once and replay exactly those slots
     // on the sequential kernel (their states are still the pre-batch ones)
-    DevBuf& grouped = e->group.batch_records;
-    CUDA_TRY(e, grouped.reserve(n_records * 64));
-    CUDA_TRY(e, e->inc_offsets.reserve((n_agg + 2) * 8));
-    unsigned long long bad = 0;
-    cudaError_t ce = group_by_agg_stable(e->group, (const uint8_t*)d_records, n_records, n_agg, (uint8_t*)grouped.p, (uint64_t*)e->inc_offsets.p,
-                                         nullptr, nullptr, (unsigned long long*)e->counters.p, e->stream, &bad);
-    if (ce != cudaSuccess) return fail(e, SGR_ERR_CUDA, "group-by (replay): %s", cudaGetErrorString(ce));
-    CUDA_TRY(e, cudaMemsetAsync(e->counters.p, 0, 64, e->stream));
-    FoldArgs a{};
-    a.events = (const uint8_t*)grouped.p; a.seg_offsets = (const uint64_t*)e->inc_offsets.p; a.n_seg = h[3];
-    a.seg_list = (const uint32_t*)e->inc_err_ids.p; a.states_in = (const uint8_t*)e->states.p; a.states_out = (uint8_t*)e->states.p;
-    a.counters = (unsigned long long*)e->counters.p;
-    FoldLaunchInfo info{};
-    cudaError_t le2 = launch_fold_stream(a, e->dprog, -1, e->num_sms, e->max_record_bytes, e->stream, &info);
-    if (le2 != cudaSuccess) return fail(e, SGR_ERR_CUDA, "replay launch: %s", cudaGetErrorString(le2));
-    unsigned long long h2[8];
-    CUDA_TRY(e, cudaMemcpyAsync(h2, e->counters.p, 64, cudaMemcpyDeviceToHost, e->stream));
-    CUDA_TRY(e, cudaStreamSynchronize(e->stream));
-    h[1] = h2[1]; h[6] = h2[4];   // throwing slots, events dropped after their throw
+    unsigned long long thr = 0, drop = 0;
+    int32_t rr = replay_throwing_slots(e, d_records, n_records, n_agg, (const uint32_t*)e->inc_err_ids.p, h[3], &thr, &drop);
+    if (rr) return rr;
+    h[1] = thr; h[6] = drop;   // throwing slots, events dropped after their throw
   }
   e->inc_atomic_prev_valid = true;
   e->inc_prev_upper = (uint32_t)(h[5]);
@@ -750,6 +774,7 @@ static int32_t fold_incremental_impl(sgr_engine* e, const void* d_records, uint6
 }
 
 int32_t sgr_fold_incremental_device(sgr_engine* e, const void* d_records, uint64_t n_records) {
+  OpLock op_lock(e);
   if (!e || (!d_records && n_records)) return fail(e, SGR_ERR_INVALID, "null argument");
   if (!e->has_program) return fail(e, SGR_ERR_NO_PROGRAM, "no fold program registered");
   int32_t rc = use_device(e); if (rc) return rc;
@@ -758,6 +783,7 @@ int32_t sgr_fold_incremental_device(sgr_engine* e, const void* d_records, uint64
 }
 
 int32_t sgr_fold_incremental(sgr_engine* e, const void* records, uint64_t n_records) {
+  OpLock op_lock(e);
   if (!e || (!records && n_records)) return fail(e, SGR_ERR_INVALID, "null argument");
   if (!e->has_program) return fail(e, SGR_ERR_NO_PROGRAM, "no fold program registered");
   int32_t rc = use_device(e); if (rc) return rc;
@@ -779,6 +805,7 @@ int32_t sgr_load_keys(sgr_engine* e, const uint8_t* keys, const uint32_t* key_of
 }
 
 int32_t sgr_grow_states(sgr_engine* e, uint64_t n_agg) {
+  OpLock op_lock(e);
   if (!e) return SGR_ERR_INVALID;
   if (!e->has_program) return fail(e, SGR_ERR_NO_PROGRAM, "register a fold program first");
   int32_t rc = use_device(e); if (rc) return rc;
@@ -804,6 +831,7 @@ static void* pinned_alloc(size_t n) { void* p = nullptr; return cudaHostAlloc(&p
 static void pinned_free(void* p) { cudaFreeHost(p); }
 
 int32_t sgr_fold_ingested(sgr_engine* e, sgr_ingest* g) {
+  OpLock op_lock(e);
   if (!e || !g) return fail(e, SGR_ERR_INVALID, "null argument");
   { int32_t rc0 = use_device(e); if (rc0) return rc0; }
   // from now on the ingest decodes straight into page-locked memory (what is pending right now is moved once)
@@ -883,6 +911,7 @@ int32_t sgr_get(sgr_engine* e, const uint8_t* key, uint32_t klen, void* out, uin
 }
 
 int32_t sgr_export_states(sgr_engine* e, void* out, uint64_t cap, uint8_t* exists_bits, uint8_t* changed_bits, uint8_t* error_bits) {
+  OpLock op_lock(e);
   if (!e) return SGR_ERR_INVALID;
   if (!e->states_valid) return fail(e, SGR_ERR_STATE, "no folded state table to export");
   int32_t rc = use_device(e); if (rc) return rc;
@@ -914,6 +943,7 @@ int32_t sgr_export_states(sgr_engine* e, void* out, uint64_t cap, uint8_t* exist
 }
 
 int32_t sgr_states_device(sgr_engine* e, void** d_states, uint64_t* n_agg, uint32_t* state_bytes) {
+  OpLock op_lock(e);
   if (!e) return SGR_ERR_INVALID;
   if (!e->states_valid) return fail(e, SGR_ERR_STATE, "no folded state table");
   if (d_states) *d_states = e->states.p;
@@ -932,14 +962,82 @@ int32_t sgr_events_device(sgr_engine* e, void** d_events, uint64_t* nbytes, uint
 }
 
 int32_t sgr_get_stats(sgr_engine* e, sgr_stats* out) {
+  OpLock op_lock(e);
   if (!e || !out) return SGR_ERR_INVALID;
   if (e->fold_pending) { int32_t rc = use_device(e); if (rc) return rc; rc = finish_fold(e); if (rc) return rc; }
   *out = e->stats;
   return SGR_OK;
 }
 
+// Exact replay of the slots that saw a throwing event in a sort-free fold: the batch is grouped once (K5) and exactly those
+// slots are folded sequentially onto their untouched prior states (exact err_idx, state kept: PersistentActor.scala:260-263).
+// h_throwing / h_dropped: aggregates in error, events dropped after their throw.
+static int32_t replay_throwing_slots(sgr_engine* e, const void* d_records, uint64_t n_records, uint64_t n_agg, const uint32_t* d_err_ids,
+                                     uint64_t n_err, unsigned long long* h_throwing, unsigned long long* h_dropped) {
+  DevBuf& grouped = e->group.batch_records;
+  CUDA_TRY(e, grouped.reserve(n_records * 64));
+  CUDA_TRY(e, e->inc_offsets.reserve((n_agg + 2) * 8));
+  unsigned long long bad = 0;
+  cudaError_t ce = group_by_agg_stable(e->group, (const uint8_t*)d_records, n_records, n_agg, (uint8_t*)grouped.p, (uint64_t*)e->inc_offsets.p,
+                                       nullptr, nullptr, (unsigned long long*)e->counters.p, e->stream, &bad);
+  if (ce != cudaSuccess) return fail(e, SGR_ERR_CUDA, "group-by (replay): %s", cudaGetErrorString(ce));
+  CUDA_TRY(e, cudaMemsetAsync(e->counters.p, 0, 64, e->stream));
+  FoldArgs a{};
+  a.events = (const uint8_t*)grouped.p; a.seg_offsets = (const uint64_t*)e->inc_offsets.p; a.n_seg = n_err;
+  a.seg_list = d_err_ids; a.states_in = (const uint8_t*)e->states.p; a.states_out = (uint8_t*)e->states.p;
+  a.counters = (unsigned long long*)e->counters.p;
+  FoldLaunchInfo info{};
+  cudaError_t le2 = launch_fold_stream(a, e->dprog, -1, e->num_sms, e->max_record_bytes, e->stream, &info);
+  if (le2 != cudaSuccess) return fail(e, SGR_ERR_CUDA, "replay launch: %s", cudaGetErrorString(le2));
+  unsigned long long h2[8];
+  CUDA_TRY(e, cudaMemcpyAsync(h2, e->counters.p, 64, cudaMemcpyDeviceToHost, e->stream));
+  CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+  *h_throwing = h2[1]; *h_dropped = h2[4];
+  return SGR_OK;
+}
+
+static int32_t ensure_bulk_buffers(sgr_engine* e, uint64_t n_agg) {
+  if (e->bulk_scratch_slots != n_agg || !e->bulk_scratch.p) {
+    const size_t need = bulk_scratch_bytes(e->bulk_lay, n_agg);
+    CUDA_TRY(e, e->bulk_scratch.reserve(need));
+    CUDA_TRY(e, cudaMemsetAsync(e->bulk_scratch.p, 0, need, e->stream));   // the finish pass leaves it zero again
+    e->bulk_scratch_slots = n_agg;
+  }
+  CUDA_TRY(e, e->bulk_err_ids.reserve((n_agg + 1) * 4));
+  CUDA_TRY(e, e->bulk_counters.reserve(64));
+  return SGR_OK;
+}
+
+// sort-free fold of a large arrival-order log onto the (zeroed or prior) state table: accumulate + finish (bulk_fold.cu)
+static int32_t fold_bulk(sgr_engine* e, const uint8_t* d_records, uint64_t n_records, uint64_t n_agg) {
+  int32_t rc = ensure_bulk_buffers(e, n_agg); if (rc) return rc;
+  unsigned long long* cnt = (unsigned long long*)e->bulk_counters.p;
+  CUDA_TRY(e, cudaEventRecord(e->ev0, e->stream));
+  CUDA_TRY(e, cudaMemsetAsync(cnt, 0, 64, e->stream));
+  BulkSrc src{};
+  src.n_regions = 1; src.base[0] = d_records; src.count[0] = n_records; src.rec_bytes = 64;
+  cudaError_t le = launch_bulk_accumulate(src, n_agg, e->bulk_scratch.p, e->row_prog, e->bulk_lay, cnt, e->num_sms, e->stream);
+  if (le == cudaSuccess) le = launch_bulk_finish(n_agg, e->bulk_scratch.p, (uint8_t*)e->states.p, (uint32_t*)e->bulk_err_ids.p, e->bulk_lay, cnt, e->stream);
+  if (le != cudaSuccess) return fail(e, SGR_ERR_CUDA, "bulk fold launch: %s", cudaGetErrorString(le));
+  CUDA_TRY(e, cudaEventRecord(e->ev1, e->stream));
+  unsigned long long h[8];
+  CUDA_TRY(e, cudaMemcpyAsync(h, cnt, 64, cudaMemcpyDeviceToHost, e->stream));
+  CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+  CUDA_TRY(e, cudaEventElapsedTime(&e->stats.ms_fold, e->ev0, e->ev1));
+  if (h[4]) { e->states_valid = false; return fail(e, SGR_ERR_INVALID, "%llu records carry an aggregate index >= n_agg; nothing was applied", h[4]); }
+  unsigned long long throwing = 0, dropped = 0;
+  if (h[3]) { rc = replay_throwing_slots(e, d_records, n_records, n_agg, (const uint32_t*)e->bulk_err_ids.p, h[3], &throwing, &dropped); if (rc) return rc; }
+  e->stats.ms_group = 0;
+  e->stats.n_aggregates = n_agg; e->stats.n_errors = throwing; e->stats.n_events = n_records - dropped;
+  e->stats.event_bytes = n_records * 64; e->stats.n_long_segments = 0;
+  e->stats.algorithmic_bytes = n_records * 64 + (uint64_t)(16 + 2 * e->program.state_bytes) * n_agg;
+  e->stats.fold_launches = 2;
+  mark_dirty(e);
+  return SGR_OK;
+}
+
 // Fold an arrival-order log (aggregates interleaved, per-aggregate order kept) from None.
-// class-0 programs need no grouping at all: the records are folded with integer atomics (incremental.cu);
+// class-0 programs need no grouping at all: the records are folded with integer atomics (bulk_fold.cu / incremental.cu);
 // other programs are grouped stably (K5) and folded from the CSR.
 static int32_t fold_arrival_order(sgr_engine* e, const uint8_t* d_records, uint64_t n_records, uint64_t n_agg) {
   const bool sort_free = e->row_ok && e->row_prog.user_words == 2 && e->row_prog.cls == 0 && !e->row_prog.f64_mask && e->opt_kernel != 1 && e->opt_kernel != 3 &&
@@ -948,8 +1046,13 @@ static int32_t fold_arrival_order(sgr_engine* e, const uint8_t* d_records, uint6
   if (sort_free) {
     rc = ensure_states(e, n_agg); if (rc) return rc;
     CUDA_TRY(e, cudaMemsetAsync(e->states.p, 0, (size_t)n_agg * e->program.state_bytes, e->stream));
-    e->states_valid = true; e->inc_atomic_prev_valid = true; e->inc_prev_upper = 0;   // a fresh all-None table: no per-batch flags to clear
+    e->states_valid = true;
     e->loaded = false;
+    if (e->bulk_ok && e->opt_bulk && n_records < (1ull << 30)) {
+      e->inc_atomic_prev_valid = false; e->inc_prev_n = 0;   // the next micro-batch clears every slot's per-batch flags
+      return fold_bulk(e, d_records, n_records, n_agg);
+    }
+    e->inc_atomic_prev_valid = true; e->inc_prev_upper = 0;   // a fresh all-None table: no per-batch flags to clear
     rc = fold_incremental_atomic(e, d_records, n_records);
     if (rc) return rc;
     e->stats.ms_group = 0;
@@ -962,6 +1065,7 @@ static int32_t fold_arrival_order(sgr_engine* e, const uint8_t* d_records, uint6
 }
 
 int32_t sgr_fold_unsorted_device(sgr_engine* e, const void* d_records, uint64_t n_records, uint64_t n_agg) {
+  OpLock op_lock(e);
   if (!e || (!d_records && n_records)) return fail(e, SGR_ERR_INVALID, "null argument");
   if (!e->has_program) return fail(e, SGR_ERR_NO_PROGRAM, "register a fold program first");
   if (e->program.record_kind != SGR_REC_FIXED64) return fail(e, SGR_ERR_UNSUPPORTED, "arrival-order logs take fixed 64-byte records");
@@ -971,6 +1075,7 @@ int32_t sgr_fold_unsorted_device(sgr_engine* e, const void* d_records, uint64_t 
 }
 
 int32_t sgr_fold_unsorted(sgr_engine* e, const void* records, uint64_t n_records, uint64_t n_agg) {
+  OpLock op_lock(e);
   if (!e || (!records && n_records)) return fail(e, SGR_ERR_INVALID, "null argument");
   if (!e->has_program) return fail(e, SGR_ERR_NO_PROGRAM, "register a fold program first");
   if (e->program.record_kind != SGR_REC_FIXED64) return fail(e, SGR_ERR_UNSUPPORTED, "arrival-order logs take fixed 64-byte records");
@@ -994,6 +1099,7 @@ int32_t sgr_dist_unique_id(void* out128) {
 }
 
 int32_t sgr_dist_init(sgr_engine* e, int32_t rank, int32_t nranks, const void* unique_id128, uint64_t recv_capacity_records) {
+  OpLock op_lock(e);
   if (!e || (nranks > 1 && !unique_id128)) return fail(e, SGR_ERR_INVALID, "null argument");
   int32_t rc = use_device(e); if (rc) return rc;
   if (e->dist) { dist_destroy(e->dist); e->dist = nullptr; }
@@ -1005,6 +1111,7 @@ int32_t sgr_dist_init(sgr_engine* e, int32_t rank, int32_t nranks, const void* u
 }
 
 int32_t sgr_dist_set_partitions(sgr_engine* e, const uint32_t* partition_of_agg, uint64_t n_global_agg) {
+  OpLock op_lock(e);
   if (!e || !partition_of_agg) return fail(e, SGR_ERR_INVALID, "null argument");
   if (!e->dist) return fail(e, SGR_ERR_NOT_LOADED, "call sgr_dist_init first");
   int32_t rc = before_load(e); if (rc) return rc;
@@ -1015,6 +1122,7 @@ int32_t sgr_dist_set_partitions(sgr_engine* e, const uint32_t* partition_of_agg,
 }
 
 int32_t sgr_dist_ipc_export(sgr_engine* e, void* out64) {
+  OpLock op_lock(e);
   if (!e || !out64 || !e->dist) return fail(e, SGR_ERR_INVALID, "null argument / no dist state");
   int32_t rc = use_device(e); if (rc) return rc;
   std::string err;
@@ -1024,6 +1132,7 @@ int32_t sgr_dist_ipc_export(sgr_engine* e, void* out64) {
 }
 
 int32_t sgr_dist_ipc_import(sgr_engine* e, const void* handles64_by_rank) {
+  OpLock op_lock(e);
   if (!e || !handles64_by_rank || !e->dist) return fail(e, SGR_ERR_INVALID, "null argument / no dist state");
   int32_t rc = use_device(e); if (rc) return rc;
   std::string err;
@@ -1033,6 +1142,7 @@ int32_t sgr_dist_ipc_import(sgr_engine* e, const void* handles64_by_rank) {
 }
 
 int32_t sgr_dist_route_and_fold(sgr_engine* e, const void* d_records, uint64_t n_records, int32_t fused) {
+  OpLock op_lock(e);
   if (!e || (!d_records && n_records)) return fail(e, SGR_ERR_INVALID, "null argument");
   if (!e->has_program) return fail(e, SGR_ERR_NO_PROGRAM, "register a fold program first");
   if (!e->dist) return fail(e, SGR_ERR_NOT_LOADED, "call sgr_dist_init first");
@@ -1042,6 +1152,43 @@ int32_t sgr_dist_route_and_fold(sgr_engine* e, const void* d_records, uint64_t n
   uint64_t n_recv = 0;
   e->stats.ms_h2d = 0;
   const bool routed = dist_nranks(e->dist) > 1 || e->opt_force_route;
+  // fused >= 2: pipelined push (route + exchange + fold overlapped, route_push.cu); 3 = exchange only the words the program reads.
+  // Programs outside the sort-free formulation take the scatter + group-by path below (every rank holds the same program).
+  if (routed && fused >= 2 && e->bulk_ok && e->opt_incremental != 1) {
+    const uint64_t n_local = dist_n_local(e->dist);
+    rc = ensure_states(e, n_local); if (rc) return rc;
+    rc = ensure_bulk_buffers(e, n_local); if (rc) return rc;
+    CUDA_TRY(e, cudaMemsetAsync(e->states.p, 0, (size_t)n_local * e->program.state_bytes, e->stream));
+    e->states_valid = true; e->loaded = false; e->inc_atomic_prev_valid = false; e->inc_prev_n = 0;
+    PushFoldArgs pf{};
+    pf.prog = &e->row_prog; pf.lay = &e->bulk_lay; pf.scratch = e->bulk_scratch.p; pf.states = (uint8_t*)e->states.p;
+    pf.err_ids = (uint32_t*)e->bulk_err_ids.p; pf.counters = (unsigned long long*)e->bulk_counters.p; pf.n_slots = n_local;
+    pf.n_chunks = (uint32_t)e->opt_push_chunks; pf.compact = fused == 3; pf.num_sms = e->num_sms;
+    PushFoldResult res;
+    int r = dist_push_fold(e->dist, (const uint8_t*)d_records, n_records, pf, e->stream, &res, &err);
+    if (r) { e->states_valid = false; e->bulk_scratch_slots = 0; return fail(e, r, "%s", err.c_str()); }
+    unsigned long long throwing = 0, dropped = 0;
+    if (res.n_err_slots) {
+      const uint8_t* contiguous = nullptr;
+      r = dist_gather_regions(e->dist, res, e->row_prog, e->stream, &contiguous, &err);
+      if (r) return fail(e, r, "%s", err.c_str());
+      rc = replay_throwing_slots(e, contiguous, res.n_recv, n_local, (const uint32_t*)e->bulk_err_ids.p, res.n_err_slots, &throwing, &dropped);
+      if (rc) return rc;
+    }
+    e->stats.ms_group = 0; e->stats.ms_fold = res.ms_total - res.ms_push;   // what the fold adds behind the last push
+    e->stats.n_aggregates = n_local; e->stats.n_errors = throwing; e->stats.n_events = res.n_recv - dropped;
+    e->stats.event_bytes = res.n_recv * 64; e->stats.n_long_segments = 0; e->stats.fold_launches = 2 * (uint32_t)e->opt_push_chunks + 1;
+    e->stats.algorithmic_bytes = res.n_recv * 64 + (uint64_t)(16 + 2 * e->program.state_bytes) * n_local;
+    mark_dirty(e);
+    const DistStats* ds = dist_stats(e->dist);
+    e->dstats = sgr_dist_stats{};
+    e->dstats.n_sent = ds->n_sent; e->dstats.n_sent_remote = ds->n_sent_remote; e->dstats.n_recv = ds->n_recv;
+    e->dstats.n_local_aggregates = n_local;
+    e->dstats.ms_scatter = res.ms_push; e->dstats.ms_fold = e->stats.ms_fold;
+    e->dstats.ms_pipeline = res.ms_total; e->dstats.exchange_record_bytes = res.out_bytes;
+    return SGR_OK;
+  }
+  if (fused >= 2) fused = dist_nranks(e->dist) > 1 ? 1 : 0;
   if (!routed) {
     // one rank owns everything and local index == global index: no exchange
     dist_clear_stats(e->dist, n_records);
@@ -1070,6 +1217,7 @@ int32_t sgr_dist_get_stats(sgr_engine* e, sgr_dist_stats* out) {
 }
 
 int32_t sgr_dist_local_aggregates(sgr_engine* e, uint32_t* out, uint64_t cap, uint64_t* n_local) {
+  OpLock op_lock(e);
   if (!e || !e->dist) return fail(e, SGR_ERR_INVALID, "no dist state");
   const uint64_t n = dist_n_local(e->dist);
   if (n_local) *n_local = n;
@@ -1082,12 +1230,53 @@ int32_t sgr_dist_local_aggregates(sgr_engine* e, uint32_t* out, uint64_t cap, ui
   return SGR_OK;
 }
 
+int32_t sgr_dist_set_peers(sgr_engine* e, void* const* recv_bases_by_rank) {
+  OpLock op_lock(e);
+  if (!e || !recv_bases_by_rank || !e->dist) return fail(e, SGR_ERR_INVALID, "null argument / no dist state");
+  std::string err;
+  int r = dist_set_peers(e->dist, recv_bases_by_rank, &err);
+  if (r) return fail(e, r, "%s", err.c_str());
+  return SGR_OK;
+}
+
+int32_t sgr_dist_recv_base(sgr_engine* e, void** base) {
+  if (!e || !base || !e->dist) return fail(e, SGR_ERR_INVALID, "null argument / no dist state");
+  *base = dist_recv_base(e->dist);
+  return SGR_OK;
+}
+
+int32_t sgr_states_hash(sgr_engine* e, uint64_t* out) {
+  OpLock op_lock(e);
+  if (!e || !out) return fail(e, SGR_ERR_INVALID, "null argument");
+  if (!e->states_valid) return fail(e, SGR_ERR_STATE, "no folded state table");
+  int32_t rc = use_device(e); if (rc) return rc;
+  rc = finish_fold(e); if (rc) return rc;
+  CUDA_TRY(e, e->hash_out.reserve(64));
+  // a routed table is hashed under its GLOBAL aggregate indices, so the sum over the ranks does not depend on their number
+  const uint32_t* gids = (e->dist && (dist_nranks(e->dist) > 1 || e->opt_force_route) && dist_n_local(e->dist) == e->states_n) ? dist_global_of_local(e->dist) : nullptr;
+  cudaError_t ce = launch_states_hash((const uint8_t*)e->states.p, e->states_n, e->program.state_bytes, gids, (unsigned long long*)e->hash_out.p, e->stream);
+  if (ce != cudaSuccess) return fail(e, SGR_ERR_CUDA, "hash launch: %s", cudaGetErrorString(ce));
+  unsigned long long h = 0;
+  CUDA_TRY(e, cudaMemcpyAsync(&h, e->hash_out.p, 8, cudaMemcpyDeviceToHost, e->stream));
+  CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+  *out = h;
+  return SGR_OK;
+}
+
 int32_t sgr_set_option(sgr_engine* e, const char* name, int64_t value) {
   if (!e || !name) return SGR_ERR_INVALID;
   if (!strcmp(name, "fold_variant")) { e->opt_variant = value; return SGR_OK; }
   if (!strcmp(name, "kernel")) { e->opt_kernel = value; return SGR_OK; }
   if (!strcmp(name, "incremental")) { e->opt_incremental = value; return SGR_OK; }
   if (!strcmp(name, "force_route")) { e->opt_force_route = value; return SGR_OK; }
+  if (!strcmp(name, "bulk")) { e->opt_bulk = value; return SGR_OK; }
+  if (!strcmp(name, "bulk_unroll")) { bulk_tuning().unroll = (int)value; return SGR_OK; }
+  if (!strcmp(name, "bulk_hints")) { bulk_tuning().hints = (int)value; return SGR_OK; }
+  if (!strcmp(name, "bulk_blocks_per_sm")) { bulk_tuning().blocks_per_sm = (int)value; return SGR_OK; }
+  if (!strcmp(name, "push_chunks")) {
+    if (value < 1 || value > 256) return fail(e, SGR_ERR_INVALID, "push_chunks must be in [1, 256]");
+    e->opt_push_chunks = value; return SGR_OK;
+  }
   if (!strcmp(name, "replay_budget")) { e->opt_replay_budget = value; return SGR_OK; }
   if (!strcmp(name, "var_stage_bytes")) { e->opt_var_stage_bytes = value; return SGR_OK; }
   if (!strcmp(name, "var_stages")) { e->opt_var_stages = (value >= 1 && value <= 3) ? value : 2; return SGR_OK; }

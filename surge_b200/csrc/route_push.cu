@@ -1,0 +1,447 @@
+// route_push.cu — pipelined route + exchange + fold over peer memory (sm_100a, NVLink 5 / NVSwitch).
+//
+// The reference shards by key and lets the BROKER shuffle: aggregateId -> partitionForKey
+// (modules/common/src/main/scala/surge/kafka/KafkaPartitioner.scala:7-9) -> owner node
+// (KafkaProducerHelperCommon.getPartitionFor, modules/common/src/main/scala/surge/kafka/KafkaProducer.scala:45-57).
+// Here every rank holds the records of its source partitions in arrival order and ONE pass does route + all-to-all:
+//
+//   source log, cut into C chunks in log order
+//     push kernel (one launch per chunk, 1024 records per CTA):
+//        cp.async the CTA's records into shared memory (64 KiB), look up owner | local index of every record,
+//        counting-sort the CTA's records by owner in shared memory (stable), obtain the CTA's offset inside each owner's
+//        region by a decoupled look-back over the earlier CTAs of the chunk (ordered by a ticket), then write every owner's
+//        run CONTIGUOUSLY into region (me, chunk) of that owner's receive buffer through the peer mapping: 512 contiguous
+//        bytes per warp store, records rewritten to the owner's local aggregate index. One read of the log, one write, no
+//        send buffer, no count pass, no host synchronisation.
+//     flag kernel: (epoch << 32 | count + 1) into every owner's header -> region (me, chunk) is complete
+//   second stream, per chunk: wait for the flags of all sources, then the sort-free accumulate (bulk_fold.cu) over the
+//     chunk's regions; after the last chunk the finish pass by slot. The fold of chunk c overlaps the push of chunk c+1.
+//
+// Per-aggregate order: all events of an aggregate come from ONE source (one key -> one partition); chunks are in log order,
+// the partition inside a CTA is stable, CTAs are ordered by the look-back, and the arrival index the fold uses is
+// chunk * region_capacity + position: monotone along the aggregate's own order. Nothing else matters to the fold.
+//
+// Receive layout on every rank: header | regions [source][chunk] of region_capacity records. Fixed-capacity regions are
+// what makes the single pass possible; a region that would overflow drops nothing silently: the sender marks the flag,
+// every rank learns it (error gather) and the call fails with SGR_ERR_CAPACITY on ALL ranks before any state is published.
+//
+// compact != 0: only what the fold program reads crosses NVLink (projection): u32 local index + the program's slot words,
+// 16 bytes per record for the Counter model instead of 64.
+#include "route_push.cuh"
+
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/sgr.h"
+#include "dist_state.h"
+
+namespace sgr {
+namespace {
+
+constexpr int kPushThreads = 256;
+constexpr int kPushRecs = 1024;
+constexpr int kPushRounds = kPushRecs / kPushThreads;   // 4
+constexpr int kPushWarps = kPushThreads / 32;           // 8
+constexpr size_t kPushSmem = (size_t)kPushRecs * 64 + kPushRecs * 4 + kPushRecs * 2 + kPushRecs;
+constexpr unsigned long long kSpinLimit = 1ull << 26;   // ~ seconds: a lost peer must not hang the GPU
+
+struct PushArgs {
+  const uint8_t* rec;            // first record of this chunk
+  uint32_t n;                    // records in this chunk
+  uint32_t nranks;
+  uint64_t n_global;
+  const uint32_t* route_of;      // owner << 28 | local index
+  uint8_t* dst[kMaxRanks];       // region (me, chunk) in every owner's receive buffer
+  uint32_t cap_region;           // records
+  uint32_t out_bytes;            // 64, or the compact stride
+  unsigned long long* lb;        // look-back cells of this chunk: [cta][kMaxRanks], flag << 62 | count (1 local, 2 inclusive)
+  uint32_t* ticket;              // CTA order of this chunk
+  uint32_t* totals;              // [kMaxRanks]: records sent to each owner by this chunk
+  unsigned long long* status;    // [0] records with a global index out of range [1] records that did not fit their region
+                                 // [2] spin time-outs [3] error flags received
+  uint32_t n_proj;               // compact: number of projected record words
+  uint32_t proj_word[7];
+};
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void st_na_v4(void* p, const uint4& v) {
+  asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+extern __shared__ __align__(16) uint8_t push_smem[];
+
+__global__ void __launch_bounds__(kPushThreads) route_push_kernel(const __grid_constant__ PushArgs a) {
+  uint8_t* srec = push_smem;                                              // [1024][64]
+  uint32_t* loc = reinterpret_cast<uint32_t*>(push_smem + kPushRecs * 64); // [1024] local index, by record
+  uint16_t* perm = reinterpret_cast<uint16_t*>(loc + kPushRecs);          // [1024] sorted position -> record
+  uint8_t* own_s = reinterpret_cast<uint8_t*>(perm + kPushRecs);          // [1024] owner, by sorted position
+  __shared__ uint32_t wcnt[kPushRounds][kPushWarps][kMaxRanks];
+  __shared__ uint32_t start[kMaxRanks + 1], excl[kMaxRanks], cnt[kMaxRanks];
+  __shared__ uint32_t s_bid, s_ok;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const uint32_t R = a.nranks;
+  if (t == 0) { s_bid = atomicAdd(a.ticket, 1u); s_ok = 0xffffffffu; }
+  __syncthreads();
+  const uint32_t bid = s_bid;
+  const uint32_t base = bid * kPushRecs;
+  const uint32_t nrec = a.n - base < (uint32_t)kPushRecs ? a.n - base : (uint32_t)kPushRecs;
+  const uint8_t* src = a.rec + (uint64_t)base * 64;
+  // ---- the CTA's records -> shared memory (asynchronous; the owner lookups below run meanwhile)
+#pragma unroll
+  for (int it = 0; it < 16; ++it) {
+    const uint32_t q = it * kPushThreads + t;
+    if (q < nrec * 4) cp_async16(srec + (size_t)q * 16, src + (size_t)q * 16);
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  // ---- owner | local index of this thread's 4 records (record r = round * 256 + t: lanes hold consecutive records)
+  unsigned long long g[kPushRounds];
+#pragma unroll
+  for (int j = 0; j < kPushRounds; ++j) {
+    const uint32_t r = j * kPushThreads + t;
+    g[j] = r < nrec ? *reinterpret_cast<const unsigned long long*>(src + (size_t)r * 64 + 8) : ~0ull;
+  }
+  uint32_t o[kPushRounds], rk[kPushRounds];
+#pragma unroll
+  for (int j = 0; j < kPushRounds; ++j) {
+    const uint32_t r = j * kPushThreads + t;
+    o[j] = 0xffu; rk[j] = 0;
+    if (r < nrec) {
+      if (g[j] < a.n_global) { const uint32_t ro = __ldg(a.route_of + g[j]); o[j] = ro >> 28; loc[r] = ro & 0x0fffffffu; }
+      else atomicAdd(a.status + 0, 1ull);
+    }
+  }
+  // ---- stable rank inside the warp, per owner
+#pragma unroll
+  for (int j = 0; j < kPushRounds; ++j) {
+    for (uint32_t rr = 0; rr < R; ++rr) {
+      const uint32_t m = __ballot_sync(0xffffffffu, o[j] == rr);
+      if (o[j] == rr) rk[j] = __popc(m & ((1u << lane) - 1u));
+      if (lane == 0) wcnt[j][warp][rr] = __popc(m);
+    }
+  }
+  __syncthreads();
+  // ---- exclusive scan over (round, warp) per owner
+  if (t < (int)R) {
+    uint32_t run = 0;
+#pragma unroll
+    for (int j = 0; j < kPushRounds; ++j)
+#pragma unroll
+      for (int w = 0; w < kPushWarps; ++w) { const uint32_t c = wcnt[j][w][t]; wcnt[j][w][t] = run; run += c; }
+    cnt[t] = run;
+  }
+  __syncthreads();
+  if (t == 0) {
+    uint32_t s = 0;
+    for (uint32_t rr = 0; rr < R; ++rr) { start[rr] = s; s += cnt[rr]; }
+    start[R] = s;
+  }
+  // ---- decoupled look-back (warp 1, lane = owner): this CTA's offset inside each owner's region of the chunk
+  if (warp == 1 && lane < (int)R) {
+    const uint32_t local = cnt[lane];
+    unsigned long long* mine = a.lb + (size_t)bid * kMaxRanks + lane;
+    uint32_t ex = 0;
+    if (bid == 0) {
+      st_relaxed_u64(mine, (2ull << 62) | local);
+    } else {
+      st_relaxed_u64(mine, (1ull << 62) | local);
+      uint32_t jb = bid - 1;
+      unsigned long long spins = 0;
+      for (;;) {
+        const unsigned long long v = ld_relaxed_u64(a.lb + (size_t)jb * kMaxRanks + lane);
+        const uint32_t fl = (uint32_t)(v >> 62);
+        if (fl == 0) {
+          if (++spins > kSpinLimit) { atomicAdd(a.status + 2, 1ull); break; }
+          __nanosleep(20);
+          continue;
+        }
+        ex += (uint32_t)v;
+        if (fl == 2 || jb == 0) break;
+        --jb;
+      }
+      st_relaxed_u64(mine, (2ull << 62) | (ex + local));
+    }
+    excl[lane] = ex;
+    if ((unsigned long long)ex + local > a.cap_region) {   // would overflow the region: nothing of this CTA goes to that owner
+      atomicAnd(&s_ok, ~(1u << lane));
+      atomicAdd(a.status + 1, (unsigned long long)local);
+    }
+    if (base + nrec >= a.n) a.totals[lane] = ex + local;    // the chunk's last CTA: its inclusive prefix is the chunk total
+  }
+  __syncthreads();
+  // ---- sorted position of every record
+#pragma unroll
+  for (int j = 0; j < kPushRounds; ++j) {
+    if (o[j] != 0xffu) {
+      const uint32_t p = start[o[j]] + wcnt[j][warp][o[j]] + rk[j];
+      perm[p] = (uint16_t)(j * kPushThreads + t);
+      own_s[p] = (uint8_t)o[j];
+    }
+  }
+  asm volatile("cp.async.wait_all;" ::: "memory");
+  __syncthreads();
+  const uint32_t nvalid = start[R];
+  const uint32_t ok = s_ok;
+  if (a.out_bytes == 64u) {
+    // ---- every owner's run, contiguous: thread -> (sorted position, 16-byte piece)
+#pragma unroll 4
+    for (int it = 0; it < 16; ++it) {
+      const uint32_t q = it * kPushThreads + t;
+      const uint32_t p = q >> 2, k = q & 3u;
+      if (p < nvalid) {
+        const uint32_t r = perm[p], ow = own_s[p];
+        if ((ok >> ow) & 1u) {
+          uint4 v = *reinterpret_cast<const uint4*>(srec + (size_t)r * 64 + k * 16);
+          if (k == 0) { v.z = loc[r]; v.w = 0u; }   // agg := the owner's LOCAL aggregate index
+          st_na_v4(a.dst[ow] + (size_t)(excl[ow] + p - start[ow]) * 64 + k * 16, v);
+        }
+      }
+    }
+  } else {
+    // ---- projection: u32 local index, then the program's slot words (slot 0 = event type)
+    const uint32_t ow4 = a.out_bytes >> 2;
+#pragma unroll
+    for (int j = 0; j < kPushRounds; ++j) {
+      const uint32_t p = j * kPushThreads + t;
+      if (p < nvalid) {
+        const uint32_t r = perm[p], ow = own_s[p];
+        if ((ok >> ow) & 1u) {
+          const uint32_t* rw = reinterpret_cast<const uint32_t*>(srec + (size_t)r * 64);
+          uint32_t out[8];
+          out[0] = loc[r];
+#pragma unroll
+          for (uint32_t k = 0; k < 7; ++k) out[1 + k] = k < a.n_proj ? rw[a.proj_word[k]] : 0u;
+          uint8_t* dp = a.dst[ow] + (size_t)(excl[ow] + p - start[ow]) * a.out_bytes;
+          st_na_v4(dp, make_uint4(out[0], out[1], out[2], out[3]));
+          if (ow4 > 4) st_na_v4(dp + 16, make_uint4(out[4], out[5], out[6], out[7]));
+        }
+      }
+    }
+  }
+}
+
+struct FlagArgs {
+  unsigned long long* peer_flag[kMaxRanks];   // &header(owner).flags[me][chunk]
+  const uint32_t* totals;
+  const unsigned long long* status;
+  uint32_t nranks, epoch;
+};
+// after the chunk's push kernel (stream order): every store of the chunk is performed, publish the counts
+__global__ void push_flag_kernel(const __grid_constant__ FlagArgs f) {
+  const uint32_t lane = threadIdx.x;
+  if (lane < f.nranks) {
+    const bool bad = f.status[1] != 0 || f.status[2] != 0;
+    const unsigned long long v = ((unsigned long long)f.epoch << 32) | (bad ? 0xffffffffull : (unsigned long long)(f.totals[lane] + 1u));
+    __threadfence_system();
+    st_release_sys(f.peer_flag[lane], v);
+  }
+}
+// receiver: region (s, chunk) of every source is complete (or a source reported an error)
+__global__ void push_wait_kernel(const unsigned long long* flags, uint32_t chunk, uint32_t nranks, uint32_t epoch, unsigned long long* status) {
+  const uint32_t lane = threadIdx.x;
+  if (lane < nranks) {
+    const unsigned long long* p = flags + (size_t)lane * kMaxChunks + chunk;
+    unsigned long long spins = 0;
+    for (;;) {
+      const unsigned long long v = ld_acquire_sys(p);
+      if ((uint32_t)(v >> 32) == epoch) { if ((uint32_t)v == 0xffffffffu) atomicAdd(status + 3, 1ull); break; }
+      if (++spins > kSpinLimit) { atomicAdd(status + 2, 1ull); break; }
+      __nanosleep(100);
+    }
+  }
+}
+
+// replay support: region -> contiguous 64-byte records (compact records are expanded: the program reads nothing else)
+__global__ void gather_region_kernel(const uint8_t* __restrict__ src, uint32_t n, uint32_t in_bytes, uint8_t* __restrict__ dst,
+                                     uint32_t n_proj, const uint32_t* __restrict__ proj_word) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint4* d4 = reinterpret_cast<uint4*>(dst + i * 64);
+  if (in_bytes == 64u) {
+    const uint4* s4 = reinterpret_cast<const uint4*>(src + i * 64);
+    for (int k = 0; k < 4; ++k) d4[k] = s4[k];
+    return;
+  }
+  uint32_t w[16];
+  for (int k = 0; k < 16; ++k) w[k] = 0;
+  const uint32_t* s = reinterpret_cast<const uint32_t*>(src + i * in_bytes);
+  for (uint32_t k = 0; k < n_proj; ++k) {
+    const uint32_t pw = proj_word[k];
+    for (int q = 0; q < 16; ++q) if ((uint32_t)q == pw) w[q] = s[1 + k];
+  }
+  w[2] = s[0]; w[3] = 0;
+  for (int k = 0; k < 4; ++k) d4[k] = make_uint4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
+}
+
+}  // namespace
+
+int dist_push_fold(DistState* d, const uint8_t* d_records, uint64_t n, const PushFoldArgs& pf, cudaStream_t st, PushFoldResult* out,
+                   std::string* err) {
+  cudaError_t ce;
+#define DTRY(x) if ((ce = (x)) != cudaSuccess) { *err = std::string(#x ": ") + cudaGetErrorString(ce); return SGR_ERR_CUDA; }
+#define NTRY(x) { ncclResult_t _r = (x); if (_r != ncclSuccess) { *err = std::string(#x ": ") + nccl_api().GetErrorString(_r); return SGR_ERR_DIST; } }
+  const int R = d->nranks;
+  if (!d->n_global) { *err = "no partition table: call sgr_dist_set_partitions first"; return SGR_ERR_NOT_LOADED; }
+  if (R > 1 && !d->peers_mapped) { *err = "the push path needs the peers' receive buffers (sgr_dist_ipc_import / sgr_dist_set_peers)"; return SGR_ERR_NOT_LOADED; }
+  if (d->n_global > (1ull << 28)) { *err = "push path: at most 2^28 global aggregates"; return SGR_ERR_UNSUPPORTED; }
+  const uint32_t C = pf.n_chunks;
+  if (C < 1 || C > (uint32_t)kMaxChunks) { *err = "push_chunks out of range"; return SGR_ERR_INVALID; }
+  const uint64_t cap_region = d->recv_capacity / ((uint64_t)R * C);
+  if (!cap_region) { *err = "receive buffer too small for R x chunks regions"; return SGR_ERR_CAPACITY; }
+  if ((uint64_t)C * cap_region >= (1ull << 30)) { *err = "push path: chunks x region capacity must stay below 2^30 records"; return SGR_ERR_UNSUPPORTED; }
+  // chunk size: whole CTAs, the same number of chunks on every rank (the flags are indexed by chunk)
+  uint64_t chunk_recs = (n + C - 1) / C;
+  chunk_recs = (chunk_recs + kPushRecs - 1) / kPushRecs * kPushRecs;
+  if (chunk_recs >= (1ull << 31)) { *err = "push path: chunk too large, raise push_chunks"; return SGR_ERR_UNSUPPORTED; }
+  const uint32_t out_bytes = pf.compact ? ((1 + pf.prog->n_slots) * 4 <= 16 ? 16u : 32u) : 64u;
+  if (pf.compact && pf.prog->n_slots > 7) { *err = "compact exchange: program reads more than 7 record words"; return SGR_ERR_UNSUPPORTED; }
+  const uint64_t ctas_per_chunk = chunk_recs / kPushRecs;
+  // control block: tickets[C] | totals[C][kMaxRanks] | status[8] u64 | proj words
+  const size_t off_tot = (size_t)kMaxChunks * 4, off_status = off_tot + (size_t)kMaxChunks * kMaxRanks * 4, off_proj = off_status + 64;
+  DTRY(d->push_ctl.reserve(off_proj + 64));
+  DTRY(d->lb.reserve((size_t)C * ctas_per_chunk * kMaxRanks * 8 + 256));
+  DTRY(d->counts_all.reserve((size_t)kMaxRanks * kMaxRanks * 8 + 64));
+  uint32_t* tickets = (uint32_t*)d->push_ctl.p;
+  uint32_t* totals = (uint32_t*)((uint8_t*)d->push_ctl.p + off_tot);
+  unsigned long long* status = (unsigned long long*)((uint8_t*)d->push_ctl.p + off_status);
+  static bool attr_set = false;
+  if (!attr_set) {
+    DTRY(cudaFuncSetAttribute(route_push_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPushSmem));
+    attr_set = true;
+  }
+  const uint32_t epoch = ++d->epoch;
+  cudaStream_t s0 = st, s1 = d->stream2;
+  DTRY(cudaMemsetAsync(d->push_ctl.p, 0, off_proj + 64, s0));
+  DTRY(cudaMemsetAsync(d->lb.p, 0, (size_t)C * ctas_per_chunk * kMaxRanks * 8, s0));
+  DTRY(cudaMemsetAsync(pf.counters, 0, 64, s0));
+  // everybody has finished the previous call (its folds read the regions this call overwrites)
+  if (R > 1 && !d->loopback) NTRY(nccl_api().AllGather((uint8_t*)d->push_ctl.p + off_proj, d->counts_all.p, 1, ncclUint32, d->comm, s0));
+  DTRY(cudaEventRecord(d->pev[0], s0));
+  DTRY(cudaStreamWaitEvent(s1, d->pev[0], 0));
+  unsigned long long* my_flags = (unsigned long long*)d->peer_base[d->rank];
+  for (uint32_t c = 0; c < C; ++c) {
+    const uint64_t begin = (uint64_t)c * chunk_recs;
+    const uint64_t cn = begin >= n ? 0 : (n - begin < chunk_recs ? n - begin : chunk_recs);
+    if (cn) {
+      PushArgs a{};
+      a.rec = d_records + begin * 64; a.n = (uint32_t)cn; a.nranks = (uint32_t)R; a.n_global = d->n_global;
+      a.route_of = (const uint32_t*)d->route_of.p;
+      for (int q = 0; q < R; ++q) a.dst[q] = d->peer_recv[q] + ((uint64_t)d->rank * C + c) * cap_region * out_bytes;
+      a.cap_region = (uint32_t)cap_region; a.out_bytes = out_bytes;
+      a.lb = (unsigned long long*)d->lb.p + (size_t)c * ctas_per_chunk * kMaxRanks;
+      a.ticket = tickets + c; a.totals = totals + (size_t)c * kMaxRanks; a.status = status;
+      if (pf.compact) { a.n_proj = pf.prog->n_slots; for (uint32_t k = 0; k < a.n_proj; ++k) a.proj_word[k] = pf.prog->slot_word[k]; }
+      const uint32_t grid = (uint32_t)((cn + kPushRecs - 1) / kPushRecs);
+      route_push_kernel<<<grid, kPushThreads, kPushSmem, s0>>>(a);
+    }
+    FlagArgs f{};
+    for (int q = 0; q < R; ++q) f.peer_flag[q] = (unsigned long long*)d->peer_base[q] + (size_t)d->rank * kMaxChunks + c;
+    f.totals = totals + (size_t)c * kMaxRanks; f.status = status; f.nranks = (uint32_t)R; f.epoch = epoch;
+    push_flag_kernel<<<1, 32, 0, s0>>>(f);
+    // ---- receiver side of chunk c
+    push_wait_kernel<<<1, 32, 0, s1>>>(my_flags, c, (uint32_t)R, epoch, status);
+    BulkSrc bs{};
+    bs.n_regions = (uint32_t)R; bs.compact = pf.compact ? 1u : 0u; bs.rec_bytes = out_bytes;
+    for (int s = 0; s < R; ++s) {
+      bs.base[s] = d->peer_recv[d->rank] + ((uint64_t)s * C + c) * cap_region * out_bytes;
+      bs.count_flag[s] = my_flags + (size_t)s * kMaxChunks + c;
+      bs.count[s] = cap_region;
+      bs.idx_base[s] = (uint32_t)((uint64_t)c * cap_region);
+    }
+    DTRY(launch_bulk_accumulate(bs, pf.n_slots, pf.scratch, *pf.prog, *pf.lay, pf.counters, pf.num_sms, s1));
+  }
+  DTRY(cudaGetLastError());
+  DTRY(cudaEventRecord(d->pev[1], s0));    // all pushes issued and flagged
+  DTRY(launch_bulk_finish(pf.n_slots, pf.scratch, pf.states, pf.err_ids, *pf.lay, pf.counters, s1));
+  DTRY(cudaEventRecord(d->pev[2], s1));
+  DTRY(cudaStreamWaitEvent(s0, d->pev[2], 0));
+  DTRY(cudaEventRecord(d->pev[3], s0));
+  // ---- results
+  unsigned long long h_status[8], h_cnt[8];
+  std::vector<unsigned long long> h_flags((size_t)kMaxRanks * kMaxChunks);
+  DTRY(cudaMemcpyAsync(h_status, status, 64, cudaMemcpyDeviceToHost, s0));
+  DTRY(cudaMemcpyAsync(h_cnt, pf.counters, 64, cudaMemcpyDeviceToHost, s0));
+  DTRY(cudaMemcpyAsync(h_flags.data(), my_flags, h_flags.size() * 8, cudaMemcpyDeviceToHost, s0));
+  DTRY(cudaStreamSynchronize(s0));
+  float ms_push = 0, ms_total = 0;
+  cudaEventElapsedTime(&ms_push, d->pev[0], d->pev[1]);
+  cudaEventElapsedTime(&ms_total, d->pev[0], d->pev[3]);
+  uint64_t n_recv = 0; bool remote_err = false;
+  out->regions.clear();
+  for (int s = 0; s < R; ++s)
+    for (uint32_t c = 0; c < C; ++c) {
+      const unsigned long long v = h_flags[(size_t)s * kMaxChunks + c];
+      if ((uint32_t)(v >> 32) != epoch || (uint32_t)v == 0xffffffffu) { remote_err = true; continue; }
+      const uint32_t cnt = (uint32_t)v - 1u;
+      n_recv += cnt;
+      out->regions.push_back({d->peer_recv[d->rank] + ((uint64_t)s * C + c) * cap_region * out_bytes, cnt});
+    }
+  int my_err = SGR_OK;
+  if (h_status[0]) { *err = std::to_string(h_status[0]) + " records carry a global aggregate index >= n_global"; my_err = SGR_ERR_INVALID; }
+  else if (h_status[2]) { *err = "time-out waiting for a peer / an earlier CTA (push path)"; my_err = SGR_ERR_DIST; }
+  else if (h_status[1]) { *err = std::to_string(h_status[1]) + " records did not fit their receive region (capacity " + std::to_string(cap_region) + " records per source and chunk)"; my_err = SGR_ERR_CAPACITY; }
+  else if (remote_err || h_status[3]) { *err = "a source rank reported a full receive region"; my_err = SGR_ERR_CAPACITY; }
+  else if (h_cnt[4]) { *err = std::to_string(h_cnt[4]) + " arrived records carry a local index out of range"; my_err = SGR_ERR_INVALID; }
+  // every rank fails or nobody does: gather the verdicts (the fold of a failed call is discarded by the caller)
+  if (R > 1 && !d->loopback) {
+    uint32_t mine = my_err ? 1u : 0u, all[kMaxRanks] = {};
+    DTRY(cudaMemcpyAsync((uint8_t*)d->push_ctl.p + off_proj, &mine, 4, cudaMemcpyHostToDevice, s0));
+    NTRY(nccl_api().AllGather((uint8_t*)d->push_ctl.p + off_proj, d->counts_all.p, 1, ncclUint32, d->comm, s0));
+    DTRY(cudaMemcpyAsync(all, d->counts_all.p, (size_t)R * 4, cudaMemcpyDeviceToHost, s0));
+    DTRY(cudaStreamSynchronize(s0));
+    if (!my_err) for (int q = 0; q < R; ++q) if (all[q]) { *err = "rank " + std::to_string(q) + " failed the exchange"; my_err = SGR_ERR_DIST; break; }
+  }
+  out->n_recv = n_recv; out->n_err_slots = h_cnt[3]; out->ms_push = ms_push; out->ms_total = ms_total; out->out_bytes = out_bytes;
+  d->stats = DistStats{};
+  d->stats.n_sent = n; d->stats.n_recv = n_recv;
+  d->stats.ms_scatter = ms_push; d->stats.ms_exchange = 0;
+  uint64_t kept = 0;
+  {
+    // what stayed local: region (me, *) — read back from my own flags
+    for (uint32_t c = 0; c < C; ++c) { const unsigned long long v = h_flags[(size_t)d->rank * kMaxChunks + c]; if ((uint32_t)(v >> 32) == epoch && (uint32_t)v != 0xffffffffu) kept += (uint32_t)v - 1u; }
+  }
+  d->stats.n_sent_remote = n >= kept ? n - kept : 0;
+  return my_err;
+#undef DTRY
+#undef NTRY
+}
+
+// contiguous 64-byte copy of everything that arrived, regions in (source, chunk) order: an aggregate's events keep their order
+int dist_gather_regions(DistState* d, const PushFoldResult& res, const RowProgram& prog, cudaStream_t st, const uint8_t** out, std::string* err) {
+  cudaError_t ce = d->gather_buf.reserve(res.n_recv * 64 + 256);
+  if (ce != cudaSuccess) { *err = std::string("gather buffer: ") + cudaGetErrorString(ce); return SGR_ERR_OOM; }
+  uint32_t* d_proj = nullptr;
+  if (res.out_bytes != 64u) {
+    d_proj = (uint32_t*)((uint8_t*)d->gather_buf.p + res.n_recv * 64);
+    if ((ce = cudaMemcpyAsync(d_proj, prog.slot_word, 7 * 4, cudaMemcpyHostToDevice, st)) != cudaSuccess) { *err = cudaGetErrorString(ce); return SGR_ERR_CUDA; }
+  }
+  uint64_t off = 0;
+  for (const auto& rg : res.regions) {
+    if (!rg.count) continue;
+    gather_region_kernel<<<(rg.count + 255) / 256, 256, 0, st>>>(rg.base, rg.count, res.out_bytes, (uint8_t*)d->gather_buf.p + off * 64, prog.n_slots, d_proj);
+    off += rg.count;
+  }
+  if ((ce = cudaGetLastError()) != cudaSuccess) { *err = cudaGetErrorString(ce); return SGR_ERR_CUDA; }
+  *out = (const uint8_t*)d->gather_buf.p;
+  return SGR_OK;
+}
+
+}  // namespace sgr

@@ -1,0 +1,38 @@
+// route_push.cuh — pipelined route + exchange + fold over peer memory (route_push.cu), used by engine.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "bulk_fold.cuh"
+#include "dist.cuh"
+
+namespace sgr {
+
+struct PushFoldArgs {
+  const RowProgram* prog;
+  const BulkLayout* lay;
+  void* scratch;                 // bulk_scratch_bytes(lay, n_slots), zero outside a fold
+  uint8_t* states;               // n_slots x 16, prior states (all zero for a rebuild)
+  uint32_t* err_ids;             // n_slots + 1
+  unsigned long long* counters;  // 8 x u64
+  uint64_t n_slots;
+  uint32_t n_chunks;             // the same on every rank
+  bool compact;                  // exchange only the record words the program reads
+  int num_sms;
+};
+struct PushRegion { const uint8_t* base; uint32_t count; };
+struct PushFoldResult {
+  uint64_t n_recv = 0, n_err_slots = 0;
+  float ms_push = 0, ms_total = 0;
+  uint32_t out_bytes = 64;
+  std::vector<PushRegion> regions;   // what arrived, in (source, chunk) order
+};
+
+int dist_push_fold(DistState* d, const uint8_t* d_records, uint64_t n, const PushFoldArgs& pf, cudaStream_t st, PushFoldResult* out,
+                   std::string* err);
+int dist_gather_regions(DistState* d, const PushFoldResult& res, const RowProgram& prog, cudaStream_t st, const uint8_t** out, std::string* err);
+
+}  // namespace sgr

@@ -55,6 +55,30 @@ def route_on_host(records: np.ndarray, owner: np.ndarray, local: np.ndarray, nra
     return out
 
 
+def _splitmix64(x: np.ndarray) -> np.ndarray:
+    x = (x + np.uint64(0x9E3779B97F4A7C15)).astype(np.uint64)
+    x = (x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+    x = (x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+    return x ^ (x >> np.uint64(31))
+
+
+def states_hash(states: np.ndarray, global_ids: Optional[np.ndarray] = None) -> int:
+    """numpy twin of sgr_states_hash (csrc/bulk_fold.cu states_hash_kernel): sum over slots of
+    mix(id, state bytes) mod 2^64 — order independent, so per-rank hashes of a routed table add up to the hash of the
+    whole table under global aggregate indices."""
+    st = np.ascontiguousarray(states).view(np.uint8)
+    n = st.shape[0]
+    if n == 0:
+        return 0
+    words = st.reshape(n, -1).view(np.uint64)
+    ids = np.arange(n, dtype=np.uint64) if global_ids is None else np.asarray(global_ids).astype(np.uint64)
+    with np.errstate(over="ignore"):
+        h = _splitmix64(ids)
+        for k in range(words.shape[1]):
+            h = _splitmix64(h ^ words[:, k])
+        return int(h.sum(dtype=np.uint64))
+
+
 def partitions_of_rank(rank: int, nranks: int, num_partitions: int) -> List[int]:
     """Topic partitions a rank consumes when the store is fed from the topic itself (surge_b200/ingest.py): the broker has already
     done the shuffle — every record of an aggregate sits in partition partitionForKey(id) — so rank r decodes and folds the

@@ -231,11 +231,28 @@ class ReplayEngine:
         blob = C.create_string_buffer(b"".join(handles), 64 * len(handles))
         self._ck(self._lib.sgr_dist_ipc_import(self._h, blob))
 
-    def dist_route_and_fold(self, records, fused: bool) -> None:
-        """records: CUDA tensor of fixed 64-byte records in arrival order carrying GLOBAL aggregate indices."""
+    def dist_route_and_fold(self, records, fused) -> None:
+        """records: CUDA tensor of fixed 64-byte records in arrival order carrying GLOBAL aggregate indices.
+        fused: 0 NCCL all-to-all, 1 peer scatter, 2 pipelined push + fold, 3 the same with projected records (see sgr.h)."""
         r = records.contiguous().view(-1)
         self._keep = [r]
-        self._ck(self._lib.sgr_dist_route_and_fold(self._h, r.data_ptr(), r.numel() * r.element_size() // 64, 1 if fused else 0))
+        self._ck(self._lib.sgr_dist_route_and_fold(self._h, r.data_ptr(), r.numel() * r.element_size() // 64, int(fused)))
+
+    def dist_recv_base(self) -> int:
+        p = C.c_void_p()
+        self._ck(self._lib.sgr_dist_recv_base(self._h, C.byref(p)))
+        return int(p.value or 0)
+
+    def dist_set_peers(self, bases: Sequence[int]) -> None:
+        """Loopback ranks (one process, one device): the other ranks' receive allocations as raw device pointers."""
+        arr = (C.c_void_p * len(bases))(*[C.c_void_p(b) for b in bases])
+        self._ck(self._lib.sgr_dist_set_peers(self._h, arr))
+
+    def states_hash(self) -> int:
+        """Order-independent 64-bit hash of the live table (global aggregate indices on a routed engine)."""
+        h = C.c_uint64()
+        self._ck(self._lib.sgr_states_hash(self._h, C.byref(h)))
+        return int(h.value)
 
     def dist_stats(self) -> N.sgr_dist_stats:
         s = N.sgr_dist_stats()

@@ -60,7 +60,8 @@ class sgr_config(C.Structure):
 class sgr_dist_stats(C.Structure):
     _fields_ = [("n_sent", C.c_uint64), ("n_sent_remote", C.c_uint64), ("n_recv", C.c_uint64), ("n_local_aggregates", C.c_uint64),
                 ("ms_count", C.c_float), ("ms_counts_exchange", C.c_float), ("ms_scatter", C.c_float), ("ms_exchange", C.c_float),
-                ("ms_group", C.c_float), ("ms_fold", C.c_float), ("reserved", C.c_uint32 * 6)]
+                ("ms_group", C.c_float), ("ms_fold", C.c_float), ("ms_pipeline", C.c_float), ("exchange_record_bytes", C.c_uint32),
+                ("reserved", C.c_uint32 * 4)]
 
 
 class sgr_stats(C.Structure):
@@ -125,6 +126,9 @@ ABI = [
     ("sgr_dist_ipc_export", C.c_int32, [_P, _P]),
     ("sgr_dist_ipc_import", C.c_int32, [_P, _P]),
     ("sgr_dist_route_and_fold", C.c_int32, [_P, _P, C.c_uint64, C.c_int32]),
+    ("sgr_dist_recv_base", C.c_int32, [_P, C.POINTER(C.c_void_p)]),
+    ("sgr_dist_set_peers", C.c_int32, [_P, _P]),
+    ("sgr_states_hash", C.c_int32, [_P, C.POINTER(C.c_uint64)]),
     ("sgr_dist_get_stats", C.c_int32, [_P, C.POINTER(sgr_dist_stats)]),
     ("sgr_dist_local_aggregates", C.c_int32, [_P, _P, C.c_uint64, C.POINTER(C.c_uint64)]),
     ("sgr_partitions_for_keys", C.c_int32, [_P, _P, C.c_uint64, C.c_uint32, C.c_int32, _P]),

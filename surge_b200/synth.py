@@ -126,3 +126,68 @@ def counter_csr_device(n_agg: int, events_per_agg: int, seed: int, device: str =
     rec[:, 8:16] = torch.randint(-(1 << 31), 1 << 31, (n, 8), generator=g, device=device, dtype=torch.int64).to(torch.int32)
     off = torch.arange(n_agg + 1, device=device, dtype=torch.int64) * (events_per_agg * 64)
     return rec, off
+
+
+# ---------------------------------------------------------------- configs[2]: a log that is a pure function of (aggregate, event index)
+# Every rank count sees the SAME logical log (so state hashes are comparable across N), and the CPU oracle can regenerate the
+# events of any sampled aggregate without holding the 64 GB log.
+_SM_A, _SM_B, _SM_G = 0xBF58476D1CE4E5B9, 0x94D049BB133111EB, 0x9E3779B97F4A7C15
+
+
+def _routed_key(g, k, seed):
+    return g * 1000003 + k * 7919 + seed * 0x51ED27
+
+
+def routed_events_host(g_ids: np.ndarray, epa: int, seed: int) -> Tuple[np.ndarray, np.ndarray]:
+    """Counter events of the given global aggregates, CSR order (numpy twin of routed_log_device): event k of aggregate g has
+    type/by = f(splitmix64(g, k, seed)), seq = k + 1. Records carry agg = position in g_ids."""
+    g = np.repeat(np.asarray(g_ids, dtype=np.uint64), epa)
+    k = np.tile(np.arange(epa, dtype=np.uint64), len(g_ids))
+    with np.errstate(over="ignore"):
+        x = _routed_key(g, k, np.uint64(seed)) + np.uint64(_SM_G)
+        x = (x ^ (x >> np.uint64(30))) * np.uint64(_SM_A)
+        x = (x ^ (x >> np.uint64(27))) * np.uint64(_SM_B)
+        x = x ^ (x >> np.uint64(31))
+    u = (x & np.uint64(0xFFFF)).astype(np.int64)
+    types = np.where(u < 29491, F.COUNT_INCREMENTED, np.where(u < 58982, F.COUNT_DECREMENTED, F.NO_OP_EVENT)).astype(np.uint32)
+    by = ((x >> np.uint64(16)) & np.uint64(0x7FFFFFFF)).astype(np.int64).astype(np.int32)
+    agg = np.repeat(np.arange(len(g_ids), dtype=np.uint64), epa)
+    rec = F.counter_records(types, (k + np.uint64(1)).astype(np.uint32), agg, by)
+    return rec, F.csr_offsets_from_counts(np.full(len(g_ids), epa, dtype=np.int64))
+
+
+def routed_log_device(rank: int, world: int, n_global: int, epa: int, seed: int, device: str):
+    """This rank's share of the configs[2] log, on the device, in ARRIVAL order: the rank holds the source partitions of the
+    aggregates g with g % world == rank; event k of every one of its aggregates comes before event k+1 of any (aggregates
+    interleaved, every aggregate's own order kept). Records carry the GLOBAL aggregate index. int32[n, 16] CUDA tensor."""
+    import torch
+
+    def s64(c):
+        return c - (1 << 64) if c >= (1 << 63) else c
+
+    def lsr(x, k):
+        return (x >> k) & ((1 << (64 - k)) - 1)
+
+    g = torch.arange(rank, n_global, world, device=device, dtype=torch.int64)
+    na = g.numel()
+    rec = torch.zeros((na * epa, 16), dtype=torch.int32, device=device)
+    g32 = g.to(torch.int32)
+    for k in range(epa):   # one round of events at a time keeps the temporaries small (the full log is 64 GB)
+        x = g * 1000003 + (k * 7919 + seed * 0x51ED27) + s64(_SM_G)
+        x = (x ^ lsr(x, 30)) * s64(_SM_A)
+        x = (x ^ lsr(x, 27)) * s64(_SM_B)
+        x = x ^ lsr(x, 31)
+        u = x & 0xFFFF
+        blk = rec[k * na:(k + 1) * na]
+        blk[:, 0] = torch.where(u < 29491, F.COUNT_INCREMENTED, torch.where(u < 58982, F.COUNT_DECREMENTED, F.NO_OP_EVENT)).to(torch.int32)
+        blk[:, 1] = k + 1
+        blk[:, 2] = g32
+        blk[:, 4] = (lsr(x, 16) & 0x7FFFFFFF).to(torch.int32)
+    return rec
+
+
+def routed_partitions(n_global: int, num_partitions: int = 64) -> np.ndarray:
+    """State-topic partition of every dense aggregate id for the synthetic configs[2] runs: ids are pre-hashed once on load
+     — a multiplicative hash stands in for partitionForKey on 10^7 synthetic ids."""
+    with np.errstate(over="ignore"):
+        return ((np.arange(n_global, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15)) >> np.uint64(40)).astype(np.uint32) % np.uint32(num_partitions)
