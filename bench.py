@@ -1,22 +1,27 @@
 #!/usr/bin/env python
 """bench.py — events/sec of the segmented event fold (BASELINE.json metric) on N B200s of one node.
 
-A "step" is one full pass of the hot path over one batch of synthetic input: rebuilding every
-aggregate's state from its CSR event log (configs[1]: 1,048,576 aggregates x 32 fixed 64-byte
-events = 2 GiB of events per GPU; the log is far larger than the 126 MB L2, so no flush is needed
-between timed iterations).
+A "step" is one full pass of the hot path over one batch of synthetic input: rebuilding every aggregate's state from its
+CSR event log (configs[1]: 1,048,576 aggregates x 32 fixed 64-byte events = 2 GiB of events per GPU; the log is far larger
+than the 126 MB L2, so no flush is needed between timed iterations).
 
-  value   whole-job events/s with the log resident in HBM, K pipelined folds, CUDA events on the
-          engine's stream, max over ranks (weak scaling: every rank folds its own shard of
-          aggregates, no data-path collective — aggregates are independent units)
-  e2e     the same metric through the C ABI with HOST buffers: every step copies the log from pinned
-          host memory (sgr_load_events), folds (sgr_fold) and reads the state table back
-          (sgr_export_states)
+  value   whole-job events/s with the log resident in HBM, K pipelined folds, CUDA events on the engine's stream, max over
+          ranks (weak scaling of the fold itself: every rank folds its own shard of aggregates)
+  e2e     the same metric through the C ABI with HOST buffers: every step copies the log from pinned host memory
+          (sgr_load_events), folds (sgr_fold) and reads the state table back (sgr_export_states)
   roofline   algorithmic bytes / device time of the fold kernel against the measured HBM peak
-  cpu_baseline   the CPU oracle (port of the reference's fold) on this box's host cores
+  cpu_baseline   the CPU oracle (port of the reference's fold) on this box's host cores, NUMA-placed log, pinned threads
+  routed  configs[2], the configuration north_star names for N GPUs: the FULL problem (10 M aggregates x 100 events = 64 GB,
+          arrival order, pre-distributed by source partition) strong-scaled over the N ranks: hash-partition by aggregate, ONE
+          exchange over NVLink, fold — pipelined (surge_b200/csrc/route_push.cu). Every mode prints a 64-bit hash of the
+          whole state table (sum over ranks; identical at N = 1, 2, 4, 8 by construction of the log), the same hash from an
+          independent vectorised torch restatement of the Counter fold over the full table, and a 4096-aggregate sample
+          checked against the CPU oracle.
+  configs every other BASELINE.json config (N = 1 only): configs[0] BankAccount, configs[3] Zipf / variable records at full
+          size, configs[4] streaming micro-batches — each with its own parity check.
 
-`--impl reference` times the reference's CPU implementation of the path instead (the oracle port:
-the reference is Scala/JVM and cannot be built in this image), rank 0 only.
+`--impl reference` times the reference's CPU implementation of the path instead (the oracle port: the reference is Scala/JVM
+and cannot be built in this image), rank 0 only.
 """
 from __future__ import annotations
 
@@ -37,6 +42,11 @@ EVENTS_PER_AGG = 32
 STATE_BYTES = 16
 METRIC = "events/sec replayed (segmented per-aggregate event fold)"
 WORKLOAD = "configs[1]: 1,048,576 aggregates x 32 fixed-width 64-B events, single B200 segmented fold (per GPU)"
+ROUTED_N_GLOBAL = 10_000_000     # configs[2]: 10 M aggregates x 100 events, hash-partitioned, one exchange
+ROUTED_EPA = 100
+ROUTED_SEED = 3
+NVLINK_PEAK_GBS = 770.0          # measured peer copy per direction per GPU on this pool (B200_PROFILING.md)
+M64 = (1 << 64) - 1
 
 
 def algorithmic_bytes(n_agg: int, epa: int) -> int:
@@ -111,8 +121,9 @@ class ClockSampler:
                 "samples": len(mhz)}
 
 
+# ---------------------------------------------------------------------------------------------------- CPU legs
 def host_config2_log(n_agg: int, epa: int, seed: int):
-    """The config-2 Counter log built on the host (numpy), for the CPU legs."""
+    """The configs[1] Counter log built on the host (numpy), for the CPU legs."""
     import numpy as np
 
     from surge_b200 import formats as F
@@ -130,14 +141,24 @@ def host_config2_log(n_agg: int, epa: int, seed: int):
     return rec, off
 
 
-def time_cpu_oracle(rec, off, threads: int, min_seconds: float, max_reps: int):
+def cpu_fold_setup(rec, off, threads: int):
+    """NUMA-sane CPU arm: the log is copied once into fresh memory by the pinned workers that will fold it (first touch puts
+    every worker's byte range on its own node); every timed pass then runs with worker t on CPU t."""
     from oracle import oracle as O
 
     O.fold_packed(O.MODEL_COUNTER, O.REC_FIXED64, rec[: 64 * 16], off[:33], threads=1)  # load the library
+    return O.place_log(rec, off, threads)
+
+
+def time_cpu_oracle(rec, off, threads: int, min_seconds: float, max_reps: int):
+    from oracle import oracle as O
+
+    placed = cpu_fold_setup(rec, off, threads)
+    O.fold_packed(O.MODEL_COUNTER, O.REC_FIXED64, placed, off, threads=threads, pinned=True)   # warm-up pass
     reps, t_total, nev = 0, 0.0, 0
     while reps < max_reps and (reps == 0 or t_total < min_seconds):
         t0 = time.perf_counter()
-        _, n, _ = O.fold_packed(O.MODEL_COUNTER, O.REC_FIXED64, rec, off, threads=threads)
+        _, n, _ = O.fold_packed(O.MODEL_COUNTER, O.REC_FIXED64, placed, off, threads=threads, pinned=True)
         t_total += time.perf_counter() - t0
         nev += n
         reps += 1
@@ -150,118 +171,386 @@ def run_reference(args) -> None:
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    # one step = one pass over the full configs[1] log (33.5 M events, 2 GiB, far larger than any CPU cache, like the
-    # GPU arm's step); a cache-resident sample would overstate what the CPU path does on this workload
-    n_agg = N_AGG
-    rec, off = host_config2_log(n_agg, EVENTS_PER_AGG, seed=2)
+    # one step = one pass over the full configs[1] log (33.5 M events, 2 GiB, far larger than any CPU cache, like the GPU arm's
+    # step); a cache-resident sample would overstate what the CPU path does on this workload
+    rec, off = host_config2_log(N_AGG, EVENTS_PER_AGG, seed=2)
     from oracle import oracle as O
 
+    placed = cpu_fold_setup(rec, off, cores)
+    del rec
     for _ in range(max(args.warmup, 1)):
-        O.fold_packed(O.MODEL_COUNTER, O.REC_FIXED64, rec, off, threads=cores)
+        O.fold_packed(O.MODEL_COUNTER, O.REC_FIXED64, placed, off, threads=cores, pinned=True)
     t0 = time.perf_counter()
     nev = 0
     for _ in range(args.steps):
-        _, n, _ = O.fold_packed(O.MODEL_COUNTER, O.REC_FIXED64, rec, off, threads=cores)
+        _, n, _ = O.fold_packed(O.MODEL_COUNTER, O.REC_FIXED64, placed, off, threads=cores, pinned=True)
         nev += n
     dt = time.perf_counter() - t0
     value = nev / dt
-    sample = f"{n_agg} aggregates x {EVENTS_PER_AGG} events per step (the full configs[1] log, pageable host memory), {args.steps} steps"
+    sample = (f"{N_AGG} aggregates x {EVENTS_PER_AGG} events per step (the full configs[1] log, host memory first-touched by the "
+              f"pinned worker that folds it), {args.steps} steps")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": "events/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "i32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": sample, "impl_note": "CPU port of the reference's fold (oracle/sgr_oracle.c); the Scala/JVM reference cannot be built in this image"},
+        "config": {"workload": WORKLOAD, "sample": sample, "impl_note": "CPU port of the reference's fold (oracle/sgr_oracle.c), one pinned thread per "
+                   "hardware thread; the Scala/JVM reference cannot be built in this image"},
         "cpu_baseline": {"value": value, "unit": "events/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "events/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
 
-ROUTED_AGG_PER_GPU = 1_250_000   # configs[2]: 10 M aggregates x 100 events over 8 GPUs = 1.25 M x 100 per GPU
-ROUTED_EPA = 100
+# ---------------------------------------------------------------------------------------------------- parity helpers (torch)
+def _s64(c: int) -> int:
+    return c - (1 << 64) if c >= (1 << 63) else c
 
 
-def routed_pipeline(rank, world, local_rank, dev, barrier, note, strong=False):
-    """configs[2]-shaped per-GPU work (weak: 1.25 M aggregates x 100 events of 64 B originate on every rank):
-    route (K4) + exchange (NCCL all-to-all, then fused peer-memory scatter) + stable group-by (K5) + fold.
-    Stage times are CUDA-event times on the engine's stream, max over ranks; the job rate uses the wall time
-    of the whole call, max over ranks."""
+def _lsr(x, k: int):
+    return (x >> k) & ((1 << (64 - k)) - 1)
+
+
+def _splitmix64_t(x):
+    x = x + _s64(0x9E3779B97F4A7C15)
+    x = (x ^ _lsr(x, 30)) * _s64(0xBF58476D1CE4E5B9)
+    x = (x ^ _lsr(x, 27)) * _s64(0x94D049BB133111EB)
+    return x ^ _lsr(x, 31)
+
+
+def torch_states_hash(words64, gids) -> int:
+    """torch twin of sgr_states_hash (csrc/bulk_fold.cu): words64 = the state table viewed as int64 [n, state_bytes / 8]."""
+    h = _splitmix64_t(gids)
+    for k in range(words64.shape[1]):
+        h = _splitmix64_t(h ^ words64[:, k])
+    return int(h.sum().item()) & M64
+
+
+def routed_expected_hash(gids, epa: int, seed: int) -> int:
+    """Independent vectorised restatement of the Counter fold (scaladsl TestBoundedContext.scala:77-89) over the deterministic
+    configs[2] log, for the aggregates `gids` (int64 CUDA tensor), from None: count = wrapped sum of +-by, version = seq of the
+    last counting event, every aggregate exists and changed. Returns the state hash of that table."""
+    import torch
+
+    from surge_b200 import synth as S
+
+    count = torch.zeros_like(gids, dtype=torch.int32)
+    version = torch.zeros_like(gids, dtype=torch.int32)
+    for k in range(epa):
+        typ, by = S.routed_round(gids, k, seed)
+        count = count + torch.where(typ == 0, by, torch.where(typ == 1, -by, torch.zeros_like(by)))
+        version = torch.where(typ < 2, torch.full_like(version, k + 1), version)
+    w0 = (count.to(torch.int64) & 0xFFFFFFFF) | (version.to(torch.int64) << 32)
+    w1 = torch.full_like(w0, 3)   # EXISTS | CHANGED, err_idx 0
+    return torch_states_hash(torch.stack([w0, w1], 1), gids)
+
+
+# ---------------------------------------------------------------------------------------------------- configs[2]
+def config2_routed(rank, world, local_rank, dev, barrier, note, scale: float, iters: int):
     import numpy as np
     import torch
     import torch.distributed as dist
 
+    from oracle import oracle as O
     from surge_b200 import ReplayEngine
     from surge_b200 import dist as D
     from surge_b200 import programs as P
+    from surge_b200 import synth as S
 
-    n_global = ROUTED_AGG_PER_GPU * (8 if strong else world)   # strong: always the full 10 M x 100 problem
+    n_global = max(int(ROUTED_N_GLOBAL * scale) // 64 * 64, 64)
     epa = ROUTED_EPA
-    # this rank's source partitions hold the aggregates g with g % world == rank, in arrival order
-    # (event k of every aggregate before event k+1: aggregates interleaved, per-aggregate order kept)
-    g_mine = torch.arange(rank, n_global, world, device=dev, dtype=torch.int64)
-    n = g_mine.numel() * epa
-    gen = torch.Generator(device=dev)
-    gen.manual_seed(1000 + rank)
-    r = torch.zeros((n, 16), dtype=torch.int32, device=dev)
-    na = g_mine.numel()
-    g32 = (g_mine & 0xFFFFFFFF).to(torch.int32)
-    for k in range(epa):   # one "round" of events at a time keeps the temporaries small (matters for the 64 GB case)
-        blk = r[k * na:(k + 1) * na]
-        u = torch.rand(na, generator=gen, device=dev)
-        blk[:, 0] = torch.where(u < 0.45, 0, torch.where(u < 0.9, 1, 2)).to(torch.int32)
-        blk[:, 1] = k + 1
-        blk[:, 2] = g32
-        blk[:, 4] = torch.randint(0, 1 << 31, (na,), generator=gen, device=dev, dtype=torch.int64).to(torch.int32)
-    del u, g32
-    # ownership: partition = a multiplicative hash of the dense id (ids are pre-hashed once on load, SURVEY 8e), 64 partitions
-    part = ((np.arange(n_global, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15)) >> np.uint64(40)).astype(np.uint32) % np.uint32(64)
-    cap = int(n * 1.15) + 1_000_000
-    res = {"workload": (f"configs[2] FULL problem, strong: {n_global} aggregates x {epa} events x 64 B = {n_global * epa * 64 / 1e9:.0f} GB split over {world} rank(s)"
-                        if strong else f"configs[2] shape, weak: {ROUTED_AGG_PER_GPU} aggregates x {epa} events x 64 B originate per GPU, "
-                        f"{n_global} aggregates hash-partitioned over {world} rank(s)"), "events_total": int(n) * world}
-    # sort-free: the arrived records are folded with integer atomics (K6 kernel), no group-by; sorted_group: K5 + K1
-    for mode, fused, sort_based in (("nccl_all_to_all", False, False), ("fused_peer_scatter", True, False), ("nccl_all_to_all_sorted_group", False, True)):
-        if world == 1 and fused:
-            continue
-        if strong and sort_based:
-            continue   # the group-by's scratch does not fit next to 64 GB of records on one GPU
-        eng = ReplayEngine(local_rank)
-        eng.register_program(P.counter_program())
-        if sort_based:
-            eng.set_option("incremental", 1)
-        D.exchange_ids(eng, rank, world, cap, fused=fused)
+    rec = S.routed_log_device(rank, world, n_global, epa, ROUTED_SEED, dev)
+    n = rec.shape[0]
+    flat = rec.view(torch.uint8).view(-1)
+    part = S.routed_partitions(n_global, 64)
+    total_events = n_global * epa
+    res = {"workload": f"configs[2]{'' if scale == 1.0 else f' x {scale}'}: {n_global} aggregates x {epa} events x 64 B = {total_events * 64 / 1e9:.1f} GB, "
+                       f"arrival order, pre-distributed by source partition over {world} rank(s); owner = partition(hash(id)) % nranks; strong scaling",
+           "events_total": total_events, "n_ranks": world}
+    # the oracle's word on a sample of aggregates (the same sample at every N)
+    sample = np.random.default_rng(2024).choice(n_global, size=min(4096, n_global), replace=False).astype(np.int64)
+    sample.sort()
+    srec, soff = S.routed_events_host(sample, epa, ROUTED_SEED)
+    want_sample, _, _ = O.fold_packed(O.MODEL_COUNTER, O.REC_FIXED64, srec, soff, threads=min(os.cpu_count() or 1, 16))
+
+    eng = ReplayEngine(local_rank)
+    eng.register_program(P.counter_program())
+    if world > 1:
+        cap = int(n * 1.12) + 64 * 1024 * world
+        D.exchange_ids(eng, rank, world, cap, fused=True)
         eng.dist_set_partitions(part)
-        best = None
-        for it in range(3):
+        modes = [("push_pipelined", 2), ("push_projected_16B", 3), ("nccl_all_to_all", 0)]
+    else:
+        modes = [("single_gpu_sort_free", None)]
+    expected_hash = None
+    for name, fused in modes:
+        times = []
+        its = iters if fused != 0 else min(iters, 2)
+        for it in range(its + 1):   # first iteration is the warm-up (allocations, NCCL connections)
             barrier()
             t0 = time.perf_counter()
-            eng.dist_route_and_fold(r.view(torch.uint8), fused)
+            if fused is None:
+                eng.fold_unsorted(flat, n_global)
+            else:
+                eng.dist_route_and_fold(flat, fused)
             torch.cuda.synchronize()
             dt = time.perf_counter() - t0
-            ds = eng.dist_stats()
-            v = [dt, ds.ms_count, ds.ms_counts_exchange, ds.ms_scatter, ds.ms_exchange, ds.ms_group, ds.ms_fold]
+            ds = eng.dist_stats() if fused is not None else None
+            v = [dt, eng.stats().ms_fold, ds.ms_pipeline if ds else 0.0, ds.ms_scatter if ds else 0.0, ds.ms_exchange if ds else 0.0,
+                 ds.ms_count if ds else 0.0, ds.ms_group if ds else 0.0]
             t = torch.tensor(v, dtype=torch.float64, device=dev)
             if world > 1:
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            v = [float(x) for x in t]
-            if it > 0 and (best is None or v[0] < best[0]):
-                best = v
-        ds = eng.dist_stats()
+            if it > 0:
+                times.append([float(x) for x in t])
+        best = min(times, key=lambda r: r[0])
+        # ---- parity: hash of the whole table (sum over ranks), the torch restatement's hash, the oracle on the sample
+        h = torch.tensor([np.int64(np.uint64(eng.states_hash()))], dtype=torch.int64, device=dev)
+        gl = torch.from_numpy(eng.dist_local_aggregates().astype(np.int64)).to(dev) if fused is not None else torch.arange(n_global, device=dev, dtype=torch.int64)
+        if expected_hash is None:
+            eh = torch.tensor([np.int64(np.uint64(routed_expected_hash(gl, epa, ROUTED_SEED)))], dtype=torch.int64, device=dev)
+            if world > 1:
+                dist.all_reduce(eh)
+            expected_hash = int(eh.item()) & M64
+        states = eng.states_tensor()
+        pos = torch.searchsorted(gl, torch.from_numpy(sample).to(dev))
+        pos_c = pos.clamp(max=gl.numel() - 1)
+        mine = gl[pos_c] == torch.from_numpy(sample).to(dev)
+        got = states[pos_c[mine]].cpu().numpy()
+        bad = torch.tensor([int((got != want_sample[mine.cpu().numpy()]).any(axis=1).sum()), int(mine.sum())], dtype=torch.int64, device=dev)
+        if world > 1:
+            dist.all_reduce(h)
+            dist.all_reduce(bad)
+        state_hash = int(h.item()) & M64
         ev = int(eng.stats().n_events)
         tot = torch.tensor([ev], dtype=torch.int64, device=dev)
         if world > 1:
             dist.all_reduce(tot)
-        assert int(tot[0]) == n * world, (int(tot[0]), n * world)
-        res[("single_gpu_" + ("sorted_group" if sort_based else "sort_free")) if world == 1 else mode] = {
-            "events_per_s": n * world / best[0], "ms_wall": best[0] * 1e3, "ms_route_count": best[1], "ms_counts_exchange": best[2],
-            "ms_route_scatter": best[3], "ms_exchange": best[4], "ms_group": best[5], "ms_fold": best[6],
-            "fold_events_per_s_per_gpu": ds.n_recv / (best[6] * 1e-3) if best[6] else None,
-            "remote_fraction": ds.n_sent_remote / max(ds.n_sent, 1)}
-        eng.close()
-        del eng
-        torch.cuda.empty_cache()
+        wire = (ds.exchange_record_bytes if ds and ds.exchange_record_bytes else 64)
+        remote = (ds.n_sent_remote if ds else 0)
+        xfer_ms = best[2] if fused in (2, 3) else best[4]
+        res[name] = {
+            "events_per_s": total_events / best[0], "ms_wall": best[0] * 1e3, "ms_wall_all": [round(r[0] * 1e3, 3) for r in times],
+            "ms_device_pipeline": best[2] if fused in (2, 3) else None, "ms_push_issue": best[3] if fused in (2, 3) else None,
+            "ms_route_count": best[5] if fused == 0 else None, "ms_route_scatter": best[3] if fused == 0 else None, "ms_exchange": best[4] if fused == 0 else None,
+            "ms_fold": best[1], "ms_group": best[6],
+            "exchange_bytes_per_record": wire,
+            "nvlink_out_gb_per_s_per_gpu": (remote * wire / (xfer_ms * 1e-3) / 1e9) if (world > 1 and xfer_ms) else None,
+            "parity": {"state_hash": f"{state_hash:016x}", "torch_restatement_hash": f"{expected_hash:016x}",
+                       "full_table_equals_restatement": state_hash == expected_hash,
+                       "oracle_sample_aggregates": int(bad[1]), "oracle_sample_mismatches": int(bad[0]),
+                       "events_folded": int(tot.item()), "events_expected": total_events},
+        }
+        note(f"routed {name}: {res[name]['ms_wall']:.2f} ms, hash ok {state_hash == expected_hash}")
+    if world > 1:
+        res["nvlink_peak_gb_per_s"] = NVLINK_PEAK_GBS
+        res["exchange_lower_bound_ms"] = (total_events / world) * (world - 1) / world * 64 / (NVLINK_PEAK_GBS * 1e9) * 1e3
+    eng.close()
+    del eng, rec, flat
+    torch.cuda.empty_cache()
     return res
 
 
+# ---------------------------------------------------------------------------------------------------- configs[0], [3], [4] (N = 1)
+def config0_bank(dev, peak):
+    """configs[0]: BankAccount, 1k aggregates x 10 events (the reference's CPU-runnable case) bit-exact vs the oracle, and the
+    same model on the configs[1] shape for the wide-state kernel's rate."""
+    import uuid
+
+    import numpy as np
+    import torch
+
+    from oracle import oracle as O
+    from surge_b200 import ReplayEngine
+    from surge_b200 import formats as F
+    from surge_b200 import programs as P
+
+    recs = []
+    for a in range(1000):
+        acct = str(uuid.UUID(int=(a * 0x9E3779B97F4A7C15 + 1) & ((1 << 128) - 1)))
+        recs.append(F.bank_created_record(a, 1, acct, f"owner-{a}", "c0de", 1000.0))
+        for k in range(9):
+            recs.append(F.bank_updated_record(a, k + 2, acct, 1000.0 + (k + 1) * 0.25))
+    log = np.frombuffer(b"".join(recs), dtype=np.uint8)
+    off = np.arange(1001, dtype=np.uint64) * np.uint64(640)
+    want, nev, _ = O.fold_packed(O.MODEL_BANK_ACCOUNT, O.REC_FIXED64, log, off)
+    with ReplayEngine(0) as e:
+        e.register_program(P.bank_account_program())
+        e.load_events(log, off)
+        e.fold()
+        small_ok = bool(np.array_equal(e.export_states(), want))
+    n_agg, epa = 1 << 20, 32
+    n = n_agg * epa
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(9)
+    r = torch.randint(-(1 << 31), 1 << 31, (n, 16), generator=gen, device=dev, dtype=torch.int64).to(torch.int32)
+    idx = torch.arange(n, device=dev, dtype=torch.int64)
+    r[:, 0] = (idx % epa != 0).to(torch.int32)   # first event of every account creates it, the rest update the balance
+    r[:, 1] = (idx % epa + 1).to(torch.int32)
+    r[:, 2] = (idx // epa).to(torch.int32)
+    r[:, 3] = 0
+    offd = torch.arange(n_agg + 1, device=dev, dtype=torch.int64) * (epa * 64)
+    b_alg = n * 64 + 8 * (n_agg + 1) + 64 * n_agg
+    out = {"workload": "configs[0]: BankAccount sample aggregate (64-byte state, IF_EXISTS rule, JVM Double balance)",
+           "small_1k_x_10": {"events": int(nev), "bit_exact_vs_oracle": small_ok}}
+    tabs = []
+    for label, kernel in (("auto", 0), ("lane_sequential_tma", 1)):
+        with ReplayEngine(0) as e:
+            e.register_program(P.bank_account_program())
+            e.set_option("kernel", kernel)
+            e.load_events(r.view(torch.uint8), offd)
+            ms = []
+            for _ in range(4):
+                e.set_initial_states(None)
+                e.fold()
+                ms.append(e.stats().ms_fold)
+            tabs.append(e.states_tensor().clone())
+            # a 2048-aggregate sample against the oracle
+            if kernel == 0:
+                sel = torch.arange(0, n_agg, n_agg // 2048, device=dev)
+                seg = r.view(n_agg, epa * 16)[sel].cpu().numpy().view(np.uint8).reshape(-1)
+                soff = np.arange(len(sel) + 1, dtype=np.uint64) * np.uint64(epa * 64)
+                w, _, _ = O.fold_packed(O.MODEL_BANK_ACCOUNT, O.REC_FIXED64, seg, soff)
+                sample_ok = bool(np.array_equal(e.states_tensor()[sel].cpu().numpy(), w))
+        best = min(ms[1:])
+        out[f"configs1_shape_{label}"] = {"ms_fold": best, "events_per_s": n / best * 1e3, "achieved_gb_per_s": b_alg / best / 1e6, "frac_of_hbm_peak": b_alg / best / 1e6 / peak}
+    out["configs1_shape_kernels_agree"] = bool(torch.equal(tabs[0], tabs[1]))
+    out["configs1_shape_oracle_sample_ok"] = sample_ok
+    return out
+
+
+def config3_zipf(dev, peak, scale: float):
+    """configs[3]: Zipf(1.1) keys, 10 M aggregates, 3.2e8 events, payloads 32-512 B (variable records, ~95 GB) on one B200."""
+    import numpy as np
+    import torch
+
+    from oracle import oracle as O
+    from surge_b200 import ReplayEngine
+    from surge_b200 import native as N
+    from surge_b200 import programs as P
+
+    n_keys, n_events = int(10_000_000 * scale), int(320_000_000 * scale)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(4)
+    w = 1.0 / torch.pow(torch.arange(1, n_keys + 1, device=dev, dtype=torch.float64), 1.1)
+    cdf = torch.cumsum(w, 0)
+    cdf /= cdf[-1].clone()
+    counts = torch.zeros(n_keys, dtype=torch.int64, device=dev)
+    step = 40_000_000
+    for lo in range(0, n_events, step):   # inverse-CDF sampling, in slices (temporaries stay small)
+        k = torch.searchsorted(cdf, torch.rand(min(step, n_events - lo), generator=gen, device=dev, dtype=torch.float64)).clamp_(max=n_keys - 1)
+        counts += torch.bincount(k, minlength=n_keys)
+    del w, cdf, k
+    plen = torch.randint(32, 513, (n_events,), generator=gen, device=dev, dtype=torch.int64)
+    rlen = 16 + ((plen + 15) // 16) * 16
+    rec_off = torch.zeros(n_events + 1, dtype=torch.int64, device=dev)
+    rec_off[1:] = torch.cumsum(rlen, 0)
+    del rlen
+    total = int(rec_off[-1])
+    starts = torch.zeros(n_keys + 1, dtype=torch.int64, device=dev)
+    starts[1:] = torch.cumsum(counts, 0)
+    seg = rec_off[starts]
+    buf = torch.empty(total, dtype=torch.uint8, device=dev)
+    chunk = 1 << 32
+    for lo in range(0, total, chunk):     # filler the fold must still read
+        hi = min(total, lo + chunk)
+        buf[lo:hi] = torch.randint(0, 256, (hi - lo,), generator=gen, device=dev, dtype=torch.uint8)
+    w32 = buf.view(torch.int32)
+    agg = torch.repeat_interleave(torch.arange(n_keys, device=dev, dtype=torch.int64), counts)
+    pos = rec_off[:-1] // 4
+    w32[pos + 3] = agg.to(torch.int32)
+    w32[pos + 1] = (torch.arange(n_events, device=dev, dtype=torch.int64) - starts[agg] + 1).to(torch.int32)
+    del agg
+    w32[pos + 2] = plen.to(torch.int32)
+    del plen
+    u = torch.rand(n_events, generator=gen, device=dev)
+    w32[pos] = torch.where(u < 0.45, 0, torch.where(u < 0.9, 1, 2)).to(torch.int32)
+    # the Counter's `by` (first 4 payload bytes) stays random filler: any i32 is a legal increment
+    del u, pos
+    torch.cuda.synchronize()
+    hot = int(counts.max())
+    b_alg = total + 8 * (n_keys + 1) + 16 * n_keys + 8 * (n_events + 1)
+    out = {"workload": f"configs[3]{'' if scale == 1.0 else f' x {scale}'}: Zipf(1.1) keys, {n_keys} aggregates, {n_events} events, payloads 32-512 B, {total / 1e9:.1f} GB log, one B200",
+           "hottest_key_share": hot / n_events, "algorithmic_bytes": b_alg}
+    with ReplayEngine(0) as e:
+        e.register_program(P.counter_program(N.REC_VAR16))
+        e.load_events_indexed(buf, seg, rec_off)
+        ms = []
+        for _ in range(3):
+            e.set_initial_states(None)
+            e.fold()
+            ms.append(e.stats().ms_fold)
+        st = e.stats()
+        best = min(ms[1:])
+        out.update({"ms_fold": best, "events_per_s": n_events / best * 1e3, "achieved_gb_per_s": b_alg / best / 1e6, "frac_of_hbm_peak": b_alg / best / 1e6 / peak,
+                    "events_folded": int(st.n_events), "launches": int(st.fold_launches), "kernel": "fold_vruns_kernel"})
+        # oracle on a sample of aggregates: 4096 random ones with segments of at most 8 MiB, plus the 8 largest below that bound
+        seg_h = seg.cpu().numpy()
+        seg_len = np.diff(seg_h)
+        ok_idx = np.nonzero(seg_len <= (8 << 20))[0]
+        rng = np.random.default_rng(31)
+        pick = np.unique(np.concatenate([rng.choice(ok_idx, size=min(4096, len(ok_idx)), replace=False), ok_idx[np.argsort(seg_len[ok_idx])[-8:]]]))
+        parts = [buf[int(seg_h[i]):int(seg_h[i + 1])].cpu().numpy() for i in pick]
+        soff = np.zeros(len(pick) + 1, dtype=np.uint64)
+        np.cumsum([len(p) for p in parts], out=soff[1:])
+        want, _, _ = O.fold_packed(O.MODEL_COUNTER, O.REC_VAR16, np.concatenate(parts) if parts else np.zeros(0, np.uint8), soff, threads=min(os.cpu_count() or 1, 16))
+        got = e.states_tensor()[torch.from_numpy(pick).to(dev)].cpu().numpy()
+        out["parity"] = {"oracle_sample_aggregates": int(len(pick)), "oracle_sample_mismatches": int((got != want).any(axis=1).sum()),
+                         "events_folded_equals_events": int(st.n_events) == n_events, "state_hash": f"{e.states_hash():016x}"}
+    del buf, w32, rec_off, seg, starts, counts
+    torch.cuda.empty_cache()
+    return out
+
+
+def config4_microbatch(dev, n_batches: int):
+    """configs[4]: 100k-event batches appended to 1,048,576 live aggregates (incremental fold), sustained rate and latency."""
+    import numpy as np
+    import torch
+
+    from oracle import oracle as O
+    from surge_b200 import ReplayEngine
+    from surge_b200 import programs as P
+    from surge_b200 import synth as S
+
+    n_agg, batch = 1 << 20, 100_000
+    rec, off = S.counter_csr_device(n_agg, 4, seed=5, device=dev)
+    out = {"workload": f"configs[4]: {n_batches} batches of {batch} events onto {n_agg} live aggregates, incremental fold"}
+    with ReplayEngine(0) as e:
+        e.register_program(P.counter_program())
+        e.load_events(rec.view(torch.uint8), off)
+        e.fold()
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(55)
+        nb_pool = min(n_batches, 200)   # 200 distinct batches (1.28 GB), cycled
+        pool = torch.zeros((nb_pool, batch, 16), dtype=torch.int32, device=dev)
+        u = torch.rand((nb_pool, batch), generator=gen, device=dev)
+        pool[:, :, 0] = torch.where(u < 0.45, 0, torch.where(u < 0.9, 1, 2)).to(torch.int32)
+        pool[:, :, 1] = torch.arange(batch, device=dev, dtype=torch.int32)[None, :]
+        pool[:, :, 2] = torch.randint(0, n_agg, (nb_pool, batch), generator=gen, device=dev, dtype=torch.int64).to(torch.int32)
+        pool[:, :, 4] = torch.randint(0, 1 << 31, (nb_pool, batch), generator=gen, device=dev, dtype=torch.int64).to(torch.int32)
+        torch.cuda.synchronize()
+        want = e.export_states()
+        for b in range(3):
+            want = O.fold_incremental(O.MODEL_COUNTER, pool[b].cpu().numpy().view(np.uint8).reshape(-1), want)
+            e.fold_incremental(pool[b].view(torch.uint8))
+        out["bit_exact_vs_oracle_after_3_batches"] = bool(np.array_equal(e.export_states(), want))
+        for b in range(10):
+            e.fold_incremental(pool[b % nb_pool].view(torch.uint8))
+        lat = []
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for b in range(n_batches):
+            t1 = time.perf_counter()
+            e.fold_incremental(pool[b % nb_pool].view(torch.uint8))
+            lat.append(time.perf_counter() - t1)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        st = e.stats()
+        lat = np.array(lat) * 1e6
+        out.update({"events_per_s": n_batches * batch / dt, "batch_latency_us": {"p50": float(np.percentile(lat, 50)), "p99": float(np.percentile(lat, 99))},
+                    "device_ms_last_batch": float(st.ms_fold), "note": "launch-bound: one persistent launch per batch (6.4 MB of records), far below the HBM roofline by design"})
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------- main
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -271,10 +560,10 @@ def main() -> None:
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the host-buffer region (default min(steps, 20))")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--verbose", action="store_true", help="progress markers on stderr")
-    ap.add_argument("--no-routed", action="store_true", help="skip the routed (configs[2]-shaped) pipeline measurement")
-    ap.add_argument("--routed-strong", action="store_true",
-                    help="routed pipeline on the FULL configs[2] problem (10 M aggregates x 100 events = 64 GB) split over the ranks "
-                         "(strong scaling; needs 64 GB of records on one GPU at N=1) instead of 8 GB per rank")
+    ap.add_argument("--no-routed", action="store_true", help="skip configs[2] (the routed 10 M x 100 problem)")
+    ap.add_argument("--no-configs", action="store_true", help="skip configs[0], [3], [4] (N = 1)")
+    ap.add_argument("--scale", type=float, default=1.0, help="shrink configs[2] and configs[3] (debugging on a busy box); 1.0 = the BASELINE sizes")
+    ap.add_argument("--routed-iters", type=int, default=3)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -309,6 +598,7 @@ def main() -> None:
             dist.barrier()
         torch.cuda.synchronize()
 
+    peak, peak_src = measured_peak_gbs()
     # ---- this rank's shard: its own 2^20 aggregates (hash-partitioned aggregates are independent units)
     note("generating the log on the device")
     rec, off = S.counter_csr_device(N_AGG, EVENTS_PER_AGG, seed=2 + rank, device=dev)
@@ -378,18 +668,31 @@ def main() -> None:
     # the e2e result must be the same table the resident fold produced
     same = bool(torch.equal(torch.from_numpy(host_states_np.reshape(-1)).to(dev), eng.states_tensor().reshape(-1)))
     assert same, "e2e state table differs from the HBM-resident fold"
+    e2.close(); eng.close()
+    cpu_rec = np.array(host_log_np, copy=True) if (world == 1 and not args.no_cpu_baseline) else None
+    del rec, host_log, host_log_np
+    torch.cuda.empty_cache()
 
-    # ---- configs[2] shape: events arrive by source partition, one exchange routes them to the owning rank
+    # ---- configs[2]: the routed problem north_star names, strong-scaled, parity-hashed
     routed = None
     if not args.no_routed:
         try:
-            note("routed pipeline")
-            e2.close(); eng.close()
-            del rec
-            torch.cuda.empty_cache()
-            routed = routed_pipeline(rank, world, local_rank, dev, barrier, note, strong=args.routed_strong)
+            note("configs[2] routed")
+            routed = config2_routed(rank, world, local_rank, dev, barrier, note, args.scale, args.routed_iters)
         except Exception as ex:  # noqa: BLE001 - the headline line must survive a failure of the extra measurement
             routed = {"error": f"{type(ex).__name__}: {ex}"}
+            torch.cuda.empty_cache()
+    configs = None
+    if world == 1 and not args.no_configs:
+        configs = {}
+        for key, fn in (("configs[0]", lambda: config0_bank(dev, peak)), ("configs[3]", lambda: config3_zipf(dev, peak, args.scale)),
+                        ("configs[4]", lambda: config4_microbatch(dev, 1000))):
+            try:
+                note(key)
+                configs[key] = fn()
+            except Exception as ex:  # noqa: BLE001
+                configs[key] = {"error": f"{type(ex).__name__}: {ex}"}
+            torch.cuda.empty_cache()
 
     # ---- max over ranks
     if world > 1:
@@ -399,17 +702,18 @@ def main() -> None:
     value = world * n_events * K / (ms_total * 1e-3)
     e2e_value = world * n_events * ke / e2e_s
 
-    out = None
     if rank == 0:
-        peak, peak_src = measured_peak_gbs()
         achieved = b_alg / (kernel_ms * 1e-3) / 1e9
-        traffic = None
-        tp = os.path.join(ROOT, "profiles", "r01_fold_runs_traffic.json")
-        if os.path.exists(tp):
-            try:
-                traffic = json.load(open(tp))["dram_bytes_per_launch"]
-            except Exception:  # noqa: BLE001
-                traffic = None
+        traffic, traffic_src = None, None
+        for name in ("r02_fold_runs_traffic.json", "r01_fold_runs_traffic.json"):
+            tp = os.path.join(ROOT, "profiles", name)
+            if os.path.exists(tp):
+                try:
+                    traffic = json.load(open(tp))["dram_bytes_per_launch"]
+                    traffic_src = f"profiles/{name} (ncu --set full capture of the same kernel and shape; not re-measured in this run)"
+                    break
+                except Exception:  # noqa: BLE001
+                    traffic = None
         out = {
             "metric": METRIC, "value": value, "unit": "events/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -417,10 +721,11 @@ def main() -> None:
             "config": {"workload": WORKLOAD, "aggregates_per_gpu": N_AGG, "events_per_aggregate": EVENTS_PER_AGG,
                        "record_bytes": 64, "state_bytes": STATE_BYTES, "model": "Counter (scaladsl TestBoundedContext)",
                        "l2": "inputs (2 GiB log per GPU) are 16x the 126 MB L2; no flush between iterations",
-                       "sharding": "aggregates sharded across ranks, no data-path collective (see DESIGN.md multi-GPU)"},
+                       "sharding": "value: aggregates sharded across ranks, no data-path collective; the hash-partitioned configuration with "
+                                   "its exchange (configs[2]) is the `routed` block (see DESIGN.md multi-GPU)"},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "algorithmic_bytes_per_launch": b_alg, "kernel": "fold_runs_kernel",
+                         "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes_per_launch": b_alg, "kernel": "fold_runs_kernel",
                          "kernel_ms": kernel_ms, "peak_source": peak_src,
                          "pipelined_frac": (b_alg / (ms_total / K * 1e-3) / 1e9) / peak},
             "e2e": {"value": e2e_value, "unit": "events/s", "h2d_bytes_per_step": int(log_bytes + host_off.nbytes),
@@ -433,12 +738,14 @@ def main() -> None:
         }
         if routed is not None:
             out["routed"] = routed
-        if world == 1 and not args.no_cpu_baseline:
+        if configs is not None:
+            out["configs"] = configs
+        if cpu_rec is not None:
             cores = os.cpu_count() or 1
-            cpu_rec = np.array(host_log_np, copy=True)   # pageable copy: pinned memory is not what a CPU-only deployment would read
-            v, reps, secs = time_cpu_oracle(cpu_rec, host_off, cores, min_seconds=8.0, max_reps=20)
+            v, reps, secs = time_cpu_oracle(cpu_rec, host_off, cores, min_seconds=8.0, max_reps=40)
             out["cpu_baseline"] = {"value": v, "unit": "events/s", "cores": cores, "kind": "port",
-                                   "sample": f"full configs[1] log ({n_events} events, pageable host memory) x {reps} passes, {secs:.1f} s, oracle/sgr_oracle.c with {cores} threads"}
+                                   "sample": f"full configs[1] log ({n_events} events, host memory first-touched by the pinned worker that folds it) x {reps} passes, "
+                                             f"{secs:.1f} s, oracle/sgr_oracle.c with {cores} pinned threads"}
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.barrier()

@@ -43,6 +43,10 @@ def lib():
         L.orc_fold_packed.argtypes = [C.c_int, C.c_uint32, u8p, u64p, C.c_uint64, u8p, u8p, u64p, u64p]
         L.orc_fold_packed_mt.restype = C.c_int
         L.orc_fold_packed_mt.argtypes = [C.c_int, C.c_uint32, u8p, u64p, C.c_uint64, u8p, u8p, C.c_int, u64p, u64p]
+        L.orc_fold_packed_mt_pinned.restype = C.c_int
+        L.orc_fold_packed_mt_pinned.argtypes = [C.c_int, C.c_uint32, u8p, u64p, C.c_uint64, u8p, u8p, C.c_int, u64p, u64p]
+        L.orc_place_log_mt.restype = C.c_int
+        L.orc_place_log_mt.argtypes = [u8p, u8p, u64p, C.c_uint64, C.c_int]
         L.orc_fold_incremental.restype = C.c_int
         L.orc_fold_incremental.argtypes = [C.c_int, u8p, C.c_uint64, u8p, C.c_uint64]
         L.orc_group_by_agg.restype = C.c_int
@@ -66,8 +70,8 @@ def state_bytes(model: int) -> int:
 
 
 def fold_packed(model: int, record_kind: int, events: np.ndarray, seg_offsets: np.ndarray,
-                initial_states: Optional[np.ndarray] = None, threads: int = 1) -> Tuple[np.ndarray, int, int]:
-    """Returns (states[n_agg, state_bytes] u8, n_events, n_errors)."""
+                initial_states: Optional[np.ndarray] = None, threads: int = 1, pinned: bool = False) -> Tuple[np.ndarray, int, int]:
+    """Returns (states[n_agg, state_bytes] u8, n_events, n_errors). pinned: worker t runs on CPU t (see place_log)."""
     events = np.ascontiguousarray(events).view(np.uint8).reshape(-1)
     seg_offsets = np.ascontiguousarray(seg_offsets, dtype=np.uint64)
     n_agg = len(seg_offsets) - 1
@@ -77,7 +81,8 @@ def fold_packed(model: int, record_kind: int, events: np.ndarray, seg_offsets: n
         initial_states = np.ascontiguousarray(initial_states).view(np.uint8).reshape(n_agg, sb)
     nev, nerr = C.c_uint64(0), C.c_uint64(0)
     if threads > 1:
-        rc = lib().orc_fold_packed_mt(model, record_kind, _ptr(events), _ptr(seg_offsets), n_agg, _ptr(initial_states),
+        fn = lib().orc_fold_packed_mt_pinned if pinned else lib().orc_fold_packed_mt
+        rc = fn(model, record_kind, _ptr(events), _ptr(seg_offsets), n_agg, _ptr(initial_states),
                                       _ptr(out), threads, C.addressof(nev), C.addressof(nerr))
     else:
         rc = lib().orc_fold_packed(model, record_kind, _ptr(events), _ptr(seg_offsets), n_agg, _ptr(initial_states),
@@ -85,6 +90,17 @@ def fold_packed(model: int, record_kind: int, events: np.ndarray, seg_offsets: n
     if rc != 0:
         raise ValueError("oracle: malformed input")
     return out, int(nev.value), int(nerr.value)
+
+
+def place_log(events: np.ndarray, seg_offsets: np.ndarray, threads: int) -> np.ndarray:
+    """NUMA-aware copy of a CSR log for the CPU arm of bench.py: the copy is written by the pinned workers that will later
+    fold it (same byte sharding), so first touch puts every worker's range on its own node."""
+    events = np.ascontiguousarray(events).view(np.uint8).reshape(-1)
+    seg_offsets = np.ascontiguousarray(seg_offsets, dtype=np.uint64)
+    dst = np.empty(events.size, dtype=np.uint8)   # fresh mapping: pages untouched until the workers write them
+    if lib().orc_place_log_mt(_ptr(dst), _ptr(events), _ptr(seg_offsets), len(seg_offsets) - 1, threads) != 0:
+        raise ValueError("oracle: placement failed")
+    return dst
 
 
 def group_by_agg(records: np.ndarray, n_agg: int) -> Tuple[np.ndarray, np.ndarray]:

@@ -1,3 +1,4 @@
+#define _GNU_SOURCE
 /*
  * sgr_oracle.c — CPU restatement of the reference's event-replay path (see sgr_oracle.h).
  * TEST INFRASTRUCTURE ONLY: never linked into or called from the product (surge_b200/).
@@ -13,6 +14,8 @@
  */
 #include "sgr_oracle.h"
 #include <pthread.h>
+#include <sched.h>
+#include <unistd.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -277,25 +280,47 @@ int orc_fold_packed(int model, uint32_t record_kind, const uint8_t* events, cons
 typedef struct {
   int model; uint32_t kind; const uint8_t* events; const uint64_t* offs; uint64_t lo, hi;
   const uint8_t* init; uint8_t* out; uint64_t nev, nerr; int rc;
+  int cpu;              /* >= 0: pin the worker to this CPU (NUMA-stable placement across calls) */
+  uint8_t* place_dst;   /* != 0: the job copies its byte range of the log here instead of folding (first touch) */
 } mt_job;
+
+static void pin_self(int cpu) {
+#ifdef __linux__
+  if (cpu < 0) return;
+  cpu_set_t set; CPU_ZERO(&set); CPU_SET(cpu, &set);
+  pthread_setaffinity_np(pthread_self(), sizeof set, &set);   /* best effort: a restricted cpuset just leaves the thread unpinned */
+#else
+  (void)cpu;
+#endif
+}
 
 static void* mt_worker(void* arg) {
   mt_job* j = (mt_job*)arg;
+  pin_self(j->cpu);
+  if (j->place_dst) {
+    uint64_t b = j->offs[j->lo], e = j->offs[j->hi];
+    memcpy(j->place_dst + b, j->events + b, (size_t)(e - b));
+    j->rc = 0;
+    return 0;
+  }
   uint32_t sb = orc_state_bytes(j->model);
   j->rc = orc_fold_packed(j->model, j->kind, j->events, j->offs + j->lo, j->hi - j->lo,
                           j->init ? j->init + j->lo * sb : 0, j->out + j->lo * sb, &j->nev, &j->nerr);
   return 0;
 }
 
-int orc_fold_packed_mt(int model, uint32_t record_kind, const uint8_t* events, const uint64_t* seg_offsets,
-                       uint64_t n_agg, const uint8_t* initial_states, uint8_t* out_states,
-                       int n_threads, uint64_t* n_events_out, uint64_t* n_errors_out) {
+/* shard by bytes, not by aggregate count, so skewed logs stay balanced; the same function of (offsets, n_threads) for the
+   placement pass and for every fold, so thread t always reads the pages thread t touched first */
+static int mt_run(int model, uint32_t record_kind, const uint8_t* events, const uint64_t* seg_offsets, uint64_t n_agg,
+                  const uint8_t* initial_states, uint8_t* out_states, int n_threads, int pin, uint8_t* place_dst,
+                  uint64_t* n_events_out, uint64_t* n_errors_out) {
   if (n_threads < 1) n_threads = 1;
   if ((uint64_t)n_threads > n_agg && n_agg > 0) n_threads = (int)n_agg;
   mt_job* jobs = (mt_job*)calloc((size_t)n_threads, sizeof(mt_job));
   pthread_t* th = (pthread_t*)calloc((size_t)n_threads, sizeof(pthread_t));
   if (!jobs || !th) { free(jobs); free(th); return -1; }
-  /* shard by bytes, not by aggregate count, so skewed logs stay balanced */
+  long ncpu = sysconf(_SC_NPROCESSORS_ONLN);
+  if (ncpu < 1) ncpu = 1;
   uint64_t total = n_agg ? seg_offsets[n_agg] - seg_offsets[0] : 0;
   uint64_t lo = 0;
   for (int t = 0; t < n_threads; t++) {
@@ -311,6 +336,7 @@ int orc_fold_packed_mt(int model, uint32_t record_kind, const uint8_t* events, c
     }
     jobs[t].model = model; jobs[t].kind = record_kind; jobs[t].events = events; jobs[t].offs = seg_offsets;
     jobs[t].lo = lo; jobs[t].hi = hi; jobs[t].init = initial_states; jobs[t].out = out_states;
+    jobs[t].cpu = pin ? (int)(t % ncpu) : -1; jobs[t].place_dst = place_dst;
     lo = hi;
   }
   for (int t = 0; t < n_threads; t++) pthread_create(&th[t], 0, mt_worker, &jobs[t]);
@@ -323,6 +349,25 @@ int orc_fold_packed_mt(int model, uint32_t record_kind, const uint8_t* events, c
   if (n_events_out) *n_events_out = nev;
   if (n_errors_out) *n_errors_out = nerr;
   return rc;
+}
+
+int orc_fold_packed_mt(int model, uint32_t record_kind, const uint8_t* events, const uint64_t* seg_offsets,
+                       uint64_t n_agg, const uint8_t* initial_states, uint8_t* out_states,
+                       int n_threads, uint64_t* n_events_out, uint64_t* n_errors_out) {
+  return mt_run(model, record_kind, events, seg_offsets, n_agg, initial_states, out_states, n_threads, 0, 0, n_events_out, n_errors_out);
+}
+
+/* The same fold with worker t pinned to CPU t: together with orc_place_log_mt every worker reads memory of its own NUMA node. */
+int orc_fold_packed_mt_pinned(int model, uint32_t record_kind, const uint8_t* events, const uint64_t* seg_offsets,
+                              uint64_t n_agg, const uint8_t* initial_states, uint8_t* out_states,
+                              int n_threads, uint64_t* n_events_out, uint64_t* n_errors_out) {
+  return mt_run(model, record_kind, events, seg_offsets, n_agg, initial_states, out_states, n_threads, 1, 0, n_events_out, n_errors_out);
+}
+
+/* Copy the log into `dst` (untouched pages) with the fold's own sharding and pinning: first touch places every worker's byte
+   range on that worker's NUMA node. Measurement hygiene for the CPU arm of bench.py, not part of the algorithm. */
+int orc_place_log_mt(uint8_t* dst, const uint8_t* src, const uint64_t* seg_offsets, uint64_t n_agg, int n_threads) {
+  return mt_run(0, 0, src, seg_offsets, n_agg, 0, 0, n_threads, 1, dst, 0, 0);
 }
 
 /* ------------------------------------------------------------------ stable group-by (Kafka log order per key) */

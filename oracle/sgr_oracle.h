@@ -60,6 +60,13 @@ int orc_fold_packed_mt(int model, uint32_t record_kind, const uint8_t* events, c
 
 /* Incremental: records in arrival order (fixed64), applied per aggregate in arrival
  * order onto states (in place). Equivalent to one ApplyEvents per touched aggregate. */
+/* NUMA-stable variants for the CPU arm of bench.py: worker t pinned to CPU t; orc_place_log_mt copies the log into untouched
+   memory with the fold's own sharding, so every worker later reads pages of its own node. */
+int orc_fold_packed_mt_pinned(int model, uint32_t record_kind, const uint8_t* events, const uint64_t* seg_offsets,
+                              uint64_t n_agg, const uint8_t* initial_states, uint8_t* out_states,
+                              int n_threads, uint64_t* n_events_out, uint64_t* n_errors_out);
+int orc_place_log_mt(uint8_t* dst, const uint8_t* src, const uint64_t* seg_offsets, uint64_t n_agg, int n_threads);
+
 int orc_fold_incremental(int model, const uint8_t* records, uint64_t n_records,
                          uint8_t* states, uint64_t n_agg);
 

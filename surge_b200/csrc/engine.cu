@@ -1100,7 +1100,7 @@ int32_t sgr_dist_unique_id(void* out128) {
 
 int32_t sgr_dist_init(sgr_engine* e, int32_t rank, int32_t nranks, const void* unique_id128, uint64_t recv_capacity_records) {
   OpLock op_lock(e);
-  if (!e || (nranks > 1 && !unique_id128)) return fail(e, SGR_ERR_INVALID, "null argument");
+  if (!e) return fail(e, SGR_ERR_INVALID, "null argument");   // unique_id128 == NULL with nranks > 1: a loopback rank (sgr.h)
   int32_t rc = use_device(e); if (rc) return rc;
   if (e->dist) { dist_destroy(e->dist); e->dist = nullptr; }
   e->dist = dist_create();

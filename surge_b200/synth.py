@@ -156,33 +156,42 @@ def routed_events_host(g_ids: np.ndarray, epa: int, seed: int) -> Tuple[np.ndarr
     return rec, F.csr_offsets_from_counts(np.full(len(g_ids), epa, dtype=np.int64))
 
 
+def routed_round(g, k: int, seed: int):
+    """(type, by) int32 CUDA tensors of event k of the global aggregates g (int64 CUDA tensor): the torch form of the generator."""
+    import torch
+
+    def s64(c):
+        return c - (1 << 64) if c >= (1 << 63) else c
+
+    def lsr(x, n):
+        return (x >> n) & ((1 << (64 - n)) - 1)
+
+    x = g * 1000003 + (k * 7919 + seed * 0x51ED27) + s64(_SM_G)
+    x = (x ^ lsr(x, 30)) * s64(_SM_A)
+    x = (x ^ lsr(x, 27)) * s64(_SM_B)
+    x = x ^ lsr(x, 31)
+    u = x & 0xFFFF
+    typ = torch.where(u < 29491, F.COUNT_INCREMENTED, torch.where(u < 58982, F.COUNT_DECREMENTED, F.NO_OP_EVENT)).to(torch.int32)
+    return typ, (lsr(x, 16) & 0x7FFFFFFF).to(torch.int32)
+
+
 def routed_log_device(rank: int, world: int, n_global: int, epa: int, seed: int, device: str):
     """This rank's share of the configs[2] log, on the device, in ARRIVAL order: the rank holds the source partitions of the
     aggregates g with g % world == rank; event k of every one of its aggregates comes before event k+1 of any (aggregates
     interleaved, every aggregate's own order kept). Records carry the GLOBAL aggregate index. int32[n, 16] CUDA tensor."""
     import torch
 
-    def s64(c):
-        return c - (1 << 64) if c >= (1 << 63) else c
-
-    def lsr(x, k):
-        return (x >> k) & ((1 << (64 - k)) - 1)
-
     g = torch.arange(rank, n_global, world, device=device, dtype=torch.int64)
     na = g.numel()
     rec = torch.zeros((na * epa, 16), dtype=torch.int32, device=device)
     g32 = g.to(torch.int32)
     for k in range(epa):   # one round of events at a time keeps the temporaries small (the full log is 64 GB)
-        x = g * 1000003 + (k * 7919 + seed * 0x51ED27) + s64(_SM_G)
-        x = (x ^ lsr(x, 30)) * s64(_SM_A)
-        x = (x ^ lsr(x, 27)) * s64(_SM_B)
-        x = x ^ lsr(x, 31)
-        u = x & 0xFFFF
+        typ, by = routed_round(g, k, seed)
         blk = rec[k * na:(k + 1) * na]
-        blk[:, 0] = torch.where(u < 29491, F.COUNT_INCREMENTED, torch.where(u < 58982, F.COUNT_DECREMENTED, F.NO_OP_EVENT)).to(torch.int32)
+        blk[:, 0] = typ
         blk[:, 1] = k + 1
         blk[:, 2] = g32
-        blk[:, 4] = (lsr(x, 16) & 0x7FFFFFFF).to(torch.int32)
+        blk[:, 4] = by
     return rec
 
 
