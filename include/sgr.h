@@ -311,6 +311,10 @@ int32_t sgr_dist_route_and_fold(sgr_engine* e, const void* d_records, uint64_t n
  * pointers (sgr_dist_recv_base -> sgr_dist_set_peers) and the caller runs every rank's sgr_dist_route_and_fold(fused >= 2)
  * concurrently (one host thread per rank), with a barrier of its own between calls. fused <= 1 needs NCCL and is refused. */
 int32_t sgr_dist_recv_base(sgr_engine* e, void** base);
+/* Allocate everything sgr_dist_route_and_fold(fused >= 2) needs for logs of up to max_records records now (after
+ * sgr_dist_set_partitions and the "push_chunks" option), so that the call itself allocates nothing. Optional for real ranks;
+ * loopback ranks share one device, where an allocation can wait for another rank's kernel: call it on every rank first. */
+int32_t sgr_dist_reserve(sgr_engine* e, uint64_t max_records);
 int32_t sgr_dist_set_peers(sgr_engine* e, void* const* recv_bases_by_rank);
 /* 64-bit order-independent hash of the live state table: sum over slots of mix(aggregate index, state bytes) mod 2^64, the
  * index being the GLOBAL aggregate index on a routed engine — so the sum of the ranks' hashes does not depend on how many ranks

@@ -52,6 +52,7 @@ struct DistState {
   cudaStream_t stream2 = nullptr;
   cudaEvent_t pev[4] = {};
   uint32_t epoch = 0;
+  void* h_pinned = nullptr;              // page-locked landing area of the per-call read-backs
 };
 
 }  // namespace sgr

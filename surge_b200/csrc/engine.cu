@@ -1239,6 +1239,22 @@ int32_t sgr_dist_set_peers(sgr_engine* e, void* const* recv_bases_by_rank) {
   return SGR_OK;
 }
 
+int32_t sgr_dist_reserve(sgr_engine* e, uint64_t max_records) {
+  OpLock op_lock(e);
+  if (!e || !e->dist) return fail(e, SGR_ERR_INVALID, "null argument / no dist state");
+  if (!e->has_program) return fail(e, SGR_ERR_NO_PROGRAM, "register a fold program first");
+  int32_t rc = use_device(e); if (rc) return rc;
+  rc = before_load(e); if (rc) return rc;
+  const uint64_t n_local = dist_n_local(e->dist);
+  rc = ensure_states(e, n_local); if (rc) return rc;
+  if (e->bulk_ok) { rc = ensure_bulk_buffers(e, n_local); if (rc) return rc; }
+  std::string err;
+  int r = dist_push_reserve(e->dist, max_records, (uint32_t)e->opt_push_chunks, &err);
+  if (r) return fail(e, r, "%s", err.c_str());
+  CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+  return SGR_OK;
+}
+
 int32_t sgr_dist_recv_base(sgr_engine* e, void** base) {
   if (!e || !base || !e->dist) return fail(e, SGR_ERR_INVALID, "null argument / no dist state");
   *base = dist_recv_base(e->dist);

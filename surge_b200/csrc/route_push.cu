@@ -293,6 +293,28 @@ __global__ void gather_region_kernel(const uint8_t* __restrict__ src, uint32_t n
 
 }  // namespace
 
+// every allocation the push path makes for logs of up to n records, up front: a cudaMalloc inside the call can wait for a
+// peer's spinning wait kernel when several ranks share one device (loopback)
+int dist_push_reserve(DistState* d, uint64_t n, uint32_t n_chunks, std::string* err) {
+  if (n_chunks < 1 || n_chunks > (uint32_t)kMaxChunks) { *err = "push_chunks out of range"; return SGR_ERR_INVALID; }
+  uint64_t chunk_recs = (n + n_chunks - 1) / n_chunks;
+  chunk_recs = (chunk_recs + kPushRecs - 1) / kPushRecs * kPushRecs;
+  const uint64_t ctas_per_chunk = chunk_recs / kPushRecs;
+  cudaError_t ce;
+  if (!d->h_pinned && (ce = cudaHostAlloc(&d->h_pinned, 128 + (size_t)kMaxRanks * kMaxChunks * 8 + 128, cudaHostAllocDefault)) != cudaSuccess) {
+    *err = std::string("page-locked read-back buffer: ") + cudaGetErrorString(ce);
+    return SGR_ERR_OOM;
+  }
+  if ((ce = d->push_ctl.reserve((size_t)kMaxChunks * 4 + (size_t)kMaxChunks * kMaxRanks * 4 + 64 + 64)) != cudaSuccess ||
+      (ce = d->lb.reserve((size_t)n_chunks * ctas_per_chunk * kMaxRanks * 8 + 256)) != cudaSuccess ||
+      (ce = d->counts_all.reserve((size_t)kMaxRanks * kMaxRanks * 8 + 64)) != cudaSuccess ||
+      (ce = cudaFuncSetAttribute(route_push_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPushSmem)) != cudaSuccess) {
+    *err = std::string("push buffers: ") + cudaGetErrorString(ce);
+    return ce == cudaErrorMemoryAllocation ? SGR_ERR_OOM : SGR_ERR_CUDA;
+  }
+  return SGR_OK;
+}
+
 int dist_push_fold(DistState* d, const uint8_t* d_records, uint64_t n, const PushFoldArgs& pf, cudaStream_t st, PushFoldResult* out,
                    std::string* err) {
   cudaError_t ce;
@@ -316,17 +338,10 @@ int dist_push_fold(DistState* d, const uint8_t* d_records, uint64_t n, const Pus
   const uint64_t ctas_per_chunk = chunk_recs / kPushRecs;
   // control block: tickets[C] | totals[C][kMaxRanks] | status[8] u64 | proj words
   const size_t off_tot = (size_t)kMaxChunks * 4, off_status = off_tot + (size_t)kMaxChunks * kMaxRanks * 4, off_proj = off_status + 64;
-  DTRY(d->push_ctl.reserve(off_proj + 64));
-  DTRY(d->lb.reserve((size_t)C * ctas_per_chunk * kMaxRanks * 8 + 256));
-  DTRY(d->counts_all.reserve((size_t)kMaxRanks * kMaxRanks * 8 + 64));
+  { int rr = dist_push_reserve(d, n, C, err); if (rr) return rr; }
   uint32_t* tickets = (uint32_t*)d->push_ctl.p;
   uint32_t* totals = (uint32_t*)((uint8_t*)d->push_ctl.p + off_tot);
   unsigned long long* status = (unsigned long long*)((uint8_t*)d->push_ctl.p + off_status);
-  static bool attr_set = false;
-  if (!attr_set) {
-    DTRY(cudaFuncSetAttribute(route_push_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPushSmem));
-    attr_set = true;
-  }
   const uint32_t epoch = ++d->epoch;
   cudaStream_t s0 = st, s1 = d->stream2;
   DTRY(cudaMemsetAsync(d->push_ctl.p, 0, off_proj + 64, s0));
@@ -375,11 +390,14 @@ int dist_push_fold(DistState* d, const uint8_t* d_records, uint64_t n, const Pus
   DTRY(cudaStreamWaitEvent(s0, d->pev[2], 0));
   DTRY(cudaEventRecord(d->pev[3], s0));
   // ---- results
-  unsigned long long h_status[8], h_cnt[8];
-  std::vector<unsigned long long> h_flags((size_t)kMaxRanks * kMaxChunks);
+  // page-locked landing area: a copy into pageable memory blocks inside the driver, which stalls the launches of the other
+  // ranks of a loopback job (one process, one context) and with them the flags this rank is waiting for
+  unsigned long long* h_status = (unsigned long long*)d->h_pinned;
+  unsigned long long* h_cnt = h_status + 8;
+  unsigned long long* h_flags = h_status + 16;
   DTRY(cudaMemcpyAsync(h_status, status, 64, cudaMemcpyDeviceToHost, s0));
   DTRY(cudaMemcpyAsync(h_cnt, pf.counters, 64, cudaMemcpyDeviceToHost, s0));
-  DTRY(cudaMemcpyAsync(h_flags.data(), my_flags, h_flags.size() * 8, cudaMemcpyDeviceToHost, s0));
+  DTRY(cudaMemcpyAsync(h_flags, my_flags, (size_t)kMaxRanks * kMaxChunks * 8, cudaMemcpyDeviceToHost, s0));
   DTRY(cudaStreamSynchronize(s0));
   float ms_push = 0, ms_total = 0;
   cudaEventElapsedTime(&ms_push, d->pev[0], d->pev[1]);
@@ -402,8 +420,10 @@ int dist_push_fold(DistState* d, const uint8_t* d_records, uint64_t n, const Pus
   else if (h_cnt[4]) { *err = std::to_string(h_cnt[4]) + " arrived records carry a local index out of range"; my_err = SGR_ERR_INVALID; }
   // every rank fails or nobody does: gather the verdicts (the fold of a failed call is discarded by the caller)
   if (R > 1 && !d->loopback) {
-    uint32_t mine = my_err ? 1u : 0u, all[kMaxRanks] = {};
-    DTRY(cudaMemcpyAsync((uint8_t*)d->push_ctl.p + off_proj, &mine, 4, cudaMemcpyHostToDevice, s0));
+    uint32_t* all = (uint32_t*)((uint8_t*)d->h_pinned + 128 + (size_t)kMaxRanks * kMaxChunks * 8);
+    uint32_t* mine = all + kMaxRanks - 1 + 1;   // behind the gathered verdicts
+    *mine = my_err ? 1u : 0u;
+    DTRY(cudaMemcpyAsync((uint8_t*)d->push_ctl.p + off_proj, mine, 4, cudaMemcpyHostToDevice, s0));
     NTRY(nccl_api().AllGather((uint8_t*)d->push_ctl.p + off_proj, d->counts_all.p, 1, ncclUint32, d->comm, s0));
     DTRY(cudaMemcpyAsync(all, d->counts_all.p, (size_t)R * 4, cudaMemcpyDeviceToHost, s0));
     DTRY(cudaStreamSynchronize(s0));

@@ -31,6 +31,7 @@ struct PushFoldResult {
   std::vector<PushRegion> regions;   // what arrived, in (source, chunk) order
 };
 
+int dist_push_reserve(DistState* d, uint64_t n, uint32_t n_chunks, std::string* err);
 int dist_push_fold(DistState* d, const uint8_t* d_records, uint64_t n, const PushFoldArgs& pf, cudaStream_t st, PushFoldResult* out,
                    std::string* err);
 int dist_gather_regions(DistState* d, const PushFoldResult& res, const RowProgram& prog, cudaStream_t st, const uint8_t** out, std::string* err);

@@ -18,6 +18,17 @@ def _is_cuda_tensor(x) -> bool:
     return hasattr(x, "is_cuda") and bool(getattr(x, "is_cuda"))
 
 
+def _producer_done(*tensors) -> None:
+    """The engine launches on its own non-blocking stream: a tensor torch is still writing on ITS current stream must be complete
+    before the engine borrows it (the `_device` entry points take plain pointers, they cannot order against torch's stream)."""
+    import torch
+
+    for t in tensors:
+        if _is_cuda_tensor(t):
+            torch.cuda.current_stream(t.device).synchronize()
+            return
+
+
 class _DevView:
     """Exposes a raw device pointer through __cuda_array_interface__ (for torch.as_tensor)."""
 
@@ -75,6 +86,7 @@ class ReplayEngine:
             ev = events.contiguous().view(-1)
             nbytes = ev.numel() * ev.element_size()
             n_agg = seg_offsets.numel() - 1
+            _producer_done(ev)
             self._keep = [ev, seg_offsets]
             self._ck(self._lib.sgr_load_events_device(self._h, ev.data_ptr(), nbytes, seg_offsets.data_ptr(), n_agg))
             return
@@ -86,6 +98,7 @@ class ReplayEngine:
         """Variable records + record directory (rec_offsets[n_records+1]): enables the record-parallel kernel."""
         if _is_cuda_tensor(events):
             ev = events.contiguous().view(-1)
+            _producer_done(ev)
             self._keep = [ev, seg_offsets, rec_offsets]
             self._ck(self._lib.sgr_load_events_indexed_device(self._h, ev.data_ptr(), ev.numel() * ev.element_size(), seg_offsets.data_ptr(),
                                                               seg_offsets.numel() - 1, rec_offsets.data_ptr(), rec_offsets.numel() - 1))
@@ -100,6 +113,7 @@ class ReplayEngine:
         if _is_cuda_tensor(records):
             r = records.contiguous().view(-1)
             n = r.numel() * r.element_size() // 64
+            _producer_done(r)
             self._keep = [r]
             self._ck(self._lib.sgr_load_unsorted_device(self._h, r.data_ptr(), n, n_agg))
             return
@@ -110,6 +124,7 @@ class ReplayEngine:
         """Rebuild all states from an arrival-order log (Kafka partition order) in one call."""
         if _is_cuda_tensor(records):
             r = records.contiguous().view(-1)
+            _producer_done(r)
             self._keep = [r]
             self._ck(self._lib.sgr_fold_unsorted_device(self._h, r.data_ptr(), r.numel() * r.element_size() // 64, n_agg))
             return
@@ -137,6 +152,7 @@ class ReplayEngine:
     def fold_incremental(self, records) -> None:
         if _is_cuda_tensor(records):
             r = records.contiguous().view(-1)
+            _producer_done(r)
             self._keep.append(r)
             self._ck(self._lib.sgr_fold_incremental_device(self._h, r.data_ptr(), r.numel() * r.element_size() // 64))
             self._keep.pop()
@@ -235,6 +251,7 @@ class ReplayEngine:
         """records: CUDA tensor of fixed 64-byte records in arrival order carrying GLOBAL aggregate indices.
         fused: 0 NCCL all-to-all, 1 peer scatter, 2 pipelined push + fold, 3 the same with projected records (see sgr.h)."""
         r = records.contiguous().view(-1)
+        _producer_done(r)
         self._keep = [r]
         self._ck(self._lib.sgr_dist_route_and_fold(self._h, r.data_ptr(), r.numel() * r.element_size() // 64, int(fused)))
 
@@ -247,6 +264,10 @@ class ReplayEngine:
         """Loopback ranks (one process, one device): the other ranks' receive allocations as raw device pointers."""
         arr = (C.c_void_p * len(bases))(*[C.c_void_p(b) for b in bases])
         self._ck(self._lib.sgr_dist_set_peers(self._h, arr))
+
+    def dist_reserve(self, max_records: int) -> None:
+        """Allocate everything the pipelined push needs up front (required for loopback ranks, see sgr.h)."""
+        self._ck(self._lib.sgr_dist_reserve(self._h, int(max_records)))
 
     def states_hash(self) -> int:
         """Order-independent 64-bit hash of the live table (global aggregate indices on a routed engine)."""

@@ -128,6 +128,7 @@ ABI = [
     ("sgr_dist_route_and_fold", C.c_int32, [_P, _P, C.c_uint64, C.c_int32]),
     ("sgr_dist_recv_base", C.c_int32, [_P, C.POINTER(C.c_void_p)]),
     ("sgr_dist_set_peers", C.c_int32, [_P, _P]),
+    ("sgr_dist_reserve", C.c_int32, [_P, C.c_uint64]),
     ("sgr_states_hash", C.c_int32, [_P, C.POINTER(C.c_uint64)]),
     ("sgr_dist_get_stats", C.c_int32, [_P, C.POINTER(sgr_dist_stats)]),
     ("sgr_dist_local_aggregates", C.c_int32, [_P, _P, C.c_uint64, C.POINTER(C.c_uint64)]),

@@ -3,6 +3,10 @@ import sys
 
 import pytest
 
+# The loopback multi-rank tests run several ranks' streams on ONE device, some of them holding a spinning wait kernel: give every
+# stream its own hardware queue so a push kernel never queues behind another rank's wait (must be set before CUDA initialises).
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

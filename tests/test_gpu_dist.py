@@ -179,8 +179,9 @@ def _loopback_job(R, n_global, rec_all, part, fused, chunks, capacity, prog=None
         mine = arrival[src == r]
         feeds.append(torch.from_numpy(mine.view(np.uint8).reshape(-1).copy()).to("cuda:0"))
     bases = [e.dist_recv_base() for e in engines]
-    for e in engines:
+    for r, e in enumerate(engines):
         e.dist_set_peers(bases)
+        e.dist_reserve(feeds[r].numel() // 64)   # ranks share one device here: nothing may allocate while a peer's wait kernel spins
     errors = [None] * R
 
     def run(r):
