@@ -39,10 +39,7 @@ namespace sgr {
 namespace {
 
 constexpr int kPushThreads = 256;
-constexpr int kPushRecs = 1024;
-constexpr int kPushRounds = kPushRecs / kPushThreads;   // 4
 constexpr int kPushWarps = kPushThreads / 32;           // 8
-constexpr size_t kPushSmem = (size_t)kPushRecs * 64 + kPushRecs * 4 + kPushRecs * 2 + kPushRecs;
 constexpr unsigned long long kSpinLimit = 1ull << 26;   // ~ seconds: a lost peer must not hang the GPU
 
 struct PushArgs {
@@ -54,7 +51,8 @@ struct PushArgs {
   uint8_t* dst[kMaxRanks];       // region (me, chunk) in every owner's receive buffer
   uint32_t cap_region;           // records
   uint32_t out_bytes;            // 64, or the compact stride
-  unsigned long long* lb;        // look-back cells of this chunk: [cta][kMaxRanks], flag << 62 | count (1 local, 2 inclusive)
+  unsigned long long* lb;        // look-back cells of this chunk: [owner][cta], flag << 62 | count (1 local, 2 inclusive)
+  uint32_t n_ctas;               // CTAs (tiles) per chunk: the row length of lb
   uint32_t* ticket;              // CTA order of this chunk
   uint32_t* totals;              // [kMaxRanks]: records sent to each owner by this chunk
   unsigned long long* status;    // [0] records with a global index out of range [1] records that did not fit their region
@@ -89,12 +87,16 @@ __device__ __forceinline__ void st_na_v4(void* p, const uint4& v) {
 
 extern __shared__ __align__(16) uint8_t push_smem[];
 
+// One CTA = one tile of RECS consecutive records of the chunk (RECS = 256 * ROUNDS). Smaller tiles put more CTAs on an SM, so
+// that tiles in their load, sort and store phases overlap (the store phase is where NVLink back-pressure lands).
+template <int ROUNDS>
 __global__ void __launch_bounds__(kPushThreads) route_push_kernel(const __grid_constant__ PushArgs a) {
-  uint8_t* srec = push_smem;                                              // [1024][64]
-  uint32_t* loc = reinterpret_cast<uint32_t*>(push_smem + kPushRecs * 64); // [1024] local index, by record
-  uint16_t* perm = reinterpret_cast<uint16_t*>(loc + kPushRecs);          // [1024] sorted position -> record
-  uint8_t* own_s = reinterpret_cast<uint8_t*>(perm + kPushRecs);          // [1024] owner, by sorted position
-  __shared__ uint32_t wcnt[kPushRounds][kPushWarps][kMaxRanks];
+  constexpr int RECS = ROUNDS * kPushThreads;
+  uint8_t* srec = push_smem;                                           // [RECS][64]
+  uint32_t* loc = reinterpret_cast<uint32_t*>(push_smem + RECS * 64);  // [RECS] local index, by record
+  uint16_t* perm = reinterpret_cast<uint16_t*>(loc + RECS);            // [RECS] sorted position -> record
+  uint8_t* own_s = reinterpret_cast<uint8_t*>(perm + RECS);            // [RECS] owner, by sorted position
+  __shared__ uint32_t wcnt[ROUNDS][kPushWarps][kMaxRanks];
   __shared__ uint32_t start[kMaxRanks + 1], excl[kMaxRanks], cnt[kMaxRanks];
   __shared__ uint32_t s_bid, s_ok;
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
@@ -102,26 +104,26 @@ __global__ void __launch_bounds__(kPushThreads) route_push_kernel(const __grid_c
   if (t == 0) { s_bid = atomicAdd(a.ticket, 1u); s_ok = 0xffffffffu; }
   __syncthreads();
   const uint32_t bid = s_bid;
-  const uint32_t base = bid * kPushRecs;
-  const uint32_t nrec = a.n - base < (uint32_t)kPushRecs ? a.n - base : (uint32_t)kPushRecs;
+  const uint32_t base = bid * RECS;
+  const uint32_t nrec = a.n - base < (uint32_t)RECS ? a.n - base : (uint32_t)RECS;
   const uint8_t* src = a.rec + (uint64_t)base * 64;
   // ---- the CTA's records -> shared memory (asynchronous; the owner lookups below run meanwhile)
 #pragma unroll
-  for (int it = 0; it < 16; ++it) {
+  for (int it = 0; it < 4 * ROUNDS; ++it) {
     const uint32_t q = it * kPushThreads + t;
     if (q < nrec * 4) cp_async16(srec + (size_t)q * 16, src + (size_t)q * 16);
   }
   asm volatile("cp.async.commit_group;" ::: "memory");
-  // ---- owner | local index of this thread's 4 records (record r = round * 256 + t: lanes hold consecutive records)
-  unsigned long long g[kPushRounds];
+  // ---- owner | local index of this thread's records (record r = round * 256 + t: lanes hold consecutive records)
+  unsigned long long g[ROUNDS];
 #pragma unroll
-  for (int j = 0; j < kPushRounds; ++j) {
+  for (int j = 0; j < ROUNDS; ++j) {
     const uint32_t r = j * kPushThreads + t;
     g[j] = r < nrec ? *reinterpret_cast<const unsigned long long*>(src + (size_t)r * 64 + 8) : ~0ull;
   }
-  uint32_t o[kPushRounds], rk[kPushRounds];
+  uint32_t o[ROUNDS], rk[ROUNDS];
 #pragma unroll
-  for (int j = 0; j < kPushRounds; ++j) {
+  for (int j = 0; j < ROUNDS; ++j) {
     const uint32_t r = j * kPushThreads + t;
     o[j] = 0xffu; rk[j] = 0;
     if (r < nrec) {
@@ -131,7 +133,7 @@ __global__ void __launch_bounds__(kPushThreads) route_push_kernel(const __grid_c
   }
   // ---- stable rank inside the warp, per owner
 #pragma unroll
-  for (int j = 0; j < kPushRounds; ++j) {
+  for (int j = 0; j < ROUNDS; ++j) {
     for (uint32_t rr = 0; rr < R; ++rr) {
       const uint32_t m = __ballot_sync(0xffffffffu, o[j] == rr);
       if (o[j] == rr) rk[j] = __popc(m & ((1u << lane) - 1u));
@@ -143,7 +145,7 @@ __global__ void __launch_bounds__(kPushThreads) route_push_kernel(const __grid_c
   if (t < (int)R) {
     uint32_t run = 0;
 #pragma unroll
-    for (int j = 0; j < kPushRounds; ++j)
+    for (int j = 0; j < ROUNDS; ++j)
 #pragma unroll
       for (int w = 0; w < kPushWarps; ++w) { const uint32_t c = wcnt[j][w][t]; wcnt[j][w][t] = run; run += c; }
     cnt[t] = run;
@@ -154,42 +156,51 @@ __global__ void __launch_bounds__(kPushThreads) route_push_kernel(const __grid_c
     for (uint32_t rr = 0; rr < R; ++rr) { start[rr] = s; s += cnt[rr]; }
     start[R] = s;
   }
-  // ---- decoupled look-back (warp 1, lane = owner): this CTA's offset inside each owner's region of the chunk
-  if (warp == 1 && lane < (int)R) {
-    const uint32_t local = cnt[lane];
-    unsigned long long* mine = a.lb + (size_t)bid * kMaxRanks + lane;
+  // ---- decoupled look-back: this CTA's offset inside each owner's region of the chunk. One warp per owner; the 32 lanes
+  //      examine a window of 32 predecessors at once (cells are [owner][cta], a window is one coalesced read).
+  for (uint32_t rr = warp; rr < R; rr += kPushWarps) {
+    const uint32_t local = cnt[rr];
+    unsigned long long* cells = a.lb + (size_t)rr * a.n_ctas;
     uint32_t ex = 0;
     if (bid == 0) {
-      st_relaxed_u64(mine, (2ull << 62) | local);
+      if (lane == 0) st_relaxed_u64(cells, (2ull << 62) | local);
     } else {
-      st_relaxed_u64(mine, (1ull << 62) | local);
-      uint32_t jb = bid - 1;
+      if (lane == 0) st_relaxed_u64(cells + bid, (1ull << 62) | local);
+      uint32_t hi = bid;                    // predecessors hi-1, hi-2, ... are still to be summed
       unsigned long long spins = 0;
       for (;;) {
-        const unsigned long long v = ld_relaxed_u64(a.lb + (size_t)jb * kMaxRanks + lane);
+        const bool in = (uint32_t)lane < hi;
+        const unsigned long long v = in ? ld_relaxed_u64(cells + (hi - 1 - lane)) : (2ull << 62);   // before CTA 0: inclusive 0
         const uint32_t fl = (uint32_t)(v >> 62);
-        if (fl == 0) {
-          if (++spins > kSpinLimit) { atomicAdd(a.status + 2, 1ull); break; }
+        const uint32_t inc = __ballot_sync(0xffffffffu, fl == 2u);
+        const uint32_t need = inc ? ((2u << (__ffs(inc) - 1)) - 1u) : 0xffffffffu;   // lanes up to the nearest inclusive prefix
+        if (__ballot_sync(0xffffffffu, fl == 0u) & need) {
+          if (++spins > kSpinLimit) { if (lane == 0) atomicAdd(a.status + 2, 1ull); break; }
           __nanosleep(20);
           continue;
         }
-        ex += (uint32_t)v;
-        if (fl == 2 || jb == 0) break;
-        --jb;
+        uint32_t part = ((need >> lane) & 1u) ? (uint32_t)v : 0u;
+#pragma unroll
+        for (int of = 16; of; of >>= 1) part += __shfl_xor_sync(0xffffffffu, part, of);
+        ex += part;
+        if (inc) break;
+        hi -= 32;
       }
-      st_relaxed_u64(mine, (2ull << 62) | (ex + local));
+      if (lane == 0) st_relaxed_u64(cells + bid, (2ull << 62) | (ex + local));
     }
-    excl[lane] = ex;
-    if ((unsigned long long)ex + local > a.cap_region) {   // would overflow the region: nothing of this CTA goes to that owner
-      atomicAnd(&s_ok, ~(1u << lane));
-      atomicAdd(a.status + 1, (unsigned long long)local);
+    if (lane == 0) {
+      excl[rr] = ex;
+      if ((unsigned long long)ex + local > a.cap_region) {   // would overflow the region: nothing of this CTA goes to that owner
+        atomicAnd(&s_ok, ~(1u << rr));
+        atomicAdd(a.status + 1, (unsigned long long)local);
+      }
+      if (base + nrec >= a.n) a.totals[rr] = ex + local;     // the chunk's last CTA: its inclusive prefix is the chunk total
     }
-    if (base + nrec >= a.n) a.totals[lane] = ex + local;    // the chunk's last CTA: its inclusive prefix is the chunk total
   }
   __syncthreads();
   // ---- sorted position of every record
 #pragma unroll
-  for (int j = 0; j < kPushRounds; ++j) {
+  for (int j = 0; j < ROUNDS; ++j) {
     if (o[j] != 0xffu) {
       const uint32_t p = start[o[j]] + wcnt[j][warp][o[j]] + rk[j];
       perm[p] = (uint16_t)(j * kPushThreads + t);
@@ -203,7 +214,7 @@ __global__ void __launch_bounds__(kPushThreads) route_push_kernel(const __grid_c
   if (a.out_bytes == 64u) {
     // ---- every owner's run, contiguous: thread -> (sorted position, 16-byte piece)
 #pragma unroll 4
-    for (int it = 0; it < 16; ++it) {
+    for (int it = 0; it < 4 * ROUNDS; ++it) {
       const uint32_t q = it * kPushThreads + t;
       const uint32_t p = q >> 2, k = q & 3u;
       if (p < nvalid) {
@@ -219,7 +230,7 @@ __global__ void __launch_bounds__(kPushThreads) route_push_kernel(const __grid_c
     // ---- projection: u32 local index, then the program's slot words (slot 0 = event type)
     const uint32_t ow4 = a.out_bytes >> 2;
 #pragma unroll
-    for (int j = 0; j < kPushRounds; ++j) {
+    for (int j = 0; j < ROUNDS; ++j) {
       const uint32_t p = j * kPushThreads + t;
       if (p < nvalid) {
         const uint32_t r = perm[p], ow = own_s[p];
@@ -237,6 +248,9 @@ __global__ void __launch_bounds__(kPushThreads) route_push_kernel(const __grid_c
     }
   }
 }
+
+template <int ROUNDS>
+constexpr size_t push_smem_bytes() { return (size_t)ROUNDS * kPushThreads * (64 + 4 + 2 + 1); }
 
 struct FlagArgs {
   unsigned long long* peer_flag[kMaxRanks];   // &header(owner).flags[me][chunk]
@@ -295,11 +309,19 @@ __global__ void gather_region_kernel(const uint8_t* __restrict__ src, uint32_t n
 
 // every allocation the push path makes for logs of up to n records, up front: a cudaMalloc inside the call can wait for a
 // peer's spinning wait kernel when several ranks share one device (loopback)
+PushTuning& push_tuning() { static PushTuning t; return t; }
+
+static int tile_recs() { const int t = push_tuning().tile; return t == 256 || t == 1024 ? t : 512; }
+// chunks are whole multiples of 1024 records (the largest tile), so the chunk boundaries do not depend on the tile size
+static uint64_t chunk_records(uint64_t n, uint32_t n_chunks) {
+  const uint64_t c = (n + n_chunks - 1) / n_chunks;
+  return (c + 1023) / 1024 * 1024;
+}
+
 int dist_push_reserve(DistState* d, uint64_t n, uint32_t n_chunks, std::string* err) {
   if (n_chunks < 1 || n_chunks > (uint32_t)kMaxChunks) { *err = "push_chunks out of range"; return SGR_ERR_INVALID; }
-  uint64_t chunk_recs = (n + n_chunks - 1) / n_chunks;
-  chunk_recs = (chunk_recs + kPushRecs - 1) / kPushRecs * kPushRecs;
-  const uint64_t ctas_per_chunk = chunk_recs / kPushRecs;
+  const uint64_t chunk_recs = chunk_records(n, n_chunks);
+  const uint64_t ctas_per_chunk = chunk_recs / 256;   // sized for the smallest tile
   cudaError_t ce;
   if (!d->h_pinned && (ce = cudaHostAlloc(&d->h_pinned, 128 + (size_t)kMaxRanks * kMaxChunks * 8 + 128, cudaHostAllocDefault)) != cudaSuccess) {
     *err = std::string("page-locked read-back buffer: ") + cudaGetErrorString(ce);
@@ -308,7 +330,9 @@ int dist_push_reserve(DistState* d, uint64_t n, uint32_t n_chunks, std::string* 
   if ((ce = d->push_ctl.reserve((size_t)kMaxChunks * 4 + (size_t)kMaxChunks * kMaxRanks * 4 + 64 + 64)) != cudaSuccess ||
       (ce = d->lb.reserve((size_t)n_chunks * ctas_per_chunk * kMaxRanks * 8 + 256)) != cudaSuccess ||
       (ce = d->counts_all.reserve((size_t)kMaxRanks * kMaxRanks * 8 + 64)) != cudaSuccess ||
-      (ce = cudaFuncSetAttribute(route_push_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPushSmem)) != cudaSuccess) {
+      (ce = cudaFuncSetAttribute(route_push_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)push_smem_bytes<1>())) != cudaSuccess ||
+      (ce = cudaFuncSetAttribute(route_push_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)push_smem_bytes<2>())) != cudaSuccess ||
+      (ce = cudaFuncSetAttribute(route_push_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)push_smem_bytes<4>())) != cudaSuccess) {
     *err = std::string("push buffers: ") + cudaGetErrorString(ce);
     return ce == cudaErrorMemoryAllocation ? SGR_ERR_OOM : SGR_ERR_CUDA;
   }
@@ -330,12 +354,12 @@ int dist_push_fold(DistState* d, const uint8_t* d_records, uint64_t n, const Pus
   if (!cap_region) { *err = "receive buffer too small for R x chunks regions"; return SGR_ERR_CAPACITY; }
   if ((uint64_t)C * cap_region >= (1ull << 30)) { *err = "push path: chunks x region capacity must stay below 2^30 records"; return SGR_ERR_UNSUPPORTED; }
   // chunk size: whole CTAs, the same number of chunks on every rank (the flags are indexed by chunk)
-  uint64_t chunk_recs = (n + C - 1) / C;
-  chunk_recs = (chunk_recs + kPushRecs - 1) / kPushRecs * kPushRecs;
+  const uint64_t chunk_recs = chunk_records(n, C);
+  const int tile = tile_recs();
   if (chunk_recs >= (1ull << 31)) { *err = "push path: chunk too large, raise push_chunks"; return SGR_ERR_UNSUPPORTED; }
   const uint32_t out_bytes = pf.compact ? ((1 + pf.prog->n_slots) * 4 <= 16 ? 16u : 32u) : 64u;
   if (pf.compact && pf.prog->n_slots > 7) { *err = "compact exchange: program reads more than 7 record words"; return SGR_ERR_UNSUPPORTED; }
-  const uint64_t ctas_per_chunk = chunk_recs / kPushRecs;
+  const uint64_t ctas_per_chunk = chunk_recs / tile;
   // control block: tickets[C] | totals[C][kMaxRanks] | status[8] u64 | proj words
   const size_t off_tot = (size_t)kMaxChunks * 4, off_status = off_tot + (size_t)kMaxChunks * kMaxRanks * 4, off_proj = off_status + 64;
   { int rr = dist_push_reserve(d, n, C, err); if (rr) return rr; }
@@ -361,11 +385,13 @@ int dist_push_fold(DistState* d, const uint8_t* d_records, uint64_t n, const Pus
       a.route_of = (const uint32_t*)d->route_of.p;
       for (int q = 0; q < R; ++q) a.dst[q] = d->peer_recv[q] + ((uint64_t)d->rank * C + c) * cap_region * out_bytes;
       a.cap_region = (uint32_t)cap_region; a.out_bytes = out_bytes;
-      a.lb = (unsigned long long*)d->lb.p + (size_t)c * ctas_per_chunk * kMaxRanks;
+      a.lb = (unsigned long long*)d->lb.p + (size_t)c * ctas_per_chunk * kMaxRanks; a.n_ctas = (uint32_t)ctas_per_chunk;
       a.ticket = tickets + c; a.totals = totals + (size_t)c * kMaxRanks; a.status = status;
       if (pf.compact) { a.n_proj = pf.prog->n_slots; for (uint32_t k = 0; k < a.n_proj; ++k) a.proj_word[k] = pf.prog->slot_word[k]; }
-      const uint32_t grid = (uint32_t)((cn + kPushRecs - 1) / kPushRecs);
-      route_push_kernel<<<grid, kPushThreads, kPushSmem, s0>>>(a);
+      const uint32_t grid = (uint32_t)((cn + tile - 1) / tile);
+      if (tile == 256) route_push_kernel<1><<<grid, kPushThreads, push_smem_bytes<1>(), s0>>>(a);
+      else if (tile == 512) route_push_kernel<2><<<grid, kPushThreads, push_smem_bytes<2>(), s0>>>(a);
+      else route_push_kernel<4><<<grid, kPushThreads, push_smem_bytes<4>(), s0>>>(a);
     }
     FlagArgs f{};
     for (int q = 0; q < R; ++q) f.peer_flag[q] = (unsigned long long*)d->peer_base[q] + (size_t)d->rank * kMaxChunks + c;

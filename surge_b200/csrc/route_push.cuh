@@ -11,6 +11,10 @@
 
 namespace sgr {
 
+// measurement knob (sgr_set_option "push_tile"): records per CTA of the push kernel, 256 / 512 / 1024
+struct PushTuning { int tile = 512; };
+PushTuning& push_tuning();
+
 struct PushFoldArgs {
   const RowProgram* prog;
   const BulkLayout* lay;
