@@ -23,7 +23,7 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device(dev))
     scale = float(sys.argv[1]) if len(sys.argv) > 1 else 1.0
-    variants = sys.argv[2].split(",") if len(sys.argv) > 2 else ["1024:16:2", "512:16:2", "256:16:2", "512:32:2", "512:16:3", "256:16:3"]
+    variants = sys.argv[2].split(",") if len(sys.argv) > 2 else ["512:16:2:1:2:0", "1024:16:2:1:2:0", "256:16:2:1:2:0", "512:16:2:1:1:0", "512:16:2:1:2:1", "512:16:2:0:2:0", "512:16:2:0:2:1", "512:16:3:1:2:0", "512:16:3:0:2:0"]
     n_global = int(10_000_000 * scale) // 64 * 64
     rec = S.routed_log_device(rank, world, n_global, 100, 3, dev)
     flat = rec.view(torch.uint8).view(-1)
@@ -37,8 +37,11 @@ def main():
     e.dist_set_partitions(part)
     hashes = set()
     for v in variants:
-        tile, chunks, fused = (int(x) for x in v.split(":"))
+        tile, chunks, fused, pull, fbs, staged = (int(x) for x in v.split(":"))
+        e.set_option("push_staged", staged)
+        e.set_option("push_fold_blocks_per_sm", fbs)
         e.set_option("push_tile", tile)
+        e.set_option("push_pull", pull)
         e.set_option("push_chunks", chunks)
         best = None
         for it in range(4):
@@ -58,7 +61,7 @@ def main():
         ds = e.dist_stats()
         if rank == 0:
             wire = ds.exchange_record_bytes
-            print(f"tile={tile:5d} chunks={chunks:3d} fused={fused}: pipeline {best[0]:8.3f} ms (push issue {best[1]:8.3f})  {n_global * 100 / best[0] / 1e6:7.2f} G ev/s job  "
+            print(f"tile={tile:5d} chunks={chunks:3d} fused={fused} pull={pull} fold_blocks/SM={fbs} staged={staged}: pipeline {best[0]:8.3f} ms (push issue {best[1]:8.3f})  {n_global * 100 / best[0] / 1e6:7.2f} G ev/s job  "
                   f"NVLink out {ds.n_sent_remote * wire / best[0] / 1e6:6.1f} GB/s/GPU  source read {n * 64 / best[0] / 1e6:6.1f} GB/s/GPU  hash {int(h.item()) & ((1 << 64) - 1):016x}", flush=True)
     assert len(hashes) == 1, hashes
     e.close()

@@ -47,6 +47,15 @@ __device__ __forceinline__ uint4 ldg_stream(const void* p, uint64_t pol) {
   else asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
   return v;
 }
+// one 32-byte sector in one request (LDG.256): the two halves of a record's first sector never travel twice — matters when
+// the records are read from a peer over NVLink
+template <bool HINTS>
+__device__ __forceinline__ void ldg_stream32(const void* p, uint64_t pol, uint4& a, uint4& b) {
+  if (HINTS) asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
+                          : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(p), "l"(pol));
+  else asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                    : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(p));
+}
 template <bool HINTS>
 __device__ __forceinline__ void red_add_u32(uint32_t* p, uint32_t v, uint64_t pol) {
   if (HINTS) asm volatile("red.relaxed.gpu.global.add.L2::cache_hint.u32 [%0], %1, %2;" ::"l"(p), "r"(v), "l"(pol) : "memory");
@@ -94,8 +103,8 @@ template <bool HINTS>
 __device__ __forceinline__ void load_rec(RecView& r, const uint8_t* p, bool live, bool two, uint64_t pol) {
   r.p = p; r.live = live;
   if (live) {
-    r.q0 = ldg_stream<HINTS>(p, pol);
-    if (two) r.q1 = ldg_stream<HINTS>(p + 16, pol); else r.q1 = make_uint4(0, 0, 0, 0);
+    if (two) ldg_stream32<HINTS>(p, pol, r.q0, r.q1);
+    else { r.q0 = ldg_stream<HINTS>(p, pol); r.q1 = make_uint4(0, 0, 0, 0); }
   }
 }
 
@@ -138,30 +147,45 @@ __global__ void __launch_bounds__(kThreads) bulk_accumulate_kernel(const __grid_
   for (int i = threadIdx.x; i < 16 * kTabStride; i += kThreads) tab[i] = pg.tab[i];
   __syncthreads();
   const uint64_t pol_first = policy_evict_first(), pol_last = policy_evict_last();
-  const uint64_t tid = (uint64_t)blockIdx.x * kThreads + threadIdx.x, nthreads = (uint64_t)gridDim.x * kThreads;
   const uint32_t stride = a.src.rec_bytes;
   // the second 16 bytes are needed when a slot word lies there (full records: `by` at word 4; compact: records wider than 16 B)
   bool two = COMPACT ? stride > 16u : false;
   if (!COMPACT) for (uint32_t s = 1; s < pg.n_slots; ++s) two |= pg.slot_word[s] >= 4u;
-  for (uint32_t rg = 0; rg < a.src.n_regions; ++rg) {
+  // record counts of the regions (given, or published by the sender in an arrival flag)
+  __shared__ uint64_t n_of[kMaxRanks];
+  __shared__ uint64_t n_max;
+  if (threadIdx.x < a.src.n_regions) {
+    const uint32_t rg = threadIdx.x;
     uint64_t n = a.src.count[rg];
     if (a.src.count_flag[rg]) {   // (epoch << 32) | count + 1; 0xffffffff = the sender gave up on this region
       const uint32_t f = (uint32_t)ld_acquire_sys_u64(a.src.count_flag[rg]);
       const uint64_t got = (f == 0xffffffffu || f == 0u) ? 0ull : (uint64_t)(f - 1u);
       n = got < n ? got : n;
     }
+    n_of[rg] = n;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) { uint64_t m = 0; for (uint32_t rg = 0; rg < a.src.n_regions; ++rg) m = n_of[rg] > m ? n_of[rg] : m; n_max = m; }
+  __syncthreads();
+  // tiles of kThreads * kUnroll records; consecutive tiles rotate over the regions (starting at `rotate`), so the regions —
+  // one per source rank when they are read over NVLink — are all in flight together instead of one peer at a time
+  constexpr uint32_t kTile = kThreads * kUnroll;
+  const uint32_t R = a.src.n_regions;
+  const uint64_t tiles_per_region = (n_max + kTile - 1) / kTile, total = tiles_per_region * R;
+  for (uint64_t T = blockIdx.x; T < total; T += gridDim.x) {
+    const uint32_t rg = (uint32_t)((T + a.src.rotate) % R);
+    const uint64_t n = n_of[rg], i0 = (T / R) * kTile + threadIdx.x;
+    if ((T / R) * kTile >= n) continue;
     const uint8_t* base = a.src.base[rg];
     const uint32_t ib = a.src.idx_base[rg] + 1u;
-    for (uint64_t i0 = tid; i0 < n; i0 += nthreads * kUnroll) {
-      RecView r[kUnroll];
+    RecView r[kUnroll];
 #pragma unroll
-      for (int u = 0; u < kUnroll; ++u) {
-        const uint64_t i = i0 + (uint64_t)u * nthreads;
-        load_rec<HINTS>(r[u], base + i * stride, i < n, two, pol_first);
-      }
-#pragma unroll
-      for (int u = 0; u < kUnroll; ++u) apply_rec<COMPACT, HINTS>(r[u], ib + (uint32_t)(i0 + (uint64_t)u * nthreads), a, pg, tab, pol_last);
+    for (int u = 0; u < kUnroll; ++u) {
+      const uint64_t i = i0 + (uint64_t)u * kThreads;
+      load_rec<HINTS>(r[u], base + i * stride, i < n, two, pol_first);
     }
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) apply_rec<COMPACT, HINTS>(r[u], ib + (uint32_t)(i0 + (uint64_t)u * kThreads), a, pg, tab, pol_last);
   }
 }
 
@@ -301,11 +325,11 @@ cudaError_t launch_bulk_accumulate(const BulkSrc& src, uint64_t n_slots, void* d
   a.src = src; a.n_slots = n_slots; a.scr = (uint8_t*)d_scratch; a.throw_bits = throw_bits_of(d_scratch, lay, n_slots);
   a.counters = d_counters; a.lay = lay;
   uint64_t work = 0;
-  for (uint32_t r = 0; r < src.n_regions; ++r) work = work > src.count[r] ? work : src.count[r];
+  for (uint32_t r = 0; r < src.n_regions; ++r) work += src.count[r];
   if (!work) return cudaSuccess;
   const BulkTuning& t = bulk_tuning();
   const int unroll = t.unroll == 1 || t.unroll == 2 ? t.unroll : 4;
-  const int grid = grid_for(num_sms, (work + unroll - 1) / unroll, t.blocks_per_sm > 0 ? t.blocks_per_sm : 8);
+  const int grid = grid_for(num_sms, (work + unroll - 1) / unroll, src.blocks_per_sm ? (int)src.blocks_per_sm : (t.blocks_per_sm > 0 ? t.blocks_per_sm : 8));
 #define SGR_BULK_LAUNCH(C, H, U) bulk_accumulate_kernel<C, H, U><<<grid, kThreads, 0, st>>>(a, prog)
 #define SGR_BULK_U(C, H) (unroll == 1 ? SGR_BULK_LAUNCH(C, H, 1) : unroll == 2 ? SGR_BULK_LAUNCH(C, H, 2) : SGR_BULK_LAUNCH(C, H, 4))
   if (src.compact) { if (t.hints) SGR_BULK_U(true, true); else SGR_BULK_U(true, false); }

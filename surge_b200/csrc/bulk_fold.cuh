@@ -39,6 +39,9 @@ struct BulkSrc {
   uint64_t count[kMaxRanks];
   uint32_t idx_base[kMaxRanks];   // arrival index of the region's first record: monotone per aggregate across launches
   uint32_t n_regions;
+  uint32_t blocks_per_sm;         // 0: the tuning default; else the grid cap of this launch (a fold that reads peers over NVLink
+                                  // must leave the SMs to the partition kernel running beside it)
+  uint32_t rotate;                // region the first tile starts with (the reader's rank: staggers the peers)
   uint32_t compact;               // 0: 64-byte records (agg u64 at +8); 1: projected records (u32 local agg, then the slot words)
   uint32_t rec_bytes;             // record stride
 };

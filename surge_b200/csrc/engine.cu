@@ -1293,6 +1293,9 @@ int32_t sgr_set_option(sgr_engine* e, const char* name, int64_t value) {
     if (value != 256 && value != 512 && value != 1024) return fail(e, SGR_ERR_INVALID, "push_tile must be 256, 512 or 1024");
     push_tuning().tile = (int)value; return SGR_OK;
   }
+  if (!strcmp(name, "push_fold_blocks_per_sm")) { push_tuning().fold_blocks_per_sm = (int)value; return SGR_OK; }
+  if (!strcmp(name, "push_staged")) { push_tuning().staged = (int)value; return SGR_OK; }
+  if (!strcmp(name, "push_pull")) { push_tuning().pull = value ? 1 : 0; return SGR_OK; }
   if (!strcmp(name, "push_chunks")) {
     if (value < 1 || value > 256) return fail(e, SGR_ERR_INVALID, "push_chunks must be in [1, 256]");
     e->opt_push_chunks = value; return SGR_OK;

@@ -85,6 +85,41 @@ __device__ __forceinline__ void st_na_v4(void* p, const uint4& v) {
   asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
+// Decoupled look-back of one warp for one owner: the exclusive prefix, over the earlier CTAs of the chunk, of the per-CTA record
+// counts for that owner. Every CTA first publishes its own count (flag 1), then sums predecessors back to the nearest one that
+// already knows its inclusive prefix (flag 2), 32 predecessors per step (cells are [owner][cta]: a window is one coalesced read),
+// and publishes its own inclusive prefix. All lanes return the prefix.
+__device__ __forceinline__ uint32_t look_back(unsigned long long* cells, uint32_t bid, uint32_t local, int lane, unsigned long long* status) {
+  uint32_t ex = 0;
+  if (bid == 0) {
+    if (lane == 0) st_relaxed_u64(cells, (2ull << 62) | local);
+    return 0;
+  }
+  if (lane == 0) st_relaxed_u64(cells + bid, (1ull << 62) | local);
+  uint32_t hi = bid;                    // predecessors hi-1, hi-2, ... are still to be summed
+  unsigned long long spins = 0;
+  for (;;) {
+    const bool in = (uint32_t)lane < hi;
+    const unsigned long long v = in ? ld_relaxed_u64(cells + (hi - 1 - lane)) : (2ull << 62);   // before CTA 0: inclusive 0
+    const uint32_t fl = (uint32_t)(v >> 62);
+    const uint32_t inc = __ballot_sync(0xffffffffu, fl == 2u);
+    const uint32_t need = inc ? ((2u << (__ffs(inc) - 1)) - 1u) : 0xffffffffu;   // lanes up to the nearest inclusive prefix
+    if (__ballot_sync(0xffffffffu, fl == 0u) & need) {
+      if (++spins > kSpinLimit) { if (lane == 0) atomicAdd(status + 2, 1ull); break; }
+      __nanosleep(20);
+      continue;
+    }
+    uint32_t part = ((need >> lane) & 1u) ? (uint32_t)v : 0u;
+#pragma unroll
+    for (int of = 16; of; of >>= 1) part += __shfl_xor_sync(0xffffffffu, part, of);
+    ex += part;
+    if (inc) break;
+    hi -= 32;
+  }
+  if (lane == 0) st_relaxed_u64(cells + bid, (2ull << 62) | (ex + local));
+  return ex;
+}
+
 extern __shared__ __align__(16) uint8_t push_smem[];
 
 // One CTA = one tile of RECS consecutive records of the chunk (RECS = 256 * ROUNDS). Smaller tiles put more CTAs on an SM, so
@@ -160,34 +195,7 @@ __global__ void __launch_bounds__(kPushThreads) route_push_kernel(const __grid_c
   //      examine a window of 32 predecessors at once (cells are [owner][cta], a window is one coalesced read).
   for (uint32_t rr = warp; rr < R; rr += kPushWarps) {
     const uint32_t local = cnt[rr];
-    unsigned long long* cells = a.lb + (size_t)rr * a.n_ctas;
-    uint32_t ex = 0;
-    if (bid == 0) {
-      if (lane == 0) st_relaxed_u64(cells, (2ull << 62) | local);
-    } else {
-      if (lane == 0) st_relaxed_u64(cells + bid, (1ull << 62) | local);
-      uint32_t hi = bid;                    // predecessors hi-1, hi-2, ... are still to be summed
-      unsigned long long spins = 0;
-      for (;;) {
-        const bool in = (uint32_t)lane < hi;
-        const unsigned long long v = in ? ld_relaxed_u64(cells + (hi - 1 - lane)) : (2ull << 62);   // before CTA 0: inclusive 0
-        const uint32_t fl = (uint32_t)(v >> 62);
-        const uint32_t inc = __ballot_sync(0xffffffffu, fl == 2u);
-        const uint32_t need = inc ? ((2u << (__ffs(inc) - 1)) - 1u) : 0xffffffffu;   // lanes up to the nearest inclusive prefix
-        if (__ballot_sync(0xffffffffu, fl == 0u) & need) {
-          if (++spins > kSpinLimit) { if (lane == 0) atomicAdd(a.status + 2, 1ull); break; }
-          __nanosleep(20);
-          continue;
-        }
-        uint32_t part = ((need >> lane) & 1u) ? (uint32_t)v : 0u;
-#pragma unroll
-        for (int of = 16; of; of >>= 1) part += __shfl_xor_sync(0xffffffffu, part, of);
-        ex += part;
-        if (inc) break;
-        hi -= 32;
-      }
-      if (lane == 0) st_relaxed_u64(cells + bid, (2ull << 62) | (ex + local));
-    }
+    const uint32_t ex = look_back(a.lb + (size_t)rr * a.n_ctas, bid, local, lane, a.status);
     if (lane == 0) {
       excl[rr] = ex;
       if ((unsigned long long)ex + local > a.cap_region) {   // would overflow the region: nothing of this CTA goes to that owner
@@ -244,6 +252,118 @@ __global__ void __launch_bounds__(kPushThreads) route_push_kernel(const __grid_c
           st_na_v4(dp, make_uint4(out[0], out[1], out[2], out[3]));
           if (ow4 > 4) st_na_v4(dp + 16, make_uint4(out[4], out[5], out[6], out[7]));
         }
+      }
+    }
+  }
+}
+
+// The same partition WITHOUT staging the records in shared memory: positions first (headers -> owner -> stable rank ->
+// look-back), then every record is copied global -> global, 4 lanes x 16 bytes per record (coalesced 512-byte reads; 64-byte
+// writes at the record's position in its owner's region). Nine bytes of shared memory per record instead of 71, so eight CTAs
+// fit on an SM and tiles in their latency-bound phases (route lookup, look-back) overlap with tiles that are copying. This is
+// the kernel of the PULL mode, where every region is in this rank's own HBM (64-byte writes are full DRAM bursts there);
+// contiguous per-owner runs only matter for stores that cross NVLink.
+template <int ROUNDS>
+__global__ void __launch_bounds__(kPushThreads) route_part_kernel(const __grid_constant__ PushArgs a) {
+  constexpr int RECS = ROUNDS * kPushThreads;
+  __shared__ uint32_t dpos[RECS];                 // position inside the owner's region, by record
+  __shared__ uint32_t loc[RECS];                  // owner's local aggregate index, by record
+  __shared__ uint8_t own[RECS];                   // owner (0xff: dropped), by record
+  __shared__ uint32_t wcnt[ROUNDS][kPushWarps][kMaxRanks];
+  __shared__ uint32_t excl[kMaxRanks], cnt[kMaxRanks];
+  __shared__ uint32_t s_bid, s_ok;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const uint32_t R = a.nranks;
+  if (t == 0) { s_bid = atomicAdd(a.ticket, 1u); s_ok = 0xffffffffu; }
+  __syncthreads();
+  const uint32_t bid = s_bid;
+  const uint32_t base = bid * RECS;
+  const uint32_t nrec = a.n - base < (uint32_t)RECS ? a.n - base : (uint32_t)RECS;
+  const uint8_t* src = a.rec + (uint64_t)base * 64;
+  unsigned long long g[ROUNDS];
+#pragma unroll
+  for (int j = 0; j < ROUNDS; ++j) {
+    const uint32_t r = j * kPushThreads + t;
+    g[j] = r < nrec ? *reinterpret_cast<const unsigned long long*>(src + (size_t)r * 64 + 8) : ~0ull;
+  }
+  uint32_t o[ROUNDS], rk[ROUNDS];
+#pragma unroll
+  for (int j = 0; j < ROUNDS; ++j) {
+    const uint32_t r = j * kPushThreads + t;
+    o[j] = 0xffu; rk[j] = 0;
+    if (r < nrec) {
+      if (g[j] < a.n_global) { const uint32_t ro = __ldg(a.route_of + g[j]); o[j] = ro >> 28; loc[r] = ro & 0x0fffffffu; }
+      else atomicAdd(a.status + 0, 1ull);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < ROUNDS; ++j) {
+    for (uint32_t rr = 0; rr < R; ++rr) {
+      const uint32_t m = __ballot_sync(0xffffffffu, o[j] == rr);
+      if (o[j] == rr) rk[j] = __popc(m & ((1u << lane) - 1u));
+      if (lane == 0) wcnt[j][warp][rr] = __popc(m);
+    }
+  }
+  __syncthreads();
+  if (t < (int)R) {
+    uint32_t run = 0;
+#pragma unroll
+    for (int j = 0; j < ROUNDS; ++j)
+#pragma unroll
+      for (int w = 0; w < kPushWarps; ++w) { const uint32_t c = wcnt[j][w][t]; wcnt[j][w][t] = run; run += c; }
+    cnt[t] = run;
+  }
+  __syncthreads();
+  for (uint32_t rr = warp; rr < R; rr += kPushWarps) {
+    const uint32_t local = cnt[rr];
+    const uint32_t ex = look_back(a.lb + (size_t)rr * a.n_ctas, bid, local, lane, a.status);
+    if (lane == 0) {
+      excl[rr] = ex;
+      if ((unsigned long long)ex + local > a.cap_region) {   // would overflow the region: nothing of this CTA goes to that owner
+        atomicAnd(&s_ok, ~(1u << rr));
+        atomicAdd(a.status + 1, (unsigned long long)local);
+      }
+      if (base + nrec >= a.n) a.totals[rr] = ex + local;     // the chunk's last CTA: its inclusive prefix is the chunk total
+    }
+  }
+  __syncthreads();
+  const uint32_t ok = s_ok;
+#pragma unroll
+  for (int j = 0; j < ROUNDS; ++j) {
+    const uint32_t r = j * kPushThreads + t;
+    const bool keep = o[j] != 0xffu && ((ok >> o[j]) & 1u);
+    own[r] = keep ? (uint8_t)o[j] : (uint8_t)0xff;
+    if (keep) dpos[r] = excl[o[j]] + wcnt[j][warp][o[j]] + rk[j];
+  }
+  __syncthreads();
+  if (a.out_bytes == 64u) {
+#pragma unroll 4
+    for (int it = 0; it < 4 * ROUNDS; ++it) {
+      const uint32_t q = it * kPushThreads + t;
+      const uint32_t r = q >> 2, k = q & 3u;
+      if (r < nrec) {
+        const uint32_t ow = own[r];
+        if (ow != 0xffu) {
+          uint4 v = __ldg(reinterpret_cast<const uint4*>(src + (size_t)r * 64) + k);
+          if (k == 0) { v.z = loc[r]; v.w = 0u; }   // agg := the owner's LOCAL aggregate index
+          *reinterpret_cast<uint4*>(a.dst[ow] + (size_t)dpos[r] * 64 + k * 16) = v;
+        }
+      }
+    }
+  } else {
+    const uint32_t ow4 = a.out_bytes >> 2;
+#pragma unroll
+    for (int j = 0; j < ROUNDS; ++j) {
+      const uint32_t r = j * kPushThreads + t;
+      if (r < nrec && own[r] != 0xffu) {
+        const uint32_t* rw = reinterpret_cast<const uint32_t*>(src + (size_t)r * 64);
+        uint32_t out[8];
+        out[0] = loc[r];
+#pragma unroll
+        for (uint32_t k = 0; k < 7; ++k) out[1 + k] = k < a.n_proj ? __ldg(rw + a.proj_word[k]) : 0u;
+        uint8_t* dp = a.dst[own[r]] + (size_t)dpos[r] * a.out_bytes;
+        *reinterpret_cast<uint4*>(dp) = make_uint4(out[0], out[1], out[2], out[3]);
+        if (ow4 > 4) *reinterpret_cast<uint4*>(dp + 16) = make_uint4(out[4], out[5], out[6], out[7]);
       }
     }
   }
@@ -366,6 +486,7 @@ int dist_push_fold(DistState* d, const uint8_t* d_records, uint64_t n, const Pus
   uint32_t* tickets = (uint32_t*)d->push_ctl.p;
   uint32_t* totals = (uint32_t*)((uint8_t*)d->push_ctl.p + off_tot);
   unsigned long long* status = (unsigned long long*)((uint8_t*)d->push_ctl.p + off_status);
+  const bool pull = push_tuning().pull != 0;
   const uint32_t epoch = ++d->epoch;
   cudaStream_t s0 = st, s1 = d->stream2;
   DTRY(cudaMemsetAsync(d->push_ctl.p, 0, off_proj + 64, s0));
@@ -383,15 +504,25 @@ int dist_push_fold(DistState* d, const uint8_t* d_records, uint64_t n, const Pus
       PushArgs a{};
       a.rec = d_records + begin * 64; a.n = (uint32_t)cn; a.nranks = (uint32_t)R; a.n_global = d->n_global;
       a.route_of = (const uint32_t*)d->route_of.p;
-      for (int q = 0; q < R; ++q) a.dst[q] = d->peer_recv[q] + ((uint64_t)d->rank * C + c) * cap_region * out_bytes;
+      // push: region (me, chunk) inside every owner's buffer (remote stores); pull: region (owner, chunk) inside MY buffer
+      for (int q = 0; q < R; ++q)
+        a.dst[q] = pull ? d->peer_recv[d->rank] + ((uint64_t)q * C + c) * cap_region * out_bytes
+                        : d->peer_recv[q] + ((uint64_t)d->rank * C + c) * cap_region * out_bytes;
       a.cap_region = (uint32_t)cap_region; a.out_bytes = out_bytes;
       a.lb = (unsigned long long*)d->lb.p + (size_t)c * ctas_per_chunk * kMaxRanks; a.n_ctas = (uint32_t)ctas_per_chunk;
       a.ticket = tickets + c; a.totals = totals + (size_t)c * kMaxRanks; a.status = status;
       if (pf.compact) { a.n_proj = pf.prog->n_slots; for (uint32_t k = 0; k < a.n_proj; ++k) a.proj_word[k] = pf.prog->slot_word[k]; }
       const uint32_t grid = (uint32_t)((cn + tile - 1) / tile);
-      if (tile == 256) route_push_kernel<1><<<grid, kPushThreads, push_smem_bytes<1>(), s0>>>(a);
-      else if (tile == 512) route_push_kernel<2><<<grid, kPushThreads, push_smem_bytes<2>(), s0>>>(a);
-      else route_push_kernel<4><<<grid, kPushThreads, push_smem_bytes<4>(), s0>>>(a);
+      const bool staged = push_tuning().staged >= 0 ? push_tuning().staged != 0 : !pull;   // contiguous runs only pay across NVLink
+      if (staged) {
+        if (tile == 256) route_push_kernel<1><<<grid, kPushThreads, push_smem_bytes<1>(), s0>>>(a);
+        else if (tile == 512) route_push_kernel<2><<<grid, kPushThreads, push_smem_bytes<2>(), s0>>>(a);
+        else route_push_kernel<4><<<grid, kPushThreads, push_smem_bytes<4>(), s0>>>(a);
+      } else {
+        if (tile == 256) route_part_kernel<1><<<grid, kPushThreads, 0, s0>>>(a);
+        else if (tile == 512) route_part_kernel<2><<<grid, kPushThreads, 0, s0>>>(a);
+        else route_part_kernel<4><<<grid, kPushThreads, 0, s0>>>(a);
+      }
     }
     FlagArgs f{};
     for (int q = 0; q < R; ++q) f.peer_flag[q] = (unsigned long long*)d->peer_base[q] + (size_t)d->rank * kMaxChunks + c;
@@ -400,9 +531,12 @@ int dist_push_fold(DistState* d, const uint8_t* d_records, uint64_t n, const Pus
     // ---- receiver side of chunk c
     push_wait_kernel<<<1, 32, 0, s1>>>(my_flags, c, (uint32_t)R, epoch, status);
     BulkSrc bs{};
-    bs.n_regions = (uint32_t)R; bs.compact = pf.compact ? 1u : 0u; bs.rec_bytes = out_bytes;
+    bs.n_regions = (uint32_t)R; bs.compact = pf.compact ? 1u : 0u; bs.rec_bytes = out_bytes; bs.rotate = (uint32_t)d->rank;
+    bs.blocks_per_sm = (uint32_t)push_tuning().fold_blocks_per_sm;
     for (int s = 0; s < R; ++s) {
-      bs.base[s] = d->peer_recv[d->rank] + ((uint64_t)s * C + c) * cap_region * out_bytes;
+      // pull: source s keeps what it has for me in ITS buffer, region (me, chunk): the fold reads it over NVLink
+      bs.base[s] = pull ? d->peer_recv[s] + ((uint64_t)d->rank * C + c) * cap_region * out_bytes
+                        : d->peer_recv[d->rank] + ((uint64_t)s * C + c) * cap_region * out_bytes;
       bs.count_flag[s] = my_flags + (size_t)s * kMaxChunks + c;
       bs.count[s] = cap_region;
       bs.idx_base[s] = (uint32_t)((uint64_t)c * cap_region);
@@ -436,7 +570,8 @@ int dist_push_fold(DistState* d, const uint8_t* d_records, uint64_t n, const Pus
       if ((uint32_t)(v >> 32) != epoch || (uint32_t)v == 0xffffffffu) { remote_err = true; continue; }
       const uint32_t cnt = (uint32_t)v - 1u;
       n_recv += cnt;
-      out->regions.push_back({d->peer_recv[d->rank] + ((uint64_t)s * C + c) * cap_region * out_bytes, cnt});
+      out->regions.push_back({pull ? d->peer_recv[s] + ((uint64_t)d->rank * C + c) * cap_region * out_bytes
+                                   : d->peer_recv[d->rank] + ((uint64_t)s * C + c) * cap_region * out_bytes, cnt});
     }
   int my_err = SGR_OK;
   if (h_status[0]) { *err = std::to_string(h_status[0]) + " records carry a global aggregate index >= n_global"; my_err = SGR_ERR_INVALID; }

@@ -12,7 +12,11 @@
 namespace sgr {
 
 // measurement knob (sgr_set_option "push_tile"): records per CTA of the push kernel, 256 / 512 / 1024
-struct PushTuning { int tile = 512; };
+// "push_pull": 1 = the sender partitions into its OWN buffer and the owner's fold reads the regions over NVLink (remote loads);
+//              0 = the sender writes into the owner's buffer (remote stores). The same on every rank.
+// "push_staged": 1 = partition through shared memory (contiguous per-owner runs), 0 = position pass + direct copy, -1 = staged iff
+//                the regions are written over NVLink (pull == 0)
+struct PushTuning { int tile = 512; int pull = 1; int fold_blocks_per_sm = 2; int staged = -1; };
 PushTuning& push_tuning();
 
 struct PushFoldArgs {

@@ -236,6 +236,31 @@ def test_loopback_push_pipeline_matches_oracle(R, fused):
             e.close()
 
 
+@pytest.mark.parametrize("pull,staged,tile", [(0, 1, 1024), (0, 0, 256), (1, 1, 512), (1, 0, 1024), (1, 0, 256)])
+def test_loopback_exchange_variants_agree(pull, staged, tile):
+    """remote stores vs remote loads, staged vs direct partition kernel, every tile size: the same tables."""
+    R, n_global = 4, 20000
+    rng = np.random.default_rng(pull * 7 + staged * 3 + tile)
+    counts = rng.integers(0, 35, size=n_global)
+    rec, off = S.counter_csr(n_global, counts, seed=tile + pull, p_throw=0.001)
+    want, _, _ = O.fold_packed(O.MODEL_COUNTER, O.REC_FIXED64, rec, off)
+    part = D.partitions_for_keys([f"agg-{g}" for g in range(n_global)], 32)
+    knobs = ReplayEngine(0)
+    try:
+        knobs.set_option("push_pull", pull); knobs.set_option("push_staged", staged); knobs.set_option("push_tile", tile)
+        for fused in (2, 3):
+            engines, errors = _loopback_job(R, n_global, rec, part, fused, chunks=3, capacity=int(len(rec) / R * 1.6) + 200000)
+            try:
+                assert not any(errors), errors
+                _check_loopback(engines, want, R)
+            finally:
+                for e in engines:
+                    e.close()
+    finally:
+        knobs.set_option("push_pull", 1); knobs.set_option("push_staged", -1); knobs.set_option("push_tile", 512)
+        knobs.close()
+
+
 def test_loopback_push_with_throwing_events_replays_exactly():
     R, n_global = 4, 12000
     rng = np.random.default_rng(77)
