@@ -409,6 +409,10 @@ int32_t sgr_ingest_set_json_packer(sgr_ingest* g, const char* discriminator, con
  * record with a null value deletes the key (CORE/internal/SurgeModel.scala:62-64). With event_type >= 0 such a record becomes an
  * event of that type (the program's SGR_TOMBSTONE rule) instead of being dropped; -1 (default) drops it. */
 int32_t sgr_ingest_set_null_value_type(sgr_ingest* g, int32_t event_type);
+/* The id dictionary holds at most 2^31 ids and 4 GiB of id bytes (32-bit fields). A call that could exceed a bound fails with
+ * SGR_ERR_CAPACITY before anything is applied (every id of the call is counted as new: conservative). Lower bounds can be set
+ * to fail earlier (operators; tests). */
+int32_t sgr_ingest_set_dictionary_limits(sgr_ingest* g, uint64_t max_ids, uint64_t max_id_bytes);
 /* aborted transactions of the next fetch of `partition`: (producerId, firstOffset) pairs */
 int32_t sgr_ingest_set_aborted(sgr_ingest* g, int32_t partition, const int64_t* producer_ids, const int64_t* first_offsets, uint64_t n);
 int32_t sgr_ingest_record_batches(sgr_ingest* g, int32_t partition, const void* data, uint64_t nbytes, sgr_ingest_stats* stats);

@@ -62,6 +62,18 @@ __global__ void route_table_kernel(const uint8_t* __restrict__ owner_of, const u
   if (i < n) route_of[i] = ((uint32_t)owner_of[i] << 28) | (local_of[i] & 0x0fffffffu);
 }
 
+// my row of the count matrix: records per owner, my receive capacity, how many of my records carry a bad aggregate index
+__global__ void route_row_kernel(const uint32_t* __restrict__ owner_total, const unsigned long long* __restrict__ bad, uint64_t capacity,
+                                 uint32_t* __restrict__ row) {
+  const uint32_t i = threadIdx.x;
+  if (i < (uint32_t)kMaxRanks) row[i] = owner_total[i];
+  if (i == 0) {
+    row[kMaxRanks] = (uint32_t)capacity; row[kMaxRanks + 1] = (uint32_t)(capacity >> 32);
+    const unsigned long long b = *bad;
+    row[kMaxRanks + 2] = b > 0xffffffffull ? 0xffffffffu : (uint32_t)b; row[kMaxRanks + 3] = 0;
+  }
+}
+
 // ---------------------------------------------------------------- K4: count
 // hist[owner * nblocks + block] = records of this block owned by `owner`
 __global__ void __launch_bounds__(kRouteThreads) route_count_kernel(const uint8_t* __restrict__ rec, uint64_t n, uint64_t n_global,
@@ -350,7 +362,6 @@ int dist_route(DistState* d, const uint8_t* d_records, uint64_t n, bool fused, u
   DTRY(d->hist.reserve((size_t)(kMaxRanks + 1) * nblocks * 4 + 64));
   DTRY(d->scan_tmp.reserve(((size_t)2 * (((size_t)(kMaxRanks + 1) * nblocks) / 4096 + 2) + 4 * 4096) * 4));
   DTRY(d->owner_total.reserve(2 * kMaxRanks * 4));
-  DTRY(d->counts_all.reserve((size_t)kMaxRanks * kMaxRanks * 8 + 64));
   uint32_t* owner_total = (uint32_t*)d->owner_total.p;
   uint32_t* owner_total_ex = owner_total + kMaxRanks;
 
@@ -364,26 +375,44 @@ int dist_route(DistState* d, const uint8_t* d_records, uint64_t n, bool fused, u
   DTRY(cudaGetLastError());
   DTRY(cudaEventRecord(d->ev[1], st));
 
-  // ---- counts: send[r] on every rank -> nranks x nranks matrix on every rank
+  // ---- counts: send[r] on every rank -> nranks x nranks matrix on every rank. Each row also carries the rank's receive capacity
+  //      and its count of bad records, so that EVERY rank evaluates EVERY rank's outcome and all fail (or proceed) together,
+  //      before anything is written into a peer: a rank over capacity is never written past, nobody is left alone in a collective
+  constexpr int kRow = kMaxRanks + 4;   // counts | capacity lo, hi | bad | pad
+  DTRY(d->counts_all.reserve((size_t)(kMaxRanks + 1) * kRow * 4 + 64));
+  uint32_t* d_row = (uint32_t*)d->counts_all.p;                 // my row
+  uint32_t* d_all = d_row + kRow;                               // the gathered matrix
+  route_row_kernel<<<1, 32, 0, st>>>(owner_total, d_counters + 4, d->recv_capacity, d_row);
   std::vector<uint32_t> send_cnt(kMaxRanks, 0);
-  std::vector<uint32_t> all_cnt((size_t)R * kMaxRanks, 0);
-  unsigned long long bad = 0;
+  std::vector<uint32_t> rows((size_t)R * kRow, 0);
   if (R > 1) {
-    uint32_t* d_all = (uint32_t*)d->counts_all.p;
-    NTRY(g_nccl.AllGather(owner_total, d_all, kMaxRanks, ncclUint32, d->comm, st));
-    DTRY(cudaMemcpyAsync(all_cnt.data(), d_all, (size_t)R * kMaxRanks * 4, cudaMemcpyDeviceToHost, st));
+    NTRY(g_nccl.AllGather(d_row, d_all, kRow, ncclUint32, d->comm, st));
+    DTRY(cudaMemcpyAsync(rows.data(), d_all, (size_t)R * kRow * 4, cudaMemcpyDeviceToHost, st));
   } else {
-    DTRY(cudaMemcpyAsync(all_cnt.data(), owner_total, kMaxRanks * 4, cudaMemcpyDeviceToHost, st));
+    DTRY(cudaMemcpyAsync(rows.data(), d_row, kRow * 4, cudaMemcpyDeviceToHost, st));
   }
-  DTRY(cudaMemcpyAsync(&bad, d_counters + 4, 8, cudaMemcpyDeviceToHost, st));
   DTRY(cudaStreamSynchronize(st));
-  if (bad) { *err = std::to_string(bad) + " records carry a global aggregate index >= n_global"; return SGR_ERR_INVALID; }
+  std::vector<uint32_t> all_cnt((size_t)R * kMaxRanks, 0);
+  for (int s = 0; s < R; ++s) for (int q = 0; q < kMaxRanks; ++q) all_cnt[(size_t)s * kMaxRanks + q] = rows[(size_t)s * kRow + q];
+  for (int s = 0; s < R; ++s)
+    if (rows[(size_t)s * kRow + kMaxRanks + 2]) {
+      *err = "rank " + std::to_string(s) + ": " + std::to_string(rows[(size_t)s * kRow + kMaxRanks + 2]) + "+ records carry a global aggregate index >= n_global";
+      return SGR_ERR_INVALID;
+    }
   for (int r = 0; r < R; ++r) send_cnt[r] = all_cnt[(size_t)d->rank * kMaxRanks + r];
   // receive layout on rank q: blocks by source rank s, in rank order
   uint64_t n_recv = 0;
   std::vector<uint64_t> recv_off(R, 0);
   for (int s = 0; s < R; ++s) { recv_off[s] = n_recv; n_recv += all_cnt[(size_t)s * kMaxRanks + d->rank]; }
-  if (n_recv > d->recv_capacity) { *err = "receive buffer too small: " + std::to_string(n_recv) + " > " + std::to_string(d->recv_capacity) + " records"; return SGR_ERR_CAPACITY; }
+  for (int q = 0; q < R; ++q) {
+    uint64_t nq = 0;
+    for (int s = 0; s < R; ++s) nq += all_cnt[(size_t)s * kMaxRanks + q];
+    const uint64_t capq = ((uint64_t)rows[(size_t)q * kRow + kMaxRanks + 1] << 32) | rows[(size_t)q * kRow + kMaxRanks];
+    if (nq > capq) {
+      *err = "receive buffer of rank " + std::to_string(q) + " too small: " + std::to_string(nq) + " > " + std::to_string(capq) + " records";
+      return SGR_ERR_CAPACITY;
+    }
+  }
   *n_recv_out = n_recv;
   DTRY(cudaEventRecord(d->ev[2], st));
 

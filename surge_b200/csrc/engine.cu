@@ -411,7 +411,12 @@ int32_t finish_fold(sgr_engine* e) {
     a.events = e->pending_events; a.seg_offsets = e->pending_offsets; a.seg_ids = e->pending_ids; a.n_seg = e->pending_n_seg;
     a.states_in = e->pending_prior ? (const uint8_t*)e->states.p : nullptr; a.states_out = (uint8_t*)e->states.p;
     a.counters = (unsigned long long*)e->counters.p;
-    if (e->pending_prior) return fail(e, SGR_ERR_UNSUPPORTED, "replay list overflow on an in-place incremental fold");
+    if (e->pending_prior) {
+      // the kernel has already overwritten the non-throwing aggregates in place: the table is half-applied. It must not be
+      // served, and a retry must not double-apply — invalidate it (reads fail with SGR_ERR_STATE until the next full fold)
+      e->states_valid = false; mark_dirty(e);
+      return fail(e, SGR_ERR_UNSUPPORTED, "replay list overflow on an in-place incremental fold: state table invalidated, rebuild it");
+    }
     CUDA_TRY(e, cudaMemsetAsync(e->counters.p, 0, 64, e->stream));
     CUDA_TRY(e, cudaEventRecord(e->ev2, e->stream));
     FoldLaunchInfo info{};

@@ -324,6 +324,7 @@ class ShardedDict {
     sl.off_len = ((uint64_t)offs_[nk.final_idx] << 24) | nk.len;
   }
   uint64_t size() const { return n_; }
+  uint64_t arena_bytes() const { return bytes_.size(); }
   const uint8_t* bytes() const { return bytes_.data(); }
   const uint32_t* offsets() const { return offs_.data(); }
 
@@ -699,6 +700,7 @@ struct sgr_ingest {
   std::map<int32_t, PartitionState> parts;
   sgr_ingest_stats total{};
   uint64_t keys_at_mark = 0;
+  uint64_t max_ids = 1ull << 31, max_id_bytes = 1ull << 32;   // what the 32-bit dictionary fields can address
   int32_t value_framing = 0;        // SGR_VALUE_PACKED | SGR_VALUE_PROTOBUF_EVENT | SGR_VALUE_JSON
   JsonPacker json;
   int32_t null_value_type = -1;     // >= 0: a keyed record with a null value becomes an event of this type (state-topic tombstones)
@@ -783,6 +785,13 @@ int32_t sgr_ingest_set_value_framing(sgr_ingest* g, int32_t framing) {
 int32_t sgr_ingest_set_null_value_type(sgr_ingest* g, int32_t event_type) {
   if (!g || event_type >= (int32_t)SGR_MAX_TYPES) return ifail(g, SGR_ERR_INVALID, "event type out of range");
   g->null_value_type = event_type < 0 ? -1 : event_type;
+  return SGR_OK;
+}
+
+int32_t sgr_ingest_set_dictionary_limits(sgr_ingest* g, uint64_t max_ids, uint64_t max_id_bytes) {
+  if (!g || max_ids == 0 || max_ids > (1ull << 31) || max_id_bytes == 0 || max_id_bytes > (1ull << 32))
+    return ifail(g, SGR_ERR_INVALID, "limits must be in (0, 2^31] ids and (0, 2^32] bytes");
+  g->max_ids = max_ids; g->max_id_bytes = max_id_bytes;
   return SGR_OK;
 }
 
@@ -1095,6 +1104,17 @@ int32_t sgr_ingest_record_batches_mt(sgr_ingest* g, uint32_t n, const int32_t* p
   size_t add = 0, n_rec_total = 0;
   for (uint32_t i = 0; i < n; ++i) { add += staged[i].recs.size(); n_rec_total += staged[i].keys.size(); }
   if (!g->pending.grow_to(g->pending.n + add)) return ifail(g, SGR_ERR_OOM, "pending log of %zu bytes", g->pending.n + add);
+  // The dictionary addresses its id arena with 32-bit offsets and keeps bit 31 of an index for provisional slots: refuse, BEFORE
+  // anything is probed or admitted, a call that could carry it past either bound (conservative: every id of the call counted as
+  // new). Without this a restore of more than 4 GiB of id bytes or 2^31 ids would wrap silently and fold events into the wrong
+  // aggregates.
+  {
+    uint64_t id_bytes = 0;
+    for (uint32_t i = 0; i < n; ++i) for (const KeyRef& k : staged[i].keys) id_bytes += k.len;
+    if (g->dict.arena_bytes() + id_bytes >= g->max_id_bytes || g->dict.size() + n_rec_total >= g->max_ids)
+      return ifail(g, SGR_ERR_CAPACITY, "id dictionary full: %llu ids / %llu id bytes held, this call may add %zu / %llu (limits 2^31 ids, 4 GiB)",
+                   (unsigned long long)g->dict.size(), (unsigned long long)g->dict.arena_bytes(), n_rec_total, (unsigned long long)id_bytes);
+  }
   // ids -> dense indices: shards probed in parallel, new ids admitted serially in arrival order, slots published in parallel
   const uint32_t n_workers = std::max(1u, std::min<uint32_t>(std::min<uint32_t>(threads ? threads : 1, (uint32_t)ShardedDict::kShards),
                                                              (uint32_t)(n_rec_total / 1024 + 1)));   // a worker per ~1k ids at least

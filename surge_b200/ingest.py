@@ -83,6 +83,10 @@ class Ingest:
         """State-topic mode: null-valued records become events of `event_type` (the program's tombstone rule); -1 drops them."""
         self._check(self._lib.sgr_ingest_set_null_value_type(self._h, event_type))
 
+    def set_dictionary_limits(self, max_ids: int, max_id_bytes: int) -> None:
+        """Fail with SGR_ERR_CAPACITY once a call could carry the id dictionary past these bounds (defaults 2^31 ids, 4 GiB)."""
+        self._check(self._lib.sgr_ingest_set_dictionary_limits(self._h, max_ids, max_id_bytes))
+
     def set_aborted(self, partition: int, aborted: Sequence[Tuple[int, int]]) -> None:
         """aborted = [(producer_id, first_offset)] from the fetch response."""
         if not aborted:

@@ -141,6 +141,7 @@ ABI = [
     ("sgr_ingest_set_value_framing", C.c_int32, [_P, C.c_int32]),
     ("sgr_ingest_set_json_packer", C.c_int32, [_P, C.c_char_p, C.POINTER(sgr_json_event), C.c_uint32, C.c_int32]),
     ("sgr_ingest_set_null_value_type", C.c_int32, [_P, C.c_int32]),
+    ("sgr_ingest_set_dictionary_limits", C.c_int32, [_P, C.c_uint64, C.c_uint64]),
     ("sgr_ingest_set_aborted", C.c_int32, [_P, C.c_int32, _P, _P, C.c_uint64]),
     ("sgr_ingest_record_batches", C.c_int32, [_P, C.c_int32, _P, C.c_uint64, C.POINTER(sgr_ingest_stats)]),
     ("sgr_ingest_record_batches_mt", C.c_int32, [_P, C.c_uint32, _P, _P, _P, C.c_uint32, _P]),

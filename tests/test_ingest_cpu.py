@@ -376,6 +376,28 @@ def test_multi_fetch_call_is_all_or_nothing():
     assert sum(s["n_records"] for s in st) == len(ing.pending()) - 1
 
 
+def test_id_dictionary_refuses_to_wrap_its_32_bit_fields():
+    """ADVICE r1 (ingest.cpp ShardedDict): past 2^31 ids / 4 GiB of id bytes the dictionary would wrap silently and fold events
+    into the wrong aggregates. The bound is checked before anything is applied; lowered here to make it reachable."""
+    rng = np.random.default_rng(5)
+    ing = Ingest()
+    first, nxt = _batch_stream(rng, 2, 20, "none", 0)
+    ing.record_batches(0, first)
+    keys_before, pending_before, offs_before = ing.keys(), len(ing.pending()), ing.offsets(0)
+    ing.set_dictionary_limits(len(keys_before) + 5, 1 << 32)          # room for 5 more ids; the next fetch carries dozens of records
+    more, _ = _batch_stream(rng, 3, 500, "lz4", nxt)
+    with pytest.raises(IngestError) as ei:
+        ing.record_batches(0, more)
+    assert ei.value.code == N.SGR_ERR_CAPACITY and "id dictionary full" in str(ei.value)
+    assert ing.keys() == keys_before and len(ing.pending()) == pending_before and ing.offsets(0) == offs_before   # nothing applied
+    ing.set_dictionary_limits(1 << 31, sum(len(k) for k in keys_before) + 16)   # the byte bound
+    with pytest.raises(IngestError):
+        ing.record_batches(0, more)
+    ing.set_dictionary_limits(1 << 31, 1 << 32)
+    ing.record_batches(0, more)                                      # and with the real bounds the same fetch goes through
+    assert len(ing.pending()) > pending_before
+
+
 def test_pending_log_moves_to_a_caller_supplied_allocator(lib):
     """sgr_fold_ingested installs page-locked memory this way; here: counting wrappers around libc malloc/free."""
     libc = C.CDLL(None)
