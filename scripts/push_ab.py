@@ -23,7 +23,7 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device(dev))
     scale = float(sys.argv[1]) if len(sys.argv) > 1 else 1.0
-    variants = sys.argv[2].split(",") if len(sys.argv) > 2 else ["512:16:2:1:2:0", "1024:16:2:1:2:0", "256:16:2:1:2:0", "512:16:2:1:1:0", "512:16:2:1:2:1", "512:16:2:0:2:0", "512:16:2:0:2:1", "512:16:3:1:2:0", "512:16:3:0:2:0"]
+    variants = sys.argv[2].split(",") if len(sys.argv) > 2 else ["512:16:2:1:2:0", "1024:16:2:1:2:0", "256:16:2:1:2:0", "256:16:2:1:1:0", "512:16:2:0:2:0", "512:16:3:1:2:0", "256:16:3:1:2:0", "512:16:3:0:2:0"]
     n_global = int(10_000_000 * scale) // 64 * 64
     rec = S.routed_log_device(rank, world, n_global, 100, 3, dev)
     flat = rec.view(torch.uint8).view(-1)

@@ -257,18 +257,34 @@ __global__ void __launch_bounds__(kPushThreads) route_push_kernel(const __grid_c
   }
 }
 
-// The same partition WITHOUT staging the records in shared memory: positions first (headers -> owner -> stable rank ->
-// look-back), then every record is copied global -> global, 4 lanes x 16 bytes per record (coalesced 512-byte reads; 64-byte
-// writes at the record's position in its owner's region). Nine bytes of shared memory per record instead of 71, so eight CTAs
-// fit on an SM and tiles in their latency-bound phases (route lookup, look-back) overlap with tiles that are copying. This is
-// the kernel of the PULL mode, where every region is in this rank's own HBM (64-byte writes are full DRAM bursts there);
-// contiguous per-owner runs only matter for stores that cross NVLink.
+// The same partition WITHOUT staging the records in shared memory: every thread keeps ITS records in registers.
+//   load    2 x LDG.256 per record, all issued up front (each 32-byte sector requested exactly once)
+//   place   owner | local index from the record's aggregate index, stable rank by ballots, per-owner counts, look-back
+//   store   2 x STG.256 per record at its position in the owner's region (agg rewritten to the owner's local index)
+// One read of every byte, one write, 3 barriers, a few hundred bytes of shared memory: eight CTAs per SM, and the DRAM latency
+// of the records overlaps the latency chain of the placement (route lookup -> counts -> look-back). Consecutive records of one
+// owner land on consecutive positions, so L2 merges the 64-byte writes into full lines. This is the kernel of the PULL mode,
+// where every region is in this rank's own HBM; contiguous per-owner runs (route_push_kernel) only pay for stores over NVLink.
+__device__ __forceinline__ void ldg256(const void* p, uint4& a, uint4& b) {
+  asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(p));
+}
+__device__ __forceinline__ void stg256(void* p, const uint4& a, const uint4& b) {
+  asm volatile("st.global.v8.u32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y),
+               "r"(b.z), "r"(b.w) : "memory");
+}
+__device__ __forceinline__ uint32_t word_of(const uint4& a, const uint4& b, const uint4& c, const uint4& d, uint32_t w) {
+  // value selects only: taking a reference to one of the four would push the records to local memory
+  const uint32_t x = (w & 8u) ? ((w & 4u) ? d.x : c.x) : ((w & 4u) ? b.x : a.x);
+  const uint32_t y = (w & 8u) ? ((w & 4u) ? d.y : c.y) : ((w & 4u) ? b.y : a.y);
+  const uint32_t z = (w & 8u) ? ((w & 4u) ? d.z : c.z) : ((w & 4u) ? b.z : a.z);
+  const uint32_t v = (w & 8u) ? ((w & 4u) ? d.w : c.w) : ((w & 4u) ? b.w : a.w);
+  return (w & 2u) ? ((w & 1u) ? v : z) : ((w & 1u) ? y : x);
+}
+
 template <int ROUNDS>
 __global__ void __launch_bounds__(kPushThreads) route_part_kernel(const __grid_constant__ PushArgs a) {
   constexpr int RECS = ROUNDS * kPushThreads;
-  __shared__ uint32_t dpos[RECS];                 // position inside the owner's region, by record
-  __shared__ uint32_t loc[RECS];                  // owner's local aggregate index, by record
-  __shared__ uint8_t own[RECS];                   // owner (0xff: dropped), by record
   __shared__ uint32_t wcnt[ROUNDS][kPushWarps][kMaxRanks];
   __shared__ uint32_t excl[kMaxRanks], cnt[kMaxRanks];
   __shared__ uint32_t s_bid, s_ok;
@@ -280,19 +296,27 @@ __global__ void __launch_bounds__(kPushThreads) route_part_kernel(const __grid_c
   const uint32_t base = bid * RECS;
   const uint32_t nrec = a.n - base < (uint32_t)RECS ? a.n - base : (uint32_t)RECS;
   const uint8_t* src = a.rec + (uint64_t)base * 64;
-  unsigned long long g[ROUNDS];
+  const bool full = a.out_bytes == 64u;
+  bool second = full;   // the second half of the record is needed for a full copy, or when the projection reaches into it
+  for (uint32_t k = 0; k < a.n_proj; ++k) second |= a.proj_word[k] >= 8u;
+  uint4 d0[ROUNDS], d1[ROUNDS], d2[ROUNDS], d3[ROUNDS];
 #pragma unroll
   for (int j = 0; j < ROUNDS; ++j) {
     const uint32_t r = j * kPushThreads + t;
-    g[j] = r < nrec ? *reinterpret_cast<const unsigned long long*>(src + (size_t)r * 64 + 8) : ~0ull;
-  }
-  uint32_t o[ROUNDS], rk[ROUNDS];
-#pragma unroll
-  for (int j = 0; j < ROUNDS; ++j) {
-    const uint32_t r = j * kPushThreads + t;
-    o[j] = 0xffu; rk[j] = 0;
+    d0[j] = d1[j] = d2[j] = d3[j] = make_uint4(0, 0, 0, 0);
     if (r < nrec) {
-      if (g[j] < a.n_global) { const uint32_t ro = __ldg(a.route_of + g[j]); o[j] = ro >> 28; loc[r] = ro & 0x0fffffffu; }
+      ldg256(src + (size_t)r * 64, d0[j], d1[j]);
+      if (second) ldg256(src + (size_t)r * 64 + 32, d2[j], d3[j]);
+    }
+  }
+  uint32_t o[ROUNDS], rk[ROUNDS], loc[ROUNDS];
+#pragma unroll
+  for (int j = 0; j < ROUNDS; ++j) {
+    const uint32_t r = j * kPushThreads + t;
+    o[j] = 0xffu; rk[j] = 0; loc[j] = 0;
+    if (r < nrec) {
+      const unsigned long long g = ((unsigned long long)d0[j].w << 32) | d0[j].z;
+      if (g < a.n_global) { const uint32_t ro = __ldg(a.route_of + g); o[j] = ro >> 28; loc[j] = ro & 0x0fffffffu; }
       else atomicAdd(a.status + 0, 1ull);
     }
   }
@@ -330,41 +354,21 @@ __global__ void __launch_bounds__(kPushThreads) route_part_kernel(const __grid_c
   const uint32_t ok = s_ok;
 #pragma unroll
   for (int j = 0; j < ROUNDS; ++j) {
-    const uint32_t r = j * kPushThreads + t;
-    const bool keep = o[j] != 0xffu && ((ok >> o[j]) & 1u);
-    own[r] = keep ? (uint8_t)o[j] : (uint8_t)0xff;
-    if (keep) dpos[r] = excl[o[j]] + wcnt[j][warp][o[j]] + rk[j];
-  }
-  __syncthreads();
-  if (a.out_bytes == 64u) {
-#pragma unroll 4
-    for (int it = 0; it < 4 * ROUNDS; ++it) {
-      const uint32_t q = it * kPushThreads + t;
-      const uint32_t r = q >> 2, k = q & 3u;
-      if (r < nrec) {
-        const uint32_t ow = own[r];
-        if (ow != 0xffu) {
-          uint4 v = __ldg(reinterpret_cast<const uint4*>(src + (size_t)r * 64) + k);
-          if (k == 0) { v.z = loc[r]; v.w = 0u; }   // agg := the owner's LOCAL aggregate index
-          *reinterpret_cast<uint4*>(a.dst[ow] + (size_t)dpos[r] * 64 + k * 16) = v;
-        }
-      }
-    }
-  } else {
-    const uint32_t ow4 = a.out_bytes >> 2;
+    if (o[j] == 0xffu || !((ok >> o[j]) & 1u)) continue;
+    const uint32_t pos = excl[o[j]] + wcnt[j][warp][o[j]] + rk[j];
+    if (full) {
+      uint8_t* dp = a.dst[o[j]] + (size_t)pos * 64;
+      d0[j].z = loc[j]; d0[j].w = 0u;               // agg := the owner's LOCAL aggregate index
+      stg256(dp, d0[j], d1[j]);
+      stg256(dp + 32, d2[j], d3[j]);
+    } else {
+      uint32_t out[8];
+      out[0] = loc[j];
 #pragma unroll
-    for (int j = 0; j < ROUNDS; ++j) {
-      const uint32_t r = j * kPushThreads + t;
-      if (r < nrec && own[r] != 0xffu) {
-        const uint32_t* rw = reinterpret_cast<const uint32_t*>(src + (size_t)r * 64);
-        uint32_t out[8];
-        out[0] = loc[r];
-#pragma unroll
-        for (uint32_t k = 0; k < 7; ++k) out[1 + k] = k < a.n_proj ? __ldg(rw + a.proj_word[k]) : 0u;
-        uint8_t* dp = a.dst[own[r]] + (size_t)dpos[r] * a.out_bytes;
-        *reinterpret_cast<uint4*>(dp) = make_uint4(out[0], out[1], out[2], out[3]);
-        if (ow4 > 4) *reinterpret_cast<uint4*>(dp + 16) = make_uint4(out[4], out[5], out[6], out[7]);
-      }
+      for (uint32_t k = 0; k < 7; ++k) out[1 + k] = k < a.n_proj ? word_of(d0[j], d1[j], d2[j], d3[j], a.proj_word[k]) : 0u;
+      uint8_t* dp = a.dst[o[j]] + (size_t)pos * a.out_bytes;
+      if (a.out_bytes == 16u) *reinterpret_cast<uint4*>(dp) = make_uint4(out[0], out[1], out[2], out[3]);
+      else stg256(dp, make_uint4(out[0], out[1], out[2], out[3]), make_uint4(out[4], out[5], out[6], out[7]));
     }
   }
 }
