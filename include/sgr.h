@@ -53,6 +53,7 @@ extern "C" {
                                       COMMON/kafka/streams/SurgeAggregateStore.scala:31-46) */
 #define SGR_ERR_DIST          -9   /* NCCL / peer-memory failure */
 #define SGR_ERR_CAPACITY     -10   /* caller buffer too small */
+#define SGR_ERR_AGAIN        -11   /* loopback ranks only: repeat the call on every rank with option "push_ordered" = 1 */
 
 /* ------------------------------------------------------------------ packed formats
  *
@@ -303,6 +304,13 @@ int32_t sgr_dist_ipc_import(sgr_engine* e, const void* handles64_by_rank);
  *               other programs silently take fused == 1. Receive regions have a fixed capacity of
  *               recv_capacity / (nranks * push_chunks) records per (source, chunk): a region that would overflow fails the call
  *               with SGR_ERR_CAPACITY on EVERY rank (nothing is written out of bounds); retry with fused <= 1 or more capacity.
+ *               Option "push_pull" (default 1): the source partitions into ITS OWN buffer and the owner's fold reads those
+ *               regions over NVLink (remote loads: only the 32-byte sectors the fold touches cross the link); 0: the source
+ *               writes into the owner's buffer (remote stores). By default a CTA takes its place inside a region with one
+ *               atomicAdd per owner and every record carries its index within the chunk, which is the only order the
+ *               sort-free fold needs; when any rank meets a throwing aggregate (the exact replay wants positional log order)
+ *               every rank repeats the exchange in ordered mode (decoupled look-back) — automatically on real ranks, by
+ *               SGR_ERR_AGAIN + option "push_ordered" on loopback ranks.
  *   fused == 3  as 2, but only the record words the fold program reads cross NVLink (u32 local index + slot words:
  *               16 bytes per record for the Counter model). */
 int32_t sgr_dist_route_and_fold(sgr_engine* e, const void* d_records, uint64_t n_records, int32_t fused);

@@ -109,12 +109,13 @@ __device__ __forceinline__ void load_rec(RecView& r, const uint8_t* p, bool live
 }
 
 template <bool COMPACT, bool HINTS>
-__device__ __forceinline__ void apply_rec(const RecView& r, uint32_t idx1, const BulkArgs& a, const RowProgram& pg,
+__device__ __forceinline__ void apply_rec(const RecView& r, uint32_t idx1, uint32_t ib, const BulkArgs& a, const RowProgram& pg,
                                           const uint32_t* tab, uint64_t pol_last) {
   if (!r.live) return;
   unsigned long long slot;
   uint32_t type;
-  if (COMPACT) { slot = r.q0.x; type = r.q0.y; }
+  if (COMPACT) { slot = r.q0.x; type = r.q0.y >> 27; idx1 = ib + (r.q0.y & 0x07ffffffu); }
+  else if (a.src.carried) { slot = r.q0.z; type = r.q0.x; idx1 = ib + r.q0.w; }
   else { slot = ((unsigned long long)r.q0.w << 32) | r.q0.z; type = r.q0.x; }
   if (slot >= a.n_slots) { atomicAdd(a.counters + 4, 1ull); return; }
   uint8_t* entry = a.scr + (slot << a.lay.entry_shift);
@@ -185,7 +186,7 @@ __global__ void __launch_bounds__(kThreads) bulk_accumulate_kernel(const __grid_
       load_rec<HINTS>(r[u], base + i * stride, i < n, two, pol_first);
     }
 #pragma unroll
-    for (int u = 0; u < kUnroll; ++u) apply_rec<COMPACT, HINTS>(r[u], ib + (uint32_t)(i0 + (uint64_t)u * kThreads), a, pg, tab, pol_last);
+    for (int u = 0; u < kUnroll; ++u) apply_rec<COMPACT, HINTS>(r[u], ib + (uint32_t)(i0 + (uint64_t)u * kThreads), ib, a, pg, tab, pol_last);
   }
 }
 

@@ -42,7 +42,10 @@ struct BulkSrc {
   uint32_t blocks_per_sm;         // 0: the tuning default; else the grid cap of this launch (a fold that reads peers over NVLink
                                   // must leave the SMs to the partition kernel running beside it)
   uint32_t rotate;                // region the first tile starts with (the reader's rank: staggers the peers)
-  uint32_t compact;               // 0: 64-byte records (agg u64 at +8); 1: projected records (u32 local agg, then the slot words)
+  uint32_t carried;               // routed records: the arrival index is idx_base + the index the record carries (full records:
+                                  // upper half of the agg field; projected: low 27 bits of word 1), not its position
+  uint32_t compact;               // 0: 64-byte records (agg u64 at +8); 1: projected records: u32 local agg, type << 27 | index,
+                                  //    then the slot words 1..
   uint32_t rec_bytes;             // record stride
 };
 

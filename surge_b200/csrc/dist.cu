@@ -341,6 +341,7 @@ int dist_set_partitions(DistState* d, const uint32_t* partition_of_agg, uint64_t
 
 uint64_t dist_n_local(const DistState* d) { return d->n_local; }
 int dist_nranks(const DistState* d) { return d->nranks; }
+bool dist_is_loopback(const DistState* d) { return d->loopback; }
 void dist_clear_stats(DistState* d, uint64_t n_records) { d->stats = DistStats{}; d->stats.n_sent = n_records; d->stats.n_recv = n_records; }
 const uint32_t* dist_global_of_local(const DistState* d) { return (const uint32_t*)d->global_of_local.p; }
 const DistStats* dist_stats(const DistState* d) { return &d->stats; }

@@ -28,6 +28,7 @@ int dist_route(DistState* d, const uint8_t* d_records, uint64_t n, bool fused, u
                uint64_t* n_recv_out, std::string* err);
 uint64_t dist_n_local(const DistState* d);
 int dist_nranks(const DistState* d);
+bool dist_is_loopback(const DistState* d);
 void dist_clear_stats(DistState* d, uint64_t n_records);
 const uint32_t* dist_global_of_local(const DistState* d);
 const DistStats* dist_stats(const DistState* d);

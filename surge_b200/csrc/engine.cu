@@ -113,6 +113,7 @@ struct sgr_engine {
   DevBuf bulk_scratch, bulk_err_ids, bulk_counters, hash_out;
   uint64_t bulk_scratch_slots = 0;
   int64_t opt_bulk = 1;           // 0: keep arrival-order logs on the single-launch micro-batch kernel (incremental.cu)
+  int64_t opt_push_ordered = 0;   // 1: positions inside the exchange regions follow the log from the first attempt (look-back)
   int64_t opt_push_chunks = 16;   // chunks of the pipelined route + exchange + fold (route_push.cu); the same on every rank
 
   sgr_stats stats{};
@@ -1169,9 +1170,23 @@ int32_t sgr_dist_route_and_fold(sgr_engine* e, const void* d_records, uint64_t n
     pf.prog = &e->row_prog; pf.lay = &e->bulk_lay; pf.scratch = e->bulk_scratch.p; pf.states = (uint8_t*)e->states.p;
     pf.err_ids = (uint32_t*)e->bulk_err_ids.p; pf.counters = (unsigned long long*)e->bulk_counters.p; pf.n_slots = n_local;
     pf.n_chunks = (uint32_t)e->opt_push_chunks; pf.compact = fused == 3; pf.num_sms = e->num_sms;
+    // First attempt: CTAs place their records with atomics and the records carry their own arrival index — nothing waits for
+    // anything. The exact replay of a throwing aggregate needs the records in POSITIONAL log order, so if any rank saw one,
+    // every rank runs the exchange again in ordered mode (look-back) and replays from that. Throwing events are the exception.
+    pf.ordered = e->opt_push_ordered != 0;
     PushFoldResult res;
     int r = dist_push_fold(e->dist, (const uint8_t*)d_records, n_records, pf, e->stream, &res, &err);
     if (r) { e->states_valid = false; e->bulk_scratch_slots = 0; return fail(e, r, "%s", err.c_str()); }
+    if (!pf.ordered && res.any_err_slots) {
+      if (dist_is_loopback(e->dist)) {   // loopback ranks have no collective to agree over: the caller does (sgr.h)
+        e->states_valid = false;
+        return fail(e, SGR_ERR_AGAIN, "throwing aggregates: every rank must repeat the call with option push_ordered = 1");
+      }
+      CUDA_TRY(e, cudaMemsetAsync(e->states.p, 0, (size_t)n_local * e->program.state_bytes, e->stream));
+      pf.ordered = true;
+      r = dist_push_fold(e->dist, (const uint8_t*)d_records, n_records, pf, e->stream, &res, &err);
+      if (r) { e->states_valid = false; e->bulk_scratch_slots = 0; return fail(e, r, "%s", err.c_str()); }
+    }
     unsigned long long throwing = 0, dropped = 0;
     if (res.n_err_slots) {
       const uint8_t* contiguous = nullptr;
@@ -1299,6 +1314,7 @@ int32_t sgr_set_option(sgr_engine* e, const char* name, int64_t value) {
     push_tuning().tile = (int)value; return SGR_OK;
   }
   if (!strcmp(name, "push_fold_blocks_per_sm")) { push_tuning().fold_blocks_per_sm = (int)value; return SGR_OK; }
+  if (!strcmp(name, "push_ordered")) { e->opt_push_ordered = value ? 1 : 0; return SGR_OK; }
   if (!strcmp(name, "push_staged")) { push_tuning().staged = (int)value; return SGR_OK; }
   if (!strcmp(name, "push_pull")) { push_tuning().pull = value ? 1 : 0; return SGR_OK; }
   if (!strcmp(name, "push_chunks")) {

@@ -59,7 +59,14 @@ struct PushArgs {
                                  // [2] spin time-outs [3] error flags received
   uint32_t n_proj;               // compact: number of projected record words
   uint32_t proj_word[7];
+  uint32_t ordered;              // 1: CTAs take their place inside the regions in log order (look-back): position == arrival order.
+                                 // 0: a CTA takes its place with one atomicAdd per owner; the order travels INSIDE the records
+                                 //    (record index within the chunk), which is all the sort-free fold needs
 };
+
+// Every routed record carries its index within the source's chunk: full records in the (now free) upper half of the agg field,
+// projected records next to the event type: word 1 = min(type, 16) << 27 | index (chunks hold fewer than 2^27 records).
+constexpr uint32_t kIdxBits = 27;
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
   const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
@@ -229,7 +236,7 @@ __global__ void __launch_bounds__(kPushThreads) route_push_kernel(const __grid_c
         const uint32_t r = perm[p], ow = own_s[p];
         if ((ok >> ow) & 1u) {
           uint4 v = *reinterpret_cast<const uint4*>(srec + (size_t)r * 64 + k * 16);
-          if (k == 0) { v.z = loc[r]; v.w = 0u; }   // agg := the owner's LOCAL aggregate index
+          if (k == 0) { v.z = loc[r]; v.w = base + r; }   // agg := the owner's LOCAL aggregate index | index within the chunk
           st_na_v4(a.dst[ow] + (size_t)(excl[ow] + p - start[ow]) * 64 + k * 16, v);
         }
       }
@@ -246,8 +253,9 @@ __global__ void __launch_bounds__(kPushThreads) route_push_kernel(const __grid_c
           const uint32_t* rw = reinterpret_cast<const uint32_t*>(srec + (size_t)r * 64);
           uint32_t out[8];
           out[0] = loc[r];
+          { const uint32_t ty = rw[a.proj_word[0]]; out[1] = ((ty < 16u ? ty : 16u) << kIdxBits) | (base + r); }
 #pragma unroll
-          for (uint32_t k = 0; k < 7; ++k) out[1 + k] = k < a.n_proj ? rw[a.proj_word[k]] : 0u;
+          for (uint32_t k = 1; k < 7; ++k) out[1 + k] = k < a.n_proj ? rw[a.proj_word[k]] : 0u;
           uint8_t* dp = a.dst[ow] + (size_t)(excl[ow] + p - start[ow]) * a.out_bytes;
           st_na_v4(dp, make_uint4(out[0], out[1], out[2], out[3]));
           if (ow4 > 4) st_na_v4(dp + 16, make_uint4(out[4], out[5], out[6], out[7]));
@@ -290,9 +298,13 @@ __global__ void __launch_bounds__(kPushThreads) route_part_kernel(const __grid_c
   __shared__ uint32_t s_bid, s_ok;
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const uint32_t R = a.nranks;
-  if (t == 0) { s_bid = atomicAdd(a.ticket, 1u); s_ok = 0xffffffffu; }
-  __syncthreads();
-  const uint32_t bid = s_bid;
+  uint32_t bid = blockIdx.x;
+  if (t == 0) s_ok = 0xffffffffu;
+  if (a.ordered) {   // the look-back needs every earlier tile to be running already: tiles are taken in ticket order
+    if (t == 0) s_bid = atomicAdd(a.ticket, 1u);
+    __syncthreads();
+    bid = s_bid;
+  }
   const uint32_t base = bid * RECS;
   const uint32_t nrec = a.n - base < (uint32_t)RECS ? a.n - base : (uint32_t)RECS;
   const uint8_t* src = a.rec + (uint64_t)base * 64;
@@ -338,17 +350,25 @@ __global__ void __launch_bounds__(kPushThreads) route_part_kernel(const __grid_c
     cnt[t] = run;
   }
   __syncthreads();
-  for (uint32_t rr = warp; rr < R; rr += kPushWarps) {
-    const uint32_t local = cnt[rr];
-    const uint32_t ex = look_back(a.lb + (size_t)rr * a.n_ctas, bid, local, lane, a.status);
-    if (lane == 0) {
-      excl[rr] = ex;
-      if ((unsigned long long)ex + local > a.cap_region) {   // would overflow the region: nothing of this CTA goes to that owner
-        atomicAnd(&s_ok, ~(1u << rr));
-        atomicAdd(a.status + 1, (unsigned long long)local);
+  if (a.ordered) {
+    for (uint32_t rr = warp; rr < R; rr += kPushWarps) {
+      const uint32_t local = cnt[rr];
+      const uint32_t ex = look_back(a.lb + (size_t)rr * a.n_ctas, bid, local, lane, a.status);
+      if (lane == 0) {
+        excl[rr] = ex;
+        if ((unsigned long long)ex + local > a.cap_region) {   // would overflow the region: nothing of this CTA goes to that owner
+          atomicAnd(&s_ok, ~(1u << rr));
+          atomicAdd(a.status + 1, (unsigned long long)local);
+        }
+        if (base + nrec >= a.n) a.totals[rr] = ex + local;     // the chunk's last CTA: its inclusive prefix is the chunk total
       }
-      if (base + nrec >= a.n) a.totals[rr] = ex + local;     // the chunk's last CTA: its inclusive prefix is the chunk total
     }
+  } else if (t < (int)R) {
+    // no CTA waits for another: the chunk totals double as allocation cursors (they end up as the totals the flag kernel sends)
+    const uint32_t local = cnt[t];
+    const uint32_t ex = local ? atomicAdd(a.totals + t, local) : 0u;
+    excl[t] = ex;
+    if ((unsigned long long)ex + local > a.cap_region) { atomicAnd(&s_ok, ~(1u << t)); atomicAdd(a.status + 1, (unsigned long long)local); }
   }
   __syncthreads();
   const uint32_t ok = s_ok;
@@ -358,14 +378,15 @@ __global__ void __launch_bounds__(kPushThreads) route_part_kernel(const __grid_c
     const uint32_t pos = excl[o[j]] + wcnt[j][warp][o[j]] + rk[j];
     if (full) {
       uint8_t* dp = a.dst[o[j]] + (size_t)pos * 64;
-      d0[j].z = loc[j]; d0[j].w = 0u;               // agg := the owner's LOCAL aggregate index
+      d0[j].z = loc[j]; d0[j].w = base + j * kPushThreads + t;   // agg := the owner's LOCAL aggregate index | index within the chunk
       stg256(dp, d0[j], d1[j]);
       stg256(dp + 32, d2[j], d3[j]);
     } else {
       uint32_t out[8];
       out[0] = loc[j];
+      { const uint32_t ty = word_of(d0[j], d1[j], d2[j], d3[j], a.proj_word[0]); out[1] = ((ty < 16u ? ty : 16u) << kIdxBits) | (base + j * kPushThreads + t); }
 #pragma unroll
-      for (uint32_t k = 0; k < 7; ++k) out[1 + k] = k < a.n_proj ? word_of(d0[j], d1[j], d2[j], d3[j], a.proj_word[k]) : 0u;
+      for (uint32_t k = 1; k < 7; ++k) out[1 + k] = k < a.n_proj ? word_of(d0[j], d1[j], d2[j], d3[j], a.proj_word[k]) : 0u;
       uint8_t* dp = a.dst[o[j]] + (size_t)pos * a.out_bytes;
       if (a.out_bytes == 16u) *reinterpret_cast<uint4*>(dp) = make_uint4(out[0], out[1], out[2], out[3]);
       else stg256(dp, make_uint4(out[0], out[1], out[2], out[3]), make_uint4(out[4], out[5], out[6], out[7]));
@@ -416,6 +437,7 @@ __global__ void gather_region_kernel(const uint8_t* __restrict__ src, uint32_t n
   if (in_bytes == 64u) {
     const uint4* s4 = reinterpret_cast<const uint4*>(src + i * 64);
     for (int k = 0; k < 4; ++k) d4[k] = s4[k];
+    reinterpret_cast<uint32_t*>(d4)[3] = 0u;   // the upper half of the agg field carried the index within the chunk
     return;
   }
   uint32_t w[16];
@@ -423,7 +445,8 @@ __global__ void gather_region_kernel(const uint8_t* __restrict__ src, uint32_t n
   const uint32_t* s = reinterpret_cast<const uint32_t*>(src + i * in_bytes);
   for (uint32_t k = 0; k < n_proj; ++k) {
     const uint32_t pw = proj_word[k];
-    for (int q = 0; q < 16; ++q) if ((uint32_t)q == pw) w[q] = s[1 + k];
+    const uint32_t val = k == 0 ? s[1] >> kIdxBits : s[1 + k];   // word 1 = type << 27 | index within the chunk
+    for (int q = 0; q < 16; ++q) if ((uint32_t)q == pw) w[q] = val;
   }
   w[2] = s[0]; w[3] = 0;
   for (int k = 0; k < 4; ++k) d4[k] = make_uint4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
@@ -447,7 +470,7 @@ int dist_push_reserve(DistState* d, uint64_t n, uint32_t n_chunks, std::string* 
   const uint64_t chunk_recs = chunk_records(n, n_chunks);
   const uint64_t ctas_per_chunk = chunk_recs / 256;   // sized for the smallest tile
   cudaError_t ce;
-  if (!d->h_pinned && (ce = cudaHostAlloc(&d->h_pinned, 128 + (size_t)kMaxRanks * kMaxChunks * 8 + 128, cudaHostAllocDefault)) != cudaSuccess) {
+  if (!d->h_pinned && (ce = cudaHostAlloc(&d->h_pinned, 128 + (size_t)kMaxRanks * kMaxChunks * 8 + 256, cudaHostAllocDefault)) != cudaSuccess) {
     *err = std::string("page-locked read-back buffer: ") + cudaGetErrorString(ce);
     return SGR_ERR_OOM;
   }
@@ -476,11 +499,11 @@ int dist_push_fold(DistState* d, const uint8_t* d_records, uint64_t n, const Pus
   if (C < 1 || C > (uint32_t)kMaxChunks) { *err = "push_chunks out of range"; return SGR_ERR_INVALID; }
   const uint64_t cap_region = d->recv_capacity / ((uint64_t)R * C);
   if (!cap_region) { *err = "receive buffer too small for R x chunks regions"; return SGR_ERR_CAPACITY; }
-  if ((uint64_t)C * cap_region >= (1ull << 30)) { *err = "push path: chunks x region capacity must stay below 2^30 records"; return SGR_ERR_UNSUPPORTED; }
+  if (n >= (1ull << 30)) { *err = "push path: at most 2^30 records per rank per call"; return SGR_ERR_UNSUPPORTED; }
   // chunk size: whole CTAs, the same number of chunks on every rank (the flags are indexed by chunk)
   const uint64_t chunk_recs = chunk_records(n, C);
   const int tile = tile_recs();
-  if (chunk_recs >= (1ull << 31)) { *err = "push path: chunk too large, raise push_chunks"; return SGR_ERR_UNSUPPORTED; }
+  if (chunk_recs >= (1ull << kIdxBits)) { *err = "push path: chunk too large (2^27 records), raise push_chunks"; return SGR_ERR_UNSUPPORTED; }
   const uint32_t out_bytes = pf.compact ? ((1 + pf.prog->n_slots) * 4 <= 16 ? 16u : 32u) : 64u;
   if (pf.compact && pf.prog->n_slots > 7) { *err = "compact exchange: program reads more than 7 record words"; return SGR_ERR_UNSUPPORTED; }
   const uint64_t ctas_per_chunk = chunk_recs / tile;
@@ -515,9 +538,11 @@ int dist_push_fold(DistState* d, const uint8_t* d_records, uint64_t n, const Pus
       a.cap_region = (uint32_t)cap_region; a.out_bytes = out_bytes;
       a.lb = (unsigned long long*)d->lb.p + (size_t)c * ctas_per_chunk * kMaxRanks; a.n_ctas = (uint32_t)ctas_per_chunk;
       a.ticket = tickets + c; a.totals = totals + (size_t)c * kMaxRanks; a.status = status;
+      a.ordered = pf.ordered ? 1u : 0u;
       if (pf.compact) { a.n_proj = pf.prog->n_slots; for (uint32_t k = 0; k < a.n_proj; ++k) a.proj_word[k] = pf.prog->slot_word[k]; }
       const uint32_t grid = (uint32_t)((cn + tile - 1) / tile);
-      const bool staged = push_tuning().staged >= 0 ? push_tuning().staged != 0 : !pull;   // contiguous runs only pay across NVLink
+      // contiguous per-owner runs only pay across NVLink; the staged kernel is always ordered
+      const bool staged = pf.ordered && (push_tuning().staged >= 0 ? push_tuning().staged != 0 : !pull);
       if (staged) {
         if (tile == 256) route_push_kernel<1><<<grid, kPushThreads, push_smem_bytes<1>(), s0>>>(a);
         else if (tile == 512) route_push_kernel<2><<<grid, kPushThreads, push_smem_bytes<2>(), s0>>>(a);
@@ -535,7 +560,7 @@ int dist_push_fold(DistState* d, const uint8_t* d_records, uint64_t n, const Pus
     // ---- receiver side of chunk c
     push_wait_kernel<<<1, 32, 0, s1>>>(my_flags, c, (uint32_t)R, epoch, status);
     BulkSrc bs{};
-    bs.n_regions = (uint32_t)R; bs.compact = pf.compact ? 1u : 0u; bs.rec_bytes = out_bytes; bs.rotate = (uint32_t)d->rank;
+    bs.n_regions = (uint32_t)R; bs.compact = pf.compact ? 1u : 0u; bs.rec_bytes = out_bytes; bs.rotate = (uint32_t)d->rank; bs.carried = 1;
     bs.blocks_per_sm = (uint32_t)push_tuning().fold_blocks_per_sm;
     for (int s = 0; s < R; ++s) {
       // pull: source s keeps what it has for me in ITS buffer, region (me, chunk): the fold reads it over NVLink
@@ -543,7 +568,7 @@ int dist_push_fold(DistState* d, const uint8_t* d_records, uint64_t n, const Pus
                         : d->peer_recv[d->rank] + ((uint64_t)s * C + c) * cap_region * out_bytes;
       bs.count_flag[s] = my_flags + (size_t)s * kMaxChunks + c;
       bs.count[s] = cap_region;
-      bs.idx_base[s] = (uint32_t)((uint64_t)c * cap_region);
+      bs.idx_base[s] = (uint32_t)((uint64_t)c * chunk_recs);   // + the index the record carries: monotone along every aggregate's log
     }
     DTRY(launch_bulk_accumulate(bs, pf.n_slots, pf.scratch, *pf.prog, *pf.lay, pf.counters, pf.num_sms, s1));
   }
@@ -583,16 +608,21 @@ int dist_push_fold(DistState* d, const uint8_t* d_records, uint64_t n, const Pus
   else if (h_status[1]) { *err = std::to_string(h_status[1]) + " records did not fit their receive region (capacity " + std::to_string(cap_region) + " records per source and chunk)"; my_err = SGR_ERR_CAPACITY; }
   else if (remote_err || h_status[3]) { *err = "a source rank reported a full receive region"; my_err = SGR_ERR_CAPACITY; }
   else if (h_cnt[4]) { *err = std::to_string(h_cnt[4]) + " arrived records carry a local index out of range"; my_err = SGR_ERR_INVALID; }
-  // every rank fails or nobody does: gather the verdicts (the fold of a failed call is discarded by the caller)
+  // every rank fails or nobody does: gather the verdicts (the fold of a failed call is discarded by the caller), and whether
+  // ANY rank saw a throwing slot (then every rank repeats the call in ordered mode, see engine.cu)
+  out->any_err_slots = h_cnt[3] != 0;
   if (R > 1 && !d->loopback) {
     uint32_t* all = (uint32_t*)((uint8_t*)d->h_pinned + 128 + (size_t)kMaxRanks * kMaxChunks * 8);
-    uint32_t* mine = all + kMaxRanks - 1 + 1;   // behind the gathered verdicts
-    *mine = my_err ? 1u : 0u;
-    DTRY(cudaMemcpyAsync((uint8_t*)d->push_ctl.p + off_proj, mine, 4, cudaMemcpyHostToDevice, s0));
-    NTRY(nccl_api().AllGather((uint8_t*)d->push_ctl.p + off_proj, d->counts_all.p, 1, ncclUint32, d->comm, s0));
-    DTRY(cudaMemcpyAsync(all, d->counts_all.p, (size_t)R * 4, cudaMemcpyDeviceToHost, s0));
+    uint32_t* mine = all + 2 * kMaxRanks;   // behind the gathered verdicts
+    mine[0] = my_err ? 1u : 0u; mine[1] = h_cnt[3] ? 1u : 0u;
+    DTRY(cudaMemcpyAsync((uint8_t*)d->push_ctl.p + off_proj, mine, 8, cudaMemcpyHostToDevice, s0));
+    NTRY(nccl_api().AllGather((uint8_t*)d->push_ctl.p + off_proj, d->counts_all.p, 2, ncclUint32, d->comm, s0));
+    DTRY(cudaMemcpyAsync(all, d->counts_all.p, (size_t)R * 8, cudaMemcpyDeviceToHost, s0));
     DTRY(cudaStreamSynchronize(s0));
-    if (!my_err) for (int q = 0; q < R; ++q) if (all[q]) { *err = "rank " + std::to_string(q) + " failed the exchange"; my_err = SGR_ERR_DIST; break; }
+    for (int q = 0; q < R; ++q) {
+      if (!my_err && all[2 * q]) { *err = "rank " + std::to_string(q) + " failed the exchange"; my_err = SGR_ERR_DIST; }
+      if (all[2 * q + 1]) out->any_err_slots = true;
+    }
   }
   out->n_recv = n_recv; out->n_err_slots = h_cnt[3]; out->ms_push = ms_push; out->ms_total = ms_total; out->out_bytes = out_bytes;
   d->stats = DistStats{};

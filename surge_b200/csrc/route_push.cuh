@@ -29,11 +29,13 @@ struct PushFoldArgs {
   uint64_t n_slots;
   uint32_t n_chunks;             // the same on every rank
   bool compact;                  // exchange only the record words the program reads
+  bool ordered;                  // positions inside the regions follow the log (needed by the exact replay of throwing slots)
   int num_sms;
 };
 struct PushRegion { const uint8_t* base; uint32_t count; };
 struct PushFoldResult {
   uint64_t n_recv = 0, n_err_slots = 0;
+  bool any_err_slots = false;        // some rank of the job saw a throwing slot
   float ms_push = 0, ms_total = 0;
   uint32_t out_bytes = 64;
   std::vector<PushRegion> regions;   // what arrived, in (source, chunk) order

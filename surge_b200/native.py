@@ -15,10 +15,11 @@ SGR_OK = 0
 ERR_NAMES = {
     -1: "SGR_ERR_INVALID", -2: "SGR_ERR_NO_DEVICE", -3: "SGR_ERR_CUDA", -4: "SGR_ERR_NO_PROGRAM",
     -5: "SGR_ERR_NOT_LOADED", -6: "SGR_ERR_UNSUPPORTED", -7: "SGR_ERR_OOM", -8: "SGR_ERR_STATE",
-    -9: "SGR_ERR_DIST", -10: "SGR_ERR_CAPACITY",
+    -9: "SGR_ERR_DIST", -10: "SGR_ERR_CAPACITY", -11: "SGR_ERR_AGAIN",
 }
 SGR_ERR_INVALID, SGR_ERR_NO_DEVICE, SGR_ERR_CUDA, SGR_ERR_NO_PROGRAM, SGR_ERR_NOT_LOADED = -1, -2, -3, -4, -5
 SGR_ERR_UNSUPPORTED, SGR_ERR_OOM, SGR_ERR_STATE, SGR_ERR_DIST, SGR_ERR_CAPACITY = -6, -7, -8, -9, -10
+SGR_ERR_AGAIN = -11
 
 REC_FIXED64, REC_VAR16 = 0, 1
 ST_EXISTS, ST_CHANGED, ST_ERROR = 1, 2, 4
