@@ -13,7 +13,9 @@ than the 126 MB L2, so no flush is needed between timed iterations).
   cpu_baseline   the CPU oracle (port of the reference's fold) on this box's host cores, NUMA-placed log, pinned threads
   routed  configs[2], the configuration north_star names for N GPUs: the FULL problem (10 M aggregates x 100 events = 64 GB,
           arrival order, pre-distributed by source partition) strong-scaled over the N ranks: hash-partition by aggregate, ONE
-          exchange over NVLink, fold — pipelined (surge_b200/csrc/route_push.cu). Every mode prints a 64-bit hash of the
+          exchange over NVLink, fold — pipelined (surge_b200/csrc/route_push.cu): `exchange_pipelined` moves whole 64-byte
+          records' sectors, `exchange_projected_16B` only the words the fold program reads, `nccl_all_to_all` is the
+          count + pack + grouped ncclSend/ncclRecv path for comparison. Every mode prints a 64-bit hash of the
           whole state table (sum over ranks; identical at N = 1, 2, 4, 8 by construction of the log), the same hash from an
           independent vectorised torch restatement of the Counter fold over the full table, and a 4096-aggregate sample
           checked against the CPU oracle.
@@ -277,7 +279,7 @@ def config2_routed(rank, world, local_rank, dev, barrier, note, scale: float, it
         cap = int(n * 1.12) + 64 * 1024 * world
         D.exchange_ids(eng, rank, world, cap, fused=True)
         eng.dist_set_partitions(part)
-        modes = [("push_pipelined", 2), ("push_projected_16B", 3), ("nccl_all_to_all", 0)]
+        modes = [("exchange_pipelined", 2), ("exchange_projected_16B", 3), ("nccl_all_to_all", 0)]
     else:
         modes = [("single_gpu_sort_free", None)]
     expected_hash = None
@@ -329,7 +331,7 @@ def config2_routed(rank, world, local_rank, dev, barrier, note, scale: float, it
         xfer_ms = best[2] if fused in (2, 3) else best[4]
         res[name] = {
             "events_per_s": total_events / best[0], "ms_wall": best[0] * 1e3, "ms_wall_all": [round(r[0] * 1e3, 3) for r in times],
-            "ms_device_pipeline": best[2] if fused in (2, 3) else None, "ms_push_issue": best[3] if fused in (2, 3) else None,
+            "ms_device_pipeline": best[2] if fused in (2, 3) else None, "ms_partition": best[3] if fused in (2, 3) else None,
             "ms_route_count": best[5] if fused == 0 else None, "ms_route_scatter": best[3] if fused == 0 else None, "ms_exchange": best[4] if fused == 0 else None,
             "ms_fold": best[1], "ms_group": best[6],
             "exchange_bytes_per_record": wire,

@@ -277,6 +277,18 @@ int grid_for(int num_sms, uint64_t work_items, int per_sm) {
 
 BulkTuning& bulk_tuning() { static BulkTuning t; return t; }
 
+cudaError_t bulk_preload_kernels() {
+  cudaFuncAttributes fa;
+  cudaError_t e;
+#define SGR_TOUCH(...) if ((e = cudaFuncGetAttributes(&fa, __VA_ARGS__)) != cudaSuccess) return e;
+#define SGR_TOUCH_U(C, H) SGR_TOUCH(bulk_accumulate_kernel<C, H, 1>) SGR_TOUCH(bulk_accumulate_kernel<C, H, 2>) SGR_TOUCH(bulk_accumulate_kernel<C, H, 4>)
+  SGR_TOUCH_U(true, true) SGR_TOUCH_U(true, false) SGR_TOUCH_U(false, true) SGR_TOUCH_U(false, false)
+  SGR_TOUCH(bulk_finish_kernel) SGR_TOUCH(states_hash_kernel)
+#undef SGR_TOUCH_U
+#undef SGR_TOUCH
+  return cudaSuccess;
+}
+
 bool bulk_layout_for(const RowProgram& prog, BulkLayout* out) {
   if (prog.user_words != 2 || prog.cls != 0 || prog.f64_mask || prog.slot_word[0] != 0) return false;
   uint32_t has_add = 0, has_set = 0, has_none = 0;
@@ -330,7 +342,17 @@ cudaError_t launch_bulk_accumulate(const BulkSrc& src, uint64_t n_slots, void* d
   if (!work) return cudaSuccess;
   const BulkTuning& t = bulk_tuning();
   const int unroll = t.unroll == 1 || t.unroll == 2 ? t.unroll : 4;
-  const int grid = grid_for(num_sms, (work + unroll - 1) / unroll, src.blocks_per_sm ? (int)src.blocks_per_sm : (t.blocks_per_sm > 0 ? t.blocks_per_sm : 8));
+  // blocks_per_sm == ~0: one tile per CTA (many short CTAs: a low-priority launch then yields to a concurrent high-priority kernel
+  // at CTA granularity instead of squatting on the SMs with a persistent grid)
+  int grid;
+  if (src.blocks_per_sm == 0xffffffffu) {
+    uint64_t mx = 0;
+    for (uint32_t r = 0; r < src.n_regions; ++r) mx = mx > src.count[r] ? mx : src.count[r];
+    const uint64_t tiles = (mx + (uint64_t)kThreads * unroll - 1) / ((uint64_t)kThreads * unroll) * src.n_regions;
+    grid = (int)(tiles < 0x7fffffffull ? (tiles ? tiles : 1) : 0x7fffffffull);
+  } else {
+    grid = grid_for(num_sms, (work + unroll - 1) / unroll, src.blocks_per_sm ? (int)src.blocks_per_sm : (t.blocks_per_sm > 0 ? t.blocks_per_sm : 8));
+  }
 #define SGR_BULK_LAUNCH(C, H, U) bulk_accumulate_kernel<C, H, U><<<grid, kThreads, 0, st>>>(a, prog)
 #define SGR_BULK_U(C, H) (unroll == 1 ? SGR_BULK_LAUNCH(C, H, 1) : unroll == 2 ? SGR_BULK_LAUNCH(C, H, 2) : SGR_BULK_LAUNCH(C, H, 4))
   if (src.compact) { if (t.hints) SGR_BULK_U(true, true); else SGR_BULK_U(true, false); }

@@ -25,6 +25,7 @@ struct BulkLayout {
 // measurement knobs (sgr_set_option "bulk_unroll" / "bulk_hints" / "bulk_blocks_per_sm"); the defaults are the measured best
 struct BulkTuning { int unroll = 4; int hints = 1; int blocks_per_sm = 8; };
 BulkTuning& bulk_tuning();
+cudaError_t bulk_preload_kernels();   // force the (lazy) load of every kernel of this file
 
 // false when the program is outside the sort-free formulation (a word both added and set, wide state, class 1, f64 fields)
 bool bulk_layout_for(const RowProgram& prog, BulkLayout* out);

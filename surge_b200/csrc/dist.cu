@@ -216,6 +216,7 @@ void dist_destroy(DistState* d) {
   d->send_buf.release(); d->recv_buf.release();
   d->route_of.release(); d->lb.release(); d->push_ctl.release(); d->gather_buf.release();
   if (d->stream2) cudaStreamDestroy(d->stream2);
+  if (d->stream_hi) cudaStreamDestroy(d->stream_hi);
   if (d->h_pinned) cudaFreeHost(d->h_pinned);
   for (auto& e : d->pev) if (e) cudaEventDestroy(e);
   for (auto& e : d->ev) if (e) cudaEventDestroy(e);
@@ -241,7 +242,8 @@ int dist_init(DistState* d, int rank, int nranks, const void* unique_id, uint64_
   if (!d->stream2) {
     int lo = 0, hi = 0;
     cudaDeviceGetStreamPriorityRange(&lo, &hi);
-    if (cudaStreamCreateWithPriority(&d->stream2, cudaStreamNonBlocking, hi) != cudaSuccess) { *err = "cudaStreamCreate"; return SGR_ERR_CUDA; }
+    if (cudaStreamCreateWithPriority(&d->stream2, cudaStreamNonBlocking, lo) != cudaSuccess ||
+        cudaStreamCreateWithPriority(&d->stream_hi, cudaStreamNonBlocking, hi) != cudaSuccess) { *err = "cudaStreamCreate"; return SGR_ERR_CUDA; }
   }
   if (nranks > 1 && !d->loopback) {
     if (!g_nccl.load(err)) return SGR_ERR_DIST;

@@ -49,7 +49,7 @@ struct DistState {
   // pipelined push path (route_push.cu)
   DevBuf route_of;                       // owner << 28 | local index, per global aggregate
   DevBuf lb, push_ctl, gather_buf;       // look-back cells; tickets + chunk totals + status; contiguous copy for the replay
-  cudaStream_t stream2 = nullptr;
+  cudaStream_t stream2 = nullptr, stream_hi = nullptr;   // fold (low priority) and partition (high priority) streams
   cudaEvent_t pev[4] = {};
   uint32_t epoch = 0;
   void* h_pinned = nullptr;              // page-locked landing area of the per-call read-backs

@@ -465,8 +465,22 @@ static uint64_t chunk_records(uint64_t n, uint32_t n_chunks) {
   return (c + 1023) / 1024 * 1024;
 }
 
+// CUDA loads a kernel lazily at its first launch, and that load can wait for the kernels already running on the device — such as
+// another loopback rank's spinning wait kernel, which in turn waits for THIS rank's flags. Touch every kernel of the path once.
+static cudaError_t preload_kernels() {
+  cudaFuncAttributes fa;
+  cudaError_t e;
+#define SGR_TOUCH(k) if ((e = cudaFuncGetAttributes(&fa, k)) != cudaSuccess) return e;
+  SGR_TOUCH(route_push_kernel<1>) SGR_TOUCH(route_push_kernel<2>) SGR_TOUCH(route_push_kernel<4>)
+  SGR_TOUCH(route_part_kernel<1>) SGR_TOUCH(route_part_kernel<2>) SGR_TOUCH(route_part_kernel<4>)
+  SGR_TOUCH(push_flag_kernel) SGR_TOUCH(push_wait_kernel) SGR_TOUCH(gather_region_kernel)
+#undef SGR_TOUCH
+  return bulk_preload_kernels();
+}
+
 int dist_push_reserve(DistState* d, uint64_t n, uint32_t n_chunks, std::string* err) {
   if (n_chunks < 1 || n_chunks > (uint32_t)kMaxChunks) { *err = "push_chunks out of range"; return SGR_ERR_INVALID; }
+  { cudaError_t pe = preload_kernels(); if (pe != cudaSuccess) { *err = std::string("kernel preload: ") + cudaGetErrorString(pe); return SGR_ERR_CUDA; } }
   const uint64_t chunk_recs = chunk_records(n, n_chunks);
   const uint64_t ctas_per_chunk = chunk_recs / 256;   // sized for the smallest tile
   cudaError_t ce;
@@ -503,7 +517,8 @@ int dist_push_fold(DistState* d, const uint8_t* d_records, uint64_t n, const Pus
   // chunk size: whole CTAs, the same number of chunks on every rank (the flags are indexed by chunk)
   const uint64_t chunk_recs = chunk_records(n, C);
   const int tile = tile_recs();
-  if (chunk_recs >= (1ull << kIdxBits)) { *err = "push path: chunk too large (2^27 records), raise push_chunks"; return SGR_ERR_UNSUPPORTED; }
+  const uint64_t idx_stride = ((1ull << 30) - 2) / C;   // the same on every rank: arrival index = chunk * idx_stride + index within the chunk < 2^30
+  if (chunk_recs >= (1ull << kIdxBits) || chunk_recs > idx_stride) { *err = "push path: chunk too large, raise push_chunks"; return SGR_ERR_UNSUPPORTED; }
   const uint32_t out_bytes = pf.compact ? ((1 + pf.prog->n_slots) * 4 <= 16 ? 16u : 32u) : 64u;
   if (pf.compact && pf.prog->n_slots > 7) { *err = "compact exchange: program reads more than 7 record words"; return SGR_ERR_UNSUPPORTED; }
   const uint64_t ctas_per_chunk = chunk_recs / tile;
@@ -515,7 +530,9 @@ int dist_push_fold(DistState* d, const uint8_t* d_records, uint64_t n, const Pus
   unsigned long long* status = (unsigned long long*)((uint8_t*)d->push_ctl.p + off_status);
   const bool pull = push_tuning().pull != 0;
   const uint32_t epoch = ++d->epoch;
-  cudaStream_t s0 = st, s1 = d->stream2;
+  // st: the engine's stream (brackets the call); sp: partition + flag kernels, HIGH priority; s1: wait + fold kernels, LOW
+  // priority with one tile per CTA — the fold fills whatever the partition leaves free and takes the whole GPU once it is done
+  cudaStream_t s0 = st, sp = d->stream_hi, s1 = d->stream2;
   DTRY(cudaMemsetAsync(d->push_ctl.p, 0, off_proj + 64, s0));
   DTRY(cudaMemsetAsync(d->lb.p, 0, (size_t)C * ctas_per_chunk * kMaxRanks * 8, s0));
   DTRY(cudaMemsetAsync(pf.counters, 0, 64, s0));
@@ -523,6 +540,7 @@ int dist_push_fold(DistState* d, const uint8_t* d_records, uint64_t n, const Pus
   if (R > 1 && !d->loopback) NTRY(nccl_api().AllGather((uint8_t*)d->push_ctl.p + off_proj, d->counts_all.p, 1, ncclUint32, d->comm, s0));
   DTRY(cudaEventRecord(d->pev[0], s0));
   DTRY(cudaStreamWaitEvent(s1, d->pev[0], 0));
+  DTRY(cudaStreamWaitEvent(sp, d->pev[0], 0));
   unsigned long long* my_flags = (unsigned long long*)d->peer_base[d->rank];
   for (uint32_t c = 0; c < C; ++c) {
     const uint64_t begin = (uint64_t)c * chunk_recs;
@@ -544,36 +562,40 @@ int dist_push_fold(DistState* d, const uint8_t* d_records, uint64_t n, const Pus
       // contiguous per-owner runs only pay across NVLink; the staged kernel is always ordered
       const bool staged = pf.ordered && (push_tuning().staged >= 0 ? push_tuning().staged != 0 : !pull);
       if (staged) {
-        if (tile == 256) route_push_kernel<1><<<grid, kPushThreads, push_smem_bytes<1>(), s0>>>(a);
-        else if (tile == 512) route_push_kernel<2><<<grid, kPushThreads, push_smem_bytes<2>(), s0>>>(a);
-        else route_push_kernel<4><<<grid, kPushThreads, push_smem_bytes<4>(), s0>>>(a);
+        if (tile == 256) route_push_kernel<1><<<grid, kPushThreads, push_smem_bytes<1>(), sp>>>(a);
+        else if (tile == 512) route_push_kernel<2><<<grid, kPushThreads, push_smem_bytes<2>(), sp>>>(a);
+        else route_push_kernel<4><<<grid, kPushThreads, push_smem_bytes<4>(), sp>>>(a);
       } else {
-        if (tile == 256) route_part_kernel<1><<<grid, kPushThreads, 0, s0>>>(a);
-        else if (tile == 512) route_part_kernel<2><<<grid, kPushThreads, 0, s0>>>(a);
-        else route_part_kernel<4><<<grid, kPushThreads, 0, s0>>>(a);
+        if (tile == 256) route_part_kernel<1><<<grid, kPushThreads, 0, sp>>>(a);
+        else if (tile == 512) route_part_kernel<2><<<grid, kPushThreads, 0, sp>>>(a);
+        else route_part_kernel<4><<<grid, kPushThreads, 0, sp>>>(a);
       }
     }
     FlagArgs f{};
     for (int q = 0; q < R; ++q) f.peer_flag[q] = (unsigned long long*)d->peer_base[q] + (size_t)d->rank * kMaxChunks + c;
     f.totals = totals + (size_t)c * kMaxRanks; f.status = status; f.nranks = (uint32_t)R; f.epoch = epoch;
-    push_flag_kernel<<<1, 32, 0, s0>>>(f);
+    push_flag_kernel<<<1, 32, 0, sp>>>(f);
     // ---- receiver side of chunk c
     push_wait_kernel<<<1, 32, 0, s1>>>(my_flags, c, (uint32_t)R, epoch, status);
     BulkSrc bs{};
     bs.n_regions = (uint32_t)R; bs.compact = pf.compact ? 1u : 0u; bs.rec_bytes = out_bytes; bs.rotate = (uint32_t)d->rank; bs.carried = 1;
-    bs.blocks_per_sm = (uint32_t)push_tuning().fold_blocks_per_sm;
+    bs.blocks_per_sm = push_tuning().fold_blocks_per_sm > 0 ? (uint32_t)push_tuning().fold_blocks_per_sm : 0xffffffffu;
     for (int s = 0; s < R; ++s) {
       // pull: source s keeps what it has for me in ITS buffer, region (me, chunk): the fold reads it over NVLink
       bs.base[s] = pull ? d->peer_recv[s] + ((uint64_t)d->rank * C + c) * cap_region * out_bytes
                         : d->peer_recv[d->rank] + ((uint64_t)s * C + c) * cap_region * out_bytes;
       bs.count_flag[s] = my_flags + (size_t)s * kMaxChunks + c;
       bs.count[s] = cap_region;
-      bs.idx_base[s] = (uint32_t)((uint64_t)c * chunk_recs);   // + the index the record carries: monotone along every aggregate's log
+      // + the index the record carries within ITS SOURCE's chunk c. The sources cut their logs into chunks of different lengths
+      // (each from its own record count), so the base must not depend on any rank's chunk length: a fixed stride that bounds
+      // them all keeps the arrival index monotone along every aggregate's log
+      bs.idx_base[s] = (uint32_t)((uint64_t)c * idx_stride);
     }
     DTRY(launch_bulk_accumulate(bs, pf.n_slots, pf.scratch, *pf.prog, *pf.lay, pf.counters, pf.num_sms, s1));
   }
   DTRY(cudaGetLastError());
-  DTRY(cudaEventRecord(d->pev[1], s0));    // all pushes issued and flagged
+  DTRY(cudaEventRecord(d->pev[1], sp));    // all partition kernels done and flagged
+  DTRY(cudaStreamWaitEvent(s0, d->pev[1], 0));
   DTRY(launch_bulk_finish(pf.n_slots, pf.scratch, pf.states, pf.err_ids, *pf.lay, pf.counters, s1));
   DTRY(cudaEventRecord(d->pev[2], s1));
   DTRY(cudaStreamWaitEvent(s0, d->pev[2], 0));

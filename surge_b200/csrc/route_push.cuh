@@ -16,7 +16,9 @@ namespace sgr {
 //              0 = the sender writes into the owner's buffer (remote stores). The same on every rank.
 // "push_staged": 1 = partition through shared memory (contiguous per-owner runs), 0 = position pass + direct copy, -1 = staged iff
 //                the regions are written over NVLink (pull == 0)
-struct PushTuning { int tile = 512; int pull = 1; int fold_blocks_per_sm = 2; int staged = -1; };
+// "push_fold_blocks_per_sm": grid cap of the fold launches beside the partition kernel; 0 = one tile per CTA (the low-priority fold
+//                            then fills what the high-priority partition leaves free)
+struct PushTuning { int tile = 512; int pull = 1; int fold_blocks_per_sm = 0; int staged = -1; };
 PushTuning& push_tuning();
 
 struct PushFoldArgs {

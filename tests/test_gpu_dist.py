@@ -249,7 +249,7 @@ def test_loopback_push_pipeline_matches_oracle(R, fused):
             e.close()
 
 
-@pytest.mark.parametrize("pull,staged,tile", [(0, 1, 1024), (0, 0, 256), (1, 1, 512), (1, 0, 1024), (1, 0, 256)])
+@pytest.mark.parametrize("pull,staged,tile", [(0, 1, 1024), (0, 0, 256), (1, 1, 512), (1, 0, 1024), (1, 0, 256), (0, 1, 512), (1, 1, 1024), (1, 1, 256), (1, 0, 512)])
 def test_loopback_exchange_variants_agree(pull, staged, tile):
     """remote stores vs remote loads, staged vs direct partition kernel, every tile size: the same tables."""
     R, n_global = 4, 20000
