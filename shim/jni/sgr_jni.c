@@ -13,6 +13,20 @@
 
 #define H(h) ((sgr_engine*)(intptr_t)(h))
 
+/* Lengths and buffers come from Java: check them here, throw IllegalArgumentException, never read past what was handed over
+ * (round-1 review: a short `firsts` array, a non-direct buffer (GetDirectBufferAddress == NULL) or an nbytes beyond the
+ * buffer's capacity went straight to the C ABI). */
+static int bad_arg(JNIEnv* env, const char* what) {
+  (*env)->ThrowNew(env, (*env)->FindClass(env, "java/lang/IllegalArgumentException"), what);
+  return SGR_ERR_INVALID;
+}
+/* direct buffer address, checked: non-NULL and at least `need` bytes of capacity */
+static void* direct(JNIEnv* env, jobject buf, jlong need, const char* what, int* ok) {
+  void* p = buf ? (*env)->GetDirectBufferAddress(env, buf) : 0;
+  if (!p || need < 0 || (*env)->GetDirectBufferCapacity(env, buf) < need) { bad_arg(env, what); *ok = 0; return 0; }
+  return p;
+}
+
 static void throw_for(JNIEnv* env, sgr_engine* e, int32_t rc) {
   const char* cls = rc == SGR_ERR_STATE ? "org/apache/kafka/streams/errors/InvalidStateStoreException" : "java/lang/RuntimeException";
   (*env)->ThrowNew(env, (*env)->FindClass(env, cls), sgr_last_error(e));
@@ -28,23 +42,35 @@ JNIEXPORT jlong JNICALL Java_surge_gpu_Native_00024_create(JNIEnv* env, jobject 
 JNIEXPORT jint JNICALL Java_surge_gpu_Native_00024_destroy(JNIEnv* env, jobject o, jlong h) { return sgr_destroy(H(h)); }
 JNIEXPORT jstring JNICALL Java_surge_gpu_Native_00024_lastError(JNIEnv* env, jobject o, jlong h) { return (*env)->NewStringUTF(env, sgr_last_error(H(h))); }
 JNIEXPORT jint JNICALL Java_surge_gpu_Native_00024_registerProgram(JNIEnv* env, jobject o, jlong h, jobject prog) {
-  return sgr_register_program(H(h), (const sgr_fold_program*)(*env)->GetDirectBufferAddress(env, prog));
+  int ok = 1; void* p = direct(env, prog, (jlong)sizeof(sgr_fold_program), "program: direct buffer of sizeof(sgr_fold_program) bytes", &ok);
+  return ok ? sgr_register_program(H(h), (const sgr_fold_program*)p) : SGR_ERR_INVALID;
 }
 JNIEXPORT jint JNICALL Java_surge_gpu_Native_00024_loadEvents(JNIEnv* env, jobject o, jlong h, jobject ev, jlong nbytes, jobject offs, jlong n_agg) {
-  return sgr_load_events(H(h), (*env)->GetDirectBufferAddress(env, ev), (uint64_t)nbytes, (const uint64_t*)(*env)->GetDirectBufferAddress(env, offs), (uint64_t)n_agg);
+  int ok = 1;
+  void* e = direct(env, ev, nbytes, "events: direct buffer shorter than nbytes", &ok);
+  void* so = ok && n_agg >= 0 ? direct(env, offs, (n_agg + 1) * 8, "segOffsets: direct buffer of (nAgg + 1) u64", &ok) : 0;
+  return ok && so ? sgr_load_events(H(h), e, (uint64_t)nbytes, (const uint64_t*)so, (uint64_t)n_agg) : SGR_ERR_INVALID;
 }
 JNIEXPORT jint JNICALL Java_surge_gpu_Native_00024_loadUnsorted(JNIEnv* env, jobject o, jlong h, jobject rec, jlong n, jlong n_agg) {
-  return sgr_load_unsorted(H(h), (*env)->GetDirectBufferAddress(env, rec), (uint64_t)n, (uint64_t)n_agg);
+  int ok = 1; void* r = n >= 0 && n <= (INT64_MAX / 64) ? direct(env, rec, n * 64, "records: direct buffer shorter than nRecords * 64", &ok) : (bad_arg(env, "nRecords"), (void*)0);
+  return ok && r ? sgr_load_unsorted(H(h), r, (uint64_t)n, (uint64_t)n_agg) : SGR_ERR_INVALID;
 }
 JNIEXPORT jint JNICALL Java_surge_gpu_Native_00024_setInitialStates(JNIEnv* env, jobject o, jlong h, jobject st, jlong n_agg) {
-  return sgr_set_initial_states(H(h), st ? (*env)->GetDirectBufferAddress(env, st) : 0, (uint64_t)n_agg);
+  if (!st) return sgr_set_initial_states(H(h), 0, 0);
+  int ok = 1; void* p = direct(env, st, 16 * n_agg, "states: direct buffer shorter than nAgg states", &ok);   /* >= 16 bytes per state */
+  return ok ? sgr_set_initial_states(H(h), p, (uint64_t)n_agg) : SGR_ERR_INVALID;
 }
 JNIEXPORT jint JNICALL Java_surge_gpu_Native_00024_fold(JNIEnv* env, jobject o, jlong h) { return sgr_fold(H(h)); }
 JNIEXPORT jint JNICALL Java_surge_gpu_Native_00024_foldIncremental(JNIEnv* env, jobject o, jlong h, jobject rec, jlong n) {
-  return sgr_fold_incremental(H(h), (*env)->GetDirectBufferAddress(env, rec), (uint64_t)n);
+  int ok = 1; void* r = n >= 0 && n <= (INT64_MAX / 64) ? direct(env, rec, n * 64, "records: direct buffer shorter than nRecords * 64", &ok) : (bad_arg(env, "nRecords"), (void*)0);
+  return ok && r ? sgr_fold_incremental(H(h), r, (uint64_t)n) : SGR_ERR_INVALID;
 }
 JNIEXPORT jint JNICALL Java_surge_gpu_Native_00024_loadKeys(JNIEnv* env, jobject o, jlong h, jobject keys, jobject offs, jlong n) {
-  return sgr_load_keys(H(h), (const uint8_t*)(*env)->GetDirectBufferAddress(env, keys), (const uint32_t*)(*env)->GetDirectBufferAddress(env, offs), (uint64_t)n);
+  int ok = 1;
+  const uint32_t* ko = n >= 0 ? (const uint32_t*)direct(env, offs, (n + 1) * 4, "keyOffsets: direct buffer of (n + 1) u32", &ok) : 0;
+  if (!ok || !ko) return SGR_ERR_INVALID;
+  const uint8_t* k = (const uint8_t*)direct(env, keys, (jlong)ko[n], "keys: direct buffer shorter than keyOffsets[n]", &ok);
+  return ok ? sgr_load_keys(H(h), k, ko, (uint64_t)n) : SGR_ERR_INVALID;
 }
 JNIEXPORT jbyteArray JNICALL Java_surge_gpu_Native_00024_get(JNIEnv* env, jobject o, jlong h, jbyteArray key) {
   jsize klen = (*env)->GetArrayLength(env, key);
@@ -66,8 +92,9 @@ JNIEXPORT jint JNICALL Java_surge_gpu_Native_00024_partitionForKey(JNIEnv* env, 
   jsize klen = (*env)->GetArrayLength(env, key);
   jbyte* k = (*env)->GetByteArrayElements(env, key, 0);
   int32_t p = -1;
-  sgr_partition_for_key_utf8((const uint8_t*)k, (uint32_t)klen, (uint32_t)n, up_to_colon ? 1 : 0, &p);
+  int32_t rc = n > 0 ? sgr_partition_for_key_utf8((const uint8_t*)k, (uint32_t)klen, (uint32_t)n, up_to_colon ? 1 : 0, &p) : SGR_ERR_INVALID;
   (*env)->ReleaseByteArrayElements(env, key, k, JNI_ABORT);
+  if (rc != SGR_OK) { bad_arg(env, "partitionForKey: numPartitions must be positive and the key valid UTF-8"); return -1; }
   return p;
 }
 
@@ -84,6 +111,7 @@ JNIEXPORT jint JNICALL Java_surge_gpu_Native_00024_ingestSetNullValueType(JNIEnv
 /* sgr_ingest_set_json_packer takes an array of structs with strings: bind it with a small marshaller (or JNA) on the maintainer's side. */
 JNIEXPORT jint JNICALL Java_surge_gpu_Native_00024_ingestSetAborted(JNIEnv* env, jobject o, jlong g, jint partition, jlongArray pids, jlongArray firsts) {
   jsize n = (*env)->GetArrayLength(env, pids);
+  if ((*env)->GetArrayLength(env, firsts) != n) return bad_arg(env, "producerIds and firstOffsets differ in length");
   jlong* p = (*env)->GetLongArrayElements(env, pids, 0);
   jlong* f = (*env)->GetLongArrayElements(env, firsts, 0);
   int32_t rc = sgr_ingest_set_aborted(G(g), partition, (const int64_t*)p, (const int64_t*)f, (uint64_t)n);
@@ -93,7 +121,9 @@ JNIEXPORT jint JNICALL Java_surge_gpu_Native_00024_ingestSetAborted(JNIEnv* env,
 }
 JNIEXPORT jlong JNICALL Java_surge_gpu_Native_00024_ingestRecordBatches(JNIEnv* env, jobject o, jlong g, jint partition, jobject data, jlong nbytes) {
   sgr_ingest_stats st;
-  int32_t rc = sgr_ingest_record_batches(G(g), partition, (*env)->GetDirectBufferAddress(env, data), (uint64_t)nbytes, &st);
+  int ok = 1; void* d = direct(env, data, nbytes, "data: direct buffer shorter than nbytes", &ok);
+  if (!ok) return -1;
+  int32_t rc = sgr_ingest_record_batches(G(g), partition, d, (uint64_t)nbytes, &st);
   if (rc != SGR_OK) {   /* a corrupt batch kills the stream thread, as a CorruptRecordException would */
     (*env)->ThrowNew(env, (*env)->FindClass(env, "java/lang/RuntimeException"), sgr_ingest_last_error(G(g)));
     return -1;

@@ -86,3 +86,21 @@ def counter_snapshot_restore_program() -> N.sgr_fold_program:
         (N.CREATE, [(N.OP_SET, 0, 16, 4), (N.OP_SET, 4, 20, 4)]),
         (N.TOMBSTONE, []),
     ])
+
+
+COUNTER_SNAPSHOT_TYPE, COUNTER_TOMBSTONE_TYPE = 4, 5
+
+
+def counter_program_with_snapshot_rules() -> N.sgr_fold_program:
+    """The Counter handler plus the two rules that let ONE table take both feeds of the state store (shim/scala
+    GpuReplayPersistencePlugin.scala): events of the events topic (types 0-3 as in counter_program) and records of the compacted
+    STATE topic — type 4 = a snapshot (CREATE + SET every state word from the record: count @16, version @20: last write wins,
+    SurgeStateStoreConsumer.scala:57-76), type 5 = a null value (TOMBSTONE: the key is deleted, SurgeModel.scala:62-64)."""
+    return make_program(16, N.REC_FIXED64, [
+        (N.MATERIALISE, [(N.OP_ADD_I32, 0, 16, 4), (N.OP_SET, 4, 4, 4)]),
+        (N.MATERIALISE, [(N.OP_SUB_I32, 0, 16, 4), (N.OP_SET, 4, 4, 4)]),
+        (N.MATERIALISE, []),
+        (N.THROW, []),
+        (N.CREATE, [(N.OP_SET, 0, 16, 4), (N.OP_SET, 4, 20, 4)]),
+        (N.TOMBSTONE, []),
+    ])

@@ -112,6 +112,15 @@ def aggregate_id_of_record_key(key: str) -> str:
     return key if i < 0 else key[:i]
 
 
+class StateCodec:
+    """serialized state bytes (what the state topic and the actors hold) <-> the packed program bytes of the GPU table
+    (trait GpuStateCodec of shim/scala GpuReplayPersistencePlugin.scala). snapshot_type / tombstone_type are the two extra rules of
+    the registered fold program (programs.counter_program_with_snapshot_rules)."""
+
+    def __init__(self, to_packed: Callable[[str, bytes], bytes], from_packed: Callable[[str, bytes], bytes], snapshot_type: int, tombstone_type: int):
+        self.to_packed, self.from_packed, self.snapshot_type, self.tombstone_type = to_packed, from_packed, snapshot_type, tombstone_type
+
+
 class GpuReplayKeyValueStore:
     """KeyValueStore[Bytes, Array[Byte]] whose content is the GPU-folded state table.
 
@@ -122,8 +131,13 @@ class GpuReplayKeyValueStore:
     read side (32-thread pool in the reference): get() is thread-safe.
     """
 
-    def __init__(self, name: str, program: N.sgr_fold_program, device: int = 0, state_formatter: Optional[Callable[[str, bytes], bytes]] = None):
+    def __init__(self, name: str, program: N.sgr_fold_program, device: int = 0, state_formatter: Optional[Callable[[str, bytes], bytes]] = None,
+                 codec: Optional[StateCodec] = None):
         self._name = name
+        # with a codec, put()/delete() are records of the STATE topic folded on the GPU as snapshot / tombstone events (feed (i) of
+        # the Scala store): flush() — which Kafka Streams calls before it commits offsets — makes them readable from the table
+        self._codec = codec
+        self._unflushed: Dict[str, Optional[bytes]] = {}
         self._engine = ReplayEngine(device)
         self._engine.register_program(program)
         self._formatter = state_formatter
@@ -181,8 +195,10 @@ class GpuReplayKeyValueStore:
             if self._ingest is not None:
                 raise N.SgrError(N.SGR_ERR_INVALID, "this store is already fed through restore_record_batches")
             rec = np.frombuffer(packed_event, dtype=np.uint8).copy()
-            rec[8:16] = np.frombuffer(np.uint64(self._slot(aggregate_id_of_record_key(record_key))).tobytes(), dtype=np.uint8)
+            agg_id = aggregate_id_of_record_key(record_key)
+            rec[8:16] = np.frombuffer(np.uint64(self._slot(agg_id)).tobytes(), dtype=np.uint8)
             self._pending.append(rec)
+            self._unflushed.pop(agg_id, None)   # an event supersedes an unflushed snapshot view
 
     def restore(self, records: Iterable[Tuple[Optional[str], bytes]]) -> None:
         for k, v in records:
@@ -240,17 +256,35 @@ class GpuReplayKeyValueStore:
             if self._keys_loaded != (n_keys, self._capacity):
                 self._engine.load_keys(self._keys + [f"\0unused-{i}" for i in range(n_keys, self._capacity)])
                 self._keys_loaded = (n_keys, self._capacity)
+            self._unflushed.clear()
 
     # -- KeyValueStore
+    def _state_record(self, key: str, value: Optional[bytes]) -> None:
+        rec = np.zeros(64, dtype=np.uint8)
+        rec[0:4] = np.frombuffer(np.uint32(self._codec.tombstone_type if value is None else self._codec.snapshot_type).tobytes(), dtype=np.uint8)
+        rec[8:16] = np.frombuffer(np.uint64(self._slot(key)).tobytes(), dtype=np.uint8)
+        if value is not None:
+            packed = self._codec.to_packed(key, value)
+            if len(packed) > 48:
+                raise ValueError("snapshot records carry at most 48 program bytes")
+            rec[16:16 + len(packed)] = np.frombuffer(packed, dtype=np.uint8)
+        self._pending.append(rec)
+        self._unflushed[key] = value
+
     def put(self, key: str, value: Optional[bytes]) -> None:
+        if not key:      # the producer's flush record: empty key, empty value (KafkaProducerActorImpl.scala:321-329)
+            return
         with self._lock:
-            self._overlay[key] = value
+            if self._codec is not None:
+                self._state_record(key, value)
+            else:
+                self._overlay[key] = value
 
     def putIfAbsent(self, key: str, value: bytes) -> Optional[bytes]:  # noqa: N802
         with self._lock:
             cur = self.get(key)
             if cur is None:
-                self._overlay[key] = value
+                self.put(key, value)
             return cur
 
     def putAll(self, entries: Sequence[Tuple[str, Optional[bytes]]]) -> None:  # noqa: N802
@@ -260,7 +294,7 @@ class GpuReplayKeyValueStore:
     def delete(self, key: str) -> Optional[bytes]:
         with self._lock:
             cur = self.get(key)
-            self._overlay[key] = None
+            self.put(key, None)
             return cur
 
     def get(self, key: str) -> Optional[bytes]:
@@ -268,17 +302,22 @@ class GpuReplayKeyValueStore:
             raise InvalidStateStoreException(N.SGR_ERR_STATE, f"store {self._name} is not open")
         if key in self._overlay:
             return self._overlay[key]
+        if key in self._unflushed:            # read-your-writes between put() and flush()
+            return self._unflushed[key]
         if not self._folded:
             raise InvalidStateStoreException(N.SGR_ERR_STATE, f"store {self._name} has not been restored yet")
         b = self._engine.get(key)
         if b is None:
             return None
+        if self._codec is not None:
+            return self._codec.from_packed(key, b)
         return self._formatter(key, b) if self._formatter else b
 
     def all(self) -> Iterator[Tuple[str, bytes]]:
         with self._lock:
             # KeyValueStore[Bytes, _] iterates in Bytes order: unsigned lexicographic over the UTF-8 key bytes
-            keys = sorted(set(self._ingest.keys() if self._ingest is not None else self._keys) | set(self._overlay), key=lambda k: k.encode("utf-8"))
+            keys = sorted(set(self._ingest.keys() if self._ingest is not None else self._keys) | set(self._overlay) | set(self._unflushed),
+                          key=lambda k: k.encode("utf-8"))
         for k in keys:
             v = self.get(k)
             if v is not None:

@@ -132,3 +132,40 @@ def test_store_restores_from_raw_record_batches_and_reports_committed_offsets():
     with pytest.raises(N.SgrError):
         store.put_event("x:1", bytes(64))
     store.close()
+
+
+@pytest.mark.gpu
+def test_state_topic_records_and_events_fold_into_one_table():
+    """Feed (i) + (ii) of the Scala store: put(key, serializedState) / put(key, null) are snapshot / tombstone events of the same
+    fold program as the model's own events; flush() folds them in arrival order; get() answers in the model's serialized form.
+    Checked against the program interpreter (the written semantics of include/sgr.h)."""
+    from oracle import program_interp as I
+
+    codec = ST.StateCodec(
+        to_packed=lambda key, b: np.array([int(x) for x in b.decode().split(",")], dtype="<i4").tobytes(),
+        from_packed=lambda key, p: ",".join(str(x) for x in np.frombuffer(p, dtype="<i4")).encode(),
+        snapshot_type=P.COUNTER_SNAPSHOT_TYPE, tombstone_type=P.COUNTER_TOMBSTONE_TYPE)
+    store = ST.GpuReplayKeyValueStore("s", P.counter_program_with_snapshot_rules(), codec=codec)
+    store.init()
+    assert store.get("a") is None or True
+    store.put("a", b"10,3"); store.put("b", b"7,1"); store.put("", b"")           # the last one is a flush record: ignored
+    assert store.get("a") == b"10,3"                                                # read-your-writes before the fold
+    store.flush()
+    assert store.get("a") == b"10,3" and store.get("b") == b"7,1" and store.get("zz") is None
+    store.put_event("a:4", _ev(0, 4, 5))          # an event on top of the snapshot: count 15, version 4
+    store.put("b", b"100,9")                      # a newer snapshot of b wins over the old one
+    store.put_event("b:10", _ev(1, 10, 1))        # ... and an event after it applies to the NEW snapshot: 99, 10
+    store.put("c", b"1,1"); store.delete("c")     # written and deleted inside one batch
+    store.flush()
+    assert store.get("a") == b"15,4" and store.get("b") == b"99,10" and store.get("c") is None
+    assert [k for k, _ in store.all()] == ["a", "b"]
+    store.delete("a"); store.flush()
+    assert store.get("a") is None and [k for k, _ in store.all()] == ["b"]
+    # the same log through the interpreter
+    rules = [(I.MATERIALISE, [(I.OP_ADD_I32, 0, 16, 4), (I.OP_SET, 4, 4, 4)]), (I.MATERIALISE, [(I.OP_SUB_I32, 0, 16, 4), (I.OP_SET, 4, 4, 4)]),
+             (I.MATERIALISE, []), (I.THROW, []), (I.CREATE, [(I.OP_SET, 0, 16, 4), (I.OP_SET, 4, 20, 4)]), (I.TOMBSTONE, [])]
+    snap = lambda c, v: F.counter_records([4], [0], [0], [c]).tobytes()[:20] + np.int32(v).tobytes() + bytes(40)   # noqa: E731
+    log_b = np.frombuffer(snap(7, 1) + snap(100, 9) + _ev(1, 10, 1), dtype=np.uint8)
+    want_b = I.fold(rules, 16, log_b, [0, len(log_b)])
+    assert np.frombuffer(want_b[0, :8].tobytes(), dtype="<i4").tolist() == [99, 10]
+    store.close()
