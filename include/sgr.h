@@ -447,6 +447,36 @@ int32_t sgr_grow_states(sgr_engine* e, uint64_t n_agg);
  * to sgr_get, and mark the ingest folded: poll -> sgr_ingest_record_batches -> sgr_fold_ingested is the whole restore loop. */
 int32_t sgr_fold_ingested(sgr_engine* e, sgr_ingest* g);
 
+/* Append ids to the key table sgr_get reads: the ids of dense indices [n, n + n_new) where n is the number of ids `owner` has
+ * appended so far (a different owner starts a new table). owner is an opaque tag: the id dictionary the table mirrors. */
+int32_t sgr_append_keys(sgr_engine* e, const void* owner, const uint8_t* keys, const uint32_t* key_offsets, uint64_t n_new);
+
+/* ------------------------------------------------------------------ device ingest: the same decode ON THE GPU
+ * Same input (raw bytes of fetch responses, RecordBatch magic 2, compression none / lz4, read_committed semantics) and the same
+ * outcome as sgr_ingest_* + sgr_fold_ingested, but only the WIRE bytes cross PCIe: CRC-32C, lz4, record parsing, id interning and
+ * the fold run on the engine's device (csrc/dingest_kernels.cu); the host walks the 61-byte batch headers and keeps the
+ * read_committed bookkeeping (control batches, aborted transactions, partition positions). csrc/ingest.cpp is its checker
+ * (tests/test_gpu_dingest.py: identical states, ids, offsets and statistics on the same bytes).
+ *   - value framing: SGR_VALUE_PACKED only (protobuf / JSON values: use the host ingest);
+ *   - programs in the sort-free class (16-byte state, class 0): dropped records stay in place as holes the fold skips;
+ *   - dense indices are stable per id but follow no arrival-order promise (they come from an atomic counter);
+ *   - the id dictionary is sized at creation: max_keys ids, max_id_bytes id bytes (0 = 32 per id); exceeding either fails the
+ *     poll with SGR_ERR_CAPACITY and applies nothing.
+ * poll loop:  sgr_dingest_set_aborted* -> sgr_dingest_submit(partition, bytes)* -> sgr_dingest_fold.
+ * `data` of a submit must stay valid until the fold returns (with page-locked memory the copy is one asynchronous DMA). */
+typedef struct sgr_dingest sgr_dingest;
+int32_t sgr_dingest_create(sgr_engine* e, uint64_t max_keys, uint64_t max_id_bytes, sgr_dingest** out);
+int32_t sgr_dingest_destroy(sgr_dingest* g);
+const char* sgr_dingest_last_error(const sgr_dingest* g);
+int32_t sgr_dingest_set_null_value_type(sgr_dingest* g, int32_t event_type);
+int32_t sgr_dingest_set_aborted(sgr_dingest* g, int32_t partition, const int64_t* producer_ids, const int64_t* first_offsets, uint64_t n);
+int32_t sgr_dingest_submit(sgr_dingest* g, int32_t partition, const void* data, uint64_t nbytes, sgr_ingest_stats* stats);
+/* decode + intern + fold everything submitted since the last fold onto the engine's live table (grown as ids appear), publish
+ * the new ids to sgr_get, advance the partitions' positions. All or nothing. stats (optional): this poll's totals. */
+int32_t sgr_dingest_fold(sgr_dingest* g, sgr_ingest_stats* stats);
+int32_t sgr_dingest_offsets(sgr_dingest* g, int32_t partition, int64_t* decoded_next, int64_t* folded_next);
+int32_t sgr_dingest_get_stats(sgr_dingest* g, sgr_ingest_stats* out);
+
 /* building blocks, exported for the known-answer tests */
 uint32_t sgr_crc32c(const void* data, uint64_t nbytes);            /* RFC 3720 CRC-32C (SSE4.2 when present) */
 uint32_t sgr_crc32c_portable(const void* data, uint64_t nbytes);   /* table-driven twin */

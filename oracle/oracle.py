@@ -23,7 +23,8 @@ ST_EXISTS, ST_CHANGED, ST_ERROR = 1, 2, 4
 def build(force: bool = False) -> str:
     src = os.path.join(_HERE, "sgr_oracle.c")
     hdr = os.path.join(_HERE, "sgr_oracle.h")
-    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+    enc = os.path.join(_HERE, "kafka_encode.c")
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < max(os.path.getmtime(src), os.path.getmtime(hdr), os.path.getmtime(enc)):
         subprocess.check_call(["make", "-s", "-C", _HERE, "-B"])
     return _LIB_PATH
 
@@ -47,6 +48,10 @@ def lib():
         L.orc_fold_packed_mt_pinned.argtypes = [C.c_int, C.c_uint32, u8p, u64p, C.c_uint64, u8p, u8p, C.c_int, u64p, u64p]
         L.orc_place_log_mt.restype = C.c_int
         L.orc_place_log_mt.argtypes = [u8p, u8p, u64p, C.c_uint64, C.c_int]
+        L.orc_kafka_encode_bound.restype = C.c_uint64
+        L.orc_kafka_encode_bound.argtypes = [C.c_uint64, C.c_uint32]
+        L.orc_kafka_encode_counter.restype = C.c_int64
+        L.orc_kafka_encode_counter.argtypes = [u8p, u8p, u8p, u8p, C.c_uint64, C.c_uint32, C.c_int, C.c_int64, u8p, C.c_uint64]
         L.orc_fold_incremental.restype = C.c_int
         L.orc_fold_incremental.argtypes = [C.c_int, u8p, C.c_uint64, u8p, C.c_uint64]
         L.orc_group_by_agg.restype = C.c_int
@@ -101,6 +106,23 @@ def place_log(events: np.ndarray, seg_offsets: np.ndarray, threads: int) -> np.n
     if lib().orc_place_log_mt(_ptr(dst), _ptr(events), _ptr(seg_offsets), len(seg_offsets) - 1, threads) != 0:
         raise ValueError("oracle: placement failed")
     return dst
+
+
+def kafka_encode_counter(agg: np.ndarray, types: np.ndarray, seqs: np.ndarray, bys: np.ndarray, recs_per_batch: int = 512, lz4: bool = True,
+                         base_offset: int = 0, out: Optional[np.ndarray] = None) -> np.ndarray:
+    """Producer-side bytes of one partition of the Counter events topic (oracle/kafka_encode.c): consecutive RecordBatch v2
+    structures of recs_per_batch records, key "agg-<n>:<seq>", value = packed (type, seq, by). Returns a uint8 view of `out`
+    (allocated when None). Test / bench INPUT construction only."""
+    agg = np.ascontiguousarray(agg, dtype=np.uint32); types = np.ascontiguousarray(types, dtype=np.uint32)
+    seqs = np.ascontiguousarray(seqs, dtype=np.uint32); bys = np.ascontiguousarray(bys, dtype=np.int32)
+    n = len(agg)
+    bound = int(lib().orc_kafka_encode_bound(n, recs_per_batch))
+    if out is None:
+        out = np.empty(bound, dtype=np.uint8)
+    got = lib().orc_kafka_encode_counter(_ptr(agg), _ptr(types), _ptr(seqs), _ptr(bys), n, recs_per_batch, 1 if lz4 else 0, base_offset, _ptr(out), out.size)
+    if got < 0:
+        raise ValueError("kafka_encode: output buffer too small")
+    return out[:got]
 
 
 def group_by_agg(records: np.ndarray, n_agg: int) -> Tuple[np.ndarray, np.ndarray]:

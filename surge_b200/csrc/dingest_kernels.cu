@@ -1,0 +1,391 @@
+// dingest_kernels.cu — Kafka RecordBatch v2 decode ON THE DEVICE (sm_100a): the step right before the fold.
+//
+// What feeds the store today is a read_committed consumer of a topic whose producer compresses with lz4
+// (modules/common/src/main/scala/surge/kafka/streams/SurgeStateStoreConsumer.scala:38; modules/common/src/main/resources/
+// reference.conf:124). Round 1 decoded those bytes on the host (csrc/ingest.cpp) and copied 64-byte packed records over PCIe —
+// the copy was 95 % of the end-to-end step. Here the WIRE bytes cross PCIe (about 25 B per event instead of 64) and everything
+// per-batch and per-record happens on the GPU; the host keeps only the walk over the 61-byte batch headers and the
+// read_committed bookkeeping (csrc/dingest.cu). csrc/ingest.cpp stays as the byte-equal checker (tests/test_gpu_dingest.py).
+//
+//   crc_size    one THREAD per batch: CRC-32C of the batch (slicing-by-8, tables in shared memory) against the header's field;
+//               lz4 frames: header + block walk that only ADDS UP sequence lengths -> decompressed size (the arena is then laid
+//               out by an exclusive scan on the host: 4 bytes per batch come back)
+//   decode_walk one thread per batch: lz4 sequences copied into the batch's arena slot (byte-serial by nature: matches may
+//               overlap their own output), then the record-boundary walk — a chain of varints — writes every record's offset
+//   parse       one thread per RECORD: varint fields, key -> aggregate id (up to ':', KafkaPartitioner.scala:38-42), value ->
+//               packed 64-byte record at the record's own slot (arrival order kept), id -> dense index through a device hash
+//               table (64-bit hash tag claimed by CAS, id bytes compared, index from an atomic counter)
+// Records a read_committed consumer would not deliver (flush markers, duplicates below the partition position, dropped null
+// values) become HOLES (agg == ~0) that the fold kernels skip; nothing is compacted.
+//
+// Thread-per-batch is deliberate: a 16 KiB producer batch is ~1 k lz4 sequences and ~500 varint-delimited records, strictly
+// serial inside; the parallelism is the tens of thousands of batches of a restore poll. All of it is HBM/latency-bound
+// byte work — no tensor cores anywhere.
+#include "dingest_kernels.cuh"
+
+#include <string.h>
+
+namespace sgr {
+namespace {
+
+constexpr int kThreads = 128;
+__device__ uint32_t g_crc_tab[8][256];
+
+struct CrcInit {
+  uint32_t t[8][256];
+  CrcInit() {
+    for (uint32_t i = 0; i < 256; ++i) {
+      uint32_t c = i;
+      for (int k = 0; k < 8; ++k) c = (c >> 1) ^ (0x82F63B78u & (0u - (c & 1u)));
+      t[0][i] = c;
+    }
+    for (uint32_t i = 0; i < 256; ++i)
+      for (int k = 1; k < 8; ++k) t[k][i] = (t[k - 1][i] >> 8) ^ t[0][t[k - 1][i] & 0xff];
+  }
+};
+
+cudaError_t ensure_crc_tables() {
+  static bool done = false;
+  if (done) return cudaSuccess;
+  static const CrcInit init;
+  cudaError_t e = cudaMemcpyToSymbol(g_crc_tab, init.t, sizeof init.t);
+  if (e == cudaSuccess) done = true;
+  return e;
+}
+
+__device__ __forceinline__ uint32_t rd32le(const uint8_t* p) { return p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
+
+__device__ uint32_t crc32c_dev(const uint32_t (*tab)[256], const uint8_t* p, uint64_t n) {
+  uint32_t crc = 0xffffffffu;
+  while (n && ((uintptr_t)p & 7)) { crc = (crc >> 8) ^ tab[0][(crc ^ *p++) & 0xff]; --n; }
+  while (n >= 8) {
+    const unsigned long long w = *reinterpret_cast<const unsigned long long*>(p);
+    const uint32_t lo = (uint32_t)w ^ crc, hi = (uint32_t)(w >> 32);
+    crc = tab[7][lo & 0xff] ^ tab[6][(lo >> 8) & 0xff] ^ tab[5][(lo >> 16) & 0xff] ^ tab[4][lo >> 24] ^
+          tab[3][hi & 0xff] ^ tab[2][(hi >> 8) & 0xff] ^ tab[1][(hi >> 16) & 0xff] ^ tab[0][hi >> 24];
+    p += 8; n -= 8;
+  }
+  while (n--) crc = (crc >> 8) ^ tab[0][(crc ^ *p++) & 0xff];
+  return ~crc;
+}
+
+__device__ __forceinline__ uint32_t rotl32(uint32_t x, int r) { return (x << r) | (x >> (32 - r)); }
+__device__ uint32_t xxh32_dev(const uint8_t* p, uint64_t len, uint32_t seed) {
+  const uint32_t P1 = 2654435761u, P2 = 2246822519u, P3 = 3266489917u, P4 = 668265263u, P5 = 374761393u;
+  const uint8_t* end = p + len;
+  uint32_t h;
+  if (len >= 16) {
+    const uint8_t* limit = end - 16;
+    uint32_t v1 = seed + P1 + P2, v2 = seed + P2, v3 = seed, v4 = seed - P1;
+    do {
+      v1 = rotl32(v1 + rd32le(p) * P2, 13) * P1; p += 4;
+      v2 = rotl32(v2 + rd32le(p) * P2, 13) * P1; p += 4;
+      v3 = rotl32(v3 + rd32le(p) * P2, 13) * P1; p += 4;
+      v4 = rotl32(v4 + rd32le(p) * P2, 13) * P1; p += 4;
+    } while (p <= limit);
+    h = rotl32(v1, 1) + rotl32(v2, 7) + rotl32(v3, 12) + rotl32(v4, 18);
+  } else {
+    h = seed + P5;
+  }
+  h += (uint32_t)len;
+  while (p + 4 <= end) { h = rotl32(h + rd32le(p) * P3, 17) * P4; p += 4; }
+  while (p < end) { h = rotl32(h + (*p++) * P5, 11) * P1; }
+  h ^= h >> 15; h *= P2; h ^= h >> 13; h *= P3; h ^= h >> 16;
+  return h;
+}
+
+// LZ4 frame walk. out == nullptr: only the decoded size is computed (and everything validated except the content checksum).
+// Mirrors lz4_frame_decode of csrc/ingest.cpp decision for decision (same accept / reject behaviour).
+__device__ uint32_t lz4_frame(const uint8_t* src, uint64_t n, uint8_t* out, uint64_t out_cap, uint64_t* out_len) {
+  if (n < 7) return DG_LZ4_HEADER;
+  if (rd32le(src) != 0x184D2204u) return DG_LZ4_HEADER;
+  const uint8_t flg = src[4], bd = src[5];
+  if ((flg >> 6) != 1 || (flg & 0x02)) return DG_LZ4_HEADER;
+  const bool block_checksum = flg & 0x10, content_size = flg & 0x08, content_checksum = flg & 0x04, dict_id = flg & 0x01;
+  const uint32_t bs_code = (bd >> 4) & 7;
+  if (bs_code < 4 || (bd & 0x8F)) return DG_LZ4_HEADER;
+  const uint64_t max_block = 1ull << (8 + 2 * bs_code);
+  const uint64_t desc_len = 2 + (content_size ? 8 : 0) + (dict_id ? 4 : 0);
+  if (n < 4 + desc_len + 1) return DG_LZ4_HEADER;
+  uint64_t declared = 0;
+  if (content_size) for (int k = 7; k >= 0; --k) declared = (declared << 8) | src[6 + k];
+  if (((xxh32_dev(src + 4, desc_len, 0) >> 8) & 0xff) != src[4 + desc_len]) return DG_LZ4_HEADER;
+  uint64_t pos = 4 + desc_len + 1, op = 0;
+  for (;;) {
+    if (pos + 4 > n) return DG_LZ4_BLOCK;
+    const uint32_t word = rd32le(src + pos); pos += 4;
+    if (word == 0) break;
+    const bool stored = word & 0x80000000u;
+    const uint64_t bsz = word & 0x7FFFFFFFu;
+    if (bsz > max_block) return DG_LZ4_BLOCK;
+    if (pos + bsz + (block_checksum ? 4 : 0) > n) return DG_LZ4_BLOCK;
+    const uint8_t* b = src + pos;
+    if (block_checksum && xxh32_dev(b, bsz, 0) != rd32le(b + bsz)) return DG_LZ4_CHECKSUM;
+    if (stored) {
+      if (out) { if (op + bsz > out_cap) return DG_LZ4_TOO_LARGE; for (uint64_t k = 0; k < bsz; ++k) out[op + k] = b[k]; }
+      op += bsz;
+    } else {
+      const uint64_t block_start = op;
+      uint64_t ip = 0;
+      for (;;) {
+        if (ip >= bsz) return DG_LZ4_SEQUENCE;
+        const uint8_t token = b[ip++];
+        uint64_t lit = token >> 4;
+        if (lit == 15) {
+          uint8_t s;
+          do { if (ip >= bsz) return DG_LZ4_SEQUENCE; s = b[ip++]; lit += s; } while (s == 255);
+        }
+        if (lit > bsz - ip) return DG_LZ4_SEQUENCE;
+        if (op - block_start + lit > max_block) return DG_LZ4_TOO_LARGE;
+        if (out) { if (op + lit > out_cap) return DG_LZ4_TOO_LARGE; for (uint64_t k = 0; k < lit; ++k) out[op + k] = b[ip + k]; }
+        op += lit; ip += lit;
+        if (ip == bsz) break;   // the last sequence carries literals only
+        if (ip + 2 > bsz) return DG_LZ4_SEQUENCE;
+        const uint32_t off = b[ip] | ((uint32_t)b[ip + 1] << 8); ip += 2;
+        uint64_t mlen = token & 15;
+        if (mlen == 15) {
+          uint8_t s;
+          do { if (ip >= bsz) return DG_LZ4_SEQUENCE; s = b[ip++]; mlen += s; } while (s == 255);
+        }
+        mlen += 4;
+        if (off == 0 || off > op) return DG_LZ4_SEQUENCE;   // matches may reach back across blocks, never before the frame
+        if (op - block_start + mlen > max_block) return DG_LZ4_TOO_LARGE;
+        if (out) {
+          if (op + mlen > out_cap) return DG_LZ4_TOO_LARGE;
+          for (uint64_t k = 0; k < mlen; ++k) out[op + k] = out[op + k - off];   // overlapping matches replicate, byte by byte
+        }
+        op += mlen;
+      }
+    }
+    pos += bsz + (block_checksum ? 4 : 0);
+  }
+  if (content_checksum) {
+    if (pos + 4 > n) return DG_LZ4_BLOCK;
+    if (out && xxh32_dev(out, op, 0) != rd32le(src + pos)) return DG_LZ4_CHECKSUM;
+    pos += 4;
+  }
+  if (content_size && declared != op) return DG_LZ4_BLOCK;
+  *out_len = op;
+  return DG_OK;
+}
+
+__global__ void __launch_bounds__(kThreads) dg_crc_size_kernel(const uint8_t* __restrict__ wire, DgBatch* __restrict__ batches, uint32_t n) {
+  __shared__ uint32_t tab[8][256];
+  for (int i = threadIdx.x; i < 8 * 256; i += kThreads) (&tab[0][0])[i] = (&g_crc_tab[0][0])[i];
+  __syncthreads();
+  const uint32_t i = blockIdx.x * kThreads + threadIdx.x;
+  if (i >= n) return;
+  DgBatch bt = batches[i];
+  const uint8_t* b = wire + bt.src_off;
+  uint32_t err = DG_OK, dsize = bt.total_len - 61u;
+  if (crc32c_dev(tab, b + 21, (uint64_t)bt.total_len - 21) != bt.stored_crc) err = DG_CRC;
+  else if (bt.codec == 3) {
+    uint64_t len = 0;
+    err = lz4_frame(b + 61, (uint64_t)bt.total_len - 61, nullptr, 0, &len);
+    if (!err && len > 0xffffffffull) err = DG_LZ4_TOO_LARGE;
+    dsize = (uint32_t)len;
+  }
+  if (!err && (uint64_t)bt.n_records > (uint64_t)dsize / 7 + 1) err = DG_RECORD_COUNT;   // every record is at least 7 bytes on the wire
+  batches[i].dsize = dsize;
+  batches[i].err = err;
+  batches[i].err_record = 0;
+}
+
+struct Cur {   // zig-zag varints of org.apache.kafka.common.utils.ByteUtils over a byte range
+  const uint8_t* p; uint64_t n, pos; bool ok;
+  __device__ Cur(const uint8_t* p_, uint64_t n_) : p(p_), n(n_), pos(0), ok(true) {}
+  __device__ int64_t varlong() {
+    unsigned long long v = 0; int shift = 0;
+    for (int i = 0; i < 10; ++i) {
+      if (pos >= n) { ok = false; return 0; }
+      const uint8_t b = p[pos++];
+      v |= (unsigned long long)(b & 0x7f) << shift;
+      if (!(b & 0x80)) return (int64_t)(v >> 1) ^ -(int64_t)(v & 1);
+      shift += 7;
+    }
+    ok = false; return 0;
+  }
+  __device__ int32_t varint() {
+    uint32_t v = 0; int shift = 0;
+    for (int i = 0; i < 5; ++i) {
+      if (pos >= n) { ok = false; return 0; }
+      const uint8_t b = p[pos++];
+      v |= (uint32_t)(b & 0x7f) << shift;
+      if (!(b & 0x80)) return (int32_t)(v >> 1) ^ -(int32_t)(v & 1);
+      shift += 7;
+    }
+    ok = false; return 0;
+  }
+  __device__ const uint8_t* bytes(uint64_t k) {
+    if (k > n - pos) { ok = false; return nullptr; }
+    const uint8_t* r = p + pos; pos += k; return r;
+  }
+};
+
+__global__ void __launch_bounds__(kThreads) dg_decode_walk_kernel(const uint8_t* __restrict__ wire, uint8_t* __restrict__ arena, DgBatch* __restrict__ batches,
+                                                                  uint32_t n, uint32_t* __restrict__ rec_off, uint32_t* __restrict__ rec_batch) {
+  const uint32_t i = blockIdx.x * kThreads + threadIdx.x;
+  if (i >= n) return;
+  DgBatch bt = batches[i];
+  if (bt.err) return;
+  const uint8_t* sect = wire + bt.src_off + 61;
+  uint64_t sect_len = (uint64_t)bt.total_len - 61;
+  if (bt.codec == 3) {
+    uint64_t len = 0;
+    const uint32_t e = lz4_frame(sect, sect_len, arena + bt.arena_off, bt.dsize, &len);
+    if (e || len != bt.dsize) { batches[i].err = e ? e : DG_LZ4_BLOCK; return; }
+    sect = arena + bt.arena_off; sect_len = len;
+  }
+  Cur c(sect, sect_len);
+  for (uint32_t r = 0; r < bt.n_records; ++r) {
+    const uint64_t at = c.pos;
+    const int32_t len = c.varint();
+    if (!c.ok || len < 0 || (uint64_t)len > sect_len - c.pos) { batches[i].err = DG_RECORD_LENGTH; batches[i].err_record = r; return; }
+    rec_off[bt.rec_base + r] = (uint32_t)at;
+    rec_batch[bt.rec_base + r] = i;
+    c.pos += (uint64_t)len;
+  }
+  if (c.pos != sect_len) { batches[i].err = DG_STRAY_BYTES; batches[i].err_record = bt.n_records; }
+}
+
+__device__ __forceinline__ unsigned long long hash_id(const uint8_t* k, uint32_t len) {
+  unsigned long long h = 0x9e3779b97f4a7c15ull ^ ((unsigned long long)len * 0xff51afd7ed558ccdull);
+  while (len >= 8) {
+    unsigned long long w = 0;
+    for (int q = 7; q >= 0; --q) w = (w << 8) | k[q];
+    h = (h ^ w) * 0x9fb21c651e98df25ull; h ^= h >> 32; k += 8; len -= 8;
+  }
+  if (len) {
+    unsigned long long w = 0;
+    for (int q = (int)len - 1; q >= 0; --q) w = (w << 8) | k[q];
+    h = (h ^ w) * 0x9fb21c651e98df25ull; h ^= h >> 32;
+  }
+  h *= 0xc4ceb9fe1a85ec53ull; h ^= h >> 29;
+  return h ? h : 1ull;
+}
+
+__device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+
+// id -> dense index. Returns 0xffffffff when the dictionary is full (the call then fails as a whole).
+__device__ uint32_t intern(const DgDict& d, const uint8_t* id, uint32_t len) {
+  const unsigned long long h = hash_id(id, len);
+  uint64_t pos = h & d.slots_mask;
+  for (uint64_t probes = 0; probes <= d.slots_mask; ++probes, pos = (pos + 1) & d.slots_mask) {
+    unsigned long long tag = __ldcg(d.tags + pos);
+    if (tag == 0ull) {
+      tag = atomicCAS(d.tags + pos, 0ull, h);
+      if (tag == 0ull) {   // this thread owns the slot: the id is new
+        const unsigned long long idx = atomicAdd(d.ctl + 0, 1ull);
+        const unsigned long long need = ((unsigned long long)len + 7) & ~7ull;
+        const unsigned long long off = atomicAdd(d.ctl + 1, need);
+        if (idx >= d.max_keys || off + need > d.arena_cap) {
+          atomicAdd(d.ctl + 5, 1ull);
+          __threadfence();
+          atomicExch(d.slot_idx + pos, 0xffffffffu);
+          return 0xffffffffu;
+        }
+        for (uint32_t k = 0; k < len; ++k) d.arena[off + k] = id[k];
+        d.key_ref[idx] = make_uint2((uint32_t)(off >> 3), len);
+        __threadfence();
+        atomicExch(d.slot_idx + pos, (uint32_t)idx + 1u);
+        return (uint32_t)idx;
+      }
+    }
+    if (tag != h) continue;
+    uint32_t v;
+    while ((v = ld_volatile_u32(d.slot_idx + pos)) == 0u) __nanosleep(40);   // the owner is still writing the id
+    if (v == 0xffffffffu) return 0xffffffffu;
+    __threadfence();
+    // (L2 loads: an L1 line fetched before the owner wrote its part would be stale)
+    const uint2 ref = __ldcg(d.key_ref + (v - 1u));
+    if (ref.y != len) continue;                                               // same 64-bit hash, another id: keep probing
+    const uint8_t* have = d.arena + ((unsigned long long)ref.x << 3);
+    bool same = true;
+    for (uint32_t k = 0; k < len && same; ++k) same = __ldcg(have + k) == id[k];
+    if (same) return v - 1u;
+  }
+  atomicAdd(d.ctl + 5, 1ull);
+  return 0xffffffffu;
+}
+
+__global__ void __launch_bounds__(kThreads) dg_parse_kernel(const __grid_constant__ DgParse p) {
+  const uint32_t i = blockIdx.x * kThreads + threadIdx.x;
+  if (i >= p.n_records) return;
+  uint4* out = reinterpret_cast<uint4*>(p.out + (size_t)i * 64);
+  const uint4 zero = make_uint4(0, 0, 0, 0), hole = make_uint4(0, 0, 0xffffffffu, 0xffffffffu);
+  out[1] = zero; out[2] = zero; out[3] = zero;
+  out[0] = hole;
+  const uint32_t bi = p.rec_batch[i];
+  if (bi >= p.n_batches) return;    // a slot the walk never reached (its batch failed earlier)
+  DgBatch& bt = p.batches[bi];
+  if (bt.err) return;
+  const uint8_t* sect = bt.codec == 3 ? p.arena + bt.arena_off : p.wire + bt.src_off + 61;
+  const uint32_t r = i - bt.rec_base;
+  Cur c(sect + p.rec_off[i], (uint64_t)bt.dsize - p.rec_off[i]);
+  const int32_t rec_len = c.varint();
+  Cur q(sect + p.rec_off[i] + c.pos, (uint64_t)rec_len);   // the walk validated the length
+  q.bytes(1);                 // record attributes (unused in v2)
+  q.varlong();                // timestampDelta
+  const int32_t offset_delta = q.varint();
+  const int32_t key_len = q.varint();
+  const uint8_t* key = key_len > 0 ? q.bytes((uint64_t)key_len) : nullptr;
+  const int32_t val_len = q.varint();
+  const uint8_t* val = val_len > 0 ? q.bytes((uint64_t)val_len) : nullptr;
+  const int32_t n_headers = q.varint();
+  for (int32_t h = 0; q.ok && h < n_headers; ++h) {
+    const int32_t hk = q.varint(); if (hk < 0) { q.ok = false; break; } q.bytes((uint64_t)hk);
+    const int32_t hv = q.varint(); if (hv > 0) q.bytes((uint64_t)hv);
+  }
+  if (!q.ok || q.pos != q.n || n_headers < 0) { if (atomicCAS(&bt.err, 0u, (uint32_t)DG_RECORD_MALFORMED) == 0u) bt.err_record = r; return; }
+  if (bt.base_offset + offset_delta < bt.min_offset) { atomicAdd(p.dict.ctl + 4, 1ull); return; }      // refetch after a restart
+  if (key_len <= 0) { atomicAdd(p.dict.ctl + 2, 1ull); return; }                                        // the producer's flush record
+  if (val_len < 0 && p.null_value_type < 0) { atomicAdd(p.dict.ctl + 3, 1ull); return; }
+  if (val_len >= 0 && (val_len < 8 || val_len > 56)) { if (atomicCAS(&bt.err, 0u, (uint32_t)DG_VALUE_LENGTH) == 0u) bt.err_record = r; return; }
+  uint32_t id_len = (uint32_t)key_len;
+  for (uint32_t k = 0; k < (uint32_t)key_len; ++k) if (key[k] == ':') { id_len = k; break; }          // PartitionStringUpToColon
+  if (id_len >= (1u << 24)) { if (atomicCAS(&bt.err, 0u, (uint32_t)DG_ID_LENGTH) == 0u) bt.err_record = r; return; }
+  const uint32_t idx = intern(p.dict, key, id_len);
+  if (idx == 0xffffffffu) return;   // dictionary full: counted in ctl[5], the whole call fails
+  uint32_t w[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) w[k] = 0;
+  if (val_len < 0) { w[0] = (uint32_t)p.null_value_type; atomicAdd(p.dict.ctl + 3, 1ull); }
+  else {
+    w[0] = rd32le(val); w[1] = rd32le(val + 4);
+    uint8_t* pay = reinterpret_cast<uint8_t*>(w + 4);
+    for (int32_t k = 8; k < val_len; ++k) pay[k - 8] = val[k];
+  }
+  w[2] = idx; w[3] = 0;
+  out[0] = make_uint4(w[0], w[1], w[2], w[3]); out[1] = make_uint4(w[4], w[5], w[6], w[7]);
+  out[2] = make_uint4(w[8], w[9], w[10], w[11]); out[3] = make_uint4(w[12], w[13], w[14], w[15]);
+  atomicAdd(p.dict.ctl + 6, 1ull);
+}
+
+}  // namespace
+
+uint32_t dg_crc32c_host_reference_polynomial() { return 0x82F63B78u; }
+
+cudaError_t dg_launch_crc_size(const uint8_t* wire, DgBatch* batches, uint32_t n, cudaStream_t st) {
+  cudaError_t e = ensure_crc_tables();
+  if (e != cudaSuccess || !n) return e;
+  dg_crc_size_kernel<<<(n + kThreads - 1) / kThreads, kThreads, 0, st>>>(wire, batches, n);
+  return cudaGetLastError();
+}
+
+cudaError_t dg_launch_decode_walk(const uint8_t* wire, uint8_t* arena, DgBatch* batches, uint32_t n, uint32_t* rec_off, uint32_t* rec_batch, cudaStream_t st) {
+  if (!n) return cudaSuccess;
+  dg_decode_walk_kernel<<<(n + kThreads - 1) / kThreads, kThreads, 0, st>>>(wire, arena, batches, n, rec_off, rec_batch);
+  return cudaGetLastError();
+}
+
+cudaError_t dg_launch_parse(const DgParse& p, cudaStream_t st) {
+  if (!p.n_records) return cudaSuccess;
+  dg_parse_kernel<<<(p.n_records + kThreads - 1) / kThreads, kThreads, 0, st>>>(p);
+  return cudaGetLastError();
+}
+
+}  // namespace sgr

@@ -127,7 +127,7 @@ struct sgr_engine {
   std::mutex keys_mu;
   std::vector<uint8_t> ing_key_bytes;
   std::vector<uint32_t> ing_key_offs;
-  const sgr_ingest* ing_keys_from = nullptr;
+  const void* ing_keys_from = nullptr;      // whose dictionary the appended ids mirror (an sgr_ingest or an sgr_dingest)
   std::atomic<bool> keys_stale{false};
   // Every call that changes the engine (loads, folds, table growth) and the snapshot refresh of a reader hold op_mu:
   // a reader never sees a table being freed or swapped, and a snapshot is only marked clean for the generation it copied.
@@ -836,6 +836,34 @@ int32_t sgr_grow_states(sgr_engine* e, uint64_t n_agg) {
 static void* pinned_alloc(size_t n) { void* p = nullptr; return cudaHostAlloc(&p, n, cudaHostAllocPortable) == cudaSuccess ? p : nullptr; }
 static void pinned_free(void* p) { cudaFreeHost(p); }
 
+// the key table follows an append-only id dictionary kept elsewhere (host ingest, device ingest): ids [have, n_keys) are appended,
+// the hash index is rebuilt lazily by the first sgr_get that follows (a restore polls thousands of times before anybody reads)
+static int32_t sgr_append_keys_upto(sgr_engine* e, const void* owner, const uint8_t* keys, const uint32_t* key_offsets, uint64_t n_keys) {
+  std::lock_guard<std::mutex> lk(e->keys_mu);
+  if (e->ing_keys_from != owner) { e->ing_keys_from = owner; e->ing_key_bytes.clear(); e->ing_key_offs.assign(1, 0u); }
+  const uint64_t have = e->ing_key_offs.size() - 1;
+  if (n_keys > have) {
+    e->ing_key_bytes.insert(e->ing_key_bytes.end(), keys + key_offsets[have], keys + key_offsets[n_keys]);
+    const uint32_t shift = e->ing_key_offs.back() - key_offsets[have];
+    for (uint64_t i = have + 1; i <= n_keys; ++i) e->ing_key_offs.push_back(key_offsets[i] + shift);
+    e->keys_stale.store(true, std::memory_order_release);
+  }
+  return SGR_OK;
+}
+
+int32_t sgr_append_keys(sgr_engine* e, const void* owner, const uint8_t* keys, const uint32_t* key_offsets, uint64_t n_new) {
+  if (!e || !key_offsets || (!keys && n_new && key_offsets[n_new])) return fail(e, SGR_ERR_INVALID, "null argument");
+  std::lock_guard<std::mutex> lk(e->keys_mu);
+  if (e->ing_keys_from != owner) { e->ing_keys_from = owner; e->ing_key_bytes.clear(); e->ing_key_offs.assign(1, 0u); }
+  if (n_new) {
+    e->ing_key_bytes.insert(e->ing_key_bytes.end(), keys + key_offsets[0], keys + key_offsets[n_new]);
+    const uint32_t shift = e->ing_key_offs.back() - key_offsets[0];
+    for (uint64_t i = 1; i <= n_new; ++i) e->ing_key_offs.push_back(key_offsets[i] + shift);
+    e->keys_stale.store(true, std::memory_order_release);
+  }
+  return SGR_OK;
+}
+
 int32_t sgr_fold_ingested(sgr_engine* e, sgr_ingest* g) {
   OpLock op_lock(e);
   if (!e || !g) return fail(e, SGR_ERR_INVALID, "null argument");
@@ -854,16 +882,7 @@ int32_t sgr_fold_ingested(sgr_engine* e, sgr_ingest* g) {
     int32_t rc = sgr_grow_states(e, cap); if (rc) return rc;
   }
   if (n_records) { int32_t rc = sgr_fold_incremental(e, recs, n_records); if (rc) return rc; }
-  {
-    std::lock_guard<std::mutex> lk(e->keys_mu);
-    if (e->ing_keys_from != g) { e->ing_keys_from = g; e->ing_key_bytes.clear(); e->ing_key_offs.assign(1, 0u); }
-    const uint64_t have = e->ing_key_offs.size() - 1;
-    if (n_keys > have) {
-      e->ing_key_bytes.insert(e->ing_key_bytes.end(), keys + key_offsets[have], keys + key_offsets[n_keys]);
-      e->ing_key_offs.insert(e->ing_key_offs.end(), key_offsets + have + 1, key_offsets + n_keys + 1);
-      e->keys_stale.store(true, std::memory_order_release);
-    }
-  }
+  if (n_keys) { int32_t rc = sgr_append_keys_upto(e, g, keys, key_offsets, n_keys); if (rc) return rc; }
   sgr_ingest_mark_folded(g);
   return SGR_OK;
 }

@@ -108,6 +108,7 @@ __global__ void __launch_bounds__(256) inc_fused_kernel(const __grid_constant__ 
     for (uint64_t i = tid; i < a.n; i += nthreads) {
       const uint8_t* r = a.rec + i * 64;
       const unsigned long long slot = *reinterpret_cast<const unsigned long long*>(r + 8);
+      if (slot == ~0ull) continue;   // hole left by the device decode
       if (slot >= a.n_slots) { atomicAdd(a.counters + 4, 1ull); continue; }
       uint32_t* sw = reinterpret_cast<uint32_t*>(a.scr + slot);
       unsigned long long* s64 = reinterpret_cast<unsigned long long*>(sw + 2);
@@ -160,7 +161,8 @@ __global__ void __launch_bounds__(256) inc_fused_kernel(const __grid_constant__ 
   for (uint64_t i = tid; i < a.n; i += nthreads) {
     const uint8_t* r = a.rec + i * 64;
     const unsigned long long slot = *reinterpret_cast<const unsigned long long*>(r + 8);
-    if (slot >= a.n_slots) { atomicAdd(a.counters + 4, 1ull); continue; }
+    if (slot == ~0ull) continue;   // hole left by the device decode
+      if (slot >= a.n_slots) { atomicAdd(a.counters + 4, 1ull); continue; }
     Scratch* s = a.scr + slot;
     uint32_t fl, mode[W], val[W];
     atomicMax(&s->last_event, (uint32_t)i + 1);
@@ -175,6 +177,7 @@ __global__ void __launch_bounds__(256) inc_fused_kernel(const __grid_constant__ 
     for (uint64_t i = tid; i < a.n; i += nthreads) {
       const uint8_t* r = a.rec + i * 64;
       const unsigned long long slot = *reinterpret_cast<const unsigned long long*>(r + 8);
+      if (slot == ~0ull) continue;   // hole left by the device decode
       Scratch* s = a.scr + slot;
       uint32_t fl, mode[W], val[W];
       if (!decode(tab, pg, r, &fl, mode, val)) continue;

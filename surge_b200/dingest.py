@@ -1,0 +1,82 @@
+"""DeviceIngest: Kafka RecordBatch bytes -> folded state table with the decode ON THE GPU (include/sgr.h "device ingest").
+
+The same input and the same outcome as Ingest + ReplayEngine.fold_ingested (surge_b200/ingest.py), but only the wire bytes cross
+PCIe: CRC-32C, lz4, record parsing, id interning and the fold run on the engine's device (csrc/dingest_kernels.cu). The host
+walks batch headers and keeps the read_committed bookkeeping of the consumer the reference configures
+(modules/common/src/main/scala/surge/kafka/streams/SurgeStateStoreConsumer.scala:38).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Sequence, Tuple
+
+import numpy as np
+
+from . import native as N
+from .ingest import IngestError, _as_pointer
+
+
+class DeviceIngest:
+    def __init__(self, engine, max_keys: int, max_id_bytes: int = 0):
+        self._lib = N.load_library()
+        self._engine = engine
+        self._h = C.c_void_p()
+        rc = self._lib.sgr_dingest_create(engine._h, int(max_keys), int(max_id_bytes), C.byref(self._h))
+        if rc != N.SGR_OK:
+            raise IngestError(rc, "sgr_dingest_create failed")
+        self._keep = []   # submitted buffers stay alive until the fold (the H2D copy may be asynchronous)
+
+    def close(self) -> None:
+        if self._h:
+            self._lib.sgr_dingest_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, rc: int) -> None:
+        if rc != N.SGR_OK:
+            msg = self._lib.sgr_dingest_last_error(self._h)
+            raise IngestError(rc, msg.decode("utf-8", "replace") if msg else "")
+
+    @staticmethod
+    def _stats(st) -> Dict[str, int]:
+        return {n: int(getattr(st, n)) for n, _ in N.sgr_ingest_stats._fields_ if n != "reserved"}
+
+    def set_null_value_type(self, event_type: int) -> None:
+        self._check(self._lib.sgr_dingest_set_null_value_type(self._h, event_type))
+
+    def set_aborted(self, partition: int, aborted: Sequence[Tuple[int, int]]) -> None:
+        if not aborted:
+            return
+        pids = np.asarray([a[0] for a in aborted], dtype=np.int64)
+        offs = np.asarray([a[1] for a in aborted], dtype=np.int64)
+        self._check(self._lib.sgr_dingest_set_aborted(self._h, partition, pids.ctypes.data, offs.ctypes.data, len(aborted)))
+
+    def submit(self, partition: int, data) -> Dict[str, int]:
+        """bytes of one fetch response (bytes, numpy uint8 array, or a pinned torch uint8 tensor): header walk + H2D copy."""
+        st = N.sgr_ingest_stats()
+        if hasattr(data, "data_ptr"):
+            ptr, n = C.c_void_p(data.data_ptr()), int(data.numel())
+        else:
+            ptr, n = _as_pointer(data), len(data)
+        self._keep.append(data)
+        self._check(self._lib.sgr_dingest_submit(self._h, partition, ptr, n, C.byref(st)))
+        return self._stats(st)
+
+    def fold(self) -> Dict[str, int]:
+        """decode + intern + fold everything submitted since the last fold; returns the poll's statistics."""
+        st = N.sgr_ingest_stats()
+        try:
+            self._check(self._lib.sgr_dingest_fold(self._h, C.byref(st)))
+        finally:
+            self._keep = []
+        return self._stats(st)
+
+    def offsets(self, partition: int) -> Tuple[int, int]:
+        d, f = C.c_int64(), C.c_int64()
+        self._check(self._lib.sgr_dingest_offsets(self._h, partition, C.byref(d), C.byref(f)))
+        return d.value, f.value

@@ -152,6 +152,16 @@ ABI = [
     ("sgr_ingest_mark_folded", C.c_int32, [_P]),
     ("sgr_ingest_offsets", C.c_int32, [_P, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     ("sgr_ingest_get_stats", C.c_int32, [_P, C.POINTER(sgr_ingest_stats)]),
+    ("sgr_append_keys", C.c_int32, [_P, _P, _P, _P, C.c_uint64]),
+    ("sgr_dingest_create", C.c_int32, [_P, C.c_uint64, C.c_uint64, C.POINTER(C.c_void_p)]),
+    ("sgr_dingest_destroy", C.c_int32, [_P]),
+    ("sgr_dingest_last_error", C.c_char_p, [_P]),
+    ("sgr_dingest_set_null_value_type", C.c_int32, [_P, C.c_int32]),
+    ("sgr_dingest_set_aborted", C.c_int32, [_P, C.c_int32, _P, _P, C.c_uint64]),
+    ("sgr_dingest_submit", C.c_int32, [_P, C.c_int32, _P, C.c_uint64, _P]),
+    ("sgr_dingest_fold", C.c_int32, [_P, _P]),
+    ("sgr_dingest_offsets", C.c_int32, [_P, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    ("sgr_dingest_get_stats", C.c_int32, [_P, _P]),
     ("sgr_grow_states", C.c_int32, [_P, C.c_uint64]),
     ("sgr_fold_ingested", C.c_int32, [_P, _P]),
     ("sgr_crc32c", C.c_uint32, [_P, C.c_uint64]),
