@@ -475,6 +475,12 @@ int32_t sgr_dingest_submit(sgr_dingest* g, int32_t partition, const void* data, 
  * the new ids to sgr_get, advance the partitions' positions. All or nothing. stats (optional): this poll's totals. */
 int32_t sgr_dingest_fold(sgr_dingest* g, sgr_ingest_stats* stats);
 int32_t sgr_dingest_offsets(sgr_dingest* g, int32_t partition, int64_t* decoded_next, int64_t* folded_next);
+/* Forget everything (dictionary, partition positions, statistics): the next poll starts a rebuild from offset 0 with dense
+ * indices from 0. The engine's table is the caller's to reset (sgr_set_initial_states(e, NULL, 0)). */
+int32_t sgr_dingest_reset(sgr_dingest* g);
+/* host-clock milliseconds of the last sgr_dingest_fold: [0] wait for the copies + CRC / lz4 size pass, [1] lz4 decode + record walk,
+ * [2] record parse + id interning, [3] new ids to the host key table, [4] table growth + fold, [5] the whole call */
+int32_t sgr_dingest_last_timing(sgr_dingest* g, float* ms8);
 int32_t sgr_dingest_get_stats(sgr_dingest* g, sgr_ingest_stats* out);
 
 /* building blocks, exported for the known-answer tests */

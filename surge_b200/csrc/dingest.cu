@@ -13,9 +13,11 @@
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <map>
 #include <string>
 #include <unordered_set>
@@ -69,17 +71,50 @@ struct sgr_dingest {
   int32_t null_value_type = -1;
   // staged submissions
   KeepBuf wire;
-  std::vector<DgBatch> batches;
+  // descriptors of the poll's data batches, in PAGE-LOCKED memory: every copy of them is a true asynchronous DMA (a copy from
+  // pageable memory makes the host wait for the stream, which serialised the submissions behind each other's CRC kernels)
+  struct PinnedBatches {
+    DgBatch* p = nullptr; size_t n = 0, cap = 0;
+    bool reserve(size_t want) {
+      if (want <= cap) return true;
+      size_t c = cap ? cap : 4096;
+      while (c < want) c *= 2;
+      DgBatch* np = nullptr;
+      if (cudaHostAlloc((void**)&np, c * sizeof(DgBatch), cudaHostAllocDefault) != cudaSuccess) return false;
+      if (n) memcpy(np, p, n * sizeof(DgBatch));
+      if (p) cudaFreeHost(p);
+      p = np; cap = c;
+      return true;
+    }
+    size_t size() const { return n; }
+    bool empty() const { return n == 0; }
+    void clear() { n = 0; }
+    DgBatch* data() { return p; }
+    DgBatch& operator[](size_t i) { return p[i]; }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; n = cap = 0; }
+  } batches;
   uint64_t n_record_slots = 0;
   sgr_ingest_stats poll{};                  // statistics of the current poll (host-side parts)
   sgr_ingest_stats total{};
+  struct Sub { uint32_t batch_begin, batch_end; uint64_t nbytes; cudaEvent_t copied; };
+  std::vector<Sub> subs;                    // the submissions of the current poll, in order
+  std::vector<cudaEvent_t> event_pool;
+  cudaStream_t copy_stream = nullptr;       // H2D copies of the wire bytes: they overlap the decode of earlier submissions
   // device scratch
-  DevBuf d_batches, arena, rec_off, rec_batch, out;
+  KeepBuf arena, d_batches;
+  uint64_t d_batches_used = 0;              // descriptors uploaded by the submissions of this poll
+  uint64_t crc_launched = 0;                // ... of which the CRC + size pass has been launched
+  DevBuf rec_off, rec_batch, out, key_offs_dev, key_bytes_dev;
+  void* h_keys = nullptr; uint64_t h_keys_cap = 0;   // page-locked landing area of the new ids
   // device dictionary
   DevBuf tags, slot_idx, key_ref, id_arena, ctl;
   uint64_t slots = 0, max_keys = 0, arena_cap = 0;
   uint64_t keys_on_host = 0;                // ids already appended to the engine's key table
+  uint64_t generation = 0;                  // bumped by sgr_dingest_reset: a new dictionary is a new owner of the engine's key table
   void* h_ctl = nullptr;                    // page-locked landing area
+  bool timing_syncs = false;                // SGR_DINGEST_TIMING=1: an extra synchronisation separates decode from parse in ms[]
+  float ms[8] = {};                         // last fold: [0] wait for H2D + crc/size [1] decode + walk [2] parse + intern [3] keys to host
+                                            //            [4] table growth + fold [5] total
 };
 
 namespace {
@@ -114,7 +149,9 @@ const char* dg_err_text(uint32_t e) {
 }
 
 void discard_poll(sgr_dingest* g) {
-  g->wire.used = 0; g->batches.clear(); g->n_record_slots = 0; g->staged = g->parts; g->poll = sgr_ingest_stats{};
+  if (g->copy_stream) cudaStreamSynchronize(g->copy_stream);   // no copy may still be landing in the buffer the next poll reuses
+  if (g->stream) cudaStreamSynchronize(g->stream);
+  g->wire.used = 0; g->batches.clear(); g->n_record_slots = 0; g->staged = g->parts; g->poll = sgr_ingest_stats{}; g->subs.clear(); g->d_batches_used = 0; g->crc_launched = 0;
 }
 }  // namespace
 
@@ -127,6 +164,8 @@ int32_t sgr_dingest_create(sgr_engine* e, uint64_t max_keys, uint64_t max_id_byt
   if (sgr_stream(e, &st) != SGR_OK) return SGR_ERR_INVALID;
   sgr_dingest* g = new sgr_dingest();
   g->eng = e; g->stream = (cudaStream_t)st;
+  g->timing_syncs = getenv("SGR_DINGEST_TIMING") != nullptr;
+  if (cudaStreamCreateWithFlags(&g->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { delete g; return SGR_ERR_CUDA; }
   g->max_keys = max_keys;
   g->slots = 1024;
   while (g->slots < 2 * max_keys) g->slots *= 2;          // load factor <= 0.5
@@ -146,7 +185,12 @@ int32_t sgr_dingest_create(sgr_engine* e, uint64_t max_keys, uint64_t max_id_byt
 
 int32_t sgr_dingest_destroy(sgr_dingest* g) {
   if (!g) return SGR_OK;
-  g->wire.b.release(); g->d_batches.release(); g->arena.release(); g->rec_off.release(); g->rec_batch.release(); g->out.release();
+  if (g->copy_stream) { cudaStreamSynchronize(g->copy_stream); cudaStreamDestroy(g->copy_stream); }
+  for (cudaEvent_t ev : g->event_pool) cudaEventDestroy(ev);
+  if (g->h_keys) cudaFreeHost(g->h_keys);
+  g->batches.release();
+  g->wire.b.release(); g->d_batches.b.release(); g->arena.b.release(); g->rec_off.release(); g->rec_batch.release(); g->out.release();
+  g->key_offs_dev.release(); g->key_bytes_dev.release();
   g->tags.release(); g->slot_idx.release(); g->key_ref.release(); g->id_arena.release(); g->ctl.release();
   if (g->h_ctl) cudaFreeHost(g->h_ctl);
   delete g;
@@ -228,12 +272,48 @@ int32_t sgr_dingest_submit(sgr_dingest* g, int32_t partition, const void* data, 
   }
   st.n_bytes = pos; st.n_trailing_bytes = nbytes - pos;
   if (g->n_record_slots + slots >= (1ull << 32)) return dfail(g, SGR_ERR_CAPACITY, "more than 2^32 records in one poll");
+  sgr_dingest::Sub sub{};
+  sub.batch_begin = (uint32_t)g->batches.size(); sub.batch_end = sub.batch_begin + (uint32_t)add.size(); sub.nbytes = pos;
+  if (g->subs.size() >= g->event_pool.size()) {
+    cudaEvent_t ev;
+    DG_TRY(g, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    g->event_pool.push_back(ev);
+  }
+  sub.copied = g->event_pool[g->subs.size()];
   if (pos) {
-    DG_TRY(g, g->wire.ensure(pos + 16, g->stream));
-    DG_TRY(g, cudaMemcpyAsync((uint8_t*)g->wire.b.p + g->wire.used, buf, pos, cudaMemcpyHostToDevice, g->stream));
+    if (g->wire.used + pos + 16 > g->wire.b.cap) {   // the buffer moves: no copy may be in flight, no kernel reading it
+      DG_TRY(g, cudaStreamSynchronize(g->copy_stream));
+      DG_TRY(g, cudaStreamSynchronize(g->stream));
+    }
+    DG_TRY(g, g->wire.ensure(pos + 16, g->copy_stream));
+    DG_TRY(g, cudaMemcpyAsync((uint8_t*)g->wire.b.p + g->wire.used, buf, pos, cudaMemcpyHostToDevice, g->copy_stream));
     g->wire.used += (pos + 15) & ~15ull;
   }
-  g->batches.insert(g->batches.end(), add.begin(), add.end());
+  DG_TRY(g, cudaEventRecord(sub.copied, g->copy_stream));
+  g->subs.push_back(sub);
+  if (!add.empty()) {
+    if (g->batches.n + add.size() > g->batches.cap) {   // the pinned array moves: nothing may still be copying from / into it
+      DG_TRY(g, cudaStreamSynchronize(g->stream));
+      if (!g->batches.reserve(g->batches.n + add.size())) return dfail(g, SGR_ERR_OOM, "page-locked descriptor array");
+    }
+    memcpy(g->batches.p + g->batches.n, add.data(), add.size() * sizeof(DgBatch));
+    const DgBatch* src_desc = g->batches.p + g->batches.n;
+    g->batches.n += add.size();
+    // descriptors go up right away; the CRC + lz4 size pass is launched once >= 32 k batches are waiting (one thread per batch:
+    // a small launch takes as long as a large one, it is the serial walk of ONE batch) — it then runs while the host walks
+    // the next fetches and the copy engine brings them in; sgr_dingest_fold launches the remainder
+    if ((g->d_batches_used + add.size()) * sizeof(DgBatch) > g->d_batches.b.cap) DG_TRY(g, cudaStreamSynchronize(g->stream));
+    g->d_batches.used = g->d_batches_used * sizeof(DgBatch);
+    DG_TRY(g, g->d_batches.ensure(add.size() * sizeof(DgBatch) + 64, g->stream));
+    DgBatch* db = (DgBatch*)g->d_batches.b.p + g->d_batches_used;
+    DG_TRY(g, cudaMemcpyAsync(db, src_desc, add.size() * sizeof(DgBatch), cudaMemcpyHostToDevice, g->stream));
+    g->d_batches_used += add.size();
+    if (g->d_batches_used - g->crc_launched >= 32768) {
+      DG_TRY(g, cudaStreamWaitEvent(g->stream, sub.copied, 0));
+      DG_TRY(g, dg_launch_crc_size((const uint8_t*)g->wire.b.p, (DgBatch*)g->d_batches.b.p + g->crc_launched, (uint32_t)(g->d_batches_used - g->crc_launched), g->stream));
+      g->crc_launched = g->d_batches_used;
+    }
+  }
   g->n_record_slots += slots;
   g->staged[partition] = ps;
   sgr_ingest_stats& t = g->poll;
@@ -250,41 +330,54 @@ int32_t sgr_dingest_fold(sgr_dingest* g, sgr_ingest_stats* stats) {
   const uint32_t nrec = (uint32_t)g->n_record_slots;
   sgr_ingest_stats st = g->poll;
   unsigned long long* h = (unsigned long long*)g->h_ctl;
+  typedef std::chrono::steady_clock Clk;
+  const Clk::time_point t_begin = Clk::now();
+  Clk::time_point t_last = t_begin;
+  auto lap = [&](int i) { const Clk::time_point now = Clk::now(); g->ms[i] += std::chrono::duration<float, std::milli>(now - t_last).count(); t_last = now; };
+  memset(g->ms, 0, sizeof g->ms);
   if (nb) {
-    DG_TRY(g, g->d_batches.reserve((size_t)nb * sizeof(DgBatch)));
-    DG_TRY(g, cudaMemcpyAsync(g->d_batches.p, g->batches.data(), (size_t)nb * sizeof(DgBatch), cudaMemcpyHostToDevice, g->stream));
-    DG_TRY(g, dg_launch_crc_size((const uint8_t*)g->wire.b.p, (DgBatch*)g->d_batches.p, nb, g->stream));
-    DG_TRY(g, cudaMemcpyAsync(g->batches.data(), g->d_batches.p, (size_t)nb * sizeof(DgBatch), cudaMemcpyDeviceToHost, g->stream));
+    DG_TRY(g, g->rec_off.reserve((size_t)nrec * 4 + 64));
+    DG_TRY(g, g->rec_batch.reserve((size_t)nrec * 4 + 64));
+    DG_TRY(g, g->out.reserve((size_t)nrec * 64 + 64));
+    DG_TRY(g, cudaMemsetAsync(g->rec_batch.p, 0xff, (size_t)nrec * 4 + 4, g->stream));
+    // per-poll counters: [2] markers [3] null values [4] duplicates [6] records written; [0] keys / [1] arena persist
+    DG_TRY(g, cudaMemcpyAsync(h, g->ctl.p, 64, cudaMemcpyDeviceToHost, g->stream));
     DG_TRY(g, cudaStreamSynchronize(g->stream));
+    const unsigned long long keys_before = h[0];
+    h[2] = h[3] = h[4] = h[5] = h[6] = 0;
+    DG_TRY(g, cudaMemcpyAsync(g->ctl.p, h, 64, cudaMemcpyHostToDevice, g->stream));
+    DgParse p{};
+    p.batches = (DgBatch*)g->d_batches.b.p; p.n_batches = nb;
+    p.rec_off = (const uint32_t*)g->rec_off.p; p.rec_batch = (const uint32_t*)g->rec_batch.p; p.out = (uint8_t*)g->out.p; p.null_value_type = g->null_value_type;
+    p.dict.tags = (unsigned long long*)g->tags.p; p.dict.slot_idx = (uint32_t*)g->slot_idx.p; p.dict.key_ref = (uint2*)g->key_ref.p;
+    p.dict.arena = (uint8_t*)g->id_arena.p; p.dict.ctl = (unsigned long long*)g->ctl.p; p.dict.slots_mask = g->slots - 1;
+    p.dict.max_keys = g->max_keys; p.dict.arena_cap = g->arena_cap;
+    // ---- the CRC + lz4 size pass: most of it was launched by sgr_dingest_submit behind the copies; the rest now
+    if (g->crc_launched < nb) {
+      DG_TRY(g, cudaStreamWaitEvent(g->stream, g->subs.back().copied, 0));
+      DG_TRY(g, dg_launch_crc_size((const uint8_t*)g->wire.b.p, (DgBatch*)g->d_batches.b.p + g->crc_launched, (uint32_t)(nb - g->crc_launched), g->stream));
+      g->crc_launched = nb;
+    }
+    DG_TRY(g, cudaMemcpyAsync(g->batches.data(), g->d_batches.b.p, (size_t)nb * sizeof(DgBatch), cudaMemcpyDeviceToHost, g->stream));
+    DG_TRY(g, cudaStreamSynchronize(g->stream));
+    lap(0);
     uint64_t arena_need = 0;
     for (uint32_t i = 0; i < nb; ++i) {
       DgBatch& b = g->batches[i];
       if (b.err) { const int32_t rc = dfail(g, SGR_ERR_INVALID, "offset %lld: %s", (long long)b.base_offset, dg_err_text(b.err)); discard_poll(g); return rc; }
       if (b.codec == 3) { b.arena_off = arena_need; arena_need += ((uint64_t)b.dsize + 15) & ~15ull; st.n_decompressed_bytes += b.dsize; }
     }
-    DG_TRY(g, g->arena.reserve(arena_need + 64));
-    DG_TRY(g, g->rec_off.reserve((size_t)nrec * 4 + 64));
-    DG_TRY(g, g->rec_batch.reserve((size_t)nrec * 4 + 64));
-    DG_TRY(g, g->out.reserve((size_t)nrec * 64 + 64));
-    DG_TRY(g, cudaMemsetAsync(g->rec_batch.p, 0xff, (size_t)nrec * 4 + 4, g->stream));
-    DG_TRY(g, cudaMemcpyAsync(g->d_batches.p, g->batches.data(), (size_t)nb * sizeof(DgBatch), cudaMemcpyHostToDevice, g->stream));
-    DG_TRY(g, dg_launch_decode_walk((const uint8_t*)g->wire.b.p, (uint8_t*)g->arena.p, (DgBatch*)g->d_batches.p, nb, (uint32_t*)g->rec_off.p, (uint32_t*)g->rec_batch.p, g->stream));
-    // per-poll counters: [2] markers [3] null values [4] duplicates [6] records written; [0] keys / [1] arena / [5] overflow persist
-    DG_TRY(g, cudaMemcpyAsync(h, g->ctl.p, 64, cudaMemcpyDeviceToHost, g->stream));
-    DG_TRY(g, cudaStreamSynchronize(g->stream));
-    const unsigned long long keys_before = h[0], arena_before = h[1];
-    h[2] = h[3] = h[4] = h[5] = h[6] = 0;
-    DG_TRY(g, cudaMemcpyAsync(g->ctl.p, h, 64, cudaMemcpyHostToDevice, g->stream));
-    DgParse p{};
-    p.wire = (const uint8_t*)g->wire.b.p; p.arena = (const uint8_t*)g->arena.p; p.batches = (DgBatch*)g->d_batches.p; p.n_batches = nb; p.n_records = nrec;
-    p.rec_off = (const uint32_t*)g->rec_off.p; p.rec_batch = (const uint32_t*)g->rec_batch.p; p.out = (uint8_t*)g->out.p; p.null_value_type = g->null_value_type;
-    p.dict.tags = (unsigned long long*)g->tags.p; p.dict.slot_idx = (uint32_t*)g->slot_idx.p; p.dict.key_ref = (uint2*)g->key_ref.p;
-    p.dict.arena = (uint8_t*)g->id_arena.p; p.dict.ctl = (unsigned long long*)g->ctl.p; p.dict.slots_mask = g->slots - 1;
-    p.dict.max_keys = g->max_keys; p.dict.arena_cap = g->arena_cap;
+    g->arena.used = 0;
+    DG_TRY(g, g->arena.ensure(arena_need + 64, g->stream));
+    DG_TRY(g, cudaMemcpyAsync(g->d_batches.b.p, g->batches.data(), (size_t)nb * sizeof(DgBatch), cudaMemcpyHostToDevice, g->stream));
+    DG_TRY(g, dg_launch_decode_walk((const uint8_t*)g->wire.b.p, (uint8_t*)g->arena.b.p, (DgBatch*)g->d_batches.b.p, nb, 0, (uint32_t*)g->rec_off.p, (uint32_t*)g->rec_batch.p, g->stream));
+    if (g->timing_syncs) { DG_TRY(g, cudaStreamSynchronize(g->stream)); lap(1); }
+    p.wire = (const uint8_t*)g->wire.b.p; p.arena = (const uint8_t*)g->arena.b.p; p.rec_begin = 0; p.n_records = nrec;
     DG_TRY(g, dg_launch_parse(p, g->stream));
-    DG_TRY(g, cudaMemcpyAsync(g->batches.data(), g->d_batches.p, (size_t)nb * sizeof(DgBatch), cudaMemcpyDeviceToHost, g->stream));
+    DG_TRY(g, cudaMemcpyAsync(g->batches.data(), g->d_batches.b.p, (size_t)nb * sizeof(DgBatch), cudaMemcpyDeviceToHost, g->stream));
     DG_TRY(g, cudaMemcpyAsync(h, g->ctl.p, 64, cudaMemcpyDeviceToHost, g->stream));
     DG_TRY(g, cudaStreamSynchronize(g->stream));
+    lap(2);
     for (uint32_t i = 0; i < nb; ++i)
       if (g->batches[i].err) {
         const int32_t rc = dfail(g, SGR_ERR_INVALID, "offset %lld, record %u: %s", (long long)g->batches[i].base_offset, g->batches[i].err_record, dg_err_text(g->batches[i].err));
@@ -296,7 +389,6 @@ int32_t sgr_dingest_fold(sgr_dingest* g, sgr_ingest_stats* stats) {
       discard_poll(g); return rc;
     }
     st.n_markers = h[2]; st.n_null_values = h[3]; st.n_duplicates += h[4]; st.n_records = h[6]; st.n_new_keys = h[0] - keys_before;
-    (void)arena_before;
     // ---- grow the table for the new ids, hand their names to the engine's key table, fold
     const uint64_t n_keys = h[0];
     void* d_states = nullptr; uint64_t n_agg = 0; uint32_t sb = 0;
@@ -309,31 +401,45 @@ int32_t sgr_dingest_fold(sgr_dingest* g, sgr_ingest_stats* stats) {
       int32_t rc = sgr_grow_states(g->eng, cap);
       if (rc) { dfail(g, rc, "engine: %s", sgr_last_error(g->eng)); discard_poll(g); return rc; }
     }
+    lap(4);
     if (n_keys > g->keys_on_host) {
+      // the new ids, gathered on the device into dense-index order, land in page-locked memory in two copies
       const uint64_t add = n_keys - g->keys_on_host;
-      std::vector<uint2> refs(add);
-      DG_TRY(g, cudaMemcpyAsync(refs.data(), (uint2*)g->key_ref.p + g->keys_on_host, add * 8, cudaMemcpyDeviceToHost, g->stream));
-      std::vector<uint8_t> ar(h[1]);
-      DG_TRY(g, cudaMemcpyAsync(ar.data(), g->id_arena.p, h[1], cudaMemcpyDeviceToHost, g->stream));   // (whole arena: new ids are scattered in it)
-      DG_TRY(g, cudaStreamSynchronize(g->stream));
-      std::vector<uint8_t> bytes; std::vector<uint32_t> offs(add + 1, 0);
-      for (uint64_t i = 0; i < add; ++i) {
-        bytes.insert(bytes.end(), ar.data() + ((uint64_t)refs[i].x << 3), ar.data() + ((uint64_t)refs[i].x << 3) + refs[i].y);
-        offs[i + 1] = (uint32_t)bytes.size();
+      const uint64_t id_bytes_max = h[1];   // (an upper bound: the arena's total use)
+      DG_TRY(g, g->key_offs_dev.reserve((add + 2) * 4 + (2 * (add / 4096 + 2) + 4 * 4096) * 4));
+      DG_TRY(g, g->key_bytes_dev.reserve(id_bytes_max + 64));
+      uint32_t* d_offs = (uint32_t*)g->key_offs_dev.p;
+      uint32_t* d_tmp = d_offs + add + 2;
+      DG_TRY(g, dg_gather_keys(p.dict, g->keys_on_host, (uint32_t)add, d_offs, (uint8_t*)g->key_bytes_dev.p, d_tmp, g->stream));
+      if (g->h_keys_cap < (add + 2) * 4 + id_bytes_max + 64) {
+        if (g->h_keys) cudaFreeHost(g->h_keys);
+        g->h_keys = nullptr; g->h_keys_cap = 0;
+        const uint64_t want = 2 * ((add + 2) * 4 + id_bytes_max + 64);
+        DG_TRY(g, cudaHostAlloc(&g->h_keys, want, cudaHostAllocDefault));
+        g->h_keys_cap = want;
       }
-      int32_t rc = sgr_append_keys(g->eng, g, bytes.data(), offs.data(), add);
+      uint32_t* h_offs = (uint32_t*)g->h_keys;
+      uint8_t* h_bytes = (uint8_t*)g->h_keys + (add + 2) * 4;
+      DG_TRY(g, cudaMemcpyAsync(h_offs, d_offs, (add + 1) * 4, cudaMemcpyDeviceToHost, g->stream));
+      DG_TRY(g, cudaStreamSynchronize(g->stream));
+      DG_TRY(g, cudaMemcpyAsync(h_bytes, g->key_bytes_dev.p, h_offs[add], cudaMemcpyDeviceToHost, g->stream));
+      DG_TRY(g, cudaStreamSynchronize(g->stream));
+      int32_t rc = sgr_append_keys(g->eng, (const char*)g + g->generation, h_bytes, h_offs, add);
       if (rc) { dfail(g, rc, "engine: %s", sgr_last_error(g->eng)); discard_poll(g); return rc; }
       g->keys_on_host = n_keys;
     }
+    lap(3);
     if (nrec) {
       int32_t rc = sgr_fold_incremental_device(g->eng, g->out.p, nrec);
       if (rc) { dfail(g, rc, "engine: %s", sgr_last_error(g->eng)); discard_poll(g); return rc; }
     }
   }
+  lap(4);
+  g->ms[5] = std::chrono::duration<float, std::milli>(Clk::now() - t_begin).count();
   // ---- commit: the staged positions become the live ones and everything decoded is folded
   for (auto& kv : g->staged) { kv.second.folded_next = kv.second.decoded_next; }
   g->parts = g->staged;
-  g->wire.used = 0; g->batches.clear(); g->n_record_slots = 0; g->poll = sgr_ingest_stats{};
+  g->wire.used = 0; g->batches.clear(); g->n_record_slots = 0; g->poll = sgr_ingest_stats{}; g->subs.clear(); g->d_batches_used = 0; g->crc_launched = 0;
   sgr_ingest_stats& t = g->total;
   t.n_bytes += st.n_bytes; t.n_batches += st.n_batches; t.n_records += st.n_records; t.n_markers += st.n_markers; t.n_null_values += st.n_null_values;
   t.n_control_batches += st.n_control_batches; t.n_aborted_batches += st.n_aborted_batches; t.n_aborted_records += st.n_aborted_records;
@@ -342,11 +448,27 @@ int32_t sgr_dingest_fold(sgr_dingest* g, sgr_ingest_stats* stats) {
   return SGR_OK;
 }
 
+int32_t sgr_dingest_reset(sgr_dingest* g) {
+  if (!g) return SGR_ERR_INVALID;
+  discard_poll(g);
+  g->parts.clear(); g->staged.clear(); g->total = sgr_ingest_stats{}; g->keys_on_host = 0; ++g->generation;
+  DG_TRY(g, cudaMemsetAsync(g->tags.p, 0, g->slots * 8, g->stream));
+  DG_TRY(g, cudaMemsetAsync(g->slot_idx.p, 0, g->slots * 4, g->stream));
+  DG_TRY(g, cudaMemsetAsync(g->ctl.p, 0, 64, g->stream));
+  return SGR_OK;
+}
+
 int32_t sgr_dingest_offsets(sgr_dingest* g, int32_t partition, int64_t* decoded_next, int64_t* folded_next) {
   if (!g) return SGR_ERR_INVALID;
   auto it = g->parts.find(partition);
   if (decoded_next) *decoded_next = it == g->parts.end() ? 0 : it->second.decoded_next;
   if (folded_next) *folded_next = it == g->parts.end() ? 0 : it->second.folded_next;
+  return SGR_OK;
+}
+
+int32_t sgr_dingest_last_timing(sgr_dingest* g, float* ms8) {
+  if (!g || !ms8) return SGR_ERR_INVALID;
+  memcpy(ms8, g->ms, sizeof g->ms);
   return SGR_OK;
 }
 

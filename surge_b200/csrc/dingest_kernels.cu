@@ -23,6 +23,7 @@
 // byte work — no tensor cores anywhere.
 #include "dingest_kernels.cuh"
 
+#include <stdlib.h>
 #include <string.h>
 
 namespace sgr {
@@ -94,9 +95,37 @@ __device__ uint32_t xxh32_dev(const uint8_t* p, uint64_t len, uint32_t seed) {
   return h;
 }
 
+// dst[0..n) = src[0..n) for one thread, 4 bytes per memory instruction: aligned word stores, aligned word loads funnel-shifted
+// to the source's misalignment (a GPU has no unaligned accesses). The regions must not overlap within 8 bytes (the caller sends
+// close overlapping matches down the byte path). Byte-wise copies were the bulk of the decode: every byte access of every thread
+// is an L1 wavefront of its own.
+__device__ __forceinline__ void copy_words(uint8_t* dst, const uint8_t* src, uint64_t n) {
+  uint64_t k = 0;
+  while (k < n && ((uintptr_t)(dst + k) & 3)) { dst[k] = src[k]; ++k; }
+  if (n - k >= 4) {
+    const uint8_t* s = src + k;
+    const uint32_t mis = (uint32_t)((uintptr_t)s & 3);
+    const uint32_t* sw = reinterpret_cast<const uint32_t*>(s - mis);
+    uint32_t* dw = reinterpret_cast<uint32_t*>(dst + k);
+    const uint64_t words = (n - k) >> 2;
+    if (mis == 0) {
+      for (uint64_t w = 0; w < words; ++w) dw[w] = sw[w];
+    } else {
+      uint32_t lo = sw[0];
+      for (uint64_t w = 0; w < words; ++w) { const uint32_t hi = sw[w + 1]; dw[w] = __funnelshift_r(lo, hi, mis * 8); lo = hi; }
+    }
+    k += words << 2;
+  }
+  while (k < n) { dst[k] = src[k]; ++k; }
+}
+
 // LZ4 frame walk. out == nullptr: only the decoded size is computed (and everything validated except the content checksum).
 // Mirrors lz4_frame_decode of csrc/ingest.cpp decision for decision (same accept / reject behaviour).
-__device__ uint32_t lz4_frame(const uint8_t* src, uint64_t n, uint8_t* out, uint64_t out_cap, uint64_t* out_len) {
+// `lane`/`lanes`: every participating thread runs the SAME control flow over the same compressed bytes (broadcast loads) and copies
+// its share of every literal run and match (bytes lane, lane + lanes, ...): one thread (0, 1) for the size pass, a whole warp
+// (lane, 32) for the decode — 32 consecutive bytes per step, coalesced. An overlapping match (offset < length) repeats its last
+// `offset` bytes, so byte k of the match is byte (k mod offset) of that period: independent per byte, no serial dependency.
+__device__ uint32_t lz4_frame(const uint8_t* src, uint64_t n, uint8_t* out, uint64_t out_cap, uint64_t* out_len, uint32_t lane = 0, uint32_t lanes = 1) {
   if (n < 7) return DG_LZ4_HEADER;
   if (rd32le(src) != 0x184D2204u) return DG_LZ4_HEADER;
   const uint8_t flg = src[4], bd = src[5];
@@ -122,7 +151,11 @@ __device__ uint32_t lz4_frame(const uint8_t* src, uint64_t n, uint8_t* out, uint
     const uint8_t* b = src + pos;
     if (block_checksum && xxh32_dev(b, bsz, 0) != rd32le(b + bsz)) return DG_LZ4_CHECKSUM;
     if (stored) {
-      if (out) { if (op + bsz > out_cap) return DG_LZ4_TOO_LARGE; for (uint64_t k = 0; k < bsz; ++k) out[op + k] = b[k]; }
+      if (out) {
+        if (op + bsz > out_cap) return DG_LZ4_TOO_LARGE;
+        if (lanes == 1) copy_words(out + op, b, bsz);
+        else { for (uint64_t k = lane; k < bsz; k += lanes) out[op + k] = b[k]; __syncwarp(); }
+      }
       op += bsz;
     } else {
       const uint64_t block_start = op;
@@ -137,7 +170,11 @@ __device__ uint32_t lz4_frame(const uint8_t* src, uint64_t n, uint8_t* out, uint
         }
         if (lit > bsz - ip) return DG_LZ4_SEQUENCE;
         if (op - block_start + lit > max_block) return DG_LZ4_TOO_LARGE;
-        if (out) { if (op + lit > out_cap) return DG_LZ4_TOO_LARGE; for (uint64_t k = 0; k < lit; ++k) out[op + k] = b[ip + k]; }
+        if (out) {
+          if (op + lit > out_cap) return DG_LZ4_TOO_LARGE;
+          if (lanes == 1) copy_words(out + op, b + ip, lit);
+          else for (uint64_t k = lane; k < lit; k += lanes) out[op + k] = b[ip + k];
+        }
         op += lit; ip += lit;
         if (ip == bsz) break;   // the last sequence carries literals only
         if (ip + 2 > bsz) return DG_LZ4_SEQUENCE;
@@ -152,7 +189,15 @@ __device__ uint32_t lz4_frame(const uint8_t* src, uint64_t n, uint8_t* out, uint
         if (op - block_start + mlen > max_block) return DG_LZ4_TOO_LARGE;
         if (out) {
           if (op + mlen > out_cap) return DG_LZ4_TOO_LARGE;
-          for (uint64_t k = 0; k < mlen; ++k) out[op + k] = out[op + k - off];   // overlapping matches replicate, byte by byte
+          if (lanes > 1) __syncwarp();                                  // the literals (and earlier matches) this match may read
+          const uint8_t* period = out + op - off;
+          if (lanes == 1 && off >= 8) {
+            // a far match never reads a word it has not finished writing when copied in pieces of at most `off` bytes
+            for (uint64_t done = 0; done < mlen; done += off) copy_words(out + op + done, period + done, mlen - done < off ? mlen - done : off);
+          } else {
+            for (uint64_t k = lane; k < mlen; k += lanes) out[op + k] = period[off >= mlen ? k : k % off];
+          }
+          if (lanes > 1) __syncwarp();
         }
         op += mlen;
       }
@@ -161,6 +206,7 @@ __device__ uint32_t lz4_frame(const uint8_t* src, uint64_t n, uint8_t* out, uint
   }
   if (content_checksum) {
     if (pos + 4 > n) return DG_LZ4_BLOCK;
+    if (out && lanes > 1) __syncwarp();
     if (out && xxh32_dev(out, op, 0) != rd32le(src + pos)) return DG_LZ4_CHECKSUM;
     pos += 4;
   }
@@ -222,9 +268,15 @@ struct Cur {   // zig-zag varints of org.apache.kafka.common.utils.ByteUtils ove
   }
 };
 
+// one WARP per batch: cooperative lz4 copies, then the (serial) record-boundary walk run redundantly by all lanes — same loads,
+// broadcast — with the writes spread over the lanes
+template <int WARP>
 __global__ void __launch_bounds__(kThreads) dg_decode_walk_kernel(const uint8_t* __restrict__ wire, uint8_t* __restrict__ arena, DgBatch* __restrict__ batches,
-                                                                  uint32_t n, uint32_t* __restrict__ rec_off, uint32_t* __restrict__ rec_batch) {
-  const uint32_t i = blockIdx.x * kThreads + threadIdx.x;
+                                                                  uint32_t n, uint32_t index_base, uint32_t* __restrict__ rec_off, uint32_t* __restrict__ rec_batch) {
+  // WARP == 1: one warp per batch (cooperative copies); 0: one thread per batch (word-wise copies, 32x more batches in flight —
+  // measured faster on 16 KiB producer batches, where the token chain, not the copy width, is the latency)
+  const uint32_t i = WARP ? (blockIdx.x * kThreads + threadIdx.x) >> 5 : blockIdx.x * kThreads + threadIdx.x;
+  const uint32_t lane = WARP ? threadIdx.x & 31 : 0;
   if (i >= n) return;
   DgBatch bt = batches[i];
   if (bt.err) return;
@@ -232,20 +284,35 @@ __global__ void __launch_bounds__(kThreads) dg_decode_walk_kernel(const uint8_t*
   uint64_t sect_len = (uint64_t)bt.total_len - 61;
   if (bt.codec == 3) {
     uint64_t len = 0;
-    const uint32_t e = lz4_frame(sect, sect_len, arena + bt.arena_off, bt.dsize, &len);
-    if (e || len != bt.dsize) { batches[i].err = e ? e : DG_LZ4_BLOCK; return; }
+    const uint32_t e = lz4_frame(sect, sect_len, arena + bt.arena_off, bt.dsize, &len, lane, WARP ? 32 : 1);
+    if (WARP) __syncwarp();
+    if (e || len != bt.dsize) { if (lane == 0) batches[i].err = e ? e : DG_LZ4_BLOCK; return; }
     sect = arena + bt.arena_off; sect_len = len;
   }
   Cur c(sect, sect_len);
   for (uint32_t r = 0; r < bt.n_records; ++r) {
     const uint64_t at = c.pos;
     const int32_t len = c.varint();
-    if (!c.ok || len < 0 || (uint64_t)len > sect_len - c.pos) { batches[i].err = DG_RECORD_LENGTH; batches[i].err_record = r; return; }
-    rec_off[bt.rec_base + r] = (uint32_t)at;
-    rec_batch[bt.rec_base + r] = i;
+    if (!c.ok || len < 0 || (uint64_t)len > sect_len - c.pos) { if (lane == 0) { batches[i].err = DG_RECORD_LENGTH; batches[i].err_record = r; } return; }
+    if (!WARP || lane == (r & 31u)) { rec_off[bt.rec_base + r] = (uint32_t)at; rec_batch[bt.rec_base + r] = index_base + i; }
     c.pos += (uint64_t)len;
   }
-  if (c.pos != sect_len) { batches[i].err = DG_STRAY_BYTES; batches[i].err_record = bt.n_records; }
+  if (c.pos != sect_len && lane == 0) { batches[i].err = DG_STRAY_BYTES; batches[i].err_record = bt.n_records; }
+}
+
+// ---- new ids -> contiguous bytes in dense-index order, for the host key table (lengths, [scan outside], copy)
+__global__ void dg_key_lens_kernel(const uint2* __restrict__ key_ref, uint64_t from, uint32_t n, uint32_t* __restrict__ lens) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i <= n) lens[i] = i < n ? key_ref[from + i].y : 0u;
+}
+__global__ void dg_key_copy_kernel(const uint2* __restrict__ key_ref, const uint8_t* __restrict__ arena, uint64_t from, uint32_t n,
+                                   const uint32_t* __restrict__ offs, uint8_t* __restrict__ out) {
+  const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 3, part = threadIdx.x & 7;   // 8 lanes per id
+  if (i >= n) return;
+  const uint2 ref = key_ref[from + i];
+  const uint8_t* src = arena + ((unsigned long long)ref.x << 3);
+  uint8_t* dst = out + offs[i];
+  for (uint32_t k = part; k < ref.y; k += 8) dst[k] = src[k];
 }
 
 __device__ __forceinline__ unsigned long long hash_id(const uint8_t* k, uint32_t len) {
@@ -313,7 +380,7 @@ __device__ uint32_t intern(const DgDict& d, const uint8_t* id, uint32_t len) {
 }
 
 __global__ void __launch_bounds__(kThreads) dg_parse_kernel(const __grid_constant__ DgParse p) {
-  const uint32_t i = blockIdx.x * kThreads + threadIdx.x;
+  const uint32_t i = p.rec_begin + blockIdx.x * kThreads + threadIdx.x;
   if (i >= p.n_records) return;
   uint4* out = reinterpret_cast<uint4*>(p.out + (size_t)i * 64);
   const uint4 zero = make_uint4(0, 0, 0, 0), hole = make_uint4(0, 0, 0xffffffffu, 0xffffffffu);
@@ -362,7 +429,9 @@ __global__ void __launch_bounds__(kThreads) dg_parse_kernel(const __grid_constan
   w[2] = idx; w[3] = 0;
   out[0] = make_uint4(w[0], w[1], w[2], w[3]); out[1] = make_uint4(w[4], w[5], w[6], w[7]);
   out[2] = make_uint4(w[8], w[9], w[10], w[11]); out[3] = make_uint4(w[12], w[13], w[14], w[15]);
-  atomicAdd(p.dict.ctl + 6, 1ull);
+  // one atomic per converged group of lanes, not per record: 3e7 atomics on one address serialise in the L2
+  const uint32_t grp = __activemask();
+  if ((threadIdx.x & 31) == (uint32_t)(__ffs(grp) - 1)) atomicAdd(p.dict.ctl + 6, (unsigned long long)__popc(grp));
 }
 
 }  // namespace
@@ -376,15 +445,34 @@ cudaError_t dg_launch_crc_size(const uint8_t* wire, DgBatch* batches, uint32_t n
   return cudaGetLastError();
 }
 
-cudaError_t dg_launch_decode_walk(const uint8_t* wire, uint8_t* arena, DgBatch* batches, uint32_t n, uint32_t* rec_off, uint32_t* rec_batch, cudaStream_t st) {
+cudaError_t dg_launch_decode_walk(const uint8_t* wire, uint8_t* arena, DgBatch* batches, uint32_t n, uint32_t index_base, uint32_t* rec_off, uint32_t* rec_batch, cudaStream_t st) {
   if (!n) return cudaSuccess;
-  dg_decode_walk_kernel<<<(n + kThreads - 1) / kThreads, kThreads, 0, st>>>(wire, arena, batches, n, rec_off, rec_batch);
+  static const bool warp_mode = getenv("SGR_DINGEST_WARP_DECODE") != nullptr;
+  if (warp_mode) {
+    const uint32_t warps_per_block = kThreads / 32;
+    dg_decode_walk_kernel<1><<<(n + warps_per_block - 1) / warps_per_block, kThreads, 0, st>>>(wire, arena, batches, n, index_base, rec_off, rec_batch);
+  } else {
+    dg_decode_walk_kernel<0><<<(n + kThreads - 1) / kThreads, kThreads, 0, st>>>(wire, arena, batches, n, index_base, rec_off, rec_batch);
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t exclusive_scan_u32_public(const uint32_t* in, uint32_t* out, uint32_t n, uint32_t* tmp, cudaStream_t st);
+
+// ids [from, from + n) of the dictionary as contiguous bytes in dense-index order: d_offs[n + 1] (exclusive prefix of the lengths),
+// d_bytes. d_tmp: scratch of at least 2 * (n / 4096 + 2) + 4 * 4096 u32.
+cudaError_t dg_gather_keys(const DgDict& d, uint64_t from, uint32_t n, uint32_t* d_offs, uint8_t* d_bytes, uint32_t* d_tmp, cudaStream_t st) {
+  if (!n) return cudaSuccess;
+  dg_key_lens_kernel<<<(n + 1 + 255) / 256, 256, 0, st>>>(d.key_ref, from, n, d_offs);
+  cudaError_t e = exclusive_scan_u32_public(d_offs, d_offs, n + 1, d_tmp, st);
+  if (e != cudaSuccess) return e;
+  dg_key_copy_kernel<<<(uint32_t)(((uint64_t)n * 8 + 255) / 256), 256, 0, st>>>(d.key_ref, d.arena, from, n, d_offs, d_bytes);
   return cudaGetLastError();
 }
 
 cudaError_t dg_launch_parse(const DgParse& p, cudaStream_t st) {
-  if (!p.n_records) return cudaSuccess;
-  dg_parse_kernel<<<(p.n_records + kThreads - 1) / kThreads, kThreads, 0, st>>>(p);
+  if (p.n_records <= p.rec_begin) return cudaSuccess;
+  dg_parse_kernel<<<(p.n_records - p.rec_begin + kThreads - 1) / kThreads, kThreads, 0, st>>>(p);
   return cudaGetLastError();
 }
 

@@ -818,6 +818,15 @@ int32_t sgr_grow_states(sgr_engine* e, uint64_t n_agg) {
   rc = before_load(e); if (rc) return rc;
   if (e->states_valid && n_agg <= e->states_n) return SGR_OK;
   const size_t sb = e->program.state_bytes;
+  if (!e->states_valid && e->states.p && e->states.cap >= (size_t)n_agg * sb) {
+    // a table that was reset (sgr_set_initial_states(NULL)) and is large enough: all None, no reallocation, no device-wide
+    // synchronisation by cudaFree
+    CUDA_TRY(e, cudaMemsetAsync(e->states.p, 0, (size_t)n_agg * sb, e->stream));
+    e->states_n = n_agg; e->states_valid = true;
+    e->inc_atomic_prev_valid = false; e->inc_prev_n = 0;
+    mark_dirty(e);
+    return SGR_OK;
+  }
   struct Guard { DevBuf b; ~Guard() { b.release(); } } guard;   // frees the old table on success, the new one on failure
   DevBuf& nb = guard.b;
   CUDA_TRY(e, nb.reserve((size_t)n_agg * sb));

@@ -76,6 +76,16 @@ class DeviceIngest:
             self._keep = []
         return self._stats(st)
 
+    def last_timing(self) -> Dict[str, float]:
+        ms = (C.c_float * 8)()
+        self._check(self._lib.sgr_dingest_last_timing(self._h, ms))
+        return dict(zip(("wait_h2d_crc_size", "decode_walk", "parse_intern", "keys_to_host", "grow_fold", "total"), [float(x) for x in ms[:6]]))
+
+    def reset(self) -> None:
+        """Forget dictionary, positions and statistics: the next poll rebuilds from offset 0."""
+        self._keep = []
+        self._check(self._lib.sgr_dingest_reset(self._h))
+
     def offsets(self, partition: int) -> Tuple[int, int]:
         d, f = C.c_int64(), C.c_int64()
         self._check(self._lib.sgr_dingest_offsets(self._h, partition, C.byref(d), C.byref(f)))

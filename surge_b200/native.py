@@ -161,6 +161,8 @@ ABI = [
     ("sgr_dingest_submit", C.c_int32, [_P, C.c_int32, _P, C.c_uint64, _P]),
     ("sgr_dingest_fold", C.c_int32, [_P, _P]),
     ("sgr_dingest_offsets", C.c_int32, [_P, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    ("sgr_dingest_reset", C.c_int32, [_P]),
+    ("sgr_dingest_last_timing", C.c_int32, [_P, _P]),
     ("sgr_dingest_get_stats", C.c_int32, [_P, _P]),
     ("sgr_grow_states", C.c_int32, [_P, C.c_uint64]),
     ("sgr_fold_ingested", C.c_int32, [_P, _P]),
