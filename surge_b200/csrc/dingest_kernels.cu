@@ -54,6 +54,23 @@ cudaError_t ensure_crc_tables() {
   return e;
 }
 
+// A lone thread walking a byte stream pays one global access (hundreds of ns) per byte it looks at: the profile of the first
+// version (profiles/r02_dingest_launches.csv) shows the decode kernel taking ~10 ms whatever the number of batches — it is the
+// serial latency of ONE batch. ByteWin keeps the aligned 16-byte chunk around the cursor in registers: one load per 16 bytes of
+// tokens, lengths, offsets and varints instead of one per byte. (Buffers are padded so the chunk load never leaves them.)
+struct ByteWin {
+  const uint8_t* chunk;
+  uint4 w;
+  __device__ ByteWin() : chunk(nullptr), w(make_uint4(0, 0, 0, 0)) {}
+  __device__ __forceinline__ uint32_t at(const uint8_t* p) {
+    const uint8_t* c = reinterpret_cast<const uint8_t*>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)15);
+    if (c != chunk) { chunk = c; w = *reinterpret_cast<const uint4*>(c); }
+    const uint32_t i = (uint32_t)(reinterpret_cast<uintptr_t>(p) & 15);
+    const uint32_t word = (i & 8u) ? ((i & 4u) ? w.w : w.z) : ((i & 4u) ? w.y : w.x);
+    return (word >> ((i & 3u) * 8u)) & 0xffu;
+  }
+};
+
 __device__ __forceinline__ uint32_t rd32le(const uint8_t* p) { return p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
 
 __device__ uint32_t crc32c_dev(const uint32_t (*tab)[256], const uint8_t* p, uint64_t n) {
@@ -160,13 +177,14 @@ __device__ uint32_t lz4_frame(const uint8_t* src, uint64_t n, uint8_t* out, uint
     } else {
       const uint64_t block_start = op;
       uint64_t ip = 0;
+      ByteWin win;
       for (;;) {
         if (ip >= bsz) return DG_LZ4_SEQUENCE;
-        const uint8_t token = b[ip++];
+        const uint8_t token = (uint8_t)win.at(b + ip++);
         uint64_t lit = token >> 4;
         if (lit == 15) {
           uint8_t s;
-          do { if (ip >= bsz) return DG_LZ4_SEQUENCE; s = b[ip++]; lit += s; } while (s == 255);
+          do { if (ip >= bsz) return DG_LZ4_SEQUENCE; s = (uint8_t)win.at(b + ip++); lit += s; } while (s == 255);
         }
         if (lit > bsz - ip) return DG_LZ4_SEQUENCE;
         if (op - block_start + lit > max_block) return DG_LZ4_TOO_LARGE;
@@ -178,11 +196,11 @@ __device__ uint32_t lz4_frame(const uint8_t* src, uint64_t n, uint8_t* out, uint
         op += lit; ip += lit;
         if (ip == bsz) break;   // the last sequence carries literals only
         if (ip + 2 > bsz) return DG_LZ4_SEQUENCE;
-        const uint32_t off = b[ip] | ((uint32_t)b[ip + 1] << 8); ip += 2;
+        const uint32_t off = win.at(b + ip) | (win.at(b + ip + 1) << 8); ip += 2;
         uint64_t mlen = token & 15;
         if (mlen == 15) {
           uint8_t s;
-          do { if (ip >= bsz) return DG_LZ4_SEQUENCE; s = b[ip++]; mlen += s; } while (s == 255);
+          do { if (ip >= bsz) return DG_LZ4_SEQUENCE; s = (uint8_t)win.at(b + ip++); mlen += s; } while (s == 255);
         }
         mlen += 4;
         if (off == 0 || off > op) return DG_LZ4_SEQUENCE;   // matches may reach back across blocks, never before the frame
@@ -239,12 +257,13 @@ __global__ void __launch_bounds__(kThreads) dg_crc_size_kernel(const uint8_t* __
 
 struct Cur {   // zig-zag varints of org.apache.kafka.common.utils.ByteUtils over a byte range
   const uint8_t* p; uint64_t n, pos; bool ok;
+  ByteWin win;
   __device__ Cur(const uint8_t* p_, uint64_t n_) : p(p_), n(n_), pos(0), ok(true) {}
   __device__ int64_t varlong() {
     unsigned long long v = 0; int shift = 0;
     for (int i = 0; i < 10; ++i) {
       if (pos >= n) { ok = false; return 0; }
-      const uint8_t b = p[pos++];
+      const uint8_t b = (uint8_t)win.at(p + pos++);
       v |= (unsigned long long)(b & 0x7f) << shift;
       if (!(b & 0x80)) return (int64_t)(v >> 1) ^ -(int64_t)(v & 1);
       shift += 7;
@@ -255,7 +274,7 @@ struct Cur {   // zig-zag varints of org.apache.kafka.common.utils.ByteUtils ove
     uint32_t v = 0; int shift = 0;
     for (int i = 0; i < 5; ++i) {
       if (pos >= n) { ok = false; return 0; }
-      const uint8_t b = p[pos++];
+      const uint8_t b = (uint8_t)win.at(p + pos++);
       v |= (uint32_t)(b & 0x7f) << shift;
       if (!(b & 0x80)) return (int32_t)(v >> 1) ^ -(int32_t)(v & 1);
       shift += 7;

@@ -140,8 +140,10 @@ __global__ void __launch_bounds__(kThreads) radix_scatter_kernel(const uint32_t*
   const uint32_t tile0 = blockIdx.x * kTile;
   const uint32_t start = tile0 + warp * kPerWarp;
   uint32_t key[kRounds];
+  uint16_t pre[kRounds];   // keys with the same digit in this warp's earlier rounds + in lower lanes of this round
   const uint32_t lt = (1u << lane) - 1u;
-  // phase 1: this warp's digit counts
+  // phase 1: this warp's digit counts, and every key's rank among the warp's keys of its digit — ONE match per key: the second
+  // MATCH.ANY of the placement phase (r01: 32 per warp and tile, the kernel's main cost) is replaced by a register
 #pragma unroll
   for (int r = 0; r < kRounds; ++r) {
     const uint32_t i = start + r * 32 + lane;
@@ -149,7 +151,10 @@ __global__ void __launch_bounds__(kThreads) radix_scatter_kernel(const uint32_t*
     key[r] = valid ? keys_in[i] : 0u;
     const uint32_t d = (key[r] >> shift) & 255u;
     const uint32_t m = match_digit(d, valid);
-    if (valid && (m & lt) == 0) wh[warp][d] += __popc(m);
+    const uint32_t earlier = valid ? wh[warp][d] : 0u;    // read by every lane of the digit before its leader adds this round
+    pre[r] = (uint16_t)(earlier + __popc(m & lt));
+    __syncwarp();
+    if (valid && (m & lt) == 0) wh[warp][d] = earlier + __popc(m);
     __syncwarp();
   }
   __syncthreads();
@@ -170,15 +175,10 @@ __global__ void __launch_bounds__(kThreads) radix_scatter_kernel(const uint32_t*
 #pragma unroll
   for (int r = 0; r < kRounds; ++r) {
     const uint32_t i = start + r * 32 + lane;
-    const bool valid = i < n;
-    const uint32_t d = (key[r] >> shift) & 255u;
-    const uint32_t m = match_digit(d, valid);
-    uint32_t pos = 0;
-    if (valid) pos = wh[warp][d] + __popc(m & lt);
-    __syncwarp();
-    if (valid && (m & lt) == 0) wh[warp][d] += __popc(m);
-    __syncwarp();
-    if (valid) { skey[pos] = key[r]; sidx[pos] = idx_in ? idx_in[i] : i; }
+    if (i < n) {
+      const uint32_t pos = wh[warp][(key[r] >> shift) & 255u] + pre[r];
+      skey[pos] = key[r]; sidx[pos] = idx_in ? idx_in[i] : i;
+    }
   }
   __syncthreads();
   // phase 4: write the tile out in sorted order
