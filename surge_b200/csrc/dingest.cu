@@ -7,9 +7,18 @@
 // the device as they are; CRC, lz4, record parsing, id interning and the fold never touch the CPU.
 //
 // Call sequence per poll:   sgr_dingest_submit(partition, fetch bytes)*  ->  sgr_dingest_fold()
-// submit = header walk + one asynchronous H2D copy of the fetch (page-locked source memory makes it a single DMA);
-// fold   = crc_size -> (dsize back, arena offsets out) -> decode_walk -> parse + intern -> table growth -> the sort-free fold of
-//          the decoded records onto the engine's live table; only then do the partitions' positions advance. All or nothing.
+// submit = header walk + one asynchronous H2D copy of the fetch (page-locked source memory makes it a single DMA). Whenever
+//          `group_batches` data batches have accumulated, their whole chain
+//              descriptors up -> crc_size (claims each batch's arena slot) -> decode_walk -> parse + intern
+//          is enqueued on one of a few streams behind the copy that brought the group's last byte: no host round trip inside
+//          the chain, so groups decode while later fetches are still crossing PCIe and while the host walks their headers.
+// fold   = the chain of the remainder, one synchronisation, the verdicts (any error: nothing of the poll is applied), table
+//          growth, new ids to the engine's key table, the sort-free fold of the decoded records onto the live table; only
+//          then do the partitions' positions advance. All or nothing.
+// The arena the batches decompress into is sized from the wire bytes (3x); if a poll compresses better than that the claims
+// overflow, the flag comes back with the verdicts and the poll is decoded again from an exact host-side layout.
+// SGR_DINGEST_V1=1 selects the first generation (memory-walking kernels, arena laid out on the host between two
+// synchronisations) for A/B runs.
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
@@ -103,8 +112,17 @@ struct sgr_dingest {
   // device scratch
   KeepBuf arena, d_batches;
   uint64_t d_batches_used = 0;              // descriptors uploaded by the submissions of this poll
-  uint64_t crc_launched = 0;                // ... of which the CRC + size pass has been launched
-  DevBuf rec_off, rec_batch, out, key_offs_dev, key_bytes_dev;
+  uint64_t crc_launched = 0;                // ... of which the CRC + size pass (v1) / the whole chain (default) has been launched
+  KeepBuf rec_off, rec_batch, out;          // per record slot; they keep their content when a later group needs them larger
+  DevBuf key_offs_dev, key_bytes_dev;
+  // chains of launches per group of batches
+  bool v1 = false;                          // SGR_DINGEST_V1
+  uint32_t group_batches = 8192;            // SGR_DINGEST_GROUP
+  static constexpr int kGroupStreams = 8;
+  cudaStream_t gstream[kGroupStreams] = {};
+  std::vector<cudaEvent_t> group_events;    // pool; the first n_groups are this poll's "group done" events
+  uint32_t n_groups = 0;
+  uint64_t launched_records = 0;            // record slots covered by the launched chains
   void* h_keys = nullptr; uint64_t h_keys_cap = 0;   // page-locked landing area of the new ids
   // device dictionary
   DevBuf tags, slot_idx, key_ref, id_arena, ctl;
@@ -148,10 +166,95 @@ const char* dg_err_text(uint32_t e) {
   return "unknown";
 }
 
+cudaError_t sync_all(sgr_dingest* g) {
+  cudaError_t e = cudaSuccess, x;
+  if (g->copy_stream && (x = cudaStreamSynchronize(g->copy_stream)) != cudaSuccess) e = x;
+  for (cudaStream_t s : g->gstream) if (s && (x = cudaStreamSynchronize(s)) != cudaSuccess) e = x;
+  if (g->stream && (x = cudaStreamSynchronize(g->stream)) != cudaSuccess) e = x;
+  return e;
+}
+
+// per-poll device counters back to zero: [2] markers [3] null values [4] duplicates [5] dictionary overflow [6] records written,
+// [8] arena bytes claimed, [10] arena overflow; [0] keys / [1] id bytes / [9] arena capacity persist
+cudaError_t reset_poll_counters(sgr_dingest* g) {
+  cudaError_t e = cudaMemsetAsync((unsigned long long*)g->ctl.p + 2, 0, 5 * 8, g->stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync((unsigned long long*)g->ctl.p + 8, 0, 8, g->stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync((unsigned long long*)g->ctl.p + 10, 0, 8, g->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(g->stream);   // group streams of the next poll must see it
+  return e;
+}
+
+void clear_poll(sgr_dingest* g) {
+  g->wire.used = 0; g->batches.clear(); g->n_record_slots = 0; g->poll = sgr_ingest_stats{}; g->subs.clear(); g->d_batches_used = 0; g->crc_launched = 0;
+  g->n_groups = 0; g->launched_records = 0;
+}
+
 void discard_poll(sgr_dingest* g) {
-  if (g->copy_stream) cudaStreamSynchronize(g->copy_stream);   // no copy may still be landing in the buffer the next poll reuses
-  if (g->stream) cudaStreamSynchronize(g->stream);
-  g->wire.used = 0; g->batches.clear(); g->n_record_slots = 0; g->staged = g->parts; g->poll = sgr_ingest_stats{}; g->subs.clear(); g->d_batches_used = 0; g->crc_launched = 0;
+  sync_all(g);   // no copy may still be landing in the buffer the next poll reuses, no chain still running
+  reset_poll_counters(g);
+  clear_poll(g);
+  g->staged = g->parts;
+}
+
+DgParse parse_args(sgr_dingest* g) {
+  DgParse p{};
+  p.wire = (const uint8_t*)g->wire.b.p; p.arena = (const uint8_t*)g->arena.b.p;
+  p.batches = (DgBatch*)g->d_batches.b.p;
+  p.rec_off = (const uint32_t*)g->rec_off.b.p; p.rec_batch = (const uint32_t*)g->rec_batch.b.p; p.out = (uint8_t*)g->out.b.p; p.null_value_type = g->null_value_type;
+  p.dict.tags = (unsigned long long*)g->tags.p; p.dict.slot_idx = (uint32_t*)g->slot_idx.p; p.dict.key_ref = (uint2*)g->key_ref.p;
+  p.dict.arena = (uint8_t*)g->id_arena.p; p.dict.ctl = (unsigned long long*)g->ctl.p; p.dict.slots_mask = g->slots - 1;
+  p.dict.max_keys = g->max_keys; p.dict.arena_cap = g->arena_cap;
+  return p;
+}
+
+// grow a content-keeping buffer; anything that moves waits for every stream first (kernels in flight hold the old address)
+cudaError_t grow_keeping(sgr_dingest* g, KeepBuf& kb, uint64_t keep_bytes, uint64_t want_bytes) {
+  if (want_bytes <= kb.b.cap) return cudaSuccess;
+  cudaError_t e = sync_all(g);
+  if (e != cudaSuccess) return e;
+  kb.used = keep_bytes;
+  return kb.ensure(want_bytes - keep_bytes, g->stream);   // (ensure doubles, copies `used` bytes and synchronises)
+}
+
+cudaError_t set_arena_capacity(sgr_dingest* g) {
+  const unsigned long long cap = g->arena.b.cap >= 512 ? g->arena.b.cap - 512 : 0;   // (the walk's ring reads 256 bytes past a slot)
+  return cudaMemcpy((unsigned long long*)g->ctl.p + 9, &cap, 8, cudaMemcpyHostToDevice);
+}
+
+// Enqueue descriptors-up -> crc_size (+ arena claim) -> decode_walk -> parse for the batches [crc_launched, batch_end) — record
+// slots [launched_records, rec_end) — behind `landed` (the copy of the last fetch that contributes to the group).
+int32_t launch_group(sgr_dingest* g, uint64_t batch_end, uint64_t rec_end, cudaEvent_t landed) {
+  const uint64_t b0 = g->crc_launched, nb = batch_end - b0;
+  if (!nb) return SGR_OK;
+  const uint64_t r0 = g->launched_records;
+  DG_TRY(g, grow_keeping(g, g->d_batches, b0 * sizeof(DgBatch), batch_end * sizeof(DgBatch) + 64));
+  DG_TRY(g, grow_keeping(g, g->rec_off, r0 * 4, rec_end * 4 + 64));
+  DG_TRY(g, grow_keeping(g, g->rec_batch, r0 * 4, rec_end * 4 + 64));
+  DG_TRY(g, grow_keeping(g, g->out, r0 * 64, rec_end * 64 + 64));
+  const uint64_t arena_want = 3 * (uint64_t)g->wire.b.cap + 512;
+  if (g->arena.b.cap < arena_want) {
+    DG_TRY(g, grow_keeping(g, g->arena, b0 ? g->arena.b.cap : 0, arena_want));
+    DG_TRY(g, set_arena_capacity(g));
+  }
+  if (g->n_groups >= g->group_events.size()) {
+    cudaEvent_t ev;
+    DG_TRY(g, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    g->group_events.push_back(ev);
+  }
+  cudaStream_t s = g->gstream[g->n_groups % sgr_dingest::kGroupStreams];
+  DG_TRY(g, cudaStreamWaitEvent(s, landed, 0));
+  DgBatch* db = (DgBatch*)g->d_batches.b.p + b0;
+  DG_TRY(g, cudaMemcpyAsync(db, g->batches.p + b0, nb * sizeof(DgBatch), cudaMemcpyHostToDevice, s));
+  if (rec_end > r0) DG_TRY(g, cudaMemsetAsync((uint32_t*)g->rec_batch.b.p + r0, 0xff, (rec_end - r0) * 4, s));
+  DG_TRY(g, dg_launch_crc_size_fast((const uint8_t*)g->wire.b.p, db, (uint32_t)nb, (unsigned long long*)g->ctl.p + 8, s));
+  DG_TRY(g, dg_launch_decode_walk_fast((const uint8_t*)g->wire.b.p, (uint8_t*)g->arena.b.p, db, (uint32_t)nb, (uint32_t)b0, (uint32_t*)g->rec_off.b.p, (uint32_t*)g->rec_batch.b.p, s));
+  DgParse p = parse_args(g);
+  p.n_batches = (uint32_t)batch_end; p.rec_begin = (uint32_t)r0; p.n_records = (uint32_t)rec_end;
+  DG_TRY(g, dg_launch_parse(p, s));
+  DG_TRY(g, cudaEventRecord(g->group_events[g->n_groups], s));
+  ++g->n_groups;
+  g->crc_launched = batch_end; g->launched_records = rec_end;
+  return SGR_OK;
 }
 }  // namespace
 
@@ -165,7 +268,12 @@ int32_t sgr_dingest_create(sgr_engine* e, uint64_t max_keys, uint64_t max_id_byt
   sgr_dingest* g = new sgr_dingest();
   g->eng = e; g->stream = (cudaStream_t)st;
   g->timing_syncs = getenv("SGR_DINGEST_TIMING") != nullptr;
+  g->v1 = getenv("SGR_DINGEST_V1") != nullptr;
+  if (const char* gb = getenv("SGR_DINGEST_GROUP")) { const long v = atol(gb); if (v >= 64 && v <= (1l << 24)) g->group_batches = (uint32_t)v; }
+  if (dg_prepare() != cudaSuccess) { delete g; return SGR_ERR_CUDA; }
   if (cudaStreamCreateWithFlags(&g->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { delete g; return SGR_ERR_CUDA; }
+  for (cudaStream_t& s : g->gstream)
+    if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) { sgr_dingest_destroy(g); return SGR_ERR_CUDA; }
   g->max_keys = max_keys;
   g->slots = 1024;
   while (g->slots < 2 * max_keys) g->slots *= 2;          // load factor <= 0.5
@@ -173,9 +281,9 @@ int32_t sgr_dingest_create(sgr_engine* e, uint64_t max_keys, uint64_t max_id_byt
   cudaError_t ce;
   if ((ce = g->tags.reserve(g->slots * 8)) != cudaSuccess || (ce = g->slot_idx.reserve(g->slots * 4)) != cudaSuccess ||
       (ce = g->key_ref.reserve(max_keys * 8)) != cudaSuccess || (ce = g->id_arena.reserve(g->arena_cap + 64)) != cudaSuccess ||
-      (ce = g->ctl.reserve(64)) != cudaSuccess || (ce = cudaHostAlloc(&g->h_ctl, 256, cudaHostAllocDefault)) != cudaSuccess ||
+      (ce = g->ctl.reserve(128)) != cudaSuccess || (ce = cudaHostAlloc(&g->h_ctl, 256, cudaHostAllocDefault)) != cudaSuccess ||
       (ce = cudaMemsetAsync(g->tags.p, 0, g->slots * 8, g->stream)) != cudaSuccess || (ce = cudaMemsetAsync(g->slot_idx.p, 0, g->slots * 4, g->stream)) != cudaSuccess ||
-      (ce = cudaMemsetAsync(g->ctl.p, 0, 64, g->stream)) != cudaSuccess || (ce = cudaStreamSynchronize(g->stream)) != cudaSuccess) {
+      (ce = cudaMemsetAsync(g->ctl.p, 0, 128, g->stream)) != cudaSuccess || (ce = cudaStreamSynchronize(g->stream)) != cudaSuccess) {
     sgr_dingest_destroy(g);
     return ce == cudaErrorMemoryAllocation ? SGR_ERR_OOM : SGR_ERR_CUDA;
   }
@@ -185,11 +293,14 @@ int32_t sgr_dingest_create(sgr_engine* e, uint64_t max_keys, uint64_t max_id_byt
 
 int32_t sgr_dingest_destroy(sgr_dingest* g) {
   if (!g) return SGR_OK;
-  if (g->copy_stream) { cudaStreamSynchronize(g->copy_stream); cudaStreamDestroy(g->copy_stream); }
+  sync_all(g);
+  if (g->copy_stream) cudaStreamDestroy(g->copy_stream);
+  for (cudaStream_t s : g->gstream) if (s) cudaStreamDestroy(s);
   for (cudaEvent_t ev : g->event_pool) cudaEventDestroy(ev);
+  for (cudaEvent_t ev : g->group_events) cudaEventDestroy(ev);
   if (g->h_keys) cudaFreeHost(g->h_keys);
   g->batches.release();
-  g->wire.b.release(); g->d_batches.b.release(); g->arena.b.release(); g->rec_off.release(); g->rec_batch.release(); g->out.release();
+  g->wire.b.release(); g->d_batches.b.release(); g->arena.b.release(); g->rec_off.b.release(); g->rec_batch.b.release(); g->out.b.release();
   g->key_offs_dev.release(); g->key_bytes_dev.release();
   g->tags.release(); g->slot_idx.release(); g->key_ref.release(); g->id_arena.release(); g->ctl.release();
   if (g->h_ctl) cudaFreeHost(g->h_ctl);
@@ -281,11 +392,8 @@ int32_t sgr_dingest_submit(sgr_dingest* g, int32_t partition, const void* data, 
   }
   sub.copied = g->event_pool[g->subs.size()];
   if (pos) {
-    if (g->wire.used + pos + 16 > g->wire.b.cap) {   // the buffer moves: no copy may be in flight, no kernel reading it
-      DG_TRY(g, cudaStreamSynchronize(g->copy_stream));
-      DG_TRY(g, cudaStreamSynchronize(g->stream));
-    }
-    DG_TRY(g, g->wire.ensure(pos + 16, g->copy_stream));
+    if (g->wire.used + pos + 272 > g->wire.b.cap) DG_TRY(g, sync_all(g));   // the buffer moves: no copy in flight, no kernel reading it
+    DG_TRY(g, g->wire.ensure(pos + 272, g->copy_stream));                     // (the input ring reads up to 256 bytes past a batch)
     DG_TRY(g, cudaMemcpyAsync((uint8_t*)g->wire.b.p + g->wire.used, buf, pos, cudaMemcpyHostToDevice, g->copy_stream));
     g->wire.used += (pos + 15) & ~15ull;
   }
@@ -293,12 +401,20 @@ int32_t sgr_dingest_submit(sgr_dingest* g, int32_t partition, const void* data, 
   g->subs.push_back(sub);
   if (!add.empty()) {
     if (g->batches.n + add.size() > g->batches.cap) {   // the pinned array moves: nothing may still be copying from / into it
-      DG_TRY(g, cudaStreamSynchronize(g->stream));
+      DG_TRY(g, sync_all(g));
       if (!g->batches.reserve(g->batches.n + add.size())) return dfail(g, SGR_ERR_OOM, "page-locked descriptor array");
     }
     memcpy(g->batches.p + g->batches.n, add.data(), add.size() * sizeof(DgBatch));
     const DgBatch* src_desc = g->batches.p + g->batches.n;
+    (void)src_desc;
     g->batches.n += add.size();
+    if (!g->v1) {
+      g->d_batches_used += add.size();
+      if (g->d_batches_used - g->crc_launched >= g->group_batches) {
+        const int32_t rc = launch_group(g, g->d_batches_used, g->n_record_slots + slots, sub.copied);
+        if (rc) { discard_poll(g); return rc; }
+      }
+    } else {
     // descriptors go up right away; the CRC + lz4 size pass is launched once >= 32 k batches are waiting (one thread per batch:
     // a small launch takes as long as a large one, it is the serial walk of ONE batch) — it then runs while the host walks
     // the next fetches and the copy engine brings them in; sgr_dingest_fold launches the remainder
@@ -312,6 +428,7 @@ int32_t sgr_dingest_submit(sgr_dingest* g, int32_t partition, const void* data, 
       DG_TRY(g, cudaStreamWaitEvent(g->stream, sub.copied, 0));
       DG_TRY(g, dg_launch_crc_size((const uint8_t*)g->wire.b.p, (DgBatch*)g->d_batches.b.p + g->crc_launched, (uint32_t)(g->d_batches_used - g->crc_launched), g->stream));
       g->crc_launched = g->d_batches_used;
+    }
     }
   }
   g->n_record_slots += slots;
@@ -336,22 +453,52 @@ int32_t sgr_dingest_fold(sgr_dingest* g, sgr_ingest_stats* stats) {
   auto lap = [&](int i) { const Clk::time_point now = Clk::now(); g->ms[i] += std::chrono::duration<float, std::milli>(now - t_last).count(); t_last = now; };
   memset(g->ms, 0, sizeof g->ms);
   if (nb) {
-    DG_TRY(g, g->rec_off.reserve((size_t)nrec * 4 + 64));
-    DG_TRY(g, g->rec_batch.reserve((size_t)nrec * 4 + 64));
-    DG_TRY(g, g->out.reserve((size_t)nrec * 64 + 64));
-    DG_TRY(g, cudaMemsetAsync(g->rec_batch.p, 0xff, (size_t)nrec * 4 + 4, g->stream));
-    // per-poll counters: [2] markers [3] null values [4] duplicates [6] records written; [0] keys / [1] arena persist
-    DG_TRY(g, cudaMemcpyAsync(h, g->ctl.p, 64, cudaMemcpyDeviceToHost, g->stream));
-    DG_TRY(g, cudaStreamSynchronize(g->stream));
-    const unsigned long long keys_before = h[0];
-    h[2] = h[3] = h[4] = h[5] = h[6] = 0;
-    DG_TRY(g, cudaMemcpyAsync(g->ctl.p, h, 64, cudaMemcpyHostToDevice, g->stream));
-    DgParse p{};
-    p.batches = (DgBatch*)g->d_batches.b.p; p.n_batches = nb;
-    p.rec_off = (const uint32_t*)g->rec_off.p; p.rec_batch = (const uint32_t*)g->rec_batch.p; p.out = (uint8_t*)g->out.p; p.null_value_type = g->null_value_type;
-    p.dict.tags = (unsigned long long*)g->tags.p; p.dict.slot_idx = (uint32_t*)g->slot_idx.p; p.dict.key_ref = (uint2*)g->key_ref.p;
-    p.dict.arena = (uint8_t*)g->id_arena.p; p.dict.ctl = (unsigned long long*)g->ctl.p; p.dict.slots_mask = g->slots - 1;
-    p.dict.max_keys = g->max_keys; p.dict.arena_cap = g->arena_cap;
+    DgParse p = parse_args(g);
+    if (!g->v1) {
+      // ---- chains: launch the remainder, wait for every group, bring the verdicts back
+      { const int32_t rc = launch_group(g, nb, nrec, g->subs.back().copied); if (rc) { discard_poll(g); return rc; } }
+      for (uint32_t k = 0; k < g->n_groups; ++k) DG_TRY(g, cudaStreamWaitEvent(g->stream, g->group_events[k], 0));
+      DG_TRY(g, cudaMemcpyAsync(g->batches.data(), g->d_batches.b.p, (size_t)nb * sizeof(DgBatch), cudaMemcpyDeviceToHost, g->stream));
+      DG_TRY(g, cudaMemcpyAsync(h, g->ctl.p, 128, cudaMemcpyDeviceToHost, g->stream));
+      DG_TRY(g, cudaStreamSynchronize(g->stream));
+      lap(0);
+      if (h[10]) {
+        // the arena claims overflowed (the poll compresses better than 3x): lay the arena out exactly and decode + parse again.
+        // Ids the first attempt interned stay (an id is an id); its records are overwritten slot for slot.
+        uint64_t need = 0;
+        for (uint32_t i = 0; i < nb; ++i) {
+          DgBatch& b = g->batches[i];
+          if (b.err == DG_ARENA_FULL) b.err = DG_OK;
+          if (b.err) { const int32_t rc = dfail(g, SGR_ERR_INVALID, "offset %lld: %s", (long long)b.base_offset, dg_err_text(b.err)); discard_poll(g); return rc; }
+          b.err_record = 0;
+          if (b.codec == 3) { b.arena_off = need; need += ((uint64_t)b.dsize + 15) & ~15ull; }
+        }
+        g->arena.used = 0;
+        DG_TRY(g, g->arena.ensure(need + 512, g->stream));
+        DG_TRY(g, set_arena_capacity(g));
+        p = parse_args(g);
+        h[2] = h[3] = h[4] = h[5] = h[6] = 0; h[8] = need; h[10] = 0;
+        DG_TRY(g, cudaMemcpyAsync((unsigned long long*)g->ctl.p + 2, h + 2, 5 * 8, cudaMemcpyHostToDevice, g->stream));
+        DG_TRY(g, cudaMemcpyAsync((unsigned long long*)g->ctl.p + 8, h + 8, 8, cudaMemcpyHostToDevice, g->stream));
+        DG_TRY(g, cudaMemcpyAsync((unsigned long long*)g->ctl.p + 10, h + 10, 8, cudaMemcpyHostToDevice, g->stream));
+        DG_TRY(g, cudaMemsetAsync(g->rec_batch.b.p, 0xff, (size_t)nrec * 4 + 4, g->stream));
+        DG_TRY(g, cudaMemcpyAsync(g->d_batches.b.p, g->batches.data(), (size_t)nb * sizeof(DgBatch), cudaMemcpyHostToDevice, g->stream));
+        DG_TRY(g, dg_launch_decode_walk_fast((const uint8_t*)g->wire.b.p, (uint8_t*)g->arena.b.p, (DgBatch*)g->d_batches.b.p, nb, 0, (uint32_t*)g->rec_off.b.p, (uint32_t*)g->rec_batch.b.p, g->stream));
+        p.n_batches = nb; p.rec_begin = 0; p.n_records = nrec;
+        DG_TRY(g, dg_launch_parse(p, g->stream));
+        DG_TRY(g, cudaMemcpyAsync(g->batches.data(), g->d_batches.b.p, (size_t)nb * sizeof(DgBatch), cudaMemcpyDeviceToHost, g->stream));
+        DG_TRY(g, cudaMemcpyAsync(h, g->ctl.p, 128, cudaMemcpyDeviceToHost, g->stream));
+        DG_TRY(g, cudaStreamSynchronize(g->stream));
+        lap(1);
+      }
+      for (uint32_t i = 0; i < nb; ++i) if (g->batches[i].codec == 3 && !g->batches[i].err) st.n_decompressed_bytes += g->batches[i].dsize;
+    } else {
+    DG_TRY(g, g->rec_off.b.reserve((size_t)nrec * 4 + 64));
+    DG_TRY(g, g->rec_batch.b.reserve((size_t)nrec * 4 + 64));
+    DG_TRY(g, g->out.b.reserve((size_t)nrec * 64 + 64));
+    p = parse_args(g);
+    DG_TRY(g, cudaMemsetAsync(g->rec_batch.b.p, 0xff, (size_t)nrec * 4 + 4, g->stream));
+    p.n_batches = nb;
     // ---- the CRC + lz4 size pass: most of it was launched by sgr_dingest_submit behind the copies; the rest now
     if (g->crc_launched < nb) {
       DG_TRY(g, cudaStreamWaitEvent(g->stream, g->subs.back().copied, 0));
@@ -370,14 +517,15 @@ int32_t sgr_dingest_fold(sgr_dingest* g, sgr_ingest_stats* stats) {
     g->arena.used = 0;
     DG_TRY(g, g->arena.ensure(arena_need + 64, g->stream));
     DG_TRY(g, cudaMemcpyAsync(g->d_batches.b.p, g->batches.data(), (size_t)nb * sizeof(DgBatch), cudaMemcpyHostToDevice, g->stream));
-    DG_TRY(g, dg_launch_decode_walk((const uint8_t*)g->wire.b.p, (uint8_t*)g->arena.b.p, (DgBatch*)g->d_batches.b.p, nb, 0, (uint32_t*)g->rec_off.p, (uint32_t*)g->rec_batch.p, g->stream));
+    DG_TRY(g, dg_launch_decode_walk((const uint8_t*)g->wire.b.p, (uint8_t*)g->arena.b.p, (DgBatch*)g->d_batches.b.p, nb, 0, (uint32_t*)g->rec_off.b.p, (uint32_t*)g->rec_batch.b.p, g->stream));
     if (g->timing_syncs) { DG_TRY(g, cudaStreamSynchronize(g->stream)); lap(1); }
     p.wire = (const uint8_t*)g->wire.b.p; p.arena = (const uint8_t*)g->arena.b.p; p.rec_begin = 0; p.n_records = nrec;
     DG_TRY(g, dg_launch_parse(p, g->stream));
     DG_TRY(g, cudaMemcpyAsync(g->batches.data(), g->d_batches.b.p, (size_t)nb * sizeof(DgBatch), cudaMemcpyDeviceToHost, g->stream));
-    DG_TRY(g, cudaMemcpyAsync(h, g->ctl.p, 64, cudaMemcpyDeviceToHost, g->stream));
+    DG_TRY(g, cudaMemcpyAsync(h, g->ctl.p, 128, cudaMemcpyDeviceToHost, g->stream));
     DG_TRY(g, cudaStreamSynchronize(g->stream));
     lap(2);
+    }
     for (uint32_t i = 0; i < nb; ++i)
       if (g->batches[i].err) {
         const int32_t rc = dfail(g, SGR_ERR_INVALID, "offset %lld, record %u: %s", (long long)g->batches[i].base_offset, g->batches[i].err_record, dg_err_text(g->batches[i].err));
@@ -388,7 +536,7 @@ int32_t sgr_dingest_fold(sgr_dingest* g, sgr_ingest_stats* stats) {
       const int32_t rc = dfail(g, SGR_ERR_CAPACITY, "device id dictionary full (%llu ids / %llu id bytes allowed): create the device ingest with larger bounds", (unsigned long long)g->max_keys, (unsigned long long)g->arena_cap);
       discard_poll(g); return rc;
     }
-    st.n_markers = h[2]; st.n_null_values = h[3]; st.n_duplicates += h[4]; st.n_records = h[6]; st.n_new_keys = h[0] - keys_before;
+    st.n_markers = h[2]; st.n_null_values = h[3]; st.n_duplicates += h[4]; st.n_records = h[6]; st.n_new_keys = h[0] - g->keys_on_host;   // (ids a failed poll interned become visible with the next good one)
     // ---- grow the table for the new ids, hand their names to the engine's key table, fold
     const uint64_t n_keys = h[0];
     void* d_states = nullptr; uint64_t n_agg = 0; uint32_t sb = 0;
@@ -430,7 +578,7 @@ int32_t sgr_dingest_fold(sgr_dingest* g, sgr_ingest_stats* stats) {
     }
     lap(3);
     if (nrec) {
-      int32_t rc = sgr_fold_incremental_device(g->eng, g->out.p, nrec);
+      int32_t rc = sgr_fold_incremental_device(g->eng, g->out.b.p, nrec);
       if (rc) { dfail(g, rc, "engine: %s", sgr_last_error(g->eng)); discard_poll(g); return rc; }
     }
   }
@@ -439,7 +587,8 @@ int32_t sgr_dingest_fold(sgr_dingest* g, sgr_ingest_stats* stats) {
   // ---- commit: the staged positions become the live ones and everything decoded is folded
   for (auto& kv : g->staged) { kv.second.folded_next = kv.second.decoded_next; }
   g->parts = g->staged;
-  g->wire.used = 0; g->batches.clear(); g->n_record_slots = 0; g->poll = sgr_ingest_stats{}; g->subs.clear(); g->d_batches_used = 0; g->crc_launched = 0;
+  if (nb) DG_TRY(g, reset_poll_counters(g));
+  clear_poll(g);
   sgr_ingest_stats& t = g->total;
   t.n_bytes += st.n_bytes; t.n_batches += st.n_batches; t.n_records += st.n_records; t.n_markers += st.n_markers; t.n_null_values += st.n_null_values;
   t.n_control_batches += st.n_control_batches; t.n_aborted_batches += st.n_aborted_batches; t.n_aborted_records += st.n_aborted_records;
@@ -454,7 +603,9 @@ int32_t sgr_dingest_reset(sgr_dingest* g) {
   g->parts.clear(); g->staged.clear(); g->total = sgr_ingest_stats{}; g->keys_on_host = 0; ++g->generation;
   DG_TRY(g, cudaMemsetAsync(g->tags.p, 0, g->slots * 8, g->stream));
   DG_TRY(g, cudaMemsetAsync(g->slot_idx.p, 0, g->slots * 4, g->stream));
-  DG_TRY(g, cudaMemsetAsync(g->ctl.p, 0, 64, g->stream));
+  DG_TRY(g, cudaMemsetAsync(g->ctl.p, 0, 9 * 8, g->stream));                                  // ([9], the arena's capacity, stays)
+  DG_TRY(g, cudaMemsetAsync((unsigned long long*)g->ctl.p + 10, 0, 8, g->stream));
+  DG_TRY(g, cudaStreamSynchronize(g->stream));                                                   // the group streams must see it
   return SGR_OK;
 }
 

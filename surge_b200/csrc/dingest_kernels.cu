@@ -18,10 +18,18 @@
 // Records a read_committed consumer would not deliver (flush markers, duplicates below the partition position, dropped null
 // values) become HOLES (agg == ~0) that the fold kernels skip; nothing is compacted.
 //
-// Thread-per-batch is deliberate: a 16 KiB producer batch is ~1 k lz4 sequences and ~500 varint-delimited records, strictly
+// Thread-per-batch is deliberate: a 16 KiB producer batch is ~2 k lz4 sequences and ~500 varint-delimited records, strictly
 // serial inside; the parallelism is the tens of thousands of batches of a restore poll. All of it is HBM/latency-bound
 // byte work — no tensor cores anywhere.
+//
+// Two generations live here. The first (dg_crc_size_kernel, dg_decode_walk_kernel; SGR_DINGEST_V1=1 selects it) walks the bytes
+// through global memory and spends ~10 ms on the decode of ANY number of batches: ~10 dependent memory round trips per lz4
+// sequence, and in a warp of 32 independent batches some lane misses at every step. The second (the *_fast kernels, default)
+// reads its input through a per-thread cp.async ring in shared memory and keeps memory current behind an 8-byte output
+// accumulator (lz4_fast.h) — one dependent access per sequence — and claims each batch's arena slot with an atomicAdd in the size pass, so that CRC -> decode -> parse of a group of batches is one chain of launches with
+// no host round trip in between (csrc/dingest.cu runs such chains on several streams behind the H2D copies).
 #include "dingest_kernels.cuh"
+#include "lz4_fast.h"
 
 #include <stdlib.h>
 #include <string.h>
@@ -319,6 +327,165 @@ __global__ void __launch_bounds__(kThreads) dg_decode_walk_kernel(const uint8_t*
   if (c.pos != sect_len && lane == 0) { batches[i].err = DG_STRAY_BYTES; batches[i].err_record = bt.n_records; }
 }
 
+// ---------------------------------------------------------------------------------------------- second generation
+constexpr int kFastThreads = 64;   // thread-per-batch kernels: small CTAs spread a group of a few thousand batches over all SMs
+constexpr int kRingChunks = 8;     // 16-byte chunks per thread in the input ring
+
+// Input policy of lz4_fast.h on the device: a private ring of eight 16-byte chunks per thread in shared memory, kept six
+// chunks ahead of the read position by cp.async. An asynchronous copy has no destination register, so nobody stalls on it
+// (a register prefetch does not survive SIMT: the scoreboard of a load's destination is per warp, and in a warp of 32 independent
+// streams some lane touches that register name at every step). Streams are read front to back; buffers are padded by 256 bytes.
+struct RingIn {
+  uint32_t cell;            // shared-space address of this thread's 16 bytes in ring row 0
+  const uint8_t* base;      // 16-byte aligned address of the chunk that holds the read position
+  static constexpr uint32_t kRow = kFastThreads * 16;
+  __device__ __forceinline__ void init(const uint4* ring_row0) {
+    cell = (uint32_t)__cvta_generic_to_shared(ring_row0 + threadIdx.x);
+    base = nullptr;
+  }
+  static __device__ __forceinline__ uint32_t slot_at(uint32_t cell, const uint8_t* chunk) { return cell + (((uint32_t)reinterpret_cast<uintptr_t>(chunk) >> 4) & (kRingChunks - 1)) * kRow; }
+  __device__ __forceinline__ uint32_t slot_of(const uint8_t* chunk) const { return slot_at(cell, chunk); }
+  static __device__ __forceinline__ void issue_at(uint32_t cell, const uint8_t* chunk) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n\tcp.async.commit_group;" ::"r"(slot_at(cell, chunk)), "l"(chunk) : "memory");
+  }
+  __device__ __forceinline__ void issue(const uint8_t* chunk) { issue_at(cell, chunk); }
+  // (out of line and by value: the ring's state stays in registers, the eight requests are not replicated at every call site)
+  static __device__ __noinline__ const uint8_t* seek_at(uint32_t cell, const uint8_t* p) {
+    asm volatile("cp.async.wait_all;" ::: "memory");   // nothing of the previous stream may still land in the ring
+    const uint8_t* b = reinterpret_cast<const uint8_t*>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)15);
+#pragma unroll
+    for (int k = 0; k < kRingChunks; ++k) issue_at(cell, b + 16 * k);
+    asm volatile("cp.async.wait_group %0;" ::"n"(kRingChunks - 2) : "memory");   // this chunk and the next have landed
+    return b;
+  }
+  __device__ __forceinline__ void seek(const uint8_t* p) { base = seek_at(cell, p); }
+  __device__ __forceinline__ void advance(const uint8_t* p) {   // afterwards base <= p < base + 16 and chunks base, base + 16 are readable
+    if (p >= base + 16) {
+      if (p >= base + 16 * kRingChunks) { seek(p); return; }
+      do { issue(base + 16 * kRingChunks); base += 16; } while (p >= base + 16);
+      asm volatile("cp.async.wait_group %0;" ::"n"(kRingChunks - 2) : "memory");
+    }
+  }
+  __device__ __forceinline__ unsigned long long word_at(const uint8_t* a8) const {   // a8 is 8-byte aligned, inside chunks base / base + 16
+    unsigned long long v;
+    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(slot_of(a8) + ((uint32_t)reinterpret_cast<uintptr_t>(a8) & 8u)) : "memory");
+    return v;
+  }
+  __device__ __forceinline__ uint64_t get64(const uint8_t* p) const {   // bytes p .. p+7, base <= p < base + 16
+    const uint8_t* a = reinterpret_cast<const uint8_t*>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)7);
+    return lzf::funnel(word_at(a), word_at(a + 8), (uint32_t)reinterpret_cast<uintptr_t>(p) & 7u);
+  }
+};
+
+// CRC-32C over a byte range read through the ring
+__device__ uint32_t crc32c_ring(const uint32_t (*tab)[256], RingIn& in, const uint8_t* p, uint64_t n) {
+  uint32_t crc = 0xffffffffu;
+  if (!n) return ~crc;
+  in.seek(p);
+  while (n && ((uintptr_t)p & 7)) { crc = (crc >> 8) ^ tab[0][(crc ^ (uint32_t)in.get64(p)) & 0xff]; ++p; --n; in.advance(p); }
+  while (n >= 8) {
+    const unsigned long long w = in.get64(p);
+    const uint32_t lo = (uint32_t)w ^ crc, hi = (uint32_t)(w >> 32);
+    crc = tab[7][lo & 0xff] ^ tab[6][(lo >> 8) & 0xff] ^ tab[5][(lo >> 16) & 0xff] ^ tab[4][lo >> 24] ^
+          tab[3][hi & 0xff] ^ tab[2][(hi >> 8) & 0xff] ^ tab[1][(hi >> 16) & 0xff] ^ tab[0][hi >> 24];
+    p += 8; n -= 8;
+    in.advance(p);
+  }
+  while (n) { crc = (crc >> 8) ^ tab[0][(crc ^ (uint32_t)in.get64(p)) & 0xff]; ++p; --n; in.advance(p); }
+  return ~crc;
+}
+
+// arena_ctl (optional): [0] bytes claimed so far, [1] capacity, [2] set when a claim did not fit. With it every lz4 batch leaves
+// the kernel with its arena slot; without it the host lays the arena out from the sizes.
+__device__ __forceinline__ void crc_size_one(const uint32_t (*tab)[256], RingIn& in, const uint8_t* __restrict__ wire, DgBatch* __restrict__ batches, uint32_t i,
+                                             unsigned long long* __restrict__ arena_ctl) {
+  const DgBatch bt = batches[i];
+  const uint8_t* b = wire + bt.src_off;
+  uint32_t err = DG_OK, dsize = bt.total_len - 61u;
+  unsigned long long arena_off = 0;
+  if (crc32c_ring(tab, in, b + 21, (uint64_t)bt.total_len - 21) != bt.stored_crc) err = DG_CRC;
+  else if (bt.codec == 3) {
+    uint64_t len = 0;
+    err = lzf::frame<false>(in, b + 61, (uint64_t)bt.total_len - 61, nullptr, 0, &len);
+    if (!err && len > 0xffffffffull) err = DG_LZ4_TOO_LARGE;
+    dsize = (uint32_t)len;
+  }
+  if (!err && (uint64_t)bt.n_records > (uint64_t)dsize / 7 + 1) err = DG_RECORD_COUNT;   // every record is at least 7 bytes on the wire
+  if (!err && bt.codec == 3 && arena_ctl) {
+    const unsigned long long need = ((unsigned long long)dsize + 15ull) & ~15ull;
+    arena_off = atomicAdd(arena_ctl + 0, need);
+    if (arena_off + need > arena_ctl[1]) { arena_ctl[2] = 1ull; err = DG_ARENA_FULL; }
+  }
+  batches[i].dsize = dsize;
+  if (arena_ctl) batches[i].arena_off = arena_off;
+  batches[i].err = err;
+  batches[i].err_record = 0;
+}
+
+__global__ void __launch_bounds__(kFastThreads) dg_crc_size_fast_kernel(const uint8_t* __restrict__ wire, DgBatch* __restrict__ batches, uint32_t n,
+                                                                        unsigned long long* __restrict__ arena_ctl) {
+  __shared__ uint32_t tab[8][256];
+  __shared__ uint4 ring[kRingChunks][kFastThreads];
+  for (int i = threadIdx.x; i < 8 * 256; i += kFastThreads) (&tab[0][0])[i] = (&g_crc_tab[0][0])[i];
+  __syncthreads();
+  const uint32_t i = blockIdx.x * kFastThreads + threadIdx.x;
+  if (i >= n) return;
+  RingIn in;
+  in.init(&ring[0][0]);
+  crc_size_one(tab, in, wire, batches, i, arena_ctl);
+  asm volatile("cp.async.wait_all;" ::: "memory");   // chunks requested ahead of the last byte land before the CTA's memory goes
+}
+
+// one thread per batch: lz4 into the batch's arena slot, then the record-boundary walk (a chain of varints) over the decoded
+// bytes, read back through the same ring three records ahead
+__device__ __forceinline__ void decode_walk_one(RingIn& in, const uint8_t* __restrict__ wire, uint8_t* arena, DgBatch* __restrict__ batches, uint32_t i, uint32_t index_base,
+                                                uint32_t* __restrict__ rec_off, uint32_t* __restrict__ rec_batch) {
+  const DgBatch bt = batches[i];
+  if (bt.err) return;
+  const uint8_t* sect = wire + bt.src_off + 61;
+  uint64_t sect_len = (uint64_t)bt.total_len - 61;
+  if (bt.codec == 3) {
+    uint64_t len = 0;
+    const uint32_t e = lzf::frame<true>(in, sect, sect_len, arena + bt.arena_off, bt.dsize, &len);
+    if (e || len != bt.dsize) { batches[i].err = e ? e : DG_LZ4_BLOCK; return; }
+    sect = arena + bt.arena_off; sect_len = len;
+  }
+  in.seek(sect);
+  uint64_t pos = 0;
+  for (uint32_t r = 0; r < bt.n_records; ++r) {
+    bool ok = pos < sect_len;
+    uint32_t raw = 0, used = 0;
+    if (ok) {
+      in.advance(sect + pos);
+      const unsigned long long v = in.get64(sect + pos);
+      ok = false;
+#pragma unroll
+      for (int k = 0; k < 5; ++k) {
+        const uint32_t byte = (uint32_t)(v >> (8 * k)) & 0xffu;
+        raw |= (byte & 0x7fu) << (7 * k);
+        if (!(byte & 0x80u)) { used = k + 1; ok = true; break; }
+      }
+      ok = ok && pos + used <= sect_len;
+    }
+    const int32_t len = (int32_t)(raw >> 1) ^ -(int32_t)(raw & 1u);
+    if (!ok || len < 0 || (uint64_t)len > sect_len - (pos + used)) { batches[i].err = DG_RECORD_LENGTH; batches[i].err_record = r; return; }
+    rec_off[bt.rec_base + r] = (uint32_t)pos; rec_batch[bt.rec_base + r] = index_base + i;
+    pos += used + (uint64_t)len;
+  }
+  if (pos != sect_len) { batches[i].err = DG_STRAY_BYTES; batches[i].err_record = bt.n_records; }
+}
+
+__global__ void __launch_bounds__(kFastThreads) dg_decode_walk_fast_kernel(const uint8_t* __restrict__ wire, uint8_t* arena, DgBatch* __restrict__ batches,
+                                                                           uint32_t n, uint32_t index_base, uint32_t* __restrict__ rec_off, uint32_t* __restrict__ rec_batch) {
+  __shared__ uint4 ring[kRingChunks][kFastThreads];
+  const uint32_t i = blockIdx.x * kFastThreads + threadIdx.x;
+  if (i >= n) return;
+  RingIn in;
+  in.init(&ring[0][0]);
+  decode_walk_one(in, wire, arena, batches, i, index_base, rec_off, rec_batch);
+  asm volatile("cp.async.wait_all;" ::: "memory");
+}
+
 // ---- new ids -> contiguous bytes in dense-index order, for the host key table (lengths, [scan outside], copy)
 __global__ void dg_key_lens_kernel(const uint2* __restrict__ key_ref, uint64_t from, uint32_t n, uint32_t* __restrict__ lens) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -461,6 +628,21 @@ cudaError_t dg_launch_crc_size(const uint8_t* wire, DgBatch* batches, uint32_t n
   cudaError_t e = ensure_crc_tables();
   if (e != cudaSuccess || !n) return e;
   dg_crc_size_kernel<<<(n + kThreads - 1) / kThreads, kThreads, 0, st>>>(wire, batches, n);
+  return cudaGetLastError();
+}
+
+cudaError_t dg_prepare() { return ensure_crc_tables(); }
+
+cudaError_t dg_launch_crc_size_fast(const uint8_t* wire, DgBatch* batches, uint32_t n, unsigned long long* arena_ctl, cudaStream_t st) {
+  cudaError_t e = ensure_crc_tables();
+  if (e != cudaSuccess || !n) return e;
+  dg_crc_size_fast_kernel<<<(n + kFastThreads - 1) / kFastThreads, kFastThreads, 0, st>>>(wire, batches, n, arena_ctl);
+  return cudaGetLastError();
+}
+
+cudaError_t dg_launch_decode_walk_fast(const uint8_t* wire, uint8_t* arena, DgBatch* batches, uint32_t n, uint32_t index_base, uint32_t* rec_off, uint32_t* rec_batch, cudaStream_t st) {
+  if (!n) return cudaSuccess;
+  dg_decode_walk_fast_kernel<<<(n + kFastThreads - 1) / kFastThreads, kFastThreads, 0, st>>>(wire, arena, batches, n, index_base, rec_off, rec_batch);
   return cudaGetLastError();
 }
 

@@ -9,6 +9,7 @@ namespace sgr {
 enum DgErr : uint32_t {
   DG_OK = 0, DG_CRC = 1, DG_LZ4_HEADER = 2, DG_LZ4_BLOCK = 3, DG_LZ4_SEQUENCE = 4, DG_LZ4_CHECKSUM = 5, DG_LZ4_TOO_LARGE = 6,
   DG_RECORD_LENGTH = 7, DG_RECORD_MALFORMED = 8, DG_RECORD_COUNT = 9, DG_VALUE_LENGTH = 10, DG_ID_LENGTH = 11, DG_STRAY_BYTES = 12,
+  DG_ARENA_FULL = 13,   // not a data error: the batch's arena claim did not fit (the host lays the arena out exactly and repeats)
 };
 
 // One data batch that survived the host's header walk (control batches, aborted transactions and anything below the partition's
@@ -35,6 +36,7 @@ struct DgDict {           // device id dictionary: open addressing on a 64-bit h
   uint8_t* arena;             // id bytes, 8-byte aligned entries
   unsigned long long* ctl;    // [0] n_keys [1] arena bytes used [2] records dropped as markers [3] null values [4] duplicates
                               // [5] dictionary overflow (keys or arena) [6] packed records written (non-holes)
+                              // [8] [9] [10] decode arena: bytes claimed, capacity, overflow flag (dg_launch_crc_size_fast)
   uint64_t slots_mask;        // slots - 1 (power of two)
   uint64_t max_keys, arena_cap;
 };
@@ -57,6 +59,10 @@ cudaError_t dg_launch_crc_size(const uint8_t* wire, DgBatch* batches, uint32_t n
 // batches: the sub-array to process (n of them), whose first element has index `index_base` in the full array (what rec_batch records)
 cudaError_t dg_launch_decode_walk(const uint8_t* wire, uint8_t* arena, DgBatch* batches, uint32_t n, uint32_t index_base, uint32_t* rec_off, uint32_t* rec_batch, cudaStream_t st);
 cudaError_t dg_launch_parse(const DgParse& p, cudaStream_t st);
+// second generation (register-window decode, device-side arena claims); wire and arena need 64 readable bytes past their content
+cudaError_t dg_prepare();   // uploads the CRC tables (a synchronous copy: call it before anything runs on other streams)
+cudaError_t dg_launch_crc_size_fast(const uint8_t* wire, DgBatch* batches, uint32_t n, unsigned long long* arena_ctl, cudaStream_t st);
+cudaError_t dg_launch_decode_walk_fast(const uint8_t* wire, uint8_t* arena, DgBatch* batches, uint32_t n, uint32_t index_base, uint32_t* rec_off, uint32_t* rec_batch, cudaStream_t st);
 cudaError_t dg_gather_keys(const DgDict& d, uint64_t from, uint32_t n, uint32_t* d_offs, uint8_t* d_bytes, uint32_t* d_tmp, cudaStream_t st);
 uint32_t dg_crc32c_host_reference_polynomial();   // 0x82F63B78: the tables of the device CRC are built from it at first use
 

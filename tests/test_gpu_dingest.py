@@ -182,3 +182,52 @@ def test_large_log_from_the_fast_encoder_matches_the_oracle():
             assert st["n_records"] == n_agg * epa and st["n_new_keys"] == n_agg
             for g in list(range(0, n_agg, 997)) + [n_agg - 1]:
                 assert e.get(f"agg-{g}") == want[g, :8].tobytes(), g
+
+
+def _compare_with_host(fetches, max_keys=1 << 14):
+    want, want_offs, host = _host_fold(fetches)
+    with ReplayEngine(0) as e:
+        e.register_program(P.counter_program())
+        with DeviceIngest(e, max_keys) as dg:
+            for part, data in fetches:
+                dg.submit(part, data)
+            st = dg.fold()
+            for k, v in want.items():
+                assert e.get(k) == v, k
+            assert {p: dg.offsets(p) for p, _ in fetches} == want_offs
+            assert st["n_new_keys"] == len(want)
+            return st, dg.last_timing()
+
+
+@pytest.mark.parametrize("compression", ["none", "lz4"])
+def test_small_groups_chain_on_several_streams(monkeypatch, compression):
+    """SGR_DINGEST_GROUP=64: a poll of ~600 batches becomes ~10 chains (descriptors, CRC + arena claim, decode, parse) spread over
+    the group streams while later fetches are still being copied; buffers grow between groups and must keep their content."""
+    monkeypatch.setenv("SGR_DINGEST_GROUP", "64")
+    rng = np.random.default_rng(31)
+    fetches = []
+    for part in range(6):
+        data, _ = _stream(rng, 100, 3000, compression, base=part * 100000, max_per_batch=40)
+        fetches.append((part, data))
+    st, _ = _compare_with_host(fetches)
+    assert st["n_batches"] == 600
+
+
+def test_arena_overflow_falls_back_to_an_exact_layout():
+    """Batches that compress far better than the 3x the arena is sized for: the device-side claims overflow, the poll is decoded
+    again from a host-side layout and the result is the same."""
+    protos = [K.encode_record_batch(0, [(d, b"agg-%d" % ((i + d) % 5), _ev(0, d, 1 + i, b"\x00" * 40)) for d in range(400)], compression="lz4") for i in range(4)]
+    parts = []
+    for i in range(320):   # baseOffset sits in front of the CRC'd region: the same batch bytes serve at any offset
+        parts.append(struct.pack(">q", 400 * i) + protos[i % 4][8:])
+    one = b"".join(parts)
+    fetches = [(0, one)]
+    st, _ = _compare_with_host(fetches)
+    assert st["n_decompressed_bytes"] > 3.2 * len(one), (st["n_decompressed_bytes"], len(one))
+
+
+def test_first_generation_kernels_still_agree(monkeypatch):
+    monkeypatch.setenv("SGR_DINGEST_V1", "1")
+    rng = np.random.default_rng(32)
+    fetches = [(p, _stream(rng, 20, 500, "lz4", base=p * 5000)[0]) for p in range(3)]
+    _compare_with_host(fetches)
