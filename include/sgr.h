@@ -460,6 +460,9 @@ int32_t sgr_append_keys(sgr_engine* e, const void* owner, const uint8_t* keys, c
  *   - value framing: SGR_VALUE_PACKED only (protobuf / JSON values: use the host ingest);
  *   - programs in the sort-free class (16-byte state, class 0): dropped records stay in place as holes the fold skips;
  *   - dense indices are stable per id but follow no arrival-order promise (they come from an atomic counter);
+ *   - polls are processed in groups of SGR_DINGEST_GROUP (default 8192) batches, each group one chain of launches on one of eight
+ *     streams; batches decompress into an arena of 3x the wire bytes (a poll that compresses better is decoded a second time from
+ *     an exact layout — correct, slower); SGR_DINGEST_TIMING=1 prints each group's device timeline to stderr;
  *   - the id dictionary is sized at creation: max_keys ids, max_id_bytes id bytes (0 = 32 per id); exceeding either fails the
  *     poll with SGR_ERR_CAPACITY and applies nothing.
  * poll loop:  sgr_dingest_set_aborted* -> sgr_dingest_submit(partition, bytes)* -> sgr_dingest_fold.
@@ -478,8 +481,11 @@ int32_t sgr_dingest_offsets(sgr_dingest* g, int32_t partition, int64_t* decoded_
 /* Forget everything (dictionary, partition positions, statistics): the next poll starts a rebuild from offset 0 with dense
  * indices from 0. The engine's table is the caller's to reset (sgr_set_initial_states(e, NULL, 0)). */
 int32_t sgr_dingest_reset(sgr_dingest* g);
-/* host-clock milliseconds of the last sgr_dingest_fold: [0] wait for the copies + CRC / lz4 size pass, [1] lz4 decode + record walk,
- * [2] record parse + id interning, [3] new ids to the host key table, [4] table growth + fold, [5] the whole call */
+/* host-clock milliseconds of the last sgr_dingest_fold: [0] wait for the copies and for every group's chain (CRC, lz4 decode +
+ * record walk, record parse + id interning — launched by the submits behind the copies), [1] a repeat from an exact arena
+ * layout when the 3x estimate was too small (normally 0), [2] unused, [3] launch of the new ids' gather and download,
+ * [4] table growth + fold, with the ids handed to the key table by a helper thread meanwhile, [5] the whole call.
+ * (SGR_DINGEST_V1=1, the first generation: [0] copies + CRC / size pass, [1] decode + walk, [2] parse + intern.) */
 int32_t sgr_dingest_last_timing(sgr_dingest* g, float* ms8);
 int32_t sgr_dingest_get_stats(sgr_dingest* g, sgr_ingest_stats* out);
 

@@ -29,6 +29,7 @@
 #include <chrono>
 #include <map>
 #include <string>
+#include <thread>
 #include <unordered_set>
 #include <vector>
 
@@ -89,7 +90,7 @@ struct sgr_dingest {
       size_t c = cap ? cap : 4096;
       while (c < want) c *= 2;
       DgBatch* np = nullptr;
-      if (cudaHostAlloc((void**)&np, c * sizeof(DgBatch), cudaHostAllocDefault) != cudaSuccess) return false;
+      if (cudaHostAlloc((void**)&np, c * sizeof(DgBatch), cudaHostAllocMapped) != cudaSuccess) return false;
       if (n) memcpy(np, p, n * sizeof(DgBatch));
       if (p) cudaFreeHost(p);
       p = np; cap = c;
@@ -123,11 +124,17 @@ struct sgr_dingest {
   std::vector<cudaEvent_t> group_events;    // pool; the first n_groups are this poll's "group done" events
   uint32_t n_groups = 0;
   uint64_t launched_records = 0;            // record slots covered by the launched chains
+  // SGR_DINGEST_TIMING: per group the device times (ms since the poll's first copy was queued) at which its bytes had landed,
+  // its CRC + size pass, its decode and its parse ended; printed to stderr by sgr_dingest_fold
+  std::vector<cudaEvent_t> tl_events;       // 4 per group, + [last] the poll's origin
+  cudaEvent_t tl_origin = nullptr;
   void* h_keys = nullptr; uint64_t h_keys_cap = 0;   // page-locked landing area of the new ids
   // device dictionary
   DevBuf tags, slot_idx, key_ref, id_arena, ctl;
   uint64_t slots = 0, max_keys = 0, arena_cap = 0;
   uint64_t keys_on_host = 0;                // ids already appended to the engine's key table
+  uint64_t id_bytes_on_host = 0;            // ... and the id-arena bytes they occupy
+  cudaEvent_t keys_landed = nullptr;
   uint64_t generation = 0;                  // bumped by sgr_dingest_reset: a new dictionary is a new owner of the engine's key table
   void* h_ctl = nullptr;                    // page-locked landing area
   bool timing_syncs = false;                // SGR_DINGEST_TIMING=1: an extra synchronisation separates decode from parse in ms[]
@@ -243,14 +250,27 @@ int32_t launch_group(sgr_dingest* g, uint64_t batch_end, uint64_t rec_end, cudaE
   }
   cudaStream_t s = g->gstream[g->n_groups % sgr_dingest::kGroupStreams];
   DG_TRY(g, cudaStreamWaitEvent(s, landed, 0));
+  cudaEvent_t* tl = nullptr;
+  if (g->timing_syncs) {
+    while (g->tl_events.size() < 4 * (size_t)(g->n_groups + 1)) { cudaEvent_t ev; DG_TRY(g, cudaEventCreate(&ev)); g->tl_events.push_back(ev); }
+    tl = g->tl_events.data() + 4 * (size_t)g->n_groups;
+    DG_TRY(g, cudaEventRecord(tl[0], s));
+  }
   DgBatch* db = (DgBatch*)g->d_batches.b.p + b0;
-  DG_TRY(g, cudaMemcpyAsync(db, g->batches.p + b0, nb * sizeof(DgBatch), cudaMemcpyHostToDevice, s));
+  {
+    void* mapped = nullptr;   // the descriptors go up by a kernel: a copy-engine transfer would queue behind every fetch of the poll
+    DG_TRY(g, cudaHostGetDevicePointer(&mapped, g->batches.p + b0, 0));
+    DG_TRY(g, dg_copy_from_mapped_host(mapped, db, nb * sizeof(DgBatch), s));
+  }
   if (rec_end > r0) DG_TRY(g, cudaMemsetAsync((uint32_t*)g->rec_batch.b.p + r0, 0xff, (rec_end - r0) * 4, s));
   DG_TRY(g, dg_launch_crc_size_fast((const uint8_t*)g->wire.b.p, db, (uint32_t)nb, (unsigned long long*)g->ctl.p + 8, s));
-  DG_TRY(g, dg_launch_decode_walk_fast((const uint8_t*)g->wire.b.p, (uint8_t*)g->arena.b.p, db, (uint32_t)nb, (uint32_t)b0, (uint32_t*)g->rec_off.b.p, (uint32_t*)g->rec_batch.b.p, s));
+  if (tl) DG_TRY(g, cudaEventRecord(tl[1], s));
+  DG_TRY(g, dg_launch_decode_walk_fast((const uint8_t*)g->wire.b.p, (uint8_t*)g->arena.b.p, db, (uint32_t)nb, (uint32_t)b0, (uint32_t*)g->rec_off.b.p, (uint32_t*)g->rec_batch.b.p, (unsigned long long*)g->ctl.p + 8, s));
+  if (tl) DG_TRY(g, cudaEventRecord(tl[2], s));
   DgParse p = parse_args(g);
   p.n_batches = (uint32_t)batch_end; p.rec_begin = (uint32_t)r0; p.n_records = (uint32_t)rec_end;
   DG_TRY(g, dg_launch_parse(p, s));
+  if (tl) DG_TRY(g, cudaEventRecord(tl[3], s));
   DG_TRY(g, cudaEventRecord(g->group_events[g->n_groups], s));
   ++g->n_groups;
   g->crc_launched = batch_end; g->launched_records = rec_end;
@@ -298,6 +318,9 @@ int32_t sgr_dingest_destroy(sgr_dingest* g) {
   for (cudaStream_t s : g->gstream) if (s) cudaStreamDestroy(s);
   for (cudaEvent_t ev : g->event_pool) cudaEventDestroy(ev);
   for (cudaEvent_t ev : g->group_events) cudaEventDestroy(ev);
+  for (cudaEvent_t ev : g->tl_events) cudaEventDestroy(ev);
+  if (g->tl_origin) cudaEventDestroy(g->tl_origin);
+  if (g->keys_landed) cudaEventDestroy(g->keys_landed);
   if (g->h_keys) cudaFreeHost(g->h_keys);
   g->batches.release();
   g->wire.b.release(); g->d_batches.b.release(); g->arena.b.release(); g->rec_off.b.release(); g->rec_batch.b.release(); g->out.b.release();
@@ -391,6 +414,10 @@ int32_t sgr_dingest_submit(sgr_dingest* g, int32_t partition, const void* data, 
     g->event_pool.push_back(ev);
   }
   sub.copied = g->event_pool[g->subs.size()];
+  if (g->timing_syncs && g->subs.empty()) {
+    if (!g->tl_origin) DG_TRY(g, cudaEventCreate(&g->tl_origin));
+    DG_TRY(g, cudaEventRecord(g->tl_origin, g->copy_stream));
+  }
   if (pos) {
     if (g->wire.used + pos + 272 > g->wire.b.cap) DG_TRY(g, sync_all(g));   // the buffer moves: no copy in flight, no kernel reading it
     DG_TRY(g, g->wire.ensure(pos + 272, g->copy_stream));                     // (the input ring reads up to 256 bytes past a batch)
@@ -462,9 +489,20 @@ int32_t sgr_dingest_fold(sgr_dingest* g, sgr_ingest_stats* stats) {
       DG_TRY(g, cudaMemcpyAsync(h, g->ctl.p, 128, cudaMemcpyDeviceToHost, g->stream));
       DG_TRY(g, cudaStreamSynchronize(g->stream));
       lap(0);
+      if (g->timing_syncs && g->tl_origin) {
+        for (uint32_t k = 0; k < g->n_groups; ++k) {
+          float t[4] = {0, 0, 0, 0};
+          for (int j = 0; j < 4; ++j) cudaEventElapsedTime(&t[j], g->tl_origin, g->tl_events[4 * (size_t)k + j]);
+          fprintf(stderr, "[dingest] group %u: landed %.2f  crc+size %.2f  decode+walk %.2f  parse %.2f ms\n", k, t[0], t[1], t[2], t[3]);
+        }
+      }
       if (h[10]) {
         // the arena claims overflowed (the poll compresses better than 3x): lay the arena out exactly and decode + parse again.
         // Ids the first attempt interned stay (an id is an id); its records are overwritten slot for slot.
+        // (exact sizes first: the claim mode never measured them)
+        DG_TRY(g, dg_launch_crc_size_fast((const uint8_t*)g->wire.b.p, (DgBatch*)g->d_batches.b.p, nb, nullptr, g->stream));
+        DG_TRY(g, cudaMemcpyAsync(g->batches.data(), g->d_batches.b.p, (size_t)nb * sizeof(DgBatch), cudaMemcpyDeviceToHost, g->stream));
+        DG_TRY(g, cudaStreamSynchronize(g->stream));
         uint64_t need = 0;
         for (uint32_t i = 0; i < nb; ++i) {
           DgBatch& b = g->batches[i];
@@ -483,7 +521,7 @@ int32_t sgr_dingest_fold(sgr_dingest* g, sgr_ingest_stats* stats) {
         DG_TRY(g, cudaMemcpyAsync((unsigned long long*)g->ctl.p + 10, h + 10, 8, cudaMemcpyHostToDevice, g->stream));
         DG_TRY(g, cudaMemsetAsync(g->rec_batch.b.p, 0xff, (size_t)nrec * 4 + 4, g->stream));
         DG_TRY(g, cudaMemcpyAsync(g->d_batches.b.p, g->batches.data(), (size_t)nb * sizeof(DgBatch), cudaMemcpyHostToDevice, g->stream));
-        DG_TRY(g, dg_launch_decode_walk_fast((const uint8_t*)g->wire.b.p, (uint8_t*)g->arena.b.p, (DgBatch*)g->d_batches.b.p, nb, 0, (uint32_t*)g->rec_off.b.p, (uint32_t*)g->rec_batch.b.p, g->stream));
+        DG_TRY(g, dg_launch_decode_walk_fast((const uint8_t*)g->wire.b.p, (uint8_t*)g->arena.b.p, (DgBatch*)g->d_batches.b.p, nb, 0, (uint32_t*)g->rec_off.b.p, (uint32_t*)g->rec_batch.b.p, nullptr, g->stream));
         p.n_batches = nb; p.rec_begin = 0; p.n_records = nrec;
         DG_TRY(g, dg_launch_parse(p, g->stream));
         DG_TRY(g, cudaMemcpyAsync(g->batches.data(), g->d_batches.b.p, (size_t)nb * sizeof(DgBatch), cudaMemcpyDeviceToHost, g->stream));
@@ -550,10 +588,13 @@ int32_t sgr_dingest_fold(sgr_dingest* g, sgr_ingest_stats* stats) {
       if (rc) { dfail(g, rc, "engine: %s", sgr_last_error(g->eng)); discard_poll(g); return rc; }
     }
     lap(4);
+    // The new ids, gathered on the device into dense-index order, come down in two copies queued BEHIND nothing the fold needs
+    // and IN FRONT of the fold's kernels; a helper thread hands them to the engine's key table while this thread runs the fold.
+    std::thread appender;
+    int32_t rc_append = SGR_OK;
     if (n_keys > g->keys_on_host) {
-      // the new ids, gathered on the device into dense-index order, land in page-locked memory in two copies
       const uint64_t add = n_keys - g->keys_on_host;
-      const uint64_t id_bytes_max = h[1];   // (an upper bound: the arena's total use)
+      const uint64_t id_bytes_max = h[1] - g->id_bytes_on_host;   // (an upper bound: arena entries are padded to 8 bytes)
       DG_TRY(g, g->key_offs_dev.reserve((add + 2) * 4 + (2 * (add / 4096 + 2) + 4 * 4096) * 4));
       DG_TRY(g, g->key_bytes_dev.reserve(id_bytes_max + 64));
       uint32_t* d_offs = (uint32_t*)g->key_offs_dev.p;
@@ -569,18 +610,25 @@ int32_t sgr_dingest_fold(sgr_dingest* g, sgr_ingest_stats* stats) {
       uint32_t* h_offs = (uint32_t*)g->h_keys;
       uint8_t* h_bytes = (uint8_t*)g->h_keys + (add + 2) * 4;
       DG_TRY(g, cudaMemcpyAsync(h_offs, d_offs, (add + 1) * 4, cudaMemcpyDeviceToHost, g->stream));
-      DG_TRY(g, cudaStreamSynchronize(g->stream));
-      DG_TRY(g, cudaMemcpyAsync(h_bytes, g->key_bytes_dev.p, h_offs[add], cudaMemcpyDeviceToHost, g->stream));
-      DG_TRY(g, cudaStreamSynchronize(g->stream));
-      int32_t rc = sgr_append_keys(g->eng, (const char*)g + g->generation, h_bytes, h_offs, add);
-      if (rc) { dfail(g, rc, "engine: %s", sgr_last_error(g->eng)); discard_poll(g); return rc; }
-      g->keys_on_host = n_keys;
+      if (id_bytes_max) DG_TRY(g, cudaMemcpyAsync(h_bytes, g->key_bytes_dev.p, id_bytes_max, cudaMemcpyDeviceToHost, g->stream));
+      if (!g->keys_landed) DG_TRY(g, cudaEventCreateWithFlags(&g->keys_landed, cudaEventDisableTiming));
+      DG_TRY(g, cudaEventRecord(g->keys_landed, g->stream));
+      int dev = 0;
+      cudaGetDevice(&dev);
+      const void* owner = (const char*)g + g->generation;
+      appender = std::thread([g, dev, owner, h_offs, h_bytes, add, &rc_append]() {
+        cudaSetDevice(dev);
+        if (cudaEventSynchronize(g->keys_landed) != cudaSuccess) { rc_append = SGR_ERR_CUDA; return; }
+        rc_append = sgr_append_keys(g->eng, owner, h_bytes, h_offs, add);
+      });
     }
     lap(3);
-    if (nrec) {
-      int32_t rc = sgr_fold_incremental_device(g->eng, g->out.b.p, nrec);
-      if (rc) { dfail(g, rc, "engine: %s", sgr_last_error(g->eng)); discard_poll(g); return rc; }
-    }
+    int32_t rc_fold = SGR_OK;
+    if (nrec) rc_fold = sgr_fold_incremental_device(g->eng, g->out.b.p, nrec);
+    if (appender.joinable()) appender.join();
+    if (rc_fold) { dfail(g, rc_fold, "engine: %s", sgr_last_error(g->eng)); discard_poll(g); return rc_fold; }
+    if (rc_append) { dfail(g, rc_append, "engine: %s", sgr_last_error(g->eng)); discard_poll(g); return rc_append; }
+    g->keys_on_host = n_keys; g->id_bytes_on_host = h[1];
   }
   lap(4);
   g->ms[5] = std::chrono::duration<float, std::milli>(Clk::now() - t_begin).count();
@@ -600,7 +648,7 @@ int32_t sgr_dingest_fold(sgr_dingest* g, sgr_ingest_stats* stats) {
 int32_t sgr_dingest_reset(sgr_dingest* g) {
   if (!g) return SGR_ERR_INVALID;
   discard_poll(g);
-  g->parts.clear(); g->staged.clear(); g->total = sgr_ingest_stats{}; g->keys_on_host = 0; ++g->generation;
+  g->parts.clear(); g->staged.clear(); g->total = sgr_ingest_stats{}; g->keys_on_host = 0; g->id_bytes_on_host = 0; ++g->generation;
   DG_TRY(g, cudaMemsetAsync(g->tags.p, 0, g->slots * 8, g->stream));
   DG_TRY(g, cudaMemsetAsync(g->slot_idx.p, 0, g->slots * 4, g->stream));
   DG_TRY(g, cudaMemsetAsync(g->ctl.p, 0, 9 * 8, g->stream));                                  // ([9], the arena's capacity, stays)

@@ -362,8 +362,14 @@ struct RingIn {
   __device__ __forceinline__ void advance(const uint8_t* p) {   // afterwards base <= p < base + 16 and chunks base, base + 16 are readable
     if (p >= base + 16) {
       if (p >= base + 16 * kRingChunks) { seek(p); return; }
-      do { issue(base + 16 * kRingChunks); base += 16; } while (p >= base + 16);
-      asm volatile("cp.async.wait_group %0;" ::"n"(kRingChunks - 2) : "memory");
+      // One chunk at a time, each followed by its wait: a request goes into the slot of the OLDEST chunk, and that slot's
+      // previous request must have landed first — copies in flight complete in any order, and two of them aimed at one slot
+      // would leave whichever arrives last. (Issuing k requests and waiting once was wrong for k >= 3: the third reuses a slot
+      // whose copy may still be among the six allowed to be pending. Found by the 40-byte records of scripts/dingest_race.py.)
+      do {
+        issue(base + 16 * kRingChunks); base += 16;
+        asm volatile("cp.async.wait_group %0;" ::"n"(kRingChunks - 2) : "memory");
+      } while (p >= base + 16);
     }
   }
   __device__ __forceinline__ unsigned long long word_at(const uint8_t* a8) const {   // a8 is 8-byte aligned, inside chunks base / base + 16
@@ -377,8 +383,22 @@ struct RingIn {
   }
 };
 
+// The same interface over plain global loads (two aligned 8-byte words per read): the A/B partner of the ring
+// (SGR_DINGEST_DEBUG bit 1: record walk, bit 2: CRC + lz4 input) — every read is a dependent round trip.
+struct DirectIn {
+  __device__ __forceinline__ void seek(const uint8_t*) {}
+  __device__ __forceinline__ void advance(const uint8_t*) {}
+  __device__ __forceinline__ uint64_t get64(const uint8_t* p) const {
+    const uint8_t* a = reinterpret_cast<const uint8_t*>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)7);
+    return lzf::funnel(__ldcg(reinterpret_cast<const unsigned long long*>(a)), __ldcg(reinterpret_cast<const unsigned long long*>(a + 8)), (uint32_t)reinterpret_cast<uintptr_t>(p) & 7u);
+  }
+};
+
+__device__ uint32_t g_dbg_flags = 0;   // SGR_DINGEST_DEBUG: 1 walk without the ring, 2 CRC + lz4 input without the ring, 4 match sources bypass L1, 8 fence before the walk
+
 // CRC-32C over a byte range read through the ring
-__device__ uint32_t crc32c_ring(const uint32_t (*tab)[256], RingIn& in, const uint8_t* p, uint64_t n) {
+template <class IN>
+__device__ uint32_t crc32c_ring(const uint32_t (*tab)[256], IN& in, const uint8_t* p, uint64_t n) {
   uint32_t crc = 0xffffffffu;
   if (!n) return ~crc;
   in.seek(p);
@@ -395,9 +415,11 @@ __device__ uint32_t crc32c_ring(const uint32_t (*tab)[256], RingIn& in, const ui
   return ~crc;
 }
 
-// arena_ctl (optional): [0] bytes claimed so far, [1] capacity, [2] set when a claim did not fit. With it every lz4 batch leaves
-// the kernel with its arena slot; without it the host lays the arena out from the sizes.
-__device__ __forceinline__ void crc_size_one(const uint32_t (*tab)[256], RingIn& in, const uint8_t* __restrict__ wire, DgBatch* __restrict__ batches, uint32_t i,
+// arena_ctl (optional): [0] bytes claimed so far, [1] capacity, [2] set when a claim (or, later, a batch in its slot) did not fit.
+// With it: CRC only, and every lz4 batch leaves the kernel with an arena slot of 3x its compressed size. Without it: CRC and the
+// exact decoded size (an lz4 walk that only adds up lengths); the host then lays the arena out.
+template <class IN>
+__device__ __forceinline__ void crc_size_one(const uint32_t (*tab)[256], IN& in, const uint8_t* __restrict__ wire, DgBatch* __restrict__ batches, uint32_t i,
                                              unsigned long long* __restrict__ arena_ctl) {
   const DgBatch bt = batches[i];
   const uint8_t* b = wire + bt.src_off;
@@ -405,17 +427,22 @@ __device__ __forceinline__ void crc_size_one(const uint32_t (*tab)[256], RingIn&
   unsigned long long arena_off = 0;
   if (crc32c_ring(tab, in, b + 21, (uint64_t)bt.total_len - 21) != bt.stored_crc) err = DG_CRC;
   else if (bt.codec == 3) {
-    uint64_t len = 0;
-    err = lzf::frame<false>(in, b + 61, (uint64_t)bt.total_len - 61, nullptr, 0, &len);
-    if (!err && len > 0xffffffffull) err = DG_LZ4_TOO_LARGE;
-    dsize = (uint32_t)len;
+    if (arena_ctl) {
+      // claim mode: no size walk. The slot is 3x the compressed bytes (what the arena is sized for as a whole); a batch that
+      // decodes to more reports DG_ARENA_FULL from the decode kernel and the poll is repeated from exact sizes.
+      const unsigned long long cap = min(3ull * (bt.total_len - 61u) + 64ull, 0xfffffff0ull);
+      const unsigned long long need = (cap + 15ull) & ~15ull;
+      dsize = (uint32_t)cap;   // (the slot's capacity until the decode kernel replaces it by the decoded size)
+      arena_off = atomicAdd(arena_ctl + 0, need);
+      if (arena_off + need > arena_ctl[1]) { arena_ctl[2] = 1ull; err = DG_ARENA_FULL; }
+    } else {
+      uint64_t len = 0;
+      err = lzf::frame<false>(in, b + 61, (uint64_t)bt.total_len - 61, nullptr, 0, &len);
+      if (!err && len > 0xffffffffull) err = DG_LZ4_TOO_LARGE;
+      dsize = (uint32_t)len;
+    }
   }
-  if (!err && (uint64_t)bt.n_records > (uint64_t)dsize / 7 + 1) err = DG_RECORD_COUNT;   // every record is at least 7 bytes on the wire
-  if (!err && bt.codec == 3 && arena_ctl) {
-    const unsigned long long need = ((unsigned long long)dsize + 15ull) & ~15ull;
-    arena_off = atomicAdd(arena_ctl + 0, need);
-    if (arena_off + need > arena_ctl[1]) { arena_ctl[2] = 1ull; err = DG_ARENA_FULL; }
-  }
+  if (!err && !(bt.codec == 3 && arena_ctl) && (uint64_t)bt.n_records > (uint64_t)dsize / 7 + 1) err = DG_RECORD_COUNT;   // every record is at least 7 bytes on the wire
   batches[i].dsize = dsize;
   if (arena_ctl) batches[i].arena_off = arena_off;
   batches[i].err = err;
@@ -432,22 +459,30 @@ __global__ void __launch_bounds__(kFastThreads) dg_crc_size_fast_kernel(const ui
   if (i >= n) return;
   RingIn in;
   in.init(&ring[0][0]);
-  crc_size_one(tab, in, wire, batches, i, arena_ctl);
+  if (g_dbg_flags & 2u) { DirectIn din; crc_size_one(tab, din, wire, batches, i, arena_ctl); }
+  else crc_size_one(tab, in, wire, batches, i, arena_ctl);
   asm volatile("cp.async.wait_all;" ::: "memory");   // chunks requested ahead of the last byte land before the CTA's memory goes
 }
 
 // one thread per batch: lz4 into the batch's arena slot, then the record-boundary walk (a chain of varints) over the decoded
 // bytes, read back through the same ring three records ahead
-__device__ __forceinline__ void decode_walk_one(RingIn& in, const uint8_t* __restrict__ wire, uint8_t* arena, DgBatch* __restrict__ batches, uint32_t i, uint32_t index_base,
-                                                uint32_t* __restrict__ rec_off, uint32_t* __restrict__ rec_batch) {
+template <class IN, class WIN>
+__device__ __forceinline__ void decode_walk_one(IN& lzin, WIN& in, const uint8_t* __restrict__ wire, uint8_t* arena, DgBatch* __restrict__ batches, uint32_t i, uint32_t index_base,
+                                                uint32_t* __restrict__ rec_off, uint32_t* __restrict__ rec_batch, unsigned long long* __restrict__ arena_ctl) {
   const DgBatch bt = batches[i];
   if (bt.err) return;
   const uint8_t* sect = wire + bt.src_off + 61;
   uint64_t sect_len = (uint64_t)bt.total_len - 61;
   if (bt.codec == 3) {
     uint64_t len = 0;
-    const uint32_t e = lzf::frame<true>(in, sect, sect_len, arena + bt.arena_off, bt.dsize, &len);
-    if (e || len != bt.dsize) { batches[i].err = e ? e : DG_LZ4_BLOCK; return; }
+    const uint32_t e = lzf::frame<true>(lzin, sect, sect_len, arena + bt.arena_off, bt.dsize, &len, (g_dbg_flags & 4u) != 0);
+    if (g_dbg_flags & 8u) __threadfence();
+    if (arena_ctl) {   // bt.dsize was the capacity of a claimed slot
+      if (e == DG_LZ4_TOO_LARGE) { arena_ctl[2] = 1ull; batches[i].err = DG_ARENA_FULL; return; }   // (or a block past its maximum: the exact pass tells)
+      if (e) { batches[i].err = e; return; }
+      if ((uint64_t)bt.n_records > len / 7 + 1) { batches[i].err = DG_RECORD_COUNT; return; }
+      batches[i].dsize = (uint32_t)len;
+    } else if (e || len != bt.dsize) { batches[i].err = e ? e : DG_LZ4_BLOCK; return; }
     sect = arena + bt.arena_off; sect_len = len;
   }
   in.seek(sect);
@@ -468,7 +503,23 @@ __device__ __forceinline__ void decode_walk_one(RingIn& in, const uint8_t* __res
       ok = ok && pos + used <= sect_len;
     }
     const int32_t len = (int32_t)(raw >> 1) ^ -(int32_t)(raw & 1u);
-    if (!ok || len < 0 || (uint64_t)len > sect_len - (pos + used)) { batches[i].err = DG_RECORD_LENGTH; batches[i].err_record = r; return; }
+    if (!ok || len < 0 || (uint64_t)len > sect_len - (pos + used)) {
+      uint32_t diag = 0;
+      if (g_dbg_flags & 16u) {   // diagnosis: does the same walk over plain L2 loads succeed? (bit 31: yes -> the ring served stale bytes)
+        DirectIn d; uint64_t q = 0; bool fine = true;
+        for (uint32_t r2 = 0; r2 < bt.n_records && fine; ++r2) {
+          if (q >= sect_len) { fine = false; break; }
+          const unsigned long long v2 = d.get64(sect + q);
+          uint32_t raw2 = 0, used2 = 0; bool t = false;
+          for (int k = 0; k < 5; ++k) { const uint32_t byte = (uint32_t)(v2 >> (8 * k)) & 0xffu; raw2 |= (byte & 0x7fu) << (7 * k); if (!(byte & 0x80u)) { used2 = k + 1; t = true; break; } }
+          const int32_t l2 = (int32_t)(raw2 >> 1) ^ -(int32_t)(raw2 & 1u);
+          if (!t || l2 < 0 || q + used2 > sect_len || (uint64_t)l2 > sect_len - (q + used2)) fine = false; else q += used2 + (uint64_t)l2;
+        }
+        if (fine && q == sect_len) diag = 0x80000000u;
+        diag |= ((uint32_t)pos & 0xfffffu) << 8;
+      }
+      batches[i].err = DG_RECORD_LENGTH; batches[i].err_record = r | diag; return;
+    }
     rec_off[bt.rec_base + r] = (uint32_t)pos; rec_batch[bt.rec_base + r] = index_base + i;
     pos += used + (uint64_t)len;
   }
@@ -476,13 +527,19 @@ __device__ __forceinline__ void decode_walk_one(RingIn& in, const uint8_t* __res
 }
 
 __global__ void __launch_bounds__(kFastThreads) dg_decode_walk_fast_kernel(const uint8_t* __restrict__ wire, uint8_t* arena, DgBatch* __restrict__ batches,
-                                                                           uint32_t n, uint32_t index_base, uint32_t* __restrict__ rec_off, uint32_t* __restrict__ rec_batch) {
+                                                                           uint32_t n, uint32_t index_base, uint32_t* __restrict__ rec_off, uint32_t* __restrict__ rec_batch,
+                                                                           unsigned long long* __restrict__ arena_ctl) {
   __shared__ uint4 ring[kRingChunks][kFastThreads];
   const uint32_t i = blockIdx.x * kFastThreads + threadIdx.x;
   if (i >= n) return;
   RingIn in;
   in.init(&ring[0][0]);
-  decode_walk_one(in, wire, arena, batches, i, index_base, rec_off, rec_batch);
+  const uint32_t dbg = g_dbg_flags;
+  DirectIn din;
+  if ((dbg & 3u) == 0u) decode_walk_one(in, in, wire, arena, batches, i, index_base, rec_off, rec_batch, arena_ctl);
+  else if ((dbg & 3u) == 1u) decode_walk_one(in, din, wire, arena, batches, i, index_base, rec_off, rec_batch, arena_ctl);
+  else if ((dbg & 3u) == 2u) decode_walk_one(din, in, wire, arena, batches, i, index_base, rec_off, rec_batch, arena_ctl);
+  else decode_walk_one(din, din, wire, arena, batches, i, index_base, rec_off, rec_batch, arena_ctl);
   asm volatile("cp.async.wait_all;" ::: "memory");
 }
 
@@ -631,7 +688,27 @@ cudaError_t dg_launch_crc_size(const uint8_t* wire, DgBatch* batches, uint32_t n
   return cudaGetLastError();
 }
 
-cudaError_t dg_prepare() { return ensure_crc_tables(); }
+// descriptors host -> device by the SMs (zero-copy read of page-locked memory): the copy engine's queue is full of the poll's
+// fetches, and a cudaMemcpyAsync for 512 KiB of descriptors would wait behind ALL of them
+__global__ void dg_copy16_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, uint64_t n16) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (uint64_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+
+cudaError_t dg_copy_from_mapped_host(const void* host_mapped, void* dst, uint64_t nbytes, cudaStream_t st) {
+  if (!nbytes) return cudaSuccess;
+  const uint64_t n16 = (nbytes + 15) / 16;
+  const uint32_t blocks = (uint32_t)((n16 + 255) / 256 < 592 ? (n16 + 255) / 256 : 592);
+  dg_copy16_kernel<<<blocks, 256, 0, st>>>((const uint4*)host_mapped, (uint4*)dst, n16);
+  return cudaGetLastError();
+}
+
+cudaError_t dg_prepare() {
+  cudaError_t e = ensure_crc_tables();
+  if (e != cudaSuccess) return e;
+  const char* d = getenv("SGR_DINGEST_DEBUG");
+  const uint32_t flags = d ? (uint32_t)atoi(d) : 0u;
+  return cudaMemcpyToSymbol(g_dbg_flags, &flags, sizeof flags);
+}
 
 cudaError_t dg_launch_crc_size_fast(const uint8_t* wire, DgBatch* batches, uint32_t n, unsigned long long* arena_ctl, cudaStream_t st) {
   cudaError_t e = ensure_crc_tables();
@@ -640,9 +717,10 @@ cudaError_t dg_launch_crc_size_fast(const uint8_t* wire, DgBatch* batches, uint3
   return cudaGetLastError();
 }
 
-cudaError_t dg_launch_decode_walk_fast(const uint8_t* wire, uint8_t* arena, DgBatch* batches, uint32_t n, uint32_t index_base, uint32_t* rec_off, uint32_t* rec_batch, cudaStream_t st) {
+cudaError_t dg_launch_decode_walk_fast(const uint8_t* wire, uint8_t* arena, DgBatch* batches, uint32_t n, uint32_t index_base, uint32_t* rec_off, uint32_t* rec_batch,
+                                       unsigned long long* arena_ctl, cudaStream_t st) {
   if (!n) return cudaSuccess;
-  dg_decode_walk_fast_kernel<<<(n + kFastThreads - 1) / kFastThreads, kFastThreads, 0, st>>>(wire, arena, batches, n, index_base, rec_off, rec_batch);
+  dg_decode_walk_fast_kernel<<<(n + kFastThreads - 1) / kFastThreads, kFastThreads, 0, st>>>(wire, arena, batches, n, index_base, rec_off, rec_batch, arena_ctl);
   return cudaGetLastError();
 }
 

@@ -867,7 +867,10 @@ int32_t sgr_append_keys(sgr_engine* e, const void* owner, const uint8_t* keys, c
   if (n_new) {
     e->ing_key_bytes.insert(e->ing_key_bytes.end(), keys + key_offsets[0], keys + key_offsets[n_new]);
     const uint32_t shift = e->ing_key_offs.back() - key_offsets[0];
-    for (uint64_t i = 1; i <= n_new; ++i) e->ing_key_offs.push_back(key_offsets[i] + shift);
+    const size_t old = e->ing_key_offs.size();
+    e->ing_key_offs.resize(old + n_new);
+    uint32_t* dst = e->ing_key_offs.data() + old;
+    for (uint64_t i = 0; i < n_new; ++i) dst[i] = key_offsets[i + 1] + shift;
     e->keys_stale.store(true, std::memory_order_release);
   }
   return SGR_OK;

@@ -79,7 +79,9 @@ class DeviceIngest:
     def last_timing(self) -> Dict[str, float]:
         ms = (C.c_float * 8)()
         self._check(self._lib.sgr_dingest_last_timing(self._h, ms))
-        return dict(zip(("wait_h2d_crc_size", "decode_walk", "parse_intern", "keys_to_host", "grow_fold", "total"), [float(x) for x in ms[:6]]))
+        # default (chained) mode: [0] is the wait for the copies and every group's CRC -> decode -> parse chain, [1] only the repeat
+        # from an exact arena layout (0 normally), [2] unused; SGR_DINGEST_V1: the three passes of the first generation
+        return dict(zip(("wait_copies_and_chains", "decode_walk", "parse_intern", "keys_gather", "grow_fold_append_keys", "total"), [float(x) for x in ms[:6]]))
 
     def reset(self) -> None:
         """Forget dictionary, positions and statistics: the next poll rebuilds from offset 0."""

@@ -231,3 +231,26 @@ def test_first_generation_kernels_still_agree(monkeypatch):
     rng = np.random.default_rng(32)
     fetches = [(p, _stream(rng, 20, 500, "lz4", base=p * 5000)[0]) for p in range(3)]
     _compare_with_host(fetches)
+
+
+def test_forty_byte_records_walk_through_the_ring():
+    """Records of ~38 bytes make the record walk advance its input ring by three 16-byte chunks per record, every record, in every
+    lane — the access pattern that exposed two asynchronous copies aimed at one ring slot (csrc/dingest_kernels.cu, RingIn::advance).
+    Several polls of 600 batches x 512 records against the host decoder."""
+    rng = np.random.default_rng(77)
+    n = 512 * 600
+    for rep in range(3):
+        agg = rng.integers(0, 150_000, size=n).astype(np.uint32)
+        wire = O.kafka_encode_counter(agg, rng.integers(0, 3, size=n).astype(np.uint32), (np.arange(n, dtype=np.uint32) + 3_000_000 * (rep + 1)),
+                                      rng.integers(0, 1 << 31, size=n).astype(np.int32), recs_per_batch=512, lz4=True).tobytes()
+        want, want_offs, _ = _host_fold([(0, wire)])
+        with ReplayEngine(0) as e:
+            e.register_program(P.counter_program())
+            with DeviceIngest(e, 1 << 18) as dg:
+                dg.submit(0, wire)
+                st = dg.fold()
+                assert st["n_records"] == n and st["n_new_keys"] == len(want)
+                keys = list(want)
+                for k in keys[::37] + keys[-5:]:
+                    assert e.get(k) == want[k], k
+                assert dg.offsets(0) == want_offs[0]
