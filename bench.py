@@ -671,11 +671,32 @@ def main() -> None:
     # the e2e result must be the same table the resident fold produced
     same = bool(torch.equal(torch.from_numpy(host_states_np.reshape(-1)).to(dev), eng.states_tensor().reshape(-1)))
     assert same, "e2e state table differs from the HBM-resident fold"
+    # ---- configs[2]: the routed problem north_star names, strong-scaled, parity-hashed. Runs after the wire-format section;
+    #      SGR_BENCH_ROUTED_FIRST=1 runs it before (an A/B kept from checking that the order does not change its time: it does not).
+    routed = None
+    routed_first = os.environ.get("SGR_BENCH_ROUTED_FIRST", "0") == "1"
+
+    def run_routed():
+        nonlocal routed
+        if args.no_routed:
+            return
+        try:
+            note("configs[2] routed")
+            routed = config2_routed(rank, world, local_rank, dev, barrier, note, args.scale, args.routed_iters)
+        except Exception as ex:  # noqa: BLE001 - the headline line must survive a failure of the extra measurement
+            routed = {"error": f"{type(ex).__name__}: {ex}"}
+        torch.cuda.empty_cache()
+
+    if routed_first:
+        run_routed()
+
     # ---- timed region 3 (e2e over the WIRE format): what the topic holds — lz4 RecordBatch bytes — goes to the device as it is;
     #      CRC, lz4, record parse, id interning and the fold run there (surge_b200/csrc/dingest_kernels.cu). Every step: submit
     #      the 32 partitions' bytes from pinned host memory, decode + fold into a fresh table, read the table back.
     wire_res = None
     try:
+        if os.environ.get("SGR_BENCH_SKIP_WIRE"):
+            raise RuntimeError("skipped (SGR_BENCH_SKIP_WIRE)")
         note("encoding the topic (32 partitions, lz4 batches of 512 records)")
         from concurrent.futures import ThreadPoolExecutor
 
@@ -748,15 +769,8 @@ def main() -> None:
     del rec, host_log, host_log_np
     torch.cuda.empty_cache()
 
-    # ---- configs[2]: the routed problem north_star names, strong-scaled, parity-hashed
-    routed = None
-    if not args.no_routed:
-        try:
-            note("configs[2] routed")
-            routed = config2_routed(rank, world, local_rank, dev, barrier, note, args.scale, args.routed_iters)
-        except Exception as ex:  # noqa: BLE001 - the headline line must survive a failure of the extra measurement
-            routed = {"error": f"{type(ex).__name__}: {ex}"}
-            torch.cuda.empty_cache()
+    if not routed_first:
+        run_routed()
     configs = None
     if world == 1 and not args.no_configs:
         configs = {}
