@@ -694,6 +694,7 @@ def main() -> None:
     #      CRC, lz4, record parse, id interning and the fold run there (surge_b200/csrc/dingest_kernels.cu). Every step: submit
     #      the 32 partitions' bytes from pinned host memory, decode + fold into a fresh table, read the table back.
     wire_res = None
+    wire = {}          # what the set-up leaves for the timed part
     try:
         if os.environ.get("SGR_BENCH_SKIP_WIRE"):
             raise RuntimeError("skipped (SGR_BENCH_SKIP_WIRE)")
@@ -709,7 +710,7 @@ def main() -> None:
             sel = cols[p::n_part].reshape(-1, 4)
             return O.kafka_encode_counter(sel[:, 2].astype(np.uint32), sel[:, 0].astype(np.uint32), sel[:, 1].astype(np.uint32), sel[:, 3].astype(np.int32),
                                           recs_per_batch=512, lz4=True)
-        with ThreadPoolExecutor(max_workers=min(n_part, os.cpu_count() or 1)) as ex:
+        with ThreadPoolExecutor(max_workers=max(1, min(n_part, (os.cpu_count() or 1) // world))) as ex:
             wires = list(ex.map(encode, range(n_part)))
         wire_bytes = int(sum(len(w) for w in wires))
         pinned = []
@@ -719,8 +720,10 @@ def main() -> None:
             pinned.append(t)
         del wires, cols
         e3 = ReplayEngine(local_rank)
+        wire["e3"] = e3
         e3.register_program(P.counter_program())
         dg = DeviceIngest(e3, 1 << 21)
+        wire["dg"] = dg
 
         phase = [0.0, 0.0, 0.0]
 
@@ -740,29 +743,48 @@ def main() -> None:
         for _ in range(2):
             stw = wire_step()
         assert stw["n_records"] == n_events and stw["n_new_keys"] == N_AGG, stw
-        barrier()
-        note("timed region 3 (e2e, wire format)")
-        phase[:] = [0.0, 0.0, 0.0]
-        t0 = time.perf_counter()
-        for _ in range(ke):
-            wire_step()
         torch.cuda.synchronize()
-        wire_s = time.perf_counter() - t0
-        barrier()
-        # parity of the wire path: a sample of aggregates by id against the HBM-resident fold's table
-        ref_tab = eng.states_tensor().cpu().numpy()
-        bad = 0
-        for g in range(0, N_AGG, N_AGG // 4096):
-            got = e3.get(f"agg-{g}")
-            bad += int(got != ref_tab[g, :8].tobytes())
-        wire_res = {"seconds": wire_s, "wire_bytes": wire_bytes, "last_step_ms": dg.last_timing(), "host_ms_per_step": {"submit": phase[0] / ke * 1e3, "fold": phase[1] / ke * 1e3, "export": phase[2] / ke * 1e3}, "bytes_per_event": wire_bytes / n_events, "sample_mismatches": bad,
-                    "decompressed_bytes": int(stw["n_decompressed_bytes"]), "batches": int(stw["n_batches"])}
-        assert bad == 0, "wire-format e2e differs from the resident fold"
-        dg.close()
-        e3.close()
-        del pinned
+        wire["ready"] = True
     except Exception as ex:  # noqa: BLE001 - the headline line must survive
         wire_res = {"error": f"{type(ex).__name__}: {ex}"}
+    # Every rank reports whether its set-up worked; the all-reduce is also the barrier in front of the timed region. (No barrier may
+    # sit inside a try block: a rank that failed would never reach it and the others would wait for it forever.)
+    all_ready = bool(wire.get("ready"))
+    if world > 1:
+        flag = torch.tensor([1 if all_ready else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        all_ready = bool(int(flag.item()))
+    if all_ready:
+        try:
+            note("timed region 3 (e2e, wire format)")
+            phase[:] = [0.0, 0.0, 0.0]
+            t0 = time.perf_counter()
+            for _ in range(ke):
+                wire_step()
+            torch.cuda.synchronize()
+            wire_s = time.perf_counter() - t0
+            # parity of the wire path: a sample of aggregates by id against the HBM-resident fold's table
+            ref_tab = eng.states_tensor().cpu().numpy()
+            bad = 0
+            for g in range(0, N_AGG, N_AGG // 4096):
+                got = e3.get(f"agg-{g}")
+                bad += int(got != ref_tab[g, :8].tobytes())
+            wire_res = {"seconds": wire_s, "wire_bytes": wire_bytes, "last_step_ms": dg.last_timing(), "host_ms_per_step": {"submit": phase[0] / ke * 1e3, "fold": phase[1] / ke * 1e3, "export": phase[2] / ke * 1e3}, "bytes_per_event": wire_bytes / n_events, "sample_mismatches": bad,
+                        "decompressed_bytes": int(stw["n_decompressed_bytes"]), "batches": int(stw["n_batches"])}
+            assert bad == 0, "wire-format e2e differs from the resident fold"
+        except Exception as ex:  # noqa: BLE001 - the headline line must survive
+            wire_res = {"error": f"{type(ex).__name__}: {ex}"}
+    elif wire_res is None:
+        wire_res = {"error": "another rank could not set up the wire-format run"}
+    try:
+        if "dg" in wire:
+            wire["dg"].close()
+        if "e3" in wire:
+            wire["e3"].close()
+    except Exception:  # noqa: BLE001
+        pass
+    wire.clear()
+    pinned = None
     clocks = sampler.stop()
     e2.close(); eng.close()
     cpu_rec = np.array(host_log_np, copy=True) if (world == 1 and not args.no_cpu_baseline) else None
