@@ -432,7 +432,7 @@ int32_t sgr_dingest_submit(sgr_dingest* g, int32_t partition, const void* data, 
       if (!g->batches.reserve(g->batches.n + add.size())) return dfail(g, SGR_ERR_OOM, "page-locked descriptor array");
     }
     memcpy(g->batches.p + g->batches.n, add.data(), add.size() * sizeof(DgBatch));
-    const DgBatch* src_desc = g->batches.p + g->batches.n;
+    const DgBatch* src_desc = g->batches.p + g->batches.n;   // (the first generation uploads them from here right away)
     (void)src_desc;
     g->batches.n += add.size();
     if (!g->v1) {
@@ -442,20 +442,20 @@ int32_t sgr_dingest_submit(sgr_dingest* g, int32_t partition, const void* data, 
         if (rc) { discard_poll(g); return rc; }
       }
     } else {
-    // descriptors go up right away; the CRC + lz4 size pass is launched once >= 32 k batches are waiting (one thread per batch:
-    // a small launch takes as long as a large one, it is the serial walk of ONE batch) — it then runs while the host walks
-    // the next fetches and the copy engine brings them in; sgr_dingest_fold launches the remainder
-    if ((g->d_batches_used + add.size()) * sizeof(DgBatch) > g->d_batches.b.cap) DG_TRY(g, cudaStreamSynchronize(g->stream));
-    g->d_batches.used = g->d_batches_used * sizeof(DgBatch);
-    DG_TRY(g, g->d_batches.ensure(add.size() * sizeof(DgBatch) + 64, g->stream));
-    DgBatch* db = (DgBatch*)g->d_batches.b.p + g->d_batches_used;
-    DG_TRY(g, cudaMemcpyAsync(db, src_desc, add.size() * sizeof(DgBatch), cudaMemcpyHostToDevice, g->stream));
-    g->d_batches_used += add.size();
-    if (g->d_batches_used - g->crc_launched >= 32768) {
-      DG_TRY(g, cudaStreamWaitEvent(g->stream, sub.copied, 0));
-      DG_TRY(g, dg_launch_crc_size((const uint8_t*)g->wire.b.p, (DgBatch*)g->d_batches.b.p + g->crc_launched, (uint32_t)(g->d_batches_used - g->crc_launched), g->stream));
-      g->crc_launched = g->d_batches_used;
-    }
+      // descriptors go up right away; the CRC + lz4 size pass is launched once >= 32 k batches are waiting (one thread per batch:
+      // a small launch takes as long as a large one, it is the serial walk of ONE batch) — it then runs while the host walks
+      // the next fetches and the copy engine brings them in; sgr_dingest_fold launches the remainder
+      if ((g->d_batches_used + add.size()) * sizeof(DgBatch) > g->d_batches.b.cap) DG_TRY(g, cudaStreamSynchronize(g->stream));
+      g->d_batches.used = g->d_batches_used * sizeof(DgBatch);
+      DG_TRY(g, g->d_batches.ensure(add.size() * sizeof(DgBatch) + 64, g->stream));
+      DgBatch* db = (DgBatch*)g->d_batches.b.p + g->d_batches_used;
+      DG_TRY(g, cudaMemcpyAsync(db, src_desc, add.size() * sizeof(DgBatch), cudaMemcpyHostToDevice, g->stream));
+      g->d_batches_used += add.size();
+      if (g->d_batches_used - g->crc_launched >= 32768) {
+        DG_TRY(g, cudaStreamWaitEvent(g->stream, sub.copied, 0));
+        DG_TRY(g, dg_launch_crc_size((const uint8_t*)g->wire.b.p, (DgBatch*)g->d_batches.b.p + g->crc_launched, (uint32_t)(g->d_batches_used - g->crc_launched), g->stream));
+        g->crc_launched = g->d_batches_used;
+      }
     }
   }
   g->n_record_slots += slots;
@@ -531,38 +531,38 @@ int32_t sgr_dingest_fold(sgr_dingest* g, sgr_ingest_stats* stats) {
       }
       for (uint32_t i = 0; i < nb; ++i) if (g->batches[i].codec == 3 && !g->batches[i].err) st.n_decompressed_bytes += g->batches[i].dsize;
     } else {
-    DG_TRY(g, g->rec_off.b.reserve((size_t)nrec * 4 + 64));
-    DG_TRY(g, g->rec_batch.b.reserve((size_t)nrec * 4 + 64));
-    DG_TRY(g, g->out.b.reserve((size_t)nrec * 64 + 64));
-    p = parse_args(g);
-    DG_TRY(g, cudaMemsetAsync(g->rec_batch.b.p, 0xff, (size_t)nrec * 4 + 4, g->stream));
-    p.n_batches = nb;
-    // ---- the CRC + lz4 size pass: most of it was launched by sgr_dingest_submit behind the copies; the rest now
-    if (g->crc_launched < nb) {
-      DG_TRY(g, cudaStreamWaitEvent(g->stream, g->subs.back().copied, 0));
-      DG_TRY(g, dg_launch_crc_size((const uint8_t*)g->wire.b.p, (DgBatch*)g->d_batches.b.p + g->crc_launched, (uint32_t)(nb - g->crc_launched), g->stream));
-      g->crc_launched = nb;
-    }
-    DG_TRY(g, cudaMemcpyAsync(g->batches.data(), g->d_batches.b.p, (size_t)nb * sizeof(DgBatch), cudaMemcpyDeviceToHost, g->stream));
-    DG_TRY(g, cudaStreamSynchronize(g->stream));
-    lap(0);
-    uint64_t arena_need = 0;
-    for (uint32_t i = 0; i < nb; ++i) {
-      DgBatch& b = g->batches[i];
-      if (b.err) { const int32_t rc = dfail(g, SGR_ERR_INVALID, "offset %lld: %s", (long long)b.base_offset, dg_err_text(b.err)); discard_poll(g); return rc; }
-      if (b.codec == 3) { b.arena_off = arena_need; arena_need += ((uint64_t)b.dsize + 15) & ~15ull; st.n_decompressed_bytes += b.dsize; }
-    }
-    g->arena.used = 0;
-    DG_TRY(g, g->arena.ensure(arena_need + 64, g->stream));
-    DG_TRY(g, cudaMemcpyAsync(g->d_batches.b.p, g->batches.data(), (size_t)nb * sizeof(DgBatch), cudaMemcpyHostToDevice, g->stream));
-    DG_TRY(g, dg_launch_decode_walk((const uint8_t*)g->wire.b.p, (uint8_t*)g->arena.b.p, (DgBatch*)g->d_batches.b.p, nb, 0, (uint32_t*)g->rec_off.b.p, (uint32_t*)g->rec_batch.b.p, g->stream));
-    if (g->timing_syncs) { DG_TRY(g, cudaStreamSynchronize(g->stream)); lap(1); }
-    p.wire = (const uint8_t*)g->wire.b.p; p.arena = (const uint8_t*)g->arena.b.p; p.rec_begin = 0; p.n_records = nrec;
-    DG_TRY(g, dg_launch_parse(p, g->stream));
-    DG_TRY(g, cudaMemcpyAsync(g->batches.data(), g->d_batches.b.p, (size_t)nb * sizeof(DgBatch), cudaMemcpyDeviceToHost, g->stream));
-    DG_TRY(g, cudaMemcpyAsync(h, g->ctl.p, 128, cudaMemcpyDeviceToHost, g->stream));
-    DG_TRY(g, cudaStreamSynchronize(g->stream));
-    lap(2);
+      DG_TRY(g, g->rec_off.b.reserve((size_t)nrec * 4 + 64));
+      DG_TRY(g, g->rec_batch.b.reserve((size_t)nrec * 4 + 64));
+      DG_TRY(g, g->out.b.reserve((size_t)nrec * 64 + 64));
+      p = parse_args(g);
+      DG_TRY(g, cudaMemsetAsync(g->rec_batch.b.p, 0xff, (size_t)nrec * 4 + 4, g->stream));
+      p.n_batches = nb;
+      // ---- the CRC + lz4 size pass: most of it was launched by sgr_dingest_submit behind the copies; the rest now
+      if (g->crc_launched < nb) {
+        DG_TRY(g, cudaStreamWaitEvent(g->stream, g->subs.back().copied, 0));
+        DG_TRY(g, dg_launch_crc_size((const uint8_t*)g->wire.b.p, (DgBatch*)g->d_batches.b.p + g->crc_launched, (uint32_t)(nb - g->crc_launched), g->stream));
+        g->crc_launched = nb;
+      }
+      DG_TRY(g, cudaMemcpyAsync(g->batches.data(), g->d_batches.b.p, (size_t)nb * sizeof(DgBatch), cudaMemcpyDeviceToHost, g->stream));
+      DG_TRY(g, cudaStreamSynchronize(g->stream));
+      lap(0);
+      uint64_t arena_need = 0;
+      for (uint32_t i = 0; i < nb; ++i) {
+        DgBatch& b = g->batches[i];
+        if (b.err) { const int32_t rc = dfail(g, SGR_ERR_INVALID, "offset %lld: %s", (long long)b.base_offset, dg_err_text(b.err)); discard_poll(g); return rc; }
+        if (b.codec == 3) { b.arena_off = arena_need; arena_need += ((uint64_t)b.dsize + 15) & ~15ull; st.n_decompressed_bytes += b.dsize; }
+      }
+      g->arena.used = 0;
+      DG_TRY(g, g->arena.ensure(arena_need + 64, g->stream));
+      DG_TRY(g, cudaMemcpyAsync(g->d_batches.b.p, g->batches.data(), (size_t)nb * sizeof(DgBatch), cudaMemcpyHostToDevice, g->stream));
+      DG_TRY(g, dg_launch_decode_walk((const uint8_t*)g->wire.b.p, (uint8_t*)g->arena.b.p, (DgBatch*)g->d_batches.b.p, nb, 0, (uint32_t*)g->rec_off.b.p, (uint32_t*)g->rec_batch.b.p, g->stream));
+      if (g->timing_syncs) { DG_TRY(g, cudaStreamSynchronize(g->stream)); lap(1); }
+      p.wire = (const uint8_t*)g->wire.b.p; p.arena = (const uint8_t*)g->arena.b.p; p.rec_begin = 0; p.n_records = nrec;
+      DG_TRY(g, dg_launch_parse(p, g->stream));
+      DG_TRY(g, cudaMemcpyAsync(g->batches.data(), g->d_batches.b.p, (size_t)nb * sizeof(DgBatch), cudaMemcpyDeviceToHost, g->stream));
+      DG_TRY(g, cudaMemcpyAsync(h, g->ctl.p, 128, cudaMemcpyDeviceToHost, g->stream));
+      DG_TRY(g, cudaStreamSynchronize(g->stream));
+      lap(2);
     }
     for (uint32_t i = 0; i < nb; ++i)
       if (g->batches[i].err) {
