@@ -139,5 +139,62 @@ JNIEXPORT jlongArray JNICALL Java_surge_gpu_Native_00024_ingestOffsets(JNIEnv* e
   (*env)->SetLongArrayRegion(env, r, 0, 2, (const jlong*)v);
   return r;
 }
+
+/* ---- device ingest: the same bytes, decoded on the GPU (include/sgr.h "device ingest") */
+#define DG(g) ((sgr_dingest*)(intptr_t)(g))
+JNIEXPORT jlong JNICALL Java_surge_gpu_Native_00024_dingestCreate(JNIEnv* env, jobject o, jlong h, jlong max_keys, jlong max_id_bytes) {
+  sgr_dingest* g = 0;
+  if (max_keys <= 0 || max_id_bytes < 0) { bad_arg(env, "maxKeys must be positive, maxIdBytes non-negative"); return 0; }
+  int32_t rc = sgr_dingest_create(H(h), (uint64_t)max_keys, (uint64_t)max_id_bytes, &g);
+  if (rc != SGR_OK) { (*env)->ThrowNew(env, (*env)->FindClass(env, "java/lang/RuntimeException"), "sgr_dingest_create failed (no device memory, or no engine)"); return 0; }
+  return (jlong)(intptr_t)g;
+}
+JNIEXPORT jint JNICALL Java_surge_gpu_Native_00024_dingestDestroy(JNIEnv* env, jobject o, jlong g) { return sgr_dingest_destroy(DG(g)); }
+JNIEXPORT jint JNICALL Java_surge_gpu_Native_00024_dingestSetNullValueType(JNIEnv* env, jobject o, jlong g, jint event_type) { return sgr_dingest_set_null_value_type(DG(g), event_type); }
+JNIEXPORT jint JNICALL Java_surge_gpu_Native_00024_dingestSetAborted(JNIEnv* env, jobject o, jlong g, jint partition, jlongArray pids, jlongArray firsts) {
+  jsize n = (*env)->GetArrayLength(env, pids);
+  if ((*env)->GetArrayLength(env, firsts) != n) return bad_arg(env, "producerIds and firstOffsets differ in length");
+  jlong* p = (*env)->GetLongArrayElements(env, pids, 0);
+  jlong* f = (*env)->GetLongArrayElements(env, firsts, 0);
+  int32_t rc = sgr_dingest_set_aborted(DG(g), partition, (const int64_t*)p, (const int64_t*)f, (uint64_t)n);
+  (*env)->ReleaseLongArrayElements(env, pids, p, JNI_ABORT);
+  (*env)->ReleaseLongArrayElements(env, firsts, f, JNI_ABORT);
+  return rc;
+}
+/* `data` must be a DIRECT buffer that stays untouched until dingestFold returns: the copy to the device is asynchronous.
+ * Returns the number of data batches queued; throws on a malformed fetch (nothing of it is queued). */
+JNIEXPORT jlong JNICALL Java_surge_gpu_Native_00024_dingestSubmit(JNIEnv* env, jobject o, jlong g, jint partition, jobject data, jlong nbytes) {
+  sgr_ingest_stats st;
+  int ok = 1; void* d = direct(env, data, nbytes, "data: direct buffer shorter than nbytes", &ok);
+  if (!ok) return -1;
+  int32_t rc = sgr_dingest_submit(DG(g), partition, d, (uint64_t)nbytes, &st);
+  if (rc != SGR_OK) {
+    (*env)->ThrowNew(env, (*env)->FindClass(env, "java/lang/RuntimeException"), sgr_dingest_last_error(DG(g)));
+    return -1;
+  }
+  return (jlong)st.n_batches;
+}
+/* decode + intern + fold of everything submitted; Array(records folded, new aggregate ids). A corrupt batch fails the whole poll
+ * (nothing applied, positions unchanged) and kills the consuming thread, as a CorruptRecordException would. */
+JNIEXPORT jlongArray JNICALL Java_surge_gpu_Native_00024_dingestFold(JNIEnv* env, jobject o, jlong g) {
+  sgr_ingest_stats st;
+  int32_t rc = sgr_dingest_fold(DG(g), &st);
+  if (rc != SGR_OK) {
+    (*env)->ThrowNew(env, (*env)->FindClass(env, "java/lang/RuntimeException"), sgr_dingest_last_error(DG(g)));
+    return 0;
+  }
+  int64_t v[2] = {(int64_t)st.n_records, (int64_t)st.n_new_keys};
+  jlongArray r = (*env)->NewLongArray(env, 2);
+  (*env)->SetLongArrayRegion(env, r, 0, 2, (const jlong*)v);
+  return r;
+}
+JNIEXPORT jlongArray JNICALL Java_surge_gpu_Native_00024_dingestOffsets(JNIEnv* env, jobject o, jlong g, jint partition) {
+  int64_t v[2] = {0, 0};
+  sgr_dingest_offsets(DG(g), partition, &v[0], &v[1]);
+  jlongArray r = (*env)->NewLongArray(env, 2);
+  (*env)->SetLongArrayRegion(env, r, 0, 2, (const jlong*)v);
+  return r;
+}
+JNIEXPORT jint JNICALL Java_surge_gpu_Native_00024_dingestReset(JNIEnv* env, jobject o, jlong g) { return sgr_dingest_reset(DG(g)); }
 #endif
 #endif

@@ -39,4 +39,17 @@ object Native {
   @native def growStates(handle: Long, nAgg: Long): Int                            // sgr_grow_states
   /** Array(decodedNext, foldedNext) */
   @native def ingestOffsets(ingest: Long, partition: Int): Array[Long]             // sgr_ingest_offsets
+
+  // the same bytes decoded ON THE DEVICE: only the wire bytes cross PCIe (include/sgr.h "device ingest"); packed values only
+  @native def dingestCreate(handle: Long, maxKeys: Long, maxIdBytes: Long): Long   // sgr_dingest_create (maxIdBytes 0 = 32 per id)
+  @native def dingestDestroy(dingest: Long): Int                                   // sgr_dingest_destroy
+  @native def dingestSetNullValueType(dingest: Long, eventType: Int): Int          // sgr_dingest_set_null_value_type
+  @native def dingestSetAborted(dingest: Long, partition: Int, producerIds: Array[Long], firstOffsets: Array[Long]): Int // sgr_dingest_set_aborted
+  /** queues one fetch response's bytes (a DIRECT buffer, untouched until dingestFold returns); returns the data batches queued */
+  @native def dingestSubmit(dingest: Long, partition: Int, data: ByteBuffer, nbytes: Long): Long // sgr_dingest_submit
+  /** CRC, lz4, parse, intern and fold of everything submitted, all or nothing; Array(recordsFolded, newAggregateIds) */
+  @native def dingestFold(dingest: Long): Array[Long]                              // sgr_dingest_fold
+  /** Array(decodedNext, foldedNext) */
+  @native def dingestOffsets(dingest: Long, partition: Int): Array[Long]           // sgr_dingest_offsets
+  @native def dingestReset(dingest: Long): Int                                     // sgr_dingest_reset
 }
