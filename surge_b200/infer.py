@@ -144,14 +144,17 @@ def _infer_rule(handler: Handler, etype: int, user: int, rng: np.random.Generato
             continue
         found: Optional[Op] = None
         # a 64-bit add first: its low half alone looks like a 32-bit add
-        if exists_rule != N.CREATE and w + 8 <= user and w % 8 == 0:
+        if w + 8 <= user and w % 8 == 0:
             old64 = [_w64(s, w) for s in base_olds]
             new64 = [_w64(o, w) for o in outs]
             for src in _SRC_OFFSETS:
-                if src + 8 > 64:
+                if src + 8 > 64 or src < 16:
                     continue
                 rq = [_w64(r, src) for r in recs]
-                if [(n - o) & 0xFFFFFFFFFFFFFFFF for n, o in zip(new64, old64)] == rq:
+                if exists_rule == N.CREATE:
+                    if [(-n) & 0xFFFFFFFFFFFFFFFF for n in new64] == rq:
+                        found = (N.OP_SUB_I64, w, src, 8)          # 0 - x on the fresh default (0 + x is a plain copy, found below)
+                elif [(n - o) & 0xFFFFFFFFFFFFFFFF for n, o in zip(new64, old64)] == rq:
                     found = (N.OP_ADD_I64, w, src, 8)
                 elif [(o - n) & 0xFFFFFFFFFFFFFFFF for n, o in zip(new64, old64)] == rq:
                     found = (N.OP_SUB_I64, w, src, 8)

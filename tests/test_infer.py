@@ -152,3 +152,78 @@ def test_sixty_four_bit_adds_and_byte_copies():
         return struct.pack("<QQ", total, spent) + rec[40:48]
     got = INF.infer_program(box, 24, 1)
     assert got.rules == [(N.MATERIALISE, [(N.OP_ADD_I64, 0, 24, 8), (N.OP_SUB_I64, 8, 32, 8), (N.OP_SET, 16, 40, 8)])]
+
+
+# ---------------------------------------------------------------- random programs: derive them back from their own interpreter
+def _random_rules(rng, user, n_types):
+    rules = []
+    for _ in range(n_types):
+        exists_rule = int(rng.choice([N.IF_EXISTS, N.MATERIALISE, N.MATERIALISE, N.CREATE, N.CREATE, N.TOMBSTONE, N.THROW]))
+        ops = []
+        if exists_rule in (N.IF_EXISTS, N.MATERIALISE, N.CREATE):
+            w = 0
+            while w < user and len(ops) < N.MAX_OPS:
+                kind = rng.random()
+                if kind < 0.35:
+                    w += 4                                          # this word is kept
+                    continue
+                src32 = int(rng.choice([4] + list(range(16, 64, 4))))
+                if kind < 0.6:
+                    ln = int(rng.choice([4, 4, 8, 16]))
+                    ln = 4 if src32 == 4 else min(ln, user - w, 64 - src32)    # (+8..16 is the engine's aggregate index: no handler sees it)
+                    ops.append((N.OP_SET, w, src32, ln))
+                    w += ln
+                elif kind < 0.85 or w % 8 or w + 8 > user:
+                    ops.append((int(rng.choice([N.OP_ADD_I32, N.OP_SUB_I32])), w, src32, 4))
+                    w += 4
+                else:
+                    src64 = int(rng.choice(list(range(16, 60, 4))))
+                    ops.append((int(rng.choice([N.OP_ADD_I64, N.OP_SUB_I64])), w, src64, 8))
+                    w += 8
+        rules.append((exists_rule, ops))
+    return rules
+
+
+def _box_of(rules, user):
+    def h(state, rec):
+        out = I._handle(rules, user, None if state is None else bytearray(state), rec)     # raises on THROW / MatchError
+        return None if out is None else bytes(out)
+    return h
+
+
+def test_random_programs_are_derived_back_from_their_interpreter():
+    rng = np.random.default_rng(2026)
+    derived = refused = 0
+    for trial in range(120):
+        user = int(rng.choice([8, 8, 16, 24, 56]))
+        n_types = int(rng.integers(1, 6))
+        rules = _random_rules(rng, user, n_types)
+        box = _box_of(rules, user)
+        creates = any(r in (N.MATERIALISE, N.CREATE) for r, _ in rules)
+        try:
+            got = INF.infer_program(box, user, n_types, seed=trial, probes=10, check_sequences=40, check_length=12)
+        except INF.InferenceError as ex:
+            assert not creates, (trial, rules, str(ex))       # the only legitimate refusal here: nothing ever creates a state
+            refused += 1
+            continue
+        derived += 1
+        # same function on every history from None: compare the two tables under the oracle's interpreter
+        for q in range(30):
+            a = b = None
+            for step in range(14):
+                rec = bytearray(rng.integers(0, 256, size=64, dtype=np.uint8).tobytes())
+                struct.pack_into("<I", rec, 0, int(rng.integers(0, n_types + 1)))             # incl. a MatchError type now and then
+                rec = bytes(rec)
+                try:
+                    na = I._handle(rules, user, a, rec)
+                except I._Throw:
+                    na = "throw"
+                try:
+                    nb = I._handle(got.rules, user, b, rec)
+                except I._Throw:
+                    nb = "throw"
+                assert (na == "throw") == (nb == "throw"), (trial, rules, got.rules)
+                if na != "throw":
+                    assert (na is None) == (nb is None) and (na is None or bytes(na) == bytes(nb)), (trial, step, rules, got.rules)
+                    a, b = na, nb
+    assert derived >= 80 and refused <= 40, (derived, refused)
