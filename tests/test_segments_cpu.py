@@ -100,3 +100,36 @@ def test_from_offset_skips_whole_segments_only(tmp_path):
     ing2 = Ingest()
     st2 = SEG.feed_partition(ing2, 0, d, from_offset=6)      # offset 6 lives in segment 0: both are read
     assert st2["n_bytes"] == len(seg0) + len(seg1)
+
+
+def test_chunks_tile_the_log_on_batch_boundaries_whatever_the_sizes():
+    """batch_chunks over random batch lengths and chunk sizes: the ranges tile [0, end of the last whole batch), every cut is a
+    batch boundary, every range but the last reaches chunk_bytes, and what lies behind a zero length or a torn batch is left out."""
+    rng = np.random.default_rng(12)
+    for trial in range(300):
+        lengths = [int(rng.integers(49, 400)) for _ in range(int(rng.integers(0, 12)))]      # batchLength fields (>= header remainder)
+        data = bytearray()
+        bounds = [0]
+        for ln in lengths:
+            data += struct.pack(">qi", len(bounds), ln) + bytes(ln)
+            bounds.append(len(data))
+        tail = int(rng.integers(0, 4))
+        if tail == 1:
+            data += bytes(int(rng.integers(1, 64)))                                          # preallocated zeros
+        elif tail == 2:
+            data += struct.pack(">qi", 99, 500) + bytes(int(rng.integers(0, 499)))           # a batch that runs past the end
+        elif tail == 3:
+            data += bytes(int(rng.integers(1, 12)))                                          # not even a length field
+        chunk = int(rng.choice([1, 60, 300, 1000, 1 << 20]))
+        got = list(SEG.batch_chunks(bytes(data), chunk))
+        if not lengths:
+            assert got == []
+            continue
+        assert got[0][0] == 0 and got[-1][1] == bounds[-1]
+        for (b0, e0), (b1, _e1) in zip(got, got[1:]):
+            assert e0 == b1
+        for b, e in got:
+            assert b in bounds and e in bounds and e > b
+        for b, e in got[:-1]:
+            assert e - b >= chunk
+            assert e - b - (e - max(x for x in bounds if x < e)) < chunk                      # ... and not a batch more than needed
